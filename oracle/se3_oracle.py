@@ -1,0 +1,267 @@
+"""CPU oracle for the se(3)-TrackNet per-frame inference hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product package imports this file.
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
+``--impl reference`` legs may import it, and only as the checker / the timed
+CPU baseline -- never as a fallback for the CUDA path.
+
+What it restates (file:line are relative to the upstream reference tree,
+wenbowen123/iros20-6d-pose-tracking @ 18dc5bac):
+
+  compute_bbox                 Utils.py:302-316
+  crop_bbox                    Utils.py:320-359
+  normalize_rotation_matrix    Utils.py:363-367
+  normalize_depth              data_augmentation.py:134-144   (OffsetDepth)
+  normalize_channels           data_augmentation.py:154-164   (NormalizeChannels)
+  to_tensor                    data_augmentation.py:179-189   (ToTensor)
+  process_data                 datasets.py:115-156            (TrackDataset.processData)
+  process_predict              datasets.py:159-175            (TrackDataset.processPredict)
+  forward                      se3_tracknet.py:81-112 + network_modules.py:59-66,86-120
+  on_track                     predict.py:217-296 (render_window output taken as an input)
+
+Third-party arithmetic the reference delegates to, and which the oracle calls
+directly because the same libraries are importable here:
+  * conv / batch-norm / pooling / linear -> PyTorch CPU fp32 (reference pins
+    torch==1.10.2+cu113, docker/dockerfile:34; here torch 2.11 CPU)
+  * so(3) exp / log -> cv2.Rodrigues (datasets.py:148,173)
+  * nearest resize -> cv2.resize(INTER_NEAREST) (Utils.py:343-344)
+
+Parity pinning: the reference ships no tests and no golden vectors (SURVEY.md
+section 8c).  The oracle is therefore pinned against OUTPUTS OF THE REFERENCE
+ITSELF RUN IN THE BUILD CONTAINER: ``oracle/make_golden.py`` imports the
+reference's own ``se3_tracknet.py`` (unchanged) and its ``Utils.py`` /
+``data_augmentation.py`` / ``datasets.py`` (with the missing third-party
+imports stubbed and ``np.float`` aliased, nothing else touched), runs them on
+seeded inputs and writes ``tests/golden/*.npz``.  ``tests/test_oracle_golden.py``
+checks this file against those fixtures bit-for-bit.
+
+numpy note: ``depth -= pose[2,3]*1000`` (data_augmentation.py:139-141) is an
+in-place op between a float32 array and a float64 scalar.  Under numpy >= 2
+(NEP 50, what runs here) the subtraction happens in float64 and is rounded once
+to float32; numpy 1.x converted the scalar to float32 first.  The two differ by
+at most ~1 ulp of float32(z*1000), i.e. < 1.3e-4 mm for z < 2 m.  The oracle follows the numpy >= 2 behaviour because
+that is what the reference does when run in this image; `legacy_numpy1=True`
+selects the other.
+"""
+import numpy as np
+import cv2
+import torch
+import torch.nn.functional as F
+
+IMAGE_SIZE = 176
+
+# ----------------------------------------------------------------------------
+# geometry / cropping  (Utils.py)
+# ----------------------------------------------------------------------------
+
+def compute_bbox(pose, K, scale_size=230, scale=(1, 1, 1)):
+    """Utils.py:302-316.  The four corners (x-+half, y-+half) of a metric square
+    of side `scale_size` centred on the (scaled) object position, at the object's
+    depth, pushed through the pinhole model in float64 and rounded with np.round
+    (half-to-even) to int32.  Row order: (-,-), (-,+), (+,-), (+,+); columns (v,u)."""
+    centre = np.array([pose[0, 3] * scale[0], pose[1, 3] * scale[1], pose[2, 3] * scale[2]],
+                      dtype=np.float64)
+    half = scale_size / 2
+    signs = np.array([[-1, -1], [-1, 1], [1, -1], [1, 1]], dtype=np.float64)
+    xs = centre[0] + signs[:, 0] * half
+    ys = centre[1] + signs[:, 1] * half
+    zs = np.full(4, centre[2])
+    vu = np.empty((4, 2), dtype=np.float64)
+    vu[:, 0] = ys * K[1, 1] / zs + K[1, 2]
+    vu[:, 1] = xs * K[0, 0] / zs + K[0, 2]
+    return np.round(vu).astype(np.int32)
+
+
+def crop_window(boundingbox):
+    """(top, left, crop_h, crop_w) of the window crop_bbox cuts: Utils.py:321-328."""
+    top, left = int(boundingbox[:, 0].min()), int(boundingbox[:, 1].min())
+    bottom, right = int(boundingbox[:, 0].max()), int(boundingbox[:, 1].max())
+    return top, left, bottom - top, right - left
+
+
+def crop_bbox(color, depth, boundingbox, output_size=(100, 100)):
+    """Utils.py:320-359 (seg=None).  The window [top,bottom) x [left,right) of the
+    frame is copied into a zero canvas (pixels outside the frame stay 0), then both
+    canvases are resized with cv2 INTER_NEAREST; the depth canvas is float64
+    (Utils.py:330) and is cast to uint16 after the resize (Utils.py:353).  The
+    trailing `* mask` multiplies (Utils.py:351-355) are identities."""
+    top, left, crop_h, crop_w = crop_window(boundingbox)
+    H, W = color.shape[:2]
+    rgb_canvas = np.zeros((crop_h, crop_w, 3), dtype=color.dtype)
+    z_canvas = np.zeros((crop_h, crop_w), dtype=np.float64)
+    # intersection of the window with the frame, in frame and in canvas coordinates
+    y0, y1 = max(top, 0), min(top + crop_h, H)
+    x0, x1 = max(left, 0), min(left + crop_w, W)
+    cy0, cx0 = abs(min(top, 0)), abs(min(left, 0))
+    cy1 = min(crop_h - (top + crop_h - H), crop_h)
+    cx1 = min(crop_w - (left + crop_w - W), crop_w)
+    rgb_canvas[cy0:cy1, cx0:cx1, :] = color[y0:y1, x0:x1, :]
+    z_canvas[cy0:cy1, cx0:cx1] = depth[y0:y1, x0:x1]
+    rgb_out = cv2.resize(rgb_canvas, output_size, interpolation=cv2.INTER_NEAREST)
+    z_out = cv2.resize(z_canvas, output_size, interpolation=cv2.INTER_NEAREST).astype(np.uint16)
+    return rgb_out * (rgb_out != 0), z_out * (z_out != 0)
+
+
+def normalize_rotation_matrix(R):
+    """Utils.py:363-367 (in place, column-normalise)."""
+    R[:, 0] = R[:, 0] / np.linalg.norm(R[:, 0])
+    R[:, 1] = R[:, 1] / np.linalg.norm(R[:, 1])
+    R[:, 2] = R[:, 2] / np.linalg.norm(R[:, 2])
+    return R
+
+
+# ----------------------------------------------------------------------------
+# post-transforms  (data_augmentation.py)
+# ----------------------------------------------------------------------------
+
+def normalize_depth(depth, pose, legacy_numpy1=False):
+    """data_augmentation.py:134-144."""
+    depth = depth.astype(np.float32)
+    invalid_mask = np.logical_or(depth <= 100, depth >= 2000)
+    z = pose[2, 3] * 1000
+    if legacy_numpy1:
+        z = np.float32(z)
+    if pose[2, 3] < 0:   # gl pose
+        depth += z
+    else:
+        depth -= z
+    depth[invalid_mask] = 2000
+    return depth
+
+
+def normalize_channels(rgb, depth, mean, std):
+    """data_augmentation.py:159-163."""
+    rgb = rgb.transpose(2, 0, 1)
+    rgb = (rgb - mean[:3, np.newaxis, np.newaxis]) / std[:3, np.newaxis, np.newaxis]
+    depth = (depth - mean[3, np.newaxis, np.newaxis]) / std[3, np.newaxis, np.newaxis]
+    return rgb, depth
+
+
+def to_tensor(rgbA, depthA, rgbB, depthB):
+    """data_augmentation.py:179-189 -> two float32 (4,H,W) arrays."""
+    bufferA = np.zeros((4, rgbA.shape[1], rgbA.shape[2]), dtype=np.float32)
+    bufferA[0:3] = rgbA
+    bufferA[3] = depthA
+    bufferB = np.zeros((4, rgbA.shape[1], rgbA.shape[2]), dtype=np.float32)
+    bufferB[0:3] = rgbB
+    bufferB[3] = depthB
+    return bufferA, bufferB
+
+
+def post_transforms(rgbA, depthA, rgbB, depthB, A_in_cam, mean, std, legacy_numpy1=False):
+    """Compose([OffsetDepth(), NormalizeChannels(mean,std), ToTensor()]) as
+    built at predict.py:189.  Both depths are offset by A's z (F12)."""
+    dA = normalize_depth(depthA, A_in_cam, legacy_numpy1)
+    dB = normalize_depth(depthB, A_in_cam, legacy_numpy1)
+    rA = rgbA.astype(np.float32)
+    rB = rgbB.astype(np.float32)
+    rA, dA = normalize_channels(rA, dA, mean[:4], std[:4])
+    rB, dB = normalize_channels(rB, dB, mean[4:], std[4:])
+    return to_tensor(rA, dA, rB, dB)
+
+
+# ----------------------------------------------------------------------------
+# TrackDataset.processData / processPredict  (datasets.py)
+# ----------------------------------------------------------------------------
+
+def process_data(rgbA, depthA, A_in_cam, rgbB, depthB, B_in_cam, mean, std,
+                 trans_normalizer=0.03, rot_normalizer=5 * np.pi / 180, legacy_numpy1=False):
+    """datasets.py:115-156 with pretransforms=augmentations=None (predict.py:191).
+    Returns ([dataA, dataB], [trans_label, rot_label])."""
+    dataA, dataB = post_transforms(rgbA, depthA, rgbB, depthB, A_in_cam, mean, std, legacy_numpy1)
+    trans_label = B_in_cam[:3, 3] - A_in_cam[:3, 3]
+    trans_label = trans_label / trans_normalizer
+    A2B = B_in_cam[:3, :3].dot(A_in_cam[:3, :3].T)
+    A2B = normalize_rotation_matrix(A2B)
+    rod = cv2.Rodrigues(A2B)[0].reshape(-1)
+    rot_label = rod / rot_normalizer
+    return [dataA, dataB], [trans_label, rot_label]
+
+
+def process_predict(A_in_cam, predB, trans_normalizer=0.03, rot_normalizer=5 * np.pi / 180):
+    """datasets.py:159-175.  dtype chain (F10): net output float32 * python float
+    stays float32; cv2.Rodrigues(float32) returns float32; .dot(float64) -> float64."""
+    B_in_cam = np.eye(4)
+    trans_pred = predB[0] * trans_normalizer
+    B_in_cam[:3, 3] = trans_pred + A_in_cam[:3, 3]
+    rot_pred = predB[1] * rot_normalizer
+    A2B = cv2.Rodrigues(rot_pred)[0].reshape(3, 3)
+    B_in_cam[:3, :3] = A2B.dot(A_in_cam[:3, :3])
+    return B_in_cam
+
+
+# ----------------------------------------------------------------------------
+# Se3TrackNet.forward  (se3_tracknet.py:81-112) as a pure function of state_dict
+# ----------------------------------------------------------------------------
+
+SELU_ALPHA = 1.6732632423543772
+SELU_SCALE = 1.0507009873554805
+BN_EPS = 1e-5
+
+def _bn(x, sd, p):
+    return F.batch_norm(x, sd[p + '.running_mean'], sd[p + '.running_var'],
+                        sd[p + '.weight'], sd[p + '.bias'], False, 0.0, BN_EPS)
+
+def _conv_bn_selu(x, sd, p, stride, pad):
+    """network_modules.py:59-66: Conv -> BN(eval) -> SELU (F1)."""
+    x = F.conv2d(x, sd[p + '.0.weight'], sd[p + '.0.bias'], stride=stride, padding=pad)
+    return F.selu(_bn(x, sd, p + '.1'))
+
+def _basic_block(x, sd, p):
+    """network_modules.py:105-120, stride 1, no downsample (F2)."""
+    out = F.conv2d(x, sd[p + '.conv1.weight'], sd[p + '.conv1.bias'], padding=1)
+    out = F.relu(_bn(out, sd, p + '.bn1'))
+    out = F.conv2d(out, sd[p + '.conv2.weight'], sd[p + '.conv2.bias'], padding=1)
+    out = _bn(out, sd, p + '.bn2')
+    return F.relu(out + x)
+
+@torch.no_grad()
+def forward(sd, A, B, return_intermediates=False):
+    """A, B: float32 (N,4,H,W) torch CPU tensors; sd: reference-format state_dict."""
+    inter = {}
+    a = _conv_bn_selu(A, sd, 'convA1', 2, 3); inter['a1'] = a
+    a = F.max_pool2d(a, 3, 2, 1); inter['a1p'] = a
+    a = _basic_block(a, sd, 'convA2'); inter['a2'] = a
+    b = _conv_bn_selu(B, sd, 'convB1', 2, 3); inter['b1'] = b
+    b = F.max_pool2d(b, 3, 2, 1); inter['b1p'] = b
+    b = _basic_block(b, sd, 'convB2'); inter['b2'] = b
+    b = _basic_block(b, sd, 'convB3'); inter['b3'] = b
+    ab = torch.cat((a, b), 1).contiguous()
+    ab = _conv_bn_selu(ab, sd, 'convAB1', 2, 1); inter['ab1'] = ab
+    ab = _basic_block(ab, sd, 'convAB2'); inter['ab2'] = ab
+    out = {'feature': ab}
+    for head in ('trans', 'rot'):
+        h = _conv_bn_selu(ab, sd, head + '_conv1', 2, 1); inter[head + '1'] = h
+        h = _basic_block(h, sd, head + '_conv2'); inter[head + '2'] = h
+        h = F.adaptive_avg_pool2d(h, 1).reshape(A.shape[0], -1)
+        h = torch.tanh(F.linear(h, sd[head + '_out.0.weight'], sd[head + '_out.0.bias']))
+        out[head] = h.contiguous()
+    if return_intermediates:
+        return out, inter
+    return out
+
+
+# ----------------------------------------------------------------------------
+# Tracker.on_track  (predict.py:217-296), renderer output supplied by the caller
+# ----------------------------------------------------------------------------
+
+def on_track(sd, prev_pose, current_rgb, current_depth, rgbA, depthA, K, object_width,
+             mean, std, trans_normalizer=0.03, rot_normalizer=5 * np.pi / 180,
+             image_size=IMAGE_SIZE, return_all=False):
+    """predict.py:217-296 with samples=1, imshow removed and render_window's
+    result (rgbA u8 HxWx3, depthA u16 mm) passed in."""
+    A_in_cam = prev_pose.copy()
+    bb = compute_bbox(A_in_cam, K, object_width, scale=(1000, 1000, 1000))
+    rgbB, depthB = crop_bbox(current_rgb, current_depth, bb, (image_size, image_size))
+    sample, _ = process_data(rgbA, depthA, A_in_cam, rgbB, depthB, np.eye(4), mean, std,
+                             trans_normalizer, rot_normalizer)
+    dataA = torch.from_numpy(sample[0]).unsqueeze(0).float()
+    dataB = torch.from_numpy(sample[1]).unsqueeze(0).float()
+    pred = forward(sd, dataA, dataB)
+    trans = pred['trans'][0].numpy()
+    rot = pred['rot'][0].numpy()
+    out = process_predict(A_in_cam, (trans, rot), trans_normalizer, rot_normalizer)
+    if return_all:
+        return out, dict(bb=bb, rgbB=rgbB, depthB=depthB, dataA=sample[0], dataB=sample[1],
+                         trans=trans, rot=rot)
+    return out

@@ -1,0 +1,37 @@
+import importlib, os, sys
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
+
+
+def pytest_collection_modifyitems(config, items):
+    import torch
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason='no CUDA device')
+    for item in items:
+        if 'gpu' in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope='session')
+def pkg():
+    return importlib.import_module('iros20-6d-pose-tracking_b200')
+
+
+@pytest.fixture(scope='session')
+def synth():
+    return importlib.import_module('iros20-6d-pose-tracking_b200.synth')
+
+
+@pytest.fixture(scope='session')
+def golden_dir():
+    return GOLDEN

@@ -1,0 +1,125 @@
+"""Pins oracle/se3_oracle.py against fixtures produced by the reference's own code
+(oracle/make_golden.py, run in the build container).  CPU only."""
+import hashlib, os
+import numpy as np
+import cv2
+import torch
+import se3_oracle as O
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_model_forward_matches_reference(synth, golden_dir):
+    g = np.load(os.path.join(golden_dir, 'golden_model.npz'))
+    sd = synth.make_state_dict(0)
+    A, B = synth.tensor_pairs(2, seed=0)
+    out, inter = O.forward(sd, A, B, return_intermediates=True)
+    # same library, same ops, same order -> bit-identical
+    assert np.array_equal(out['trans'].numpy(), g['trans'])
+    assert np.array_equal(out['rot'].numpy(), g['rot'])
+    assert sha(out['feature'].numpy()) == str(g['feature_sha'])
+    names = dict(convA1='a1', poolA1='a1p', convA2='a2', convB1='b1', poolB1='b1p', convB2='b2',
+                 convB3='b3', convAB1='ab1', convAB2='ab2', trans_conv1='trans1',
+                 trans_conv2='trans2', rot_conv1='rot1', rot_conv2='rot2')
+    for ref_name, mine in names.items():
+        assert np.array_equal(inter[mine][:, ::8, ::5, ::5].numpy(), g['act_' + ref_name + '_sub']), ref_name
+
+
+def test_config1_end_to_end(synth, golden_dir):
+    g = np.load(os.path.join(golden_dir, 'golden_model.npz'))
+    rgbA = cv2.imread(os.path.join(golden_dir, 'c1_rgbA.png'))[..., ::-1].copy()
+    rgbB = cv2.imread(os.path.join(golden_dir, 'c1_rgbB.png'))[..., ::-1].copy()
+    depthA, depthB = synth.depth_from_rgb(rgbA), synth.depth_from_rgb(rgbB)
+    mean, std = synth.default_mean_std()
+    pose = synth.config1_pose()
+    (dA, dB), _ = O.process_data(rgbA, depthA, pose, rgbB, depthB, np.eye(4), mean, std)
+    assert sha(dA) == str(g['c1_dataA_sha']) and sha(dB) == str(g['c1_dataB_sha'])
+    sd = synth.make_state_dict(0)
+    out = O.forward(sd, torch.from_numpy(dA)[None], torch.from_numpy(dB)[None])
+    assert np.array_equal(out['trans'].numpy(), g['c1_trans'])
+    assert np.array_equal(out['rot'].numpy(), g['c1_rot'])
+    pose_out = O.process_predict(pose, (out['trans'][0].numpy(), out['rot'][0].numpy()))
+    assert np.array_equal(pose_out, g['c1_pose_out'])
+
+
+def test_bbox_and_crop_small_frame(synth, golden_dir):
+    p = np.load(os.path.join(golden_dir, 'golden_pre.npz'))
+    rgb, depth, K = p['small_rgb'], p['small_depth'], p['K_small']
+    n = len(p['object_width'])
+    for i in range(n):
+        bb = O.compute_bbox(p['poses'][i], K, p['object_width'][i], scale=(1000, 1000, 1000))
+        assert bb.dtype == np.int32 and np.array_equal(bb, p[f'bb_{i}'])
+        rB, dB = O.crop_bbox(rgb, depth, bb, (176, 176))
+        assert rB.dtype == np.uint8 and dB.dtype == np.uint16
+        assert sha(rB) == str(p[f'rgbB_sha_{i}']) and sha(dB) == str(p[f'depthB_sha_{i}']), i
+        if i < 2:
+            assert np.array_equal(rB, p[f'rgbB_{i}']) and np.array_equal(dB, p[f'depthB_{i}'])
+    bb = O.compute_bbox(p['poses'][1], K, 200., scale=(1000, -1000, 1000))
+    assert np.array_equal(bb, p['bb_gl_0'])
+
+
+def test_crop_full_frame(synth, golden_dir):
+    p = np.load(os.path.join(golden_dir, 'golden_pre.npz'))
+    rgb, depth = synth.raw_frame(0)
+    assert sha(rgb) == str(p['full_rgb_sha']) and sha(depth) == str(p['full_depth_sha'])
+    poses = synth.raw_poses(8, seed=0)
+    assert np.array_equal(poses, p['full_poses'])
+    for i in range(8):
+        bb = O.compute_bbox(poses[i], synth.CAMERA_K, 200., scale=(1000, 1000, 1000))
+        assert np.array_equal(bb, p[f'full_bb_{i}'])
+        rB, dB = O.crop_bbox(rgb, depth, bb, (176, 176))
+        assert sha(rB) == str(p[f'full_rgbB_sha_{i}']) and sha(dB) == str(p[f'full_depthB_sha_{i}'])
+
+
+def test_process_data_both_dtype_chains(synth, golden_dir):
+    p = np.load(os.path.join(golden_dir, 'golden_pre.npz'))
+    rgb, depth, K = p['small_rgb'], p['small_depth'], p['K_small']
+    n = len(p['object_width'])
+    poses = p['poses']
+    rgbAs, depthAs = synth.rendered_views(n, poses, seed=7)
+    mean, std = synth.default_mean_std()
+    stats = {'f32': (mean, std), 'f64': (mean.astype(np.float64) + 0.123, std.astype(np.float64) * 1.01)}
+    for i in range(n):
+        bb = O.compute_bbox(poses[i], K, p['object_width'][i], scale=(1000, 1000, 1000))
+        rB, dB = O.crop_bbox(rgb, depth, bb, (176, 176))
+        for tag, (m, s) in stats.items():
+            (dA_, dB_), (tl, rl) = O.process_data(rgbAs[i], depthAs[i], poses[i].copy(), rB, dB,
+                                                  p[f'gtB_{i}'].copy(), m, s)
+            assert dA_.dtype == np.float32
+            assert sha(dA_) == str(p[f'dataA_sha_{tag}_{i}']), (tag, i)
+            assert sha(dB_) == str(p[f'dataB_sha_{tag}_{i}']), (tag, i)
+            assert np.array_equal(dA_[:, ::11, ::11], p[f'dataA_sub_{tag}_{i}'])
+        assert np.array_equal(tl, p[f'label_trans_{i}']) and np.array_equal(rl, p[f'label_rot_{i}'])
+
+
+def test_process_predict_and_normalize(golden_dir):
+    p = np.load(os.path.join(golden_dir, 'golden_pre.npz'))
+    n = len(p['pu_poses'])
+    for i in range(n):
+        o5 = O.process_predict(p['pu_poses'][i], (p['pu_trans'][i], p['pu_rot'][i]))
+        o30 = O.process_predict(p['pu_poses'][i], (p['pu_trans'][i], p['pu_rot'][i]),
+                                rot_normalizer=30 * np.pi / 180)
+        assert o5.dtype == np.float64
+        assert np.array_equal(o5, p['pu_out_5deg'][i]) and np.array_equal(o30, p['pu_out_30deg'][i])
+        assert np.array_equal(O.normalize_rotation_matrix(p['nrm_in'][i].copy()), p['nrm_out'][i])
+    assert np.array_equal(p['pu_out_5deg'][0], p['pu_poses'][0])     # zero residual = identity update
+
+
+def test_known_answers_rodrigues():
+    # SURVEY 8c known-answer checks on the third-party op the path leans on
+    assert np.array_equal(cv2.Rodrigues(np.zeros(3))[0], np.eye(3))
+    w = np.array([0.3, -0.2, 0.5])
+    assert np.allclose(cv2.Rodrigues(cv2.Rodrigues(w)[0])[0].ravel(), w, atol=1e-12)
+    assert cv2.Rodrigues(np.zeros(3, np.float32))[0].dtype == np.float32       # F10
+
+
+def test_numpy1_legacy_depth_differs_by_at_most_one_ulp_of_offset(synth):
+    rng = np.random.default_rng(0)
+    d = rng.integers(0, 3000, size=(64, 64)).astype(np.uint16)
+    pose = np.eye(4); pose[2, 3] = 0.7123456789
+    a = O.normalize_depth(d, pose); b = O.normalize_depth(d, pose, legacy_numpy1=True)
+    # the two differ by the rounding of the offset z*1000 to float32 (+ one result rounding)
+    bound = 2 * np.spacing(np.float32(pose[2, 3] * 1000))
+    assert np.all(np.abs(a.astype(np.float64) - b) <= bound)
