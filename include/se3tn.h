@@ -1,0 +1,145 @@
+/* libse3tn -- C ABI of the B200-native se(3)-TrackNet inference hot path.
+ *
+ * The upstream reference (wenbowen123/iros20-6d-pose-tracking @ 18dc5bac) is pure Python and has
+ * no FFI of its own; its boundary is the Python class surface.  Each entry
+ * point below is what a ctypes binding on the reference side would call INSTEAD of the cited
+ * reference code.  All tensor arguments are plain device pointers owned by the caller (PyTorch in
+ * the shipped host layer); every launch is enqueued on the caller's cudaStream_t (pass it as a
+ * void*); nothing here synchronises the stream unless stated.  No exceptions or aborts cross the
+ * boundary: every function returns SE3TN_OK or a negative code, text via se3tn_last_error().
+ * A context is single-threaded; distinct contexts are independent.
+ */
+#ifndef SE3TN_H
+#define SE3TN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct se3tn_ctx se3tn_ctx;
+
+enum {
+    SE3TN_OK = 0,
+    SE3TN_ERR_INVALID = -1,      /* bad argument (null, size, alignment, unknown id) */
+    SE3TN_ERR_CUDA = -2,         /* a CUDA runtime / driver call failed               */
+    SE3TN_ERR_NOMEM = -3,
+    SE3TN_ERR_STATE = -4,        /* e.g. forward before load_weights                  */
+    SE3TN_ERR_UNSUPPORTED = -5   /* device is not sm_100                              */
+};
+
+/* Arithmetic of the 17 convolutions. */
+enum {
+    SE3TN_PREC_TF32 = 0,   /* tcgen05 kind::tf32, fp32 accumulate; operands rounded to tf32 (rna)   */
+    SE3TN_PREC_FP32 = 1    /* plain FFMA direct convolution, no operand rounding (cross-check mode) */
+};
+
+#define SE3TN_IMAGE_SIZE 176           /* reference dataset_info.yml:15 `resolution`          */
+#define SE3TN_WEIGHT_BLOB_FLOATS 13528326u  /* see se3tn_load_weights                          */
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+
+/* Bytes of device workspace a context for batches of up to `max_batch` pairs needs. */
+size_t se3tn_workspace_bytes(int max_batch);
+
+/* Create a context on CUDA device `device` for up to `max_batch` RGB-D pairs per call.
+ * `workspace` is a caller-owned device buffer of se3tn_workspace_bytes(max_batch) bytes, 1024-byte
+ * aligned, that must outlive the context; pass NULL to let the library cudaMalloc its own.
+ * Replaces: the `.cuda()` model placement in Tracker.__init__ (reference predict.py:156-158). */
+int se3tn_create(int device, int max_batch, void* workspace, se3tn_ctx** out);
+void se3tn_destroy(se3tn_ctx* ctx);
+
+/* Message of the last error on `ctx` (or of the last failed se3tn_create when ctx is NULL). */
+const char* se3tn_last_error(se3tn_ctx* ctx);
+
+/* ---- per-object parameters --------------------------------------------------------------------
+ * One weight set per object class (reference README.md:132: one checkpoint + mean/std per object).
+ * `blob` is HOST memory: SE3TN_WEIGHT_BLOB_FLOATS float32 values produced by the packer
+ * (weights.py: eval-mode BatchNorm folded into each conv, OIHW -> [Cout][tap*Cin + c] K-major),
+ * in launch order:
+ *   W[64][224],b[64]            x2   convA1, convB1        (7x7 s2; K = 7 rows x (8 px x 4 ch))
+ *   W[64][576],b[64]            x6   convA2.{conv1,conv2}, convB2.{..}, convB3.{..}
+ *   W[256][1152],b[256]              convAB1
+ *   W[256][2304],b[256]         x2   convAB2.{conv1,conv2}
+ *   W[1024][2304],b[1024]            trans_conv1 ++ rot_conv1 (Cout concatenated)
+ *   W[1024][4608],b[1024]       x2   {trans,rot}_conv2.conv1, {trans,rot}_conv2.conv2 (2 groups)
+ *   W[6][512],b[6]                   trans_out.0 ++ rot_out.0
+ * Replaces: Se3TrackNet.load_state_dict (reference predict.py:151-155). */
+int se3tn_load_weights(se3tn_ctx* ctx, int weight_id, const float* blob, size_t n_floats);
+
+/* Per-object channel statistics (reference predict.py:657-658 mean.npy/std.npy): 8 values each,
+ * A's 4 channels then B's.  `is_f64` selects the arithmetic of the normalisation so that it
+ * reproduces numpy's for float32 resp. float64 mean/std arrays (data_augmentation.py:159-163). */
+int se3tn_set_stats(se3tn_ctx* ctx, int weight_id, const void* mean8, const void* std8, int is_f64);
+
+/* ---- the hot path ---------------------------------------------------------------------------- */
+
+/* K0.  For each of n tracks: bbox of the previous pose (reference Utils.py:302-316), zero-padded
+ * window + nearest-neighbour resize of the observed frame to 176x176 (Utils.py:320-359), depth
+ * offset/clip (data_augmentation.py:134-144), channel normalisation (:154-164) and packing
+ * (:179-189).  Results land in the context's conv-input buffers; optional outputs (any may be
+ * NULL): out_A/out_B float32 (n,4,176,176) exactly as TrackDataset.processData returns them
+ * (datasets.py:136-137), crop_rgb uint8 (n,176,176,3) / crop_depth uint16 (n,176,176) exactly
+ * as crop_bbox returns them.
+ *   frame_rgb  uint8  (H,W,3) device      frame_depth uint16 (H,W) device, millimetres
+ *   K          4 doubles HOST: fx, fy, cx, cy
+ *   poses      double (n,16) device, row-major 4x4 object-in-camera, metres
+ *   object_width double (n) device, millimetres (Tracker.object_width, predict.py:136-142)
+ *   rgbA uint8 (n,176,176,3), depthA uint16 (n,176,176) device: render_window's output contract
+ *   weight_ids int32 (n) device or NULL (all 0): which mean/std row each track uses */
+int se3tn_preprocess(se3tn_ctx* ctx, const uint8_t* frame_rgb, const uint16_t* frame_depth, int H, int W,
+                     const double* K, const double* poses, const double* object_width,
+                     const uint8_t* rgbA, const uint16_t* depthA, const int32_t* weight_ids, int n,
+                     int precision, float* out_A, float* out_B, uint8_t* crop_rgb, uint16_t* crop_depth,
+                     void* stream);
+
+/* Se3TrackNet.forward (reference se3_tracknet.py:81-112).  A, B: float32 (n,4,176,176) contiguous
+ * NCHW device tensors.  out_trans/out_rot: float32 (n,3).  out_feature: float32 (n,256,22,22) or
+ * NULL.  All n pairs use weight set `weight_id`. */
+int se3tn_forward(se3tn_ctx* ctx, int weight_id, const float* A, const float* B, int n,
+                  float* out_trans, float* out_rot, float* out_feature, int precision, void* stream);
+
+/* The conv stack on whatever se3tn_preprocess left in the conv-input buffers (tracks
+ * [first, first+n) of the last preprocess call). */
+int se3tn_forward_preprocessed(se3tn_ctx* ctx, int weight_id, int first, int n,
+                               float* out_trans, float* out_rot, float* out_feature, int precision, void* stream);
+
+/* K6.  TrackDataset.processPredict (reference datasets.py:159-175): t' = t + trans*tn,
+ * R' = Rodrigues(rot*rn) . R with the reference's float32/float64 dtype chain.
+ * poses_in/poses_out double (n,16) device (may alias); trans/rot float32 (n,3) device. */
+int se3tn_pose_update(se3tn_ctx* ctx, const double* poses_in, const float* trans, const float* rot,
+                      double trans_normalizer, double rot_normalizer, double* poses_out, int n, void* stream);
+
+/* K5.  The label half of TrackDataset.processData (reference datasets.py:141-150, Utils.py:363-367):
+ * trans_label = (tB - tA)/tn, rot_label = Rodrigues^-1(normalize_cols(R_B R_A^T))/rn; double (n,3). */
+int se3tn_so3_log(se3tn_ctx* ctx, const double* poses_a, const double* poses_b,
+                  double trans_normalizer, double rot_normalizer,
+                  double* trans_label, double* rot_label, int n, void* stream);
+
+/* Tracker.on_track for n independent tracks of one frame (reference predict.py:217-296 with the
+ * renderer's output passed in and the GUI calls dropped): K0 -> conv stack -> K6 on one stream.
+ * weight_ids_host: int32 (n) HOST array or NULL (all 0); tracks with equal ids must be contiguous
+ * (each run is one batched forward).  weight_ids_dev: the same values on the device (or NULL).
+ * out_trans/out_rot float32 (n,3) device scratch the caller provides (also returned). */
+int se3tn_track_batch(se3tn_ctx* ctx, const uint8_t* frame_rgb, const uint16_t* frame_depth, int H, int W,
+                      const double* K, const double* poses_in, const double* object_width,
+                      const uint8_t* rgbA, const uint16_t* depthA,
+                      const int32_t* weight_ids_host, const int32_t* weight_ids_dev, int n,
+                      double trans_normalizer, double rot_normalizer, int precision,
+                      float* out_trans, float* out_rot, double* poses_out, void* stream);
+
+/* ---- introspection (tests / profiling) -------------------------------------------------------- */
+
+/* Device pointer + per-image float count of an internal NHWC activation buffer.
+ * ids: 0 stemA 1 stemB 2 Y1A 3 Y1B 4 P1A 5 P1B 6 T1 7 T2 8 U 9 CAT 10 F1 11 T4 12 F2 13 H1 14 H2 15 H3 */
+int se3tn_debug_buffer(se3tn_ctx* ctx, int id, float** ptr, size_t* floats_per_image);
+
+/* Number of kernels the last forward / track_batch call on this context launched. */
+int se3tn_last_launch_count(se3tn_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SE3TN_H */

@@ -1,0 +1,400 @@
+// HBM-bound fp32/fp64 kernels either side of the conv stack: frame crop + depth clip + channel
+// normalisation (K0), layout packing, 3x3/s2 max-pool, avg-pool + FC + tanh head (K4), and the
+// R^3 x so(3) pose update / label (K6 / K5).  Each replaces numpy/cv2 CPU code in the reference;
+// the file:line each follows is cited at the kernel.
+#include "aux_kernels.h"
+#include "ptx.cuh"
+#include <cfloat>
+
+namespace se3tn {
+
+// =============================================================================================
+// K0: crop window + nearest resize + depth offset/clip + (x-mean)/std  -> padded NHWC4
+// =============================================================================================
+// bbox:   reference Utils.py:302-316 (compute_bbox): 4 corners of an object_width-mm square at the
+//         object depth, projected in float64, np.round (half-to-even == rint) to int32.
+// crop:   reference Utils.py:320-359 (crop_bbox): window copy with zero padding outside the frame,
+//         then cv2.resize(INTER_NEAREST): src = min(floor(dst * (1/(dsize/ssize))), ssize-1).
+// depth:  reference data_augmentation.py:134-144: invalid = d<=100 || d>=2000 (raw mm), then
+//         float32(double(d) -/+ z*1000), invalid -> 2000.  (numpy>=2 semantics, see oracle header.)
+// norm:   reference data_augmentation.py:154-164: (x - mean[c]) / std[c]; float32 arithmetic when
+//         mean/std are float32 arrays (what train.py:121-125 saves), float64 otherwise.
+// pack:   reference data_augmentation.py:179-189 builds CHW float32; here the result goes straight
+//         into the stem conv's zero-padded NHWC4 layout (and optionally to NCHW for the drop-in API).
+
+__device__ __forceinline__ void bbox_window(const double* pose, double fx, double fy, double cx, double cy,
+                                            double width, double sx, double sy, double sz,
+                                            int& top, int& left, int& ch, int& cw)
+{
+    const double ox = pose[3] * sx, oy = pose[7] * sy, oz = pose[11] * sz;
+    const double half = width / 2;
+    // u for x-half / x+half, v for y-half / y+half (the 4 corners share these two values each)
+    const double u0 = rint(__dadd_rn(__ddiv_rn(__dmul_rn(oz == oz ? (ox - half) : 0.0, fx), oz), cx));
+    const double u1 = rint(__dadd_rn(__ddiv_rn(__dmul_rn(ox + half, fx), oz), cx));
+    const double v0 = rint(__dadd_rn(__ddiv_rn(__dmul_rn(oy - half, fy), oz), cy));
+    const double v1 = rint(__dadd_rn(__ddiv_rn(__dmul_rn(oy + half, fy), oz), cy));
+    const double umin = fmin(u0, u1), umax = fmax(u0, u1), vmin = fmin(v0, v1), vmax = fmax(v0, v1);
+    // clamp to int range so degenerate poses (z ~ 0) cannot overflow
+    const double lim = 1.0e9;
+    left = static_cast<int>(fmax(-lim, fmin(lim, umin)));
+    top = static_cast<int>(fmax(-lim, fmin(lim, vmin)));
+    cw = static_cast<int>(fmax(-lim, fmin(lim, umax))) - left;
+    ch = static_cast<int>(fmax(-lim, fmin(lim, vmax))) - top;
+}
+
+__device__ __forceinline__ float norm_f32(float x, float m, float s) { return __fdiv_rn(__fsub_rn(x, m), s); }
+__device__ __forceinline__ float norm_f64(float x, double m, double s) { return static_cast<float>(__ddiv_rn(__dsub_rn(static_cast<double>(x), m), s)); }
+
+__device__ __forceinline__ float depth_offset(unsigned d, double z1000, bool gl) {
+    if (d <= 100u || d >= 2000u) return 2000.f;
+    return static_cast<float>(gl ? __dadd_rn(static_cast<double>(d), z1000) : __dsub_rn(static_cast<double>(d), z1000));
+}
+
+__global__ void __launch_bounds__(256)
+preprocess_kernel(PreprocessArgs a)
+{
+    const int n = blockIdx.y;
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= kImg * kImg) return;
+    const int y = pix / kImg, x = pix - y * kImg;
+    const double* pose = a.poses + n * 16;
+    const double z = pose[11];
+    const bool gl = z < 0;
+    const double z1000 = __dmul_rn(z, 1000.0);
+
+    // ---- B: observed frame crop --------------------------------------------------------------
+    int top, left, ch, cw;
+    bbox_window(pose, a.fx, a.fy, a.cx, a.cy, a.object_width[n], 1000.0, 1000.0, 1000.0, top, left, ch, cw);
+    unsigned r = 0, gch = 0, b = 0, d = 0;
+    if (ch > 0 && cw > 0) {
+        // cv2 resizeNN index: floor(dst * ifx), ifx = 1/(dsize/ssize) in double, clamped to ssize-1
+        const double ifx = 1.0 / (static_cast<double>(kImg) / cw);
+        const double ify = 1.0 / (static_cast<double>(kImg) / ch);
+        int sx = static_cast<int>(floor(x * ifx)); if (sx > cw - 1) sx = cw - 1;
+        int sy = static_cast<int>(floor(y * ify)); if (sy > ch - 1) sy = ch - 1;
+        const int fy_ = top + sy, fx_ = left + sx;
+        if (fy_ >= 0 && fy_ < a.H && fx_ >= 0 && fx_ < a.W) {
+            const size_t fo = static_cast<size_t>(fy_) * a.W + fx_;
+            const uint8_t* pr = a.frame_rgb + fo * 3;
+            r = pr[0]; gch = pr[1]; b = pr[2];
+            d = a.frame_depth[fo];
+        }
+    }
+    if (a.crop_rgb) {
+        uint8_t* o = a.crop_rgb + (static_cast<size_t>(n) * kImg * kImg + pix) * 3;
+        o[0] = r; o[1] = gch; o[2] = b;
+    }
+    if (a.crop_depth) a.crop_depth[static_cast<size_t>(n) * kImg * kImg + pix] = static_cast<uint16_t>(d);
+
+    // ---- A: rendered previous view -----------------------------------------------------------
+    const size_t ao = static_cast<size_t>(n) * kImg * kImg + pix;
+    const uint8_t* pa = a.rgbA + ao * 3;
+    const unsigned ra = pa[0], ga = pa[1], ba = pa[2], da = a.depthA[ao];
+
+    const int wi = a.weight_ids ? a.weight_ids[n] : 0;
+    float4 vA, vB;
+    const float dA = depth_offset(da, z1000, gl), dB = depth_offset(d, z1000, gl);
+    if (a.stats_f64) {
+        const double* m = a.mean64 + wi * 8; const double* s = a.std64 + wi * 8;
+        vA = make_float4(norm_f64(ra, m[0], s[0]), norm_f64(ga, m[1], s[1]), norm_f64(ba, m[2], s[2]), norm_f64(dA, m[3], s[3]));
+        vB = make_float4(norm_f64(r, m[4], s[4]), norm_f64(gch, m[5], s[5]), norm_f64(b, m[6], s[6]), norm_f64(dB, m[7], s[7]));
+    } else {
+        const float* m = a.mean32 + wi * 8; const float* s = a.std32 + wi * 8;
+        vA = make_float4(norm_f32(ra, m[0], s[0]), norm_f32(ga, m[1], s[1]), norm_f32(ba, m[2], s[2]), norm_f32(dA, m[3], s[3]));
+        vB = make_float4(norm_f32(r, m[4], s[4]), norm_f32(gch, m[5], s[5]), norm_f32(b, m[6], s[6]), norm_f32(dB, m[7], s[7]));
+    }
+    if (a.nchwA) {
+        float* oa = a.nchwA + static_cast<size_t>(n) * 4 * kImg * kImg + pix;
+        float* ob = a.nchwB + static_cast<size_t>(n) * 4 * kImg * kImg + pix;
+        oa[0] = vA.x; oa[kImg * kImg] = vA.y; oa[2 * kImg * kImg] = vA.z; oa[3 * kImg * kImg] = vA.w;
+        ob[0] = vB.x; ob[kImg * kImg] = vB.y; ob[2 * kImg * kImg] = vB.z; ob[3 * kImg * kImg] = vB.w;
+    }
+    if (a.stemA) {
+        if (a.round_tf32) {
+            vA = make_float4(ptx::to_tf32(vA.x), ptx::to_tf32(vA.y), ptx::to_tf32(vA.z), ptx::to_tf32(vA.w));
+            vB = make_float4(ptx::to_tf32(vB.x), ptx::to_tf32(vB.y), ptx::to_tf32(vB.z), ptx::to_tf32(vB.w));
+        }
+        const size_t so = (static_cast<size_t>(n) * kStemH + (y + 3)) * kStemW + (x + 3);
+        reinterpret_cast<float4*>(a.stemA)[so] = vA;
+        reinterpret_cast<float4*>(a.stemB)[so] = vB;
+    }
+}
+
+cudaError_t launch_preprocess(const PreprocessArgs& a, int n, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    dim3 grid((kImg * kImg + 255) / 256, n);
+    preprocess_kernel<<<grid, 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+// =============================================================================================
+// NCHW float32 (N,4,176,176) -> zero-padded NHWC4 stem input (for Se3TrackNet.forward(A, B))
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+nchw_to_stem_kernel(const float* __restrict__ src, float* __restrict__ dst, int round_tf32)
+{
+    const int n = blockIdx.y;
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= kImg * kImg) return;
+    const int y = pix / kImg, x = pix - y * kImg;
+    const float* s = src + static_cast<size_t>(n) * 4 * kImg * kImg + pix;
+    float4 v = make_float4(s[0], s[kImg * kImg], s[2 * kImg * kImg], s[3 * kImg * kImg]);
+    if (round_tf32) v = make_float4(ptx::to_tf32(v.x), ptx::to_tf32(v.y), ptx::to_tf32(v.z), ptx::to_tf32(v.w));
+    reinterpret_cast<float4*>(dst)[(static_cast<size_t>(n) * kStemH + (y + 3)) * kStemW + (x + 3)] = v;
+}
+
+cudaError_t launch_nchw_to_stem(const float* src, float* dst, int n, int round_tf32, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    dim3 grid((kImg * kImg + 255) / 256, n);
+    nchw_to_stem_kernel<<<grid, 256, 0, s>>>(src, dst, round_tf32);
+    return cudaGetLastError();
+}
+
+// =============================================================================================
+// MaxPool2d(3, 2, 1) on NHWC (reference se3_tracknet.py:58,62,85,89).  Padding behaves as -inf
+// (the SELU output it follows can be negative).
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+maxpool_kernel(const float4* __restrict__ in, float4* __restrict__ out, int n_img, int Hin, int Win, int C4)
+{
+    const int Ho = Hin / 2, Wo = Win / 2;
+    const long long total = static_cast<long long>(n_img) * Ho * Wo * C4;
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = static_cast<int>(i % C4);
+    long long r = i / C4;
+    const int ox = static_cast<int>(r % Wo); r /= Wo;
+    const int oy = static_cast<int>(r % Ho);
+    const int n = static_cast<int>(r / Ho);
+    float4 m = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+        const int y = 2 * oy + dy;
+        if (y < 0 || y >= Hin) continue;
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int x = 2 * ox + dx;
+            if (x < 0 || x >= Win) continue;
+            const float4 v = __ldg(&in[((static_cast<size_t>(n) * Hin + y) * Win + x) * C4 + c]);
+            m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+        }
+    }
+    out[i] = m;
+}
+
+cudaError_t launch_maxpool(const float* in, float* out, int n_img, int Hin, int Win, int C, cudaStream_t s) {
+    const long long total = static_cast<long long>(n_img) * (Hin / 2) * (Win / 2) * (C / 4);
+    if (total <= 0) return cudaSuccess;
+    maxpool_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(
+        reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), n_img, Hin, Win, C / 4);
+    return cudaGetLastError();
+}
+
+// =============================================================================================
+// K4 head: AdaptiveAvgPool2d(1) + Linear(512,3) + Tanh for both heads
+// (reference se3_tracknet.py:100-102, 107-109).  x: NHWC (N, 11*11, 1024): channels [0,512) are
+// the translation head, [512,1024) the rotation head.  One CTA (256 threads x 4 channels) per image.
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+head_kernel(const float4* __restrict__ x, const float* __restrict__ fcw /*[6][512]*/, const float* __restrict__ fcb /*[6]*/,
+            float* __restrict__ out_trans, float* __restrict__ out_rot, int npix)
+{
+    __shared__ float red[8][3];
+    const int n = blockIdx.x, t = threadIdx.x;
+    const float4* xp = x + static_cast<size_t>(n) * npix * 256 + t;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = 0; p < npix; ++p) {
+        const float4 v = __ldg(xp + static_cast<size_t>(p) * 256);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    const float inv = 1.0f / static_cast<float>(npix);
+    s.x *= inv; s.y *= inv; s.z *= inv; s.w *= inv;
+    const int head = t >> 7;                 // 0: trans, 1: rot
+    const int c = (t & 127) * 4;             // channel within the head
+    float part[3];
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(fcw + (head * 3 + o) * 512 + c));
+        part[o] = s.x * w.x + s.y * w.y + s.z * w.z + s.w * w.w;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+        for (int o = 0; o < 3; ++o) part[o] += __shfl_xor_sync(0xffffffffu, part[o], off);
+    if ((t & 31) == 0) { red[t >> 5][0] = part[0]; red[t >> 5][1] = part[1]; red[t >> 5][2] = part[2]; }
+    __syncthreads();
+    if (t < 6) {
+        const int h = t / 3, o = t % 3;
+        const float v = red[h * 4 + 0][o] + red[h * 4 + 1][o] + red[h * 4 + 2][o] + red[h * 4 + 3][o] + fcb[t];
+        (h == 0 ? out_trans : out_rot)[n * 3 + o] = tanhf(v);
+    }
+}
+
+cudaError_t launch_head(const float* x, const float* fcw, const float* fcb, float* out_trans, float* out_rot,
+                        int n_img, int npix, cudaStream_t s) {
+    if (n_img <= 0) return cudaSuccess;
+    head_kernel<<<n_img, 256, 0, s>>>(reinterpret_cast<const float4*>(x), fcw, fcb, out_trans, out_rot, npix);
+    return cudaGetLastError();
+}
+
+// =============================================================================================
+// NHWC -> NCHW (the 'feature' entry of the reference's output dict, se3_tracknet.py:96)
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+nhwc_to_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int HW, int C)
+{
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;    // 32 x 8
+    for (int j = ty; j < 32; j += 8) {
+        const int p = p0 + j, c = c0 + tx;
+        tile[j][tx] = (p < HW && c < C) ? in[(static_cast<size_t>(n) * HW + p) * C + c] : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int c = c0 + j, p = p0 + tx;
+        if (p < HW && c < C) out[(static_cast<size_t>(n) * C + c) * HW + p] = tile[tx][j];
+    }
+}
+
+cudaError_t launch_nhwc_to_nchw(const float* in, float* out, int n_img, int HW, int C, cudaStream_t s) {
+    if (n_img <= 0) return cudaSuccess;
+    dim3 grid((HW + 31) / 32, (C + 31) / 32, n_img);
+    nhwc_to_nchw_kernel<<<grid, 256, 0, s>>>(in, out, HW, C);
+    return cudaGetLastError();
+}
+
+// =============================================================================================
+// K6 pose update (reference datasets.py:159-175): t' = t + float32(trans*tn);
+// R' = float32(Rodrigues(float32(rot*rn))) . R, all remaining arithmetic in float64 (F9/F10).
+// Rodrigues follows OpenCV's cvRodrigues2 vector->matrix branch:
+//   theta = |r|; theta < DBL_EPSILON -> I; else R = cos*I + (1-cos)*rr^T + sin*[r]x, r <- r/theta.
+// =============================================================================================
+__device__ __forceinline__ void rodrigues_exp_f32in(float rx32, float ry32, float rz32, double R[9], bool round_f32)
+{
+    double rx = rx32, ry = ry32, rz = rz32;
+    const double theta = sqrt(rx * rx + ry * ry + rz * rz);
+    if (theta < DBL_EPSILON) {
+        R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
+        return;
+    }
+    const double c = cos(theta), s = sin(theta), c1 = 1.0 - c, it = 1.0 / theta;
+    rx *= it; ry *= it; rz *= it;
+    R[0] = c + c1 * rx * rx;      R[1] = c1 * rx * ry - s * rz; R[2] = c1 * rx * rz + s * ry;
+    R[3] = c1 * rx * ry + s * rz; R[4] = c + c1 * ry * ry;      R[5] = c1 * ry * rz - s * rx;
+    R[6] = c1 * rx * rz - s * ry; R[7] = c1 * ry * rz + s * rx; R[8] = c + c1 * rz * rz;
+    if (round_f32)
+#pragma unroll
+        for (int i = 0; i < 9; ++i) R[i] = static_cast<double>(static_cast<float>(R[i]));
+}
+
+__global__ void pose_update_kernel(const double* __restrict__ poses_in, const float* __restrict__ trans,
+                                   const float* __restrict__ rot, float tn, float rn,
+                                   double* __restrict__ poses_out, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* A = poses_in + i * 16;
+    double* B = poses_out + i * 16;
+    // float32 * python-float stays float32 in numpy
+    const float t0 = __fmul_rn(trans[i * 3 + 0], tn), t1 = __fmul_rn(trans[i * 3 + 1], tn), t2 = __fmul_rn(trans[i * 3 + 2], tn);
+    const float r0 = __fmul_rn(rot[i * 3 + 0], rn), r1 = __fmul_rn(rot[i * 3 + 1], rn), r2 = __fmul_rn(rot[i * 3 + 2], rn);
+    double R[9];
+    rodrigues_exp_f32in(r0, r1, r2, R, true);
+    double out[16];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            out[r * 4 + c] = __dadd_rn(__dadd_rn(__dmul_rn(R[r * 3 + 0], A[0 * 4 + c]), __dmul_rn(R[r * 3 + 1], A[1 * 4 + c])),
+                                       __dmul_rn(R[r * 3 + 2], A[2 * 4 + c]));
+    out[3] = static_cast<double>(t0) + A[3];
+    out[7] = static_cast<double>(t1) + A[7];
+    out[11] = static_cast<double>(t2) + A[11];
+    out[12] = 0; out[13] = 0; out[14] = 0; out[15] = 1;        // B_in_cam starts as np.eye(4)
+#pragma unroll
+    for (int k = 0; k < 16; ++k) B[k] = out[k];
+}
+
+cudaError_t launch_pose_update(const double* poses_in, const float* trans, const float* rot, float tn, float rn,
+                               double* poses_out, int n, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    pose_update_kernel<<<(n + 127) / 128, 128, 0, s>>>(poses_in, trans, rot, tn, rn, poses_out, n);
+    return cudaGetLastError();
+}
+
+// =============================================================================================
+// K5 so(3) log label (reference datasets.py:141-150): trans = (tB - tA)/tn;
+// rot = Rodrigues^-1(normalize_cols(R_B R_A^T))/rn  (Utils.py:363-367 + cvRodrigues2 matrix->vector
+// branch: R <- U V^T from the SVD, then the antisymmetric-part formula with its small-angle cases).
+// The SVD's U V^T is the orthogonal polar factor of R; it is computed here with the Newton
+// iteration X <- (X + X^-T)/2, which converges quadratically to the same matrix.
+// =============================================================================================
+__device__ __forceinline__ void inv_transpose3(const double* m, double* o) {
+    const double c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
+    const double det = m[0] * c00 + m[1] * c01 + m[2] * c02;
+    const double id = 1.0 / det;
+    o[0] = c00 * id; o[1] = c01 * id; o[2] = c02 * id;
+    o[3] = (m[2] * m[7] - m[1] * m[8]) * id; o[4] = (m[0] * m[8] - m[2] * m[6]) * id; o[5] = (m[1] * m[6] - m[0] * m[7]) * id;
+    o[6] = (m[1] * m[5] - m[2] * m[4]) * id; o[7] = (m[2] * m[3] - m[0] * m[5]) * id; o[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+}
+
+__global__ void so3_log_kernel(const double* __restrict__ poses_a, const double* __restrict__ poses_b,
+                               double tn, double rn, double* __restrict__ trans_label, double* __restrict__ rot_label, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* A = poses_a + i * 16; const double* B = poses_b + i * 16;
+    trans_label[i * 3 + 0] = (B[3] - A[3]) / tn;
+    trans_label[i * 3 + 1] = (B[7] - A[7]) / tn;
+    trans_label[i * 3 + 2] = (B[11] - A[11]) / tn;
+    double R[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)     // R_B . R_A^T
+            R[r * 3 + c] = B[r * 4 + 0] * A[c * 4 + 0] + B[r * 4 + 1] * A[c * 4 + 1] + B[r * 4 + 2] * A[c * 4 + 2];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {       // column normalise
+        const double nr = sqrt(R[c] * R[c] + R[3 + c] * R[3 + c] + R[6 + c] * R[6 + c]);
+        R[c] /= nr; R[3 + c] /= nr; R[6 + c] /= nr;
+    }
+    for (int it = 0; it < 12; ++it) {   // polar factor
+        double T[9]; inv_transpose3(R, T);
+        double diff = 0;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { const double v = 0.5 * (R[k] + T[k]); diff = fmax(diff, fabs(v - R[k])); R[k] = v; }
+        if (diff < 1e-16) break;
+    }
+    double rx = R[7] - R[5], ry = R[2] - R[6], rz = R[3] - R[1];
+    const double s = sqrt((rx * rx + ry * ry + rz * rz) * 0.25);
+    double c = (R[0] + R[4] + R[8] - 1) * 0.5;
+    c = c > 1. ? 1. : (c < -1. ? -1. : c);
+    double theta = acos(c);
+    if (s < 1e-5) {
+        if (c > 0) { rx = ry = rz = 0; }
+        else {
+            double t;
+            t = (R[0] + 1) * 0.5; rx = sqrt(fmax(t, 0.));
+            t = (R[4] + 1) * 0.5; ry = sqrt(fmax(t, 0.)) * (R[1] < 0 ? -1. : 1.);
+            t = (R[8] + 1) * 0.5; rz = sqrt(fmax(t, 0.)) * (R[2] < 0 ? -1. : 1.);
+            if (fabs(rx) < fabs(ry) && fabs(rx) < fabs(rz) && ((R[5] > 0) != (ry * rz > 0))) rz = -rz;
+            theta /= sqrt(rx * rx + ry * ry + rz * rz);
+            rx *= theta; ry *= theta; rz *= theta;
+        }
+    } else {
+        const double vth = theta / (2 * s);
+        rx *= vth; ry *= vth; rz *= vth;
+    }
+    rot_label[i * 3 + 0] = rx / rn; rot_label[i * 3 + 1] = ry / rn; rot_label[i * 3 + 2] = rz / rn;
+}
+
+cudaError_t launch_so3_log(const double* poses_a, const double* poses_b, double tn, double rn,
+                           double* trans_label, double* rot_label, int n, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    so3_log_kernel<<<(n + 127) / 128, 128, 0, s>>>(poses_a, poses_b, tn, rn, trans_label, rot_label, n);
+    return cudaGetLastError();
+}
+
+}  // namespace se3tn

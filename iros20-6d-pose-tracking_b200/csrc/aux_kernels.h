@@ -1,0 +1,44 @@
+// Launch wrappers for the non-GEMM kernels of the hot path (see aux_kernels.cu).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace se3tn {
+
+constexpr int kImg = 176;                 // crop resolution (reference dataset_info.yml:15)
+constexpr int kStemH = kImg + 6;          // 3-pixel zero halo for the 7x7 stem
+constexpr int kStemW = kImg + 8;          // 3 left + 176 + 5 right: the stem K-slice reads 8 pixels from x = 2*ox
+constexpr size_t kStemImgFloats = static_cast<size_t>(kStemH) * kStemW * 4;
+
+struct PreprocessArgs {
+    const uint8_t* frame_rgb;      // H x W x 3
+    const uint16_t* frame_depth;   // H x W (mm)
+    int H, W;
+    double fx, fy, cx, cy;
+    const double* poses;           // N x 16 row-major 4x4
+    const double* object_width;    // N (mm)
+    const uint8_t* rgbA;           // N x 176 x 176 x 3 (renderer output)
+    const uint16_t* depthA;        // N x 176 x 176
+    const int* weight_ids;         // N or null (all 0): selects the mean/std row
+    const float* mean32; const float* std32;      // [sets][8] when !stats_f64
+    const double* mean64; const double* std64;    // [sets][8] when stats_f64
+    int stats_f64;
+    int round_tf32;
+    float* stemA; float* stemB;    // N x 182 x 184 x 4 (nullable)
+    float* nchwA; float* nchwB;    // N x 4 x 176 x 176 (nullable)
+    uint8_t* crop_rgb;             // N x 176 x 176 x 3 (nullable)
+    uint16_t* crop_depth;          // N x 176 x 176 (nullable)
+};
+
+cudaError_t launch_preprocess(const PreprocessArgs& a, int n, cudaStream_t s);
+cudaError_t launch_nchw_to_stem(const float* src, float* dst, int n, int round_tf32, cudaStream_t s);
+cudaError_t launch_maxpool(const float* in, float* out, int n_img, int Hin, int Win, int C, cudaStream_t s);
+cudaError_t launch_head(const float* x, const float* fcw, const float* fcb, float* out_trans, float* out_rot,
+                        int n_img, int npix, cudaStream_t s);
+cudaError_t launch_nhwc_to_nchw(const float* in, float* out, int n_img, int HW, int C, cudaStream_t s);
+cudaError_t launch_pose_update(const double* poses_in, const float* trans, const float* rot, float tn, float rn,
+                               double* poses_out, int n, cudaStream_t s);
+cudaError_t launch_so3_log(const double* poses_a, const double* poses_b, double tn, double rn,
+                           double* trans_label, double* rot_label, int n, cudaStream_t s);
+
+}  // namespace se3tn

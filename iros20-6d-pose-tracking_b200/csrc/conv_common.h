@@ -1,0 +1,76 @@
+// Shared host/device descriptors for one convolution launch of the se(3)-TrackNet conv stack.
+//
+// Every conv on the path (reference se3_tracknet.py:57-78; 7x7 s2 stem, 3x3 s1, 3x3 s2) is
+// described the same way: an NHWC activation tensor, a list of filter "taps", each tap a
+// displacement in input pixels plus `k_per_tap` contiguous input floats, and a K-major weight
+// matrix W[g*Cout + co][tap*k_per_tap + c] with the eval-mode BatchNorm folded in.
+//
+//  * 3x3:  9 taps (dy,dx) in {-1,0,1}^2, k_per_tap = Cin (channels of one pixel)
+//  * stem: 7 taps (one per filter ROW r), k_per_tap = 32 = 8 pixels x 4 channels of the
+//          zero-padded NHWC4 input starting at x = 2*ox (7 real filter columns + 1 zero column)
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace se3tn {
+
+constexpr int kMaxTaps = 9;
+constexpr int kBlockM = 128;          // UMMA M (TMEM lanes)
+constexpr int kChunkBytes = 128;      // one SWIZZLE_128B row: 32 tf32 / 64 bf16 along K
+
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_SELU = 2 };
+
+struct Tap {
+    int16_t dy, dx;      // input-pixel displacement of this tap relative to (oy*stride, ox*stride)
+    int8_t  map;         // tcgen05 path: which A tensor map (s2: 4 parity views; stem: one per filter row)
+    int8_t  c1, c2;      // tcgen05 path: TMA coordinate deltas for dims 1 (x) and 2 (y)
+    int8_t  pad_;
+};
+
+struct ConvGeom {
+    // input (NHWC, `in_cstride` floats per pixel, channel window starting at in_coff (+ g*cin))
+    int Hin, Win, in_cstride, in_coff;
+    // output
+    int Ho, Wo, stride;
+    int cin;             // K floats per tap per group
+    int cout;            // per group
+    int groups;
+    int num_taps;
+    int n_img;
+    Tap taps[kMaxTaps];
+    // epilogue
+    int out_cstride, out_coff;
+    int res_cstride, res_coff;
+    int act;
+    int round_tf32;      // round stored activations to tf32 (rna) so the next UMMA sees exact operands
+};
+
+struct ConvPtrs {
+    const float* in;
+    const float* w;      // [groups*cout][num_taps*cin]
+    const float* bias;   // [groups*cout]
+    const float* res;    // nullable, NHWC
+    float* out;
+};
+
+// ---- tcgen05 path only ------------------------------------------------------------------
+struct UmmaTiling {
+    int bw, bh, bn;          // pixel box of one M tile: bw*bh*bn <= 128 rows
+    int tiles_x, tiles_y;    // boxes per image
+    int m_tiles;             // ceil(n_img/bn) * tiles_y * tiles_x
+    int n_tiles;             // cout / BLOCK_N
+    int chunks_per_tap;      // cin / 32
+    int img_first;           // absolute index of the first image this launch covers
+};
+
+struct alignas(64) UmmaMaps {
+    CUtensorMap a[7];
+    CUtensorMap b;
+};
+
+cudaError_t launch_conv_umma(const UmmaMaps& maps, const ConvGeom& g, const UmmaTiling& t,
+                             const ConvPtrs& p, int block_n, int num_sms, cudaStream_t stream);
+cudaError_t launch_conv_direct(const ConvGeom& g, const ConvPtrs& p, cudaStream_t stream);
+
+}  // namespace se3tn

@@ -1,0 +1,571 @@
+// libse3tn: context, per-object weight sets, TMA tensor maps and the launch schedule of the
+// se(3)-TrackNet hot path behind the C ABI declared in include/se3tn.h.
+#include "../../include/se3tn.h"
+#include "conv_common.h"
+#include "aux_kernels.h"
+#include "ptx.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace se3tn;
+
+namespace {
+
+// --------------------------------------------------------------------------------------------
+// Network schedule: 14 conv launches cover the reference's 17 convs (se3_tracknet.py:57-78).
+// --------------------------------------------------------------------------------------------
+enum Buf { B_X0A, B_X0B, B_Y1A, B_Y1B, B_P1A, B_P1B, B_T1, B_T2, B_U, B_CAT, B_F1, B_T4, B_F2, B_H1, B_H2, B_H3, B_COUNT };
+
+constexpr size_t kBufFloats[B_COUNT] = {
+    kStemImgFloats, kStemImgFloats,                 // X0A, X0B  (182 x 184 x 4)
+    88 * 88 * 64, 88 * 88 * 64,                     // Y1A, Y1B
+    44 * 44 * 64, 44 * 44 * 64,                     // P1A, P1B
+    44 * 44 * 64, 44 * 44 * 64, 44 * 44 * 64,       // T1, T2, U
+    44 * 44 * 128,                                  // CAT
+    22 * 22 * 256, 22 * 22 * 256, 22 * 22 * 256,    // F1, T4, F2
+    11 * 11 * 1024, 11 * 11 * 1024, 11 * 11 * 1024  // H1, H2, H3
+};
+
+enum Kind { K_STEM, K_S1, K_S2 };
+
+struct LayerSpec {
+    Kind kind;
+    Buf in, out, res;            // res == B_COUNT: none
+    int Hin, Win, in_c;          // input spatial + channels per pixel of the input buffer
+    int cin, cout, groups;       // per group
+    int out_c, out_coff;         // channels per pixel of the output buffer, channel offset
+    int act;
+    int block_n;
+};
+
+constexpr Buf NONE = B_COUNT;
+const LayerSpec kLayers[14] = {
+    // kind   in     out    res    Hin  Win  in_c  cin  cout groups out_c coff act       BN
+    {K_STEM, B_X0A, B_Y1A, NONE,  182, 184,   4,   32,   64, 1,    64,   0, ACT_SELU,  64},   // convA1
+    {K_STEM, B_X0B, B_Y1B, NONE,  182, 184,   4,   32,   64, 1,    64,   0, ACT_SELU,  64},   // convB1
+    {K_S1,   B_P1A, B_T1,  NONE,   44,  44,  64,   64,   64, 1,    64,   0, ACT_RELU,  64},   // convA2.conv1
+    {K_S1,   B_T1,  B_CAT, B_P1A,  44,  44,  64,   64,   64, 1,   128,   0, ACT_RELU,  64},   // convA2.conv2 (+id) -> cat[0:64]
+    {K_S1,   B_P1B, B_T2,  NONE,   44,  44,  64,   64,   64, 1,    64,   0, ACT_RELU,  64},   // convB2.conv1
+    {K_S1,   B_T2,  B_U,   B_P1B,  44,  44,  64,   64,   64, 1,    64,   0, ACT_RELU,  64},   // convB2.conv2 (+id)
+    {K_S1,   B_U,   B_T2,  NONE,   44,  44,  64,   64,   64, 1,    64,   0, ACT_RELU,  64},   // convB3.conv1
+    {K_S1,   B_T2,  B_CAT, B_U,    44,  44,  64,   64,   64, 1,   128,  64, ACT_RELU,  64},   // convB3.conv2 (+id) -> cat[64:128]
+    {K_S2,   B_CAT, B_F1,  NONE,   44,  44, 128,  128,  256, 1,   256,   0, ACT_SELU, 128},   // convAB1
+    {K_S1,   B_F1,  B_T4,  NONE,   22,  22, 256,  256,  256, 1,   256,   0, ACT_RELU, 128},   // convAB2.conv1
+    {K_S1,   B_T4,  B_F2,  B_F1,   22,  22, 256,  256,  256, 1,   256,   0, ACT_RELU, 128},   // convAB2.conv2 (+id) = 'feature'
+    {K_S2,   B_F2,  B_H1,  NONE,   22,  22, 256,  256, 1024, 1,  1024,   0, ACT_SELU, 256},   // trans_conv1 ++ rot_conv1
+    {K_S1,   B_H1,  B_H2,  NONE,   11,  11, 1024, 512,  512, 2,  1024,   0, ACT_RELU, 256},   // {trans,rot}_conv2.conv1
+    {K_S1,   B_H2,  B_H3,  B_H1,   11,  11, 1024, 512,  512, 2,  1024,   0, ACT_RELU, 256},   // {trans,rot}_conv2.conv2 (+id)
+};
+
+inline int layer_taps(const LayerSpec& L) { return L.kind == K_STEM ? 7 : 9; }
+inline int layer_ktot(const LayerSpec& L) { return layer_taps(L) * L.cin; }
+inline int layer_rows(const LayerSpec& L) { return L.cout * L.groups; }
+inline int layer_Ho(const LayerSpec& L) { return L.kind == K_STEM ? 88 : (L.kind == K_S2 ? L.Hin / 2 : L.Hin); }
+
+constexpr size_t kFcFloats = 6 * 512 + 6;
+
+size_t blob_floats() {
+    size_t n = 0;
+    for (const LayerSpec& L : kLayers) n += static_cast<size_t>(layer_rows(L)) * layer_ktot(L) + layer_rows(L);
+    return n + kFcFloats;
+}
+
+struct WeightSet {
+    float* dev = nullptr;           // exact fp32 blob
+    float* dev_tf32 = nullptr;      // same layout, conv weights rounded to tf32 (biases / fc untouched)
+    size_t w_off[14], b_off[14];
+    size_t fc_off;
+    CUtensorMap bmap[14];           // over dev_tf32
+    float mean32[8], std32[8];
+    double mean64[8], std64[8];
+    int stats_f64 = 0;
+    bool has_stats = false;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+std::string g_create_error;
+
+}  // namespace
+
+struct se3tn_ctx {
+    int device = 0;
+    int max_batch = 0;
+    int num_sms = 0;
+    bool own_workspace = false;
+    uint8_t* workspace = nullptr;
+    float* buf[B_COUNT] = {};
+    CUtensorMap amap[14][7];
+    EncodeTiledFn encode = nullptr;
+    std::map<int, WeightSet> weights;
+    // device copies of per-set stats, rebuilt when a set changes: [max_id+1][8]
+    float* d_mean32 = nullptr; float* d_std32 = nullptr; double* d_mean64 = nullptr; double* d_std64 = nullptr;
+    int stats_rows = 0; bool stats_dirty = true; int stats_f64 = 0;
+    int launches = 0;
+    int umma_block_n_override = 0;
+    std::string err;
+};
+
+namespace {
+
+int fail(se3tn_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+#define CU_TRY(ctx, expr)                                                                        \
+    do { cudaError_t e_ = (expr);                                                                \
+         if (e_ != cudaSuccess) return fail((ctx), SE3TN_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); } while (0)
+
+size_t workspace_floats(int max_batch) {
+    size_t n = 0;
+    for (int b = 0; b < B_COUNT; ++b) {
+        size_t f = kBufFloats[b] * static_cast<size_t>(max_batch);
+        n += (f + 255) & ~size_t(255);           // keep every buffer 1 KB aligned
+    }
+    return n;
+}
+
+// rank-4 fp32 tensor map, SWIZZLE_128B, box inner = 32 floats
+int make_map4(se3tn_ctx* c, CUtensorMap* m, const void* base, const cuuint64_t dims[4], const cuuint64_t strides_bytes[3],
+              const cuuint32_t box[4], CUtensorMapL2promotion l2, const char* what) {
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = c->encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char msg[512];
+        snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled(%s) failed: CUresult %d dims {%llu,%llu,%llu,%llu} strides {%llu,%llu,%llu} box {%u,%u,%u,%u}",
+                 what, (int)r, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2], (unsigned long long)dims[3],
+                 (unsigned long long)strides_bytes[0], (unsigned long long)strides_bytes[1], (unsigned long long)strides_bytes[2],
+                 box[0], box[1], box[2], box[3]);
+        return fail(c, SE3TN_ERR_CUDA, msg);
+    }
+    return SE3TN_OK;
+}
+
+int make_map2(se3tn_ctx* c, CUtensorMap* m, const void* base, cuuint64_t inner, cuuint64_t rows, cuuint32_t box_rows, const char* what) {
+    const cuuint64_t dims[2] = {inner, rows};
+    const cuuint64_t strides[1] = {inner * sizeof(float)};
+    const cuuint32_t box[2] = {32, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = c->encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char msg[256];
+        snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled(%s) failed: CUresult %d dims {%llu,%llu} box {32,%u}", what, (int)r,
+                 (unsigned long long)inner, (unsigned long long)rows, box_rows);
+        return fail(c, SE3TN_ERR_CUDA, msg);
+    }
+    return SE3TN_OK;
+}
+
+void tile_box(const LayerSpec& L, int& bw, int& bh, int& bn) {
+    if (L.kind == K_STEM) { bw = 8; bh = 8; bn = 2; } else { bw = 11; bh = 11; bn = 1; }
+}
+
+int block_n_of(const se3tn_ctx* c, const LayerSpec& L) {
+    int bn = L.block_n;
+    if (c->umma_block_n_override && L.cout % c->umma_block_n_override == 0 && L.cout >= c->umma_block_n_override)
+        bn = c->umma_block_n_override;
+    return bn;
+}
+
+// Activation-side tensor maps: built once per context (they depend only on the workspace layout).
+int build_activation_maps(se3tn_ctx* c) {
+    const cuuint64_t N = static_cast<cuuint64_t>(c->max_batch);
+    for (int li = 0; li < 14; ++li) {
+        const LayerSpec& L = kLayers[li];
+        const float* base = c->buf[L.in];
+        int bw, bh, bn; tile_box(L, bw, bh, bn);
+        char what[64];
+        if (L.kind == K_STEM) {
+            // Overlapping-window view of the zero-padded NHWC4 input: coordinate (k, ox, oy, n) ->
+            // float offset k + 8*ox + (2*oy + r)*rowpitch + n*imgpitch; one map per filter row r.
+            const cuuint64_t rowpitch = static_cast<cuuint64_t>(kStemW) * 4 * sizeof(float);
+            const cuuint64_t dims[4] = {32, 88, 88, N};
+            const cuuint64_t strides[3] = {8 * sizeof(float), 2 * rowpitch, static_cast<cuuint64_t>(kStemH) * rowpitch};
+            const cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+            for (int r = 0; r < 7; ++r) {
+                snprintf(what, sizeof what, "layer %d stem row %d", li, r);
+                int rc = make_map4(c, &c->amap[li][r], reinterpret_cast<const uint8_t*>(base) + r * rowpitch, dims, strides, box,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, what);
+                if (rc) return rc;
+            }
+        } else if (L.kind == K_S1) {
+            const cuuint64_t C = L.in_c, W = L.Win, H = L.Hin;
+            const cuuint64_t dims[4] = {C, W, H, N};
+            const cuuint64_t strides[3] = {C * 4, W * C * 4, H * W * C * 4};
+            const cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+            snprintf(what, sizeof what, "layer %d s1", li);
+            int rc = make_map4(c, &c->amap[li][0], base, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, what);
+            if (rc) return rc;
+        } else {
+            // stride 2: four parity views (py, px) of the input, each a dense half-resolution tensor
+            const cuuint64_t C = L.in_c, W = L.Win, H = L.Hin;
+            const cuuint64_t dims[4] = {C, W / 2, H / 2, N};
+            const cuuint64_t strides[3] = {2 * C * 4, 2 * W * C * 4, H * W * C * 4};
+            const cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+            for (int py = 0; py < 2; ++py)
+                for (int px = 0; px < 2; ++px) {
+                    snprintf(what, sizeof what, "layer %d s2 parity %d%d", li, py, px);
+                    int rc = make_map4(c, &c->amap[li][py * 2 + px], base + (static_cast<size_t>(py) * W + px) * C, dims, strides, box,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, what);
+                    if (rc) return rc;
+                }
+        }
+    }
+    return SE3TN_OK;
+}
+
+void fill_geom(const LayerSpec& L, int n, bool round_tf32, ConvGeom& g) {
+    memset(&g, 0, sizeof g);
+    g.Hin = L.Hin; g.Win = L.Win; g.in_cstride = L.in_c; g.in_coff = 0;
+    g.Ho = layer_Ho(L); g.Wo = g.Ho;
+    g.stride = (L.kind == K_S1) ? 1 : 2;
+    g.cin = L.cin; g.cout = L.cout; g.groups = L.groups;
+    g.num_taps = layer_taps(L);
+    g.n_img = n;
+    if (L.kind == K_STEM) {
+        // tap r: padded input row 2*oy + r, 32 contiguous floats from padded x = 2*ox
+        for (int r = 0; r < 7; ++r) { g.taps[r].dy = (int16_t)r; g.taps[r].dx = 0; g.taps[r].map = (int8_t)r; g.taps[r].c1 = 0; g.taps[r].c2 = 0; }
+    } else {
+        for (int r = 0; r < 3; ++r)
+            for (int s = 0; s < 3; ++s) {
+                Tap& t = g.taps[r * 3 + s];
+                t.dy = (int16_t)(r - 1); t.dx = (int16_t)(s - 1);
+                if (L.kind == K_S1) { t.map = 0; t.c1 = (int8_t)(s - 1); t.c2 = (int8_t)(r - 1); }
+                else {
+                    // iy = 2*oy + dy: dy=-1 -> odd row oy-1; dy=0 -> even row oy; dy=+1 -> odd row oy
+                    const int py = (r == 1) ? 0 : 1, px = (s == 1) ? 0 : 1;
+                    t.map = (int8_t)(py * 2 + px);
+                    t.c2 = (int8_t)(r == 0 ? -1 : 0); t.c1 = (int8_t)(s == 0 ? -1 : 0);
+                }
+            }
+    }
+    g.out_cstride = L.out_c; g.out_coff = L.out_coff;
+    g.res_cstride = (L.res != NONE) ? (L.res == B_H1 ? 1024 : (L.res == B_F1 ? 256 : 64)) : 0;
+    g.res_coff = 0;
+    g.act = L.act;
+    g.round_tf32 = round_tf32 ? 1 : 0;
+}
+
+__global__ void round_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n) {
+    size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (; i < n; i += stride) dst[i] = ptx::to_tf32(src[i]);
+}
+
+int sync_stats(se3tn_ctx* c, cudaStream_t s) {
+    if (!c->stats_dirty) return SE3TN_OK;
+    int max_id = -1, f64 = -1;
+    for (auto& kv : c->weights) if (kv.second.has_stats) {
+        if (kv.first > max_id) max_id = kv.first;
+        if (f64 < 0) f64 = kv.second.stats_f64;
+        else if (f64 != kv.second.stats_f64) return fail(c, SE3TN_ERR_STATE, "all weight sets must use the same mean/std dtype");
+    }
+    if (max_id < 0) return fail(c, SE3TN_ERR_STATE, "se3tn_set_stats has not been called");
+    const int rows = max_id + 1;
+    if (rows > c->stats_rows) {
+        cudaFree(c->d_mean32); cudaFree(c->d_std32); cudaFree(c->d_mean64); cudaFree(c->d_std64);
+        CU_TRY(c, cudaMalloc(&c->d_mean32, rows * 8 * sizeof(float)));
+        CU_TRY(c, cudaMalloc(&c->d_std32, rows * 8 * sizeof(float)));
+        CU_TRY(c, cudaMalloc(&c->d_mean64, rows * 8 * sizeof(double)));
+        CU_TRY(c, cudaMalloc(&c->d_std64, rows * 8 * sizeof(double)));
+        c->stats_rows = rows;
+    }
+    std::vector<float> m32(rows * 8, 0.f), s32(rows * 8, 1.f);
+    std::vector<double> m64(rows * 8, 0.0), s64(rows * 8, 1.0);
+    for (auto& kv : c->weights) if (kv.second.has_stats && kv.first >= 0) {
+        memcpy(&m32[kv.first * 8], kv.second.mean32, sizeof(float) * 8); memcpy(&s32[kv.first * 8], kv.second.std32, sizeof(float) * 8);
+        memcpy(&m64[kv.first * 8], kv.second.mean64, sizeof(double) * 8); memcpy(&s64[kv.first * 8], kv.second.std64, sizeof(double) * 8);
+    }
+    // synchronous copies from stack-lifetime host vectors (rare: only when stats change)
+    CU_TRY(c, cudaStreamSynchronize(s));
+    CU_TRY(c, cudaMemcpy(c->d_mean32, m32.data(), rows * 8 * sizeof(float), cudaMemcpyHostToDevice));
+    CU_TRY(c, cudaMemcpy(c->d_std32, s32.data(), rows * 8 * sizeof(float), cudaMemcpyHostToDevice));
+    CU_TRY(c, cudaMemcpy(c->d_mean64, m64.data(), rows * 8 * sizeof(double), cudaMemcpyHostToDevice));
+    CU_TRY(c, cudaMemcpy(c->d_std64, s64.data(), rows * 8 * sizeof(double), cudaMemcpyHostToDevice));
+    c->stats_f64 = f64; c->stats_dirty = false;
+    return SE3TN_OK;
+}
+
+// The conv stack on images [first, first+n) of the context buffers.
+int run_network(se3tn_ctx* c, int weight_id, int first, int n, int precision,
+                float* out_trans, float* out_rot, float* out_feature, cudaStream_t s) {
+    auto it = c->weights.find(weight_id);
+    if (it == c->weights.end()) return fail(c, SE3TN_ERR_STATE, "weight set " + std::to_string(weight_id) + " not loaded");
+    const WeightSet& ws = it->second;
+    const bool tf32 = (precision == SE3TN_PREC_TF32);
+    if (!tf32 && precision != SE3TN_PREC_FP32) return fail(c, SE3TN_ERR_INVALID, "unknown precision");
+    const float* wbase = tf32 ? ws.dev_tf32 : ws.dev;
+
+    auto bufp = [&](Buf b) { return c->buf[b] + kBufFloats[b] * static_cast<size_t>(first); };
+    for (int li = 0; li < 14; ++li) {
+        const LayerSpec& L = kLayers[li];
+        ConvGeom g; fill_geom(L, n, tf32, g);
+        ConvPtrs p;
+        p.in = bufp(L.in); p.out = bufp(L.out); p.res = (L.res != NONE) ? bufp(L.res) : nullptr;
+        p.w = wbase + ws.w_off[li]; p.bias = ws.dev + ws.b_off[li];
+        if (tf32) {
+            UmmaMaps maps;
+            const int nmaps = (L.kind == K_STEM) ? 7 : (L.kind == K_S2 ? 4 : 1);
+            for (int m = 0; m < 7; ++m) maps.a[m] = c->amap[li][m < nmaps ? m : 0];
+            maps.b = ws.bmap[li];
+            UmmaTiling t;
+            tile_box(L, t.bw, t.bh, t.bn);
+            t.tiles_x = g.Wo / t.bw; t.tiles_y = g.Ho / t.bh;
+            const int BN = block_n_of(c, L);
+            t.n_tiles = L.cout / BN;
+            t.chunks_per_tap = L.cin / 32;
+            t.m_tiles = ((n + t.bn - 1) / t.bn) * t.tiles_x * t.tiles_y;
+            // The TMA maps address images absolutely (image 0 of the buffer), so this path works in
+            // absolute image indices: tiles start at image `first`, rows are valid below first + n.
+            t.img_first = first;
+            g.n_img = first + n;
+            p.out = c->buf[L.out]; p.res = (L.res != NONE) ? c->buf[L.res] : nullptr;
+            CU_TRY(c, launch_conv_umma(maps, g, t, p, BN, c->num_sms, s));
+        } else {
+            CU_TRY(c, launch_conv_direct(g, p, s));
+        }
+        ++c->launches;
+        if (li == 0) { CU_TRY(c, launch_maxpool(bufp(B_Y1A), bufp(B_P1A), n, 88, 88, 64, s)); ++c->launches; }
+        if (li == 1) { CU_TRY(c, launch_maxpool(bufp(B_Y1B), bufp(B_P1B), n, 88, 88, 64, s)); ++c->launches; }
+    }
+    CU_TRY(c, launch_head(bufp(B_H3), ws.dev + ws.fc_off, ws.dev + ws.fc_off + 6 * 512, out_trans, out_rot, n, 121, s));
+    ++c->launches;
+    if (out_feature) { CU_TRY(c, launch_nhwc_to_nchw(bufp(B_F2), out_feature, n, 22 * 22, 256, s)); ++c->launches; }
+    return SE3TN_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+size_t se3tn_workspace_bytes(int max_batch) {
+    if (max_batch <= 0) return 0;
+    return workspace_floats(max_batch) * sizeof(float);
+}
+
+const char* se3tn_last_error(se3tn_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int se3tn_create(int device, int max_batch, void* workspace, se3tn_ctx** out) {
+    if (!out || max_batch <= 0) return fail(nullptr, SE3TN_ERR_INVALID, "se3tn_create: bad arguments");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || device < 0 || device >= ndev)
+        return fail(nullptr, SE3TN_ERR_CUDA, std::string("se3tn_create: no such CUDA device: ") + cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    CU_TRY(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(nullptr, SE3TN_ERR_UNSUPPORTED, "se3tn_create: device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                                                    ", this library is sm_100a only (no fallback path)");
+    CU_TRY(nullptr, cudaSetDevice(device));
+    se3tn_ctx* c = new se3tn_ctx();
+    c->device = device; c->max_batch = max_batch; c->num_sms = prop.multiProcessorCount;
+    if (const char* ov = getenv("SE3TN_BLOCK_N")) c->umma_block_n_override = atoi(ov);
+
+    void* fn = nullptr; cudaDriverEntryPointQueryResult qres;
+    e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+        delete c; return fail(nullptr, SE3TN_ERR_CUDA, "se3tn_create: cuTensorMapEncodeTiled entry point unavailable");
+    }
+    c->encode = reinterpret_cast<EncodeTiledFn>(fn);
+
+    const size_t bytes = se3tn_workspace_bytes(max_batch);
+    if (workspace) {
+        if (reinterpret_cast<uintptr_t>(workspace) % 1024) { delete c; return fail(nullptr, SE3TN_ERR_INVALID, "se3tn_create: workspace must be 1024-byte aligned"); }
+        c->workspace = static_cast<uint8_t*>(workspace);
+    } else {
+        e = cudaMalloc(&c->workspace, bytes);
+        if (e != cudaSuccess) { delete c; return fail(nullptr, SE3TN_ERR_NOMEM, std::string("se3tn_create: cudaMalloc(workspace): ") + cudaGetErrorString(e)); }
+        c->own_workspace = true;
+    }
+    // zero once: the stem buffers' 3-pixel halo is the conv padding and is never written again
+    e = cudaMemset(c->workspace, 0, bytes);
+    if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); se3tn_destroy(c); return fail(nullptr, SE3TN_ERR_CUDA, "se3tn_create: cudaMemset: " + m); }
+    float* p = reinterpret_cast<float*>(c->workspace);
+    for (int b = 0; b < B_COUNT; ++b) {
+        c->buf[b] = p;
+        p += (kBufFloats[b] * static_cast<size_t>(max_batch) + 255) & ~size_t(255);
+    }
+    int rc = build_activation_maps(c);
+    if (rc) { g_create_error = c->err; se3tn_destroy(c); return rc; }
+    *out = c;
+    return SE3TN_OK;
+}
+
+void se3tn_destroy(se3tn_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (auto& kv : c->weights) { cudaFree(kv.second.dev); cudaFree(kv.second.dev_tf32); }
+    cudaFree(c->d_mean32); cudaFree(c->d_std32); cudaFree(c->d_mean64); cudaFree(c->d_std64);
+    if (c->own_workspace) cudaFree(c->workspace);
+    delete c;
+}
+
+int se3tn_load_weights(se3tn_ctx* c, int weight_id, const float* blob, size_t n_floats) {
+    if (!c) return SE3TN_ERR_INVALID;
+    if (!blob || weight_id < 0) return fail(c, SE3TN_ERR_INVALID, "se3tn_load_weights: bad arguments");
+    const size_t expect = blob_floats();
+    if (n_floats != expect || expect != SE3TN_WEIGHT_BLOB_FLOATS)
+        return fail(c, SE3TN_ERR_INVALID, "se3tn_load_weights: blob has " + std::to_string(n_floats) + " floats, expected " + std::to_string(expect));
+    CU_TRY(c, cudaSetDevice(c->device));
+    WeightSet& ws = c->weights[weight_id];
+    if (!ws.dev) {
+        CU_TRY(c, cudaMalloc(&ws.dev, expect * sizeof(float)));
+        CU_TRY(c, cudaMalloc(&ws.dev_tf32, expect * sizeof(float)));
+    }
+    CU_TRY(c, cudaDeviceSynchronize());
+    CU_TRY(c, cudaMemcpy(ws.dev, blob, expect * sizeof(float), cudaMemcpyHostToDevice));
+    round_tf32_kernel<<<1024, 256>>>(ws.dev, ws.dev_tf32, expect);
+    CU_TRY(c, cudaGetLastError());
+    CU_TRY(c, cudaDeviceSynchronize());
+    size_t off = 0;
+    for (int li = 0; li < 14; ++li) {
+        const LayerSpec& L = kLayers[li];
+        ws.w_off[li] = off; off += static_cast<size_t>(layer_rows(L)) * layer_ktot(L);
+        ws.b_off[li] = off; off += layer_rows(L);
+        char what[48]; snprintf(what, sizeof what, "layer %d weights", li);
+        int rc = make_map2(c, &ws.bmap[li], ws.dev_tf32 + ws.w_off[li], layer_ktot(L), layer_rows(L), block_n_of(c, L), what);
+        if (rc) return rc;
+    }
+    ws.fc_off = off;
+    return SE3TN_OK;
+}
+
+int se3tn_set_stats(se3tn_ctx* c, int weight_id, const void* mean8, const void* std8, int is_f64) {
+    if (!c) return SE3TN_ERR_INVALID;
+    if (!mean8 || !std8 || weight_id < 0) return fail(c, SE3TN_ERR_INVALID, "se3tn_set_stats: bad arguments");
+    WeightSet& ws = c->weights[weight_id];
+    for (int i = 0; i < 8; ++i) {
+        if (is_f64) {
+            ws.mean64[i] = static_cast<const double*>(mean8)[i]; ws.std64[i] = static_cast<const double*>(std8)[i];
+            ws.mean32[i] = static_cast<float>(ws.mean64[i]); ws.std32[i] = static_cast<float>(ws.std64[i]);
+        } else {
+            ws.mean32[i] = static_cast<const float*>(mean8)[i]; ws.std32[i] = static_cast<const float*>(std8)[i];
+            ws.mean64[i] = ws.mean32[i]; ws.std64[i] = ws.std32[i];
+        }
+    }
+    ws.stats_f64 = is_f64 ? 1 : 0; ws.has_stats = true;
+    c->stats_dirty = true;
+    return SE3TN_OK;
+}
+
+int se3tn_preprocess(se3tn_ctx* c, const uint8_t* frame_rgb, const uint16_t* frame_depth, int H, int W,
+                     const double* K, const double* poses, const double* object_width,
+                     const uint8_t* rgbA, const uint16_t* depthA, const int32_t* weight_ids, int n,
+                     int precision, float* out_A, float* out_B, uint8_t* crop_rgb, uint16_t* crop_depth, void* stream) {
+    if (!c) return SE3TN_ERR_INVALID;
+    if (!frame_rgb || !frame_depth || !K || !poses || !object_width || !rgbA || !depthA || H <= 0 || W <= 0)
+        return fail(c, SE3TN_ERR_INVALID, "se3tn_preprocess: null/invalid argument");
+    if (n < 0 || n > c->max_batch) return fail(c, SE3TN_ERR_INVALID, "se3tn_preprocess: n exceeds max_batch");
+    if ((out_A == nullptr) != (out_B == nullptr)) return fail(c, SE3TN_ERR_INVALID, "se3tn_preprocess: out_A/out_B must both be given or both NULL");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CU_TRY(c, cudaSetDevice(c->device));
+    int rc = sync_stats(c, s); if (rc) return rc;
+    PreprocessArgs a;
+    a.frame_rgb = frame_rgb; a.frame_depth = frame_depth; a.H = H; a.W = W;
+    a.fx = K[0]; a.fy = K[1]; a.cx = K[2]; a.cy = K[3];
+    a.poses = poses; a.object_width = object_width; a.rgbA = rgbA; a.depthA = depthA; a.weight_ids = weight_ids;
+    a.mean32 = c->d_mean32; a.std32 = c->d_std32; a.mean64 = c->d_mean64; a.std64 = c->d_std64;
+    a.stats_f64 = c->stats_f64; a.round_tf32 = (precision == SE3TN_PREC_TF32);
+    a.stemA = c->buf[B_X0A]; a.stemB = c->buf[B_X0B]; a.nchwA = out_A; a.nchwB = out_B;
+    a.crop_rgb = crop_rgb; a.crop_depth = crop_depth;
+    CU_TRY(c, launch_preprocess(a, n, s));
+    ++c->launches;
+    return SE3TN_OK;
+}
+
+int se3tn_forward(se3tn_ctx* c, int weight_id, const float* A, const float* B, int n,
+                  float* out_trans, float* out_rot, float* out_feature, int precision, void* stream) {
+    if (!c) return SE3TN_ERR_INVALID;
+    if (!A || !B || !out_trans || !out_rot) return fail(c, SE3TN_ERR_INVALID, "se3tn_forward: null argument");
+    if (n < 0 || n > c->max_batch) return fail(c, SE3TN_ERR_INVALID, "se3tn_forward: n exceeds max_batch");
+    if (n == 0) return SE3TN_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CU_TRY(c, cudaSetDevice(c->device));
+    c->launches = 0;
+    const int round = (precision == SE3TN_PREC_TF32);
+    CU_TRY(c, launch_nchw_to_stem(A, c->buf[B_X0A], n, round, s));
+    CU_TRY(c, launch_nchw_to_stem(B, c->buf[B_X0B], n, round, s));
+    c->launches += 2;
+    return run_network(c, weight_id, 0, n, precision, out_trans, out_rot, out_feature, s);
+}
+
+int se3tn_forward_preprocessed(se3tn_ctx* c, int weight_id, int first, int n,
+                               float* out_trans, float* out_rot, float* out_feature, int precision, void* stream) {
+    if (!c) return SE3TN_ERR_INVALID;
+    if (!out_trans || !out_rot) return fail(c, SE3TN_ERR_INVALID, "se3tn_forward_preprocessed: null argument");
+    if (first < 0 || n < 0 || first + n > c->max_batch) return fail(c, SE3TN_ERR_INVALID, "se3tn_forward_preprocessed: range exceeds max_batch");
+    if (n == 0) return SE3TN_OK;
+    CU_TRY(c, cudaSetDevice(c->device));
+    return run_network(c, weight_id, first, n, precision, out_trans, out_rot, out_feature, static_cast<cudaStream_t>(stream));
+}
+
+int se3tn_pose_update(se3tn_ctx* c, const double* poses_in, const float* trans, const float* rot,
+                      double tn, double rn, double* poses_out, int n, void* stream) {
+    if (!c) return SE3TN_ERR_INVALID;
+    if (!poses_in || !trans || !rot || !poses_out || n < 0) return fail(c, SE3TN_ERR_INVALID, "se3tn_pose_update: null/invalid argument");
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, launch_pose_update(poses_in, trans, rot, static_cast<float>(tn), static_cast<float>(rn), poses_out, n, static_cast<cudaStream_t>(stream)));
+    ++c->launches;
+    return SE3TN_OK;
+}
+
+int se3tn_so3_log(se3tn_ctx* c, const double* poses_a, const double* poses_b, double tn, double rn,
+                  double* trans_label, double* rot_label, int n, void* stream) {
+    if (!c) return SE3TN_ERR_INVALID;
+    if (!poses_a || !poses_b || !trans_label || !rot_label || n < 0) return fail(c, SE3TN_ERR_INVALID, "se3tn_so3_log: null/invalid argument");
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, launch_so3_log(poses_a, poses_b, tn, rn, trans_label, rot_label, n, static_cast<cudaStream_t>(stream)));
+    return SE3TN_OK;
+}
+
+int se3tn_track_batch(se3tn_ctx* c, const uint8_t* frame_rgb, const uint16_t* frame_depth, int H, int W,
+                      const double* K, const double* poses_in, const double* object_width,
+                      const uint8_t* rgbA, const uint16_t* depthA,
+                      const int32_t* weight_ids_host, const int32_t* weight_ids_dev, int n,
+                      double tn, double rn, int precision,
+                      float* out_trans, float* out_rot, double* poses_out, void* stream) {
+    if (!c) return SE3TN_ERR_INVALID;
+    if (!out_trans || !out_rot || !poses_out) return fail(c, SE3TN_ERR_INVALID, "se3tn_track_batch: null output");
+    if ((weight_ids_host == nullptr) != (weight_ids_dev == nullptr))
+        return fail(c, SE3TN_ERR_INVALID, "se3tn_track_batch: weight_ids_host and weight_ids_dev must both be given or both NULL");
+    c->launches = 0;
+    int rc = se3tn_preprocess(c, frame_rgb, frame_depth, H, W, K, poses_in, object_width, rgbA, depthA, weight_ids_dev, n,
+                              precision, nullptr, nullptr, nullptr, nullptr, stream);
+    if (rc) return rc;
+    int first = 0;
+    while (first < n) {
+        const int wid = weight_ids_host ? weight_ids_host[first] : 0;
+        int last = first + 1;
+        while (last < n && (weight_ids_host ? weight_ids_host[last] : 0) == wid) ++last;
+        rc = run_network(c, wid, first, last - first, precision, out_trans + first * 3, out_rot + first * 3, nullptr,
+                         static_cast<cudaStream_t>(stream));
+        if (rc) return rc;
+        first = last;
+    }
+    return se3tn_pose_update(c, poses_in, out_trans, out_rot, tn, rn, poses_out, n, stream);
+}
+
+int se3tn_debug_buffer(se3tn_ctx* c, int id, float** ptr, size_t* floats_per_image) {
+    if (!c) return SE3TN_ERR_INVALID;
+    if (id < 0 || id >= B_COUNT || !ptr || !floats_per_image) return fail(c, SE3TN_ERR_INVALID, "se3tn_debug_buffer: bad id");
+    *ptr = c->buf[id]; *floats_per_image = kBufFloats[id];
+    return SE3TN_OK;
+}
+
+int se3tn_last_launch_count(se3tn_ctx* c) { return c ? c->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,200 @@
+"""Engine: one libse3tn context bound to one CUDA device, driven with torch tensors.
+
+PyTorch is used here for device-memory ownership, the current stream and (in dist.py)
+torch.distributed -- all arithmetic happens inside libse3tn.so.  There is no CPU or eager
+fallback: without a CUDA device and the built library every call raises.
+"""
+import ctypes as C
+import numpy as np
+import torch
+
+from . import _lib
+from .weights import pack_state_dict
+
+PREC = {'tf32': _lib.PREC_TF32, 'fp32': _lib.PREC_FP32}
+IMAGE_SIZE = 176
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class Engine:
+    def __init__(self, max_batch=64, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError('se3tn Engine needs a CUDA device (sm_100a); there is no CPU fallback')
+        self.lib = _lib.load()
+        self.device = torch.device('cuda', torch.cuda.current_device() if device is None else
+                                   (device.index if isinstance(device, torch.device) else int(device)))
+        self.max_batch = int(max_batch)
+        nbytes = self.lib.se3tn_workspace_bytes(self.max_batch)
+        # caller-owned workspace: a torch allocation, so torch's allocator accounts for it
+        self._workspace = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)
+        base = self._workspace.data_ptr()
+        aligned = (base + 1023) // 1024 * 1024
+        ctx = C.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = self.lib.se3tn_create(self.device.index, self.max_batch, C.c_void_p(aligned), C.byref(ctx))
+        _lib.check(rc, None)
+        self._ctx = ctx
+        self._weight_ids = set()
+
+    def close(self):
+        if getattr(self, '_ctx', None):
+            torch.cuda.synchronize(self.device)
+            self.lib.se3tn_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ parameters
+    def load_state_dict(self, state_dict, weight_id=0):
+        blob = pack_state_dict(state_dict)
+        _lib.check(self.lib.se3tn_load_weights(self._ctx, int(weight_id), blob.ctypes.data_as(C.c_void_p), blob.size), self._ctx)
+        self._weight_ids.add(int(weight_id))
+
+    def set_stats(self, mean, std, weight_id=0):
+        mean = np.ascontiguousarray(mean); std = np.ascontiguousarray(std)
+        if mean.shape != (8,) or std.shape != (8,):
+            raise ValueError('mean/std must be 8-vectors (A channels then B channels)')
+        f64 = (mean.dtype == np.float64) or (std.dtype == np.float64)
+        dt = np.float64 if f64 else np.float32
+        mean = mean.astype(dt); std = std.astype(dt)
+        _lib.check(self.lib.se3tn_set_stats(self._ctx, int(weight_id), mean.ctypes.data_as(C.c_void_p),
+                                            std.ctypes.data_as(C.c_void_p), int(f64)), self._ctx)
+
+    # ------------------------------------------------------------------ hot path
+    def forward(self, A, B, weight_id=0, precision='tf32', want_feature=False):
+        """Se3TrackNet.forward on float32 (n,4,176,176) CUDA tensors -> (trans, rot, feature|None)."""
+        self._check_img(A); self._check_img(B)
+        n = A.shape[0]
+        if B.shape[0] != n:
+            raise ValueError('A and B batch sizes differ')
+        trans = torch.empty(n, 3, dtype=torch.float32, device=self.device)
+        rot = torch.empty(n, 3, dtype=torch.float32, device=self.device)
+        feat = torch.empty(n, 256, 22, 22, dtype=torch.float32, device=self.device) if want_feature else None
+        for i0 in range(0, n, self.max_batch):
+            i1 = min(n, i0 + self.max_batch)
+            _lib.check(self.lib.se3tn_forward(self._ctx, int(weight_id), _ptr(A[i0:i1]), _ptr(B[i0:i1]), i1 - i0,
+                                              _ptr(trans[i0:i1]), _ptr(rot[i0:i1]),
+                                              _ptr(feat[i0:i1]) if feat is not None else C.c_void_p(0),
+                                              PREC[precision], _stream(self.device)), self._ctx)
+        return trans, rot, feat
+
+    def preprocess(self, frame_rgb, frame_depth, K, poses, object_width, rgbA, depthA, weight_ids=None,
+                   precision='tf32', want_tensors=False, want_crops=False):
+        n = poses.shape[0]
+        self._check_frame(frame_rgb, frame_depth, rgbA, depthA, poses, object_width, n)
+        H, W = frame_depth.shape
+        Kh = self._k4(K)
+        outA = outB = crop_rgb = crop_depth = None
+        if want_tensors:
+            outA = torch.empty(n, 4, IMAGE_SIZE, IMAGE_SIZE, dtype=torch.float32, device=self.device)
+            outB = torch.empty_like(outA)
+        if want_crops:
+            crop_rgb = torch.empty(n, IMAGE_SIZE, IMAGE_SIZE, 3, dtype=torch.uint8, device=self.device)
+            crop_depth = torch.empty(n, IMAGE_SIZE, IMAGE_SIZE, dtype=torch.uint16, device=self.device)
+        _lib.check(self.lib.se3tn_preprocess(self._ctx, _ptr(frame_rgb), _ptr(frame_depth), H, W,
+                                             Kh.ctypes.data_as(C.c_void_p), _ptr(poses), _ptr(object_width),
+                                             _ptr(rgbA), _ptr(depthA), _ptr(weight_ids), n, PREC[precision],
+                                             _ptr(outA), _ptr(outB), _ptr(crop_rgb), _ptr(crop_depth),
+                                             _stream(self.device)), self._ctx)
+        return outA, outB, crop_rgb, crop_depth
+
+    def forward_preprocessed(self, n, weight_id=0, first=0, precision='tf32', want_feature=False):
+        trans = torch.empty(n, 3, dtype=torch.float32, device=self.device)
+        rot = torch.empty(n, 3, dtype=torch.float32, device=self.device)
+        feat = torch.empty(n, 256, 22, 22, dtype=torch.float32, device=self.device) if want_feature else None
+        _lib.check(self.lib.se3tn_forward_preprocessed(self._ctx, int(weight_id), int(first), n, _ptr(trans), _ptr(rot),
+                                                       _ptr(feat), PREC[precision], _stream(self.device)), self._ctx)
+        return trans, rot, feat
+
+    def pose_update(self, poses, trans, rot, trans_normalizer, rot_normalizer, out=None):
+        n = poses.shape[0]
+        if poses.dtype != torch.float64 or not poses.is_contiguous() or poses.shape[1:] != (4, 4):
+            raise ValueError('poses must be a contiguous float64 (n,4,4) CUDA tensor')
+        out = torch.empty_like(poses) if out is None else out
+        _lib.check(self.lib.se3tn_pose_update(self._ctx, _ptr(poses), _ptr(trans), _ptr(rot), float(trans_normalizer),
+                                              float(rot_normalizer), _ptr(out), n, _stream(self.device)), self._ctx)
+        return out
+
+    def so3_log(self, poses_a, poses_b, trans_normalizer, rot_normalizer):
+        n = poses_a.shape[0]
+        tl = torch.empty(n, 3, dtype=torch.float64, device=self.device)
+        rl = torch.empty(n, 3, dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.se3tn_so3_log(self._ctx, _ptr(poses_a), _ptr(poses_b), float(trans_normalizer),
+                                          float(rot_normalizer), _ptr(tl), _ptr(rl), n, _stream(self.device)), self._ctx)
+        return tl, rl
+
+    def track_batch(self, frame_rgb, frame_depth, K, poses, object_width, rgbA, depthA,
+                    trans_normalizer, rot_normalizer, weight_ids_host=None, weight_ids_dev=None,
+                    precision='tf32', out_poses=None, out_trans=None, out_rot=None):
+        """n independent tracks of one frame: K0 -> conv stack -> K6, all enqueued on the current stream."""
+        n = poses.shape[0]
+        self._check_frame(frame_rgb, frame_depth, rgbA, depthA, poses, object_width, n)
+        H, W = frame_depth.shape
+        Kh = self._k4(K)
+        out_poses = torch.empty_like(poses) if out_poses is None else out_poses
+        out_trans = torch.empty(n, 3, dtype=torch.float32, device=self.device) if out_trans is None else out_trans
+        out_rot = torch.empty(n, 3, dtype=torch.float32, device=self.device) if out_rot is None else out_rot
+        wh = None
+        if weight_ids_host is not None:
+            wh = np.ascontiguousarray(weight_ids_host, dtype=np.int32)
+            if weight_ids_dev is None:
+                weight_ids_dev = torch.from_numpy(wh).to(self.device)
+        _lib.check(self.lib.se3tn_track_batch(self._ctx, _ptr(frame_rgb), _ptr(frame_depth), H, W,
+                                              Kh.ctypes.data_as(C.c_void_p), _ptr(poses), _ptr(object_width),
+                                              _ptr(rgbA), _ptr(depthA),
+                                              wh.ctypes.data_as(C.c_void_p) if wh is not None else C.c_void_p(0),
+                                              _ptr(weight_ids_dev), n, float(trans_normalizer), float(rot_normalizer),
+                                              PREC[precision], _ptr(out_trans), _ptr(out_rot), _ptr(out_poses),
+                                              _stream(self.device)), self._ctx)
+        return out_poses, out_trans, out_rot
+
+    # ------------------------------------------------------------------ introspection
+    def debug_buffer(self, buf_id, n):
+        """A float32 view (n, floats_per_image) of an internal NHWC activation buffer."""
+        p = C.c_void_p(); fpi = C.c_size_t()
+        _lib.check(self.lib.se3tn_debug_buffer(self._ctx, buf_id, C.byref(p), C.byref(fpi)), self._ctx)
+        offb = p.value - self._workspace.data_ptr()
+        nbytes = n * fpi.value * 4
+        return self._workspace[offb:offb + nbytes].view(torch.float32).view(n, fpi.value)
+
+    def last_launch_count(self):
+        return self.lib.se3tn_last_launch_count(self._ctx)
+
+    # ------------------------------------------------------------------ checks
+    def _check_img(self, t):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.dim() == 4 and
+                tuple(t.shape[1:]) == (4, IMAGE_SIZE, IMAGE_SIZE)):
+            raise ValueError('expected a contiguous float32 CUDA tensor of shape (n,4,176,176), got %s %s' % (t.dtype, tuple(t.shape)))
+
+    def _check_frame(self, rgb, depth, rgbA, depthA, poses, ow, n):
+        ok = (rgb.is_cuda and rgb.dtype == torch.uint8 and rgb.is_contiguous() and rgb.dim() == 3 and rgb.shape[2] == 3 and
+              depth.is_cuda and depth.dtype == torch.uint16 and depth.is_contiguous() and depth.shape == rgb.shape[:2] and
+              rgbA.is_cuda and rgbA.dtype == torch.uint8 and rgbA.is_contiguous() and tuple(rgbA.shape) == (n, IMAGE_SIZE, IMAGE_SIZE, 3) and
+              depthA.is_cuda and depthA.dtype == torch.uint16 and depthA.is_contiguous() and tuple(depthA.shape) == (n, IMAGE_SIZE, IMAGE_SIZE) and
+              poses.is_cuda and poses.dtype == torch.float64 and poses.is_contiguous() and tuple(poses.shape) == (n, 4, 4) and
+              ow.is_cuda and ow.dtype == torch.float64 and ow.is_contiguous() and tuple(ow.shape) == (n,))
+        if not ok:
+            raise ValueError('bad frame/pose tensors: need uint8 (H,W,3), uint16 (H,W), uint8 (n,176,176,3), uint16 (n,176,176), '
+                             'float64 (n,4,4), float64 (n,), all contiguous CUDA tensors')
+        if n > self.max_batch:
+            raise ValueError('n=%d exceeds max_batch=%d' % (n, self.max_batch))
+
+    @staticmethod
+    def _k4(K):
+        K = np.asarray(K, dtype=np.float64)
+        if K.shape == (3, 3):
+            return np.ascontiguousarray([K[0, 0], K[1, 1], K[0, 2], K[1, 2]], dtype=np.float64)
+        if K.shape == (4,):
+            return np.ascontiguousarray(K)
+        raise ValueError('K must be 3x3 or (fx,fy,cx,cy)')
