@@ -95,6 +95,26 @@ int se3tn_preprocess(se3tn_ctx* ctx, const uint8_t* frame_rgb, const uint16_t* f
                      int precision, float* out_A, float* out_B, uint8_t* crop_rgb, uint16_t* crop_depth,
                      void* stream);
 
+/* The post-transform half of TrackDataset.processData (reference datasets.py:136-137 ->
+ * data_augmentation.py:124-196) on crops that already exist: rgbA/rgbB uint8 (n,176,176,3),
+ * depthA/depthB uint16 (n,176,176), poses double (n,16) (A's pose: both depths are offset by its z).
+ * out_A/out_B float32 (n,4,176,176) or both NULL; the conv-input buffers are filled either way. */
+int se3tn_normalize(se3tn_ctx* ctx, const uint8_t* rgbA, const uint16_t* depthA,
+                    const uint8_t* rgbB, const uint16_t* depthB, const double* poses,
+                    const int32_t* weight_ids, int n, int precision, float* out_A, float* out_B, void* stream);
+
+/* compute_bbox (reference Utils.py:302-316): out_bbox int32 (n,4,2), rows (x-,y-),(x-,y+),(x+,y-),(x+,y+),
+ * columns (v,u).  K: 4 doubles HOST fx,fy,cx,cy; scale: 3 doubles HOST (the reference passes
+ * (1000,1000,1000), or (1000,-1000,1000) for its GL renderer, predict.py:202,232). */
+int se3tn_compute_bbox(se3tn_ctx* ctx, const double* poses, const double* K, const double* widths,
+                       const double* scale, int32_t* out_bbox, int n, void* stream);
+
+/* crop_bbox (reference Utils.py:320-359): zero-padded window [min v, max v) x [min u, max u) of the
+ * frame, cv2.INTER_NEAREST-resized to (out_h, out_w).  bbox int32 (n,4,2) device. */
+int se3tn_crop_bbox(se3tn_ctx* ctx, const uint8_t* frame_rgb, const uint16_t* frame_depth, int H, int W,
+                    const int32_t* bbox, int n, int out_h, int out_w,
+                    uint8_t* crop_rgb, uint16_t* crop_depth, void* stream);
+
 /* Se3TrackNet.forward (reference se3_tracknet.py:81-112).  A, B: float32 (n,4,176,176) contiguous
  * NCHW device tensors.  out_trans/out_rot: float32 (n,3).  out_feature: float32 (n,256,22,22) or
  * NULL.  All n pairs use weight set `weight_id`. */

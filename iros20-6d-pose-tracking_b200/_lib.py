@@ -20,6 +20,9 @@ SIGNATURES = {
     'se3tn_load_weights': (_i, [_vp, _i, _vp, _sz]),
     'se3tn_set_stats': (_i, [_vp, _i, _vp, _vp, _i]),
     'se3tn_preprocess': (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    'se3tn_normalize': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    'se3tn_compute_bbox': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    'se3tn_crop_bbox': (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
     'se3tn_forward': (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp]),
     'se3tn_forward_preprocessed': (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),
     'se3tn_pose_update': (_i, [_vp, _vp, _vp, _vp, _d, _d, _vp, _i, _vp]),

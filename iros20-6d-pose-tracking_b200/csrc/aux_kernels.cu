@@ -26,16 +26,17 @@ __device__ __forceinline__ void bbox_window(const double* pose, double fx, doubl
                                             double width, double sx, double sy, double sz,
                                             int& top, int& left, int& ch, int& cw)
 {
-    const double ox = pose[3] * sx, oy = pose[7] * sy, oz = pose[11] * sz;
+    const double ox = __dmul_rn(pose[3], sx), oy = __dmul_rn(pose[7], sy), oz = __dmul_rn(pose[11], sz);
     const double half = width / 2;
     // u for x-half / x+half, v for y-half / y+half (the 4 corners share these two values each)
-    const double u0 = rint(__dadd_rn(__ddiv_rn(__dmul_rn(oz == oz ? (ox - half) : 0.0, fx), oz), cx));
+    const double u0 = rint(__dadd_rn(__ddiv_rn(__dmul_rn(ox - half, fx), oz), cx));
     const double u1 = rint(__dadd_rn(__ddiv_rn(__dmul_rn(ox + half, fx), oz), cx));
     const double v0 = rint(__dadd_rn(__ddiv_rn(__dmul_rn(oy - half, fy), oz), cy));
     const double v1 = rint(__dadd_rn(__ddiv_rn(__dmul_rn(oy + half, fy), oz), cy));
     const double umin = fmin(u0, u1), umax = fmax(u0, u1), vmin = fmin(v0, v1), vmax = fmax(v0, v1);
     // clamp to int range so degenerate poses (z ~ 0) cannot overflow
     const double lim = 1.0e9;
+    if (!(umin == umin && umax == umax && vmin == vmin && vmax == vmax)) { top = left = 0; ch = cw = 0; return; }
     left = static_cast<int>(fmax(-lim, fmin(lim, umin)));
     top = static_cast<int>(fmax(-lim, fmin(lim, vmin)));
     cw = static_cast<int>(fmax(-lim, fmin(lim, umax))) - left;
@@ -63,21 +64,29 @@ preprocess_kernel(PreprocessArgs a)
     const double z1000 = __dmul_rn(z, 1000.0);
 
     // ---- B: observed frame crop --------------------------------------------------------------
-    int top, left, ch, cw;
-    bbox_window(pose, a.fx, a.fy, a.cx, a.cy, a.object_width[n], 1000.0, 1000.0, 1000.0, top, left, ch, cw);
     unsigned r = 0, gch = 0, b = 0, d = 0;
-    if (ch > 0 && cw > 0) {
-        // cv2 resizeNN index: floor(dst * ifx), ifx = 1/(dsize/ssize) in double, clamped to ssize-1
-        const double ifx = 1.0 / (static_cast<double>(kImg) / cw);
-        const double ify = 1.0 / (static_cast<double>(kImg) / ch);
-        int sx = static_cast<int>(floor(x * ifx)); if (sx > cw - 1) sx = cw - 1;
-        int sy = static_cast<int>(floor(y * ify)); if (sy > ch - 1) sy = ch - 1;
-        const int fy_ = top + sy, fx_ = left + sx;
-        if (fy_ >= 0 && fy_ < a.H && fx_ >= 0 && fx_ < a.W) {
-            const size_t fo = static_cast<size_t>(fy_) * a.W + fx_;
-            const uint8_t* pr = a.frame_rgb + fo * 3;
-            r = pr[0]; gch = pr[1]; b = pr[2];
-            d = a.frame_depth[fo];
+    if (a.b_precropped) {
+        // frame_rgb / frame_depth already hold n 176x176 crops (TrackDataset.processData's inputs)
+        const size_t bo = static_cast<size_t>(n) * kImg * kImg + pix;
+        const uint8_t* pr = a.frame_rgb + bo * 3;
+        r = pr[0]; gch = pr[1]; b = pr[2];
+        d = a.frame_depth[bo];
+    } else {
+        int top, left, ch, cw;
+        bbox_window(pose, a.fx, a.fy, a.cx, a.cy, a.object_width[n], 1000.0, 1000.0, 1000.0, top, left, ch, cw);
+        if (ch > 0 && cw > 0) {
+            // cv2 resizeNN index: floor(dst * ifx), ifx = 1/(dsize/ssize) in double, clamped to ssize-1
+            const double ifx = 1.0 / (static_cast<double>(kImg) / cw);
+            const double ify = 1.0 / (static_cast<double>(kImg) / ch);
+            int sx = static_cast<int>(floor(x * ifx)); if (sx > cw - 1) sx = cw - 1;
+            int sy = static_cast<int>(floor(y * ify)); if (sy > ch - 1) sy = ch - 1;
+            const int fy_ = top + sy, fx_ = left + sx;
+            if (fy_ >= 0 && fy_ < a.H && fx_ >= 0 && fx_ < a.W) {
+                const size_t fo = static_cast<size_t>(fy_) * a.W + fx_;
+                const uint8_t* pr = a.frame_rgb + fo * 3;
+                r = pr[0]; gch = pr[1]; b = pr[2];
+                d = a.frame_depth[fo];
+            }
         }
     }
     if (a.crop_rgb) {
@@ -124,6 +133,75 @@ cudaError_t launch_preprocess(const PreprocessArgs& a, int n, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
     dim3 grid((kImg * kImg + 255) / 256, n);
     preprocess_kernel<<<grid, 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+// =============================================================================================
+// Stand-alone compute_bbox / crop_bbox (reference Utils.py:302-316, 320-359) for the drop-in
+// Utils API: the same arithmetic as inside preprocess_kernel, with the bbox made visible.
+// =============================================================================================
+__global__ void bbox_kernel(const double* __restrict__ poses, double fx, double fy, double cx, double cy,
+                            const double* __restrict__ widths, double sx, double sy, double sz,
+                            int* __restrict__ out /* (n,4,2) rows (x-,y-),(x-,y+),(x+,y-),(x+,y+), cols (v,u) */, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* pose = poses + i * 16;
+    const double ox = __dmul_rn(pose[3], sx), oy = __dmul_rn(pose[7], sy), oz = __dmul_rn(pose[11], sz);
+    const double half = widths[i] / 2;
+    const double lim = 2.0e9;
+    auto proj = [&](double v, double f, double c) {
+        const double p = rint(__dadd_rn(__ddiv_rn(__dmul_rn(v, f), oz), c));
+        return static_cast<int>(fmax(-lim, fmin(lim, p == p ? p : 0.0)));
+    };
+    const int u0 = proj(ox - half, fx, cx), u1 = proj(ox + half, fx, cx);
+    const int v0 = proj(oy - half, fy, cy), v1 = proj(oy + half, fy, cy);
+    int* o = out + i * 8;
+    o[0] = v0; o[1] = u0; o[2] = v1; o[3] = u0; o[4] = v0; o[5] = u1; o[6] = v1; o[7] = u1;
+}
+
+cudaError_t launch_bbox(const double* poses, const double* K4, const double* widths, const double* scale3,
+                        int* out, int n, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    bbox_kernel<<<(n + 127) / 128, 128, 0, s>>>(poses, K4[0], K4[1], K4[2], K4[3], widths, scale3[0], scale3[1], scale3[2], out, n);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256)
+crop_kernel(const uint8_t* __restrict__ frame_rgb, const uint16_t* __restrict__ frame_depth, int H, int W,
+            const int* __restrict__ bbox, int out_h, int out_w, uint8_t* __restrict__ crop_rgb, uint16_t* __restrict__ crop_depth)
+{
+    const int n = blockIdx.y;
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= out_h * out_w) return;
+    const int y = pix / out_w, x = pix - y * out_w;
+    const int* bb = bbox + n * 8;
+    const int top = min(min(bb[0], bb[2]), min(bb[4], bb[6])), bottom = max(max(bb[0], bb[2]), max(bb[4], bb[6]));
+    const int left = min(min(bb[1], bb[3]), min(bb[5], bb[7])), right = max(max(bb[1], bb[3]), max(bb[5], bb[7]));
+    const int ch = bottom - top, cw = right - left;
+    unsigned r = 0, g = 0, b = 0, d = 0;
+    if (ch > 0 && cw > 0) {
+        const double ifx = 1.0 / (static_cast<double>(out_w) / cw);
+        const double ify = 1.0 / (static_cast<double>(out_h) / ch);
+        int sx = static_cast<int>(floor(x * ifx)); if (sx > cw - 1) sx = cw - 1;
+        int sy = static_cast<int>(floor(y * ify)); if (sy > ch - 1) sy = ch - 1;
+        const int fy_ = top + sy, fx_ = left + sx;
+        if (fy_ >= 0 && fy_ < H && fx_ >= 0 && fx_ < W) {
+            const size_t fo = static_cast<size_t>(fy_) * W + fx_;
+            r = frame_rgb[fo * 3]; g = frame_rgb[fo * 3 + 1]; b = frame_rgb[fo * 3 + 2];
+            d = frame_depth[fo];
+        }
+    }
+    const size_t o = static_cast<size_t>(n) * out_h * out_w + pix;
+    crop_rgb[o * 3] = r; crop_rgb[o * 3 + 1] = g; crop_rgb[o * 3 + 2] = b;
+    crop_depth[o] = static_cast<uint16_t>(d);
+}
+
+cudaError_t launch_crop(const uint8_t* frame_rgb, const uint16_t* frame_depth, int H, int W, const int* bbox, int n,
+                        int out_h, int out_w, uint8_t* crop_rgb, uint16_t* crop_depth, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    dim3 grid((out_h * out_w + 255) / 256, n);
+    crop_kernel<<<grid, 256, 0, s>>>(frame_rgb, frame_depth, H, W, bbox, out_h, out_w, crop_rgb, crop_depth);
     return cudaGetLastError();
 }
 
@@ -281,9 +359,11 @@ __device__ __forceinline__ void rodrigues_exp_f32in(float rx32, float ry32, floa
     }
     const double c = cos(theta), s = sin(theta), c1 = 1.0 - c, it = 1.0 / theta;
     rx *= it; ry *= it; rz *= it;
-    R[0] = c + c1 * rx * rx;      R[1] = c1 * rx * ry - s * rz; R[2] = c1 * rx * rz + s * ry;
-    R[3] = c1 * rx * ry + s * rz; R[4] = c + c1 * ry * ry;      R[5] = c1 * ry * rz - s * rx;
-    R[6] = c1 * rx * rz - s * ry; R[7] = c1 * ry * rz + s * rx; R[8] = c + c1 * rz * rz;
+    // same association as cv::Matx: c*I + c1*(r r^T) + s*[r]x, outer products formed first
+    const double xx = rx * rx, xy = rx * ry, xz = rx * rz, yy = ry * ry, yz = ry * rz, zz = rz * rz;
+    R[0] = c + c1 * xx;      R[1] = c1 * xy - s * rz; R[2] = c1 * xz + s * ry;
+    R[3] = c1 * xy + s * rz; R[4] = c + c1 * yy;      R[5] = c1 * yz - s * rx;
+    R[6] = c1 * xz - s * ry; R[7] = c1 * yz + s * rx; R[8] = c + c1 * zz;
     if (round_f32)
 #pragma unroll
         for (int i = 0; i < 9; ++i) R[i] = static_cast<double>(static_cast<float>(R[i]));

@@ -24,6 +24,7 @@ struct PreprocessArgs {
     const double* mean64; const double* std64;    // [sets][8] when stats_f64
     int stats_f64;
     int round_tf32;
+    int b_precropped;              // frame_rgb/frame_depth are n ready-made 176x176 crops (processData inputs)
     float* stemA; float* stemB;    // N x 182 x 184 x 4 (nullable)
     float* nchwA; float* nchwB;    // N x 4 x 176 x 176 (nullable)
     uint8_t* crop_rgb;             // N x 176 x 176 x 3 (nullable)
@@ -31,6 +32,10 @@ struct PreprocessArgs {
 };
 
 cudaError_t launch_preprocess(const PreprocessArgs& a, int n, cudaStream_t s);
+cudaError_t launch_bbox(const double* poses, const double* K4, const double* widths, const double* scale3,
+                        int* out, int n, cudaStream_t s);
+cudaError_t launch_crop(const uint8_t* frame_rgb, const uint16_t* frame_depth, int H, int W, const int* bbox, int n,
+                        int out_h, int out_w, uint8_t* crop_rgb, uint16_t* crop_depth, cudaStream_t s);
 cudaError_t launch_nchw_to_stem(const float* src, float* dst, int n, int round_tf32, cudaStream_t s);
 cudaError_t launch_maxpool(const float* in, float* out, int n_img, int Hin, int Win, int C, cudaStream_t s);
 cudaError_t launch_head(const float* x, const float* fcw, const float* fcb, float* out_trans, float* out_rot,

@@ -479,11 +479,51 @@ int se3tn_preprocess(se3tn_ctx* c, const uint8_t* frame_rgb, const uint16_t* fra
     a.fx = K[0]; a.fy = K[1]; a.cx = K[2]; a.cy = K[3];
     a.poses = poses; a.object_width = object_width; a.rgbA = rgbA; a.depthA = depthA; a.weight_ids = weight_ids;
     a.mean32 = c->d_mean32; a.std32 = c->d_std32; a.mean64 = c->d_mean64; a.std64 = c->d_std64;
-    a.stats_f64 = c->stats_f64; a.round_tf32 = (precision == SE3TN_PREC_TF32);
+    a.stats_f64 = c->stats_f64; a.round_tf32 = (precision == SE3TN_PREC_TF32); a.b_precropped = 0;
     a.stemA = c->buf[B_X0A]; a.stemB = c->buf[B_X0B]; a.nchwA = out_A; a.nchwB = out_B;
     a.crop_rgb = crop_rgb; a.crop_depth = crop_depth;
     CU_TRY(c, launch_preprocess(a, n, s));
     ++c->launches;
+    return SE3TN_OK;
+}
+
+int se3tn_normalize(se3tn_ctx* c, const uint8_t* rgbA, const uint16_t* depthA, const uint8_t* rgbB, const uint16_t* depthB,
+                    const double* poses, const int32_t* weight_ids, int n, int precision, float* out_A, float* out_B, void* stream) {
+    if (!c) return SE3TN_ERR_INVALID;
+    if (!rgbA || !depthA || !rgbB || !depthB || !poses) return fail(c, SE3TN_ERR_INVALID, "se3tn_normalize: null argument");
+    if (n < 0 || n > c->max_batch) return fail(c, SE3TN_ERR_INVALID, "se3tn_normalize: n exceeds max_batch");
+    if ((out_A == nullptr) != (out_B == nullptr)) return fail(c, SE3TN_ERR_INVALID, "se3tn_normalize: out_A/out_B must both be given or both NULL");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CU_TRY(c, cudaSetDevice(c->device));
+    int rc = sync_stats(c, s); if (rc) return rc;
+    PreprocessArgs a;
+    memset(&a, 0, sizeof a);
+    a.frame_rgb = rgbB; a.frame_depth = depthB; a.H = kImg; a.W = kImg; a.b_precropped = 1;
+    a.poses = poses; a.rgbA = rgbA; a.depthA = depthA; a.weight_ids = weight_ids;
+    a.mean32 = c->d_mean32; a.std32 = c->d_std32; a.mean64 = c->d_mean64; a.std64 = c->d_std64;
+    a.stats_f64 = c->stats_f64; a.round_tf32 = (precision == SE3TN_PREC_TF32);
+    a.stemA = c->buf[B_X0A]; a.stemB = c->buf[B_X0B]; a.nchwA = out_A; a.nchwB = out_B;
+    CU_TRY(c, launch_preprocess(a, n, s));
+    ++c->launches;
+    return SE3TN_OK;
+}
+
+int se3tn_compute_bbox(se3tn_ctx* c, const double* poses, const double* K, const double* widths, const double* scale,
+                       int32_t* out_bbox, int n, void* stream) {
+    if (!c) return SE3TN_ERR_INVALID;
+    if (!poses || !K || !widths || !scale || !out_bbox || n < 0) return fail(c, SE3TN_ERR_INVALID, "se3tn_compute_bbox: null/invalid argument");
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, launch_bbox(poses, K, widths, scale, out_bbox, n, static_cast<cudaStream_t>(stream)));
+    return SE3TN_OK;
+}
+
+int se3tn_crop_bbox(se3tn_ctx* c, const uint8_t* frame_rgb, const uint16_t* frame_depth, int H, int W, const int32_t* bbox, int n,
+                    int out_h, int out_w, uint8_t* crop_rgb, uint16_t* crop_depth, void* stream) {
+    if (!c) return SE3TN_ERR_INVALID;
+    if (!frame_rgb || !frame_depth || !bbox || !crop_rgb || !crop_depth || H <= 0 || W <= 0 || out_h <= 0 || out_w <= 0 || n < 0)
+        return fail(c, SE3TN_ERR_INVALID, "se3tn_crop_bbox: null/invalid argument");
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, launch_crop(frame_rgb, frame_depth, H, W, bbox, n, out_h, out_w, crop_rgb, crop_depth, static_cast<cudaStream_t>(stream)));
     return SE3TN_OK;
 }
 

@@ -109,6 +109,36 @@ class Engine:
                                              _stream(self.device)), self._ctx)
         return outA, outB, crop_rgb, crop_depth
 
+    def normalize(self, rgbA, depthA, rgbB, depthB, poses, weight_ids=None, precision='tf32', want_tensors=True):
+        """processData's post-transforms on existing 176x176 crops (all CUDA tensors)."""
+        n = poses.shape[0]
+        outA = outB = None
+        if want_tensors:
+            outA = torch.empty(n, 4, IMAGE_SIZE, IMAGE_SIZE, dtype=torch.float32, device=self.device)
+            outB = torch.empty_like(outA)
+        _lib.check(self.lib.se3tn_normalize(self._ctx, _ptr(rgbA), _ptr(depthA), _ptr(rgbB), _ptr(depthB), _ptr(poses),
+                                            _ptr(weight_ids), n, PREC[precision], _ptr(outA), _ptr(outB),
+                                            _stream(self.device)), self._ctx)
+        return outA, outB
+
+    def compute_bbox(self, poses, K, widths, scale=(1000., 1000., 1000.)):
+        n = poses.shape[0]
+        out = torch.empty(n, 4, 2, dtype=torch.int32, device=self.device)
+        Kh = self._k4(K); sc = np.ascontiguousarray(scale, dtype=np.float64)
+        _lib.check(self.lib.se3tn_compute_bbox(self._ctx, _ptr(poses), Kh.ctypes.data_as(C.c_void_p), _ptr(widths),
+                                               sc.ctypes.data_as(C.c_void_p), _ptr(out), n, _stream(self.device)), self._ctx)
+        return out
+
+    def crop_bbox(self, frame_rgb, frame_depth, bbox, out_hw=(IMAGE_SIZE, IMAGE_SIZE)):
+        n = bbox.shape[0]
+        H, W = frame_depth.shape
+        crop_rgb = torch.empty(n, out_hw[0], out_hw[1], 3, dtype=torch.uint8, device=self.device)
+        crop_depth = torch.empty(n, out_hw[0], out_hw[1], dtype=torch.uint16, device=self.device)
+        _lib.check(self.lib.se3tn_crop_bbox(self._ctx, _ptr(frame_rgb), _ptr(frame_depth), H, W, _ptr(bbox), n,
+                                            int(out_hw[0]), int(out_hw[1]), _ptr(crop_rgb), _ptr(crop_depth),
+                                            _stream(self.device)), self._ctx)
+        return crop_rgb, crop_depth
+
     def forward_preprocessed(self, n, weight_id=0, first=0, precision='tf32', want_feature=False):
         trans = torch.empty(n, 3, dtype=torch.float32, device=self.device)
         rot = torch.empty(n, 3, dtype=torch.float32, device=self.device)

@@ -1,0 +1,220 @@
+"""Drop-in for the Tracker of the reference's predict.py (reference predict.py:127-296): same
+constructor, attributes and on_track signature, so the reference's sequence drivers
+(predict.py:299-624) and predict_ros.py:59 can call it unchanged -- with the per-frame work
+(crop, depth clip, normalise, 17-conv network, pose update) running as one stream of libse3tn
+kernels instead of numpy + torch.nn.
+
+Differences, all additive:
+  * on_track(..., rgbA=None, depthA=None): the rendered previous view may be passed in.  The
+    OpenGL renderers (vispy_renderer.py / offscreen_renderer.py) are out of scope; when they are
+    importable the Tracker uses them exactly as the reference does, otherwise rgbA/depthA (or a
+    `renderer=` object with render_window(ob2cam)) must be supplied.
+  * the second, visualisation-only render + cv2.imshow (predict.py:284-290) only happens with
+    show=True.
+  * on_track_batch(): N independent tracks of one frame in one batched launch sequence (the
+    reference is batch 1, F15).
+"""
+import os
+import numpy as np
+import torch
+
+from .engine import Engine
+from .se3_tracknet import Se3TrackNet
+from .datasets import TrackDataset
+from . import Utils as U
+
+
+class PointCloud:
+    """Minimal stand-in for the open3d point cloud the reference keeps in Tracker.object_cloud
+    (predict.py:131-133): callers only read `.points`."""
+    def __init__(self, points):
+        self.points = np.asarray(points, dtype=np.float64)
+
+    def voxel_down_sample(self, voxel_size):
+        # open3d semantics: points are bucketed on a grid anchored at (min_bound - voxel/2) and each
+        # occupied voxel is replaced by the mean of its points
+        pts = self.points
+        origin = pts.min(0) - voxel_size * 0.5
+        keys = np.floor((pts - origin) / voxel_size).astype(np.int64)
+        _, inv = np.unique(keys, axis=0, return_inverse=True)
+        inv = inv.reshape(-1)
+        sums = np.zeros((inv.max() + 1, 3)); np.add.at(sums, inv, pts)
+        cnt = np.bincount(inv).astype(np.float64)[:, None]
+        return PointCloud(sums / cnt)
+
+
+def load_vertices(model_path):
+    """Vertices of a .ply (ascii / binary little endian) or .obj mesh (trimesh.load(..).vertices in
+    the reference, predict.py:131)."""
+    ext = os.path.splitext(model_path)[1].lower()
+    if ext == '.obj':
+        v = [list(map(float, l.split()[1:4])) for l in open(model_path) if l.startswith('v ')]
+        return np.asarray(v, dtype=np.float64)
+    if ext != '.ply':
+        raise ValueError('unsupported mesh format: ' + model_path)
+    with open(model_path, 'rb') as f:
+        fmt, nvert, props, in_vertex = None, 0, [], False
+        while True:
+            line = f.readline().decode('ascii', 'replace').strip()
+            if line.startswith('format'):
+                fmt = line.split()[1]
+            elif line.startswith('element'):
+                in_vertex = line.split()[1] == 'vertex'
+                if in_vertex:
+                    nvert = int(line.split()[2])
+            elif line.startswith('property') and in_vertex:
+                props.append((line.split()[1], line.split()[-1]))
+            elif line == 'end_header':
+                break
+        names = [p[1] for p in props]
+        ix = [names.index(a) for a in 'xyz']
+        if fmt == 'ascii':
+            data = np.loadtxt(f, max_rows=nvert, ndmin=2)
+            return data[:, ix].astype(np.float64)
+        np_t = {'float': '<f4', 'float32': '<f4', 'double': '<f8', 'float64': '<f8', 'uchar': 'u1', 'uint8': 'u1',
+                'char': 'i1', 'int': '<i4', 'int32': '<i4', 'uint': '<u4', 'short': '<i2', 'ushort': '<u2'}
+        dt = np.dtype([(n, np_t[t]) for t, n in props])
+        data = np.frombuffer(f.read(dt.itemsize * nvert), dtype=dt, count=nvert)
+        return np.stack([data['x'], data['y'], data['z']], 1).astype(np.float64)
+
+
+def compute_obj_max_width(points):
+    """Convex-hull diameter in mm (reference Utils.py:101-105, 450-451)."""
+    from scipy.spatial import ConvexHull, distance_matrix
+    hull = points[ConvexHull(points).vertices]
+    return float(np.max(distance_matrix(hull, hull))) * 1000
+
+
+def _as_numpy_pose(p):
+    return np.ascontiguousarray(p, dtype=np.float64)
+
+
+class Tracker:
+    def __init__(self, dataset_info, images_mean, images_std, ckpt_dir, model_path=None, trans_normalizer=0.03,
+                 rot_normalizer=5 * np.pi / 180, engine=None, weight_id=0, renderer=None, precision='tf32', max_batch=64):
+        self.dataset_info = dataset_info
+        self.image_size = (dataset_info['resolution'], dataset_info['resolution'])
+        if self.image_size[0] != 176:
+            raise NotImplementedError('libse3tn is built for the reference resolution of 176 (dataset_info.yml:15)')
+        self.object_cloud = None
+        if model_path is not None:
+            self.object_cloud = PointCloud(load_vertices(model_path)).voxel_down_sample(voxel_size=0.005)
+        if 'object_width' not in dataset_info:
+            if self.object_cloud is None:
+                raise ValueError("need model_path or dataset_info['object_width']")
+            w = compute_obj_max_width(np.asarray(self.object_cloud.points))
+            self.object_width = w + dataset_info['boundingbox'] / 100 * w
+        else:
+            self.object_width = dataset_info['object_width']
+        self.mean = images_mean
+        self.std = images_std
+        cam_cfg = dataset_info['camera']
+        self.K = np.array([cam_cfg['focalX'], 0, cam_cfg['centerX'], 0, cam_cfg['focalY'], cam_cfg['centerY'], 0, 0, 1]).reshape(3, 3)
+
+        if isinstance(ckpt_dir, dict):
+            checkpoint = ckpt_dir if 'state_dict' in ckpt_dir else {'state_dict': ckpt_dir}
+        else:
+            checkpoint = torch.load(ckpt_dir, map_location='cpu')
+        self.engine = engine if engine is not None else Engine(max_batch=max_batch)
+        self.weight_id = weight_id
+        self.precision = precision
+        self.model = Se3TrackNet(image_size=self.image_size[0], engine=self.engine, weight_id=weight_id, precision=precision)
+        self.model.load_state_dict(checkpoint['state_dict'])
+        self.model = self.model.cuda()
+        self.model.eval()
+        self.engine.set_stats(np.asarray(images_mean), np.asarray(images_std), weight_id)
+        U.set_engine(self.engine)
+
+        self.renderer = renderer if renderer is not None else self._try_reference_renderer(model_path, cam_cfg)
+        self.prev_rgb = None
+        self.prev_depth = None
+        self.frame_cnt = 0
+        self.errs = []
+        self.trans_normalizer = trans_normalizer
+        self.rot_normalizer = rot_normalizer
+        self.dataset = TrackDataset('', 'eval', images_mean, images_std, None, None, None, dataset_info,
+                                    trans_normalizer=trans_normalizer, rot_normalizer=rot_normalizer,
+                                    engine=self.engine, weight_id=weight_id, precision=precision)
+        self.dataset._stats_set = True
+
+    # ------------------------------------------------------------------ renderer glue (out-of-scope producer)
+    def _try_reference_renderer(self, model_path, cam_cfg):
+        """The reference picks pyrender or vispy by dataset_info['renderer'] (predict.py:161-182).
+        Both are OpenGL stacks outside this package; use them if the user's environment has them."""
+        if model_path is None:
+            return None
+        try:
+            if self.dataset_info.get('renderer') == 'pyrenderer':
+                from offscreen_renderer import Renderer            # reference module, if on sys.path
+                return Renderer([model_path], self.K, cam_cfg['height'], cam_cfg['width'])
+            from vispy_renderer import VispyRenderer               # reference module, if on sys.path
+            return VispyRenderer(model_path, self.K, H=self.dataset_info['resolution'], W=self.dataset_info['resolution'])
+        except Exception:
+            return None
+
+    def render_window(self, ob2cam):
+        """rgb u8 (176,176,3), depth u16 mm (176,176) of the model at `ob2cam` inside the crop window
+        (reference predict.py:193-215)."""
+        r = self.renderer
+        if r is None:
+            raise RuntimeError('no renderer available: pass rgbA/depthA to on_track, or renderer= to Tracker')
+        if hasattr(r, 'render_window'):
+            return r.render_window(ob2cam)
+        glcam_in_cvcam = np.diag([1.0, -1.0, -1.0, 1.0])
+        if hasattr(r, 'update_cam_mat'):                           # vispy-style
+            bbox = U.compute_bbox(ob2cam, self.K, self.object_width, scale=(1000, -1000, 1000))
+            ob2cam_gl = np.linalg.inv(glcam_in_cvcam).dot(ob2cam)
+            r.update_cam_mat(self.K, np.min(bbox[:, 1]), np.max(bbox[:, 1]), np.max(bbox[:, 0]), np.min(bbox[:, 0]))
+            return r.render_image(ob2cam_gl)
+        bbox = U.compute_bbox(ob2cam, self.K, self.object_width, scale=(1000, 1000, 1000))
+        rgb, depth = r.render([ob2cam])
+        return U.crop_bbox(rgb, (depth * 1000).astype(np.uint16), bbox, self.image_size)
+
+    # ------------------------------------------------------------------ the hot path
+    def on_track(self, prev_pose, current_rgb, current_depth, gt_A_in_cam=None, gt_B_in_cam=None, debug=False, samples=1,
+                 rgbA=None, depthA=None, show=False):
+        """One frame, one object (reference predict.py:217-296) -> new 4x4 float64 pose."""
+        A_in_cam = _as_numpy_pose(prev_pose).copy()
+        if rgbA is None or depthA is None:
+            rgbA, depthA = self.render_window(A_in_cam)
+        out = self.on_track_batch(A_in_cam[None], current_rgb, current_depth,
+                                  np.ascontiguousarray(rgbA, dtype=np.uint8)[None],
+                                  np.ascontiguousarray(depthA).astype(np.uint16)[None])
+        final_estimate = out[0]
+        self.prev_rgb = current_rgb
+        self.prev_depth = current_depth
+        if show:
+            import cv2
+            pred_color, _ = self.render_window(final_estimate)
+            cv2.imshow('AB', pred_color[..., ::-1])
+            cv2.waitKey(1)
+        self.frame_cnt += 1
+        return final_estimate
+
+    def on_track_batch(self, prev_poses, current_rgb, current_depth, rgbA, depthA, weight_ids=None, object_width=None):
+        """N independent tracks of ONE frame -> (N,4,4) float64.  Inputs may be numpy arrays (returns
+        numpy) or CUDA tensors (returns a CUDA tensor; nothing is synchronised)."""
+        dev = self.engine.device
+        as_numpy = not torch.is_tensor(prev_poses)
+
+        def up(x, dt):
+            if torch.is_tensor(x):
+                return x.to(dev, dt).contiguous()
+            a = np.ascontiguousarray(x)
+            if dt == torch.uint16 and a.dtype != np.uint16:
+                a = a.astype(np.uint16)
+            return torch.from_numpy(a).to(dev).to(dt)
+
+        poses = up(prev_poses, torch.float64)
+        n = poses.shape[0]
+        ow = torch.full((n,), float(self.object_width), dtype=torch.float64, device=dev) if object_width is None else up(object_width, torch.float64)
+        wh = None
+        if weight_ids is not None:
+            wh = np.ascontiguousarray(weight_ids.cpu().numpy() if torch.is_tensor(weight_ids) else weight_ids, dtype=np.int32)
+        elif self.weight_id != 0:
+            wh = np.full(n, self.weight_id, dtype=np.int32)
+        out, _, _ = self.engine.track_batch(up(current_rgb, torch.uint8), up(current_depth, torch.uint16), self.K, poses, ow,
+                                            up(rgbA, torch.uint8), up(depthA, torch.uint16),
+                                            self.trans_normalizer, self.rot_normalizer,
+                                            weight_ids_host=wh, precision=self.precision)
+        return out.cpu().numpy() if as_numpy else out
