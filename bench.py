@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py -- RGB-D pair frames/sec of the se(3)-TrackNet per-frame hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch 64] [--precision tf32]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one batch of synthetic input: `batch` (default 64)
+independent object tracks of one 480x640 RGB-D frame go through K0 (crop / depth clip / normalise),
+the 17-conv two-branch network and K6 (R^3 x so(3) pose update)  -- BASELINE.json configs[1].
+With N GPUs every rank runs its own `batch` tracks (weak scaling: 64 tracks per GPU, 512 on 8 =
+configs[3]) and the per-step exchange is one NCCL all-gather of the updated poses.
+
+Prints ONE JSON line (rank 0).  Keys beyond the base contract:
+  roofline      conv stack (the 14 tcgen05 launches) algorithmic FLOPs / their summed device time
+                (CUDA events recorded inside libse3tn on the launching stream) vs the tensor peak
+  cpu_baseline  the oracle's on_track path (torch CPU + numpy/cv2) timed on this box's host cores
+  e2e           same metric through Tracker.on_track_batch with pinned HOST buffers: H2D of the frame,
+                poses, rendered views and D2H of the poses inside every timed step
+--impl reference: the reference's own CPU implementation of the path (oracle restatement: the
+reference code itself cannot travel to the GPU box) on all host threads, bounded sample per step.
+"""
+import argparse, importlib, json, os, subprocess, sys, threading, time
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+FLOP_PER_PAIR = 5_527_109_632            # 17 convs, SURVEY.md 8d / BASELINE.md section 2
+N_INPUT_SETS = 16                        # rotated so the inputs of consecutive steps differ
+TN, RN = 0.03, 5 * np.pi / 180
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=64)
+    ap.add_argument('--precision', default='tf32', choices=['tf32', 'fp32'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-seconds', type=float, default=12.0)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, 'MEASURED_PEAKS.json'
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons DURING the timed region."""
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        try:
+            proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '100'],
+                                    stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            return
+        while not self.stop_flag:
+            line = proc.stdout.readline()
+            if not line:
+                break
+            self.samples.append([x.strip() for x in line.split(',')])
+        proc.terminate()
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace('.', '', 1).isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace('.', '', 1).isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for k, n in enumerate(names) if any(len(s) > 2 + k and s[2 + k].lower().startswith('active') for s in self.samples)]
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_on_track_rate(synth, seconds, pairs_per_call=8, threads=None):
+    """pairs/s of the oracle's hot path (crop+normalise per pair, one batched forward, pose update)."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import se3_oracle as O
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd = synth.make_state_dict(0)
+    mean, std = synth.default_mean_std()
+    rgb, depth = synth.raw_frame(0)
+    poses = synth.raw_poses(pairs_per_call, seed=0)
+    rgbA, depthA = synth.rendered_views(pairs_per_call, poses, seed=0)
+
+    def one_call():
+        dA, dB = [], []
+        for i in range(pairs_per_call):
+            bb = O.compute_bbox(poses[i], synth.CAMERA_K, 200.0, scale=(1000, 1000, 1000))
+            rB, zB = O.crop_bbox(rgb, depth, bb, (176, 176))
+            (a, b), _ = O.process_data(rgbA[i], depthA[i], poses[i], rB, zB, np.eye(4), mean, std)
+            dA.append(torch.from_numpy(a)); dB.append(torch.from_numpy(b))
+        out = O.forward(sd, torch.stack(dA), torch.stack(dB))
+        return [O.process_predict(poses[i], (out['trans'][i].numpy(), out['rot'][i].numpy())) for i in range(pairs_per_call)]
+
+    one_call()                                            # warm-up
+    t0 = time.perf_counter(); calls = 0
+    while True:
+        one_call(); calls += 1
+        if time.perf_counter() - t0 >= seconds and calls >= 2:
+            break
+    dt = time.perf_counter() - t0
+    return calls * pairs_per_call / dt, threads, '%d calls x %d pairs in %.1f s (same frame/pose generators as the GPU arm)' % (calls, pairs_per_call, dt)
+
+
+def run_reference(args, synth, rank, world):
+    """--impl reference: CPU, rank 0 only."""
+    if rank != 0:
+        return
+    per_step = 8
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import se3_oracle as O
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd = synth.make_state_dict(0)
+    mean, std = synth.default_mean_std()
+    rgb, depth = synth.raw_frame(0)
+    poses = synth.raw_poses(per_step, seed=0)
+    rgbA, depthA = synth.rendered_views(per_step, poses, seed=0)
+
+    def step():
+        dA, dB = [], []
+        for i in range(per_step):
+            bb = O.compute_bbox(poses[i], synth.CAMERA_K, 200.0, scale=(1000, 1000, 1000))
+            rB, zB = O.crop_bbox(rgb, depth, bb, (176, 176))
+            (a, b), _ = O.process_data(rgbA[i], depthA[i], poses[i], rB, zB, np.eye(4), mean, std)
+            dA.append(torch.from_numpy(a)); dB.append(torch.from_numpy(b))
+        out = O.forward(sd, torch.stack(dA), torch.stack(dB))
+        return [O.process_predict(poses[i], (out['trans'][i].numpy(), out['rot'][i].numpy())) for i in range(per_step)]
+
+    for _ in range(max(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = args.steps * per_step / dt
+    sample = 'each step = %d of the %d pairs of the workload (one batched CPU forward + per-pair numpy/cv2 pre/post)' % (per_step, args.batch)
+    line = {'impl': 'reference', 'metric': 'rgbd_pair_frames_per_sec', 'value': val, 'unit': 'pairs/s', 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'on_track hot path, %d tracks/step of one 480x640 frame @176x176 (BASELINE configs[1])' % args.batch,
+                       'tracks_per_gpu': args.batch, 'precision': 'fp32 CPU (torch oneDNN)'},
+            'cpu_baseline': {'value': val, 'unit': 'pairs/s', 'cores': threads, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': val, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    pkg = importlib.import_module('iros20-6d-pose-tracking_b200')
+    synth = pkg.synth
+    rank = int(os.environ.get('RANK', 0)); world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        run_reference(args, synth, rank, world)
+        return
+    import torch.distributed as dist
+    dist_mod = importlib.import_module('iros20-6d-pose-tracking_b200.dist')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    nb = args.batch
+
+    eng = pkg.Engine(max_batch=nb, device=local_rank)
+    sd = synth.make_state_dict(0)
+    mean, std = synth.default_mean_std()
+    eng.load_state_dict(sd, 0); eng.set_stats(mean, std, 0)
+
+    # ---- synthetic inputs, N_INPUT_SETS distinct sets resident in HBM -------
+    frames, sets = [], []
+    for k in range(N_INPUT_SETS):
+        seed = 1000 * rank + k
+        rgb, depth = synth.raw_frame(seed)
+        poses = synth.raw_poses(nb, seed=seed)
+        rgbA, depthA = synth.rendered_views(nb, poses, seed=seed)
+        host = dict(rgb=torch.from_numpy(rgb).pin_memory(), depth=torch.from_numpy(depth).pin_memory(),
+                    poses=torch.from_numpy(poses).pin_memory(), rgbA=torch.from_numpy(rgbA).pin_memory(),
+                    depthA=torch.from_numpy(depthA).pin_memory())
+        sets.append((host, {k2: v.to(dev) for k2, v in host.items()}))
+    ow = torch.full((nb,), 200.0, dtype=torch.float64, device=dev)
+    tracker = dist_mod.ShardedTracker(eng, np.zeros(nb * world, np.int32), synth.CAMERA_K, 200.0, TN, RN, rank, world, args.precision)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def step(k, gather=True):
+        d = sets[k % N_INPUT_SETS][1]
+        return tracker.step(d['rgb'], d['depth'], d['poses'], d['rgbA'], d['depthA'], gather=(gather and world > 1))
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- (1) device-resident throughput: K steps, per-step CUDA events, L2 flushed between steps -----
+    for k in range(max(args.warmup, 3)):
+        step(k)
+    sync_all()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start(); time.sleep(0.3)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches = 0
+    sync_all()
+    for k in range(args.steps):
+        flush.zero_()                                   # evict the previous step's lines from L2 (untimed)
+        ev[k][0].record()
+        step(k)
+        ev[k][1].record()
+        launches += eng.last_launch_count()
+    sync_all()
+    ms_steps = np.array([a.elapsed_time(b) for a, b in ev])
+    total_ms = torch.tensor([float(ms_steps.sum())], device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    ms_per_step = total_ms / args.steps
+    value = nb * world * args.steps / (total_ms * 1e-3)
+
+    # ---- (2) roofline of the conv stack: per-kernel events inside the library ------------------------
+    eng.set_profiling(True)
+    conv_ms, all_ms = [], []
+    for k in range(min(args.steps, 20)):
+        flush.zero_()
+        step(k, gather=False)
+        prof = eng.get_profile()
+        conv_ms.append(prof[:14].sum()); all_ms.append(prof)
+    eng.set_profiling(False)
+    conv_ms = float(np.mean(conv_ms)); per_slot = np.mean(np.stack(all_ms), 0)
+    pk, pk_src = peaks()
+    if args.precision == 'tf32':
+        peak = pk['bf16_tflops'] / 2.0
+        peak_note = 'tf32 dense = measured bf16 cuBLAS burst (%s: %.1f TF/s) / 2 (tf32 tensor rate is half of bf16); sustained equivalent %.1f' % (pk_src, pk['bf16_tflops'], pk.get('bf16_tflops_sustained', 0) / 2)
+    else:
+        peak = 75.0; peak_note = 'nominal fp32 FFMA peak (no tensor cores in this mode)'
+    achieved = nb * FLOP_PER_PAIR / (conv_ms * 1e-3) / 1e12
+    roofline = {'bound': 'tensor', 'kernel': 'conv_umma_kernel (14 launches/step)' if args.precision == 'tf32' else 'conv_direct_kernel',
+                'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None,
+                'conv_stack_ms': conv_ms, 'peak_note': peak_note,
+                'per_kernel_ms': {'conv': [round(float(x), 4) for x in per_slot[:14]], 'maxpool': [round(float(x), 4) for x in per_slot[14:16]],
+                                  'head': round(float(per_slot[16]), 4), 'preprocess': round(float(per_slot[17]), 4),
+                                  'pose_update': round(float(per_slot[18]), 4)}}
+
+    # ---- (3) end to end through the public API with pinned HOST buffers -----------------------------
+    info = {'resolution': 176, 'boundingbox': 10, 'object_width': 200.0,
+            'camera': {'focalX': synth.CAMERA_K[0, 0], 'focalY': synth.CAMERA_K[1, 1], 'centerX': synth.CAMERA_K[0, 2],
+                       'centerY': synth.CAMERA_K[1, 2], 'height': 480, 'width': 640}}
+    trk = pkg.Tracker(info, mean, std, {'state_dict': sd}, model_path=None, engine=eng, precision=args.precision)
+    pinned_out = torch.empty(nb, 4, 4, dtype=torch.float64).pin_memory()
+
+    def e2e_step(k):
+        h = sets[k % N_INPUT_SETS][0]
+        out = trk.on_track_batch(h['poses'].to(dev, non_blocking=True), h['rgb'].to(dev, non_blocking=True),
+                                 h['depth'].to(dev, non_blocking=True), h['rgbA'].to(dev, non_blocking=True),
+                                 h['depthA'].to(dev, non_blocking=True))
+        if world > 1:
+            out = dist_mod.all_gather_poses(out, tracker.shards, rank, world)[tracker.mine]
+        pinned_out.copy_(out, non_blocking=True)
+        return out
+
+    for k in range(3):
+        e2e_step(k)
+    sync_all()
+    e2e_steps = args.steps
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        e2e_step(k)
+    torch.cuda.synchronize(dev)
+    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev)
+    if world > 1:
+        dist.barrier(); dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    h0 = sets[0][0]
+    h2d = sum(h0[k2].numel() * h0[k2].element_size() for k2 in ('rgb', 'depth', 'poses', 'rgbA', 'depthA'))
+    e2e = {'value': nb * world * e2e_steps / (float(e2e_ms.item()) * 1e-3), 'unit': 'pairs/s',
+           'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(pinned_out.numel() * 8),
+           'api': 'Tracker.on_track_batch (pinned host tensors in, pinned host poses out, wall clock incl. copies)'}
+
+    clocks = None
+    if sampler:
+        sampler.stop_flag = True; time.sleep(0.15)
+        clocks = sampler.summary()
+
+    # ---- (4) CPU baseline (rank 0, N=1 only) ---------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores, sample = cpu_on_track_rate(synth, args.cpu_seconds)
+        cpu = {'value': v, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port', 'sample': sample}
+
+    if rank == 0:
+        line = {'metric': 'rgbd_pair_frames_per_sec', 'value': value, 'unit': 'pairs/s', 'n_gpus': world, 'steps': args.steps,
+                'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'tf32' if args.precision == 'tf32' else 'f32', 'data': 'synthetic',
+                'config': {'workload': 'BASELINE configs[1]: %d synthetic RGB-D pairs/GPU per step, full path K0 crop/normalise -> two-branch 17-conv forward -> se(3) update, 176x176, one 480x640 frame' % nb,
+                           'tracks_per_gpu': nb, 'total_tracks': nb * world, 'precision': args.precision,
+                           'parallelism': 'tracks sharded, %d/GPU, NCCL all-gather of poses per step' % nb if world > 1 else 'single GPU',
+                           'l2': 'flushed between timed steps (256 MiB memset, untimed); %d rotating input sets; per-step CUDA events, max over ranks' % N_INPUT_SETS,
+                           'weights': 'random-init (seeded), one weight set'},
+                'gpu_launches': int(launches), 'launches_per_step': int(launches // max(args.steps, 1)),
+                'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'clocks': clocks,
+                'ms_per_step_min': float(ms_steps.min()), 'ms_per_step_median': float(np.median(ms_steps))}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    eng.close()
+
+
+if __name__ == '__main__':
+    main()

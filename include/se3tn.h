@@ -156,6 +156,15 @@ int se3tn_track_batch(se3tn_ctx* ctx, const uint8_t* frame_rgb, const uint16_t* 
  * ids: 0 stemA 1 stemB 2 Y1A 3 Y1B 4 P1A 5 P1B 6 T1 7 T2 8 U 9 CAT 10 F1 11 T4 12 F2 13 H1 14 H2 15 H3 */
 int se3tn_debug_buffer(se3tn_ctx* ctx, int id, float** ptr, size_t* floats_per_image);
 
+/* Per-kernel device timing for bench.py's roofline line: when enabled, every launch of the hot path
+ * is bracketed by CUDA events on the caller's stream.  se3tn_get_profile synchronises those events
+ * and writes SE3TN_PROFILE_SLOTS durations (ms) of the LAST call: [0..13] the 14 conv launches in
+ * schedule order, [14],[15] the two max-pools, [16] head, [17] preprocess/normalize, [18] pose update,
+ * [19] input repack (se3tn_forward only).  Slots that did not run read 0. */
+#define SE3TN_PROFILE_SLOTS 20
+int se3tn_set_profiling(se3tn_ctx* ctx, int enable);
+int se3tn_get_profile(se3tn_ctx* ctx, float* ms);
+
 /* Number of kernels the last forward / track_batch call on this context launched. */
 int se3tn_last_launch_count(se3tn_ctx* ctx);
 

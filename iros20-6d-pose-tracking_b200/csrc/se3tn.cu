@@ -109,6 +109,9 @@ struct se3tn_ctx {
     float* d_mean32 = nullptr; float* d_std32 = nullptr; double* d_mean64 = nullptr; double* d_std64 = nullptr;
     int stats_rows = 0; bool stats_dirty = true; int stats_f64 = 0;
     int launches = 0;
+    bool profiling = false;
+    cudaEvent_t ev0[SE3TN_PROFILE_SLOTS] = {}, ev1[SE3TN_PROFILE_SLOTS] = {};
+    bool ev_used[SE3TN_PROFILE_SLOTS] = {};
     int umma_block_n_override = 0;
     std::string err;
 };
@@ -122,6 +125,14 @@ int fail(se3tn_ctx* c, int code, const std::string& msg) {
 #define CU_TRY(ctx, expr)                                                                        \
     do { cudaError_t e_ = (expr);                                                                \
          if (e_ != cudaSuccess) return fail((ctx), SE3TN_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); } while (0)
+
+struct ProfScope {
+    se3tn_ctx* c; int slot; cudaStream_t s;
+    ProfScope(se3tn_ctx* c_, int slot_, cudaStream_t s_) : c(c_), slot(slot_), s(s_) {
+        if (c->profiling) { cudaEventRecord(c->ev0[slot], s); }
+    }
+    ~ProfScope() { if (c->profiling) { cudaEventRecord(c->ev1[slot], s); c->ev_used[slot] = true; } }
+};
 
 size_t workspace_floats(int max_batch) {
     size_t n = 0;
@@ -330,15 +341,15 @@ int run_network(se3tn_ctx* c, int weight_id, int first, int n, int precision,
             t.img_first = first;
             g.n_img = first + n;
             p.out = c->buf[L.out]; p.res = (L.res != NONE) ? c->buf[L.res] : nullptr;
-            CU_TRY(c, launch_conv_umma(maps, g, t, p, BN, c->num_sms, s));
+            { ProfScope ps(c, li, s); CU_TRY(c, launch_conv_umma(maps, g, t, p, BN, c->num_sms, s)); }
         } else {
-            CU_TRY(c, launch_conv_direct(g, p, s));
+            { ProfScope ps(c, li, s); CU_TRY(c, launch_conv_direct(g, p, s)); }
         }
         ++c->launches;
-        if (li == 0) { CU_TRY(c, launch_maxpool(bufp(B_Y1A), bufp(B_P1A), n, 88, 88, 64, s)); ++c->launches; }
-        if (li == 1) { CU_TRY(c, launch_maxpool(bufp(B_Y1B), bufp(B_P1B), n, 88, 88, 64, s)); ++c->launches; }
+        if (li == 0) { ProfScope ps(c, 14, s); CU_TRY(c, launch_maxpool(bufp(B_Y1A), bufp(B_P1A), n, 88, 88, 64, s)); ++c->launches; }
+        if (li == 1) { ProfScope ps(c, 15, s); CU_TRY(c, launch_maxpool(bufp(B_Y1B), bufp(B_P1B), n, 88, 88, 64, s)); ++c->launches; }
     }
-    CU_TRY(c, launch_head(bufp(B_H3), ws.dev + ws.fc_off, ws.dev + ws.fc_off + 6 * 512, out_trans, out_rot, n, 121, s));
+    { ProfScope ps(c, 16, s); CU_TRY(c, launch_head(bufp(B_H3), ws.dev + ws.fc_off, ws.dev + ws.fc_off + 6 * 512, out_trans, out_rot, n, 121, s)); }
     ++c->launches;
     if (out_feature) { CU_TRY(c, launch_nhwc_to_nchw(bufp(B_F2), out_feature, n, 22 * 22, 256, s)); ++c->launches; }
     return SE3TN_OK;
@@ -410,6 +421,7 @@ void se3tn_destroy(se3tn_ctx* c) {
     cudaSetDevice(c->device);
     for (auto& kv : c->weights) { cudaFree(kv.second.dev); cudaFree(kv.second.dev_tf32); }
     cudaFree(c->d_mean32); cudaFree(c->d_std32); cudaFree(c->d_mean64); cudaFree(c->d_std64);
+    for (int i = 0; i < SE3TN_PROFILE_SLOTS; ++i) { if (c->ev0[i]) cudaEventDestroy(c->ev0[i]); if (c->ev1[i]) cudaEventDestroy(c->ev1[i]); }
     if (c->own_workspace) cudaFree(c->workspace);
     delete c;
 }
@@ -482,7 +494,7 @@ int se3tn_preprocess(se3tn_ctx* c, const uint8_t* frame_rgb, const uint16_t* fra
     a.stats_f64 = c->stats_f64; a.round_tf32 = (precision == SE3TN_PREC_TF32); a.b_precropped = 0;
     a.stemA = c->buf[B_X0A]; a.stemB = c->buf[B_X0B]; a.nchwA = out_A; a.nchwB = out_B;
     a.crop_rgb = crop_rgb; a.crop_depth = crop_depth;
-    CU_TRY(c, launch_preprocess(a, n, s));
+    { ProfScope ps(c, 17, s); CU_TRY(c, launch_preprocess(a, n, s)); }
     ++c->launches;
     return SE3TN_OK;
 }
@@ -503,7 +515,7 @@ int se3tn_normalize(se3tn_ctx* c, const uint8_t* rgbA, const uint16_t* depthA, c
     a.mean32 = c->d_mean32; a.std32 = c->d_std32; a.mean64 = c->d_mean64; a.std64 = c->d_std64;
     a.stats_f64 = c->stats_f64; a.round_tf32 = (precision == SE3TN_PREC_TF32);
     a.stemA = c->buf[B_X0A]; a.stemB = c->buf[B_X0B]; a.nchwA = out_A; a.nchwB = out_B;
-    CU_TRY(c, launch_preprocess(a, n, s));
+    { ProfScope ps(c, 17, s); CU_TRY(c, launch_preprocess(a, n, s)); }
     ++c->launches;
     return SE3TN_OK;
 }
@@ -537,8 +549,9 @@ int se3tn_forward(se3tn_ctx* c, int weight_id, const float* A, const float* B, i
     CU_TRY(c, cudaSetDevice(c->device));
     c->launches = 0;
     const int round = (precision == SE3TN_PREC_TF32);
-    CU_TRY(c, launch_nchw_to_stem(A, c->buf[B_X0A], n, round, s));
-    CU_TRY(c, launch_nchw_to_stem(B, c->buf[B_X0B], n, round, s));
+    { ProfScope ps(c, 19, s);
+      CU_TRY(c, launch_nchw_to_stem(A, c->buf[B_X0A], n, round, s));
+      CU_TRY(c, launch_nchw_to_stem(B, c->buf[B_X0B], n, round, s)); }
     c->launches += 2;
     return run_network(c, weight_id, 0, n, precision, out_trans, out_rot, out_feature, s);
 }
@@ -558,7 +571,7 @@ int se3tn_pose_update(se3tn_ctx* c, const double* poses_in, const float* trans, 
     if (!c) return SE3TN_ERR_INVALID;
     if (!poses_in || !trans || !rot || !poses_out || n < 0) return fail(c, SE3TN_ERR_INVALID, "se3tn_pose_update: null/invalid argument");
     CU_TRY(c, cudaSetDevice(c->device));
-    CU_TRY(c, launch_pose_update(poses_in, trans, rot, static_cast<float>(tn), static_cast<float>(rn), poses_out, n, static_cast<cudaStream_t>(stream)));
+    { ProfScope ps(c, 18, static_cast<cudaStream_t>(stream)); CU_TRY(c, launch_pose_update(poses_in, trans, rot, static_cast<float>(tn), static_cast<float>(rn), poses_out, n, static_cast<cudaStream_t>(stream))); }
     ++c->launches;
     return SE3TN_OK;
 }
@@ -607,5 +620,30 @@ int se3tn_debug_buffer(se3tn_ctx* c, int id, float** ptr, size_t* floats_per_ima
 }
 
 int se3tn_last_launch_count(se3tn_ctx* c) { return c ? c->launches : 0; }
+
+int se3tn_set_profiling(se3tn_ctx* c, int enable) {
+    if (!c) return SE3TN_ERR_INVALID;
+    CU_TRY(c, cudaSetDevice(c->device));
+    if (enable && !c->ev0[0]) {
+        for (int i = 0; i < SE3TN_PROFILE_SLOTS; ++i) { CU_TRY(c, cudaEventCreate(&c->ev0[i])); CU_TRY(c, cudaEventCreate(&c->ev1[i])); }
+    }
+    c->profiling = enable != 0;
+    for (int i = 0; i < SE3TN_PROFILE_SLOTS; ++i) c->ev_used[i] = false;
+    return SE3TN_OK;
+}
+
+int se3tn_get_profile(se3tn_ctx* c, float* ms) {
+    if (!c) return SE3TN_ERR_INVALID;
+    if (!ms) return fail(c, SE3TN_ERR_INVALID, "se3tn_get_profile: null argument");
+    if (!c->ev0[0]) return fail(c, SE3TN_ERR_STATE, "se3tn_get_profile: profiling was never enabled");
+    for (int i = 0; i < SE3TN_PROFILE_SLOTS; ++i) {
+        ms[i] = 0.f;
+        if (!c->ev_used[i]) continue;
+        CU_TRY(c, cudaEventSynchronize(c->ev1[i]));
+        CU_TRY(c, cudaEventElapsedTime(&ms[i], c->ev0[i], c->ev1[i]));
+        c->ev_used[i] = false;
+    }
+    return SE3TN_OK;
+}
 
 }  // extern "C"

@@ -1,0 +1,79 @@
+"""Multi-GPU: tracks (object instances) are independent (reference predict.py:217-296 has no
+cross-track data flow), so the track set is partitioned across ranks -- one process per GPU --
+with NO collective on the data path.  The only exchange step is an all-gather of the updated
+4x4 poses (128 B per track) when every rank wants the full pose set (NCCL over NVLink on GPUs;
+the same code runs on gloo/CPU tensors in the unit tests).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_tracks(weight_ids, world_size):
+    """Partition track indices over ranks: sort by weight id (one checkpoint per object class, F17),
+    then cut into `world_size` contiguous, equally sized (+-1) slices so each rank touches as few
+    weight sets as possible and all ranks carry the same number of tracks.
+    Returns a list (len world_size) of int64 index arrays into the original track order."""
+    weight_ids = np.asarray(weight_ids)
+    order = np.argsort(weight_ids, kind='stable')
+    n = len(order)
+    base, extra = divmod(n, world_size)
+    out, start = [], 0
+    for r in range(world_size):
+        cnt = base + (1 if r < extra else 0)
+        out.append(order[start:start + cnt].astype(np.int64))
+        start += cnt
+    return out
+
+
+def padded_count(n_tracks, world_size):
+    return (n_tracks + world_size - 1) // world_size
+
+
+def all_gather_poses(local_poses, shards, rank, world_size, group=None):
+    """local_poses: (len(shards[rank]),4,4) float64 on this rank's device.  Returns the full
+    (n_tracks,4,4) tensor in ORIGINAL track order on every rank.  Uneven shards are padded to the
+    largest shard so a single fixed-size all_gather_into_tensor suffices."""
+    n_total = int(sum(len(s) for s in shards))
+    per = max(len(s) for s in shards)
+    buf = torch.zeros(per, 4, 4, dtype=local_poses.dtype, device=local_poses.device)
+    buf[:local_poses.shape[0]] = local_poses
+    gathered = torch.empty(world_size * per, 4, 4, dtype=local_poses.dtype, device=local_poses.device)
+    if world_size == 1:
+        gathered.copy_(buf)
+    else:
+        dist.all_gather_into_tensor(gathered.view(-1), buf.view(-1), group=group)
+    out = torch.empty(n_total, 4, 4, dtype=local_poses.dtype, device=local_poses.device)
+    for r in range(world_size):
+        idx = torch.as_tensor(shards[r], device=local_poses.device)
+        out[idx] = gathered[r * per:r * per + len(shards[r])]
+    return out
+
+
+class ShardedTracker:
+    """Runs this rank's slice of a multi-object track set through an Engine and (optionally) gathers
+    all poses.  `engine` needs every weight set referenced by this rank's slice loaded."""
+    def __init__(self, engine, weight_ids, K, object_width, trans_normalizer, rot_normalizer,
+                 rank=0, world_size=1, precision='tf32'):
+        self.engine = engine
+        self.rank, self.world_size = rank, world_size
+        self.weight_ids = np.asarray(weight_ids, dtype=np.int32)
+        self.shards = shard_tracks(self.weight_ids, world_size)
+        self.mine = self.shards[rank]
+        self.K = K
+        self.tn, self.rn = trans_normalizer, rot_normalizer
+        self.precision = precision
+        dev = engine.device
+        self.local_wids_host = np.ascontiguousarray(self.weight_ids[self.mine])      # sorted => contiguous runs
+        self.local_wids_dev = torch.from_numpy(self.local_wids_host).to(dev)
+        ow = np.broadcast_to(np.asarray(object_width, dtype=np.float64), self.weight_ids.shape)
+        self.local_ow = torch.from_numpy(np.ascontiguousarray(ow[self.mine])).to(dev)
+
+    def step(self, frame_rgb, frame_depth, local_poses, local_rgbA, local_depthA, gather=True):
+        out, _, _ = self.engine.track_batch(frame_rgb, frame_depth, self.K, local_poses, self.local_ow,
+                                            local_rgbA, local_depthA, self.tn, self.rn,
+                                            weight_ids_host=self.local_wids_host, weight_ids_dev=self.local_wids_dev,
+                                            precision=self.precision)
+        if not gather:
+            return out, None
+        return out, all_gather_poses(out, self.shards, self.rank, self.world_size)

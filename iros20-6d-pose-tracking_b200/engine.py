@@ -198,6 +198,15 @@ class Engine:
         nbytes = n * fpi.value * 4
         return self._workspace[offb:offb + nbytes].view(torch.float32).view(n, fpi.value)
 
+    def set_profiling(self, enable=True):
+        _lib.check(self.lib.se3tn_set_profiling(self._ctx, int(bool(enable))), self._ctx)
+
+    def get_profile(self):
+        """Device ms of each kernel of the last call (20 slots, see include/se3tn.h)."""
+        ms = (C.c_float * 20)()
+        _lib.check(self.lib.se3tn_get_profile(self._ctx, ms), self._ctx)
+        return np.array(ms[:], dtype=np.float64)
+
     def last_launch_count(self):
         return self.lib.se3tn_last_launch_count(self._ctx)
 

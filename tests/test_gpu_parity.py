@@ -1,0 +1,308 @@
+"""GPU parity tests: the CUDA path (through the C ABI / drop-in classes) against the oracle on the
+same seeded inputs, and against the golden fixtures produced by the reference's own code.
+
+Tolerances:
+  * integer / byte / index work (bbox, crops): bit-exact
+  * preprocessing floats (fp32 chain):          bit-exact (same IEEE ops as numpy)
+  * network 6-vector, TF32 tensor-core path:    rtol 1e-3 / atol 1e-4 (BASELINE.json north_star)
+  * network 6-vector, FP32 FFMA path:           rtol 1e-4 / atol 2e-6
+  * pose update / so(3) log (fp64 + libm trig): atol 1e-7 / 1e-9
+"""
+import hashlib, importlib, os
+import numpy as np
+import pytest
+import torch
+import se3_oracle as O
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-3, 1e-4
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope='module')
+def eng(pkg, synth):
+    e = pkg.Engine(max_batch=64)
+    e.load_state_dict(synth.make_state_dict(0), 0)
+    e.load_state_dict(synth.make_state_dict(1), 1)
+    mean, std = synth.default_mean_std()
+    e.set_stats(mean, std, 0)
+    e.set_stats(mean + 1.5, std * 1.25, 1)
+    yield e
+    e.close()
+
+
+def six(trans, rot):
+    return torch.cat((trans, rot), 1).cpu()
+
+
+def assert_gate(out, ref, rtol=RTOL, atol=ATOL):
+    err = (out - ref).abs(); tol = atol + rtol * ref.abs()
+    assert torch.isfinite(out).all()
+    assert (err <= tol).all(), 'max err/tol %.3f' % (err / tol).max().item()
+    return (err / tol).max().item()
+
+
+# ------------------------------------------------------------------------------- network
+def test_config1_parity_gate(pkg, synth, golden_dir, eng):
+    """BASELINE config 1: the shipped RGB pair, batch 1, vs the REFERENCE's own forward (golden)."""
+    import cv2
+    g = np.load(os.path.join(golden_dir, 'golden_model.npz'))
+    rgbA = cv2.imread(os.path.join(golden_dir, 'c1_rgbA.png'))[..., ::-1].copy()
+    rgbB = cv2.imread(os.path.join(golden_dir, 'c1_rgbB.png'))[..., ::-1].copy()
+    depthA, depthB = synth.depth_from_rgb(rgbA), synth.depth_from_rgb(rgbB)
+    pose = synth.config1_pose()
+    dev = eng.device
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)[None]).to(dev)
+    tA, tB = eng.normalize(t(rgbA), t(depthA), t(rgbB), t(depthB), torch.from_numpy(pose[None]).to(dev))
+    assert sha(tA[0].cpu().numpy()) == str(g['c1_dataA_sha']) and sha(tB[0].cpu().numpy()) == str(g['c1_dataB_sha'])
+    ref = torch.from_numpy(np.concatenate([g['c1_trans'], g['c1_rot']], 1))
+    for prec, (rt, at) in {'tf32': (RTOL, ATOL), 'fp32': (1e-4, 2e-6)}.items():
+        trans, rot, _ = eng.forward_preprocessed(1, weight_id=0, precision=prec)
+        assert_gate(six(trans, rot), ref, rt, at)
+        pose_out = eng.pose_update(torch.from_numpy(pose[None]).to(dev), trans, rot, 0.03, 5 * np.pi / 180)[0].cpu().numpy()
+        assert np.allclose(pose_out, g['c1_pose_out'], rtol=0, atol=1e-5 if prec == 'tf32' else 1e-7)
+
+
+@pytest.mark.parametrize('n', [1, 2, 3, 7])
+def test_forward_matches_oracle_small_batches(synth, eng, n):
+    sd = synth.make_state_dict(0)
+    A, B = synth.tensor_pairs(n, seed=10 + n)
+    ref = O.forward(sd, A, B)
+    ref6 = torch.cat((ref['trans'], ref['rot']), 1)
+    for prec, (rt, at) in {'tf32': (RTOL, ATOL), 'fp32': (1e-4, 2e-6)}.items():
+        trans, rot, feat = eng.forward(A.to(eng.device), B.to(eng.device), precision=prec, want_feature=True)
+        assert_gate(six(trans, rot), ref6, rt, at)
+        ftol = 2e-2 if prec == 'tf32' else 1e-4
+        assert (feat.cpu() - ref['feature']).abs().max().item() < ftol * ref['feature'].abs().max().item()
+
+
+def test_forward_golden_fixture(synth, golden_dir, eng):
+    g = np.load(os.path.join(golden_dir, 'golden_model.npz'))
+    A, B = synth.tensor_pairs(2, seed=0)
+    trans, rot, feat = eng.forward(A.to(eng.device), B.to(eng.device), precision='tf32', want_feature=True)
+    assert_gate(six(trans, rot), torch.from_numpy(np.concatenate([g['trans'], g['rot']], 1)))
+    assert np.abs(feat.cpu().numpy()[:, ::16, ::3, ::3] - g['feature_sub']).max() < 2e-2 * np.abs(g['feature_sub']).max()
+
+
+def test_batch64_full_size_properties(synth, eng):
+    """BASELINE config 2 size.  Oracle on all 64 pairs (~1 s on CPU) + size-independent properties:
+    batch-composition independence (a pair's result does not depend on its neighbours) and
+    determinism."""
+    sd = synth.make_state_dict(0)
+    A, B = synth.tensor_pairs(64, seed=2)
+    Ad, Bd = A.to(eng.device), B.to(eng.device)
+    t1, r1, _ = eng.forward(Ad, Bd, precision='tf32')
+    ref = O.forward(sd, A, B)
+    worst = assert_gate(six(t1, r1), torch.cat((ref['trans'], ref['rot']), 1))
+    print('batch-64 TF32 worst err/tol: %.3f' % worst)
+    t2, r2, _ = eng.forward(Ad, Bd, precision='tf32')
+    assert torch.equal(t1, t2) and torch.equal(r1, r2)                       # deterministic
+    perm = torch.randperm(64, generator=torch.Generator().manual_seed(0)).to(eng.device)
+    t3, r3, _ = eng.forward(Ad[perm].contiguous(), Bd[perm].contiguous(), precision='tf32')
+    assert torch.equal(t3, t1[perm]) and torch.equal(r3, r1[perm])           # per-pair independence
+    t4, r4, _ = eng.forward(Ad[:5].contiguous(), Bd[:5].contiguous(), precision='tf32')
+    assert torch.equal(t4, t1[:5]) and torch.equal(r4, r1[:5])               # ragged tail of a batch
+    tf, rf, _ = eng.forward(Ad, Bd, precision='fp32')
+    assert_gate(six(tf, rf), torch.cat((ref['trans'], ref['rot']), 1), 1e-4, 2e-6)
+
+
+def test_second_weight_set_and_module_api(pkg, synth):
+    sd1 = synth.make_state_dict(1)
+    net = pkg.Se3TrackNet(image_size=176)
+    net.load_state_dict(sd1)
+    net = net.cuda(); net.eval()
+    A, B = synth.tensor_pairs(2, seed=5)
+    with torch.no_grad():
+        out = net(A.cuda(), B.cuda())
+    assert set(out) == {'feature', 'trans', 'rot'} and out['feature'].shape == (2, 256, 22, 22)
+    ref = O.forward(sd1, A, B)
+    assert_gate(six(out['trans'], out['rot']), torch.cat((ref['trans'], ref['rot']), 1))
+    with pytest.raises(NotImplementedError):
+        net.train()
+
+
+# -------------------------------------------------------------------------- preprocessing
+def _frame_case(synth, n, seed):
+    rgb, depth = synth.raw_frame(seed)
+    poses = synth.raw_poses(n, seed=seed)
+    rgbA, depthA = synth.rendered_views(n, poses, seed=seed)
+    return rgb, depth, poses, rgbA, depthA
+
+
+def test_preprocess_bit_exact_vs_oracle(synth, eng):
+    n = 8
+    rgb, depth, poses, rgbA, depthA = _frame_case(synth, n, 0)
+    poses[1, :3, 3] = (-0.13, -0.1, 0.5)          # window clipped at the top-left of the frame
+    poses[2, :3, 3] = (0.14, 0.1, 0.45)           # clipped bottom-right
+    poses[3, :3, 3] = (0.0, 0.0, 0.25)            # window larger than the frame
+    poses[4, :3, 3] = (0.01, 0.02, 1.9)           # far object: 112-px window upsampled
+    dev = eng.device
+    ow = np.full(n, 200.0); ow[5] = 187.3
+    wid = np.array([0, 1, 0, 1, 0, 0, 1, 1], dtype=np.int32)
+    mean, std = synth.default_mean_std()
+    stats = {0: (mean, std), 1: (mean + 1.5, std * 1.25)}
+    tA, tB, crgb, cdepth = eng.preprocess(torch.from_numpy(rgb).to(dev), torch.from_numpy(depth).to(dev), synth.CAMERA_K,
+                                          torch.from_numpy(poses).to(dev), torch.from_numpy(ow).to(dev),
+                                          torch.from_numpy(rgbA).to(dev), torch.from_numpy(depthA).to(dev),
+                                          weight_ids=torch.from_numpy(wid).to(dev), want_tensors=True, want_crops=True)
+    bbs = eng.compute_bbox(torch.from_numpy(poses).to(dev), synth.CAMERA_K, torch.from_numpy(ow).to(dev)).cpu().numpy()
+    for i in range(n):
+        bb = O.compute_bbox(poses[i], synth.CAMERA_K, ow[i], scale=(1000, 1000, 1000))
+        assert np.array_equal(bbs[i], bb)
+        rB, dB = O.crop_bbox(rgb, depth, bb, (176, 176))
+        assert np.array_equal(crgb[i].cpu().numpy(), rB) and np.array_equal(cdepth[i].cpu().numpy(), dB), i
+        m, s = stats[int(wid[i])]
+        (dA_, dB_), _ = O.process_data(rgbA[i], depthA[i], poses[i], rB, dB, np.eye(4), m, s)
+        assert np.array_equal(tA[i].cpu().numpy(), dA_) and np.array_equal(tB[i].cpu().numpy(), dB_), i
+    # the conv-input buffers hold the same values (tf32-rounded) in padded NHWC4
+    x0b = eng.debug_buffer(1, n).view(n, 182, 184, 4)[:, 3:179, 3:179, :].permute(0, 3, 1, 2)
+    assert (x0b - tB).abs().max().item() <= 2.0 ** -11 * tB.abs().max().item()
+    assert float(eng.debug_buffer(1, n).view(n, 182, 184, 4)[:, :3].abs().max()) == 0.0      # halo stays zero
+
+
+def test_golden_crops_and_process_data(pkg, synth, golden_dir, eng):
+    """Against fixtures generated by the reference's own Utils/datasets code."""
+    p = np.load(os.path.join(golden_dir, 'golden_pre.npz'))
+    dev = eng.device
+    rgb, depth, K = p['small_rgb'], p['small_depth'], p['K_small']
+    n = len(p['object_width'])
+    poses = p['poses']
+    bbs = eng.compute_bbox(torch.from_numpy(poses).to(dev), K, torch.from_numpy(p['object_width']).to(dev))
+    crgb, cdepth = eng.crop_bbox(torch.from_numpy(rgb).to(dev), torch.from_numpy(depth).to(dev), bbs)
+    for i in range(n):
+        assert np.array_equal(bbs[i].cpu().numpy(), p[f'bb_{i}'])
+        assert sha(crgb[i].cpu().numpy()) == str(p[f'rgbB_sha_{i}']) and sha(cdepth[i].cpu().numpy()) == str(p[f'depthB_sha_{i}'])
+    gl = eng.compute_bbox(torch.from_numpy(poses[1:2]).to(dev), K, torch.tensor([200.0], dtype=torch.float64, device=dev),
+                          scale=(1000., -1000., 1000.))
+    assert np.array_equal(gl[0].cpu().numpy(), p['bb_gl_0'])
+    # TrackDataset.processData drop-in, both mean/std dtype chains
+    rgbAs, depthAs = synth.rendered_views(n, poses, seed=7)
+    mean, std = synth.default_mean_std()
+    chains = {'f32': (mean, std), 'f64': (mean.astype(np.float64) + 0.123, std.astype(np.float64) * 1.01)}
+    for tag, (m, s) in chains.items():
+        e2 = pkg.Engine(max_batch=1)
+        ds = pkg.TrackDataset('', 'eval', m, s, None, None, None, None, engine=e2)
+        for i in range(n):
+            rB, dB = crgb[i].cpu().numpy(), cdepth[i].cpu().numpy()
+            sample, (tl, rl), _, _, mA, mB = ds.processData(rgbAs[i], depthAs[i], poses[i].copy(), rB, dB, p[f'gtB_{i}'].copy())
+            assert sample[0].dtype == torch.float32 and not sample[0].is_cuda
+            assert sha(sample[0].numpy()) == str(p[f'dataA_sha_{tag}_{i}']), (tag, i)
+            assert sha(sample[1].numpy()) == str(p[f'dataB_sha_{tag}_{i}']), (tag, i)
+            assert np.allclose(tl, p[f'label_trans_{i}'], rtol=0, atol=1e-12)
+            assert np.allclose(rl, p[f'label_rot_{i}'], rtol=0, atol=1e-9)
+            assert np.array_equal(mA, (depthAs[i] > 100).astype(np.uint8))
+        e2.close()
+
+
+def test_full_frame_golden_crops(synth, golden_dir, eng):
+    p = np.load(os.path.join(golden_dir, 'golden_pre.npz'))
+    rgb, depth = synth.raw_frame(0)
+    poses = synth.raw_poses(8, seed=0)
+    dev = eng.device
+    ow = torch.full((8,), 200.0, dtype=torch.float64, device=dev)
+    bbs = eng.compute_bbox(torch.from_numpy(poses).to(dev), synth.CAMERA_K, ow)
+    crgb, cdepth = eng.crop_bbox(torch.from_numpy(rgb).to(dev), torch.from_numpy(depth).to(dev), bbs)
+    for i in range(8):
+        assert np.array_equal(bbs[i].cpu().numpy(), p[f'full_bb_{i}'])
+        assert sha(crgb[i].cpu().numpy()) == str(p[f'full_rgbB_sha_{i}']) and sha(cdepth[i].cpu().numpy()) == str(p[f'full_depthB_sha_{i}'])
+
+
+def test_utils_dropins(pkg, synth):
+    U = importlib.import_module('iros20-6d-pose-tracking_b200.Utils')
+    rgb, depth = synth.raw_frame(4, 120, 160)
+    K = synth.CAMERA_K.copy(); K[:2] *= 0.25
+    pose = synth.raw_poses(1, seed=4)[0]; pose[:3, 3] = (0.01, -0.02, 0.6)
+    bb = U.compute_bbox(pose, K, 215.5, scale=(1000, 1000, 1000))
+    assert bb.dtype == np.int32 and np.array_equal(bb, O.compute_bbox(pose, K, 215.5, scale=(1000, 1000, 1000)))
+    a, b = U.crop_bbox(rgb, depth, bb, (176, 176)); c, d = O.crop_bbox(rgb, depth, bb, (176, 176))
+    assert a.dtype == np.uint8 and b.dtype == np.uint16 and np.array_equal(a, c) and np.array_equal(b, d)
+    a, b = U.crop_bbox(rgb, depth, bb, (100, 100)); c, d = O.crop_bbox(rgb, depth, bb, (100, 100))
+    assert np.array_equal(a, c) and np.array_equal(b, d)
+
+
+# ------------------------------------------------------------------------------ Lie-algebra ops
+def test_pose_update_and_log_vs_golden(golden_dir, eng):
+    p = np.load(os.path.join(golden_dir, 'golden_pre.npz'))
+    dev = eng.device
+    poses = torch.from_numpy(p['pu_poses']).to(dev)
+    tr, ro = torch.from_numpy(p['pu_trans']).to(dev), torch.from_numpy(p['pu_rot']).to(dev)
+    o5 = eng.pose_update(poses, tr, ro, 0.03, 5 * np.pi / 180).cpu().numpy()
+    o30 = eng.pose_update(poses, tr, ro, 0.03, 30 * np.pi / 180).cpu().numpy()
+    assert np.abs(o5 - p['pu_out_5deg']).max() < 1e-7 and np.abs(o30 - p['pu_out_30deg']).max() < 1e-7
+    assert np.array_equal(o5[0], p['pu_poses'][0])                      # zero residual: exact identity
+    assert np.array_equal(o5[:, 3], np.tile([0, 0, 0, 1.0], (len(o5), 1)))
+    # round trip: log(exp(w) R, R) == w
+    back_t, back_r = eng.so3_log(poses, torch.from_numpy(p['pu_out_30deg']).to(dev), 0.03, 30 * np.pi / 180)
+    assert np.abs(back_t.cpu().numpy() - p['pu_trans'].astype(np.float64)).max() < 1e-6
+    assert np.abs(back_r.cpu().numpy() - p['pu_rot'].astype(np.float64)).max() < 1e-6
+
+
+def test_so3_log_near_pi_and_identity(eng):
+    import cv2
+    dev = eng.device
+    ws = [np.zeros(3), np.array([1e-7, 0, 0]), np.array([np.pi - 1e-7, 0, 0]), np.array([0, 3.1, 0.2]),
+          np.array([2.2, -2.2, 0.1]), np.array([0.3, 0.2, -0.1])]
+    A = np.tile(np.eye(4), (len(ws), 1, 1)); B = A.copy()
+    for i, w in enumerate(ws):
+        B[i, :3, :3] = cv2.Rodrigues(w)[0]
+    _, rl = eng.so3_log(torch.from_numpy(A).to(dev), torch.from_numpy(B).to(dev), 1.0, 1.0)
+    ref = np.stack([cv2.Rodrigues(O.normalize_rotation_matrix(B[i, :3, :3].copy()))[0].ravel() for i in range(len(ws))])
+    assert np.abs(rl.cpu().numpy() - ref).max() < 1e-7
+
+
+# ------------------------------------------------------------------------------ end to end
+def test_on_track_end_to_end_vs_oracle(pkg, synth):
+    """Tracker.on_track drop-in: raw frame + pose in, pose out, against the oracle's on_track."""
+    sd = synth.make_state_dict(0)
+    mean, std = synth.default_mean_std()
+    info = {'resolution': 176, 'boundingbox': 10, 'object_width': 200.0,
+            'camera': {'focalX': synth.CAMERA_K[0, 0], 'focalY': synth.CAMERA_K[1, 1], 'centerX': synth.CAMERA_K[0, 2],
+                       'centerY': synth.CAMERA_K[1, 2], 'height': 480, 'width': 640}}
+    trk = pkg.Tracker(info, mean, std, {'state_dict': sd}, model_path=None, max_batch=8)
+    n = 4
+    rgb, depth, poses, rgbA, depthA = _frame_case(synth, n, 3)
+    for i in range(n):
+        got = trk.on_track(poses[i], rgb, depth, rgbA=rgbA[i], depthA=depthA[i])
+        ref = O.on_track(sd, poses[i], rgb, depth, rgbA[i], depthA[i], synth.CAMERA_K, 200.0, mean, std)
+        assert got.dtype == np.float64 and got.shape == (4, 4)
+        # 6-vector within the gate => translation within 1e-4*0.03 m, rotation within ~1e-4*5deg
+        assert np.abs(got - ref).max() < 2e-5
+    batch = trk.on_track_batch(poses, rgb, depth, rgbA, depthA)
+    singles = np.stack([trk.on_track(poses[i], rgb, depth, rgbA=rgbA[i], depthA=depthA[i]) for i in range(n)])
+    assert np.array_equal(batch, singles)
+    assert trk.frame_cnt == 2 * n
+
+
+def test_track_batch_mixed_weight_sets(synth, eng):
+    n = 6
+    rgb, depth, poses, rgbA, depthA = _frame_case(synth, n, 6)
+    dev = eng.device
+    wid = np.array([0, 0, 0, 1, 1, 1], dtype=np.int32)
+    ow = torch.full((n,), 200.0, dtype=torch.float64, device=dev)
+    args = (torch.from_numpy(rgb).to(dev), torch.from_numpy(depth).to(dev), synth.CAMERA_K, torch.from_numpy(poses).to(dev), ow,
+            torch.from_numpy(rgbA).to(dev), torch.from_numpy(depthA).to(dev), 0.03, 5 * np.pi / 180)
+    out, tr, ro = eng.track_batch(*args, weight_ids_host=wid)
+    mean, std = synth.default_mean_std()
+    stats = {0: (mean, std), 1: (mean + 1.5, std * 1.25)}
+    sds = {0: synth.make_state_dict(0), 1: synth.make_state_dict(1)}
+    for i in range(n):
+        w = int(wid[i])
+        ref, dbg = O.on_track(sds[w], poses[i], rgb, depth, rgbA[i], depthA[i], synth.CAMERA_K, 200.0, *stats[w], return_all=True)
+        got6 = torch.cat((tr[i], ro[i])).cpu()
+        assert_gate(got6, torch.from_numpy(np.concatenate([dbg['trans'], dbg['rot']])))
+        assert np.abs(out[i].cpu().numpy() - ref).max() < 2e-5
+
+
+def test_errors_are_reported_not_fatal(pkg, synth, eng):
+    L = importlib.import_module('iros20-6d-pose-tracking_b200._lib')
+    A, B = synth.tensor_pairs(1, seed=0)
+    with pytest.raises(L.Se3tnError) as ei:
+        eng.forward(A.to(eng.device), B.to(eng.device), weight_id=7)
+    assert ei.value.code == L.ERR_STATE and 'not loaded' in str(ei.value)
+    with pytest.raises(ValueError):
+        eng.forward(A.to(eng.device)[:, :3].contiguous(), B.to(eng.device))
+    # the context is still usable
+    eng.forward(A.to(eng.device), B.to(eng.device), weight_id=0)
