@@ -82,12 +82,39 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------
+def usable_cpus():
+    """CPUs this process may actually use: affinity mask capped by the cgroup quota."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        q, per = open('/sys/fs/cgroup/cpu.max').read().split()
+        if q != 'max':
+            n = max(1, min(n, int(float(q) / float(per) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
+def pick_threads(fn):
+    """torch CPU throughput is not monotonic in thread count on big hosts: try a few, keep the fastest."""
+    best, best_t = None, None
+    n = usable_cpus()
+    for t in sorted({n, max(1, n // 2), max(1, n // 4), min(n, 32), min(n, 16)}, reverse=True):
+        torch.set_num_threads(t)
+        fn()
+        t0 = time.perf_counter(); fn(); dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best, best_t = t, dt
+    torch.set_num_threads(best)
+    return best
+
+
 def cpu_on_track_rate(synth, seconds, pairs_per_call=8, threads=None):
     """pairs/s of the oracle's hot path (crop+normalise per pair, one batched forward, pose update)."""
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import se3_oracle as O
-    threads = threads or os.cpu_count() or 1
-    torch.set_num_threads(threads)
     sd = synth.make_state_dict(0)
     mean, std = synth.default_mean_std()
     rgb, depth = synth.raw_frame(0)
@@ -104,7 +131,7 @@ def cpu_on_track_rate(synth, seconds, pairs_per_call=8, threads=None):
         out = O.forward(sd, torch.stack(dA), torch.stack(dB))
         return [O.process_predict(poses[i], (out['trans'][i].numpy(), out['rot'][i].numpy())) for i in range(pairs_per_call)]
 
-    one_call()                                            # warm-up
+    threads = pick_threads(one_call)                      # includes warm-up
     t0 = time.perf_counter(); calls = 0
     while True:
         one_call(); calls += 1
@@ -121,8 +148,6 @@ def run_reference(args, synth, rank, world):
     per_step = 8
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import se3_oracle as O
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
     sd = synth.make_state_dict(0)
     mean, std = synth.default_mean_std()
     rgb, depth = synth.raw_frame(0)
@@ -139,6 +164,7 @@ def run_reference(args, synth, rank, world):
         out = O.forward(sd, torch.stack(dA), torch.stack(dB))
         return [O.process_predict(poses[i], (out['trans'][i].numpy(), out['rot'][i].numpy())) for i in range(per_step)]
 
+    threads = pick_threads(step)
     for _ in range(max(args.warmup, 1)):
         step()
     t0 = time.perf_counter()

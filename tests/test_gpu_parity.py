@@ -7,6 +7,8 @@ Tolerances:
   * network 6-vector, TF32 tensor-core path:    rtol 1e-3 / atol 1e-4 (BASELINE.json north_star)
   * network 6-vector, FP32 FFMA path:           rtol 1e-4 / atol 2e-6
   * pose update / so(3) log (fp64 + libm trig): atol 1e-7 / 1e-9
+  * poses produced from a TF32 6-vector: the gate propagated through datasets.py:169-174,
+    |dt| <= (1e-4 + 1e-3)*0.03 m and |dR| <= (1e-4 + 1e-3)*rot_normalizer  ->  POSE_ATOL = 1e-4
 """
 import hashlib, importlib, os
 import numpy as np
@@ -16,6 +18,7 @@ import se3_oracle as O
 
 pytestmark = pytest.mark.gpu
 RTOL, ATOL = 1e-3, 1e-4
+POSE_ATOL = 1e-4
 
 
 def sha(a):
@@ -63,7 +66,7 @@ def test_config1_parity_gate(pkg, synth, golden_dir, eng):
         trans, rot, _ = eng.forward_preprocessed(1, weight_id=0, precision=prec)
         assert_gate(six(trans, rot), ref, rt, at)
         pose_out = eng.pose_update(torch.from_numpy(pose[None]).to(dev), trans, rot, 0.03, 5 * np.pi / 180)[0].cpu().numpy()
-        assert np.allclose(pose_out, g['c1_pose_out'], rtol=0, atol=1e-5 if prec == 'tf32' else 1e-7)
+        assert np.allclose(pose_out, g['c1_pose_out'], rtol=0, atol=POSE_ATOL if prec == 'tf32' else 1e-7)
 
 
 @pytest.mark.parametrize('n', [1, 2, 3, 7])
@@ -268,8 +271,7 @@ def test_on_track_end_to_end_vs_oracle(pkg, synth):
         got = trk.on_track(poses[i], rgb, depth, rgbA=rgbA[i], depthA=depthA[i])
         ref = O.on_track(sd, poses[i], rgb, depth, rgbA[i], depthA[i], synth.CAMERA_K, 200.0, mean, std)
         assert got.dtype == np.float64 and got.shape == (4, 4)
-        # 6-vector within the gate => translation within 1e-4*0.03 m, rotation within ~1e-4*5deg
-        assert np.abs(got - ref).max() < 2e-5
+        assert np.abs(got - ref).max() < POSE_ATOL
     batch = trk.on_track_batch(poses, rgb, depth, rgbA, depthA)
     singles = np.stack([trk.on_track(poses[i], rgb, depth, rgbA=rgbA[i], depthA=depthA[i]) for i in range(n)])
     assert np.array_equal(batch, singles)
@@ -293,7 +295,7 @@ def test_track_batch_mixed_weight_sets(synth, eng):
         ref, dbg = O.on_track(sds[w], poses[i], rgb, depth, rgbA[i], depthA[i], synth.CAMERA_K, 200.0, *stats[w], return_all=True)
         got6 = torch.cat((tr[i], ro[i])).cpu()
         assert_gate(got6, torch.from_numpy(np.concatenate([dbg['trans'], dbg['rot']])))
-        assert np.abs(out[i].cpu().numpy() - ref).max() < 2e-5
+        assert np.abs(out[i].cpu().numpy() - ref).max() < POSE_ATOL
 
 
 def test_errors_are_reported_not_fatal(pkg, synth, eng):
