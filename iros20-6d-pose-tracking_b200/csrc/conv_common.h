@@ -69,6 +69,30 @@ struct alignas(64) UmmaMaps {
     CUtensorMap b;
 };
 
+// ---- tcgen05 path, second generation (conv_umma2.cu) ---------------------------------------
+struct UnitTap { int8_t row_shift; int8_t w_tap; };   // rows to advance the A descriptor; weight tap index
+struct Unit {
+    int8_t map;            // A tensor map index
+    int8_t c1, c2;         // TMA coordinate deltas (x, y) relative to the tile origin
+    int8_t ntaps;
+    uint16_t rows;         // rows the TMA box writes (bw * extended height * bn): expect_tx = rows*128
+    UnitTap taps[4];
+};
+
+struct Umma2Plan {
+    int units_per_chunk;
+    Unit units[6];
+    int chunks;                          // cin / 32
+    int step_x, step_y, off_x, off_y;    // tile origin in A-map coordinates = tile index * step + off
+    int bw, bh, bn;                      // output pixel box per tile (normal epilogue)
+    int tiles_x, tiles_y, m_tiles, n_tiles;
+    int img_first;
+    int base_off_mode;                   // 0: descriptor base_offset = 0; 1: (addr >> 7) & 7
+};
+
+cudaError_t launch_conv_umma2(const UmmaMaps& maps, const ConvGeom& g, const Umma2Plan& t, const ConvPtrs& p,
+                              int block_n, bool resident, bool pool, int num_sms, cudaStream_t stream);
+
 cudaError_t launch_conv_umma(const UmmaMaps& maps, const ConvGeom& g, const UmmaTiling& t,
                              const ConvPtrs& p, int block_n, int num_sms, cudaStream_t stream);
 cudaError_t launch_conv_direct(const ConvGeom& g, const ConvPtrs& p, cudaStream_t stream);

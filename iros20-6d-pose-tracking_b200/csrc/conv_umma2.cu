@@ -1,0 +1,359 @@
+// conv_umma2: tcgen05 implicit-GEMM convolution, second generation.
+//
+// v1 (conv_umma.cu) pulls one TMA box per (filter tap, 32-channel chunk): every activation patch
+// crosses L2 -> shared memory 9 times and every weight tile once per M tile, and the measured
+// forward is bound by that fill traffic (~11 GB per 64-pair forward), not by the tensor pipe.
+// v2 removes most of it:
+//   * "units": one TMA box per (chunk, filter COLUMN) that is `bh + 2` rows tall.  The three
+//     vertical taps of that column are the same shared-memory tile read through UMMA descriptors
+//     whose start address is advanced by whole pixel rows (bw*128 bytes) -- no data moves.
+//     A fill traffic: 9x -> 3x (+2/11 halo).  The stem does the same over its 7 filter rows with
+//     two units (even / odd input rows), stride-2 convs with six (parity views).
+//   * weights either RESIDENT in shared memory for the whole kernel (64-channel layers and the
+//     stem: the complete K-major matrix is <= 147 KB) or streamed through their own ring.
+//   * the stem's epilogue fuses MaxPool2d(3,2,1): an M tile is an 11x11 block of conv outputs that
+//     yields a 5x5 block of pooled outputs; max -> +bias -> SELU (monotone, so they commute) run
+//     on 1/4.84 of the values and the 88x88x64 intermediate never reaches HBM.
+//   * 8 epilogue warps (two per TMEM lane quadrant).
+// Same tensors, packed weights, tile boxes and epilogue semantics as v1 (see conv_common.h).
+#include "conv_common.h"
+#include "ptx.cuh"
+
+namespace se3tn {
+namespace {
+
+constexpr int kThreads2 = 384;                 // warps: 0 A-TMA, 1 MMA, 2 TMEM alloc, 3 B-TMA, 4..11 epilogue
+constexpr int kAUnitBytes = 21 * 1024;         // (33 + 128) rows * 128 B = 20,608 -> 21 KB, keeps 1 KB alignment
+constexpr int kPoolPitch = 68;                 // floats per staged conv position (64 + 4: bank spread)
+constexpr int kPoolStageBytes = 121 * kPoolPitch * 4;
+
+template <int BN, bool RESIDENT, bool POOL> struct Cfg2 {
+    static constexpr int kBTile = BN * kChunkBytes;
+    static constexpr int kAStages = RESIDENT ? (POOL ? 4 : 3) : (BN == 256 ? 3 : 4);
+    static constexpr int kBStages = RESIDENT ? 0 : (BN == 256 ? 4 : 6);
+    static constexpr int kTmemCols = 2 * BN;
+};
+
+__device__ __forceinline__ float selu_fast(float x) {
+    constexpr float kAlpha = 1.6732632423543772f, kScale = 1.0507009873554805f;
+    return x > 0.f ? kScale * x : (kScale * kAlpha) * (__expf(x) - 1.f);
+}
+
+__device__ __forceinline__ uint64_t desc_rows(uint32_t addr, uint32_t base_off_mode) {
+    // start address may be advanced by whole 128-byte rows (not 1024-aligned)
+    uint64_t d = ptx::umma_desc_sw128(addr);
+    if (base_off_mode == 1) d |= static_cast<uint64_t>((addr >> 7) & 7) << 49;
+    return d;
+}
+
+struct TileCoord2 { int ox, oy, n0, n_tile, grp, tx, ty; };
+
+__device__ __forceinline__ TileCoord2 decode2(int tile, const Umma2Plan& t) {
+    TileCoord2 c;
+    const int m = tile % t.m_tiles;
+    const int rest = tile / t.m_tiles;
+    c.n_tile = rest % t.n_tiles;
+    c.grp = rest / t.n_tiles;
+    c.tx = m % t.tiles_x;
+    const int r2 = m / t.tiles_x;
+    c.ty = r2 % t.tiles_y;
+    c.n0 = t.img_first + (r2 / t.tiles_y) * t.bn;
+    c.ox = c.tx * t.step_x + t.off_x;           // tile origin in A-map coordinates
+    c.oy = c.ty * t.step_y + t.off_y;
+    return c;
+}
+
+template <int BN, bool RESIDENT, bool POOL>
+__global__ void __launch_bounds__(kThreads2, 1)
+conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const Umma2Plan t, const ConvPtrs p)
+{
+    using C = Cfg2<BN, RESIDENT, POOL>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int w_tiles = g.num_taps * t.chunks;                          // K tiles of the weight matrix
+    uint8_t* sA = smem;                                                 // [kAStages][21 KB]
+    uint8_t* sB = sA + C::kAStages * kAUnitBytes;                       // resident: [w_tiles][BN*128]; ring: [kBStages][BN*128]
+    uint8_t* sP = sB + (RESIDENT ? w_tiles : C::kBStages) * C::kBTile;  // pool staging (POOL only): 2 x 121 x 68 floats
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (POOL ? 2 * ((kPoolStageBytes + 1023) & ~1023) : 0));
+    uint64_t* a_full = bars;                       // [kAStages]
+    uint64_t* a_empty = a_full + C::kAStages;      // [kAStages]
+    uint64_t* b_full = a_empty + C::kAStages;      // [max(kBStages,1)]  (resident: b_full[0] = "weights landed")
+    uint64_t* b_empty = b_full + (RESIDENT ? 1 : C::kBStages);
+    uint64_t* tmem_full = b_empty + (RESIDENT ? 1 : C::kBStages);   // [2]
+    uint64_t* tmem_empty = tmem_full + 2;          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int total_tiles = t.m_tiles * t.n_tiles * g.groups;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::kAStages; ++s) { ptx::mbar_init(&a_full[s], 1); ptx::mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < (RESIDENT ? 1 : C::kBStages); ++s) { ptx::mbar_init(&b_full[s], 1); ptx::mbar_init(&b_empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], 8); }
+        ptx::fence_barrier_init();
+        ptx::fence_proxy_async();
+    }
+    if (warp == 2) { ptx::tmem_alloc(tmem_slot, C::kTmemCols); ptx::tmem_relinquish(); }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ============================== A producer ================================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const TileCoord2 tc = decode2(tile, t);
+                const int cbase = g.in_coff + tc.grp * g.cin;
+                for (int ch = 0; ch < t.chunks; ++ch) {
+                    for (int u = 0; u < t.units_per_chunk; ++u) {
+                        const Unit un = t.units[u];
+                        ptx::mbar_wait(&a_empty[stage], phase ^ 1);
+                        ptx::mbar_arrive_expect_tx(&a_full[stage], static_cast<uint32_t>(un.rows) * kChunkBytes);
+                        ptx::tma_load_4d(sA + stage * kAUnitBytes, &maps.a[un.map], &a_full[stage],
+                                         cbase + ch * 32, tc.ox + un.c1, tc.oy + un.c2, tc.n0);
+                        if (++stage == C::kAStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ============================== B producer ================================
+        if (lane == 0) {
+            if (RESIDENT) {
+                // whole K-major weight matrix of this CTA's (only) N tile: loaded once
+                ptx::mbar_arrive_expect_tx(&b_full[0], static_cast<uint32_t>(w_tiles) * C::kBTile);
+                for (int tap = 0; tap < g.num_taps; ++tap)
+                    for (int ch = 0; ch < t.chunks; ++ch)
+                        ptx::tma_load_2d(sB + (tap * t.chunks + ch) * C::kBTile, &maps.b, &b_full[0], tap * g.cin + ch * 32, 0);
+            } else {
+                int stage = 0; uint32_t phase = 0;
+                for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                    const TileCoord2 tc = decode2(tile, t);
+                    const int wrow = tc.grp * g.cout + tc.n_tile * BN;
+                    for (int ch = 0; ch < t.chunks; ++ch)
+                        for (int u = 0; u < t.units_per_chunk; ++u) {
+                            const Unit un = t.units[u];
+                            for (int k = 0; k < un.ntaps; ++k) {
+                                ptx::mbar_wait(&b_empty[stage], phase ^ 1);
+                                ptx::mbar_arrive_expect_tx(&b_full[stage], C::kBTile);
+                                ptx::tma_load_2d(sB + stage * C::kBTile, &maps.b, &b_full[stage], un.taps[k].w_tap * g.cin + ch * 32, wrow);
+                                if (++stage == C::kBStages) { stage = 0; phase ^= 1; }
+                            }
+                        }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ============================== MMA issuer ================================
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::umma_idesc(2 /*tf32*/, kBlockM, BN);
+            int astage = 0; uint32_t aphase = 0;
+            int bstage = 0; uint32_t bphase = 0;
+            if (RESIDENT) { ptx::mbar_wait(&b_full[0], 0); ptx::tc_fence_after(); }
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                uint32_t first = 1;
+                for (int ch = 0; ch < t.chunks; ++ch) {
+                    for (int u = 0; u < t.units_per_chunk; ++u) {
+                        const Unit un = t.units[u];
+                        ptx::mbar_wait(&a_full[astage], aphase);
+                        ptx::tc_fence_after();
+                        const uint32_t a_base = ptx::smem_u32(sA + astage * kAUnitBytes);
+                        for (int k = 0; k < un.ntaps; ++k) {
+                            uint32_t b_addr;
+                            if (RESIDENT) {
+                                b_addr = ptx::smem_u32(sB + (un.taps[k].w_tap * t.chunks + ch) * C::kBTile);
+                            } else {
+                                ptx::mbar_wait(&b_full[bstage], bphase);
+                                ptx::tc_fence_after();
+                                b_addr = ptx::smem_u32(sB + bstage * C::kBTile);
+                            }
+                            const uint32_t a_addr = a_base + static_cast<uint32_t>(un.taps[k].row_shift) * kChunkBytes;
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {
+                                ptx::umma_tf32(d_tmem, desc_rows(a_addr + kk * 32, t.base_off_mode), ptx::umma_desc_sw128(b_addr + kk * 32),
+                                               idesc, first ? 0u : 1u);
+                                first = 0;
+                            }
+                            if (!RESIDENT) {
+                                ptx::umma_commit(&b_empty[bstage]);
+                                if (++bstage == C::kBStages) { bstage = 0; bphase ^= 1; }
+                            }
+                        }
+                        ptx::umma_commit(&a_empty[astage]);
+                        if (++astage == C::kAStages) { astage = 0; aphase ^= 1; }
+                    }
+                }
+                ptx::umma_commit(&tmem_full[acc]);
+            }
+        }
+    } else if (warp >= 4) {
+        // ============================== epilogue (8 warps) ==========================
+        const int ew = warp - 4;
+        const int q = ew & 3;                       // TMEM lane quadrant (== warp % 4)
+        const int half = ew >> 2;                   // which half of the BN columns
+        constexpr int kCols = BN / 2;
+        const int row = q * 32 + lane;
+        int it = 0;
+        if (!POOL) {
+            const int box = t.bw * t.bh;
+            const int pn = row / box;
+            const int rem = row - pn * box;
+            const int py = rem / t.bw;
+            const int px = rem - py * t.bw;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                const TileCoord2 tc = decode2(tile, t);
+                const int n = tc.n0 + pn, y = tc.ty * t.bh + py, x = tc.tx * t.bw + px;
+                const bool valid = (pn < t.bn) && (n < g.n_img) && (y < g.Ho) && (x < g.Wo);
+                const size_t pix = (static_cast<size_t>(n) * g.Ho + y) * g.Wo + x;
+                const int ch0 = tc.grp * g.cout + tc.n_tile * BN + half * kCols;
+                float* outp = p.out + pix * g.out_cstride + g.out_coff + ch0;
+                const float* resp = p.res ? p.res + pix * g.res_cstride + g.res_coff + ch0 : nullptr;
+                const float* biasp = p.bias + ch0;
+
+                ptx::mbar_wait(&tmem_full[acc], acc_phase);
+                ptx::tc_fence_after();
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + half * kCols;
+#pragma unroll 1
+                for (int c0 = 0; c0 < kCols; c0 += 32) {
+                    uint32_t r0[16], r1[16];
+                    ptx::tmem_ld16(taddr + c0, r0);
+                    ptx::tmem_ld16(taddr + c0 + 16, r1);
+                    ptx::tmem_ld_wait();
+                    if (valid) {
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            const uint32_t* r = hh ? r1 : r0;
+                            const int cc = c0 + hh * 16;
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(biasp + cc + j));
+                                float v0 = __uint_as_float(r[j]) + b4.x, v1 = __uint_as_float(r[j + 1]) + b4.y;
+                                float v2 = __uint_as_float(r[j + 2]) + b4.z, v3 = __uint_as_float(r[j + 3]) + b4.w;
+                                if (resp) {
+                                    const float4 r4 = __ldg(reinterpret_cast<const float4*>(resp + cc + j));
+                                    v0 += r4.x; v1 += r4.y; v2 += r4.z; v3 += r4.w;
+                                }
+                                if (g.act == ACT_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+                                else if (g.act == ACT_SELU) { v0 = selu_fast(v0); v1 = selu_fast(v1); v2 = selu_fast(v2); v3 = selu_fast(v3); }
+                                if (g.round_tf32) { v0 = ptx::to_tf32(v0); v1 = ptx::to_tf32(v1); v2 = ptx::to_tf32(v2); v3 = ptx::to_tf32(v3); }
+                                *reinterpret_cast<float4*>(outp + cc + j) = make_float4(v0, v1, v2, v3);
+                            }
+                        }
+                    }
+                }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+            }
+        } else {
+            // ---- stem: conv tile 11x11 -> 5x5 max-pooled outputs (MaxPool2d(3,2,1), -inf padding) ----
+            const int cy_l = row / 11, cx_l = row - cy_l * 11;          // conv position inside the tile
+            const int et = threadIdx.x - 128;                           // 0..255 among epilogue threads
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                const TileCoord2 tc = decode2(tile, t);
+                float* stage = reinterpret_cast<float*>(sP + (it & 1) * ((kPoolStageBytes + 1023) & ~1023));
+                const int cy = tc.oy + cy_l, cx = tc.ox + cx_l;             // conv output coordinates
+                const bool cvalid = (row < 121) && cy >= 0 && cy < 88 && cx >= 0 && cx < 88;
+
+                ptx::mbar_wait(&tmem_full[acc], acc_phase);
+                ptx::tc_fence_after();
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + half * kCols;
+                {
+                    uint32_t r0[16], r1[16];
+                    ptx::tmem_ld16(taddr, r0);
+                    ptx::tmem_ld16(taddr + 16, r1);
+                    ptx::tmem_ld_wait();
+                    if (row < 121) {
+                        float* srow = stage + row * kPoolPitch + half * kCols;
+                        const float ninf = -3.0e38f;
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            *reinterpret_cast<float4*>(srow + j) = cvalid ? make_float4(__uint_as_float(r0[j]), __uint_as_float(r0[j + 1]), __uint_as_float(r0[j + 2]), __uint_as_float(r0[j + 3]))
+                                                                          : make_float4(ninf, ninf, ninf, ninf);
+                            *reinterpret_cast<float4*>(srow + 16 + j) = cvalid ? make_float4(__uint_as_float(r1[j]), __uint_as_float(r1[j + 1]), __uint_as_float(r1[j + 2]), __uint_as_float(r1[j + 3]))
+                                                                               : make_float4(ninf, ninf, ninf, ninf);
+                        }
+                    }
+                }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);          // accumulator drained
+                asm volatile("bar.sync 1, 256;" ::: "memory");             // staging tile complete (epilogue warps only)
+
+                // 25 pooled pixels x 16 float4 channel groups = 400 vectors over 256 threads
+                for (int v = et; v < 400; v += 256) {
+                    const int pp = v >> 4, c4 = (v & 15) * 4;
+                    const int ppy = pp / 5, ppx = pp - ppy * 5;
+                    const int oy = tc.ty * 5 + ppy, ox = tc.tx * 5 + ppx;     // pooled output coordinates
+                    if (oy >= g.Ho || ox >= g.Wo) continue;
+                    float4 m = make_float4(-3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f);
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) {
+                            const float4 s4 = *reinterpret_cast<const float4*>(stage + ((2 * ppy + dy) * 11 + 2 * ppx + dx) * kPoolPitch + c4);
+                            m.x = fmaxf(m.x, s4.x); m.y = fmaxf(m.y, s4.y); m.z = fmaxf(m.z, s4.z); m.w = fmaxf(m.w, s4.w);
+                        }
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c4));
+                    float v0 = selu_fast(m.x + b4.x), v1 = selu_fast(m.y + b4.y), v2 = selu_fast(m.z + b4.z), v3 = selu_fast(m.w + b4.w);
+                    if (g.round_tf32) { v0 = ptx::to_tf32(v0); v1 = ptx::to_tf32(v1); v2 = ptx::to_tf32(v2); v3 = ptx::to_tf32(v3); }
+                    const int n = tc.n0;
+                    if (n < g.n_img)
+                        *reinterpret_cast<float4*>(p.out + ((static_cast<size_t>(n) * g.Ho + oy) * g.Wo + ox) * g.out_cstride + g.out_coff + c4) = make_float4(v0, v1, v2, v3);
+                }
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, C::kTmemCols); }
+}
+
+template <int BN, bool RESIDENT, bool POOL>
+cudaError_t launch2(const UmmaMaps& maps, const ConvGeom& g, const Umma2Plan& t, const ConvPtrs& p, int num_sms, cudaStream_t stream) {
+    using C = Cfg2<BN, RESIDENT, POOL>;
+    const int w_tiles = g.num_taps * t.chunks;
+    const size_t smem = static_cast<size_t>(C::kAStages) * kAUnitBytes + static_cast<size_t>(RESIDENT ? w_tiles : C::kBStages) * C::kBTile +
+                        (POOL ? 2 * ((kPoolStageBytes + 1023) & ~1023) : 0) + 1024 + 512;
+    if (smem > 232448) return cudaErrorInvalidConfiguration;
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        cudaError_t e = cudaFuncSetAttribute(conv_umma2_kernel<BN, RESIDENT, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+        attr_smem = smem;
+    }
+    const int total = t.m_tiles * t.n_tiles * g.groups;
+    const int grid = total < num_sms ? total : num_sms;
+    conv_umma2_kernel<BN, RESIDENT, POOL><<<grid, kThreads2, smem, stream>>>(maps, g, t, p);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_conv_umma2(const UmmaMaps& maps, const ConvGeom& g, const Umma2Plan& t, const ConvPtrs& p,
+                              int block_n, bool resident, bool pool, int num_sms, cudaStream_t stream) {
+    if (pool) return (block_n == 64 && resident) ? launch2<64, true, true>(maps, g, t, p, num_sms, stream) : cudaErrorInvalidValue;
+    if (resident) return block_n == 64 ? launch2<64, true, false>(maps, g, t, p, num_sms, stream) : cudaErrorInvalidValue;
+    switch (block_n) {
+        case 64:  return launch2<64, false, false>(maps, g, t, p, num_sms, stream);
+        case 128: return launch2<128, false, false>(maps, g, t, p, num_sms, stream);
+        case 256: return launch2<256, false, false>(maps, g, t, p, num_sms, stream);
+        default:  return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace se3tn

@@ -103,6 +103,9 @@ struct se3tn_ctx {
     uint8_t* workspace = nullptr;
     float* buf[B_COUNT] = {};
     CUtensorMap amap[14][7];
+    CUtensorMap amap2[14][4];        // v2 kernel: boxes extended vertically (one per filter column / parity view)
+    int conv_version = 2;            // SE3TN_CONV=1 selects the first-generation kernel
+    int base_off_mode = 0;           // SE3TN_BASE_OFF: UMMA descriptor base_offset convention for row-shifted starts
     EncodeTiledFn encode = nullptr;
     std::map<int, WeightSet> weights;
     // device copies of per-set stats, rebuilt when a set changes: [max_id+1][8]
@@ -235,6 +238,94 @@ int build_activation_maps(se3tn_ctx* c) {
     return SE3TN_OK;
 }
 
+// v2 activation maps: same tensors, boxes extended by the vertical filter extent so that the
+// vertical taps become descriptor row shifts inside one shared-memory tile (conv_umma2.cu).
+int build_activation_maps_v2(se3tn_ctx* c) {
+    const cuuint64_t N = static_cast<cuuint64_t>(c->max_batch);
+    for (int li = 0; li < 14; ++li) {
+        const LayerSpec& L = kLayers[li];
+        const float* base = c->buf[L.in];
+        char what[64];
+        if (L.kind == K_STEM) {
+            // even / odd input-row views of the zero-padded NHWC4 stem input; x is the overlapping
+            // 8-pixel window view (stride 2 pixels = 32 B, extent 128 B)
+            const cuuint64_t rowpitch = static_cast<cuuint64_t>(kStemW) * 4 * sizeof(float);
+            const cuuint64_t strides[3] = {8 * sizeof(float), 2 * rowpitch, static_cast<cuuint64_t>(kStemH) * rowpitch};
+            for (int odd = 0; odd < 2; ++odd) {
+                const cuuint64_t dims[4] = {32, 88, odd ? 90u : 91u, N};
+                const cuuint32_t box[4] = {32, 11, odd ? 13u : 14u, 1};
+                snprintf(what, sizeof what, "v2 layer %d stem %s rows", li, odd ? "odd" : "even");
+                int rc = make_map4(c, &c->amap2[li][odd], reinterpret_cast<const uint8_t*>(base) + odd * rowpitch, dims, strides, box,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, what);
+                if (rc) return rc;
+            }
+        } else if (L.kind == K_S1) {
+            const cuuint64_t C = L.in_c, W = L.Win, H = L.Hin;
+            const cuuint64_t dims[4] = {C, W, H, N};
+            const cuuint64_t strides[3] = {C * 4, W * C * 4, H * W * C * 4};
+            const cuuint32_t box[4] = {32, 11, 13, 1};
+            snprintf(what, sizeof what, "v2 layer %d s1", li);
+            int rc = make_map4(c, &c->amap2[li][0], base, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, what);
+            if (rc) return rc;
+        } else {
+            const cuuint64_t C = L.in_c, W = L.Win, H = L.Hin;
+            const cuuint64_t dims[4] = {C, W / 2, H / 2, N};
+            const cuuint64_t strides[3] = {2 * C * 4, 2 * W * C * 4, H * W * C * 4};
+            for (int py = 0; py < 2; ++py)
+                for (int px = 0; px < 2; ++px) {
+                    const cuuint32_t box[4] = {32, 11, py ? 12u : 11u, 1};
+                    snprintf(what, sizeof what, "v2 layer %d s2 parity %d%d", li, py, px);
+                    int rc = make_map4(c, &c->amap2[li][py * 2 + px], base + (static_cast<size_t>(py) * W + px) * C, dims, strides, box,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, what);
+                    if (rc) return rc;
+                }
+        }
+    }
+    return SE3TN_OK;
+}
+
+void fill_plan2(const se3tn_ctx* c, const LayerSpec& L, int first, int n, int block_n, Umma2Plan& t) {
+    memset(&t, 0, sizeof t);
+    t.chunks = L.cin / 32;
+    t.bw = 11; t.bh = 11; t.bn = 1;
+    t.img_first = first;
+    t.base_off_mode = c->base_off_mode;
+    t.n_tiles = L.cout / block_n;
+    const int Ho = layer_Ho(L);
+    if (L.kind == K_STEM) {
+        // pooled tile: 11x11 conv outputs starting at (2*5*ty - 1, 2*5*tx - 1) -> 5x5 pooled outputs
+        t.units_per_chunk = 2;
+        Unit& e = t.units[0]; e.map = 0; e.c1 = 0; e.c2 = 0; e.ntaps = 4; e.rows = 11 * 14;
+        for (int j = 0; j < 4; ++j) { e.taps[j].row_shift = (int8_t)(j * 11); e.taps[j].w_tap = (int8_t)(2 * j); }
+        Unit& o = t.units[1]; o.map = 1; o.c1 = 0; o.c2 = 0; o.ntaps = 3; o.rows = 11 * 13;
+        for (int j = 0; j < 3; ++j) { o.taps[j].row_shift = (int8_t)(j * 11); o.taps[j].w_tap = (int8_t)(2 * j + 1); }
+        t.step_x = t.step_y = 10; t.off_x = t.off_y = -1;
+        t.tiles_x = t.tiles_y = 9;
+    } else if (L.kind == K_S1) {
+        t.units_per_chunk = 3;
+        for (int s2 = 0; s2 < 3; ++s2) {
+            Unit& u = t.units[s2]; u.map = 0; u.c1 = (int8_t)(s2 - 1); u.c2 = -1; u.ntaps = 3; u.rows = 11 * 13;
+            for (int r = 0; r < 3; ++r) { u.taps[r].row_shift = (int8_t)(r * 11); u.taps[r].w_tap = (int8_t)(r * 3 + s2); }
+        }
+        t.step_x = t.step_y = 11; t.off_x = t.off_y = 0;
+        t.tiles_x = t.tiles_y = Ho / 11;
+    } else {
+        t.units_per_chunk = 6;
+        for (int s2 = 0; s2 < 3; ++s2) {
+            const int px = (s2 == 1) ? 0 : 1;
+            const int c1 = (s2 == 0) ? -1 : 0;
+            Unit& ev = t.units[s2 * 2]; ev.map = (int8_t)(0 * 2 + px); ev.c1 = (int8_t)c1; ev.c2 = 0; ev.ntaps = 1; ev.rows = 11 * 11;
+            ev.taps[0].row_shift = 0; ev.taps[0].w_tap = (int8_t)(1 * 3 + s2);
+            Unit& od = t.units[s2 * 2 + 1]; od.map = (int8_t)(1 * 2 + px); od.c1 = (int8_t)c1; od.c2 = -1; od.ntaps = 2; od.rows = 11 * 12;
+            od.taps[0].row_shift = 0;  od.taps[0].w_tap = (int8_t)(0 * 3 + s2);
+            od.taps[1].row_shift = 11; od.taps[1].w_tap = (int8_t)(2 * 3 + s2);
+        }
+        t.step_x = t.step_y = 11; t.off_x = t.off_y = 0;
+        t.tiles_x = t.tiles_y = Ho / 11;
+    }
+    t.m_tiles = n * t.tiles_x * t.tiles_y;
+}
+
 void fill_geom(const LayerSpec& L, int n, bool round_tf32, ConvGeom& g) {
     memset(&g, 0, sizeof g);
     g.Hin = L.Hin; g.Win = L.Win; g.in_cstride = L.in_c; g.in_coff = 0;
@@ -324,6 +415,26 @@ int run_network(se3tn_ctx* c, int weight_id, int first, int n, int precision,
         ConvPtrs p;
         p.in = bufp(L.in); p.out = bufp(L.out); p.res = (L.res != NONE) ? bufp(L.res) : nullptr;
         p.w = wbase + ws.w_off[li]; p.bias = ws.dev + ws.b_off[li];
+        if (tf32 && c->conv_version == 2) {
+            UmmaMaps maps;
+            const int nmaps = (L.kind == K_STEM) ? 2 : (L.kind == K_S2 ? 4 : 1);
+            for (int m = 0; m < 7; ++m) maps.a[m] = c->amap2[li][m < nmaps ? m : 0];
+            maps.b = ws.bmap[li];
+            const int BN = block_n_of(c, L);
+            const bool pool = (L.kind == K_STEM);
+            const bool resident = (BN == 64 && L.cout == 64);
+            Umma2Plan t; fill_plan2(c, L, first, n, BN, t);
+            g.n_img = first + n;                       // absolute image indices (TMA maps address image 0)
+            p.out = c->buf[L.out]; p.res = (L.res != NONE) ? c->buf[L.res] : nullptr;
+            if (pool) {                                // fused MaxPool2d(3,2,1): write the pooled tensor directly
+                g.Ho = g.Wo = 44;
+                p.out = c->buf[li == 0 ? B_P1A : B_P1B];
+                g.out_cstride = 64; g.out_coff = 0;
+            }
+            { ProfScope ps(c, li, s); CU_TRY(c, launch_conv_umma2(maps, g, t, p, BN, resident, pool, c->num_sms, s)); }
+            ++c->launches;
+            continue;
+        }
         if (tf32) {
             UmmaMaps maps;
             const int nmaps = (L.kind == K_STEM) ? 7 : (L.kind == K_S2 ? 4 : 1);
@@ -385,6 +496,8 @@ int se3tn_create(int device, int max_batch, void* workspace, se3tn_ctx** out) {
     se3tn_ctx* c = new se3tn_ctx();
     c->device = device; c->max_batch = max_batch; c->num_sms = prop.multiProcessorCount;
     if (const char* ov = getenv("SE3TN_BLOCK_N")) c->umma_block_n_override = atoi(ov);
+    if (const char* ov = getenv("SE3TN_CONV")) c->conv_version = atoi(ov) == 1 ? 1 : 2;
+    if (const char* ov = getenv("SE3TN_BASE_OFF")) c->base_off_mode = atoi(ov);
 
     void* fn = nullptr; cudaDriverEntryPointQueryResult qres;
     e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -411,6 +524,7 @@ int se3tn_create(int device, int max_batch, void* workspace, se3tn_ctx** out) {
         p += (kBufFloats[b] * static_cast<size_t>(max_batch) + 255) & ~size_t(255);
     }
     int rc = build_activation_maps(c);
+    if (!rc) rc = build_activation_maps_v2(c);
     if (rc) { g_create_error = c->err; se3tn_destroy(c); return rc; }
     *out = c;
     return SE3TN_OK;
