@@ -39,13 +39,6 @@ __device__ __forceinline__ float selu_fast(float x) {
     return x > 0.f ? kScale * x : (kScale * kAlpha) * (__expf(x) - 1.f);
 }
 
-__device__ __forceinline__ uint64_t desc_rows(uint32_t addr, uint32_t base_off_mode) {
-    // start address may be advanced by whole 128-byte rows (not 1024-aligned)
-    uint64_t d = ptx::umma_desc_sw128(addr);
-    if (base_off_mode == 1) d |= static_cast<uint64_t>((addr >> 7) & 7) << 49;
-    return d;
-}
-
 struct TileCoord2 { int ox, oy, n0, n_tile, grp, tx, ty; };
 
 __device__ __forceinline__ TileCoord2 decode2(int tile, const Umma2Plan& t) {
@@ -148,52 +141,63 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
         }
     } else if (warp == 1) {
         // ============================== MMA issuer ================================
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::umma_idesc(2 /*tf32*/, kBlockM, BN);
-            int astage = 0; uint32_t aphase = 0;
-            int bstage = 0; uint32_t bphase = 0;
-            if (RESIDENT) { ptx::mbar_wait(&b_full[0], 0); ptx::tc_fence_after(); }
-            int it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-                const int acc = it & 1;
-                const uint32_t acc_phase = (it >> 1) & 1;
-                ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-                ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
-                uint32_t first = 1;
-                for (int ch = 0; ch < t.chunks; ++ch) {
-                    for (int u = 0; u < t.units_per_chunk; ++u) {
-                        const Unit un = t.units[u];
-                        ptx::mbar_wait(&a_full[astage], aphase);
-                        ptx::tc_fence_after();
-                        const uint32_t a_base = ptx::smem_u32(sA + astage * kAUnitBytes);
-                        for (int k = 0; k < un.ntaps; ++k) {
-                            uint32_t b_addr;
-                            if (RESIDENT) {
-                                b_addr = ptx::smem_u32(sB + (un.taps[k].w_tap * t.chunks + ch) * C::kBTile);
-                            } else {
-                                ptx::mbar_wait(&b_full[bstage], bphase);
-                                ptx::tc_fence_after();
-                                b_addr = ptx::smem_u32(sB + bstage * C::kBTile);
-                            }
-                            const uint32_t a_addr = a_base + static_cast<uint32_t>(un.taps[k].row_shift) * kChunkBytes;
+        // The WHOLE warp walks the loop (warp-uniform control flow lets ptxas keep descriptors and
+        // barrier addresses in uniform registers); one elected lane issues the tcgen05 instructions.
+        constexpr uint32_t idesc = ptx::umma_idesc(2 /*tf32*/, kBlockM, BN);
+        // descriptor high word: SBO = 1024 B (>>4) | version 1 (bit 46) | SWIZZLE_128B (bits 61..63)
+        constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+        int astage = 0; uint32_t aphase = 0;
+        int bstage = 0; uint32_t bphase = 0;
+        if (RESIDENT) { ptx::mbar_wait(&b_full[0], 0); ptx::tc_fence_after(); }
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            uint32_t accumulate = 0;
+            for (int ch = 0; ch < t.chunks; ++ch) {
+                for (int u = 0; u < t.units_per_chunk; ++u) {
+                    const int ntaps = t.units[u].ntaps;
+                    ptx::mbar_wait(&a_full[astage], aphase);
+                    ptx::tc_fence_after();
+                    const uint32_t a_base = ptx::smem_u32(sA + astage * kAUnitBytes);
+                    for (int k = 0; k < ntaps; ++k) {
+                        const int w_tap = t.units[u].taps[k].w_tap;
+                        const uint32_t row_shift = static_cast<uint32_t>(t.units[u].taps[k].row_shift);
+                        uint32_t b_addr;
+                        if (RESIDENT) {
+                            b_addr = ptx::smem_u32(sB + (w_tap * t.chunks + ch) * C::kBTile);
+                        } else {
+                            ptx::mbar_wait(&b_full[bstage], bphase);
+                            ptx::tc_fence_after();
+                            b_addr = ptx::smem_u32(sB + bstage * C::kBTile);
+                        }
+                        // low words: (addr >> 4) | LBO(=1) << 16; +2 per 32-byte K step.  base_offset stays 0:
+                        // the 128B swizzle is a function of absolute smem address bits (profiles/r01_umma_desc_rowshift_probe.txt)
+                        const uint32_t a_lo = (((a_base + row_shift * kChunkBytes) & 0x3FFFFu) >> 4) | (1u << 16);
+                        const uint32_t b_lo = ((b_addr & 0x3FFFFu) >> 4) | (1u << 16);
+                        if (ptx::elect_one()) {
 #pragma unroll
                             for (int kk = 0; kk < 4; ++kk) {
-                                ptx::umma_tf32(d_tmem, desc_rows(a_addr + kk * 32, t.base_off_mode), ptx::umma_desc_sw128(b_addr + kk * 32),
-                                               idesc, first ? 0u : 1u);
-                                first = 0;
+                                const uint64_t ad = (static_cast<uint64_t>(kDescHi) << 32) | (a_lo + 2 * kk);
+                                const uint64_t bd = (static_cast<uint64_t>(kDescHi) << 32) | (b_lo + 2 * kk);
+                                ptx::umma_tf32(d_tmem, ad, bd, idesc, accumulate | (kk != 0));
                             }
-                            if (!RESIDENT) {
-                                ptx::umma_commit(&b_empty[bstage]);
-                                if (++bstage == C::kBStages) { bstage = 0; bphase ^= 1; }
-                            }
+                            if (!RESIDENT) ptx::umma_commit(&b_empty[bstage]);
                         }
-                        ptx::umma_commit(&a_empty[astage]);
-                        if (++astage == C::kAStages) { astage = 0; aphase ^= 1; }
+                        __syncwarp();
+                        accumulate = 1;
+                        if (!RESIDENT) { if (++bstage == C::kBStages) { bstage = 0; bphase ^= 1; } }
                     }
+                    if (ptx::elect_one()) ptx::umma_commit(&a_empty[astage]);
+                    __syncwarp();
+                    if (++astage == C::kAStages) { astage = 0; aphase ^= 1; }
                 }
-                ptx::umma_commit(&tmem_full[acc]);
             }
+            if (ptx::elect_one()) ptx::umma_commit(&tmem_full[acc]);
+            __syncwarp();
         }
     } else if (warp >= 4) {
         // ============================== epilogue (8 warps) ==========================

@@ -72,7 +72,7 @@ try:
     n = 6
     rgb, depth = synth.raw_frame(0)
     poses = synth.raw_poses(n, seed=0)
-    poses[1, :3, 3] = (-0.28, -0.2, 0.5)          # clipped window
+    poses[1, :3, 3] = (-0.13, -0.1, 0.5)          # clipped window
     rgbA, depthA = synth.rendered_views(n, poses, seed=2)
     mean, std = synth.default_mean_std()
     eng.set_stats(mean, std, 0)

@@ -59,10 +59,11 @@ def test_config1_parity_gate(pkg, synth, golden_dir, eng):
     pose = synth.config1_pose()
     dev = eng.device
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)[None]).to(dev)
-    tA, tB = eng.normalize(t(rgbA), t(depthA), t(rgbB), t(depthB), torch.from_numpy(pose[None]).to(dev))
-    assert sha(tA[0].cpu().numpy()) == str(g['c1_dataA_sha']) and sha(tB[0].cpu().numpy()) == str(g['c1_dataB_sha'])
     ref = torch.from_numpy(np.concatenate([g['c1_trans'], g['c1_rot']], 1))
     for prec, (rt, at) in {'tf32': (RTOL, ATOL), 'fp32': (1e-4, 2e-6)}.items():
+        # `precision` also selects whether the conv-input buffers hold tf32-rounded values
+        tA, tB = eng.normalize(t(rgbA), t(depthA), t(rgbB), t(depthB), torch.from_numpy(pose[None]).to(dev), precision=prec)
+        assert sha(tA[0].cpu().numpy()) == str(g['c1_dataA_sha']) and sha(tB[0].cpu().numpy()) == str(g['c1_dataB_sha'])
         trans, rot, _ = eng.forward_preprocessed(1, weight_id=0, precision=prec)
         assert_gate(six(trans, rot), ref, rt, at)
         pose_out = eng.pose_update(torch.from_numpy(pose[None]).to(dev), trans, rot, 0.03, 5 * np.pi / 180)[0].cpu().numpy()
