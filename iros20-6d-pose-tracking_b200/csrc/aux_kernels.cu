@@ -56,9 +56,21 @@ preprocess_kernel(PreprocessArgs a)
 {
     const int n = blockIdx.y;
     const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    const double* pose = a.poses + n * 16;
+    // the crop window and cv2's inverse scales are per track: one thread computes them for the block
+    __shared__ int s_win[4];
+    __shared__ double s_inv[2];
+    if (threadIdx.x == 0 && !a.b_precropped) {
+        int top, left, ch, cw;
+        bbox_window(pose, a.fx, a.fy, a.cx, a.cy, a.object_width[n], 1000.0, 1000.0, 1000.0, top, left, ch, cw);
+        s_win[0] = top; s_win[1] = left; s_win[2] = ch; s_win[3] = cw;
+        // cv2 resizeNN index: floor(dst * ifx), ifx = 1/(dsize/ssize) in double, clamped to ssize-1
+        s_inv[0] = (cw > 0) ? 1.0 / (static_cast<double>(kImg) / cw) : 0.0;
+        s_inv[1] = (ch > 0) ? 1.0 / (static_cast<double>(kImg) / ch) : 0.0;
+    }
+    __syncthreads();
     if (pix >= kImg * kImg) return;
     const int y = pix / kImg, x = pix - y * kImg;
-    const double* pose = a.poses + n * 16;
     const double z = pose[11];
     const bool gl = z < 0;
     const double z1000 = __dmul_rn(z, 1000.0);
@@ -72,14 +84,10 @@ preprocess_kernel(PreprocessArgs a)
         r = pr[0]; gch = pr[1]; b = pr[2];
         d = a.frame_depth[bo];
     } else {
-        int top, left, ch, cw;
-        bbox_window(pose, a.fx, a.fy, a.cx, a.cy, a.object_width[n], 1000.0, 1000.0, 1000.0, top, left, ch, cw);
+        const int top = s_win[0], left = s_win[1], ch = s_win[2], cw = s_win[3];
         if (ch > 0 && cw > 0) {
-            // cv2 resizeNN index: floor(dst * ifx), ifx = 1/(dsize/ssize) in double, clamped to ssize-1
-            const double ifx = 1.0 / (static_cast<double>(kImg) / cw);
-            const double ify = 1.0 / (static_cast<double>(kImg) / ch);
-            int sx = static_cast<int>(floor(x * ifx)); if (sx > cw - 1) sx = cw - 1;
-            int sy = static_cast<int>(floor(y * ify)); if (sy > ch - 1) sy = ch - 1;
+            int sx = static_cast<int>(floor(x * s_inv[0])); if (sx > cw - 1) sx = cw - 1;
+            int sy = static_cast<int>(floor(y * s_inv[1])); if (sy > ch - 1) sy = ch - 1;
             const int fy_ = top + sy, fx_ = left + sx;
             if (fy_ >= 0 && fy_ < a.H && fx_ >= 0 && fx_ < a.W) {
                 const size_t fo = static_cast<size_t>(fy_) * a.W + fx_;

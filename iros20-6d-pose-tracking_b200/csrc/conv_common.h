@@ -91,7 +91,7 @@ struct Umma2Plan {
 };
 
 cudaError_t launch_conv_umma2(const UmmaMaps& maps, const ConvGeom& g, const Umma2Plan& t, const ConvPtrs& p,
-                              int block_n, bool resident, bool pool, int num_sms, cudaStream_t stream);
+                              int block_n, bool resident, bool pool, int m_per_cta, int num_sms, cudaStream_t stream);
 
 cudaError_t launch_conv_umma(const UmmaMaps& maps, const ConvGeom& g, const UmmaTiling& t,
                              const ConvPtrs& p, int block_n, int num_sms, cudaStream_t stream);

@@ -15,6 +15,10 @@
 //     yields a 5x5 block of pooled outputs; max -> +bias -> SELU (monotone, so they commute) run
 //     on 1/4.84 of the values and the 88x88x64 intermediate never reaches HBM.
 //   * 8 epilogue warps (two per TMEM lane quadrant).
+//   * MT = 2 ("dual-M", BN = 256 layers): one CTA carries TWO M tiles (two accumulators, all 512
+//     TMEM columns) through the K loop, so every weight tile fetched from L2 feeds 8 MMAs instead
+//     of 4 -- the weight stream, which is >80% of the fill traffic of the deep layers, halves.
+//     At batch 64 each deep layer is exactly 128 work units: one wave on 148 SMs.
 // Same tensors, packed weights, tile boxes and epilogue semantics as v1 (see conv_common.h).
 #include "conv_common.h"
 #include "ptx.cuh"
@@ -23,15 +27,18 @@ namespace se3tn {
 namespace {
 
 constexpr int kThreads2 = 384;                 // warps: 0 A-TMA, 1 MMA, 2 TMEM alloc, 3 B-TMA, 4..11 epilogue
-constexpr int kAUnitBytes = 21 * 1024;         // (33 + 128) rows * 128 B = 20,608 -> 21 KB, keeps 1 KB alignment
+// A unit buffer: (max row shift + 128) rows * 128 B, rounded to 1 KB: stem 33+128 rows -> 21 KB, 3x3 22+128 -> 20 KB
 constexpr int kPoolPitch = 68;                 // floats per staged conv position (64 + 4: bank spread)
 constexpr int kPoolStageBytes = 121 * kPoolPitch * 4;
 
-template <int BN, bool RESIDENT, bool POOL> struct Cfg2 {
+template <int BN, bool RESIDENT, bool POOL, int MT> struct Cfg2 {
     static constexpr int kBTile = BN * kChunkBytes;
+    static constexpr int kAUnit = POOL ? 21 * 1024 : 20 * 1024;
+    static constexpr int kAStage = MT * kAUnit;
     static constexpr int kAStages = RESIDENT ? (POOL ? 4 : 3) : (BN == 256 ? 3 : 4);
-    static constexpr int kBStages = RESIDENT ? 0 : (BN == 256 ? 4 : 6);
-    static constexpr int kTmemCols = 2 * BN;
+    static constexpr int kBStages = RESIDENT ? 0 : (BN == 256 ? (MT == 2 ? 3 : 4) : 6);
+    static constexpr int kNAcc = (2 * MT * BN <= 512) ? 2 : 1;         // accumulator sets (double-buffered when they fit)
+    static constexpr int kTmemCols = kNAcc * MT * BN;                   // 128 / 256 / 512
 };
 
 __device__ __forceinline__ float selu_fast(float x) {
@@ -39,14 +46,20 @@ __device__ __forceinline__ float selu_fast(float x) {
     return x > 0.f ? kScale * x : (kScale * kAlpha) * (__expf(x) - 1.f);
 }
 
-struct TileCoord2 { int ox, oy, n0, n_tile, grp, tx, ty; };
+struct TileCoord2 { int ox, oy, n0, tx, ty; };
+struct WorkUnit { int mp, n_tile, grp; };
 
-__device__ __forceinline__ TileCoord2 decode2(int tile, const Umma2Plan& t) {
+__device__ __forceinline__ WorkUnit decode_work(int w, int m_units, const Umma2Plan& t) {
+    WorkUnit u;
+    u.mp = w % m_units;
+    const int rest = w / m_units;
+    u.n_tile = rest % t.n_tiles;
+    u.grp = rest / t.n_tiles;
+    return u;
+}
+
+__device__ __forceinline__ TileCoord2 decode2(int m, const Umma2Plan& t) {
     TileCoord2 c;
-    const int m = tile % t.m_tiles;
-    const int rest = tile / t.m_tiles;
-    c.n_tile = rest % t.n_tiles;
-    c.grp = rest / t.n_tiles;
     c.tx = m % t.tiles_x;
     const int r2 = m / t.tiles_x;
     c.ty = r2 % t.tiles_y;
@@ -56,16 +69,17 @@ __device__ __forceinline__ TileCoord2 decode2(int tile, const Umma2Plan& t) {
     return c;
 }
 
-template <int BN, bool RESIDENT, bool POOL>
+template <int BN, bool RESIDENT, bool POOL, int MT>
 __global__ void __launch_bounds__(kThreads2, 1)
 conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const Umma2Plan t, const ConvPtrs p)
 {
-    using C = Cfg2<BN, RESIDENT, POOL>;
+    using C = Cfg2<BN, RESIDENT, POOL, MT>;
+    static_assert(!(POOL && MT != 1), "pool epilogue is single-tile");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int w_tiles = g.num_taps * t.chunks;                          // K tiles of the weight matrix
-    uint8_t* sA = smem;                                                 // [kAStages][21 KB]
-    uint8_t* sB = sA + C::kAStages * kAUnitBytes;                       // resident: [w_tiles][BN*128]; ring: [kBStages][BN*128]
+    uint8_t* sA = smem;                                                 // [kAStages][MT][unit]
+    uint8_t* sB = sA + C::kAStages * C::kAStage;                       // resident: [w_tiles][BN*128]; ring: [kBStages][BN*128]
     uint8_t* sP = sB + (RESIDENT ? w_tiles : C::kBStages) * C::kBTile;  // pool staging (POOL only): 2 x 121 x 68 floats
     uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (POOL ? 2 * ((kPoolStageBytes + 1023) & ~1023) : 0));
     uint64_t* a_full = bars;                       // [kAStages]
@@ -78,12 +92,13 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int total_tiles = t.m_tiles * t.n_tiles * g.groups;
+    const int m_units = (t.m_tiles + MT - 1) / MT;
+    const int total_tiles = m_units * t.n_tiles * g.groups;       // work units
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::kAStages; ++s) { ptx::mbar_init(&a_full[s], 1); ptx::mbar_init(&a_empty[s], 1); }
         for (int s = 0; s < (RESIDENT ? 1 : C::kBStages); ++s) { ptx::mbar_init(&b_full[s], 1); ptx::mbar_init(&b_empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], 8); }
+        for (int a = 0; a < C::kNAcc; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], 8); }
         ptx::fence_barrier_init();
         ptx::fence_proxy_async();
     }
@@ -98,15 +113,23 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const TileCoord2 tc = decode2(tile, t);
-                const int cbase = g.in_coff + tc.grp * g.cin;
+                const WorkUnit wu = decode_work(tile, m_units, t);
+                TileCoord2 tc[MT];
+#pragma unroll
+                for (int j = 0; j < MT; ++j) {
+                    int m = wu.mp * MT + j; if (m >= t.m_tiles) m = t.m_tiles - 1;   // odd tail: reload a valid tile, result discarded
+                    tc[j] = decode2(m, t);
+                }
+                const int cbase = g.in_coff + wu.grp * g.cin;
                 for (int ch = 0; ch < t.chunks; ++ch) {
                     for (int u = 0; u < t.units_per_chunk; ++u) {
                         const Unit un = t.units[u];
                         ptx::mbar_wait(&a_empty[stage], phase ^ 1);
-                        ptx::mbar_arrive_expect_tx(&a_full[stage], static_cast<uint32_t>(un.rows) * kChunkBytes);
-                        ptx::tma_load_4d(sA + stage * kAUnitBytes, &maps.a[un.map], &a_full[stage],
-                                         cbase + ch * 32, tc.ox + un.c1, tc.oy + un.c2, tc.n0);
+                        ptx::mbar_arrive_expect_tx(&a_full[stage], static_cast<uint32_t>(un.rows) * kChunkBytes * MT);
+#pragma unroll
+                        for (int j = 0; j < MT; ++j)
+                            ptx::tma_load_4d(sA + stage * C::kAStage + j * C::kAUnit, &maps.a[un.map], &a_full[stage],
+                                             cbase + ch * 32, tc[j].ox + un.c1, tc[j].oy + un.c2, tc[j].n0);
                         if (++stage == C::kAStages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -124,8 +147,8 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
             } else {
                 int stage = 0; uint32_t phase = 0;
                 for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                    const TileCoord2 tc = decode2(tile, t);
-                    const int wrow = tc.grp * g.cout + tc.n_tile * BN;
+                    const WorkUnit wu = decode_work(tile, m_units, t);
+                    const int wrow = wu.grp * g.cout + wu.n_tile * BN;
                     for (int ch = 0; ch < t.chunks; ++ch)
                         for (int u = 0; u < t.units_per_chunk; ++u) {
                             const Unit un = t.units[u];
@@ -151,18 +174,18 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
         if (RESIDENT) { ptx::mbar_wait(&b_full[0], 0); ptx::tc_fence_after(); }
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            const int acc = it & 1;
-            const uint32_t acc_phase = (it >> 1) & 1;
+            const int acc = it % C::kNAcc;
+            const uint32_t acc_phase = (it / C::kNAcc) & 1;
             ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
             ptx::tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * BN;
+            const uint32_t d_tmem = tmem_base + acc * (MT * BN);
             uint32_t accumulate = 0;
             for (int ch = 0; ch < t.chunks; ++ch) {
                 for (int u = 0; u < t.units_per_chunk; ++u) {
                     const int ntaps = t.units[u].ntaps;
                     ptx::mbar_wait(&a_full[astage], aphase);
                     ptx::tc_fence_after();
-                    const uint32_t a_base = ptx::smem_u32(sA + astage * kAUnitBytes);
+                    const uint32_t a_base = ptx::smem_u32(sA + astage * C::kAStage);
                     for (int k = 0; k < ntaps; ++k) {
                         const int w_tap = t.units[u].taps[k].w_tap;
                         const uint32_t row_shift = static_cast<uint32_t>(t.units[u].taps[k].row_shift);
@@ -180,10 +203,13 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                         const uint32_t b_lo = ((b_addr & 0x3FFFFu) >> 4) | (1u << 16);
                         if (ptx::elect_one()) {
 #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk) {
-                                const uint64_t ad = (static_cast<uint64_t>(kDescHi) << 32) | (a_lo + 2 * kk);
-                                const uint64_t bd = (static_cast<uint64_t>(kDescHi) << 32) | (b_lo + 2 * kk);
-                                ptx::umma_tf32(d_tmem, ad, bd, idesc, accumulate | (kk != 0));
+                            for (int j = 0; j < MT; ++j) {
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk) {
+                                    const uint64_t ad = (static_cast<uint64_t>(kDescHi) << 32) | (a_lo + j * (C::kAUnit >> 4) + 2 * kk);
+                                    const uint64_t bd = (static_cast<uint64_t>(kDescHi) << 32) | (b_lo + 2 * kk);
+                                    ptx::umma_tf32(d_tmem + j * BN, ad, bd, idesc, accumulate | (kk != 0));
+                                }
                             }
                             if (!RESIDENT) ptx::umma_commit(&b_empty[bstage]);
                         }
@@ -214,44 +240,49 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
             const int py = rem / t.bw;
             const int px = rem - py * t.bw;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-                const int acc = it & 1;
-                const uint32_t acc_phase = (it >> 1) & 1;
-                const TileCoord2 tc = decode2(tile, t);
-                const int n = tc.n0 + pn, y = tc.ty * t.bh + py, x = tc.tx * t.bw + px;
-                const bool valid = (pn < t.bn) && (n < g.n_img) && (y < g.Ho) && (x < g.Wo);
-                const size_t pix = (static_cast<size_t>(n) * g.Ho + y) * g.Wo + x;
-                const int ch0 = tc.grp * g.cout + tc.n_tile * BN + half * kCols;
-                float* outp = p.out + pix * g.out_cstride + g.out_coff + ch0;
-                const float* resp = p.res ? p.res + pix * g.res_cstride + g.res_coff + ch0 : nullptr;
-                const float* biasp = p.bias + ch0;
-
+                const int acc = it % C::kNAcc;
+                const uint32_t acc_phase = (it / C::kNAcc) & 1;
+                const WorkUnit wu = decode_work(tile, m_units, t);
                 ptx::mbar_wait(&tmem_full[acc], acc_phase);
                 ptx::tc_fence_after();
-                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + half * kCols;
 #pragma unroll 1
-                for (int c0 = 0; c0 < kCols; c0 += 32) {
-                    uint32_t r0[16], r1[16];
-                    ptx::tmem_ld16(taddr + c0, r0);
-                    ptx::tmem_ld16(taddr + c0 + 16, r1);
-                    ptx::tmem_ld_wait();
-                    if (valid) {
+                for (int j = 0; j < MT; ++j) {
+                    const int m = wu.mp * MT + j;
+                    if (m >= t.m_tiles) break;                               // odd tail (warp-uniform)
+                    const TileCoord2 tc = decode2(m, t);
+                    const int n = tc.n0 + pn, y = tc.ty * t.bh + py, x = tc.tx * t.bw + px;
+                    const bool valid = (pn < t.bn) && (n < g.n_img) && (y < g.Ho) && (x < g.Wo);
+                    const size_t pix = (static_cast<size_t>(n) * g.Ho + y) * g.Wo + x;
+                    const int ch0 = wu.grp * g.cout + wu.n_tile * BN + half * kCols;
+                    float* outp = p.out + pix * g.out_cstride + g.out_coff + ch0;
+                    const float* resp = p.res ? p.res + pix * g.res_cstride + g.res_coff + ch0 : nullptr;
+                    const float* biasp = p.bias + ch0;
+                    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (MT * BN) + j * BN + half * kCols;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < kCols; c0 += 32) {
+                        uint32_t r0[16], r1[16];
+                        ptx::tmem_ld16(taddr + c0, r0);
+                        ptx::tmem_ld16(taddr + c0 + 16, r1);
+                        ptx::tmem_ld_wait();
+                        if (valid) {
 #pragma unroll
-                        for (int hh = 0; hh < 2; ++hh) {
-                            const uint32_t* r = hh ? r1 : r0;
-                            const int cc = c0 + hh * 16;
+                            for (int hh = 0; hh < 2; ++hh) {
+                                const uint32_t* r = hh ? r1 : r0;
+                                const int cc = c0 + hh * 16;
 #pragma unroll
-                            for (int j = 0; j < 16; j += 4) {
-                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(biasp + cc + j));
-                                float v0 = __uint_as_float(r[j]) + b4.x, v1 = __uint_as_float(r[j + 1]) + b4.y;
-                                float v2 = __uint_as_float(r[j + 2]) + b4.z, v3 = __uint_as_float(r[j + 3]) + b4.w;
-                                if (resp) {
-                                    const float4 r4 = __ldg(reinterpret_cast<const float4*>(resp + cc + j));
-                                    v0 += r4.x; v1 += r4.y; v2 += r4.z; v3 += r4.w;
+                                for (int jj = 0; jj < 16; jj += 4) {
+                                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(biasp + cc + jj));
+                                    float v0 = __uint_as_float(r[jj]) + b4.x, v1 = __uint_as_float(r[jj + 1]) + b4.y;
+                                    float v2 = __uint_as_float(r[jj + 2]) + b4.z, v3 = __uint_as_float(r[jj + 3]) + b4.w;
+                                    if (resp) {
+                                        const float4 r4 = __ldg(reinterpret_cast<const float4*>(resp + cc + jj));
+                                        v0 += r4.x; v1 += r4.y; v2 += r4.z; v3 += r4.w;
+                                    }
+                                    if (g.act == ACT_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+                                    else if (g.act == ACT_SELU) { v0 = selu_fast(v0); v1 = selu_fast(v1); v2 = selu_fast(v2); v3 = selu_fast(v3); }
+                                    if (g.round_tf32) { v0 = ptx::to_tf32(v0); v1 = ptx::to_tf32(v1); v2 = ptx::to_tf32(v2); v3 = ptx::to_tf32(v3); }
+                                    *reinterpret_cast<float4*>(outp + cc + jj) = make_float4(v0, v1, v2, v3);
                                 }
-                                if (g.act == ACT_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
-                                else if (g.act == ACT_SELU) { v0 = selu_fast(v0); v1 = selu_fast(v1); v2 = selu_fast(v2); v3 = selu_fast(v3); }
-                                if (g.round_tf32) { v0 = ptx::to_tf32(v0); v1 = ptx::to_tf32(v1); v2 = ptx::to_tf32(v2); v3 = ptx::to_tf32(v3); }
-                                *reinterpret_cast<float4*>(outp + cc + j) = make_float4(v0, v1, v2, v3);
                             }
                         }
                     }
@@ -265,9 +296,10 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
             const int cy_l = row / 11, cx_l = row - cy_l * 11;          // conv position inside the tile
             const int et = threadIdx.x - 128;                           // 0..255 among epilogue threads
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-                const int acc = it & 1;
-                const uint32_t acc_phase = (it >> 1) & 1;
-                const TileCoord2 tc = decode2(tile, t);
+                const int acc = it % C::kNAcc;
+                const uint32_t acc_phase = (it / C::kNAcc) & 1;
+                const WorkUnit wu = decode_work(tile, m_units, t);
+                const TileCoord2 tc = decode2(wu.mp, t);
                 float* stage = reinterpret_cast<float*>(sP + (it & 1) * ((kPoolStageBytes + 1023) & ~1023));
                 const int cy = tc.oy + cy_l, cx = tc.ox + cx_l;             // conv output coordinates
                 const bool cvalid = (row < 121) && cy >= 0 && cy < 88 && cx >= 0 && cx < 88;
@@ -327,35 +359,36 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
     if (warp == 2) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, C::kTmemCols); }
 }
 
-template <int BN, bool RESIDENT, bool POOL>
+template <int BN, bool RESIDENT, bool POOL, int MT>
 cudaError_t launch2(const UmmaMaps& maps, const ConvGeom& g, const Umma2Plan& t, const ConvPtrs& p, int num_sms, cudaStream_t stream) {
-    using C = Cfg2<BN, RESIDENT, POOL>;
+    using C = Cfg2<BN, RESIDENT, POOL, MT>;
     const int w_tiles = g.num_taps * t.chunks;
-    const size_t smem = static_cast<size_t>(C::kAStages) * kAUnitBytes + static_cast<size_t>(RESIDENT ? w_tiles : C::kBStages) * C::kBTile +
+    const size_t smem = static_cast<size_t>(C::kAStages) * C::kAStage + static_cast<size_t>(RESIDENT ? w_tiles : C::kBStages) * C::kBTile +
                         (POOL ? 2 * ((kPoolStageBytes + 1023) & ~1023) : 0) + 1024 + 512;
     if (smem > 232448) return cudaErrorInvalidConfiguration;
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
-        cudaError_t e = cudaFuncSetAttribute(conv_umma2_kernel<BN, RESIDENT, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        cudaError_t e = cudaFuncSetAttribute(conv_umma2_kernel<BN, RESIDENT, POOL, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;
         attr_smem = smem;
     }
-    const int total = t.m_tiles * t.n_tiles * g.groups;
+    const int total = ((t.m_tiles + MT - 1) / MT) * t.n_tiles * g.groups;
     const int grid = total < num_sms ? total : num_sms;
-    conv_umma2_kernel<BN, RESIDENT, POOL><<<grid, kThreads2, smem, stream>>>(maps, g, t, p);
+    conv_umma2_kernel<BN, RESIDENT, POOL, MT><<<grid, kThreads2, smem, stream>>>(maps, g, t, p);
     return cudaGetLastError();
 }
 
 }  // namespace
 
 cudaError_t launch_conv_umma2(const UmmaMaps& maps, const ConvGeom& g, const Umma2Plan& t, const ConvPtrs& p,
-                              int block_n, bool resident, bool pool, int num_sms, cudaStream_t stream) {
-    if (pool) return (block_n == 64 && resident) ? launch2<64, true, true>(maps, g, t, p, num_sms, stream) : cudaErrorInvalidValue;
-    if (resident) return block_n == 64 ? launch2<64, true, false>(maps, g, t, p, num_sms, stream) : cudaErrorInvalidValue;
+                              int block_n, bool resident, bool pool, int m_per_cta, int num_sms, cudaStream_t stream) {
+    if (pool) return (block_n == 64 && resident) ? launch2<64, true, true, 1>(maps, g, t, p, num_sms, stream) : cudaErrorInvalidValue;
+    if (resident) return block_n == 64 ? launch2<64, true, false, 1>(maps, g, t, p, num_sms, stream) : cudaErrorInvalidValue;
     switch (block_n) {
-        case 64:  return launch2<64, false, false>(maps, g, t, p, num_sms, stream);
-        case 128: return launch2<128, false, false>(maps, g, t, p, num_sms, stream);
-        case 256: return launch2<256, false, false>(maps, g, t, p, num_sms, stream);
+        case 64:  return launch2<64, false, false, 1>(maps, g, t, p, num_sms, stream);
+        case 128: return launch2<128, false, false, 1>(maps, g, t, p, num_sms, stream);
+        case 256: return m_per_cta == 2 ? launch2<256, false, false, 2>(maps, g, t, p, num_sms, stream)
+                                        : launch2<256, false, false, 1>(maps, g, t, p, num_sms, stream);
         default:  return cudaErrorInvalidValue;
     }
 }

@@ -54,9 +54,9 @@ const LayerSpec kLayers[14] = {
     {K_S1,   B_T2,  B_U,   B_P1B,  44,  44,  64,   64,   64, 1,    64,   0, ACT_RELU,  64},   // convB2.conv2 (+id)
     {K_S1,   B_U,   B_T2,  NONE,   44,  44,  64,   64,   64, 1,    64,   0, ACT_RELU,  64},   // convB3.conv1
     {K_S1,   B_T2,  B_CAT, B_U,    44,  44,  64,   64,   64, 1,   128,  64, ACT_RELU,  64},   // convB3.conv2 (+id) -> cat[64:128]
-    {K_S2,   B_CAT, B_F1,  NONE,   44,  44, 128,  128,  256, 1,   256,   0, ACT_SELU, 128},   // convAB1
-    {K_S1,   B_F1,  B_T4,  NONE,   22,  22, 256,  256,  256, 1,   256,   0, ACT_RELU, 128},   // convAB2.conv1
-    {K_S1,   B_T4,  B_F2,  B_F1,   22,  22, 256,  256,  256, 1,   256,   0, ACT_RELU, 128},   // convAB2.conv2 (+id) = 'feature'
+    {K_S2,   B_CAT, B_F1,  NONE,   44,  44, 128,  128,  256, 1,   256,   0, ACT_SELU, 256},   // convAB1
+    {K_S1,   B_F1,  B_T4,  NONE,   22,  22, 256,  256,  256, 1,   256,   0, ACT_RELU, 256},   // convAB2.conv1
+    {K_S1,   B_T4,  B_F2,  B_F1,   22,  22, 256,  256,  256, 1,   256,   0, ACT_RELU, 256},   // convAB2.conv2 (+id) = 'feature'
     {K_S2,   B_F2,  B_H1,  NONE,   22,  22, 256,  256, 1024, 1,  1024,   0, ACT_SELU, 256},   // trans_conv1 ++ rot_conv1
     {K_S1,   B_H1,  B_H2,  NONE,   11,  11, 1024, 512,  512, 2,  1024,   0, ACT_RELU, 256},   // {trans,rot}_conv2.conv1
     {K_S1,   B_H2,  B_H3,  B_H1,   11,  11, 1024, 512,  512, 2,  1024,   0, ACT_RELU, 256},   // {trans,rot}_conv2.conv2 (+id)
@@ -105,6 +105,7 @@ struct se3tn_ctx {
     CUtensorMap amap[14][7];
     CUtensorMap amap2[14][4];        // v2 kernel: boxes extended vertically (one per filter column / parity view)
     int conv_version = 2;            // SE3TN_CONV=1 selects the first-generation kernel
+    int dual_m = 1;                  // SE3TN_DUAL_M=0 disables two-M-tiles-per-CTA on the BN=256 layers
     int base_off_mode = 0;           // SE3TN_BASE_OFF: UMMA descriptor base_offset convention for row-shifted starts
     EncodeTiledFn encode = nullptr;
     std::map<int, WeightSet> weights;
@@ -431,7 +432,7 @@ int run_network(se3tn_ctx* c, int weight_id, int first, int n, int precision,
                 p.out = c->buf[li == 0 ? B_P1A : B_P1B];
                 g.out_cstride = 64; g.out_coff = 0;
             }
-            { ProfScope ps(c, li, s); CU_TRY(c, launch_conv_umma2(maps, g, t, p, BN, resident, pool, c->num_sms, s)); }
+            { ProfScope ps(c, li, s); CU_TRY(c, launch_conv_umma2(maps, g, t, p, BN, resident, pool, (BN == 256 && c->dual_m) ? 2 : 1, c->num_sms, s)); }
             ++c->launches;
             continue;
         }
@@ -498,6 +499,7 @@ int se3tn_create(int device, int max_batch, void* workspace, se3tn_ctx** out) {
     if (const char* ov = getenv("SE3TN_BLOCK_N")) c->umma_block_n_override = atoi(ov);
     if (const char* ov = getenv("SE3TN_CONV")) c->conv_version = atoi(ov) == 1 ? 1 : 2;
     if (const char* ov = getenv("SE3TN_BASE_OFF")) c->base_off_mode = atoi(ov);
+    if (const char* ov = getenv("SE3TN_DUAL_M")) c->dual_m = atoi(ov) != 0;
 
     void* fn = nullptr; cudaDriverEntryPointQueryResult qres;
     e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
