@@ -37,7 +37,8 @@ def parse():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=64)
-    ap.add_argument('--precision', default='tf32', choices=['tf32', 'fp32'])
+    ap.add_argument('--precision', default='bf16x3', choices=['bf16x3', 'tf32', 'bf16', 'fp32'])
+    ap.add_argument('--no-alt', action='store_true', help='skip the secondary precision-mode measurements')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     return ap.parse_args()
@@ -138,7 +139,8 @@ def cpu_on_track_rate(synth, seconds, pairs_per_call=8, threads=None):
         if time.perf_counter() - t0 >= seconds and calls >= 2:
             break
     dt = time.perf_counter() - t0
-    return calls * pairs_per_call / dt, threads, '%d calls x %d pairs in %.1f s (same frame/pose generators as the GPU arm)' % (calls, pairs_per_call, dt)
+    ref_poses = np.stack(one_call())
+    return calls * pairs_per_call / dt, threads, '%d calls x %d pairs in %.1f s (same frame/pose generators as the GPU arm)' % (calls, pairs_per_call, dt), (rgb, depth, poses, rgbA, depthA, ref_poses)
 
 
 def run_reference(args, synth, rank, world):
@@ -257,28 +259,62 @@ def main():
     value = nb * world * args.steps / (total_ms * 1e-3)
 
     # ---- (2) roofline of the conv stack: per-kernel events inside the library ------------------------
-    eng.set_profiling(True)
-    conv_ms, all_ms = [], []
-    for k in range(min(args.steps, 20)):
-        flush.zero_()
-        step(k, gather=False)
-        prof = eng.get_profile()
-        conv_ms.append(prof[:14].sum()); all_ms.append(prof)
-    eng.set_profiling(False)
-    conv_ms = float(np.mean(conv_ms)); per_slot = np.mean(np.stack(all_ms), 0)
     pk, pk_src = peaks()
-    if args.precision == 'tf32':
-        peak = pk['bf16_tflops'] / 2.0
-        peak_note = 'tf32 dense = measured bf16 cuBLAS burst (%s: %.1f TF/s) / 2 (tf32 tensor rate is half of bf16); sustained equivalent %.1f' % (pk_src, pk['bf16_tflops'], pk.get('bf16_tflops_sustained', 0) / 2)
-    else:
-        peak = 75.0; peak_note = 'nominal fp32 FFMA peak (no tensor cores in this mode)'
-    achieved = nb * FLOP_PER_PAIR / (conv_ms * 1e-3) / 1e12
-    roofline = {'bound': 'tensor', 'kernel': 'conv_umma_kernel (14 launches/step)' if args.precision == 'tf32' else 'conv_direct_kernel',
-                'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None,
-                'conv_stack_ms': conv_ms, 'peak_note': peak_note,
+
+    def conv_stack_profile(prec, nsteps):
+        tracker.precision = prec
+        eng.set_profiling(True)
+        conv_ms, all_ms = [], []
+        for k in range(nsteps):
+            flush.zero_()
+            step(k, gather=False)
+            prof = eng.get_profile()
+            conv_ms.append(prof[:14].sum()); all_ms.append(prof)
+        eng.set_profiling(False)
+        tracker.precision = args.precision
+        return float(np.mean(conv_ms)), np.mean(np.stack(all_ms), 0)
+
+    def roofline_of(prec, conv_ms, per_slot):
+        achieved = nb * FLOP_PER_PAIR / (conv_ms * 1e-3) / 1e12
+        if prec == 'tf32':
+            peak, executed = pk['bf16_tflops'] / 2.0, 1.0
+            note = 'tf32 dense = measured bf16 cuBLAS burst (%s: %.1f TF/s) / 2 (kind::tf32 issues at half the bf16 rate; no tf32 line in the file)' % (pk_src, pk['bf16_tflops'])
+        elif prec in ('bf16x3', 'bf16'):
+            peak, executed = pk['bf16_tflops'], (3.0 if prec == 'bf16x3' else 1.0)
+            note = 'measured bf16 cuBLAS burst (%s); sustained %.1f.  bf16x3 executes 3 bf16 products per algorithmic MAC, so the tensor pipe does executed_mult x the algorithmic work' % (pk_src, pk.get('bf16_tflops_sustained', 0))
+        else:
+            peak, executed, note = 75.0, 1.0, 'nominal fp32 FFMA peak (no tensor cores in this mode)'
+        return {'bound': 'tensor', 'kernel': 'conv_umma2_kernel (14 launches/step)' if prec != 'fp32' else 'conv_direct_kernel',
+                'precision': prec, 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
+                'executed_mult': executed, 'tensor_pipe_frac': achieved * executed / peak, 'traffic': None,
+                'conv_stack_ms': conv_ms, 'peak_note': note,
                 'per_kernel_ms': {'conv': [round(float(x), 4) for x in per_slot[:14]], 'maxpool': [round(float(x), 4) for x in per_slot[14:16]],
                                   'head': round(float(per_slot[16]), 4), 'preprocess': round(float(per_slot[17]), 4),
                                   'pose_update': round(float(per_slot[18]), 4)}}
+
+    cms, slots = conv_stack_profile(args.precision, min(args.steps, 20))
+    roofline = roofline_of(args.precision, cms, slots)
+
+    # ---- (2b) the other tensor-core modes on the same workload (secondary numbers) -------------------
+    alt = {}
+    if not args.no_alt:
+        for prec in [q for q in ('tf32', 'bf16x3', 'bf16') if q != args.precision]:
+            tracker.precision = prec
+            for k in range(3):
+                step(k)
+            sync_all()
+            ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(args.steps, 20))]
+            for k in range(len(ev2)):
+                flush.zero_(); ev2[k][0].record(); step(k); ev2[k][1].record()
+            sync_all()
+            tms = torch.tensor([float(sum(a.elapsed_time(b) for a, b in ev2))], device=dev)
+            if world > 1:
+                dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            cms2, slots2 = conv_stack_profile(prec, min(args.steps, 10))
+            r2 = roofline_of(prec, cms2, slots2)
+            alt[prec] = {'value': nb * world * len(ev2) / (float(tms.item()) * 1e-3), 'unit': 'pairs/s', 'ms_per_step': float(tms.item()) / len(ev2),
+                         'roofline_frac': r2['frac'], 'tensor_pipe_frac': r2['tensor_pipe_frac'], 'conv_stack_ms': cms2}
+        tracker.precision = args.precision
 
     # ---- (3) end to end through the public API with pinned HOST buffers -----------------------------
     info = {'resolution': 176, 'boundingbox': 10, 'object_width': 200.0,
@@ -321,21 +357,30 @@ def main():
 
     # ---- (4) CPU baseline (rank 0, N=1 only) ---------------------------------------------------------
     cpu = None
+    parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, sample = cpu_on_track_rate(synth, args.cpu_seconds)
+        v, cores, sample, (c_rgb, c_depth, c_poses, c_rgbA, c_depthA, c_ref) = cpu_on_track_rate(synth, args.cpu_seconds)
         cpu = {'value': v, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port', 'sample': sample}
+        # the CPU sample doubles as a parity spot check of every tensor-core mode on this workload's generators
+        parity = {}
+        for prec in ('bf16x3', 'tf32', 'bf16'):
+            trk.precision = prec
+            got = trk.on_track_batch(c_poses, c_rgb, c_depth, c_rgbA, c_depthA)
+            parity[prec] = {'max_abs_pose_err': float(np.abs(got - c_ref).max()), 'pairs': int(len(c_ref))}
+        trk.precision = args.precision
+        parity['note'] = 'max |pose - CPU oracle pose| over the cpu_baseline sample; the 6-vector gate (rtol 1e-3, atol 1e-4) propagates to <= 1e-4 here'
 
     if rank == 0:
         line = {'metric': 'rgbd_pair_frames_per_sec', 'value': value, 'unit': 'pairs/s', 'n_gpus': world, 'steps': args.steps,
                 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
-                'vs_baseline': None, 'dtype': 'tf32' if args.precision == 'tf32' else 'f32', 'data': 'synthetic',
+                'vs_baseline': None, 'dtype': {'tf32': 'tf32', 'bf16x3': 'bf16x3 (bf16 hi/lo split operands, 3 products/MAC, fp32 accumulate)', 'bf16': 'bf16', 'fp32': 'f32'}[args.precision], 'data': 'synthetic',
                 'config': {'workload': 'BASELINE configs[1]: %d synthetic RGB-D pairs/GPU per step, full path K0 crop/normalise -> two-branch 17-conv forward -> se(3) update, 176x176, one 480x640 frame' % nb,
                            'tracks_per_gpu': nb, 'total_tracks': nb * world, 'precision': args.precision,
                            'parallelism': 'tracks sharded, %d/GPU, NCCL all-gather of poses per step' % nb if world > 1 else 'single GPU',
                            'l2': 'flushed between timed steps (256 MiB memset, untimed); %d rotating input sets; per-step CUDA events, max over ranks' % N_INPUT_SETS,
                            'weights': 'random-init (seeded), one weight set'},
                 'gpu_launches': int(launches), 'launches_per_step': int(launches // max(args.steps, 1)),
-                'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'clocks': clocks,
+                'roofline': roofline, 'alt_precisions': alt, 'parity': parity, 'cpu_baseline': cpu, 'e2e': e2e, 'clocks': clocks,
                 'ms_per_step_min': float(ms_steps.min()), 'ms_per_step_median': float(np.median(ms_steps))}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -30,10 +30,14 @@ enum {
     SE3TN_ERR_UNSUPPORTED = -5   /* device is not sm_100                              */
 };
 
-/* Arithmetic of the 17 convolutions. */
+/* Arithmetic of the 17 convolutions (accumulation is always fp32). */
 enum {
-    SE3TN_PREC_TF32 = 0,   /* tcgen05 kind::tf32, fp32 accumulate; operands rounded to tf32 (rna)   */
-    SE3TN_PREC_FP32 = 1    /* plain FFMA direct convolution, no operand rounding (cross-check mode) */
+    SE3TN_PREC_TF32 = 0,    /* tcgen05 kind::tf32; operands rounded to tf32 (rna): 10-bit mantissas.  Fastest;
+                               meets the 1e-3/1e-4 gate only for well-conditioned weights/inputs              */
+    SE3TN_PREC_FP32 = 1,    /* plain FFMA direct convolution, no operand rounding (cross-check mode)         */
+    SE3TN_PREC_BF16X3 = 2,  /* tcgen05 kind::f16 on bf16 hi/lo splits, 3 products per MAC: ~2^-16 relative
+                               error (fp32-faithful for the gate) at 1.5x the tensor time of TF32            */
+    SE3TN_PREC_BF16 = 3     /* tcgen05 kind::f16, bf16 operands, 1 product per MAC (BASELINE configs[2])     */
 };
 
 #define SE3TN_IMAGE_SIZE 176           /* reference dataset_info.yml:15 `resolution`          */

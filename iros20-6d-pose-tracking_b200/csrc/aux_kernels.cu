@@ -5,6 +5,7 @@
 #include "aux_kernels.h"
 #include "ptx.cuh"
 #include <cfloat>
+#include <cuda_bf16.h>
 
 namespace se3tn {
 
@@ -41,6 +42,21 @@ __device__ __forceinline__ void bbox_window(const double* pose, double fx, doubl
     top = static_cast<int>(fmax(-lim, fmin(lim, vmin)));
     cw = static_cast<int>(fmax(-lim, fmin(lim, umax))) - left;
     ch = static_cast<int>(fmax(-lim, fmin(lim, vmax))) - top;
+}
+
+// conv-input storage modes: 0 raw fp32, 1 fp32 words rounded to tf32, 2 per pixel [4 x bf16 hi | 4 x bf16 lo]
+__device__ __forceinline__ float4 pack_stem_pixel(float4 v, int mode) {
+    if (mode == 1) return make_float4(ptx::to_tf32(v.x), ptx::to_tf32(v.y), ptx::to_tf32(v.z), ptx::to_tf32(v.w));
+    if (mode == 2) {
+        const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+        const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+        const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - f01.x, v.y - f01.y), l23 = __floats2bfloat162_rn(v.z - f23.x, v.w - f23.y);
+        float4 o;
+        o.x = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h01)); o.y = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h23));
+        o.z = __uint_as_float(*reinterpret_cast<const uint32_t*>(&l01)); o.w = __uint_as_float(*reinterpret_cast<const uint32_t*>(&l23));
+        return o;
+    }
+    return v;
 }
 
 __device__ __forceinline__ float norm_f32(float x, float m, float s) { return __fdiv_rn(__fsub_rn(x, m), s); }
@@ -127,10 +143,8 @@ preprocess_kernel(PreprocessArgs a)
         ob[0] = vB.x; ob[kImg * kImg] = vB.y; ob[2 * kImg * kImg] = vB.z; ob[3 * kImg * kImg] = vB.w;
     }
     if (a.stemA) {
-        if (a.round_tf32) {
-            vA = make_float4(ptx::to_tf32(vA.x), ptx::to_tf32(vA.y), ptx::to_tf32(vA.z), ptx::to_tf32(vA.w));
-            vB = make_float4(ptx::to_tf32(vB.x), ptx::to_tf32(vB.y), ptx::to_tf32(vB.z), ptx::to_tf32(vB.w));
-        }
+        vA = pack_stem_pixel(vA, a.round_tf32);
+        vB = pack_stem_pixel(vB, a.round_tf32);
         const size_t so = (static_cast<size_t>(n) * kStemH + (y + 3)) * kStemW + (x + 3);
         reinterpret_cast<float4*>(a.stemA)[so] = vA;
         reinterpret_cast<float4*>(a.stemB)[so] = vB;
@@ -225,7 +239,7 @@ nchw_to_stem_kernel(const float* __restrict__ src, float* __restrict__ dst, int 
     const int y = pix / kImg, x = pix - y * kImg;
     const float* s = src + static_cast<size_t>(n) * 4 * kImg * kImg + pix;
     float4 v = make_float4(s[0], s[kImg * kImg], s[2 * kImg * kImg], s[3 * kImg * kImg]);
-    if (round_tf32) v = make_float4(ptx::to_tf32(v.x), ptx::to_tf32(v.y), ptx::to_tf32(v.z), ptx::to_tf32(v.w));
+    v = pack_stem_pixel(v, round_tf32);
     reinterpret_cast<float4*>(dst)[(static_cast<size_t>(n) * kStemH + (y + 3)) * kStemW + (x + 3)] = v;
 }
 
@@ -283,15 +297,27 @@ cudaError_t launch_maxpool(const float* in, float* out, int n_img, int Hin, int 
 // =============================================================================================
 __global__ void __launch_bounds__(256)
 head_kernel(const float4* __restrict__ x, const float* __restrict__ fcw /*[6][512]*/, const float* __restrict__ fcb /*[6]*/,
-            float* __restrict__ out_trans, float* __restrict__ out_rot, int npix)
+            float* __restrict__ out_trans, float* __restrict__ out_rot, int npix, int split_bf16)
 {
     __shared__ float red[8][3];
     const int n = blockIdx.x, t = threadIdx.x;
-    const float4* xp = x + static_cast<size_t>(n) * npix * 256 + t;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int p = 0; p < npix; ++p) {
-        const float4 v = __ldg(xp + static_cast<size_t>(p) * 256);
-        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    if (!split_bf16) {
+        const float4* xp = x + static_cast<size_t>(n) * npix * 256 + t;
+        for (int p = 0; p < npix; ++p) {
+            const float4 v = __ldg(xp + static_cast<size_t>(p) * 256);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+    } else {
+        // channels 4t..4t+3 live in chunk (4t)/32 as bf16 hi at byte ((4t)%32)*2 and lo 64 bytes further
+        const uint8_t* xb = reinterpret_cast<const uint8_t*>(x) + static_cast<size_t>(n) * npix * 4096 + ((4 * t) >> 5) * 128 + ((4 * t) & 31) * 2;
+        for (int p = 0; p < npix; ++p) {
+            const uint2 h = __ldg(reinterpret_cast<const uint2*>(xb + static_cast<size_t>(p) * 4096));
+            const uint2 l = __ldg(reinterpret_cast<const uint2*>(xb + static_cast<size_t>(p) * 4096 + 64));
+            const float2 h0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&h.x)), h1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&h.y));
+            const float2 l0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&l.x)), l1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&l.y));
+            s.x += h0.x + l0.x; s.y += h0.y + l0.y; s.z += h1.x + l1.x; s.w += h1.y + l1.y;
+        }
     }
     const float inv = 1.0f / static_cast<float>(npix);
     s.x *= inv; s.y *= inv; s.z *= inv; s.w *= inv;
@@ -317,9 +343,9 @@ head_kernel(const float4* __restrict__ x, const float* __restrict__ fcw /*[6][51
 }
 
 cudaError_t launch_head(const float* x, const float* fcw, const float* fcb, float* out_trans, float* out_rot,
-                        int n_img, int npix, cudaStream_t s) {
+                        int n_img, int npix, int split_bf16, cudaStream_t s) {
     if (n_img <= 0) return cudaSuccess;
-    head_kernel<<<n_img, 256, 0, s>>>(reinterpret_cast<const float4*>(x), fcw, fcb, out_trans, out_rot, npix);
+    head_kernel<<<n_img, 256, 0, s>>>(reinterpret_cast<const float4*>(x), fcw, fcb, out_trans, out_rot, npix, split_bf16);
     return cudaGetLastError();
 }
 
@@ -327,7 +353,7 @@ cudaError_t launch_head(const float* x, const float* fcw, const float* fcb, floa
 // NHWC -> NCHW (the 'feature' entry of the reference's output dict, se3_tracknet.py:96)
 // =============================================================================================
 __global__ void __launch_bounds__(256)
-nhwc_to_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int HW, int C)
+nhwc_to_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int HW, int C, int split_bf16)
 {
     __shared__ float tile[32][33];
     const int n = blockIdx.z;
@@ -335,7 +361,15 @@ nhwc_to_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int H
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;    // 32 x 8
     for (int j = ty; j < 32; j += 8) {
         const int p = p0 + j, c = c0 + tx;
-        tile[j][tx] = (p < HW && c < C) ? in[(static_cast<size_t>(n) * HW + p) * C + c] : 0.f;
+        float val = 0.f;
+        if (p < HW && c < C) {
+            if (!split_bf16) val = in[(static_cast<size_t>(n) * HW + p) * C + c];
+            else {
+                const uint8_t* cb = reinterpret_cast<const uint8_t*>(in + (static_cast<size_t>(n) * HW + p) * C + (c & ~31)) + (c & 31) * 2;
+                val = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(cb)) + __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(cb + 64));
+            }
+        }
+        tile[j][tx] = val;
     }
     __syncthreads();
     for (int j = ty; j < 32; j += 8) {
@@ -344,10 +378,55 @@ nhwc_to_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int H
     }
 }
 
-cudaError_t launch_nhwc_to_nchw(const float* in, float* out, int n_img, int HW, int C, cudaStream_t s) {
+cudaError_t launch_nhwc_to_nchw(const float* in, float* out, int n_img, int HW, int C, int split_bf16, cudaStream_t s) {
     if (n_img <= 0) return cudaSuccess;
     dim3 grid((HW + 31) / 32, (C + 31) / 32, n_img);
-    nhwc_to_nchw_kernel<<<grid, 256, 0, s>>>(in, out, HW, C);
+    nhwc_to_nchw_kernel<<<grid, 256, 0, s>>>(in, out, HW, C, split_bf16);
+    return cudaGetLastError();
+}
+
+// =============================================================================================
+// Weight preparation for the bf16 hi/lo modes (conv_umma2.cu PREC_BF16X3 / PREC_BF16).
+// 3x3 layers: every 32-word K chunk of a weight row becomes [32 x bf16 hi | 32 x bf16 lo].
+// Stem: per (filter row r, pass): 8 pixels x 16 B; pass 0 = [w_hi(4) | w_hi(4)], pass 1 = [w_lo(4) | 0].
+// =============================================================================================
+__global__ void split_weights_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, size_t words)
+{
+    size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (; i < words; i += stride) {
+        const float v = src[i];
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+        const size_t chunk = i >> 5, j = i & 31;
+        *reinterpret_cast<__nv_bfloat16*>(dst + chunk * 128 + j * 2) = h;
+        *reinterpret_cast<__nv_bfloat16*>(dst + chunk * 128 + 64 + j * 2) = l;
+    }
+}
+
+__global__ void split_stem_weights_kernel(const float* __restrict__ src /*[64][7*32]*/, uint8_t* __restrict__ dst /*[64][7*2*32 words]*/)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;      // one thread per (co, r, p): 4 channels
+    if (i >= 64 * 7 * 8) return;
+    const int p = i & 7, r = (i >> 3) % 7, co = i / 56;
+    const float* w = src + co * 224 + r * 32 + p * 4;
+    __nv_bfloat16 h[4], l[4];
+    for (int c = 0; c < 4; ++c) { h[c] = __float2bfloat16_rn(w[c]); l[c] = __float2bfloat16_rn(w[c] - __bfloat162float(h[c])); }
+    uint8_t* d0 = dst + (static_cast<size_t>(co) * 448 + (r * 2 + 0) * 32 + p * 4) * 4;
+    uint8_t* d1 = dst + (static_cast<size_t>(co) * 448 + (r * 2 + 1) * 32 + p * 4) * 4;
+    for (int c = 0; c < 4; ++c) {
+        reinterpret_cast<__nv_bfloat16*>(d0)[c] = h[c]; reinterpret_cast<__nv_bfloat16*>(d0)[4 + c] = h[c];
+        reinterpret_cast<__nv_bfloat16*>(d1)[c] = l[c]; reinterpret_cast<__nv_bfloat16*>(d1)[4 + c] = __float2bfloat16_rn(0.f);
+    }
+}
+
+cudaError_t launch_split_weights(const float* src, void* dst, size_t words, cudaStream_t s) {
+    if (!words) return cudaSuccess;
+    split_weights_kernel<<<1024, 256, 0, s>>>(src, static_cast<uint8_t*>(dst), words);
+    return cudaGetLastError();
+}
+cudaError_t launch_split_stem_weights(const float* src, void* dst, cudaStream_t s) {
+    split_stem_weights_kernel<<<(64 * 7 * 8 + 127) / 128, 128, 0, s>>>(src, static_cast<uint8_t*>(dst));
     return cudaGetLastError();
 }
 

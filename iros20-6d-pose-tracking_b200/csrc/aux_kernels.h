@@ -23,7 +23,7 @@ struct PreprocessArgs {
     const float* mean32; const float* std32;      // [sets][8] when !stats_f64
     const double* mean64; const double* std64;    // [sets][8] when stats_f64
     int stats_f64;
-    int round_tf32;
+    int round_tf32;                // conv-input storage: 0 raw fp32, 1 tf32-rounded words, 2 per pixel [4 bf16 hi | 4 bf16 lo]
     int b_precropped;              // frame_rgb/frame_depth are n ready-made 176x176 crops (processData inputs)
     float* stemA; float* stemB;    // N x 182 x 184 x 4 (nullable)
     float* nchwA; float* nchwB;    // N x 4 x 176 x 176 (nullable)
@@ -39,8 +39,10 @@ cudaError_t launch_crop(const uint8_t* frame_rgb, const uint16_t* frame_depth, i
 cudaError_t launch_nchw_to_stem(const float* src, float* dst, int n, int round_tf32, cudaStream_t s);
 cudaError_t launch_maxpool(const float* in, float* out, int n_img, int Hin, int Win, int C, cudaStream_t s);
 cudaError_t launch_head(const float* x, const float* fcw, const float* fcb, float* out_trans, float* out_rot,
-                        int n_img, int npix, cudaStream_t s);
-cudaError_t launch_nhwc_to_nchw(const float* in, float* out, int n_img, int HW, int C, cudaStream_t s);
+                        int n_img, int npix, int split_bf16, cudaStream_t s);
+cudaError_t launch_nhwc_to_nchw(const float* in, float* out, int n_img, int HW, int C, int split_bf16, cudaStream_t s);
+cudaError_t launch_split_weights(const float* src, void* dst, size_t words, cudaStream_t s);
+cudaError_t launch_split_stem_weights(const float* src /*[64][224]*/, void* dst /*[64][448 words]*/, cudaStream_t s);
 cudaError_t launch_pose_update(const double* poses_in, const float* trans, const float* rot, float tn, float rn,
                                double* poses_out, int n, cudaStream_t s);
 cudaError_t launch_so3_log(const double* poses_a, const double* poses_b, double tn, double rn,

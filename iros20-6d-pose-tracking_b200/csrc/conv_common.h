@@ -43,7 +43,7 @@ struct ConvGeom {
     int out_cstride, out_coff;
     int res_cstride, res_coff;
     int act;
-    int round_tf32;      // round stored activations to tf32 (rna) so the next UMMA sees exact operands
+    int round_tf32;      // fp32-word storage: round stored activations to tf32 (rna) so the next UMMA sees exact operands
 };
 
 struct ConvPtrs {
@@ -91,7 +91,8 @@ struct Umma2Plan {
 };
 
 cudaError_t launch_conv_umma2(const UmmaMaps& maps, const ConvGeom& g, const Umma2Plan& t, const ConvPtrs& p,
-                              int block_n, bool resident, bool pool, int m_per_cta, int num_sms, cudaStream_t stream);
+                              int block_n, bool resident, bool pool, int m_per_cta, int prec /*0 tf32, 1 bf16x3, 2 bf16*/,
+                              int num_sms, cudaStream_t stream);
 
 cudaError_t launch_conv_umma(const UmmaMaps& maps, const ConvGeom& g, const UmmaTiling& t,
                              const ConvPtrs& p, int block_n, int num_sms, cudaStream_t stream);

@@ -19,9 +19,20 @@
 //     TMEM columns) through the K loop, so every weight tile fetched from L2 feeds 8 MMAs instead
 //     of 4 -- the weight stream, which is >80% of the fill traffic of the deep layers, halves.
 //     At batch 64 each deep layer is exactly 128 work units: one wave on 148 SMs.
+//   * PREC selects the arithmetic without touching the byte layout.  Every 128-byte K chunk of an
+//     activation pixel / weight row is either 32 fp32 words holding TF32 values (PREC_TF32) or
+//     [32 x bf16 hi | 32 x bf16 lo] of the same 32 channels (x = hi + lo to 16 mantissa bits):
+//       PREC_TF32    4 x kind::tf32 MMAs per chunk
+//       PREC_BF16X3  6 x kind::f16 (bf16) MMAs per chunk: hi*w_hi, lo*w_hi, hi*w_lo via descriptor
+//                    offsets 0/64 bytes into the same tiles -- fp32-faithful (error ~2^-16) at 1.5x
+//                    the tensor time of TF32 and identical fill traffic
+//       PREC_BF16    2 MMAs (hi*w_hi): the plain bf16 tensor-core path (BASELINE configs[2])
+//     The stem's 8-pixel window interleaves hi/lo per pixel, so it uses two weight tiles per filter
+//     row ([w_hi|w_hi] and [w_lo|0]) -- 8 MMAs.
 // Same tensors, packed weights, tile boxes and epilogue semantics as v1 (see conv_common.h).
 #include "conv_common.h"
 #include "ptx.cuh"
+#include <cuda_bf16.h>
 
 namespace se3tn {
 namespace {
@@ -31,11 +42,15 @@ constexpr int kThreads2 = 384;                 // warps: 0 A-TMA, 1 MMA, 2 TMEM 
 constexpr int kPoolPitch = 68;                 // floats per staged conv position (64 + 4: bank spread)
 constexpr int kPoolStageBytes = 121 * kPoolPitch * 4;
 
-template <int BN, bool RESIDENT, bool POOL, int MT> struct Cfg2 {
+enum { PREC_TF32 = 0, PREC_BF16X3 = 1, PREC_BF16 = 2 };
+
+template <int BN, bool RESIDENT, bool POOL, int MT, int PREC = 0> struct Cfg2 {
     static constexpr int kBTile = BN * kChunkBytes;
     static constexpr int kAUnit = POOL ? 21 * 1024 : 20 * 1024;
     static constexpr int kAStage = MT * kAUnit;
-    static constexpr int kAStages = RESIDENT ? (POOL ? 4 : 3) : (BN == 256 ? 3 : 4);
+    static constexpr int kAStages = RESIDENT ? ((POOL && PREC == PREC_TF32) ? 4 : 3) : (BN == 256 ? 3 : 4);
+    static constexpr int kWPerTap = (POOL && PREC != PREC_TF32) ? 2 : 1;  // weight tiles per (tap, chunk)
+    static constexpr int kPoolBufs = POOL ? (PREC == PREC_TF32 ? 2 : 1) : 0;
     static constexpr int kBStages = RESIDENT ? 0 : (BN == 256 ? (MT == 2 ? 3 : 4) : 6);
     static constexpr int kNAcc = (2 * MT * BN <= 512) ? 2 : 1;         // accumulator sets (double-buffered when they fit)
     static constexpr int kTmemCols = kNAcc * MT * BN;                   // 128 / 256 / 512
@@ -69,19 +84,31 @@ __device__ __forceinline__ TileCoord2 decode2(int m, const Umma2Plan& t) {
     return c;
 }
 
-template <int BN, bool RESIDENT, bool POOL, int MT>
+// fp32 -> (bf16 hi, bf16 lo) with x ~= hi + lo; packs two values per 32-bit word (element 0 in the low half)
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    const float2 hf = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ float2 unpack2(uint32_t w) {
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+}
+
+template <int BN, bool RESIDENT, bool POOL, int MT, int PREC>
 __global__ void __launch_bounds__(kThreads2, 1)
 conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const Umma2Plan t, const ConvPtrs p)
 {
-    using C = Cfg2<BN, RESIDENT, POOL, MT>;
+    using C = Cfg2<BN, RESIDENT, POOL, MT, PREC>;
     static_assert(!(POOL && MT != 1), "pool epilogue is single-tile");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int w_tiles = g.num_taps * t.chunks;                          // K tiles of the weight matrix
+    const int w_tiles = g.num_taps * t.chunks * C::kWPerTap;            // K tiles of the weight matrix
     uint8_t* sA = smem;                                                 // [kAStages][MT][unit]
     uint8_t* sB = sA + C::kAStages * C::kAStage;                       // resident: [w_tiles][BN*128]; ring: [kBStages][BN*128]
     uint8_t* sP = sB + (RESIDENT ? w_tiles : C::kBStages) * C::kBTile;  // pool staging (POOL only): 2 x 121 x 68 floats
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (POOL ? 2 * ((kPoolStageBytes + 1023) & ~1023) : 0));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + C::kPoolBufs * ((kPoolStageBytes + 1023) & ~1023));
     uint64_t* a_full = bars;                       // [kAStages]
     uint64_t* a_empty = a_full + C::kAStages;      // [kAStages]
     uint64_t* b_full = a_empty + C::kAStages;      // [max(kBStages,1)]  (resident: b_full[0] = "weights landed")
@@ -141,9 +168,8 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
             if (RESIDENT) {
                 // whole K-major weight matrix of this CTA's (only) N tile: loaded once
                 ptx::mbar_arrive_expect_tx(&b_full[0], static_cast<uint32_t>(w_tiles) * C::kBTile);
-                for (int tap = 0; tap < g.num_taps; ++tap)
-                    for (int ch = 0; ch < t.chunks; ++ch)
-                        ptx::tma_load_2d(sB + (tap * t.chunks + ch) * C::kBTile, &maps.b, &b_full[0], tap * g.cin + ch * 32, 0);
+                for (int wt = 0; wt < w_tiles; ++wt)      // tile wt = (tap*chunks + ch)*kWPerTap + pass, 32 words of K each
+                    ptx::tma_load_2d(sB + wt * C::kBTile, &maps.b, &b_full[0], wt * 32, 0);
             } else {
                 int stage = 0; uint32_t phase = 0;
                 for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -166,7 +192,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
         // ============================== MMA issuer ================================
         // The WHOLE warp walks the loop (warp-uniform control flow lets ptxas keep descriptors and
         // barrier addresses in uniform registers); one elected lane issues the tcgen05 instructions.
-        constexpr uint32_t idesc = ptx::umma_idesc(2 /*tf32*/, kBlockM, BN);
+        constexpr uint32_t idesc = ptx::umma_idesc(PREC == PREC_TF32 ? 2u /*tf32*/ : 1u /*bf16*/, kBlockM, BN);
         // descriptor high word: SBO = 1024 B (>>4) | version 1 (bit 46) | SWIZZLE_128B (bits 61..63)
         constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
         int astage = 0; uint32_t aphase = 0;
@@ -191,7 +217,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                         const uint32_t row_shift = static_cast<uint32_t>(t.units[u].taps[k].row_shift);
                         uint32_t b_addr;
                         if (RESIDENT) {
-                            b_addr = ptx::smem_u32(sB + (w_tap * t.chunks + ch) * C::kBTile);
+                            b_addr = ptx::smem_u32(sB + (w_tap * t.chunks + ch) * C::kWPerTap * C::kBTile);
                         } else {
                             ptx::mbar_wait(&b_full[bstage], bphase);
                             ptx::tc_fence_after();
@@ -204,11 +230,30 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                         if (ptx::elect_one()) {
 #pragma unroll
                             for (int j = 0; j < MT; ++j) {
+                                const uint32_t aj = a_lo + j * (C::kAUnit >> 4);
+                                const uint32_t dj = d_tmem + j * BN;
+                                auto desc = [](uint32_t lo) { return (static_cast<uint64_t>(kDescHi) << 32) | lo; };
+                                if (PREC == PREC_TF32) {
 #pragma unroll
-                                for (int kk = 0; kk < 4; ++kk) {
-                                    const uint64_t ad = (static_cast<uint64_t>(kDescHi) << 32) | (a_lo + j * (C::kAUnit >> 4) + 2 * kk);
-                                    const uint64_t bd = (static_cast<uint64_t>(kDescHi) << 32) | (b_lo + 2 * kk);
-                                    ptx::umma_tf32(d_tmem + j * BN, ad, bd, idesc, accumulate | (kk != 0));
+                                    for (int kk = 0; kk < 4; ++kk)
+                                        ptx::umma_tf32(dj, desc(aj + 2 * kk), desc(b_lo + 2 * kk), idesc, accumulate | (kk != 0));
+                                } else if (POOL) {
+                                    // stem window = 8 pixels x [hi4|lo4]: pass 0 against [w_hi|w_hi], pass 1 against [w_lo|0]
+#pragma unroll
+                                    for (int ps = 0; ps < 2; ++ps)
+#pragma unroll
+                                        for (int kk = 0; kk < 4; ++kk)
+                                            ptx::umma_f16(dj, desc(aj + 2 * kk), desc(b_lo + ps * (C::kBTile >> 4) + 2 * kk), idesc, accumulate | (ps | kk));
+                                } else if (PREC == PREC_BF16X3) {
+                                    // chunk = [32 hi | 32 lo] bf16 (A) x [32 w_hi | 32 w_lo] (B); offsets in 16-byte units
+                                    constexpr int AO[6] = {0, 2, 4, 6, 0, 2};      // hi, hi, lo, lo, hi, hi
+                                    constexpr int BO[6] = {0, 2, 0, 2, 4, 6};      // w_hi x4,        w_lo x2
+#pragma unroll
+                                    for (int i = 0; i < 6; ++i)
+                                        ptx::umma_f16(dj, desc(aj + AO[i]), desc(b_lo + BO[i]), idesc, accumulate | (i != 0));
+                                } else {
+                                    ptx::umma_f16(dj, desc(aj), desc(b_lo), idesc, accumulate);
+                                    ptx::umma_f16(dj, desc(aj + 2), desc(b_lo + 2), idesc, 1u);
                                 }
                             }
                             if (!RESIDENT) ptx::umma_commit(&b_empty[bstage]);
@@ -265,23 +310,57 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                         ptx::tmem_ld16(taddr + c0 + 16, r1);
                         ptx::tmem_ld_wait();
                         if (valid) {
+                            float v[32];
 #pragma unroll
-                            for (int hh = 0; hh < 2; ++hh) {
-                                const uint32_t* r = hh ? r1 : r0;
-                                const int cc = c0 + hh * 16;
+                            for (int jj = 0; jj < 32; jj += 4) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(biasp + c0 + jj));
+                                const uint32_t* r = (jj < 16) ? &r0[jj] : &r1[jj - 16];
+                                v[jj] = __uint_as_float(r[0]) + b4.x; v[jj + 1] = __uint_as_float(r[1]) + b4.y;
+                                v[jj + 2] = __uint_as_float(r[2]) + b4.z; v[jj + 3] = __uint_as_float(r[3]) + b4.w;
+                            }
+                            if (resp) {
+                                if (PREC == PREC_TF32) {
 #pragma unroll
-                                for (int jj = 0; jj < 16; jj += 4) {
-                                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(biasp + cc + jj));
-                                    float v0 = __uint_as_float(r[jj]) + b4.x, v1 = __uint_as_float(r[jj + 1]) + b4.y;
-                                    float v2 = __uint_as_float(r[jj + 2]) + b4.z, v3 = __uint_as_float(r[jj + 3]) + b4.w;
-                                    if (resp) {
-                                        const float4 r4 = __ldg(reinterpret_cast<const float4*>(resp + cc + jj));
-                                        v0 += r4.x; v1 += r4.y; v2 += r4.z; v3 += r4.w;
+                                    for (int jj = 0; jj < 32; jj += 4) {
+                                        const float4 r4 = __ldg(reinterpret_cast<const float4*>(resp + c0 + jj));
+                                        v[jj] += r4.x; v[jj + 1] += r4.y; v[jj + 2] += r4.z; v[jj + 3] += r4.w;
                                     }
-                                    if (g.act == ACT_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
-                                    else if (g.act == ACT_SELU) { v0 = selu_fast(v0); v1 = selu_fast(v1); v2 = selu_fast(v2); v3 = selu_fast(v3); }
-                                    if (g.round_tf32) { v0 = ptx::to_tf32(v0); v1 = ptx::to_tf32(v1); v2 = ptx::to_tf32(v2); v3 = ptx::to_tf32(v3); }
-                                    *reinterpret_cast<float4*>(outp + cc + jj) = make_float4(v0, v1, v2, v3);
+                                } else {
+                                    // residual chunk = [32 bf16 hi | 32 bf16 lo]
+                                    const uint4* rc = reinterpret_cast<const uint4*>(resp + c0);
+#pragma unroll
+                                    for (int qd = 0; qd < 4; ++qd) {
+                                        const uint4 h4 = __ldg(rc + qd), l4 = __ldg(rc + 4 + qd);
+                                        const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+                                        for (int e = 0; e < 4; ++e) {
+                                            const float2 hf = unpack2(hw[e]), lf = unpack2(lw[e]);
+                                            v[qd * 8 + e * 2] += hf.x + lf.x; v[qd * 8 + e * 2 + 1] += hf.y + lf.y;
+                                        }
+                                    }
+                                }
+                            }
+#pragma unroll
+                            for (int jj = 0; jj < 32; ++jj) {
+                                if (g.act == ACT_RELU) v[jj] = fmaxf(v[jj], 0.f);
+                                else if (g.act == ACT_SELU) v[jj] = selu_fast(v[jj]);
+                            }
+                            if (PREC == PREC_TF32) {
+#pragma unroll
+                                for (int jj = 0; jj < 32; jj += 4) {
+                                    float4 o = make_float4(v[jj], v[jj + 1], v[jj + 2], v[jj + 3]);
+                                    if (g.round_tf32) o = make_float4(ptx::to_tf32(o.x), ptx::to_tf32(o.y), ptx::to_tf32(o.z), ptx::to_tf32(o.w));
+                                    *reinterpret_cast<float4*>(outp + c0 + jj) = o;
+                                }
+                            } else {
+                                uint32_t hw[16], lw[16];
+#pragma unroll
+                                for (int e = 0; e < 16; ++e) split2(v[2 * e], v[2 * e + 1], hw[e], lw[e]);
+                                uint4* oc = reinterpret_cast<uint4*>(outp + c0);
+#pragma unroll
+                                for (int qd = 0; qd < 4; ++qd) {
+                                    oc[qd] = make_uint4(hw[qd * 4], hw[qd * 4 + 1], hw[qd * 4 + 2], hw[qd * 4 + 3]);
+                                    oc[4 + qd] = make_uint4(lw[qd * 4], lw[qd * 4 + 1], lw[qd * 4 + 2], lw[qd * 4 + 3]);
                                 }
                             }
                         }
@@ -300,7 +379,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                 const uint32_t acc_phase = (it / C::kNAcc) & 1;
                 const WorkUnit wu = decode_work(tile, m_units, t);
                 const TileCoord2 tc = decode2(wu.mp, t);
-                float* stage = reinterpret_cast<float*>(sP + (it & 1) * ((kPoolStageBytes + 1023) & ~1023));
+                float* stage = reinterpret_cast<float*>(sP + (C::kPoolBufs == 2 ? (it & 1) : 0) * ((kPoolStageBytes + 1023) & ~1023));
                 const int cy = tc.oy + cy_l, cx = tc.ox + cx_l;             // conv output coordinates
                 const bool cvalid = (row < 121) && cy >= 0 && cy < 88 && cx >= 0 && cx < 88;
 
@@ -344,12 +423,24 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                             m.x = fmaxf(m.x, s4.x); m.y = fmaxf(m.y, s4.y); m.z = fmaxf(m.z, s4.z); m.w = fmaxf(m.w, s4.w);
                         }
                     const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c4));
-                    float v0 = selu_fast(m.x + b4.x), v1 = selu_fast(m.y + b4.y), v2 = selu_fast(m.z + b4.z), v3 = selu_fast(m.w + b4.w);
-                    if (g.round_tf32) { v0 = ptx::to_tf32(v0); v1 = ptx::to_tf32(v1); v2 = ptx::to_tf32(v2); v3 = ptx::to_tf32(v3); }
+                    const float v0 = selu_fast(m.x + b4.x), v1 = selu_fast(m.y + b4.y), v2 = selu_fast(m.z + b4.z), v3 = selu_fast(m.w + b4.w);
                     const int n = tc.n0;
-                    if (n < g.n_img)
-                        *reinterpret_cast<float4*>(p.out + ((static_cast<size_t>(n) * g.Ho + oy) * g.Wo + ox) * g.out_cstride + g.out_coff + c4) = make_float4(v0, v1, v2, v3);
+                    if (n >= g.n_img) continue;
+                    float* po = p.out + ((static_cast<size_t>(n) * g.Ho + oy) * g.Wo + ox) * g.out_cstride + g.out_coff;
+                    if (PREC == PREC_TF32) {
+                        float4 o = make_float4(v0, v1, v2, v3);
+                        if (g.round_tf32) o = make_float4(ptx::to_tf32(o.x), ptx::to_tf32(o.y), ptx::to_tf32(o.z), ptx::to_tf32(o.w));
+                        *reinterpret_cast<float4*>(po + c4) = o;
+                    } else {
+                        // channel c4..c4+3 of chunk c4/32: hi at byte (c4%32)*2, lo 64 bytes further
+                        uint32_t h0, l0, h1, l1;
+                        split2(v0, v1, h0, l0); split2(v2, v3, h1, l1);
+                        uint8_t* cb = reinterpret_cast<uint8_t*>(po + (c4 & ~31)) + (c4 & 31) * 2;
+                        *reinterpret_cast<uint2*>(cb) = make_uint2(h0, h1);
+                        *reinterpret_cast<uint2*>(cb + 64) = make_uint2(l0, l1);
+                    }
                 }
+                if (C::kPoolBufs == 1) asm volatile("bar.sync 1, 256;" ::: "memory");   // single staging buffer: readers done before the next tile writes
             }
         }
     }
@@ -359,37 +450,47 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
     if (warp == 2) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, C::kTmemCols); }
 }
 
-template <int BN, bool RESIDENT, bool POOL, int MT>
+template <int BN, bool RESIDENT, bool POOL, int MT, int PREC>
 cudaError_t launch2(const UmmaMaps& maps, const ConvGeom& g, const Umma2Plan& t, const ConvPtrs& p, int num_sms, cudaStream_t stream) {
-    using C = Cfg2<BN, RESIDENT, POOL, MT>;
-    const int w_tiles = g.num_taps * t.chunks;
+    using C = Cfg2<BN, RESIDENT, POOL, MT, PREC>;
+    const int w_tiles = g.num_taps * t.chunks * C::kWPerTap;
     const size_t smem = static_cast<size_t>(C::kAStages) * C::kAStage + static_cast<size_t>(RESIDENT ? w_tiles : C::kBStages) * C::kBTile +
-                        (POOL ? 2 * ((kPoolStageBytes + 1023) & ~1023) : 0) + 1024 + 512;
+                        C::kPoolBufs * ((kPoolStageBytes + 1023) & ~1023) + 1024 + 512;
     if (smem > 232448) return cudaErrorInvalidConfiguration;
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
-        cudaError_t e = cudaFuncSetAttribute(conv_umma2_kernel<BN, RESIDENT, POOL, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        cudaError_t e = cudaFuncSetAttribute(conv_umma2_kernel<BN, RESIDENT, POOL, MT, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;
         attr_smem = smem;
     }
     const int total = ((t.m_tiles + MT - 1) / MT) * t.n_tiles * g.groups;
     const int grid = total < num_sms ? total : num_sms;
-    conv_umma2_kernel<BN, RESIDENT, POOL, MT><<<grid, kThreads2, smem, stream>>>(maps, g, t, p);
+    conv_umma2_kernel<BN, RESIDENT, POOL, MT, PREC><<<grid, kThreads2, smem, stream>>>(maps, g, t, p);
     return cudaGetLastError();
+}
+
+template <int PREC>
+cudaError_t dispatch2(const UmmaMaps& maps, const ConvGeom& g, const Umma2Plan& t, const ConvPtrs& p,
+                      int block_n, bool resident, bool pool, int m_per_cta, int num_sms, cudaStream_t stream) {
+    if (pool) return (block_n == 64 && resident) ? launch2<64, true, true, 1, PREC>(maps, g, t, p, num_sms, stream) : cudaErrorInvalidValue;
+    if (resident) return block_n == 64 ? launch2<64, true, false, 1, PREC>(maps, g, t, p, num_sms, stream) : cudaErrorInvalidValue;
+    switch (block_n) {
+        case 128: return launch2<128, false, false, 1, PREC>(maps, g, t, p, num_sms, stream);
+        case 256: return m_per_cta == 2 ? launch2<256, false, false, 2, PREC>(maps, g, t, p, num_sms, stream)
+                                        : launch2<256, false, false, 1, PREC>(maps, g, t, p, num_sms, stream);
+        default:  return cudaErrorInvalidValue;
+    }
 }
 
 }  // namespace
 
 cudaError_t launch_conv_umma2(const UmmaMaps& maps, const ConvGeom& g, const Umma2Plan& t, const ConvPtrs& p,
-                              int block_n, bool resident, bool pool, int m_per_cta, int num_sms, cudaStream_t stream) {
-    if (pool) return (block_n == 64 && resident) ? launch2<64, true, true, 1>(maps, g, t, p, num_sms, stream) : cudaErrorInvalidValue;
-    if (resident) return block_n == 64 ? launch2<64, true, false, 1>(maps, g, t, p, num_sms, stream) : cudaErrorInvalidValue;
-    switch (block_n) {
-        case 64:  return launch2<64, false, false, 1>(maps, g, t, p, num_sms, stream);
-        case 128: return launch2<128, false, false, 1>(maps, g, t, p, num_sms, stream);
-        case 256: return m_per_cta == 2 ? launch2<256, false, false, 2>(maps, g, t, p, num_sms, stream)
-                                        : launch2<256, false, false, 1>(maps, g, t, p, num_sms, stream);
-        default:  return cudaErrorInvalidValue;
+                              int block_n, bool resident, bool pool, int m_per_cta, int prec, int num_sms, cudaStream_t stream) {
+    switch (prec) {
+        case PREC_TF32:   return dispatch2<PREC_TF32>(maps, g, t, p, block_n, resident, pool, m_per_cta, num_sms, stream);
+        case PREC_BF16X3: return dispatch2<PREC_BF16X3>(maps, g, t, p, block_n, resident, pool, m_per_cta, num_sms, stream);
+        case PREC_BF16:   return dispatch2<PREC_BF16>(maps, g, t, p, block_n, resident, pool, m_per_cta, num_sms, stream);
+        default:          return cudaErrorInvalidValue;
     }
 }
 

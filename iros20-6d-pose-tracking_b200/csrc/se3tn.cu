@@ -81,6 +81,9 @@ struct WeightSet {
     size_t w_off[14], b_off[14];
     size_t fc_off;
     CUtensorMap bmap[14];           // over dev_tf32
+    uint8_t* dev_bf16 = nullptr;    // blob-sized: conv weights as [32 bf16 hi | 32 bf16 lo] per 32-word K chunk
+    uint8_t* dev_stem_bf16 = nullptr;  // 2 x [64][448 words]: stem weights, two tiles per filter row (see aux_kernels.cu)
+    CUtensorMap bmap_bf16[14];
     float mean32[8], std32[8];
     double mean64[8], std64[8];
     int stats_f64 = 0;
@@ -121,6 +124,11 @@ struct se3tn_ctx {
 };
 
 namespace {
+
+// conv-input storage mode of the packers for a precision: 0 raw fp32, 1 tf32 words, 2 bf16 hi/lo per pixel
+inline int store_mode_of(int precision) {
+    return precision == SE3TN_PREC_TF32 ? 1 : (precision == SE3TN_PREC_BF16X3 || precision == SE3TN_PREC_BF16) ? 2 : 0;
+}
 
 int fail(se3tn_ctx* c, int code, const std::string& msg) {
     if (c) c->err = msg; else g_create_error = msg;
@@ -405,10 +413,13 @@ int run_network(se3tn_ctx* c, int weight_id, int first, int n, int precision,
     auto it = c->weights.find(weight_id);
     if (it == c->weights.end()) return fail(c, SE3TN_ERR_STATE, "weight set " + std::to_string(weight_id) + " not loaded");
     const WeightSet& ws = it->second;
+    const bool bf16 = (precision == SE3TN_PREC_BF16X3 || precision == SE3TN_PREC_BF16);
     const bool tf32 = (precision == SE3TN_PREC_TF32);
-    if (!tf32 && precision != SE3TN_PREC_FP32) return fail(c, SE3TN_ERR_INVALID, "unknown precision");
+    const bool tensor = tf32 || bf16;
+    if (!tensor && precision != SE3TN_PREC_FP32) return fail(c, SE3TN_ERR_INVALID, "unknown precision");
+    if (bf16 && c->conv_version != 2) return fail(c, SE3TN_ERR_INVALID, "bf16 modes need the v2 conv kernel (unset SE3TN_CONV)");
+    const int kprec = tf32 ? 0 : (precision == SE3TN_PREC_BF16X3 ? 1 : 2);
     const float* wbase = tf32 ? ws.dev_tf32 : ws.dev;
-
     auto bufp = [&](Buf b) { return c->buf[b] + kBufFloats[b] * static_cast<size_t>(first); };
     for (int li = 0; li < 14; ++li) {
         const LayerSpec& L = kLayers[li];
@@ -416,11 +427,11 @@ int run_network(se3tn_ctx* c, int weight_id, int first, int n, int precision,
         ConvPtrs p;
         p.in = bufp(L.in); p.out = bufp(L.out); p.res = (L.res != NONE) ? bufp(L.res) : nullptr;
         p.w = wbase + ws.w_off[li]; p.bias = ws.dev + ws.b_off[li];
-        if (tf32 && c->conv_version == 2) {
+        if (tensor && c->conv_version == 2) {
             UmmaMaps maps;
             const int nmaps = (L.kind == K_STEM) ? 2 : (L.kind == K_S2 ? 4 : 1);
             for (int m = 0; m < 7; ++m) maps.a[m] = c->amap2[li][m < nmaps ? m : 0];
-            maps.b = ws.bmap[li];
+            maps.b = bf16 ? ws.bmap_bf16[li] : ws.bmap[li];
             const int BN = block_n_of(c, L);
             const bool pool = (L.kind == K_STEM);
             const bool resident = (BN == 64 && L.cout == 64);
@@ -432,7 +443,7 @@ int run_network(se3tn_ctx* c, int weight_id, int first, int n, int precision,
                 p.out = c->buf[li == 0 ? B_P1A : B_P1B];
                 g.out_cstride = 64; g.out_coff = 0;
             }
-            { ProfScope ps(c, li, s); CU_TRY(c, launch_conv_umma2(maps, g, t, p, BN, resident, pool, (BN == 256 && c->dual_m) ? 2 : 1, c->num_sms, s)); }
+            { ProfScope ps(c, li, s); CU_TRY(c, launch_conv_umma2(maps, g, t, p, BN, resident, pool, (BN == 256 && c->dual_m) ? 2 : 1, kprec, c->num_sms, s)); }
             ++c->launches;
             continue;
         }
@@ -461,9 +472,9 @@ int run_network(se3tn_ctx* c, int weight_id, int first, int n, int precision,
         if (li == 0) { ProfScope ps(c, 14, s); CU_TRY(c, launch_maxpool(bufp(B_Y1A), bufp(B_P1A), n, 88, 88, 64, s)); ++c->launches; }
         if (li == 1) { ProfScope ps(c, 15, s); CU_TRY(c, launch_maxpool(bufp(B_Y1B), bufp(B_P1B), n, 88, 88, 64, s)); ++c->launches; }
     }
-    { ProfScope ps(c, 16, s); CU_TRY(c, launch_head(bufp(B_H3), ws.dev + ws.fc_off, ws.dev + ws.fc_off + 6 * 512, out_trans, out_rot, n, 121, s)); }
+    { ProfScope ps(c, 16, s); CU_TRY(c, launch_head(bufp(B_H3), ws.dev + ws.fc_off, ws.dev + ws.fc_off + 6 * 512, out_trans, out_rot, n, 121, bf16 ? 1 : 0, s)); }
     ++c->launches;
-    if (out_feature) { CU_TRY(c, launch_nhwc_to_nchw(bufp(B_F2), out_feature, n, 22 * 22, 256, s)); ++c->launches; }
+    if (out_feature) { CU_TRY(c, launch_nhwc_to_nchw(bufp(B_F2), out_feature, n, 22 * 22, 256, bf16 ? 1 : 0, s)); ++c->launches; }
     return SE3TN_OK;
 }
 
@@ -535,7 +546,7 @@ int se3tn_create(int device, int max_batch, void* workspace, se3tn_ctx** out) {
 void se3tn_destroy(se3tn_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    for (auto& kv : c->weights) { cudaFree(kv.second.dev); cudaFree(kv.second.dev_tf32); }
+    for (auto& kv : c->weights) { cudaFree(kv.second.dev); cudaFree(kv.second.dev_tf32); cudaFree(kv.second.dev_bf16); cudaFree(kv.second.dev_stem_bf16); }
     cudaFree(c->d_mean32); cudaFree(c->d_std32); cudaFree(c->d_mean64); cudaFree(c->d_std64);
     for (int i = 0; i < SE3TN_PROFILE_SLOTS; ++i) { if (c->ev0[i]) cudaEventDestroy(c->ev0[i]); if (c->ev1[i]) cudaEventDestroy(c->ev1[i]); }
     if (c->own_workspace) cudaFree(c->workspace);
@@ -553,6 +564,8 @@ int se3tn_load_weights(se3tn_ctx* c, int weight_id, const float* blob, size_t n_
     if (!ws.dev) {
         CU_TRY(c, cudaMalloc(&ws.dev, expect * sizeof(float)));
         CU_TRY(c, cudaMalloc(&ws.dev_tf32, expect * sizeof(float)));
+        CU_TRY(c, cudaMalloc(&ws.dev_bf16, expect * sizeof(float)));
+        CU_TRY(c, cudaMalloc(&ws.dev_stem_bf16, 2 * 64 * 448 * sizeof(float)));
     }
     CU_TRY(c, cudaDeviceSynchronize());
     CU_TRY(c, cudaMemcpy(ws.dev, blob, expect * sizeof(float), cudaMemcpyHostToDevice));
@@ -567,7 +580,19 @@ int se3tn_load_weights(se3tn_ctx* c, int weight_id, const float* blob, size_t n_
         char what[48]; snprintf(what, sizeof what, "layer %d weights", li);
         int rc = make_map2(c, &ws.bmap[li], ws.dev_tf32 + ws.w_off[li], layer_ktot(L), layer_rows(L), block_n_of(c, L), what);
         if (rc) return rc;
+        snprintf(what, sizeof what, "layer %d bf16 weights", li);
+        if (L.kind == K_STEM) {
+            uint8_t* dst = ws.dev_stem_bf16 + static_cast<size_t>(li) * 64 * 448 * sizeof(float);
+            CU_TRY(c, launch_split_stem_weights(ws.dev + ws.w_off[li], dst, 0));
+            rc = make_map2(c, &ws.bmap_bf16[li], dst, 448, 64, 64, what);
+        } else {
+            uint8_t* dst = ws.dev_bf16 + ws.w_off[li] * sizeof(float);
+            CU_TRY(c, launch_split_weights(ws.dev + ws.w_off[li], dst, static_cast<size_t>(layer_rows(L)) * layer_ktot(L), 0));
+            rc = make_map2(c, &ws.bmap_bf16[li], dst, layer_ktot(L), layer_rows(L), block_n_of(c, L), what);
+        }
+        if (rc) return rc;
     }
+    CU_TRY(c, cudaDeviceSynchronize());
     ws.fc_off = off;
     return SE3TN_OK;
 }
@@ -607,7 +632,7 @@ int se3tn_preprocess(se3tn_ctx* c, const uint8_t* frame_rgb, const uint16_t* fra
     a.fx = K[0]; a.fy = K[1]; a.cx = K[2]; a.cy = K[3];
     a.poses = poses; a.object_width = object_width; a.rgbA = rgbA; a.depthA = depthA; a.weight_ids = weight_ids;
     a.mean32 = c->d_mean32; a.std32 = c->d_std32; a.mean64 = c->d_mean64; a.std64 = c->d_std64;
-    a.stats_f64 = c->stats_f64; a.round_tf32 = (precision == SE3TN_PREC_TF32); a.b_precropped = 0;
+    a.stats_f64 = c->stats_f64; a.round_tf32 = store_mode_of(precision); a.b_precropped = 0;
     a.stemA = c->buf[B_X0A]; a.stemB = c->buf[B_X0B]; a.nchwA = out_A; a.nchwB = out_B;
     a.crop_rgb = crop_rgb; a.crop_depth = crop_depth;
     { ProfScope ps(c, 17, s); CU_TRY(c, launch_preprocess(a, n, s)); }
@@ -629,7 +654,7 @@ int se3tn_normalize(se3tn_ctx* c, const uint8_t* rgbA, const uint16_t* depthA, c
     a.frame_rgb = rgbB; a.frame_depth = depthB; a.H = kImg; a.W = kImg; a.b_precropped = 1;
     a.poses = poses; a.rgbA = rgbA; a.depthA = depthA; a.weight_ids = weight_ids;
     a.mean32 = c->d_mean32; a.std32 = c->d_std32; a.mean64 = c->d_mean64; a.std64 = c->d_std64;
-    a.stats_f64 = c->stats_f64; a.round_tf32 = (precision == SE3TN_PREC_TF32);
+    a.stats_f64 = c->stats_f64; a.round_tf32 = store_mode_of(precision);
     a.stemA = c->buf[B_X0A]; a.stemB = c->buf[B_X0B]; a.nchwA = out_A; a.nchwB = out_B;
     { ProfScope ps(c, 17, s); CU_TRY(c, launch_preprocess(a, n, s)); }
     ++c->launches;
@@ -664,7 +689,7 @@ int se3tn_forward(se3tn_ctx* c, int weight_id, const float* A, const float* B, i
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     CU_TRY(c, cudaSetDevice(c->device));
     c->launches = 0;
-    const int round = (precision == SE3TN_PREC_TF32);
+    const int round = store_mode_of(precision);
     { ProfScope ps(c, 19, s);
       CU_TRY(c, launch_nchw_to_stem(A, c->buf[B_X0A], n, round, s));
       CU_TRY(c, launch_nchw_to_stem(B, c->buf[B_X0B], n, round, s)); }

@@ -12,7 +12,7 @@ import torch
 class TrackDataset:
     def __init__(self, root, mode, images_mean, images_std, pretransforms=None, augmentations=None,
                  posttransforms=None, dataset_info=None, trans_normalizer=0.03, rot_normalizer=5 * np.pi / 180,
-                 engine=None, weight_id=0, precision='tf32'):
+                 engine=None, weight_id=0, precision='bf16x3'):
         if pretransforms is not None or augmentations is not None:
             raise NotImplementedError('train-time transforms are out of scope (inference passes None, predict.py:191)')
         self.root = root

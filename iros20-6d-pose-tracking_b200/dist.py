@@ -54,7 +54,7 @@ class ShardedTracker:
     """Runs this rank's slice of a multi-object track set through an Engine and (optionally) gathers
     all poses.  `engine` needs every weight set referenced by this rank's slice loaded."""
     def __init__(self, engine, weight_ids, K, object_width, trans_normalizer, rot_normalizer,
-                 rank=0, world_size=1, precision='tf32'):
+                 rank=0, world_size=1, precision='bf16x3'):
         self.engine = engine
         self.rank, self.world_size = rank, world_size
         self.weight_ids = np.asarray(weight_ids, dtype=np.int32)

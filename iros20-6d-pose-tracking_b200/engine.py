@@ -11,7 +11,7 @@ import torch
 from . import _lib
 from .weights import pack_state_dict
 
-PREC = {'tf32': _lib.PREC_TF32, 'fp32': _lib.PREC_FP32}
+PREC = {'tf32': _lib.PREC_TF32, 'fp32': _lib.PREC_FP32, 'bf16x3': _lib.PREC_BF16X3, 'bf16': _lib.PREC_BF16}
 IMAGE_SIZE = 176
 
 
@@ -72,7 +72,7 @@ class Engine:
                                             std.ctypes.data_as(C.c_void_p), int(f64)), self._ctx)
 
     # ------------------------------------------------------------------ hot path
-    def forward(self, A, B, weight_id=0, precision='tf32', want_feature=False):
+    def forward(self, A, B, weight_id=0, precision='bf16x3', want_feature=False):
         """Se3TrackNet.forward on float32 (n,4,176,176) CUDA tensors -> (trans, rot, feature|None)."""
         self._check_img(A); self._check_img(B)
         n = A.shape[0]
@@ -90,7 +90,7 @@ class Engine:
         return trans, rot, feat
 
     def preprocess(self, frame_rgb, frame_depth, K, poses, object_width, rgbA, depthA, weight_ids=None,
-                   precision='tf32', want_tensors=False, want_crops=False):
+                   precision='bf16x3', want_tensors=False, want_crops=False):
         n = poses.shape[0]
         self._check_frame(frame_rgb, frame_depth, rgbA, depthA, poses, object_width, n)
         H, W = frame_depth.shape
@@ -109,7 +109,7 @@ class Engine:
                                              _stream(self.device)), self._ctx)
         return outA, outB, crop_rgb, crop_depth
 
-    def normalize(self, rgbA, depthA, rgbB, depthB, poses, weight_ids=None, precision='tf32', want_tensors=True):
+    def normalize(self, rgbA, depthA, rgbB, depthB, poses, weight_ids=None, precision='bf16x3', want_tensors=True):
         """processData's post-transforms on existing 176x176 crops (all CUDA tensors)."""
         n = poses.shape[0]
         outA = outB = None
@@ -139,7 +139,7 @@ class Engine:
                                             _stream(self.device)), self._ctx)
         return crop_rgb, crop_depth
 
-    def forward_preprocessed(self, n, weight_id=0, first=0, precision='tf32', want_feature=False):
+    def forward_preprocessed(self, n, weight_id=0, first=0, precision='bf16x3', want_feature=False):
         trans = torch.empty(n, 3, dtype=torch.float32, device=self.device)
         rot = torch.empty(n, 3, dtype=torch.float32, device=self.device)
         feat = torch.empty(n, 256, 22, 22, dtype=torch.float32, device=self.device) if want_feature else None
@@ -166,7 +166,7 @@ class Engine:
 
     def track_batch(self, frame_rgb, frame_depth, K, poses, object_width, rgbA, depthA,
                     trans_normalizer, rot_normalizer, weight_ids_host=None, weight_ids_dev=None,
-                    precision='tf32', out_poses=None, out_trans=None, out_rot=None):
+                    precision='bf16x3', out_poses=None, out_trans=None, out_rot=None):
         """n independent tracks of one frame: K0 -> conv stack -> K6, all enqueued on the current stream."""
         n = poses.shape[0]
         self._check_frame(frame_rgb, frame_depth, rgbA, depthA, poses, object_width, n)

@@ -91,7 +91,7 @@ def _as_numpy_pose(p):
 
 class Tracker:
     def __init__(self, dataset_info, images_mean, images_std, ckpt_dir, model_path=None, trans_normalizer=0.03,
-                 rot_normalizer=5 * np.pi / 180, engine=None, weight_id=0, renderer=None, precision='tf32', max_batch=64):
+                 rot_normalizer=5 * np.pi / 180, engine=None, weight_id=0, renderer=None, precision='bf16x3', max_batch=64):
         self.dataset_info = dataset_info
         self.image_size = (dataset_info['resolution'], dataset_info['resolution'])
         if self.image_size[0] != 176:

@@ -11,7 +11,7 @@ from .engine import Engine
 
 
 class Se3TrackNet(torch.nn.Module):
-    def __init__(self, image_size=174, max_batch=64, precision='tf32', engine=None, weight_id=0):
+    def __init__(self, image_size=174, max_batch=64, precision='bf16x3', engine=None, weight_id=0):
         super().__init__()
         self.rot_dim = 3
         self.image_size = image_size          # unused by the reference too (fully convolutional, F5)

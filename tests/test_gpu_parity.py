@@ -4,7 +4,11 @@ same seeded inputs, and against the golden fixtures produced by the reference's 
 Tolerances:
   * integer / byte / index work (bbox, crops): bit-exact
   * preprocessing floats (fp32 chain):          bit-exact (same IEEE ops as numpy)
-  * network 6-vector, TF32 tensor-core path:    rtol 1e-3 / atol 1e-4 (BASELINE.json north_star)
+  * network 6-vector, BF16X3 tensor-core path (the default): rtol 1e-3 / atol 1e-4 (BASELINE.json
+    north_star) on EVERY case here, including large-magnitude raw-regime inputs and both weight seeds
+  * network 6-vector, TF32 tensor-core path:    same gate where its 10-bit operands allow it (tensor
+    regime, raw regime with weight seed 0); documented to exceed it on raw regime / weight seed 1
+  * network 6-vector, BF16 (1 product) path:    rtol 5e-2 / atol 2e-2 (BASELINE configs[2], bf16 operands)
   * network 6-vector, FP32 FFMA path:           rtol 1e-4 / atol 2e-6
   * pose update / so(3) log (fp64 + libm trig): atol 1e-7 / 1e-9
   * poses produced from a TF32 6-vector: the gate propagated through datasets.py:169-174,
@@ -19,6 +23,7 @@ import se3_oracle as O
 pytestmark = pytest.mark.gpu
 RTOL, ATOL = 1e-3, 1e-4
 POSE_ATOL = 1e-4
+GATES = {'bf16x3': (RTOL, ATOL), 'tf32': (RTOL, ATOL), 'fp32': (1e-4, 2e-6), 'bf16': (5e-2, 2e-2)}
 
 
 def sha(a):
@@ -60,14 +65,14 @@ def test_config1_parity_gate(pkg, synth, golden_dir, eng):
     dev = eng.device
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)[None]).to(dev)
     ref = torch.from_numpy(np.concatenate([g['c1_trans'], g['c1_rot']], 1))
-    for prec, (rt, at) in {'tf32': (RTOL, ATOL), 'fp32': (1e-4, 2e-6)}.items():
+    for prec, (rt, at) in GATES.items():
         # `precision` also selects whether the conv-input buffers hold tf32-rounded values
         tA, tB = eng.normalize(t(rgbA), t(depthA), t(rgbB), t(depthB), torch.from_numpy(pose[None]).to(dev), precision=prec)
         assert sha(tA[0].cpu().numpy()) == str(g['c1_dataA_sha']) and sha(tB[0].cpu().numpy()) == str(g['c1_dataB_sha'])
         trans, rot, _ = eng.forward_preprocessed(1, weight_id=0, precision=prec)
         assert_gate(six(trans, rot), ref, rt, at)
         pose_out = eng.pose_update(torch.from_numpy(pose[None]).to(dev), trans, rot, 0.03, 5 * np.pi / 180)[0].cpu().numpy()
-        assert np.allclose(pose_out, g['c1_pose_out'], rtol=0, atol=POSE_ATOL if prec == 'tf32' else 1e-7)
+        assert np.allclose(pose_out, g['c1_pose_out'], rtol=0, atol={'fp32': 1e-7, 'bf16': 2e-3}.get(prec, POSE_ATOL))
 
 
 @pytest.mark.parametrize('n', [1, 2, 3, 7])
@@ -76,19 +81,20 @@ def test_forward_matches_oracle_small_batches(synth, eng, n):
     A, B = synth.tensor_pairs(n, seed=10 + n)
     ref = O.forward(sd, A, B)
     ref6 = torch.cat((ref['trans'], ref['rot']), 1)
-    for prec, (rt, at) in {'tf32': (RTOL, ATOL), 'fp32': (1e-4, 2e-6)}.items():
+    for prec, (rt, at) in GATES.items():
         trans, rot, feat = eng.forward(A.to(eng.device), B.to(eng.device), precision=prec, want_feature=True)
         assert_gate(six(trans, rot), ref6, rt, at)
-        ftol = 2e-2 if prec == 'tf32' else 1e-4
+        ftol = {'tf32': 2e-2, 'bf16x3': 2e-4, 'bf16': 1e-1, 'fp32': 1e-4}[prec]
         assert (feat.cpu() - ref['feature']).abs().max().item() < ftol * ref['feature'].abs().max().item()
 
 
 def test_forward_golden_fixture(synth, golden_dir, eng):
     g = np.load(os.path.join(golden_dir, 'golden_model.npz'))
     A, B = synth.tensor_pairs(2, seed=0)
-    trans, rot, feat = eng.forward(A.to(eng.device), B.to(eng.device), precision='tf32', want_feature=True)
-    assert_gate(six(trans, rot), torch.from_numpy(np.concatenate([g['trans'], g['rot']], 1)))
-    assert np.abs(feat.cpu().numpy()[:, ::16, ::3, ::3] - g['feature_sub']).max() < 2e-2 * np.abs(g['feature_sub']).max()
+    for prec, ftol in (('bf16x3', 2e-4), ('tf32', 2e-2)):
+        trans, rot, feat = eng.forward(A.to(eng.device), B.to(eng.device), precision=prec, want_feature=True)
+        assert_gate(six(trans, rot), torch.from_numpy(np.concatenate([g['trans'], g['rot']], 1)))
+        assert np.abs(feat.cpu().numpy()[:, ::16, ::3, ::3] - g['feature_sub']).max() < ftol * np.abs(g['feature_sub']).max()
 
 
 def test_batch64_full_size_properties(synth, eng):
@@ -98,19 +104,23 @@ def test_batch64_full_size_properties(synth, eng):
     sd = synth.make_state_dict(0)
     A, B = synth.tensor_pairs(64, seed=2)
     Ad, Bd = A.to(eng.device), B.to(eng.device)
-    t1, r1, _ = eng.forward(Ad, Bd, precision='tf32')
     ref = O.forward(sd, A, B)
-    worst = assert_gate(six(t1, r1), torch.cat((ref['trans'], ref['rot']), 1))
-    print('batch-64 TF32 worst err/tol: %.3f' % worst)
-    t2, r2, _ = eng.forward(Ad, Bd, precision='tf32')
-    assert torch.equal(t1, t2) and torch.equal(r1, r2)                       # deterministic
-    perm = torch.randperm(64, generator=torch.Generator().manual_seed(0)).to(eng.device)
-    t3, r3, _ = eng.forward(Ad[perm].contiguous(), Bd[perm].contiguous(), precision='tf32')
-    assert torch.equal(t3, t1[perm]) and torch.equal(r3, r1[perm])           # per-pair independence
-    t4, r4, _ = eng.forward(Ad[:5].contiguous(), Bd[:5].contiguous(), precision='tf32')
-    assert torch.equal(t4, t1[:5]) and torch.equal(r4, r1[:5])               # ragged tail of a batch
+    ref6 = torch.cat((ref['trans'], ref['rot']), 1)
+    for prec in ('bf16x3', 'tf32'):
+        t1, r1, _ = eng.forward(Ad, Bd, precision=prec)
+        worst = assert_gate(six(t1, r1), ref6)
+        print('batch-64 %s worst err/tol: %.3f' % (prec, worst))
+        t2, r2, _ = eng.forward(Ad, Bd, precision=prec)
+        assert torch.equal(t1, t2) and torch.equal(r1, r2)                       # deterministic
+        perm = torch.randperm(64, generator=torch.Generator().manual_seed(0)).to(eng.device)
+        t3, r3, _ = eng.forward(Ad[perm].contiguous(), Bd[perm].contiguous(), precision=prec)
+        assert torch.equal(t3, t1[perm]) and torch.equal(r3, r1[perm])           # per-pair independence
+        t4, r4, _ = eng.forward(Ad[:5].contiguous(), Bd[:5].contiguous(), precision=prec)
+        assert torch.equal(t4, t1[:5]) and torch.equal(r4, r1[:5])               # ragged tail of a batch
     tf, rf, _ = eng.forward(Ad, Bd, precision='fp32')
-    assert_gate(six(tf, rf), torch.cat((ref['trans'], ref['rot']), 1), 1e-4, 2e-6)
+    assert_gate(six(tf, rf), ref6, 1e-4, 2e-6)
+    tb, rb, _ = eng.forward(Ad, Bd, precision='bf16')
+    print('batch-64 bf16 worst err/(5e-2,2e-2): %.3f' % assert_gate(six(tb, rb), ref6, 5e-2, 2e-2))
 
 
 def test_second_weight_set_and_module_api(pkg, synth):
@@ -151,7 +161,7 @@ def test_preprocess_bit_exact_vs_oracle(synth, eng):
     tA, tB, crgb, cdepth = eng.preprocess(torch.from_numpy(rgb).to(dev), torch.from_numpy(depth).to(dev), synth.CAMERA_K,
                                           torch.from_numpy(poses).to(dev), torch.from_numpy(ow).to(dev),
                                           torch.from_numpy(rgbA).to(dev), torch.from_numpy(depthA).to(dev),
-                                          weight_ids=torch.from_numpy(wid).to(dev), want_tensors=True, want_crops=True)
+                                          weight_ids=torch.from_numpy(wid).to(dev), precision='tf32', want_tensors=True, want_crops=True)
     bbs = eng.compute_bbox(torch.from_numpy(poses).to(dev), synth.CAMERA_K, torch.from_numpy(ow).to(dev)).cpu().numpy()
     for i in range(n):
         bb = O.compute_bbox(poses[i], synth.CAMERA_K, ow[i], scale=(1000, 1000, 1000))
@@ -287,16 +297,27 @@ def test_track_batch_mixed_weight_sets(synth, eng):
     ow = torch.full((n,), 200.0, dtype=torch.float64, device=dev)
     args = (torch.from_numpy(rgb).to(dev), torch.from_numpy(depth).to(dev), synth.CAMERA_K, torch.from_numpy(poses).to(dev), ow,
             torch.from_numpy(rgbA).to(dev), torch.from_numpy(depthA).to(dev), 0.03, 5 * np.pi / 180)
-    out, tr, ro = eng.track_batch(*args, weight_ids_host=wid)
     mean, std = synth.default_mean_std()
     stats = {0: (mean, std), 1: (mean + 1.5, std * 1.25)}
     sds = {0: synth.make_state_dict(0), 1: synth.make_state_dict(1)}
-    for i in range(n):
-        w = int(wid[i])
-        ref, dbg = O.on_track(sds[w], poses[i], rgb, depth, rgbA[i], depthA[i], synth.CAMERA_K, 200.0, *stats[w], return_all=True)
-        got6 = torch.cat((tr[i], ro[i])).cpu()
-        assert_gate(got6, torch.from_numpy(np.concatenate([dbg['trans'], dbg['rot']])))
-        assert np.abs(out[i].cpu().numpy() - ref).max() < POSE_ATOL
+    refs = [O.on_track(sds[int(wid[i])], poses[i], rgb, depth, rgbA[i], depthA[i], synth.CAMERA_K, 200.0, *stats[int(wid[i])], return_all=True)
+            for i in range(n)]
+    ref6 = torch.from_numpy(np.stack([np.concatenate([d['trans'], d['rot']]) for _, d in refs]))
+    worst = {}
+    for prec in ('bf16x3', 'tf32'):
+        out, tr, ro = eng.track_batch(*args, weight_ids_host=wid, precision=prec)
+        got6 = torch.cat((tr, ro), 1).cpu()
+        err = (got6 - ref6).abs() / (ATOL + RTOL * ref6.abs())
+        worst[prec] = err.max().item()
+        if prec == 'bf16x3':
+            assert_gate(got6, ref6)
+            for i in range(n):
+                assert np.abs(out[i].cpu().numpy() - refs[i][0]).max() < POSE_ATOL
+    print('raw regime, weight seeds 0/1: worst err/tol bf16x3 %.3f, tf32 %.3f' % (worst['bf16x3'], worst['tf32']))
+    # Large-magnitude inputs (F13) through 17 layers: TF32's 10-bit operands are not enough for the fp32 gate
+    # with weight seed 1 (CPU emulation of exact TF32 rounding predicts err/tol 3.4) -- this is why BF16X3 is the
+    # default.  Keep TF32 honest: it must stay in the same ballpark, not silently drift.
+    assert worst['bf16x3'] < 0.5 and worst['tf32'] < 8.0
 
 
 def test_errors_are_reported_not_fatal(pkg, synth, eng):
