@@ -15,6 +15,10 @@
 //     yields a 5x5 block of pooled outputs; max -> +bias -> SELU (monotone, so they commute) run
 //     on 1/4.84 of the values and the 88x88x64 intermediate never reaches HBM.
 //   * 8 epilogue warps (two per TMEM lane quadrant).
+//   * BN = 64 tiles (stem, 64-channel layers) round-robin their MMAs over kSplit = 4 partial
+//     accumulators that the epilogue sums: a 128x64x16 MMA is 32 tensor cycles but back-to-back MMAs
+//     into ONE accumulator were measured at ~105 cycles each (accumulate dependency latency; ncu:
+//     tensor pipe 38 % active with the issuing warp never blocked on a barrier).
 //   * MT = 2 ("dual-M", BN = 256 layers): one CTA carries TWO M tiles (two accumulators, all 512
 //     TMEM columns) through the K loop, so every weight tile fetched from L2 feeds 8 MMAs instead
 //     of 4 -- the weight stream, which is >80% of the fill traffic of the deep layers, halves.
@@ -38,7 +42,7 @@ namespace se3tn {
 namespace {
 
 constexpr int kThreads2 = 384;                 // warps: 0 A-TMA, 1 MMA, 2 TMEM alloc, 3 B-TMA, 4..11 epilogue
-// A unit buffer: (max row shift + 128) rows * 128 B, rounded to 1 KB: stem 33+128 rows -> 21 KB, 3x3 22+128 -> 20 KB
+// A unit buffer: (max row shift + 128) rows * 128 B, rounded to 1 KB: stem 33+128 rows -> 21 KB, 3x3 22+128 -> 19 KB
 constexpr int kPoolPitch = 68;                 // floats per staged conv position (64 + 4: bank spread)
 constexpr int kPoolStageBytes = 121 * kPoolPitch * 4;
 
@@ -46,14 +50,16 @@ enum { PREC_TF32 = 0, PREC_BF16X3 = 1, PREC_BF16 = 2 };
 
 template <int BN, bool RESIDENT, bool POOL, int MT, int PREC = 0> struct Cfg2 {
     static constexpr int kBTile = BN * kChunkBytes;
-    static constexpr int kAUnit = POOL ? 21 * 1024 : 20 * 1024;
+    static constexpr int kAUnit = POOL ? 21 * 1024 : 19 * 1024;     // 3x3: (22 + 128) rows * 128 B = 19,200
     static constexpr int kAStage = MT * kAUnit;
-    static constexpr int kAStages = RESIDENT ? ((POOL && PREC == PREC_TF32) ? 4 : 3) : (BN == 256 ? 3 : 4);
+    static constexpr int kAStages = RESIDENT ? ((POOL && PREC != PREC_TF32) ? 3 : 4) : (BN == 256 ? 3 : 4);
     static constexpr int kWPerTap = (POOL && PREC != PREC_TF32) ? 2 : 1;  // weight tiles per (tap, chunk)
     static constexpr int kPoolBufs = POOL ? (PREC == PREC_TF32 ? 2 : 1) : 0;
     static constexpr int kBStages = RESIDENT ? 0 : (BN == 256 ? (MT == 2 ? 3 : 4) : 6);
-    static constexpr int kNAcc = (2 * MT * BN <= 512) ? 2 : 1;         // accumulator sets (double-buffered when they fit)
-    static constexpr int kTmemCols = kNAcc * MT * BN;                   // 128 / 256 / 512
+    static constexpr int kSplit = (BN == 64) ? 4 : 1;                   // partial accumulators per tile (independent MMA chains)
+    static constexpr int kAccCols = MT * BN * kSplit;                   // TMEM columns of one accumulator set
+    static constexpr int kNAcc = (2 * kAccCols <= 512) ? 2 : 1;         // accumulator sets (double-buffered when they fit)
+    static constexpr int kTmemCols = kNAcc * kAccCols;                  // 256 / 512
 };
 
 __device__ __forceinline__ float selu_fast(float x) {
@@ -204,8 +210,8 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
             const uint32_t acc_phase = (it / C::kNAcc) & 1;
             ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
             ptx::tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * (MT * BN);
-            uint32_t accumulate = 0;
+            const uint32_t d_tmem = tmem_base + acc * C::kAccCols;
+            uint32_t cnt = 0;                       // MMAs issued into this tile so far (per M tile)
             for (int ch = 0; ch < t.chunks; ++ch) {
                 for (int u = 0; u < t.units_per_chunk; ++u) {
                     const int ntaps = t.units[u].ntaps;
@@ -231,35 +237,38 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
 #pragma unroll
                             for (int j = 0; j < MT; ++j) {
                                 const uint32_t aj = a_lo + j * (C::kAUnit >> 4);
-                                const uint32_t dj = d_tmem + j * BN;
+                                const uint32_t dj = d_tmem + j * (BN * C::kSplit);
                                 auto desc = [](uint32_t lo) { return (static_cast<uint64_t>(kDescHi) << 32) | lo; };
+                                // MMA number i of this tile goes to partial accumulator i % kSplit; its first visit zero-initialises
+                                auto dst = [&](uint32_t i) { return dj + ((cnt + i) & (C::kSplit - 1)) * BN; };
+                                auto accf = [&](uint32_t i) { return (cnt + i) >= static_cast<uint32_t>(C::kSplit) ? 1u : 0u; };
                                 if (PREC == PREC_TF32) {
 #pragma unroll
                                     for (int kk = 0; kk < 4; ++kk)
-                                        ptx::umma_tf32(dj, desc(aj + 2 * kk), desc(b_lo + 2 * kk), idesc, accumulate | (kk != 0));
+                                        ptx::umma_tf32(dst(kk), desc(aj + 2 * kk), desc(b_lo + 2 * kk), idesc, accf(kk));
                                 } else if (POOL) {
                                     // stem window = 8 pixels x [hi4|lo4]: pass 0 against [w_hi|w_hi], pass 1 against [w_lo|0]
 #pragma unroll
                                     for (int ps = 0; ps < 2; ++ps)
 #pragma unroll
                                         for (int kk = 0; kk < 4; ++kk)
-                                            ptx::umma_f16(dj, desc(aj + 2 * kk), desc(b_lo + ps * (C::kBTile >> 4) + 2 * kk), idesc, accumulate | (ps | kk));
+                                            ptx::umma_f16(dst(ps * 4 + kk), desc(aj + 2 * kk), desc(b_lo + ps * (C::kBTile >> 4) + 2 * kk), idesc, accf(ps * 4 + kk));
                                 } else if (PREC == PREC_BF16X3) {
                                     // chunk = [32 hi | 32 lo] bf16 (A) x [32 w_hi | 32 w_lo] (B); offsets in 16-byte units
                                     constexpr int AO[6] = {0, 2, 4, 6, 0, 2};      // hi, hi, lo, lo, hi, hi
                                     constexpr int BO[6] = {0, 2, 0, 2, 4, 6};      // w_hi x4,        w_lo x2
 #pragma unroll
                                     for (int i = 0; i < 6; ++i)
-                                        ptx::umma_f16(dj, desc(aj + AO[i]), desc(b_lo + BO[i]), idesc, accumulate | (i != 0));
+                                        ptx::umma_f16(dst(i), desc(aj + AO[i]), desc(b_lo + BO[i]), idesc, accf(i));
                                 } else {
-                                    ptx::umma_f16(dj, desc(aj), desc(b_lo), idesc, accumulate);
-                                    ptx::umma_f16(dj, desc(aj + 2), desc(b_lo + 2), idesc, 1u);
+                                    ptx::umma_f16(dst(0), desc(aj), desc(b_lo), idesc, accf(0));
+                                    ptx::umma_f16(dst(1), desc(aj + 2), desc(b_lo + 2), idesc, accf(1));
                                 }
                             }
                             if (!RESIDENT) ptx::umma_commit(&b_empty[bstage]);
                         }
                         __syncwarp();
-                        accumulate = 1;
+                        cnt += (PREC == PREC_TF32) ? 4u : (POOL ? 8u : (PREC == PREC_BF16X3 ? 6u : 2u));
                         if (!RESIDENT) { if (++bstage == C::kBStages) { bstage = 0; bphase ^= 1; } }
                     }
                     if (ptx::elect_one()) ptx::umma_commit(&a_empty[astage]);
@@ -302,21 +311,32 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                     float* outp = p.out + pix * g.out_cstride + g.out_coff + ch0;
                     const float* resp = p.res ? p.res + pix * g.res_cstride + g.res_coff + ch0 : nullptr;
                     const float* biasp = p.bias + ch0;
-                    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (MT * BN) + j * BN + half * kCols;
+                    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * C::kAccCols + j * (BN * C::kSplit) + half * kCols;
 #pragma unroll 1
                     for (int c0 = 0; c0 < kCols; c0 += 32) {
-                        uint32_t r0[16], r1[16];
-                        ptx::tmem_ld16(taddr + c0, r0);
-                        ptx::tmem_ld16(taddr + c0 + 16, r1);
-                        ptx::tmem_ld_wait();
+                        float v[32];
+                        {
+                            uint32_t r0[16], r1[16];
+                            ptx::tmem_ld16(taddr + c0, r0);
+                            ptx::tmem_ld16(taddr + c0 + 16, r1);
+                            ptx::tmem_ld_wait();
+#pragma unroll
+                            for (int jj = 0; jj < 16; ++jj) { v[jj] = __uint_as_float(r0[jj]); v[16 + jj] = __uint_as_float(r1[jj]); }
+                        }
+#pragma unroll
+                        for (int sp = 1; sp < C::kSplit; ++sp) {             // sum the partial accumulators
+                            uint32_t r0[16], r1[16];
+                            ptx::tmem_ld16(taddr + sp * BN + c0, r0);
+                            ptx::tmem_ld16(taddr + sp * BN + c0 + 16, r1);
+                            ptx::tmem_ld_wait();
+#pragma unroll
+                            for (int jj = 0; jj < 16; ++jj) { v[jj] += __uint_as_float(r0[jj]); v[16 + jj] += __uint_as_float(r1[jj]); }
+                        }
                         if (valid) {
-                            float v[32];
 #pragma unroll
                             for (int jj = 0; jj < 32; jj += 4) {
                                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(biasp + c0 + jj));
-                                const uint32_t* r = (jj < 16) ? &r0[jj] : &r1[jj - 16];
-                                v[jj] = __uint_as_float(r[0]) + b4.x; v[jj + 1] = __uint_as_float(r[1]) + b4.y;
-                                v[jj + 2] = __uint_as_float(r[2]) + b4.z; v[jj + 3] = __uint_as_float(r[3]) + b4.w;
+                                v[jj] += b4.x; v[jj + 1] += b4.y; v[jj + 2] += b4.z; v[jj + 3] += b4.w;
                             }
                             if (resp) {
                                 if (PREC == PREC_TF32) {
@@ -385,22 +405,33 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
 
                 ptx::mbar_wait(&tmem_full[acc], acc_phase);
                 ptx::tc_fence_after();
-                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + half * kCols;
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * C::kAccCols + half * kCols;
                 {
-                    uint32_t r0[16], r1[16];
-                    ptx::tmem_ld16(taddr, r0);
-                    ptx::tmem_ld16(taddr + 16, r1);
-                    ptx::tmem_ld_wait();
+                    float v[32];
+                    {
+                        uint32_t r0[16], r1[16];
+                        ptx::tmem_ld16(taddr, r0);
+                        ptx::tmem_ld16(taddr + 16, r1);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int jj = 0; jj < 16; ++jj) { v[jj] = __uint_as_float(r0[jj]); v[16 + jj] = __uint_as_float(r1[jj]); }
+                    }
+#pragma unroll
+                    for (int sp = 1; sp < C::kSplit; ++sp) {
+                        uint32_t r0[16], r1[16];
+                        ptx::tmem_ld16(taddr + sp * BN, r0);
+                        ptx::tmem_ld16(taddr + sp * BN + 16, r1);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int jj = 0; jj < 16; ++jj) { v[jj] += __uint_as_float(r0[jj]); v[16 + jj] += __uint_as_float(r1[jj]); }
+                    }
                     if (row < 121) {
                         float* srow = stage + row * kPoolPitch + half * kCols;
                         const float ninf = -3.0e38f;
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            *reinterpret_cast<float4*>(srow + j) = cvalid ? make_float4(__uint_as_float(r0[j]), __uint_as_float(r0[j + 1]), __uint_as_float(r0[j + 2]), __uint_as_float(r0[j + 3]))
-                                                                          : make_float4(ninf, ninf, ninf, ninf);
-                            *reinterpret_cast<float4*>(srow + 16 + j) = cvalid ? make_float4(__uint_as_float(r1[j]), __uint_as_float(r1[j + 1]), __uint_as_float(r1[j + 2]), __uint_as_float(r1[j + 3]))
-                                                                               : make_float4(ninf, ninf, ninf, ninf);
-                        }
+                        for (int jj = 0; jj < 32; jj += 4)
+                            *reinterpret_cast<float4*>(srow + jj) = cvalid ? make_float4(v[jj], v[jj + 1], v[jj + 2], v[jj + 3])
+                                                                           : make_float4(ninf, ninf, ninf, ninf);
                     }
                 }
                 ptx::tc_fence_before();
