@@ -313,7 +313,8 @@ def main():
             cms2, slots2 = conv_stack_profile(prec, min(args.steps, 10))
             r2 = roofline_of(prec, cms2, slots2)
             alt[prec] = {'value': nb * world * len(ev2) / (float(tms.item()) * 1e-3), 'unit': 'pairs/s', 'ms_per_step': float(tms.item()) / len(ev2),
-                         'roofline_frac': r2['frac'], 'tensor_pipe_frac': r2['tensor_pipe_frac'], 'conv_stack_ms': cms2}
+                         'roofline_frac': r2['frac'], 'tensor_pipe_frac': r2['tensor_pipe_frac'], 'conv_stack_ms': cms2,
+                         'conv_ms': r2['per_kernel_ms']['conv']}
         tracker.precision = args.precision
 
     # ---- (3) end to end through the public API with pinned HOST buffers -----------------------------

@@ -88,6 +88,7 @@ struct Umma2Plan {
     int tiles_x, tiles_y, m_tiles, n_tiles;
     int img_first;
     int base_off_mode;                   // 0: descriptor base_offset = 0; 1: (addr >> 7) & 7
+    int debug;                           // timing experiments only (results are garbage): bit0 skip B fills, bit1 skip A fills
 };
 
 cudaError_t launch_conv_umma2(const UmmaMaps& maps, const ConvGeom& g, const Umma2Plan& t, const ConvPtrs& p,

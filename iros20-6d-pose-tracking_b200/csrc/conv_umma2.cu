@@ -15,10 +15,8 @@
 //     yields a 5x5 block of pooled outputs; max -> +bias -> SELU (monotone, so they commute) run
 //     on 1/4.84 of the values and the 88x88x64 intermediate never reaches HBM.
 //   * 8 epilogue warps (two per TMEM lane quadrant).
-//   * BN = 64 tiles (stem, 64-channel layers) round-robin their MMAs over kSplit = 4 partial
-//     accumulators that the epilogue sums: a 128x64x16 MMA is 32 tensor cycles but back-to-back MMAs
-//     into ONE accumulator were measured at ~105 cycles each (accumulate dependency latency; ncu:
-//     tensor pipe 38 % active with the issuing warp never blocked on a barrier).
+//   * N = 64 tiles (stem, 64-channel layers) are capped by the hardware: one 128xNx32B tcgen05.mma costs
+//     ~90 cycles for any N <= 128 (128 for N = 256; scripts/umma_rate.cu), i.e. 35 % of peak at N = 64.
 //   * MT = 2 ("dual-M", BN = 256 layers): one CTA carries TWO M tiles (two accumulators, all 512
 //     TMEM columns) through the K loop, so every weight tile fetched from L2 feeds 8 MMAs instead
 //     of 4 -- the weight stream, which is >80% of the fill traffic of the deep layers, halves.
@@ -56,7 +54,10 @@ template <int BN, bool RESIDENT, bool POOL, int MT, int PREC = 0> struct Cfg2 {
     static constexpr int kWPerTap = (POOL && PREC != PREC_TF32) ? 2 : 1;  // weight tiles per (tap, chunk)
     static constexpr int kPoolBufs = POOL ? (PREC == PREC_TF32 ? 2 : 1) : 0;
     static constexpr int kBStages = RESIDENT ? 0 : (BN == 256 ? (MT == 2 ? 3 : 4) : 6);
-    static constexpr int kSplit = (BN == 64) ? 4 : 1;                   // partial accumulators per tile (independent MMA chains)
+    // Partial accumulators per tile (independent MMA chains).  Measured (profiles/r01_umma_rate_microbench.txt):
+    // a 128xNx(32 B) tcgen05.mma costs ~90 cycles for N <= 128 whether or not consecutive MMAs share an
+    // accumulator, so splitting buys nothing -- kept at 1 (the code path stays for experiments).
+    static constexpr int kSplit = 1;
     static constexpr int kAccCols = MT * BN * kSplit;                   // TMEM columns of one accumulator set
     static constexpr int kNAcc = (2 * kAccCols <= 512) ? 2 : 1;         // accumulator sets (double-buffered when they fit)
     static constexpr int kTmemCols = kNAcc * kAccCols;                  // 256 / 512
@@ -158,6 +159,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                     for (int u = 0; u < t.units_per_chunk; ++u) {
                         const Unit un = t.units[u];
                         ptx::mbar_wait(&a_empty[stage], phase ^ 1);
+                        if (t.debug & 2) { ptx::mbar_arrive(&a_full[stage]); if (++stage == C::kAStages) { stage = 0; phase ^= 1; } continue; }   // timing experiment: no A fill
                         ptx::mbar_arrive_expect_tx(&a_full[stage], static_cast<uint32_t>(un.rows) * kChunkBytes * MT);
 #pragma unroll
                         for (int j = 0; j < MT; ++j)
@@ -186,6 +188,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                             const Unit un = t.units[u];
                             for (int k = 0; k < un.ntaps; ++k) {
                                 ptx::mbar_wait(&b_empty[stage], phase ^ 1);
+                                if (t.debug & 1) { ptx::mbar_arrive(&b_full[stage]); if (++stage == C::kBStages) { stage = 0; phase ^= 1; } continue; }   // timing experiment: no B fill
                                 ptx::mbar_arrive_expect_tx(&b_full[stage], C::kBTile);
                                 ptx::tma_load_2d(sB + stage * C::kBTile, &maps.b, &b_full[stage], un.taps[k].w_tap * g.cin + ch * 32, wrow);
                                 if (++stage == C::kBStages) { stage = 0; phase ^= 1; }
