@@ -70,6 +70,7 @@ struct alignas(64) UmmaMaps {
 };
 
 // ---- tcgen05 path, second generation (conv_umma2.cu) ---------------------------------------
+enum { KIND_S1 = 0, KIND_S2 = 1, KIND_STEM = 2 };   // conv kinds of the v2 kernel (compile-time unit tables)
 struct UnitTap { int8_t row_shift; int8_t w_tap; };   // rows to advance the A descriptor; weight tap index
 struct Unit {
     int8_t map;            // A tensor map index
@@ -92,7 +93,7 @@ struct Umma2Plan {
 };
 
 cudaError_t launch_conv_umma2(const UmmaMaps& maps, const ConvGeom& g, const Umma2Plan& t, const ConvPtrs& p,
-                              int block_n, bool resident, bool pool, int m_per_cta, int prec /*0 tf32, 1 bf16x3, 2 bf16*/,
+                              int block_n, bool resident, int kind /*KIND_*/, int m_per_cta, int prec /*0 tf32, 1 bf16x3, 2 bf16*/,
                               int num_sms, cudaStream_t stream);
 
 cudaError_t launch_conv_umma(const UmmaMaps& maps, const ConvGeom& g, const UmmaTiling& t,

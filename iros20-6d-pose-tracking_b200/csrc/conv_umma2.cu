@@ -46,7 +46,31 @@ constexpr int kPoolStageBytes = 121 * kPoolPitch * 4;
 
 enum { PREC_TF32 = 0, PREC_BF16X3 = 1, PREC_BF16 = 2 };
 
-template <int BN, bool RESIDENT, bool POOL, int MT, int PREC = 0> struct Cfg2 {
+// Compile-time unit/tap structure per conv kind, so the MMA issue loop is straight-line code with
+// immediate row shifts / weight-tile indices (a runtime plan table cost ~200 cycles of dependent
+// constant-bank loads per MMA group).  Must agree with the host plan (checked in launch2).
+template <int KIND> struct KTab;
+template <> struct KTab<KIND_S1> {            // 3x3 stride 1: unit = filter column s, taps = filter rows r
+    static constexpr int NU = 3;
+    __host__ __device__ static constexpr int ntaps(int) { return 3; }
+    __host__ __device__ static constexpr int shift(int, int k) { return k * 11; }
+    __host__ __device__ static constexpr int wtap(int u, int k) { return k * 3 + u; }
+};
+template <> struct KTab<KIND_S2> {            // 3x3 stride 2: per column s an even-row unit (r=1) and an odd-row unit (r=0,2)
+    static constexpr int NU = 6;
+    __host__ __device__ static constexpr int ntaps(int u) { return (u & 1) ? 2 : 1; }
+    __host__ __device__ static constexpr int shift(int, int k) { return k * 11; }
+    __host__ __device__ static constexpr int wtap(int u, int k) { return (u & 1) ? (k == 0 ? (u >> 1) : 6 + (u >> 1)) : 3 + (u >> 1); }
+};
+template <> struct KTab<KIND_STEM> {          // 7x7 stride 2 stem: even input rows (r=0,2,4,6), odd input rows (r=1,3,5)
+    static constexpr int NU = 2;
+    __host__ __device__ static constexpr int ntaps(int u) { return u == 0 ? 4 : 3; }
+    __host__ __device__ static constexpr int shift(int, int k) { return k * 11; }
+    __host__ __device__ static constexpr int wtap(int u, int k) { return 2 * k + u; }
+};
+
+template <int BN, bool RESIDENT, int KIND, int MT, int PREC = 0> struct Cfg2 {
+    static constexpr bool POOL = (KIND == KIND_STEM);
     static constexpr int kBTile = BN * kChunkBytes;
     static constexpr int kAUnit = POOL ? 21 * 1024 : 19 * 1024;     // 3x3: (22 + 128) rows * 128 B = 19,200
     static constexpr int kAStage = MT * kAUnit;
@@ -103,11 +127,13 @@ __device__ __forceinline__ float2 unpack2(uint32_t w) {
     return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
 }
 
-template <int BN, bool RESIDENT, bool POOL, int MT, int PREC>
+template <int BN, bool RESIDENT, int KIND, int MT, int PREC>
 __global__ void __launch_bounds__(kThreads2, 1)
 conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const Umma2Plan t, const ConvPtrs p)
 {
-    using C = Cfg2<BN, RESIDENT, POOL, MT, PREC>;
+    using C = Cfg2<BN, RESIDENT, KIND, MT, PREC>;
+    using KT = KTab<KIND>;
+    constexpr bool POOL = C::POOL;
     static_assert(!(POOL && MT != 1), "pool epilogue is single-tile");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -216,26 +242,25 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
             const uint32_t d_tmem = tmem_base + acc * C::kAccCols;
             uint32_t cnt = 0;                       // MMAs issued into this tile so far (per M tile)
             for (int ch = 0; ch < t.chunks; ++ch) {
-                for (int u = 0; u < t.units_per_chunk; ++u) {
-                    const int ntaps = t.units[u].ntaps;
+#pragma unroll
+                for (int u = 0; u < KT::NU; ++u) {
                     ptx::mbar_wait(&a_full[astage], aphase);
                     ptx::tc_fence_after();
-                    const uint32_t a_base = ptx::smem_u32(sA + astage * C::kAStage);
-                    for (int k = 0; k < ntaps; ++k) {
-                        const int w_tap = t.units[u].taps[k].w_tap;
-                        const uint32_t row_shift = static_cast<uint32_t>(t.units[u].taps[k].row_shift);
-                        uint32_t b_addr;
+                    // low descriptor words: (addr >> 4) | LBO(=1) << 16; +2 per 32-byte K step, +8 per pixel row.
+                    // base_offset stays 0: the 128B swizzle is a function of absolute smem address bits
+                    // (profiles/r01_umma_desc_rowshift_probe.txt)
+                    const uint32_t a_unit_lo = ((ptx::smem_u32(sA + astage * C::kAStage) & 0x3FFFFu) >> 4) | (1u << 16);
+#pragma unroll
+                    for (int k = 0; k < KT::ntaps(u); ++k) {
+                        uint32_t b_lo;
                         if (RESIDENT) {
-                            b_addr = ptx::smem_u32(sB + (w_tap * t.chunks + ch) * C::kWPerTap * C::kBTile);
+                            b_lo = ((ptx::smem_u32(sB + (KT::wtap(u, k) * t.chunks + ch) * C::kWPerTap * C::kBTile) & 0x3FFFFu) >> 4) | (1u << 16);
                         } else {
                             ptx::mbar_wait(&b_full[bstage], bphase);
                             ptx::tc_fence_after();
-                            b_addr = ptx::smem_u32(sB + bstage * C::kBTile);
+                            b_lo = ((ptx::smem_u32(sB + bstage * C::kBTile) & 0x3FFFFu) >> 4) | (1u << 16);
                         }
-                        // low words: (addr >> 4) | LBO(=1) << 16; +2 per 32-byte K step.  base_offset stays 0:
-                        // the 128B swizzle is a function of absolute smem address bits (profiles/r01_umma_desc_rowshift_probe.txt)
-                        const uint32_t a_lo = (((a_base + row_shift * kChunkBytes) & 0x3FFFFu) >> 4) | (1u << 16);
-                        const uint32_t b_lo = ((b_addr & 0x3FFFFu) >> 4) | (1u << 16);
+                        const uint32_t a_lo = a_unit_lo + KT::shift(u, k) * (kChunkBytes >> 4);
                         if (ptx::elect_one()) {
 #pragma unroll
                             for (int j = 0; j < MT; ++j) {
@@ -484,46 +509,59 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
     if (warp == 2) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, C::kTmemCols); }
 }
 
-template <int BN, bool RESIDENT, bool POOL, int MT, int PREC>
+template <int KIND>
+bool plan_matches(const Umma2Plan& t) {
+    using KT = KTab<KIND>;
+    if (t.units_per_chunk != KT::NU) return false;
+    for (int u = 0; u < KT::NU; ++u) {
+        if (t.units[u].ntaps != KT::ntaps(u)) return false;
+        for (int k = 0; k < KT::ntaps(u); ++k)
+            if (t.units[u].taps[k].row_shift != KT::shift(u, k) || t.units[u].taps[k].w_tap != KT::wtap(u, k)) return false;
+    }
+    return true;
+}
+
+template <int BN, bool RESIDENT, int KIND, int MT, int PREC>
 cudaError_t launch2(const UmmaMaps& maps, const ConvGeom& g, const Umma2Plan& t, const ConvPtrs& p, int num_sms, cudaStream_t stream) {
-    using C = Cfg2<BN, RESIDENT, POOL, MT, PREC>;
+    using C = Cfg2<BN, RESIDENT, KIND, MT, PREC>;
+    if (!plan_matches<KIND>(t)) return cudaErrorInvalidValue;
     const int w_tiles = g.num_taps * t.chunks * C::kWPerTap;
     const size_t smem = static_cast<size_t>(C::kAStages) * C::kAStage + static_cast<size_t>(RESIDENT ? w_tiles : C::kBStages) * C::kBTile +
                         C::kPoolBufs * ((kPoolStageBytes + 1023) & ~1023) + 1024 + 512;
     if (smem > 232448) return cudaErrorInvalidConfiguration;
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
-        cudaError_t e = cudaFuncSetAttribute(conv_umma2_kernel<BN, RESIDENT, POOL, MT, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        cudaError_t e = cudaFuncSetAttribute(conv_umma2_kernel<BN, RESIDENT, KIND, MT, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;
         attr_smem = smem;
     }
     const int total = ((t.m_tiles + MT - 1) / MT) * t.n_tiles * g.groups;
     const int grid = total < num_sms ? total : num_sms;
-    conv_umma2_kernel<BN, RESIDENT, POOL, MT, PREC><<<grid, kThreads2, smem, stream>>>(maps, g, t, p);
+    conv_umma2_kernel<BN, RESIDENT, KIND, MT, PREC><<<grid, kThreads2, smem, stream>>>(maps, g, t, p);
     return cudaGetLastError();
 }
 
 template <int PREC>
 cudaError_t dispatch2(const UmmaMaps& maps, const ConvGeom& g, const Umma2Plan& t, const ConvPtrs& p,
-                      int block_n, bool resident, bool pool, int m_per_cta, int num_sms, cudaStream_t stream) {
-    if (pool) return (block_n == 64 && resident) ? launch2<64, true, true, 1, PREC>(maps, g, t, p, num_sms, stream) : cudaErrorInvalidValue;
-    if (resident) return block_n == 64 ? launch2<64, true, false, 1, PREC>(maps, g, t, p, num_sms, stream) : cudaErrorInvalidValue;
-    switch (block_n) {
-        case 128: return launch2<128, false, false, 1, PREC>(maps, g, t, p, num_sms, stream);
-        case 256: return m_per_cta == 2 ? launch2<256, false, false, 2, PREC>(maps, g, t, p, num_sms, stream)
-                                        : launch2<256, false, false, 1, PREC>(maps, g, t, p, num_sms, stream);
-        default:  return cudaErrorInvalidValue;
-    }
+                      int block_n, bool resident, int kind, int m_per_cta, int num_sms, cudaStream_t stream) {
+    if (kind == KIND_STEM) return (block_n == 64 && resident) ? launch2<64, true, KIND_STEM, 1, PREC>(maps, g, t, p, num_sms, stream) : cudaErrorInvalidValue;
+    if (resident) return (block_n == 64 && kind == KIND_S1) ? launch2<64, true, KIND_S1, 1, PREC>(maps, g, t, p, num_sms, stream) : cudaErrorInvalidValue;
+    if (block_n != 256) return cudaErrorInvalidValue;
+    if (kind == KIND_S1)
+        return m_per_cta == 2 ? launch2<256, false, KIND_S1, 2, PREC>(maps, g, t, p, num_sms, stream)
+                              : launch2<256, false, KIND_S1, 1, PREC>(maps, g, t, p, num_sms, stream);
+    return m_per_cta == 2 ? launch2<256, false, KIND_S2, 2, PREC>(maps, g, t, p, num_sms, stream)
+                          : launch2<256, false, KIND_S2, 1, PREC>(maps, g, t, p, num_sms, stream);
 }
 
 }  // namespace
 
 cudaError_t launch_conv_umma2(const UmmaMaps& maps, const ConvGeom& g, const Umma2Plan& t, const ConvPtrs& p,
-                              int block_n, bool resident, bool pool, int m_per_cta, int prec, int num_sms, cudaStream_t stream) {
+                              int block_n, bool resident, int kind, int m_per_cta, int prec, int num_sms, cudaStream_t stream) {
     switch (prec) {
-        case PREC_TF32:   return dispatch2<PREC_TF32>(maps, g, t, p, block_n, resident, pool, m_per_cta, num_sms, stream);
-        case PREC_BF16X3: return dispatch2<PREC_BF16X3>(maps, g, t, p, block_n, resident, pool, m_per_cta, num_sms, stream);
-        case PREC_BF16:   return dispatch2<PREC_BF16>(maps, g, t, p, block_n, resident, pool, m_per_cta, num_sms, stream);
+        case PREC_TF32:   return dispatch2<PREC_TF32>(maps, g, t, p, block_n, resident, kind, m_per_cta, num_sms, stream);
+        case PREC_BF16X3: return dispatch2<PREC_BF16X3>(maps, g, t, p, block_n, resident, kind, m_per_cta, num_sms, stream);
+        case PREC_BF16:   return dispatch2<PREC_BF16>(maps, g, t, p, block_n, resident, kind, m_per_cta, num_sms, stream);
         default:          return cudaErrorInvalidValue;
     }
 }

@@ -445,7 +445,8 @@ int run_network(se3tn_ctx* c, int weight_id, int first, int n, int precision,
                 p.out = c->buf[li == 0 ? B_P1A : B_P1B];
                 g.out_cstride = 64; g.out_coff = 0;
             }
-            { ProfScope ps(c, li, s); CU_TRY(c, launch_conv_umma2(maps, g, t, p, BN, resident, pool, (BN == 256 && c->dual_m) ? 2 : 1, kprec, c->num_sms, s)); }
+            { ProfScope ps(c, li, s); CU_TRY(c, launch_conv_umma2(maps, g, t, p, BN, resident, L.kind == K_STEM ? KIND_STEM : (L.kind == K_S2 ? KIND_S2 : KIND_S1),
+                                                                     (BN == 256 && c->dual_m) ? 2 : 1, kprec, c->num_sms, s)); }
             ++c->launches;
             continue;
         }
