@@ -15,6 +15,10 @@
 //     yields a 5x5 block of pooled outputs; max -> +bias -> SELU (monotone, so they commute) run
 //     on 1/4.84 of the values and the 88x88x64 intermediate never reaches HBM.
 //   * 8 epilogue warps (two per TMEM lane quadrant).
+//   * Ring-weight kernels (BN = 256) transpose each 32-row x 32-column accumulator block through a
+//     per-warp shared-memory tile so that every global load/store instruction of the epilogue covers 4
+//     whole 128-byte lines (8 lanes per pixel) instead of 32 different lines (one 16-byte piece per
+//     lane): the row-per-lane epilogue was LSU-bound at ~25-30 us per dual-M work unit.
 //   * N = 64 tiles (stem, 64-channel layers) are capped by the hardware: one 128xNx32B tcgen05.mma costs
 //     ~90 cycles for any N <= 128 (128 for N = 256; scripts/umma_rate.cu), i.e. 35 % of peak at N = 64.
 //   * MT = 2 ("dual-M", BN = 256 layers): one CTA carries TWO M tiles (two accumulators, all 512
@@ -74,7 +78,11 @@ template <int BN, bool RESIDENT, int KIND, int MT, int PREC = 0> struct Cfg2 {
     static constexpr int kBTile = BN * kChunkBytes;
     static constexpr int kAUnit = POOL ? 21 * 1024 : 19 * 1024;     // 3x3: (22 + 128) rows * 128 B = 19,200
     static constexpr int kAStage = MT * kAUnit;
-    static constexpr int kAStages = RESIDENT ? ((POOL && PREC != PREC_TF32) ? 3 : 4) : (BN == 256 ? 3 : 4);
+    static constexpr int kAStages = RESIDENT ? ((POOL && PREC != PREC_TF32) ? 3 : 4) : (MT == 2 ? 2 : 3);
+    static constexpr bool kEpiT = !RESIDENT;                            // transposed (coalesced) epilogue through per-warp smem tiles
+    static constexpr int kEpiPitch = 36;                                // words per staged row (32 + 4: conflict-free 16 B accesses)
+    static constexpr int kEpiWarpBytes = 32 * kEpiPitch * 4 + 128;      // 32 rows + 32-entry pixel-index table
+    static constexpr int kEpiBytes = kEpiT ? 8 * kEpiWarpBytes : 0;
     static constexpr int kWPerTap = (POOL && PREC != PREC_TF32) ? 2 : 1;  // weight tiles per (tap, chunk)
     static constexpr int kPoolBufs = POOL ? (PREC == PREC_TF32 ? 2 : 1) : 0;
     static constexpr int kBStages = RESIDENT ? 0 : (BN == 256 ? (MT == 2 ? 3 : 4) : 6);
@@ -141,7 +149,8 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
     uint8_t* sA = smem;                                                 // [kAStages][MT][unit]
     uint8_t* sB = sA + C::kAStages * C::kAStage;                       // resident: [w_tiles][BN*128]; ring: [kBStages][BN*128]
     uint8_t* sP = sB + (RESIDENT ? w_tiles : C::kBStages) * C::kBTile;  // pool staging (POOL only): 2 x 121 x 68 floats
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + C::kPoolBufs * ((kPoolStageBytes + 1023) & ~1023));
+    uint8_t* sT = sP + C::kPoolBufs * ((kPoolStageBytes + 1023) & ~1023);   // epilogue transpose tiles (kEpiT only)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sT + ((C::kEpiBytes + 1023) & ~1023));
     uint64_t* a_full = bars;                       // [kAStages]
     uint64_t* a_empty = a_full + C::kAStages;      // [kAStages]
     uint64_t* b_full = a_empty + C::kAStages;      // [max(kBStages,1)]  (resident: b_full[0] = "weights landed")
@@ -327,6 +336,98 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                 const WorkUnit wu = decode_work(tile, m_units, t);
                 ptx::mbar_wait(&tmem_full[acc], acc_phase);
                 ptx::tc_fence_after();
+                if constexpr (C::kEpiT) {
+                    // ---------------- transposed epilogue: lane = (pixel-in-group-of-4 sub, 16-byte column group grp) ----------------
+                    float (*stg)[C::kEpiPitch] = reinterpret_cast<float (*)[C::kEpiPitch]>(sT + ew * C::kEpiWarpBytes);
+                    int* rowtab = reinterpret_cast<int*>(sT + ew * C::kEpiWarpBytes + 32 * C::kEpiPitch * 4);
+                    const int grp = lane & 7, sub = lane >> 3;
+#pragma unroll 1
+                    for (int j = 0; j < MT; ++j) {
+                        const int m = wu.mp * MT + j;
+                        if (m >= t.m_tiles) break;                           // odd tail (warp-uniform)
+                        const TileCoord2 tc = decode2(m, t);
+                        {
+                            const int n = tc.n0 + pn, y = tc.ty * t.bh + py, x = tc.tx * t.bw + px;
+                            const bool valid = (pn < t.bn) && (n < g.n_img) && (y < g.Ho) && (x < g.Wo);
+                            __syncwarp();
+                            rowtab[lane] = valid ? (n * g.Ho + y) * g.Wo + x : -1;   // pixel index of TMEM row q*32 + lane
+                        }
+                        const int ch0 = wu.grp * g.cout + wu.n_tile * BN + half * kCols;
+                        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * C::kAccCols + j * (BN * C::kSplit) + half * kCols;
+#pragma unroll 1
+                        for (int c0 = 0; c0 < kCols; c0 += 32) {
+                            {
+                                uint32_t r0[16], r1[16];
+                                ptx::tmem_ld16(taddr + c0, r0);
+                                ptx::tmem_ld16(taddr + c0 + 16, r1);
+                                ptx::tmem_ld_wait();
+                                __syncwarp();                                // previous block's readers are done with stg
+#pragma unroll
+                                for (int jj = 0; jj < 16; jj += 4) {
+                                    *reinterpret_cast<uint4*>(&stg[lane][jj]) = make_uint4(r0[jj], r0[jj + 1], r0[jj + 2], r0[jj + 3]);
+                                    *reinterpret_cast<uint4*>(&stg[lane][16 + jj]) = make_uint4(r1[jj], r1[jj + 1], r1[jj + 2], r1[jj + 3]);
+                                }
+                            }
+                            __syncwarp();
+                            const int chan = ch0 + c0;                        // first channel (word index) of this 32-channel chunk
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + chan + grp * 4));
+                            int pix[8];
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) pix[k] = rowtab[4 * k + sub];
+                            float4 a4[8];
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                a4[k] = *reinterpret_cast<const float4*>(&stg[4 * k + sub][grp * 4]);
+                                a4[k].x += b4.x; a4[k].y += b4.y; a4[k].z += b4.z; a4[k].w += b4.w;
+                            }
+                            if (p.res) {
+                                if (PREC == PREC_TF32) {
+                                    float4 r4[8];
+#pragma unroll
+                                    for (int k = 0; k < 8; ++k)
+                                        r4[k] = pix[k] >= 0 ? __ldg(reinterpret_cast<const float4*>(p.res + static_cast<size_t>(pix[k]) * g.res_cstride + g.res_coff + chan + grp * 4))
+                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                                    for (int k = 0; k < 8; ++k) { a4[k].x += r4[k].x; a4[k].y += r4[k].y; a4[k].z += r4[k].z; a4[k].w += r4[k].w; }
+                                } else {
+                                    uint2 rh[8], rl[8];                      // 4 channels: bf16 hi at byte grp*8 of the chunk, lo 64 bytes further
+#pragma unroll
+                                    for (int k = 0; k < 8; ++k) {
+                                        rh[k] = make_uint2(0u, 0u); rl[k] = make_uint2(0u, 0u);
+                                        if (pix[k] >= 0) {
+                                            const uint8_t* cb = reinterpret_cast<const uint8_t*>(p.res + static_cast<size_t>(pix[k]) * g.res_cstride + g.res_coff + chan) + grp * 8;
+                                            rh[k] = __ldg(reinterpret_cast<const uint2*>(cb));
+                                            rl[k] = __ldg(reinterpret_cast<const uint2*>(cb + 64));
+                                        }
+                                    }
+#pragma unroll
+                                    for (int k = 0; k < 8; ++k) {
+                                        const float2 h0 = unpack2(rh[k].x), h1 = unpack2(rh[k].y), l0 = unpack2(rl[k].x), l1 = unpack2(rl[k].y);
+                                        a4[k].x += h0.x + l0.x; a4[k].y += h0.y + l0.y; a4[k].z += h1.x + l1.x; a4[k].w += h1.y + l1.y;
+                                    }
+                                }
+                            }
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                float4 o = a4[k];
+                                if (g.act == ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                                else if (g.act == ACT_SELU) { o.x = selu_fast(o.x); o.y = selu_fast(o.y); o.z = selu_fast(o.z); o.w = selu_fast(o.w); }
+                                if (pix[k] < 0) continue;
+                                float* po = p.out + static_cast<size_t>(pix[k]) * g.out_cstride + g.out_coff + chan;
+                                if (PREC == PREC_TF32) {
+                                    if (g.round_tf32) o = make_float4(ptx::to_tf32(o.x), ptx::to_tf32(o.y), ptx::to_tf32(o.z), ptx::to_tf32(o.w));
+                                    *reinterpret_cast<float4*>(po + grp * 4) = o;
+                                } else {
+                                    uint32_t h0, l0, h1, l1;
+                                    split2(o.x, o.y, h0, l0); split2(o.z, o.w, h1, l1);
+                                    uint8_t* cb = reinterpret_cast<uint8_t*>(po) + grp * 8;
+                                    *reinterpret_cast<uint2*>(cb) = make_uint2(h0, h1);
+                                    *reinterpret_cast<uint2*>(cb + 64) = make_uint2(l0, l1);
+                                }
+                            }
+                        }
+                    }
+                } else {
 #pragma unroll 1
                 for (int j = 0; j < MT; ++j) {
                     const int m = wu.mp * MT + j;
@@ -413,6 +514,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                             }
                         }
                     }
+                }
                 }
                 ptx::tc_fence_before();
                 __syncwarp();
@@ -527,7 +629,7 @@ cudaError_t launch2(const UmmaMaps& maps, const ConvGeom& g, const Umma2Plan& t,
     if (!plan_matches<KIND>(t)) return cudaErrorInvalidValue;
     const int w_tiles = g.num_taps * t.chunks * C::kWPerTap;
     const size_t smem = static_cast<size_t>(C::kAStages) * C::kAStage + static_cast<size_t>(RESIDENT ? w_tiles : C::kBStages) * C::kBTile +
-                        C::kPoolBufs * ((kPoolStageBytes + 1023) & ~1023) + 1024 + 512;
+                        C::kPoolBufs * ((kPoolStageBytes + 1023) & ~1023) + ((C::kEpiBytes + 1023) & ~1023) + 1024 + 512;
     if (smem > 232448) return cudaErrorInvalidConfiguration;
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
