@@ -19,6 +19,10 @@
 //     per-warp shared-memory tile so that every global load/store instruction of the epilogue covers 4
 //     whole 128-byte lines (8 lanes per pixel) instead of 32 different lines (one 16-byte piece per
 //     lane): the row-per-lane epilogue was LSU-bound at ~25-30 us per dual-M work unit.
+//   * Programmatic dependent launch: every CTA signals launch_dependents at entry, so the next conv's
+//     CTAs start on SMs as they drain and run their prologue (barrier init, TMEM alloc, weight TMA --
+//     weights are never written during a forward) under the tail of this one; only the activation
+//     producer and the epilogue warps execute griddepcontrol.wait before touching activations.
 //   * N = 64 tiles (stem, 64-channel layers) are capped by the hardware: one 128xNx32B tcgen05.mma costs
 //     ~90 cycles for any N <= 128 (128 for N = 256; scripts/umma_rate.cu), i.e. 35 % of peak at N = 64.
 //   * MT = 2 ("dual-M", BN = 256 layers): one CTA carries TWO M tiles (two accumulators, all 512
@@ -159,6 +163,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
     uint64_t* tmem_empty = tmem_full + 2;          // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
+    ptx::grid_dep_launch();
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int m_units = (t.m_tiles + MT - 1) / MT;
@@ -180,6 +185,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
     if (warp == 0) {
         // ============================== A producer ================================
         if (lane == 0) {
+            ptx::grid_dep_wait();                   // activations come from the previous kernel
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const WorkUnit wu = decode_work(tile, m_units, t);
@@ -318,6 +324,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
         }
     } else if (warp >= 4) {
         // ============================== epilogue (8 warps) ==========================
+        ptx::grid_dep_wait();                       // residual reads / output writes must follow the previous kernel
         const int ew = warp - 4;
         const int q = ew & 3;                       // TMEM lane quadrant (== warp % 4)
         const int half = ew >> 2;                   // which half of the BN columns
@@ -639,8 +646,13 @@ cudaError_t launch2(const UmmaMaps& maps, const ConvGeom& g, const Umma2Plan& t,
     }
     const int total = ((t.m_tiles + MT - 1) / MT) * t.n_tiles * g.groups;
     const int grid = total < num_sms ? total : num_sms;
-    conv_umma2_kernel<BN, RESIDENT, KIND, MT, PREC><<<grid, kThreads2, smem, stream>>>(maps, g, t, p);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads2); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = t.pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, conv_umma2_kernel<BN, RESIDENT, KIND, MT, PREC>, maps, g, t, p);
 }
 
 template <int PREC>

@@ -20,6 +20,13 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// ------------------------------------------- programmatic dependent launch
+// launch_dependents: the next kernel in the stream (if launched with the programmatic-serialization
+// attribute) may start its CTAs as soon as every CTA of this grid has executed this or exited.
+// wait: blocks until the preceding grid has completed and its memory is visible.
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_wait()   { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

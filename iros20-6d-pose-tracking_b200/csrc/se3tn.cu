@@ -109,6 +109,7 @@ struct se3tn_ctx {
     CUtensorMap amap2[14][4];        // v2 kernel: boxes extended vertically (one per filter column / parity view)
     int conv_version = 2;            // SE3TN_CONV=1 selects the first-generation kernel
     int dual_m = 1;                  // SE3TN_DUAL_M=0 disables two-M-tiles-per-CTA on the BN=256 layers
+    int pdl = 1;                     // SE3TN_PDL=0 disables programmatic dependent launch between conv kernels
     int debug_flags = 0;             // SE3TN_DEBUG_SKIP: timing experiments (bit0 no B fills, bit1 no A fills); results invalid
     int base_off_mode = 0;           // SE3TN_BASE_OFF: UMMA descriptor base_offset convention for row-shifted starts
     EncodeTiledFn encode = nullptr;
@@ -301,6 +302,7 @@ void fill_plan2(const se3tn_ctx* c, const LayerSpec& L, int first, int n, int bl
     t.img_first = first;
     t.base_off_mode = c->base_off_mode;
     t.debug = c->debug_flags;
+    t.pdl = c->pdl;
     t.n_tiles = L.cout / block_n;
     const int Ho = layer_Ho(L);
     if (L.kind == K_STEM) {
@@ -515,6 +517,7 @@ int se3tn_create(int device, int max_batch, void* workspace, se3tn_ctx** out) {
     if (const char* ov = getenv("SE3TN_BASE_OFF")) c->base_off_mode = atoi(ov);
     if (const char* ov = getenv("SE3TN_DUAL_M")) c->dual_m = atoi(ov) != 0;
     if (const char* ov = getenv("SE3TN_DEBUG_SKIP")) c->debug_flags = atoi(ov);
+    if (const char* ov = getenv("SE3TN_PDL")) c->pdl = atoi(ov) != 0;
 
     void* fn = nullptr; cudaDriverEntryPointQueryResult qres;
     e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);

@@ -320,6 +320,26 @@ def test_track_batch_mixed_weight_sets(synth, eng):
     assert worst['bf16x3'] < 0.5 and worst['tf32'] < 8.0
 
 
+def test_empty_and_oversized_batches(synth, eng):
+    dev = eng.device
+    A0 = torch.empty(0, 4, 176, 176, device=dev); 
+    t, r, f = eng.forward(A0, A0.clone(), want_feature=True)
+    assert t.shape == (0, 3) and r.shape == (0, 3) and f.shape == (0, 256, 22, 22)
+    # more pairs than max_batch: Engine.forward walks the batch in max_batch slices
+    sd = synth.make_state_dict(0)
+    A, B = synth.tensor_pairs(66, seed=21)
+    t, r, _ = eng.forward(A.to(dev), B.to(dev))
+    ref = O.forward(sd, A[60:], B[60:])
+    assert_gate(six(t[60:], r[60:]), torch.cat((ref['trans'], ref['rot']), 1))
+    t2, r2, _ = eng.forward(A[64:].to(dev).contiguous(), B[64:].to(dev).contiguous())
+    assert torch.equal(t2, t[64:]) and torch.equal(r2, r[64:])
+    with pytest.raises(ValueError):                     # track_batch is one launch sequence: n <= max_batch
+        rgb, depth, poses, rgbA, depthA = _frame_case(synth, 65, 1)
+        eng.track_batch(torch.from_numpy(rgb).to(dev), torch.from_numpy(depth).to(dev), synth.CAMERA_K, torch.from_numpy(poses).to(dev),
+                        torch.full((65,), 200.0, dtype=torch.float64, device=dev), torch.from_numpy(rgbA).to(dev),
+                        torch.from_numpy(depthA).to(dev), 0.03, 0.0873)
+
+
 def test_errors_are_reported_not_fatal(pkg, synth, eng):
     L = importlib.import_module('iros20-6d-pose-tracking_b200._lib')
     A, B = synth.tensor_pairs(1, seed=0)
