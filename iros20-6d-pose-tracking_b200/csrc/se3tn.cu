@@ -108,7 +108,8 @@ struct se3tn_ctx {
     CUtensorMap amap[14][7];
     CUtensorMap amap2[14][4];        // v2 kernel: boxes extended vertically (one per filter column / parity view)
     int conv_version = 2;            // SE3TN_CONV=1 selects the first-generation kernel
-    int dual_m = 1;                  // SE3TN_DUAL_M=0 disables two-M-tiles-per-CTA on the BN=256 layers
+    int dual_m = 0;                  // SE3TN_DUAL_M=1: two M tiles per CTA on the BN=256 layers (halves weight fill traffic; measured
+                                     // slightly slower than MT=1 once fills stopped being the limiter: the epilogue cannot overlap)
     int pdl = 1;                     // SE3TN_PDL=0 disables programmatic dependent launch between conv kernels
     int debug_flags = 0;             // SE3TN_DEBUG_SKIP: timing experiments (bit0 no B fills, bit1 no A fills); results invalid
     int base_off_mode = 0;           // SE3TN_BASE_OFF: UMMA descriptor base_offset convention for row-shifted starts
