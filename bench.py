@@ -200,6 +200,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
+        if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':     # keep stdout to the one JSON line
+            os.environ['NCCL_DEBUG'] = 'WARN'
         dist.init_process_group('nccl', device_id=dev)
     nb = args.batch
 
@@ -294,6 +296,11 @@ def main():
 
     cms, slots = conv_stack_profile(args.precision, min(args.steps, 20))
     roofline = roofline_of(args.precision, cms, slots)
+    tj = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    if os.path.exists(tj):            # dram__bytes_read+write per launch from the committed `ncu --set full` capture
+        tr = json.load(open(tj))
+        roofline['traffic'] = tr['dram_bytes_per_launch']
+        roofline['traffic_note'] = '%s; %s' % (tr['kernel'], tr['source'])
 
     # ---- (2b) the other tensor-core modes on the same workload (secondary numbers) -------------------
     alt = {}

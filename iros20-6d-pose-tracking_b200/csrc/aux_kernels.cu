@@ -70,12 +70,14 @@ __device__ __forceinline__ float depth_offset(unsigned d, double z1000, bool gl)
 __global__ void __launch_bounds__(256)
 preprocess_kernel(PreprocessArgs a)
 {
+    ptx::grid_dep_launch();
     const int n = blockIdx.y;
-    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    const int quad = blockIdx.x * blockDim.x + threadIdx.x;     // 4 consecutive pixels of one row (176 = 44 * 4)
     const double* pose = a.poses + n * 16;
     // the crop window and cv2's inverse scales are per track: one thread computes them for the block
     __shared__ int s_win[4];
     __shared__ double s_inv[2];
+    ptx::grid_dep_wait();                                       // poses come from the previous step's pose update
     if (threadIdx.x == 0 && !a.b_precropped) {
         int top, left, ch, cw;
         bbox_window(pose, a.fx, a.fy, a.cx, a.cy, a.object_width[n], 1000.0, 1000.0, 1000.0, top, left, ch, cw);
@@ -85,77 +87,120 @@ preprocess_kernel(PreprocessArgs a)
         s_inv[1] = (ch > 0) ? 1.0 / (static_cast<double>(kImg) / ch) : 0.0;
     }
     __syncthreads();
-    if (pix >= kImg * kImg) return;
-    const int y = pix / kImg, x = pix - y * kImg;
+    if (quad >= kImg * kImg / 4) return;
+    const int pix0 = quad * 4;
+    const int y = pix0 / kImg, x0 = pix0 - y * kImg;
     const double z = pose[11];
     const bool gl = z < 0;
     const double z1000 = __dmul_rn(z, 1000.0);
+    const size_t ao = static_cast<size_t>(n) * kImg * kImg + pix0;
 
-    // ---- B: observed frame crop --------------------------------------------------------------
-    unsigned r = 0, gch = 0, b = 0, d = 0;
+    // ---- B: observed frame crop (4 pixels) -------------------------------------------------------
+    unsigned rB[4] = {0, 0, 0, 0}, gB[4] = {0, 0, 0, 0}, bB[4] = {0, 0, 0, 0}, dB[4] = {0, 0, 0, 0};
     if (a.b_precropped) {
         // frame_rgb / frame_depth already hold n 176x176 crops (TrackDataset.processData's inputs)
-        const size_t bo = static_cast<size_t>(n) * kImg * kImg + pix;
-        const uint8_t* pr = a.frame_rgb + bo * 3;
-        r = pr[0]; gch = pr[1]; b = pr[2];
-        d = a.frame_depth[bo];
+        const uint32_t* pr = reinterpret_cast<const uint32_t*>(a.frame_rgb + ao * 3);      // 12 bytes, 4-byte aligned
+        const uint32_t w0 = pr[0], w1 = pr[1], w2 = pr[2];
+        rB[0] = w0 & 255; gB[0] = (w0 >> 8) & 255; bB[0] = (w0 >> 16) & 255;
+        rB[1] = w0 >> 24; gB[1] = w1 & 255; bB[1] = (w1 >> 8) & 255;
+        rB[2] = (w1 >> 16) & 255; gB[2] = w1 >> 24; bB[2] = w2 & 255;
+        rB[3] = (w2 >> 8) & 255; gB[3] = (w2 >> 16) & 255; bB[3] = w2 >> 24;
+        const uint2 dd = *reinterpret_cast<const uint2*>(a.frame_depth + ao);
+        dB[0] = dd.x & 0xffff; dB[1] = dd.x >> 16; dB[2] = dd.y & 0xffff; dB[3] = dd.y >> 16;
     } else {
         const int top = s_win[0], left = s_win[1], ch = s_win[2], cw = s_win[3];
         if (ch > 0 && cw > 0) {
-            int sx = static_cast<int>(floor(x * s_inv[0])); if (sx > cw - 1) sx = cw - 1;
             int sy = static_cast<int>(floor(y * s_inv[1])); if (sy > ch - 1) sy = ch - 1;
-            const int fy_ = top + sy, fx_ = left + sx;
-            if (fy_ >= 0 && fy_ < a.H && fx_ >= 0 && fx_ < a.W) {
-                const size_t fo = static_cast<size_t>(fy_) * a.W + fx_;
-                const uint8_t* pr = a.frame_rgb + fo * 3;
-                r = pr[0]; gch = pr[1]; b = pr[2];
-                d = a.frame_depth[fo];
+            const int fy_ = top + sy;
+            if (fy_ >= 0 && fy_ < a.H) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    int sx = static_cast<int>(floor((x0 + i) * s_inv[0])); if (sx > cw - 1) sx = cw - 1;
+                    const int fx_ = left + sx;
+                    if (fx_ >= 0 && fx_ < a.W) {
+                        const size_t fo = static_cast<size_t>(fy_) * a.W + fx_;
+                        const uint8_t* pr = a.frame_rgb + fo * 3;
+                        rB[i] = pr[0]; gB[i] = pr[1]; bB[i] = pr[2];
+                        dB[i] = a.frame_depth[fo];
+                    }
+                }
             }
         }
     }
     if (a.crop_rgb) {
-        uint8_t* o = a.crop_rgb + (static_cast<size_t>(n) * kImg * kImg + pix) * 3;
-        o[0] = r; o[1] = gch; o[2] = b;
+        uint32_t* o = reinterpret_cast<uint32_t*>(a.crop_rgb + ao * 3);
+        o[0] = rB[0] | (gB[0] << 8) | (bB[0] << 16) | (rB[1] << 24);
+        o[1] = gB[1] | (bB[1] << 8) | (rB[2] << 16) | (gB[2] << 24);
+        o[2] = bB[2] | (rB[3] << 8) | (gB[3] << 16) | (bB[3] << 24);
     }
-    if (a.crop_depth) a.crop_depth[static_cast<size_t>(n) * kImg * kImg + pix] = static_cast<uint16_t>(d);
+    if (a.crop_depth) *reinterpret_cast<uint2*>(a.crop_depth + ao) = make_uint2(dB[0] | (dB[1] << 16), dB[2] | (dB[3] << 16));
 
-    // ---- A: rendered previous view -----------------------------------------------------------
-    const size_t ao = static_cast<size_t>(n) * kImg * kImg + pix;
-    const uint8_t* pa = a.rgbA + ao * 3;
-    const unsigned ra = pa[0], ga = pa[1], ba = pa[2], da = a.depthA[ao];
+    // ---- A: rendered previous view (4 pixels) ---------------------------------------------------
+    unsigned rA[4], gA[4], bA[4], dA[4];
+    {
+        const uint32_t* pr = reinterpret_cast<const uint32_t*>(a.rgbA + ao * 3);
+        const uint32_t w0 = pr[0], w1 = pr[1], w2 = pr[2];
+        rA[0] = w0 & 255; gA[0] = (w0 >> 8) & 255; bA[0] = (w0 >> 16) & 255;
+        rA[1] = w0 >> 24; gA[1] = w1 & 255; bA[1] = (w1 >> 8) & 255;
+        rA[2] = (w1 >> 16) & 255; gA[2] = w1 >> 24; bA[2] = w2 & 255;
+        rA[3] = (w2 >> 8) & 255; gA[3] = (w2 >> 16) & 255; bA[3] = w2 >> 24;
+        const uint2 dd = *reinterpret_cast<const uint2*>(a.depthA + ao);
+        dA[0] = dd.x & 0xffff; dA[1] = dd.x >> 16; dA[2] = dd.y & 0xffff; dA[3] = dd.y >> 16;
+    }
 
     const int wi = a.weight_ids ? a.weight_ids[n] : 0;
-    float4 vA, vB;
-    const float dA = depth_offset(da, z1000, gl), dB = depth_offset(d, z1000, gl);
-    if (a.stats_f64) {
-        const double* m = a.mean64 + wi * 8; const double* s = a.std64 + wi * 8;
-        vA = make_float4(norm_f64(ra, m[0], s[0]), norm_f64(ga, m[1], s[1]), norm_f64(ba, m[2], s[2]), norm_f64(dA, m[3], s[3]));
-        vB = make_float4(norm_f64(r, m[4], s[4]), norm_f64(gch, m[5], s[5]), norm_f64(b, m[6], s[6]), norm_f64(dB, m[7], s[7]));
-    } else {
-        const float* m = a.mean32 + wi * 8; const float* s = a.std32 + wi * 8;
-        vA = make_float4(norm_f32(ra, m[0], s[0]), norm_f32(ga, m[1], s[1]), norm_f32(ba, m[2], s[2]), norm_f32(dA, m[3], s[3]));
-        vB = make_float4(norm_f32(r, m[4], s[4]), norm_f32(gch, m[5], s[5]), norm_f32(b, m[6], s[6]), norm_f32(dB, m[7], s[7]));
+    float4 vA[4], vB[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float zA = depth_offset(dA[i], z1000, gl), zB = depth_offset(dB[i], z1000, gl);
+        if (a.stats_f64) {
+            const double* m = a.mean64 + wi * 8; const double* s = a.std64 + wi * 8;
+            vA[i] = make_float4(norm_f64(rA[i], m[0], s[0]), norm_f64(gA[i], m[1], s[1]), norm_f64(bA[i], m[2], s[2]), norm_f64(zA, m[3], s[3]));
+            vB[i] = make_float4(norm_f64(rB[i], m[4], s[4]), norm_f64(gB[i], m[5], s[5]), norm_f64(bB[i], m[6], s[6]), norm_f64(zB, m[7], s[7]));
+        } else {
+            const float* m = a.mean32 + wi * 8; const float* s = a.std32 + wi * 8;
+            vA[i] = make_float4(norm_f32(rA[i], m[0], s[0]), norm_f32(gA[i], m[1], s[1]), norm_f32(bA[i], m[2], s[2]), norm_f32(zA, m[3], s[3]));
+            vB[i] = make_float4(norm_f32(rB[i], m[4], s[4]), norm_f32(gB[i], m[5], s[5]), norm_f32(bB[i], m[6], s[6]), norm_f32(zB, m[7], s[7]));
+        }
     }
     if (a.nchwA) {
-        float* oa = a.nchwA + static_cast<size_t>(n) * 4 * kImg * kImg + pix;
-        float* ob = a.nchwB + static_cast<size_t>(n) * 4 * kImg * kImg + pix;
-        oa[0] = vA.x; oa[kImg * kImg] = vA.y; oa[2 * kImg * kImg] = vA.z; oa[3 * kImg * kImg] = vA.w;
-        ob[0] = vB.x; ob[kImg * kImg] = vB.y; ob[2 * kImg * kImg] = vB.z; ob[3 * kImg * kImg] = vB.w;
+        float* oa = a.nchwA + static_cast<size_t>(n) * 4 * kImg * kImg + pix0;
+        float* ob = a.nchwB + static_cast<size_t>(n) * 4 * kImg * kImg + pix0;
+        *reinterpret_cast<float4*>(oa) = make_float4(vA[0].x, vA[1].x, vA[2].x, vA[3].x);
+        *reinterpret_cast<float4*>(oa + kImg * kImg) = make_float4(vA[0].y, vA[1].y, vA[2].y, vA[3].y);
+        *reinterpret_cast<float4*>(oa + 2 * kImg * kImg) = make_float4(vA[0].z, vA[1].z, vA[2].z, vA[3].z);
+        *reinterpret_cast<float4*>(oa + 3 * kImg * kImg) = make_float4(vA[0].w, vA[1].w, vA[2].w, vA[3].w);
+        *reinterpret_cast<float4*>(ob) = make_float4(vB[0].x, vB[1].x, vB[2].x, vB[3].x);
+        *reinterpret_cast<float4*>(ob + kImg * kImg) = make_float4(vB[0].y, vB[1].y, vB[2].y, vB[3].y);
+        *reinterpret_cast<float4*>(ob + 2 * kImg * kImg) = make_float4(vB[0].z, vB[1].z, vB[2].z, vB[3].z);
+        *reinterpret_cast<float4*>(ob + 3 * kImg * kImg) = make_float4(vB[0].w, vB[1].w, vB[2].w, vB[3].w);
     }
     if (a.stemA) {
-        vA = pack_stem_pixel(vA, a.round_tf32);
-        vB = pack_stem_pixel(vB, a.round_tf32);
-        const size_t so = (static_cast<size_t>(n) * kStemH + (y + 3)) * kStemW + (x + 3);
-        reinterpret_cast<float4*>(a.stemA)[so] = vA;
-        reinterpret_cast<float4*>(a.stemB)[so] = vB;
+        const size_t so = (static_cast<size_t>(n) * kStemH + (y + 3)) * kStemW + (x0 + 3);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            reinterpret_cast<float4*>(a.stemA)[so + i] = pack_stem_pixel(vA[i], a.round_tf32);
+            reinterpret_cast<float4*>(a.stemB)[so + i] = pack_stem_pixel(vB[i], a.round_tf32);
+        }
     }
+}
+
+static cudaError_t launch_pdl(const void* func, dim3 grid, dim3 block, void** args, cudaStream_t s) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelExC(&cfg, func, args);
 }
 
 cudaError_t launch_preprocess(const PreprocessArgs& a, int n, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
-    dim3 grid((kImg * kImg + 255) / 256, n);
-    preprocess_kernel<<<grid, 256, 0, s>>>(a);
-    return cudaGetLastError();
+    dim3 grid((kImg * kImg / 4 + 255) / 256, n);
+    PreprocessArgs aa = a;
+    void* args[] = {&aa};
+    return launch_pdl(reinterpret_cast<const void*>(preprocess_kernel), grid, dim3(256), args, s);
 }
 
 // =============================================================================================
@@ -295,23 +340,30 @@ cudaError_t launch_maxpool(const float* in, float* out, int n_img, int Hin, int 
 // (reference se3_tracknet.py:100-102, 107-109).  x: NHWC (N, 11*11, 1024): channels [0,512) are
 // the translation head, [512,1024) the rotation head.  One CTA (256 threads x 4 channels) per image.
 // =============================================================================================
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 head_kernel(const float4* __restrict__ x, const float* __restrict__ fcw /*[6][512]*/, const float* __restrict__ fcb /*[6]*/,
             float* __restrict__ out_trans, float* __restrict__ out_rot, int npix, int split_bf16)
 {
-    __shared__ float red[8][3];
-    const int n = blockIdx.x, t = threadIdx.x;
+    // grid (n, 2): blockIdx.y = head (0 trans: channels 0..511, 1 rot: 512..1023).  512 threads =
+    // 4 pixel groups x 128 threads, each thread 4 channels.
+    ptx::grid_dep_launch();
+    __shared__ float4 part4[4][128];
+    __shared__ float red[4][3];
+    const int n = blockIdx.x, head = blockIdx.y, t = threadIdx.x;
+    const int cq = t & 127, pg = t >> 7;
+    const int c = head * 512 + cq * 4;                 // first of this thread's 4 channels
+    ptx::grid_dep_wait();
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!split_bf16) {
-        const float4* xp = x + static_cast<size_t>(n) * npix * 256 + t;
-        for (int p = 0; p < npix; ++p) {
+        const float4* xp = x + static_cast<size_t>(n) * npix * 256 + (c >> 2);
+        for (int p = pg; p < npix; p += 4) {
             const float4 v = __ldg(xp + static_cast<size_t>(p) * 256);
             s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
         }
     } else {
-        // channels 4t..4t+3 live in chunk (4t)/32 as bf16 hi at byte ((4t)%32)*2 and lo 64 bytes further
-        const uint8_t* xb = reinterpret_cast<const uint8_t*>(x) + static_cast<size_t>(n) * npix * 4096 + ((4 * t) >> 5) * 128 + ((4 * t) & 31) * 2;
-        for (int p = 0; p < npix; ++p) {
+        // channels c..c+3 live in chunk c/32 as bf16 hi at byte (c%32)*2 and lo 64 bytes further
+        const uint8_t* xb = reinterpret_cast<const uint8_t*>(x) + static_cast<size_t>(n) * npix * 4096 + (c >> 5) * 128 + (c & 31) * 2;
+        for (int p = pg; p < npix; p += 4) {
             const uint2 h = __ldg(reinterpret_cast<const uint2*>(xb + static_cast<size_t>(p) * 4096));
             const uint2 l = __ldg(reinterpret_cast<const uint2*>(xb + static_cast<size_t>(p) * 4096 + 64));
             const float2 h0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&h.x)), h1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&h.y));
@@ -319,34 +371,38 @@ head_kernel(const float4* __restrict__ x, const float* __restrict__ fcw /*[6][51
             s.x += h0.x + l0.x; s.y += h0.y + l0.y; s.z += h1.x + l1.x; s.w += h1.y + l1.y;
         }
     }
-    const float inv = 1.0f / static_cast<float>(npix);
-    s.x *= inv; s.y *= inv; s.z *= inv; s.w *= inv;
-    const int head = t >> 7;                 // 0: trans, 1: rot
-    const int c = (t & 127) * 4;             // channel within the head
-    float part[3];
-#pragma unroll
-    for (int o = 0; o < 3; ++o) {
-        const float4 w = __ldg(reinterpret_cast<const float4*>(fcw + (head * 3 + o) * 512 + c));
-        part[o] = s.x * w.x + s.y * w.y + s.z * w.z + s.w * w.w;
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1)
-#pragma unroll
-        for (int o = 0; o < 3; ++o) part[o] += __shfl_xor_sync(0xffffffffu, part[o], off);
-    if ((t & 31) == 0) { red[t >> 5][0] = part[0]; red[t >> 5][1] = part[1]; red[t >> 5][2] = part[2]; }
+    part4[pg][cq] = s;
     __syncthreads();
-    if (t < 6) {
-        const int h = t / 3, o = t % 3;
-        const float v = red[h * 4 + 0][o] + red[h * 4 + 1][o] + red[h * 4 + 2][o] + red[h * 4 + 3][o] + fcb[t];
-        (h == 0 ? out_trans : out_rot)[n * 3 + o] = tanhf(v);
+    if (t < 128) {
+        const float4 a0 = part4[0][t], a1 = part4[1][t], a2 = part4[2][t], a3 = part4[3][t];
+        const float inv = 1.0f / static_cast<float>(npix);
+        const float mx = ((a0.x + a1.x) + (a2.x + a3.x)) * inv, my = ((a0.y + a1.y) + (a2.y + a3.y)) * inv;
+        const float mz = ((a0.z + a1.z) + (a2.z + a3.z)) * inv, mw = ((a0.w + a1.w) + (a2.w + a3.w)) * inv;
+        float part[3];
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(fcw + (head * 3 + o) * 512 + t * 4));
+            part[o] = mx * w.x + my * w.y + mz * w.z + mw * w.w;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+            for (int o = 0; o < 3; ++o) part[o] += __shfl_xor_sync(0xffffffffu, part[o], off);
+        if ((t & 31) == 0) { red[t >> 5][0] = part[0]; red[t >> 5][1] = part[1]; red[t >> 5][2] = part[2]; }
+    }
+    __syncthreads();
+    if (t < 3) {
+        const float v = red[0][t] + red[1][t] + red[2][t] + red[3][t] + fcb[head * 3 + t];
+        (head == 0 ? out_trans : out_rot)[n * 3 + t] = tanhf(v);
     }
 }
 
 cudaError_t launch_head(const float* x, const float* fcw, const float* fcb, float* out_trans, float* out_rot,
                         int n_img, int npix, int split_bf16, cudaStream_t s) {
     if (n_img <= 0) return cudaSuccess;
-    head_kernel<<<n_img, 256, 0, s>>>(reinterpret_cast<const float4*>(x), fcw, fcb, out_trans, out_rot, npix, split_bf16);
-    return cudaGetLastError();
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    void* args[] = {&x4, &fcw, &fcb, &out_trans, &out_rot, &npix, &split_bf16};
+    return launch_pdl(reinterpret_cast<const void*>(head_kernel), dim3(n_img, 2), dim3(512), args, s);
 }
 
 // =============================================================================================
@@ -460,6 +516,8 @@ __global__ void pose_update_kernel(const double* __restrict__ poses_in, const fl
                                    const float* __restrict__ rot, float tn, float rn,
                                    double* __restrict__ poses_out, int n)
 {
+    ptx::grid_dep_launch();
+    ptx::grid_dep_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double* A = poses_in + i * 16;
@@ -487,8 +545,8 @@ __global__ void pose_update_kernel(const double* __restrict__ poses_in, const fl
 cudaError_t launch_pose_update(const double* poses_in, const float* trans, const float* rot, float tn, float rn,
                                double* poses_out, int n, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
-    pose_update_kernel<<<(n + 127) / 128, 128, 0, s>>>(poses_in, trans, rot, tn, rn, poses_out, n);
-    return cudaGetLastError();
+    void* args[] = {&poses_in, &trans, &rot, &tn, &rn, &poses_out, &n};
+    return launch_pdl(reinterpret_cast<const void*>(pose_update_kernel), dim3((n + 31) / 32), dim3(32), args, s);
 }
 
 // =============================================================================================
