@@ -192,10 +192,16 @@ class Tracker:
         return final_estimate
 
     def on_track_batch(self, prev_poses, current_rgb, current_depth, rgbA, depthA, weight_ids=None, object_width=None):
-        """N independent tracks of ONE frame -> (N,4,4) float64.  Inputs may be numpy arrays (returns
-        numpy) or CUDA tensors (returns a CUDA tensor; nothing is synchronised)."""
+        """N independent tracks of ONE frame -> (N,4,4) float64.
+
+        numpy inputs   -> numpy result (synchronous, like the reference's on_track).
+        CUDA tensors   -> CUDA tensor, nothing is synchronised.
+        CPU tensors    -> CUDA tensor; the host->device copies run on a side stream into double-buffered
+                          staging, so the uploads of call k overlap the kernels of call k-1 (pinned memory
+                          makes them truly asynchronous).  Nothing is synchronised."""
         dev = self.engine.device
         as_numpy = not torch.is_tensor(prev_poses)
+        staged = all(torch.is_tensor(x) and not x.is_cuda for x in (prev_poses, current_rgb, current_depth, rgbA, depthA))
 
         def up(x, dt):
             if torch.is_tensor(x):
@@ -205,7 +211,12 @@ class Tracker:
                 a = a.astype(np.uint16)
             return torch.from_numpy(a).to(dev).to(dt)
 
-        poses = up(prev_poses, torch.float64)
+        if staged:
+            poses, rgb_d, depth_d, rgbA_d, depthA_d = self._stage_uploads(prev_poses, current_rgb, current_depth, rgbA, depthA)
+        else:
+            poses = up(prev_poses, torch.float64)
+            rgb_d, depth_d = up(current_rgb, torch.uint8), up(current_depth, torch.uint16)
+            rgbA_d, depthA_d = up(rgbA, torch.uint8), up(depthA, torch.uint16)
         n = poses.shape[0]
         ow = torch.full((n,), float(self.object_width), dtype=torch.float64, device=dev) if object_width is None else up(object_width, torch.float64)
         wh = None
@@ -213,8 +224,35 @@ class Tracker:
             wh = np.ascontiguousarray(weight_ids.cpu().numpy() if torch.is_tensor(weight_ids) else weight_ids, dtype=np.int32)
         elif self.weight_id != 0:
             wh = np.full(n, self.weight_id, dtype=np.int32)
-        out, _, _ = self.engine.track_batch(up(current_rgb, torch.uint8), up(current_depth, torch.uint16), self.K, poses, ow,
-                                            up(rgbA, torch.uint8), up(depthA, torch.uint16),
+        out, _, _ = self.engine.track_batch(rgb_d, depth_d, self.K, poses, ow, rgbA_d, depthA_d,
                                             self.trans_normalizer, self.rot_normalizer,
                                             weight_ids_host=wh, precision=self.precision)
+        if staged:
+            self._stage_done[self._stage_slot].record(torch.cuda.current_stream(dev))
         return out.cpu().numpy() if as_numpy else out
+
+    # ------------------------------------------------------------------ pipelined uploads
+    def _stage_uploads(self, *cpu_tensors):
+        """Copy host tensors into one of two device staging sets on a side stream."""
+        dev = self.engine.device
+        if not hasattr(self, '_copy_stream'):
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._stage_bufs = [None, None]
+            self._stage_done = [torch.cuda.Event(), torch.cuda.Event()]
+            self._stage_slot = 0
+        self._stage_slot ^= 1
+        slot = self._stage_slot
+        want = [(torch.float64, cpu_tensors[0]), (torch.uint8, cpu_tensors[1]), (torch.uint16, cpu_tensors[2]),
+                (torch.uint8, cpu_tensors[3]), (torch.uint16, cpu_tensors[4])]
+        bufs = self._stage_bufs[slot]
+        if bufs is None or any(b.shape != t.shape for b, (_, t) in zip(bufs, want)):
+            bufs = [torch.empty(t.shape, dtype=dt, device=dev) for dt, t in want]
+            self._stage_bufs[slot] = bufs
+        cs = self._copy_stream
+        cs.wait_event(self._stage_done[slot])            # the kernels that last read this staging set are done
+        with torch.cuda.stream(cs):
+            for b, (dt, t) in zip(bufs, want):
+                b.copy_(t if t.dtype == dt else t.to(dt), non_blocking=True)
+            ev = torch.cuda.Event(); ev.record(cs)
+        torch.cuda.current_stream(dev).wait_event(ev)
+        return bufs

@@ -287,6 +287,11 @@ def test_on_track_end_to_end_vs_oracle(pkg, synth):
     singles = np.stack([trk.on_track(poses[i], rgb, depth, rgbA=rgbA[i], depthA=depthA[i]) for i in range(n)])
     assert np.array_equal(batch, singles)
     assert trk.frame_cnt == 2 * n
+    # host tensors: uploads staged on the tracker's copy stream (double-buffered); result stays on the device
+    host = [torch.from_numpy(a) for a in (poses, rgb, depth, rgbA, depthA)]
+    for _ in range(3):                                   # exercises both staging slots and their reuse
+        staged = trk.on_track_batch(*host)
+        assert staged.is_cuda and np.array_equal(staged.cpu().numpy(), batch)
 
 
 def test_track_batch_mixed_weight_sets(synth, eng):
