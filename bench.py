@@ -39,6 +39,7 @@ def parse():
     ap.add_argument('--batch', type=int, default=64)
     ap.add_argument('--precision', default='bf16x3', choices=['bf16x3', 'tf32', 'bf16', 'fp32'])
     ap.add_argument('--no-alt', action='store_true', help='skip the secondary precision-mode measurements')
+    ap.add_argument('--weight-sets', type=int, default=1, help='object classes (one checkpoint each, reference README.md:132); track i uses set i*G//batch')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     return ap.parse_args()
@@ -209,6 +210,9 @@ def main():
     sd = synth.make_state_dict(0)
     mean, std = synth.default_mean_std()
     eng.load_state_dict(sd, 0); eng.set_stats(mean, std, 0)
+    G = max(1, args.weight_sets)
+    for wid in range(1, G):
+        eng.load_state_dict(synth.make_state_dict(wid), wid); eng.set_stats(mean, std, wid)
 
     # ---- synthetic inputs, N_INPUT_SETS distinct sets resident in HBM -------
     frames, sets = [], []
@@ -222,7 +226,8 @@ def main():
                     depthA=torch.from_numpy(depthA).pin_memory())
         sets.append((host, {k2: v.to(dev) for k2, v in host.items()}))
     ow = torch.full((nb,), 200.0, dtype=torch.float64, device=dev)
-    tracker = dist_mod.ShardedTracker(eng, np.zeros(nb * world, np.int32), synth.CAMERA_K, 200.0, TN, RN, rank, world, args.precision)
+    all_wids = np.tile((np.arange(nb) * G // nb).astype(np.int32), world)       # grouped by id within every rank's slice
+    tracker = dist_mod.ShardedTracker(eng, all_wids, synth.CAMERA_K, 200.0, TN, RN, rank, world, args.precision)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
     def step(k, gather=True):
@@ -385,7 +390,7 @@ def main():
                            'tracks_per_gpu': nb, 'total_tracks': nb * world, 'precision': args.precision,
                            'parallelism': 'tracks sharded, %d/GPU, NCCL all-gather of poses per step' % nb if world > 1 else 'single GPU',
                            'l2': 'flushed between timed steps (256 MiB memset, untimed); %d rotating input sets; per-step CUDA events, max over ranks' % N_INPUT_SETS,
-                           'weights': 'random-init (seeded), one weight set'},
+                           'weights': 'random-init (seeded), %d weight set(s)%s' % (G, '' if G == 1 else ' (one per object class; all classes batched into the same 14 conv launches)')},
                 'gpu_launches': int(launches), 'launches_per_step': int(launches // max(args.steps, 1)),
                 'roofline': roofline, 'alt_precisions': alt, 'parity': parity, 'cpu_baseline': cpu, 'e2e': e2e, 'clocks': clocks,
                 'ms_per_step_min': float(ms_steps.min()), 'ms_per_step_median': float(np.median(ms_steps))}

@@ -342,7 +342,8 @@ cudaError_t launch_maxpool(const float* in, float* out, int n_img, int Hin, int 
 // =============================================================================================
 __global__ void __launch_bounds__(512)
 head_kernel(const float4* __restrict__ x, const float* __restrict__ fcw /*[6][512]*/, const float* __restrict__ fcb /*[6]*/,
-            float* __restrict__ out_trans, float* __restrict__ out_rot, int npix, int split_bf16)
+            float* __restrict__ out_trans, float* __restrict__ out_rot, int npix, int split_bf16,
+            const int* __restrict__ img_wid, const float* const* __restrict__ fc_table)
 {
     // grid (n, 2): blockIdx.y = head (0 trans: channels 0..511, 1 rot: 512..1023).  512 threads =
     // 4 pixel groups x 128 threads, each thread 4 channels.
@@ -353,6 +354,7 @@ head_kernel(const float4* __restrict__ x, const float* __restrict__ fcw /*[6][51
     const int cq = t & 127, pg = t >> 7;
     const int c = head * 512 + cq * 4;                 // first of this thread's 4 channels
     ptx::grid_dep_wait();
+    if (img_wid) { fcw = fc_table[img_wid[n]]; fcb = fcw + 6 * 512; }    // per-object head weights
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!split_bf16) {
         const float4* xp = x + static_cast<size_t>(n) * npix * 256 + (c >> 2);
@@ -398,10 +400,10 @@ head_kernel(const float4* __restrict__ x, const float* __restrict__ fcw /*[6][51
 }
 
 cudaError_t launch_head(const float* x, const float* fcw, const float* fcb, float* out_trans, float* out_rot,
-                        int n_img, int npix, int split_bf16, cudaStream_t s) {
+                        int n_img, int npix, int split_bf16, const int* img_wid, const float* const* fc_table, cudaStream_t s) {
     if (n_img <= 0) return cudaSuccess;
     const float4* x4 = reinterpret_cast<const float4*>(x);
-    void* args[] = {&x4, &fcw, &fcb, &out_trans, &out_rot, &npix, &split_bf16};
+    void* args[] = {&x4, &fcw, &fcb, &out_trans, &out_rot, &npix, &split_bf16, &img_wid, &fc_table};
     return launch_pdl(reinterpret_cast<const void*>(head_kernel), dim3(n_img, 2), dim3(512), args, s);
 }
 

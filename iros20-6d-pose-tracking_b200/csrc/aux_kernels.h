@@ -39,7 +39,7 @@ cudaError_t launch_crop(const uint8_t* frame_rgb, const uint16_t* frame_depth, i
 cudaError_t launch_nchw_to_stem(const float* src, float* dst, int n, int round_tf32, cudaStream_t s);
 cudaError_t launch_maxpool(const float* in, float* out, int n_img, int Hin, int Win, int C, cudaStream_t s);
 cudaError_t launch_head(const float* x, const float* fcw, const float* fcb, float* out_trans, float* out_rot,
-                        int n_img, int npix, int split_bf16, cudaStream_t s);
+                        int n_img, int npix, int split_bf16, const int* img_wid, const float* const* fc_table, cudaStream_t s);
 cudaError_t launch_nhwc_to_nchw(const float* in, float* out, int n_img, int HW, int C, int split_bf16, cudaStream_t s);
 cudaError_t launch_split_weights(const float* src, void* dst, size_t words, cudaStream_t s);
 cudaError_t launch_split_stem_weights(const float* src /*[64][224]*/, void* dst /*[64][448 words]*/, cudaStream_t s);

@@ -46,12 +46,19 @@ struct ConvGeom {
     int round_tf32;      // fp32-word storage: round stored activations to tf32 (rna) so the next UMMA sees exact operands
 };
 
+constexpr int kLayersPerSet = 14;     // conv launches per weight set (stride of the per-set device tables)
+
 struct ConvPtrs {
     const float* in;
     const float* w;      // [groups*cout][num_taps*cin]
     const float* bias;   // [groups*cout]
     const float* res;    // nullable, NHWC
     float* out;
+    // multi-weight-set launches (v2 kernel): weight-set id per absolute image index, and per-set tables that are
+    // already offset to this layer (entry of set w at [w * kLayersPerSet])
+    const int* img_wid;            // nullable: single-set launch (maps.b / bias above)
+    const CUtensorMap* gbmaps;     // device array of weight tensor maps
+    const float* const* gbias;     // device array of bias pointers
 };
 
 // ---- tcgen05 path only ------------------------------------------------------------------

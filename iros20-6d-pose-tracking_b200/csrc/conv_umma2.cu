@@ -23,6 +23,10 @@
 //     CTAs start on SMs as they drain and run their prologue (barrier init, TMEM alloc, weight TMA --
 //     weights are never written during a forward) under the tail of this one; only the activation
 //     producer and the epilogue warps execute griddepcontrol.wait before touching activations.
+//   * Per-object weights in ONE launch (reference README.md:132: one checkpoint per object class): with
+//     p.img_wid set, each work unit looks up its image's weight-set id and takes its weight tensor map and
+//     bias from device tables; RESIDENT kernels reload their shared-memory weights when the id changes
+//     between consecutive tiles (CTAs own CONTIGUOUS tile ranges, so with tracks grouped by id that is rare).
 //   * N = 64 tiles (stem, 64-channel layers) are capped by the hardware: one 128xNx32B tcgen05.mma costs
 //     ~90 cycles for any N <= 128 (128 for N = 256; scripts/umma_rate.cu), i.e. 35 % of peak at N = 64.
 //   * MT = 2 ("dual-M", BN = 256 layers): one CTA carries TWO M tiles (two accumulators, all 512
@@ -168,6 +172,15 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
     const int lane = threadIdx.x & 31;
     const int m_units = (t.m_tiles + MT - 1) / MT;
     const int total_tiles = m_units * t.n_tiles * g.groups;       // work units
+    // each CTA owns a contiguous range of work units (consecutive tiles of the same image / weight set)
+    const int w_begin = static_cast<int>(static_cast<long long>(blockIdx.x) * total_tiles / gridDim.x);
+    const int w_end = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * total_tiles / gridDim.x);
+    auto wid_of = [&](int work) -> int {            // weight-set id of a work unit (-1: single-set launch)
+        if (!p.img_wid) return -1;
+        const WorkUnit wu = decode_work(work, m_units, t);
+        int m = wu.mp * MT; if (m >= t.m_tiles) m = t.m_tiles - 1;
+        return p.img_wid[decode2(m, t).n0];
+    };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::kAStages; ++s) { ptx::mbar_init(&a_full[s], 1); ptx::mbar_init(&a_empty[s], 1); }
@@ -187,7 +200,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
         if (lane == 0) {
             ptx::grid_dep_wait();                   // activations come from the previous kernel
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = w_begin; tile < w_end; ++tile) {
                 const WorkUnit wu = decode_work(tile, m_units, t);
                 TileCoord2 tc[MT];
 #pragma unroll
@@ -215,15 +228,25 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
         // ============================== B producer ================================
         if (lane == 0) {
             if (RESIDENT) {
-                // whole K-major weight matrix of this CTA's (only) N tile: loaded once
-                ptx::mbar_arrive_expect_tx(&b_full[0], static_cast<uint32_t>(w_tiles) * C::kBTile);
-                for (int wt = 0; wt < w_tiles; ++wt)      // tile wt = (tap*chunks + ch)*kWPerTap + pass, 32 words of K each
-                    ptx::tma_load_2d(sB + wt * C::kBTile, &maps.b, &b_full[0], wt * 32, 0);
+                // whole K-major weight matrix of this CTA's (only) N tile; reloaded only when the weight-set id changes
+                int cur = -2; uint32_t gen = 0;
+                for (int tile = w_begin; tile < w_end; ++tile) {
+                    const int wid = wid_of(tile);
+                    if (wid == cur) continue;
+                    if (gen) ptx::mbar_wait(&b_empty[0], (gen - 1) & 1);       // MMAs that read the previous weights have retired
+                    const CUtensorMap* bm = wid < 0 ? &maps.b : p.gbmaps + wid * kLayersPerSet;
+                    ptx::mbar_arrive_expect_tx(&b_full[0], static_cast<uint32_t>(w_tiles) * C::kBTile);
+                    for (int wt = 0; wt < w_tiles; ++wt)      // tile wt = (tap*chunks + ch)*kWPerTap + pass, 32 words of K each
+                        ptx::tma_load_2d(sB + wt * C::kBTile, bm, &b_full[0], wt * 32, 0);
+                    cur = wid; ++gen;
+                }
             } else {
                 int stage = 0; uint32_t phase = 0;
-                for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                for (int tile = w_begin; tile < w_end; ++tile) {
                     const WorkUnit wu = decode_work(tile, m_units, t);
                     const int wrow = wu.grp * g.cout + wu.n_tile * BN;
+                    const int wid = wid_of(tile);
+                    const CUtensorMap* bm = wid < 0 ? &maps.b : p.gbmaps + wid * kLayersPerSet;
                     for (int ch = 0; ch < t.chunks; ++ch)
                         for (int u = 0; u < t.units_per_chunk; ++u) {
                             const Unit un = t.units[u];
@@ -231,7 +254,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                                 ptx::mbar_wait(&b_empty[stage], phase ^ 1);
                                 if (t.debug & 1) { ptx::mbar_arrive(&b_full[stage]); if (++stage == C::kBStages) { stage = 0; phase ^= 1; } continue; }   // timing experiment: no B fill
                                 ptx::mbar_arrive_expect_tx(&b_full[stage], C::kBTile);
-                                ptx::tma_load_2d(sB + stage * C::kBTile, &maps.b, &b_full[stage], un.taps[k].w_tap * g.cin + ch * 32, wrow);
+                                ptx::tma_load_2d(sB + stage * C::kBTile, bm, &b_full[stage], un.taps[k].w_tap * g.cin + ch * 32, wrow);
                                 if (++stage == C::kBStages) { stage = 0; phase ^= 1; }
                             }
                         }
@@ -247,9 +270,13 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
         constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
         int astage = 0; uint32_t aphase = 0;
         int bstage = 0; uint32_t bphase = 0;
-        if (RESIDENT) { ptx::mbar_wait(&b_full[0], 0); ptx::tc_fence_after(); }
+        int w_cur = -2; uint32_t w_gen = 0;        // RESIDENT: weight-set currently in shared memory
         int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        for (int tile = w_begin; tile < w_end; ++tile, ++it) {
+            if (RESIDENT) {
+                const int wid = wid_of(tile);
+                if (wid != w_cur) { ptx::mbar_wait(&b_full[0], w_gen & 1); ptx::tc_fence_after(); w_cur = wid; ++w_gen; }
+            }
             const int acc = it % C::kNAcc;
             const uint32_t acc_phase = (it / C::kNAcc) & 1;
             ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -319,7 +346,11 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                     if (++astage == C::kAStages) { astage = 0; aphase ^= 1; }
                 }
             }
-            if (ptx::elect_one()) ptx::umma_commit(&tmem_full[acc]);
+            if (ptx::elect_one()) {
+                ptx::umma_commit(&tmem_full[acc]);
+                // RESIDENT: the next tile uses other weights -> tell the loader when these MMAs have retired
+                if (RESIDENT && tile + 1 < w_end && wid_of(tile + 1) != w_cur) ptx::umma_commit(&b_empty[0]);
+            }
             __syncwarp();
         }
     } else if (warp >= 4) {
@@ -337,7 +368,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
             const int rem = row - pn * box;
             const int py = rem / t.bw;
             const int px = rem - py * t.bw;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            for (int tile = w_begin; tile < w_end; ++tile, ++it) {
                 const int acc = it % C::kNAcc;
                 const uint32_t acc_phase = (it / C::kNAcc) & 1;
                 const WorkUnit wu = decode_work(tile, m_units, t);
@@ -360,6 +391,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                             rowtab[lane] = valid ? (n * g.Ho + y) * g.Wo + x : -1;   // pixel index of TMEM row q*32 + lane
                         }
                         const int ch0 = wu.grp * g.cout + wu.n_tile * BN + half * kCols;
+                        const float* bias_base = p.img_wid ? p.gbias[p.img_wid[tc.n0] * kLayersPerSet] : p.bias;
                         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * C::kAccCols + j * (BN * C::kSplit) + half * kCols;
 #pragma unroll 1
                         for (int c0 = 0; c0 < kCols; c0 += 32) {
@@ -377,7 +409,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                             }
                             __syncwarp();
                             const int chan = ch0 + c0;                        // first channel (word index) of this 32-channel chunk
-                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + chan + grp * 4));
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias_base + chan + grp * 4));
                             int pix[8];
 #pragma unroll
                             for (int k = 0; k < 8; ++k) pix[k] = rowtab[4 * k + sub];
@@ -446,7 +478,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                     const int ch0 = wu.grp * g.cout + wu.n_tile * BN + half * kCols;
                     float* outp = p.out + pix * g.out_cstride + g.out_coff + ch0;
                     const float* resp = p.res ? p.res + pix * g.res_cstride + g.res_coff + ch0 : nullptr;
-                    const float* biasp = p.bias + ch0;
+                    const float* biasp = (p.img_wid ? p.gbias[p.img_wid[tc.n0] * kLayersPerSet] : p.bias) + ch0;
                     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * C::kAccCols + j * (BN * C::kSplit) + half * kCols;
 #pragma unroll 1
                     for (int c0 = 0; c0 < kCols; c0 += 32) {
@@ -531,7 +563,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
             // ---- stem: conv tile 11x11 -> 5x5 max-pooled outputs (MaxPool2d(3,2,1), -inf padding) ----
             const int cy_l = row / 11, cx_l = row - cy_l * 11;          // conv position inside the tile
             const int et = threadIdx.x - 128;                           // 0..255 among epilogue threads
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            for (int tile = w_begin; tile < w_end; ++tile, ++it) {
                 const int acc = it % C::kNAcc;
                 const uint32_t acc_phase = (it / C::kNAcc) & 1;
                 const WorkUnit wu = decode_work(tile, m_units, t);
@@ -590,7 +622,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                             const float4 s4 = *reinterpret_cast<const float4*>(stage + ((2 * ppy + dy) * 11 + 2 * ppx + dx) * kPoolPitch + c4);
                             m.x = fmaxf(m.x, s4.x); m.y = fmaxf(m.y, s4.y); m.z = fmaxf(m.z, s4.z); m.w = fmaxf(m.w, s4.w);
                         }
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c4));
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>((p.img_wid ? p.gbias[p.img_wid[tc.n0] * kLayersPerSet] : p.bias) + c4));
                     const float v0 = selu_fast(m.x + b4.x), v1 = selu_fast(m.y + b4.y), v2 = selu_fast(m.z + b4.z), v3 = selu_fast(m.w + b4.w);
                     const int n = tc.n0;
                     if (n >= g.n_img) continue;

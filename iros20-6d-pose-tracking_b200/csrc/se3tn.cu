@@ -118,6 +118,10 @@ struct se3tn_ctx {
     // device copies of per-set stats, rebuilt when a set changes: [max_id+1][8]
     float* d_mean32 = nullptr; float* d_std32 = nullptr; double* d_mean64 = nullptr; double* d_std64 = nullptr;
     int stats_rows = 0; bool stats_dirty = true; int stats_f64 = 0;
+    // per-weight-set device tables for multi-set launches, rebuilt when a set is (re)loaded: entry [wid*14 + layer]
+    CUtensorMap* d_bmaps_tf32 = nullptr; CUtensorMap* d_bmaps_bf16 = nullptr;
+    const float** d_bias = nullptr; const float** d_fc = nullptr;   // d_fc[wid] -> [6][512] weights then [6] biases
+    int table_rows = 0; bool tables_dirty = true;
     int launches = 0;
     bool profiling = false;
     cudaEvent_t ev0[SE3TN_PROFILE_SLOTS] = {}, ev1[SE3TN_PROFILE_SLOTS] = {};
@@ -412,9 +416,46 @@ int sync_stats(se3tn_ctx* c, cudaStream_t s) {
     return SE3TN_OK;
 }
 
-// The conv stack on images [first, first+n) of the context buffers.
+int sync_tables(se3tn_ctx* c, cudaStream_t s) {
+    if (!c->tables_dirty) return SE3TN_OK;
+    int max_id = -1;
+    for (auto& kv : c->weights) if (kv.second.dev && kv.first > max_id) max_id = kv.first;
+    if (max_id < 0) return fail(c, SE3TN_ERR_STATE, "no weight set loaded");
+    const int rows = max_id + 1;
+    CU_TRY(c, cudaStreamSynchronize(s));
+    if (rows > c->table_rows) {
+        cudaFree(c->d_bmaps_tf32); cudaFree(c->d_bmaps_bf16); cudaFree(c->d_bias); cudaFree(c->d_fc);
+        CU_TRY(c, cudaMalloc(&c->d_bmaps_tf32, sizeof(CUtensorMap) * rows * kLayersPerSet));
+        CU_TRY(c, cudaMalloc(&c->d_bmaps_bf16, sizeof(CUtensorMap) * rows * kLayersPerSet));
+        CU_TRY(c, cudaMalloc(&c->d_bias, sizeof(float*) * rows * kLayersPerSet));
+        CU_TRY(c, cudaMalloc(&c->d_fc, sizeof(float*) * rows));
+        c->table_rows = rows;
+    }
+    std::vector<CUtensorMap> m1(rows * kLayersPerSet), m2(rows * kLayersPerSet);
+    std::vector<const float*> bias(rows * kLayersPerSet, nullptr), fc(rows, nullptr);
+    memset(m1.data(), 0, m1.size() * sizeof(CUtensorMap)); memset(m2.data(), 0, m2.size() * sizeof(CUtensorMap));
+    for (auto& kv : c->weights) {
+        if (!kv.second.dev || kv.first < 0) continue;
+        for (int li = 0; li < kLayersPerSet; ++li) {
+            m1[kv.first * kLayersPerSet + li] = kv.second.bmap[li];
+            m2[kv.first * kLayersPerSet + li] = kv.second.bmap_bf16[li];
+            bias[kv.first * kLayersPerSet + li] = kv.second.dev + kv.second.b_off[li];
+        }
+        fc[kv.first] = kv.second.dev + kv.second.fc_off;
+    }
+    CU_TRY(c, cudaMemcpy(c->d_bmaps_tf32, m1.data(), m1.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    CU_TRY(c, cudaMemcpy(c->d_bmaps_bf16, m2.data(), m2.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    CU_TRY(c, cudaMemcpy(c->d_bias, bias.data(), bias.size() * sizeof(float*), cudaMemcpyHostToDevice));
+    CU_TRY(c, cudaMemcpy(c->d_fc, fc.data(), fc.size() * sizeof(float*), cudaMemcpyHostToDevice));
+    c->tables_dirty = false;
+    return SE3TN_OK;
+}
+
+// The conv stack on images [first, first+n) of the context buffers.  img_wid (device, indexed by absolute image
+// index) non-null: every image uses its own weight set in the same launches (tensor-core modes, v2 kernel);
+// `weight_id` is then only a representative loaded set.
 int run_network(se3tn_ctx* c, int weight_id, int first, int n, int precision,
-                float* out_trans, float* out_rot, float* out_feature, cudaStream_t s) {
+                float* out_trans, float* out_rot, float* out_feature, cudaStream_t s, const int* img_wid = nullptr) {
     auto it = c->weights.find(weight_id);
     if (it == c->weights.end()) return fail(c, SE3TN_ERR_STATE, "weight set " + std::to_string(weight_id) + " not loaded");
     const WeightSet& ws = it->second;
@@ -424,6 +465,10 @@ int run_network(se3tn_ctx* c, int weight_id, int first, int n, int precision,
     if (!tensor && precision != SE3TN_PREC_FP32) return fail(c, SE3TN_ERR_INVALID, "unknown precision");
     if (bf16 && c->conv_version != 2) return fail(c, SE3TN_ERR_INVALID, "bf16 modes need the v2 conv kernel (unset SE3TN_CONV)");
     const int kprec = tf32 ? 0 : (precision == SE3TN_PREC_BF16X3 ? 1 : 2);
+    if (img_wid) {
+        if (!tensor || c->conv_version != 2) return fail(c, SE3TN_ERR_INVALID, "multi-weight-set launches need a tensor-core precision and the v2 kernel");
+        int rc = sync_tables(c, s); if (rc) return rc;
+    }
     const float* wbase = tf32 ? ws.dev_tf32 : ws.dev;
     auto bufp = [&](Buf b) { return c->buf[b] + kBufFloats[b] * static_cast<size_t>(first); };
     for (int li = 0; li < 14; ++li) {
@@ -432,6 +477,9 @@ int run_network(se3tn_ctx* c, int weight_id, int first, int n, int precision,
         ConvPtrs p;
         p.in = bufp(L.in); p.out = bufp(L.out); p.res = (L.res != NONE) ? bufp(L.res) : nullptr;
         p.w = wbase + ws.w_off[li]; p.bias = ws.dev + ws.b_off[li];
+        p.img_wid = img_wid;
+        p.gbmaps = img_wid ? (bf16 ? c->d_bmaps_bf16 : c->d_bmaps_tf32) + li : nullptr;
+        p.gbias = img_wid ? c->d_bias + li : nullptr;
         if (tensor && c->conv_version == 2) {
             UmmaMaps maps;
             const int nmaps = (L.kind == K_STEM) ? 2 : (L.kind == K_S2 ? 4 : 1);
@@ -449,7 +497,7 @@ int run_network(se3tn_ctx* c, int weight_id, int first, int n, int precision,
                 g.out_cstride = 64; g.out_coff = 0;
             }
             { ProfScope ps(c, li, s); CU_TRY(c, launch_conv_umma2(maps, g, t, p, BN, resident, L.kind == K_STEM ? KIND_STEM : (L.kind == K_S2 ? KIND_S2 : KIND_S1),
-                                                                     (BN == 256 && c->dual_m) ? 2 : 1, kprec, c->num_sms, s)); }
+                                                                     (BN == 256 && c->dual_m && !img_wid) ? 2 : 1, kprec, c->num_sms, s)); }
             ++c->launches;
             continue;
         }
@@ -478,7 +526,8 @@ int run_network(se3tn_ctx* c, int weight_id, int first, int n, int precision,
         if (li == 0) { ProfScope ps(c, 14, s); CU_TRY(c, launch_maxpool(bufp(B_Y1A), bufp(B_P1A), n, 88, 88, 64, s)); ++c->launches; }
         if (li == 1) { ProfScope ps(c, 15, s); CU_TRY(c, launch_maxpool(bufp(B_Y1B), bufp(B_P1B), n, 88, 88, 64, s)); ++c->launches; }
     }
-    { ProfScope ps(c, 16, s); CU_TRY(c, launch_head(bufp(B_H3), ws.dev + ws.fc_off, ws.dev + ws.fc_off + 6 * 512, out_trans, out_rot, n, 121, bf16 ? 1 : 0, s)); }
+    { ProfScope ps(c, 16, s); CU_TRY(c, launch_head(bufp(B_H3), ws.dev + ws.fc_off, ws.dev + ws.fc_off + 6 * 512, out_trans, out_rot, n, 121, bf16 ? 1 : 0,
+                                                   img_wid ? img_wid + first : nullptr, img_wid ? c->d_fc : nullptr, s)); }
     ++c->launches;
     if (out_feature) { CU_TRY(c, launch_nhwc_to_nchw(bufp(B_F2), out_feature, n, 22 * 22, 256, bf16 ? 1 : 0, s)); ++c->launches; }
     return SE3TN_OK;
@@ -556,6 +605,7 @@ void se3tn_destroy(se3tn_ctx* c) {
     cudaSetDevice(c->device);
     for (auto& kv : c->weights) { cudaFree(kv.second.dev); cudaFree(kv.second.dev_tf32); cudaFree(kv.second.dev_bf16); cudaFree(kv.second.dev_stem_bf16); }
     cudaFree(c->d_mean32); cudaFree(c->d_std32); cudaFree(c->d_mean64); cudaFree(c->d_std64);
+    cudaFree(c->d_bmaps_tf32); cudaFree(c->d_bmaps_bf16); cudaFree(c->d_bias); cudaFree(c->d_fc);
     for (int i = 0; i < SE3TN_PROFILE_SLOTS; ++i) { if (c->ev0[i]) cudaEventDestroy(c->ev0[i]); if (c->ev1[i]) cudaEventDestroy(c->ev1[i]); }
     if (c->own_workspace) cudaFree(c->workspace);
     delete c;
@@ -602,6 +652,7 @@ int se3tn_load_weights(se3tn_ctx* c, int weight_id, const float* blob, size_t n_
     }
     CU_TRY(c, cudaDeviceSynchronize());
     ws.fc_off = off;
+    c->tables_dirty = true;
     return SE3TN_OK;
 }
 
@@ -748,15 +799,29 @@ int se3tn_track_batch(se3tn_ctx* c, const uint8_t* frame_rgb, const uint16_t* fr
     int rc = se3tn_preprocess(c, frame_rgb, frame_depth, H, W, K, poses_in, object_width, rgbA, depthA, weight_ids_dev, n,
                               precision, nullptr, nullptr, nullptr, nullptr, stream);
     if (rc) return rc;
-    int first = 0;
-    while (first < n) {
-        const int wid = weight_ids_host ? weight_ids_host[first] : 0;
-        int last = first + 1;
-        while (last < n && (weight_ids_host ? weight_ids_host[last] : 0) == wid) ++last;
-        rc = run_network(c, wid, first, last - first, precision, out_trans + first * 3, out_rot + first * 3, nullptr,
-                         static_cast<cudaStream_t>(stream));
+    bool multi = false;
+    if (weight_ids_host) {
+        for (int i = 0; i < n; ++i) {
+            if (c->weights.find(weight_ids_host[i]) == c->weights.end() || !c->weights[weight_ids_host[i]].dev)
+                return fail(c, SE3TN_ERR_STATE, "weight set " + std::to_string(weight_ids_host[i]) + " not loaded");
+            if (weight_ids_host[i] != weight_ids_host[0]) multi = true;
+        }
+    }
+    if (multi && precision != SE3TN_PREC_FP32 && c->conv_version == 2) {
+        // every track picks its own weight set inside the same 14 conv launches
+        rc = run_network(c, weight_ids_host[0], 0, n, precision, out_trans, out_rot, nullptr, static_cast<cudaStream_t>(stream), weight_ids_dev);
         if (rc) return rc;
-        first = last;
+    } else {
+        int first = 0;
+        while (first < n) {
+            const int wid = weight_ids_host ? weight_ids_host[first] : 0;
+            int last = first + 1;
+            while (last < n && (weight_ids_host ? weight_ids_host[last] : 0) == wid) ++last;
+            rc = run_network(c, wid, first, last - first, precision, out_trans + first * 3, out_rot + first * 3, nullptr,
+                             static_cast<cudaStream_t>(stream));
+            if (rc) return rc;
+            first = last;
+        }
     }
     return se3tn_pose_update(c, poses_in, out_trans, out_rot, tn, rn, poses_out, n, stream);
 }
