@@ -144,8 +144,11 @@ int se3tn_so3_log(se3tn_ctx* ctx, const double* poses_a, const double* poses_b,
 
 /* Tracker.on_track for n independent tracks of one frame (reference predict.py:217-296 with the
  * renderer's output passed in and the GUI calls dropped): K0 -> conv stack -> K6 on one stream.
- * weight_ids_host: int32 (n) HOST array or NULL (all 0); tracks with equal ids must be contiguous
- * (each run is one batched forward).  weight_ids_dev: the same values on the device (or NULL).
+ * weight_ids_host: int32 (n) HOST array or NULL (all 0), weight_ids_dev: the same values on the device (or NULL).
+ * In the tensor-core modes tracks of ALL object classes share the same 14 conv launches: every work unit
+ * takes its weight tensor map / bias from per-set device tables.  Any id order is correct; keeping equal ids
+ * contiguous (dist.shard_tracks does) avoids shared-memory weight reloads in the 64-channel layers.  In
+ * SE3TN_PREC_FP32 each contiguous run of equal ids is one batched forward.
  * out_trans/out_rot float32 (n,3) device scratch the caller provides (also returned). */
 int se3tn_track_batch(se3tn_ctx* ctx, const uint8_t* frame_rgb, const uint16_t* frame_depth, int H, int W,
                       const double* K, const double* poses_in, const double* object_width,
