@@ -96,6 +96,7 @@ struct Umma2Plan {
     int tiles_x, tiles_y, m_tiles, n_tiles;
     int img_first;
     int base_off_mode;                   // 0: descriptor base_offset = 0; 1: (addr >> 7) & 7
+    int pair;                            // resident-weight kernels: run as CTA pairs (cta_group::2); maps.b must then box BN/2 rows
     int pdl;                             // launch with programmatic stream serialization (overlap prologue with the previous conv's tail)
     int debug;                           // timing experiments only (results are garbage): bit0 skip B fills, bit1 skip A fills
 };

@@ -27,6 +27,11 @@
 //     p.img_wid set, each work unit looks up its image's weight-set id and takes its weight tensor map and
 //     bias from device tables; RESIDENT kernels reload their shared-memory weights when the id changes
 //     between consecutive tiles (CTAs own CONTIGUOUS tile ranges, so with tracks grouped by id that is rare).
+//   * PAIR (resident-weight kernels: stem, 64-channel layers): clusters of two CTAs run ONE tcgen05.mma.cta_group::2
+//     of M = 256 per step -- each CTA supplies its own pixel tile (A) and HALF of the weight rows (B) from its own
+//     shared memory, the leader CTA issues, commits are multicast to both.  Measured (profiles/
+//     r01_umma_rate3_cta_pair_probe.txt): an N = 64 pair MMA costs 43 cycles for twice the work of a 52-65 cycle
+//     single-CTA MMA, i.e. 74 % instead of ~35 % of the per-SM tensor peak.
 //   * N = 64 tiles (stem, 64-channel layers) are capped by the hardware: one 128xNx32B tcgen05.mma costs
 //     ~90 cycles for any N <= 128 (128 for N = 256; scripts/umma_rate.cu), i.e. 35 % of peak at N = 64.
 //   * MT = 2 ("dual-M", BN = 256 layers): one CTA carries TWO M tiles (two accumulators, all 512
@@ -47,6 +52,7 @@
 #include "conv_common.h"
 #include "ptx.cuh"
 #include <cuda_bf16.h>
+#include <algorithm>
 
 namespace se3tn {
 namespace {
@@ -81,12 +87,13 @@ template <> struct KTab<KIND_STEM> {          // 7x7 stride 2 stem: even input r
     __host__ __device__ static constexpr int wtap(int u, int k) { return 2 * k + u; }
 };
 
-template <int BN, bool RESIDENT, int KIND, int MT, int PREC = 0> struct Cfg2 {
+template <int BN, bool RESIDENT, int KIND, int MT, int PREC = 0, bool PAIR = false> struct Cfg2 {
+    static_assert(!PAIR || (RESIDENT && MT == 1), "CTA pairs are implemented for the resident-weight kernels");
     static constexpr bool POOL = (KIND == KIND_STEM);
-    static constexpr int kBTile = BN * kChunkBytes;
+    static constexpr int kBTile = (PAIR ? BN / 2 : BN) * kChunkBytes;    // pair: each CTA holds half of the weight rows
     static constexpr int kAUnit = POOL ? 21 * 1024 : 19 * 1024;     // 3x3: (22 + 128) rows * 128 B = 19,200
     static constexpr int kAStage = MT * kAUnit;
-    static constexpr int kAStages = RESIDENT ? ((POOL && PREC != PREC_TF32) ? 3 : 4) : (MT == 2 ? 2 : 3);
+    static constexpr int kAStages = RESIDENT ? (PAIR ? (POOL ? 4 : 6) : ((POOL && PREC != PREC_TF32) ? 3 : 4)) : (MT == 2 ? 2 : 3);
     static constexpr bool kEpiT = !RESIDENT;                            // transposed (coalesced) epilogue through per-warp smem tiles
     static constexpr int kEpiPitch = 36;                                // words per staged row (32 + 4: conflict-free 16 B accesses)
     static constexpr int kEpiWarpBytes = 32 * kEpiPitch * 4 + 128;      // 32 rows + 32-entry pixel-index table
@@ -143,11 +150,11 @@ __device__ __forceinline__ float2 unpack2(uint32_t w) {
     return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
 }
 
-template <int BN, bool RESIDENT, int KIND, int MT, int PREC>
+template <int BN, bool RESIDENT, int KIND, int MT, int PREC, bool PAIR>
 __global__ void __launch_bounds__(kThreads2, 1)
 conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const Umma2Plan t, const ConvPtrs p)
 {
-    using C = Cfg2<BN, RESIDENT, KIND, MT, PREC>;
+    using C = Cfg2<BN, RESIDENT, KIND, MT, PREC, PAIR>;
     using KT = KTab<KIND>;
     constexpr bool POOL = C::POOL;
     static_assert(!(POOL && MT != 1), "pool epilogue is single-tile");
@@ -172,12 +179,24 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
     const int lane = threadIdx.x & 31;
     const int m_units = (t.m_tiles + MT - 1) / MT;
     const int total_tiles = m_units * t.n_tiles * g.groups;       // work units
-    // each CTA owns a contiguous range of work units (consecutive tiles of the same image / weight set)
-    const int w_begin = static_cast<int>(static_cast<long long>(blockIdx.x) * total_tiles / gridDim.x);
-    const int w_end = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * total_tiles / gridDim.x);
+    // each CTA (pair) owns a contiguous range of work units (consecutive tiles of the same image / weight set);
+    // in a pair, CTA rank r handles tile 2*work + r of every work unit and both walk the range in lockstep
+    const uint32_t crank = PAIR ? ptx::cluster_ctarank() : 0u;
+    const bool leader = !PAIR || crank == 0;
+    const int n_split = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+    const int my_split = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int total_work = PAIR ? (total_tiles + 1) / 2 : total_tiles;
+    const int w_begin = static_cast<int>(static_cast<long long>(my_split) * total_work / n_split);
+    const int w_end = static_cast<int>(static_cast<long long>(my_split + 1) * total_work / n_split);
+    auto tile_of = [&](int work) -> int {          // this CTA's tile of a work unit (odd tail of a pair: clamp, result discarded)
+        if (!PAIR) return work;
+        const int tl = 2 * work + static_cast<int>(crank);
+        return tl < total_tiles ? tl : total_tiles - 1;
+    };
+    auto tile_valid = [&](int work) -> bool { return !PAIR || 2 * work + static_cast<int>(crank) < total_tiles; };
     auto wid_of = [&](int work) -> int {            // weight-set id of a work unit (-1: single-set launch)
         if (!p.img_wid) return -1;
-        const WorkUnit wu = decode_work(work, m_units, t);
+        const WorkUnit wu = decode_work(tile_of(work), m_units, t);
         int m = wu.mp * MT; if (m >= t.m_tiles) m = t.m_tiles - 1;
         return p.img_wid[decode2(m, t).n0];
     };
@@ -185,13 +204,16 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::kAStages; ++s) { ptx::mbar_init(&a_full[s], 1); ptx::mbar_init(&a_empty[s], 1); }
         for (int s = 0; s < (RESIDENT ? 1 : C::kBStages); ++s) { ptx::mbar_init(&b_full[s], 1); ptx::mbar_init(&b_empty[s], 1); }
-        for (int a = 0; a < C::kNAcc; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], 8); }
+        for (int a = 0; a < C::kNAcc; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], PAIR ? 16 : 8); }   // pair: both CTAs' epilogue warps arrive on the leader's
         ptx::fence_barrier_init();
         ptx::fence_proxy_async();
     }
-    if (warp == 2) { ptx::tmem_alloc(tmem_slot, C::kTmemCols); ptx::tmem_relinquish(); }
+    if (warp == 2) {
+        if (PAIR) { ptx::tmem_alloc_2sm(tmem_slot, C::kTmemCols); ptx::tmem_relinquish_2sm(); }
+        else      { ptx::tmem_alloc(tmem_slot, C::kTmemCols); ptx::tmem_relinquish(); }
+    }
     ptx::tc_fence_before();
-    __syncthreads();
+    if (PAIR) ptx::cluster_sync(); else __syncthreads();     // barrier inits must be visible to the peer before any remote signal
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -201,7 +223,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
             ptx::grid_dep_wait();                   // activations come from the previous kernel
             int stage = 0; uint32_t phase = 0;
             for (int tile = w_begin; tile < w_end; ++tile) {
-                const WorkUnit wu = decode_work(tile, m_units, t);
+                const WorkUnit wu = decode_work(tile_of(tile), m_units, t);
                 TileCoord2 tc[MT];
 #pragma unroll
                 for (int j = 0; j < MT; ++j) {
@@ -213,12 +235,19 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                     for (int u = 0; u < t.units_per_chunk; ++u) {
                         const Unit un = t.units[u];
                         ptx::mbar_wait(&a_empty[stage], phase ^ 1);
-                        if (t.debug & 2) { ptx::mbar_arrive(&a_full[stage]); if (++stage == C::kAStages) { stage = 0; phase ^= 1; } continue; }   // timing experiment: no A fill
-                        ptx::mbar_arrive_expect_tx(&a_full[stage], static_cast<uint32_t>(un.rows) * kChunkBytes * MT);
+                        if (!PAIR && (t.debug & 2)) { ptx::mbar_arrive(&a_full[stage]); if (++stage == C::kAStages) { stage = 0; phase ^= 1; } continue; }   // timing experiment: no A fill
+                        if (PAIR) {
+                            // the leader's barrier collects the bytes of BOTH CTAs' boxes
+                            if (leader) ptx::mbar_arrive_expect_tx(&a_full[stage], static_cast<uint32_t>(un.rows) * kChunkBytes * 2);
+                            ptx::tma_load_4d_2sm(sA + stage * C::kAStage, &maps.a[un.map], &a_full[stage],
+                                                 cbase + ch * 32, tc[0].ox + un.c1, tc[0].oy + un.c2, tc[0].n0);
+                        } else {
+                            ptx::mbar_arrive_expect_tx(&a_full[stage], static_cast<uint32_t>(un.rows) * kChunkBytes * MT);
 #pragma unroll
-                        for (int j = 0; j < MT; ++j)
-                            ptx::tma_load_4d(sA + stage * C::kAStage + j * C::kAUnit, &maps.a[un.map], &a_full[stage],
-                                             cbase + ch * 32, tc[j].ox + un.c1, tc[j].oy + un.c2, tc[j].n0);
+                            for (int j = 0; j < MT; ++j)
+                                ptx::tma_load_4d(sA + stage * C::kAStage + j * C::kAUnit, &maps.a[un.map], &a_full[stage],
+                                                 cbase + ch * 32, tc[j].ox + un.c1, tc[j].oy + un.c2, tc[j].n0);
+                        }
                         if (++stage == C::kAStages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -235,15 +264,21 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                     if (wid == cur) continue;
                     if (gen) ptx::mbar_wait(&b_empty[0], (gen - 1) & 1);       // MMAs that read the previous weights have retired
                     const CUtensorMap* bm = wid < 0 ? &maps.b : p.gbmaps + wid * kLayersPerSet;
-                    ptx::mbar_arrive_expect_tx(&b_full[0], static_cast<uint32_t>(w_tiles) * C::kBTile);
-                    for (int wt = 0; wt < w_tiles; ++wt)      // tile wt = (tap*chunks + ch)*kWPerTap + pass, 32 words of K each
-                        ptx::tma_load_2d(sB + wt * C::kBTile, bm, &b_full[0], wt * 32, 0);
+                    if (PAIR) {                               // each CTA loads its half of the weight rows; the leader's barrier counts both
+                        if (leader) ptx::mbar_arrive_expect_tx(&b_full[0], static_cast<uint32_t>(w_tiles) * C::kBTile * 2);
+                        for (int wt = 0; wt < w_tiles; ++wt)
+                            ptx::tma_load_2d_2sm(sB + wt * C::kBTile, bm, &b_full[0], wt * 32, static_cast<int>(crank) * (BN / 2));
+                    } else {
+                        ptx::mbar_arrive_expect_tx(&b_full[0], static_cast<uint32_t>(w_tiles) * C::kBTile);
+                        for (int wt = 0; wt < w_tiles; ++wt)      // tile wt = (tap*chunks + ch)*kWPerTap + pass, 32 words of K each
+                            ptx::tma_load_2d(sB + wt * C::kBTile, bm, &b_full[0], wt * 32, 0);
+                    }
                     cur = wid; ++gen;
                 }
             } else {
                 int stage = 0; uint32_t phase = 0;
                 for (int tile = w_begin; tile < w_end; ++tile) {
-                    const WorkUnit wu = decode_work(tile, m_units, t);
+                    const WorkUnit wu = decode_work(tile_of(tile), m_units, t);
                     const int wrow = wu.grp * g.cout + wu.n_tile * BN;
                     const int wid = wid_of(tile);
                     const CUtensorMap* bm = wid < 0 ? &maps.b : p.gbmaps + wid * kLayersPerSet;
@@ -261,11 +296,14 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                 }
             }
         }
-    } else if (warp == 1) {
-        // ============================== MMA issuer ================================
+    } else if (warp == 1 && leader) {
+        // ============================== MMA issuer (pair: leader CTA only) ========
         // The WHOLE warp walks the loop (warp-uniform control flow lets ptxas keep descriptors and
         // barrier addresses in uniform registers); one elected lane issues the tcgen05 instructions.
-        constexpr uint32_t idesc = ptx::umma_idesc(PREC == PREC_TF32 ? 2u /*tf32*/ : 1u /*bf16*/, kBlockM, BN);
+        constexpr uint32_t idesc = ptx::umma_idesc(PREC == PREC_TF32 ? 2u /*tf32*/ : 1u /*bf16*/, PAIR ? 2 * kBlockM : kBlockM, BN);
+        auto mma_tf32 = [](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc_) { if (PAIR) ptx::umma_tf32_2sm(d, a, b, id, acc_); else ptx::umma_tf32(d, a, b, id, acc_); };
+        auto mma_f16 = [](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc_) { if (PAIR) ptx::umma_f16_2sm(d, a, b, id, acc_); else ptx::umma_f16(d, a, b, id, acc_); };
+        auto commit = [](uint64_t* bar) { if (PAIR) ptx::umma_commit_2sm(bar, 3); else ptx::umma_commit(bar); };
         // descriptor high word: SBO = 1024 B (>>4) | version 1 (bit 46) | SWIZZLE_128B (bits 61..63)
         constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
         int astage = 0; uint32_t aphase = 0;
@@ -315,41 +353,41 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                                 if (PREC == PREC_TF32) {
 #pragma unroll
                                     for (int kk = 0; kk < 4; ++kk)
-                                        ptx::umma_tf32(dst(kk), desc(aj + 2 * kk), desc(b_lo + 2 * kk), idesc, accf(kk));
+                                        mma_tf32(dst(kk), desc(aj + 2 * kk), desc(b_lo + 2 * kk), idesc, accf(kk));
                                 } else if (POOL) {
                                     // stem window = 8 pixels x [hi4|lo4]: pass 0 against [w_hi|w_hi], pass 1 against [w_lo|0]
 #pragma unroll
                                     for (int ps = 0; ps < 2; ++ps)
 #pragma unroll
                                         for (int kk = 0; kk < 4; ++kk)
-                                            ptx::umma_f16(dst(ps * 4 + kk), desc(aj + 2 * kk), desc(b_lo + ps * (C::kBTile >> 4) + 2 * kk), idesc, accf(ps * 4 + kk));
+                                            mma_f16(dst(ps * 4 + kk), desc(aj + 2 * kk), desc(b_lo + ps * (C::kBTile >> 4) + 2 * kk), idesc, accf(ps * 4 + kk));
                                 } else if (PREC == PREC_BF16X3) {
                                     // chunk = [32 hi | 32 lo] bf16 (A) x [32 w_hi | 32 w_lo] (B); offsets in 16-byte units
                                     constexpr int AO[6] = {0, 2, 4, 6, 0, 2};      // hi, hi, lo, lo, hi, hi
                                     constexpr int BO[6] = {0, 2, 0, 2, 4, 6};      // w_hi x4,        w_lo x2
 #pragma unroll
                                     for (int i = 0; i < 6; ++i)
-                                        ptx::umma_f16(dst(i), desc(aj + AO[i]), desc(b_lo + BO[i]), idesc, accf(i));
+                                        mma_f16(dst(i), desc(aj + AO[i]), desc(b_lo + BO[i]), idesc, accf(i));
                                 } else {
-                                    ptx::umma_f16(dst(0), desc(aj), desc(b_lo), idesc, accf(0));
-                                    ptx::umma_f16(dst(1), desc(aj + 2), desc(b_lo + 2), idesc, accf(1));
+                                    mma_f16(dst(0), desc(aj), desc(b_lo), idesc, accf(0));
+                                    mma_f16(dst(1), desc(aj + 2), desc(b_lo + 2), idesc, accf(1));
                                 }
                             }
-                            if (!RESIDENT) ptx::umma_commit(&b_empty[bstage]);
+                            if (!RESIDENT) commit(&b_empty[bstage]);
                         }
                         __syncwarp();
                         cnt += (PREC == PREC_TF32) ? 4u : (POOL ? 8u : (PREC == PREC_BF16X3 ? 6u : 2u));
                         if (!RESIDENT) { if (++bstage == C::kBStages) { bstage = 0; bphase ^= 1; } }
                     }
-                    if (ptx::elect_one()) ptx::umma_commit(&a_empty[astage]);
+                    if (ptx::elect_one()) commit(&a_empty[astage]);
                     __syncwarp();
                     if (++astage == C::kAStages) { astage = 0; aphase ^= 1; }
                 }
             }
             if (ptx::elect_one()) {
-                ptx::umma_commit(&tmem_full[acc]);
+                commit(&tmem_full[acc]);
                 // RESIDENT: the next tile uses other weights -> tell the loader when these MMAs have retired
-                if (RESIDENT && tile + 1 < w_end && wid_of(tile + 1) != w_cur) ptx::umma_commit(&b_empty[0]);
+                if (RESIDENT && tile + 1 < w_end && wid_of(tile + 1) != w_cur) commit(&b_empty[0]);
             }
             __syncwarp();
         }
@@ -371,7 +409,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
             for (int tile = w_begin; tile < w_end; ++tile, ++it) {
                 const int acc = it % C::kNAcc;
                 const uint32_t acc_phase = (it / C::kNAcc) & 1;
-                const WorkUnit wu = decode_work(tile, m_units, t);
+                const WorkUnit wu = decode_work(tile_of(tile), m_units, t);
                 ptx::mbar_wait(&tmem_full[acc], acc_phase);
                 ptx::tc_fence_after();
                 if constexpr (C::kEpiT) {
@@ -473,7 +511,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                     if (m >= t.m_tiles) break;                               // odd tail (warp-uniform)
                     const TileCoord2 tc = decode2(m, t);
                     const int n = tc.n0 + pn, y = tc.ty * t.bh + py, x = tc.tx * t.bw + px;
-                    const bool valid = (pn < t.bn) && (n < g.n_img) && (y < g.Ho) && (x < g.Wo);
+                    const bool valid = (pn < t.bn) && (n < g.n_img) && (y < g.Ho) && (x < g.Wo) && tile_valid(tile);
                     const size_t pix = (static_cast<size_t>(n) * g.Ho + y) * g.Wo + x;
                     const int ch0 = wu.grp * g.cout + wu.n_tile * BN + half * kCols;
                     float* outp = p.out + pix * g.out_cstride + g.out_coff + ch0;
@@ -557,7 +595,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                 }
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+                if (lane == 0) { if (leader) ptx::mbar_arrive(&tmem_empty[acc]); else ptx::mbar_arrive_cluster(&tmem_empty[acc], 0); }
             }
         } else {
             // ---- stem: conv tile 11x11 -> 5x5 max-pooled outputs (MaxPool2d(3,2,1), -inf padding) ----
@@ -566,7 +604,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
             for (int tile = w_begin; tile < w_end; ++tile, ++it) {
                 const int acc = it % C::kNAcc;
                 const uint32_t acc_phase = (it / C::kNAcc) & 1;
-                const WorkUnit wu = decode_work(tile, m_units, t);
+                const WorkUnit wu = decode_work(tile_of(tile), m_units, t);
                 const TileCoord2 tc = decode2(wu.mp, t);
                 float* stage = reinterpret_cast<float*>(sP + (C::kPoolBufs == 2 ? (it & 1) : 0) * ((kPoolStageBytes + 1023) & ~1023));
                 const int cy = tc.oy + cy_l, cx = tc.ox + cx_l;             // conv output coordinates
@@ -605,7 +643,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                 }
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);          // accumulator drained
+                if (lane == 0) { if (leader) ptx::mbar_arrive(&tmem_empty[acc]); else ptx::mbar_arrive_cluster(&tmem_empty[acc], 0); }   // accumulator drained
                 asm volatile("bar.sync 1, 256;" ::: "memory");             // staging tile complete (epilogue warps only)
 
                 // 25 pooled pixels x 16 float4 channel groups = 400 vectors over 256 threads
@@ -625,7 +663,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                     const float4 b4 = __ldg(reinterpret_cast<const float4*>((p.img_wid ? p.gbias[p.img_wid[tc.n0] * kLayersPerSet] : p.bias) + c4));
                     const float v0 = selu_fast(m.x + b4.x), v1 = selu_fast(m.y + b4.y), v2 = selu_fast(m.z + b4.z), v3 = selu_fast(m.w + b4.w);
                     const int n = tc.n0;
-                    if (n >= g.n_img) continue;
+                    if (n >= g.n_img || !tile_valid(tile)) continue;
                     float* po = p.out + ((static_cast<size_t>(n) * g.Ho + oy) * g.Wo + ox) * g.out_cstride + g.out_coff;
                     if (PREC == PREC_TF32) {
                         float4 o = make_float4(v0, v1, v2, v3);
@@ -646,8 +684,11 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
     }
 
     ptx::tc_fence_before();
-    __syncthreads();
-    if (warp == 2) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, C::kTmemCols); }
+    if (PAIR) ptx::cluster_sync(); else __syncthreads();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        if (PAIR) ptx::tmem_dealloc_2sm(tmem_base, C::kTmemCols); else ptx::tmem_dealloc(tmem_base, C::kTmemCols);
+    }
 }
 
 template <int KIND>
@@ -662,36 +703,45 @@ bool plan_matches(const Umma2Plan& t) {
     return true;
 }
 
-template <int BN, bool RESIDENT, int KIND, int MT, int PREC>
+template <int BN, bool RESIDENT, int KIND, int MT, int PREC, bool PAIR = false>
 cudaError_t launch2(const UmmaMaps& maps, const ConvGeom& g, const Umma2Plan& t, const ConvPtrs& p, int num_sms, cudaStream_t stream) {
-    using C = Cfg2<BN, RESIDENT, KIND, MT, PREC>;
+    using C = Cfg2<BN, RESIDENT, KIND, MT, PREC, PAIR>;
     if (!plan_matches<KIND>(t)) return cudaErrorInvalidValue;
+    if (PAIR && (p.img_wid || t.n_tiles != 1 || g.groups != 1)) return cudaErrorInvalidValue;
     const int w_tiles = g.num_taps * t.chunks * C::kWPerTap;
     const size_t smem = static_cast<size_t>(C::kAStages) * C::kAStage + static_cast<size_t>(RESIDENT ? w_tiles : C::kBStages) * C::kBTile +
                         C::kPoolBufs * ((kPoolStageBytes + 1023) & ~1023) + ((C::kEpiBytes + 1023) & ~1023) + 1024 + 512;
     if (smem > 232448) return cudaErrorInvalidConfiguration;
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
-        cudaError_t e = cudaFuncSetAttribute(conv_umma2_kernel<BN, RESIDENT, KIND, MT, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        cudaError_t e = cudaFuncSetAttribute(conv_umma2_kernel<BN, RESIDENT, KIND, MT, PREC, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;
         attr_smem = smem;
     }
     const int total = ((t.m_tiles + MT - 1) / MT) * t.n_tiles * g.groups;
-    const int grid = total < num_sms ? total : num_sms;
+    int grid = total < num_sms ? total : num_sms;
+    if (PAIR) { const int pairs = std::min((total + 1) / 2, num_sms / 2); grid = 2 * pairs; }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads2); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = t.pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, conv_umma2_kernel<BN, RESIDENT, KIND, MT, PREC>, maps, g, t, p);
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (PAIR) { attr[na].id = cudaLaunchAttributeClusterDimension; attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1; ++na; }
+    if (t.pdl) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
+    cfg.attrs = attr; cfg.numAttrs = na;
+    return cudaLaunchKernelEx(&cfg, conv_umma2_kernel<BN, RESIDENT, KIND, MT, PREC, PAIR>, maps, g, t, p);
 }
 
 template <int PREC>
 cudaError_t dispatch2(const UmmaMaps& maps, const ConvGeom& g, const Umma2Plan& t, const ConvPtrs& p,
                       int block_n, bool resident, int kind, int m_per_cta, int num_sms, cudaStream_t stream) {
-    if (kind == KIND_STEM) return (block_n == 64 && resident) ? launch2<64, true, KIND_STEM, 1, PREC>(maps, g, t, p, num_sms, stream) : cudaErrorInvalidValue;
-    if (resident) return (block_n == 64 && kind == KIND_S1) ? launch2<64, true, KIND_S1, 1, PREC>(maps, g, t, p, num_sms, stream) : cudaErrorInvalidValue;
+    if (kind == KIND_STEM) {
+        if (block_n != 64 || !resident) return cudaErrorInvalidValue;
+        return t.pair ? launch2<64, true, KIND_STEM, 1, PREC, true>(maps, g, t, p, num_sms, stream) : launch2<64, true, KIND_STEM, 1, PREC>(maps, g, t, p, num_sms, stream);
+    }
+    if (resident) {
+        if (block_n != 64 || kind != KIND_S1) return cudaErrorInvalidValue;
+        return t.pair ? launch2<64, true, KIND_S1, 1, PREC, true>(maps, g, t, p, num_sms, stream) : launch2<64, true, KIND_S1, 1, PREC>(maps, g, t, p, num_sms, stream);
+    }
     if (block_n != 256) return cudaErrorInvalidValue;
     if (kind == KIND_S1)
         return m_per_cta == 2 ? launch2<256, false, KIND_S1, 2, PREC>(maps, g, t, p, num_sms, stream)

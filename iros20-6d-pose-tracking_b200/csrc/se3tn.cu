@@ -84,6 +84,7 @@ struct WeightSet {
     uint8_t* dev_bf16 = nullptr;    // blob-sized: conv weights as [32 bf16 hi | 32 bf16 lo] per 32-word K chunk
     uint8_t* dev_stem_bf16 = nullptr;  // 2 x [64][448 words]: stem weights, two tiles per filter row (see aux_kernels.cu)
     CUtensorMap bmap_bf16[14];
+    CUtensorMap bmap_pair[8], bmap_bf16_pair[8];   // Cout=64 layers for the CTA-pair kernels: box = 32 weight rows (half per CTA)
     float mean32[8], std32[8];
     double mean64[8], std64[8];
     int stats_f64 = 0;
@@ -110,6 +111,7 @@ struct se3tn_ctx {
     int conv_version = 2;            // SE3TN_CONV=1 selects the first-generation kernel
     int dual_m = 0;                  // SE3TN_DUAL_M=1: two M tiles per CTA on the BN=256 layers (halves weight fill traffic; measured
                                      // slightly slower than MT=1 once fills stopped being the limiter: the epilogue cannot overlap)
+    int pair = 1;                    // SE3TN_PAIR=0: run the Cout=64 layers as single CTAs instead of cta_group::2 pairs
     int pdl = 1;                     // SE3TN_PDL=0 disables programmatic dependent launch between conv kernels
     int debug_flags = 0;             // SE3TN_DEBUG_SKIP: timing experiments (bit0 no B fills, bit1 no A fills); results invalid
     int base_off_mode = 0;           // SE3TN_BASE_OFF: UMMA descriptor base_offset convention for row-shifted starts
@@ -488,7 +490,10 @@ int run_network(se3tn_ctx* c, int weight_id, int first, int n, int precision,
             const int BN = block_n_of(c, L);
             const bool pool = (L.kind == K_STEM);
             const bool resident = (BN == 64 && L.cout == 64);
+            const bool pair = resident && c->pair && !img_wid && li < 8;
+            if (pair) maps.b = bf16 ? ws.bmap_bf16_pair[li] : ws.bmap_pair[li];
             Umma2Plan t; fill_plan2(c, L, first, n, BN, t);
+            t.pair = pair ? 1 : 0;
             g.n_img = first + n;                       // absolute image indices (TMA maps address image 0)
             p.out = c->buf[L.out]; p.res = (L.res != NONE) ? c->buf[L.res] : nullptr;
             if (pool) {                                // fused MaxPool2d(3,2,1): write the pooled tensor directly
@@ -568,6 +573,7 @@ int se3tn_create(int device, int max_batch, void* workspace, se3tn_ctx** out) {
     if (const char* ov = getenv("SE3TN_DUAL_M")) c->dual_m = atoi(ov) != 0;
     if (const char* ov = getenv("SE3TN_DEBUG_SKIP")) c->debug_flags = atoi(ov);
     if (const char* ov = getenv("SE3TN_PDL")) c->pdl = atoi(ov) != 0;
+    if (const char* ov = getenv("SE3TN_PAIR")) c->pair = atoi(ov) != 0;
 
     void* fn = nullptr; cudaDriverEntryPointQueryResult qres;
     e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -649,6 +655,14 @@ int se3tn_load_weights(se3tn_ctx* c, int weight_id, const float* blob, size_t n_
             rc = make_map2(c, &ws.bmap_bf16[li], dst, layer_ktot(L), layer_rows(L), block_n_of(c, L), what);
         }
         if (rc) return rc;
+        if (L.cout == 64 && li < 8) {
+            snprintf(what, sizeof what, "layer %d pair weights", li);
+            rc = make_map2(c, &ws.bmap_pair[li], ws.dev_tf32 + ws.w_off[li], layer_ktot(L), layer_rows(L), 32, what);
+            if (rc) return rc;
+            if (L.kind == K_STEM) rc = make_map2(c, &ws.bmap_bf16_pair[li], ws.dev_stem_bf16 + static_cast<size_t>(li) * 64 * 448 * sizeof(float), 448, 64, 32, what);
+            else rc = make_map2(c, &ws.bmap_bf16_pair[li], ws.dev_bf16 + ws.w_off[li] * sizeof(float), layer_ktot(L), layer_rows(L), 32, what);
+            if (rc) return rc;
+        }
     }
     CU_TRY(c, cudaDeviceSynchronize());
     ws.fc_off = off;
