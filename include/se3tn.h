@@ -157,6 +157,20 @@ int se3tn_track_batch(se3tn_ctx* ctx, const uint8_t* frame_rgb, const uint16_t* 
                       double trans_normalizer, double rot_normalizer, int precision,
                       float* out_trans, float* out_rot, double* poses_out, void* stream);
 
+/* ---- pose-error metrics (SURVEY.md 8(f) "next" row 1; not on the per-frame path) ----------------------- */
+
+/* Utils.add / Utils.adi (reference Utils.py:72-98) for n (pred, gt) pose pairs against one model point cloud:
+ *   ADD   = mean_i |(R_p x_i + t_p) - (R_g x_i + t_g)|,   ADD-S = mean_i min_j |(R_g x_i + t_g) - (R_p x_j + t_p)|
+ * model_pts double (m,3), pred / gt double (n,16), out_add / out_adi double (n), all device; either output may be NULL.
+ * float64, exhaustive nearest neighbour (the reference uses scipy's cKDTree: same minimum). */
+int se3tn_add_adi(se3tn_ctx* ctx, const double* model_pts, int m, const double* pred, const double* gt, int n,
+                  double* out_add, double* out_adi, void* stream);
+
+/* VOCap (reference eval_ycb.py:45-64): errs double (n) device, any order -> *out_ap on the HOST (0..1; the
+ * reference multiplies by 100 when printing).  Synchronises the stream.  n == 0 or no error below 0.1 m -> 0
+ * (the reference raises IndexError there). */
+int se3tn_vocap(se3tn_ctx* ctx, const double* errs, int n, double* out_ap, void* stream);
+
 /* ---- introspection (tests / profiling) -------------------------------------------------------- */
 
 /* Device pointer + per-image float count of an internal NHWC activation buffer.

@@ -4,6 +4,7 @@ GPU through libse3tn (numpy in / numpy out like the originals):
   compute_bbox               reference Utils.py:302-316
   crop_bbox                  reference Utils.py:320-359
   normalize_rotation_matrix  reference Utils.py:363-367 (9 flops: stays numpy)
+  add / adi                  reference Utils.py:72-98 (ADD, ADD-S); `model` is anything with `.points` or an (m,3) array
 """
 import numpy as np
 import torch
@@ -50,3 +51,22 @@ def normalize_rotation_matrix(R):
     R[:, 1] = R[:, 1] / np.linalg.norm(R[:, 1])
     R[:, 2] = R[:, 2] / np.linalg.norm(R[:, 2])
     return R
+
+
+def _model_points(model):
+    pts = np.asarray(model.points if hasattr(model, 'points') else model, dtype=np.float64)
+    return np.ascontiguousarray(pts.reshape(-1, 3))
+
+
+def add(pred, gt, model):
+    eng = _eng()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(eng.device)
+    out, _ = eng.add_adi(t(_model_points(model)), t(np.asarray(pred).reshape(1, 4, 4)), t(np.asarray(gt).reshape(1, 4, 4)), want_adi=False)
+    return float(out[0].item())
+
+
+def adi(pred, gt, model):
+    eng = _eng()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(eng.device)
+    _, out = eng.add_adi(t(_model_points(model)), t(np.asarray(pred).reshape(1, 4, 4)), t(np.asarray(gt).reshape(1, 4, 4)), want_add=False)
+    return float(out[0].item())

@@ -3,6 +3,7 @@
 #include "../../include/se3tn.h"
 #include "conv_common.h"
 #include "aux_kernels.h"
+#include "metrics.h"
 #include "ptx.cuh"
 
 #include <cstdio>
@@ -111,7 +112,9 @@ struct se3tn_ctx {
     int conv_version = 2;            // SE3TN_CONV=1 selects the first-generation kernel
     int dual_m = 0;                  // SE3TN_DUAL_M=1: two M tiles per CTA on the BN=256 layers (halves weight fill traffic; measured
                                      // slightly slower than MT=1 once fills stopped being the limiter: the epilogue cannot overlap)
-    int pair = 1;                    // SE3TN_PAIR=0: run the Cout=64 layers as single CTAs instead of cta_group::2 pairs
+    int pair = 0;                    // SE3TN_PAIR=1: run the Cout=64 layers as cta_group::2 CTA pairs.  Correct, but measured no faster
+                                     // (64-ch layers equal, stem 18 % slower): the pair MMA's ~1.3x per-SM advantage at N=64 is eaten by
+                                     // the cross-CTA barrier round trips; kept as an experiment
     int pdl = 1;                     // SE3TN_PDL=0 disables programmatic dependent launch between conv kernels
     int debug_flags = 0;             // SE3TN_DEBUG_SKIP: timing experiments (bit0 no B fills, bit1 no A fills); results invalid
     int base_off_mode = 0;           // SE3TN_BASE_OFF: UMMA descriptor base_offset convention for row-shifted starts
@@ -838,6 +841,23 @@ int se3tn_track_batch(se3tn_ctx* c, const uint8_t* frame_rgb, const uint16_t* fr
         }
     }
     return se3tn_pose_update(c, poses_in, out_trans, out_rot, tn, rn, poses_out, n, stream);
+}
+
+int se3tn_add_adi(se3tn_ctx* c, const double* model_pts, int m, const double* pred, const double* gt, int n,
+                  double* out_add, double* out_adi, void* stream) {
+    if (!c) return SE3TN_ERR_INVALID;
+    if (!model_pts || !pred || !gt || m <= 0 || n < 0 || (!out_add && !out_adi)) return fail(c, SE3TN_ERR_INVALID, "se3tn_add_adi: null/invalid argument");
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, launch_add_adi(model_pts, m, pred, gt, n, out_add, out_adi, static_cast<cudaStream_t>(stream)));
+    return SE3TN_OK;
+}
+
+int se3tn_vocap(se3tn_ctx* c, const double* errs, int n, double* out_ap, void* stream) {
+    if (!c) return SE3TN_ERR_INVALID;
+    if (!out_ap || n < 0 || (n > 0 && !errs)) return fail(c, SE3TN_ERR_INVALID, "se3tn_vocap: null/invalid argument");
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, vocap(errs, n, out_ap, static_cast<cudaStream_t>(stream)));
+    return SE3TN_OK;
 }
 
 int se3tn_debug_buffer(se3tn_ctx* c, int id, float** ptr, size_t* floats_per_image) {

@@ -189,6 +189,22 @@ class Engine:
                                               _stream(self.device)), self._ctx)
         return out_poses, out_trans, out_rot
 
+    # ------------------------------------------------------------------ metrics
+    def add_adi(self, model_pts, pred, gt, want_add=True, want_adi=True):
+        """ADD / ADD-S (reference Utils.py:72-98) of n pose pairs: float64 CUDA tensors model (m,3), pred/gt (n,4,4)."""
+        n = pred.shape[0]
+        out_add = torch.empty(n, dtype=torch.float64, device=self.device) if want_add else None
+        out_adi = torch.empty(n, dtype=torch.float64, device=self.device) if want_adi else None
+        _lib.check(self.lib.se3tn_add_adi(self._ctx, _ptr(model_pts), int(model_pts.shape[0]), _ptr(pred), _ptr(gt), n,
+                                          _ptr(out_add), _ptr(out_adi), _stream(self.device)), self._ctx)
+        return out_add, out_adi
+
+    def vocap(self, errs):
+        """VOCap (reference eval_ycb.py:45-64) of a float64 CUDA error vector -> python float in [0,1]."""
+        ap = C.c_double(0.0)
+        _lib.check(self.lib.se3tn_vocap(self._ctx, _ptr(errs), int(errs.numel()), C.byref(ap), _stream(self.device)), self._ctx)
+        return ap.value
+
     # ------------------------------------------------------------------ introspection
     def debug_buffer(self, buf_id, n):
         """A float32 view (n, floats_per_image) of an internal NHWC activation buffer."""

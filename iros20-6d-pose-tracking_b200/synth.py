@@ -140,3 +140,27 @@ def rendered_views(n, poses, seed=0, size=IMAGE_SIZE):
     depthA = (z_mm + rng.integers(-40, 41, size=(n, size, size))).astype(np.uint16)
     depthA[:, ~disk] = 0
     return rgbA, depthA
+
+
+def model_points(m=2620, seed=0):
+    """A synthetic CAD-model point cloud (metres): m points on a bumpy ellipsoid about 10 x 7 x 5 cm, float64.
+    (YCB `points.xyz` files hold 2620 points; reference eval_ycb.py:72-81.)"""
+    rng = np.random.default_rng(seed + 3)
+    d = rng.normal(size=(m, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    r = 1.0 + 0.15 * np.sin(7 * d[:, 0]) * np.cos(5 * d[:, 1])
+    return d * r[:, None] * np.array([0.05, 0.035, 0.025])
+
+
+def pose_pairs(n, seed=0, trans_noise=0.01, rot_noise_deg=5.0):
+    """n (pred, gt) pairs: gt random in the tracking volume, pred = gt perturbed by a small rigid motion."""
+    rng = np.random.default_rng(seed + 4)
+    gt = raw_poses(n, seed=seed + 10)
+    pred = gt.copy()
+    w = rng.normal(size=(n, 3)); w /= np.linalg.norm(w, axis=1, keepdims=True)
+    ang = np.deg2rad(rot_noise_deg) * rng.uniform(0, 1, n)
+    for i in range(n):
+        K = np.array([[0, -w[i, 2], w[i, 1]], [w[i, 2], 0, -w[i, 0]], [-w[i, 1], w[i, 0], 0]])
+        R = np.eye(3) + np.sin(ang[i]) * K + (1 - np.cos(ang[i])) * K @ K
+        pred[i, :3, :3] = R @ gt[i, :3, :3]
+        pred[i, :3, 3] = gt[i, :3, 3] + rng.normal(size=3) * trans_noise
+    return pred, gt

@@ -164,6 +164,38 @@ def main():
     p['nrm_in'] = Rn.copy()
     p['nrm_out'] = np.stack([U.normalize_rotation_matrix(Rn[i].copy()) for i in range(n)])
     np.savez_compressed(os.path.join(args.out, 'golden_pre.npz'), **p)
+
+    # ---------------------------------------------------------------- metrics
+    # Utils.add / Utils.adi take an open3d PointCloud; open3d is not installed, so the reference functions run
+    # on a stand-in with the three members they use (deepcopy, .transform(T): p -> R p + t, .points).
+    # scipy removed cKDTree.query(n_jobs=) (Utils.py:96): `Utils.spatial` is swapped for a wrapper that drops the keyword.
+    import copy
+    from scipy import spatial
+
+    class Cloud:
+        def __init__(self, pts): self.points = np.array(pts, dtype=np.float64)
+        def transform(self, T): self.points = self.points @ T[:3, :3].T + T[:3, 3]; return self
+
+    class CompatTree:                          # scipy's cKDTree minus the removed n_jobs keyword
+        def __init__(self, pts): self._t = spatial.cKDTree(pts)
+        def query(self, x, k=1, n_jobs=None, **kw): return self._t.query(x, k=k, **kw)
+    _spatial = U.spatial
+    U.spatial = types.SimpleNamespace(cKDTree=CompatTree)
+    import eval_ycb as EV                      # reference scorer (VOCap), unmodified
+    mt = {}
+    model = synth.model_points(2620, seed=0)
+    pred, gt = synth.pose_pairs(12, seed=0)
+    pred[0] = gt[0]                            # exact pose: ADD = ADD-S = 0
+    mt['add'] = np.array([U.add(pred[i], gt[i], Cloud(model)) for i in range(12)])
+    mt['adi'] = np.array([U.adi(pred[i], gt[i], Cloud(model)) for i in range(12)])
+    rng = np.random.default_rng(21)
+    curves = {'mixed': rng.uniform(0, 0.2, 500), 'all_below': rng.uniform(0, 0.09, 300),
+              'dups': np.round(rng.uniform(0, 0.15, 400), 2), 'single': np.array([0.03]), 'sorted_add': np.sort(mt['add'])}
+    for k, v in curves.items():
+        mt['curve_' + k] = v
+        mt['vocap_' + k] = np.float64(EV.VOCap(v))
+    U.spatial = _spatial
+    np.savez_compressed(os.path.join(args.out, 'golden_metrics.npz'), **mt)
     for f in sorted(os.listdir(args.out)):
         print(f, os.path.getsize(os.path.join(args.out, f)))
 

@@ -18,6 +18,8 @@ wenbowen123/iros20-6d-pose-tracking @ 18dc5bac):
   process_predict              datasets.py:159-175            (TrackDataset.processPredict)
   forward                      se3_tracknet.py:81-112 + network_modules.py:59-66,86-120
   on_track                     predict.py:217-296 (render_window output taken as an input)
+  add / adi                    Utils.py:72-98     (ADD, ADD-S; scipy cKDTree for the nearest neighbour)
+  vocap                        eval_ycb.py:45-64  (VOCap)
 
 Third-party arithmetic the reference delegates to, and which the oracle calls
 directly because the same libraries are importable here:
@@ -265,3 +267,38 @@ def on_track(sd, prev_pose, current_rgb, current_depth, rgbA, depthA, K, object_
         return out, dict(bb=bb, rgbB=rgbB, depthB=depthB, dataA=sample[0], dataB=sample[1],
                          trans=trans, rot=rot)
     return out
+
+
+# ----------------------------------------------------------------------------
+# metrics  (Utils.py:72-98, eval_ycb.py:45-64)  -- SURVEY.md 8(f) row 1
+# ----------------------------------------------------------------------------
+
+def _transform(points, T):
+    """open3d PointCloud.transform: p -> R p + t (float64)."""
+    return points @ T[:3, :3].T + T[:3, 3]
+
+
+def add(pred, gt, model_pts):
+    """Utils.py:72-82."""
+    return np.linalg.norm(_transform(model_pts, pred) - _transform(model_pts, gt), axis=1).mean()
+
+
+def adi(pred, gt, model_pts):
+    """Utils.py:84-98 (cKDTree.query(k=1); `n_jobs=` was renamed `workers=` in scipy 1.6 and later removed)."""
+    from scipy import spatial
+    nn_index = spatial.cKDTree(_transform(model_pts, pred).copy())
+    nn_dists, _ = nn_index.query(_transform(model_pts, gt).copy(), k=1)
+    return nn_dists.mean()
+
+
+def vocap(rec):
+    """eval_ycb.py:45-64.  Forward running max over precision values that are already increasing."""
+    rec = np.sort(np.asarray(rec, dtype=np.float64).reshape(-1))
+    n = len(rec)
+    prec = np.arange(1, n + 1) / float(n)
+    keep = rec < 0.1
+    rec, prec = rec[keep], prec[keep]
+    mrec = np.concatenate(([0.0], rec, [0.1]))
+    mpre = np.maximum.accumulate(np.concatenate(([0.0], prec, [prec[-1]])))
+    i = np.where(mrec[1:] != mrec[:-1])[0] + 1
+    return np.sum((mrec[i] - mrec[i - 1]) * mpre[i]) * 10

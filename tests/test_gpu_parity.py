@@ -355,3 +355,48 @@ def test_errors_are_reported_not_fatal(pkg, synth, eng):
         eng.forward(A.to(eng.device)[:, :3].contiguous(), B.to(eng.device))
     # the context is still usable
     eng.forward(A.to(eng.device), B.to(eng.device), weight_id=0)
+
+
+# ------------------------------------------------------------------------------ metrics
+def test_add_adi_vocap_vs_reference_fixtures(pkg, synth, golden_dir, eng):
+    g = np.load(os.path.join(golden_dir, 'golden_metrics.npz'))
+    dev = eng.device
+    model = synth.model_points(2620, seed=0)
+    pred, gt = synth.pose_pairs(12, seed=0)
+    pred[0] = gt[0]
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    add, adi = eng.add_adi(t(model), t(pred), t(gt))
+    assert np.allclose(add.cpu().numpy(), g['add'], rtol=1e-12, atol=1e-15)
+    assert np.allclose(adi.cpu().numpy(), g['adi'], rtol=1e-12, atol=1e-15)
+    assert float(add[0]) == 0.0 and float(adi[0]) == 0.0
+    for k in ('mixed', 'all_below', 'dups', 'single', 'sorted_add'):
+        assert abs(eng.vocap(t(g['curve_' + k])) - float(g['vocap_' + k])) < 1e-12, k
+    assert eng.vocap(t(np.array([0.5, 0.7]))) == 0.0          # nothing below 0.1 m (the reference raises here)
+    # drop-in functions
+    U = importlib.import_module('iros20-6d-pose-tracking_b200.Utils')
+    EV = importlib.import_module('iros20-6d-pose-tracking_b200.eval_ycb')
+    U.set_engine(eng)
+    class Cloud:                                              # what callers hand over: anything with .points
+        points = model
+    assert abs(U.add(pred[3], gt[3], Cloud()) - g['add'][3]) < 1e-14 and abs(U.adi(pred[3], gt[3], model) - g['adi'][3]) < 1e-14
+    assert abs(EV.VOCap(g['curve_mixed']) - float(g['vocap_mixed'])) < 1e-12
+
+
+def test_add_adi_full_size_properties(synth, eng):
+    """YCB-Video scale: 14,025 key-frame poses (eval_ycb.py:154) x 2620 model points; properties that hold at any size."""
+    dev = eng.device
+    model = torch.from_numpy(synth.model_points(2620, seed=1)).to(dev)
+    pred, gt = synth.pose_pairs(2048, seed=3)
+    pred, gt = torch.from_numpy(pred).to(dev), torch.from_numpy(gt).to(dev)
+    add, adi = eng.add_adi(model, pred, gt)
+    assert bool((adi <= add + 1e-12).all()) and bool((add >= 0).all())
+    add2, adi2 = eng.add_adi(model, gt, pred)                  # ADD is symmetric in (pred, gt)
+    assert torch.allclose(add, add2, rtol=1e-12, atol=0)
+    T = torch.from_numpy(synth.raw_poses(1, seed=9)[0]).to(dev)   # a common rigid motion leaves both unchanged
+    add3, adi3 = eng.add_adi(model, T @ pred, T @ gt)
+    assert torch.allclose(add, add3, rtol=1e-9, atol=1e-12) and torch.allclose(adi, adi3, rtol=1e-9, atol=1e-12)
+    perm = torch.randperm(2620, generator=torch.Generator().manual_seed(1)).to(dev)
+    add4, adi4 = eng.add_adi(model[perm].contiguous(), pred[:64].contiguous(), gt[:64].contiguous())
+    assert torch.allclose(add[:64], add4, rtol=1e-12, atol=0) and torch.allclose(adi[:64], adi4, rtol=1e-12, atol=0)
+    ap = eng.vocap(adi)
+    assert 0.0 <= ap <= 1.0 and abs(ap - O.vocap(adi.cpu().numpy())) < 1e-12

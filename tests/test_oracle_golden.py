@@ -123,3 +123,19 @@ def test_numpy1_legacy_depth_differs_by_at_most_one_ulp_of_offset(synth):
     # the two differ by the rounding of the offset z*1000 to float32 (+ one result rounding)
     bound = 2 * np.spacing(np.float32(pose[2, 3] * 1000))
     assert np.all(np.abs(a.astype(np.float64) - b) <= bound)
+
+
+def test_metrics_oracle_vs_reference(synth, golden_dir):
+    """ADD / ADD-S / VOCap restatements against values produced by the reference's own Utils.add / Utils.adi /
+    eval_ycb.VOCap (oracle/make_golden.py)."""
+    g = np.load(os.path.join(golden_dir, 'golden_metrics.npz'))
+    model = synth.model_points(2620, seed=0)
+    pred, gt = synth.pose_pairs(12, seed=0)
+    pred[0] = gt[0]
+    add = np.array([O.add(pred[i], gt[i], model) for i in range(12)])
+    adi = np.array([O.adi(pred[i], gt[i], model) for i in range(12)])
+    assert np.allclose(add, g['add'], rtol=1e-13, atol=0) and add[0] == 0.0
+    assert np.allclose(adi, g['adi'], rtol=1e-13, atol=0) and adi[0] == 0.0
+    assert np.all(adi <= add + 1e-15)                      # nearest neighbour can only be closer
+    for k in ('mixed', 'all_below', 'dups', 'single', 'sorted_add'):
+        assert abs(O.vocap(g['curve_' + k]) - float(g['vocap_' + k])) < 1e-13, k
