@@ -1,5 +1,5 @@
 // Pose-error metrics on the GPU -- the first row of SURVEY.md 8(f) ("next"): what the reference's evaluation
-// scripts compute on the CPU with open3d + scipy for every key-frame pose (eval_ycb.py:103-119).
+// scripts compute on the CPU with open3d + scipy for every key-frame pose (eval_ycb.py:96-106).
 //   ADD   (reference Utils.py:72-82):  mean_i || (R_p x_i + t_p) - (R_g x_i + t_g) ||
 //   ADD-S (reference Utils.py:84-98):  mean_i min_j || (R_g x_i + t_g) - (R_p x_j + t_p) ||   (cKDTree, k=1)
 //   VOCap (reference eval_ycb.py:45-64): area under the accuracy-threshold curve below 0.1 m, x10
