@@ -478,6 +478,40 @@ __global__ void split_stem_weights_kernel(const float* __restrict__ src /*[64][7
     }
 }
 
+// STACK layouts for the resident-weight kernels (conv_umma2.cu): 128 rows, rows 0-63 carry the hi parts, rows 64-127 the lo parts.
+// 64-channel 3x3 layers: src [64][9*64] (K-major, tap*64 + c) -> dst [128][9*32 words]; a tap's 128 bytes = 64 bf16 = both chunks.
+__global__ void split_stack_weights_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 64 * 576) return;
+    const int co = i / 576, k = i - co * 576;
+    const float v = src[i];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    *reinterpret_cast<__nv_bfloat16*>(dst + (static_cast<size_t>(co) * 288) * 4 + k * 2) = h;
+    *reinterpret_cast<__nv_bfloat16*>(dst + (static_cast<size_t>(64 + co) * 288) * 4 + k * 2) = l;
+}
+// stem: src [64][7*32] -> dst [128][7*32 words]; pixel slot p of filter row r: rows 0-63 [h0..h3 h0..h3], rows 64-127 [l0..l3 0 0 0 0]
+__global__ void split_stem_stack_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;      // one thread per (co, r, p): 4 channels
+    if (i >= 64 * 7 * 8) return;
+    const int p = i & 7, r = (i >> 3) % 7, co = i / 56;
+    const float* w = src + co * 224 + r * 32 + p * 4;
+    __nv_bfloat16* d0 = reinterpret_cast<__nv_bfloat16*>(dst + (static_cast<size_t>(co) * 224 + r * 32 + p * 4) * 4);
+    __nv_bfloat16* d1 = reinterpret_cast<__nv_bfloat16*>(dst + (static_cast<size_t>(64 + co) * 224 + r * 32 + p * 4) * 4);
+    for (int c = 0; c < 4; ++c) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(w[c]);
+        d0[c] = h; d0[4 + c] = h;
+        d1[c] = __float2bfloat16_rn(w[c] - __bfloat162float(h)); d1[4 + c] = __float2bfloat16_rn(0.f);
+    }
+}
+cudaError_t launch_split_stack_weights(const float* src, void* dst, bool stem, cudaStream_t s) {
+    if (stem) split_stem_stack_kernel<<<(64 * 7 * 8 + 127) / 128, 128, 0, s>>>(src, static_cast<uint8_t*>(dst));
+    else split_stack_weights_kernel<<<(64 * 576 + 255) / 256, 256, 0, s>>>(src, static_cast<uint8_t*>(dst));
+    return cudaGetLastError();
+}
+
 cudaError_t launch_split_weights(const float* src, void* dst, size_t words, cudaStream_t s) {
     if (!words) return cudaSuccess;
     split_weights_kernel<<<1024, 256, 0, s>>>(src, static_cast<uint8_t*>(dst), words);

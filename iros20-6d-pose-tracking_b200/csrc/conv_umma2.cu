@@ -30,10 +30,15 @@
 //   * PAIR (resident-weight kernels: stem, 64-channel layers): clusters of two CTAs run ONE tcgen05.mma.cta_group::2
 //     of M = 256 per step -- each CTA supplies its own pixel tile (A) and HALF of the weight rows (B) from its own
 //     shared memory, the leader CTA issues, commits are multicast to both.  Measured (profiles/
-//     r01_umma_rate3_cta_pair_probe.txt): an N = 64 pair MMA costs 43 cycles for twice the work of a 52-65 cycle
-//     single-CTA MMA, i.e. 74 % instead of ~35 % of the per-SM tensor peak.
+//     r01_umma_rate3_cta_pair_probe.txt): an N = 64 pair MMA costs 43 cycles (74 % of the per-SM tensor peak)
+//     against 52-65 cycles (50-60 %) for a single-CTA one -- but in the network the cross-CTA barrier round trips
+//     eat that, so PAIR is opt-in (SE3TN_PAIR=1).
 //   * N = 64 tiles (stem, 64-channel layers) are capped by the hardware: one 128xNx32B tcgen05.mma costs
-//     ~90 cycles for any N <= 128 (128 for N = 256; scripts/umma_rate.cu), i.e. 35 % of peak at N = 64.
+//     52-65 cycles at N = 64, 68-74 at N = 128, 128 at N = 256 (scripts/umma_rate2.cu) -- a per-instruction floor.
+//   * STACK (resident-weight kernels, bf16 modes): because of that floor, the hi/lo weight halves are stacked along N:
+//     the weight tile of a tap has 128 rows, [w_hi rows 0-63 ; w_lo rows 64-127], so ONE N = 128 MMA forms a_hi*w_hi
+//     (accumulator columns 0-63) and a_hi*w_lo (columns 64-127), a second N = 64 MMA adds a_lo*w_hi into columns
+//     0-63, and the epilogue sums the two column halves: 4 instead of 6 MMAs per chunk-tap (stem: 4 instead of 8).
 //   * MT = 2 ("dual-M", BN = 256 layers): one CTA carries TWO M tiles (two accumulators, all 512
 //     TMEM columns) through the K loop, so every weight tile fetched from L2 feeds 8 MMAs instead
 //     of 4 -- the weight stream, which is >80% of the fill traffic of the deep layers, halves.
@@ -90,7 +95,9 @@ template <> struct KTab<KIND_STEM> {          // 7x7 stride 2 stem: even input r
 template <int BN, bool RESIDENT, int KIND, int MT, int PREC = 0, bool PAIR = false> struct Cfg2 {
     static_assert(!PAIR || (RESIDENT && MT == 1), "CTA pairs are implemented for the resident-weight kernels");
     static constexpr bool POOL = (KIND == KIND_STEM);
-    static constexpr int kBTile = (PAIR ? BN / 2 : BN) * kChunkBytes;    // pair: each CTA holds half of the weight rows
+    // STACK: hi / lo weight rows stacked along N (see the header comment); the stem's bf16 path always needs all three products
+    static constexpr int kStack = (RESIDENT && !PAIR && PREC != PREC_TF32 && (KIND == KIND_STEM || PREC == PREC_BF16X3)) ? 2 : 1;
+    static constexpr int kBTile = (PAIR ? BN / 2 : BN * kStack) * kChunkBytes;    // pair: each CTA holds half of the weight rows
     static constexpr int kAUnit = POOL ? 21 * 1024 : 19 * 1024;     // 3x3: (22 + 128) rows * 128 B = 19,200
     static constexpr int kAStage = MT * kAUnit;
     static constexpr int kAStages = RESIDENT ? (PAIR ? (POOL ? 4 : 6) : ((POOL && PREC != PREC_TF32) ? 3 : 4)) : (MT == 2 ? 2 : 3);
@@ -98,14 +105,14 @@ template <int BN, bool RESIDENT, int KIND, int MT, int PREC = 0, bool PAIR = fal
     static constexpr int kEpiPitch = 36;                                // words per staged row (32 + 4: conflict-free 16 B accesses)
     static constexpr int kEpiWarpBytes = 32 * kEpiPitch * 4 + 128;      // 32 rows + 32-entry pixel-index table
     static constexpr int kEpiBytes = kEpiT ? 8 * kEpiWarpBytes : 0;
-    static constexpr int kWPerTap = (POOL && PREC != PREC_TF32) ? 2 : 1;  // weight tiles per (tap, chunk)
+    static constexpr int kWPerTap = (POOL && PREC != PREC_TF32 && kStack == 1) ? 2 : 1;  // weight tiles per (tap, chunk)
     static constexpr int kPoolBufs = POOL ? (PREC == PREC_TF32 ? 2 : 1) : 0;
     static constexpr int kBStages = RESIDENT ? 0 : (BN == 256 ? (MT == 2 ? 3 : 4) : 6);
     // Partial accumulators per tile (independent MMA chains).  Measured (profiles/r01_umma_rate_microbench.txt):
     // a 128xNx(32 B) tcgen05.mma costs ~90 cycles for N <= 128 whether or not consecutive MMAs share an
     // accumulator, so splitting buys nothing -- kept at 1 (the code path stays for experiments).
     static constexpr int kSplit = 1;
-    static constexpr int kAccCols = MT * BN * kSplit;                   // TMEM columns of one accumulator set
+    static constexpr int kAccCols = MT * BN * kSplit * kStack;          // TMEM columns of one accumulator set
     static constexpr int kNAcc = (2 * kAccCols <= 512) ? 2 : 1;         // accumulator sets (double-buffered when they fit)
     static constexpr int kTmemCols = kNAcc * kAccCols;                  // 256 / 512
 };
@@ -160,7 +167,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
     static_assert(!(POOL && MT != 1), "pool epilogue is single-tile");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int w_tiles = g.num_taps * t.chunks * C::kWPerTap;            // K tiles of the weight matrix
+    const int w_tiles = C::kStack == 2 ? g.num_taps : g.num_taps * t.chunks * C::kWPerTap;   // K tiles of the weight matrix (STACK: one per tap, all chunks)
     uint8_t* sA = smem;                                                 // [kAStages][MT][unit]
     uint8_t* sB = sA + C::kAStages * C::kAStage;                       // resident: [w_tiles][BN*128]; ring: [kBStages][BN*128]
     uint8_t* sP = sB + (RESIDENT ? w_tiles : C::kBStages) * C::kBTile;  // pool staging (POOL only): 2 x 121 x 68 floats
@@ -301,6 +308,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
         // The WHOLE warp walks the loop (warp-uniform control flow lets ptxas keep descriptors and
         // barrier addresses in uniform registers); one elected lane issues the tcgen05 instructions.
         constexpr uint32_t idesc = ptx::umma_idesc(PREC == PREC_TF32 ? 2u /*tf32*/ : 1u /*bf16*/, PAIR ? 2 * kBlockM : kBlockM, BN);
+        constexpr uint32_t idesc_stack = ptx::umma_idesc(1u, kBlockM, BN * C::kStack);      // N = 128: [w_hi ; w_lo] rows
         auto mma_tf32 = [](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc_) { if (PAIR) ptx::umma_tf32_2sm(d, a, b, id, acc_); else ptx::umma_tf32(d, a, b, id, acc_); };
         auto mma_f16 = [](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc_) { if (PAIR) ptx::umma_f16_2sm(d, a, b, id, acc_); else ptx::umma_f16(d, a, b, id, acc_); };
         auto commit = [](uint64_t* bar) { if (PAIR) ptx::umma_commit_2sm(bar, 3); else ptx::umma_commit(bar); };
@@ -333,7 +341,9 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
 #pragma unroll
                     for (int k = 0; k < KT::ntaps(u); ++k) {
                         uint32_t b_lo;
-                        if (RESIDENT) {
+                        if (RESIDENT && C::kStack == 2) {     // one 128-row tile per tap; chunk ch sits 64 bytes (4 x 16 B) further along K
+                            b_lo = (((ptx::smem_u32(sB + KT::wtap(u, k) * C::kBTile) & 0x3FFFFu) >> 4) | (1u << 16)) + ch * 4;
+                        } else if (RESIDENT) {
                             b_lo = ((ptx::smem_u32(sB + (KT::wtap(u, k) * t.chunks + ch) * C::kWPerTap * C::kBTile) & 0x3FFFFu) >> 4) | (1u << 16);
                         } else {
                             ptx::mbar_wait(&b_full[bstage], bphase);
@@ -354,6 +364,18 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
 #pragma unroll
                                     for (int kk = 0; kk < 4; ++kk)
                                         mma_tf32(dst(kk), desc(aj + 2 * kk), desc(b_lo + 2 * kk), idesc, accf(kk));
+                                } else if (C::kStack == 2 && POOL) {
+                                    // stem window = 8 pixels x [hi4|lo4] against rows [w_hi|w_hi ; w_lo|0]: all three products in one N = 128 MMA per K step
+#pragma unroll
+                                    for (int kk = 0; kk < 4; ++kk)
+                                        mma_f16(dj, desc(aj + 2 * kk), desc(b_lo + 2 * kk), idesc_stack, (cnt + kk) ? 1u : 0u);
+                                } else if (C::kStack == 2) {
+                                    // chunk = [32 hi | 32 lo] (A); weight rows [w_hi ; w_lo]: a_hi x both (N = 128), then a_lo x w_hi (N = 64, columns 0-63)
+#pragma unroll
+                                    for (int sl = 0; sl < 2; ++sl) {
+                                        mma_f16(dj, desc(aj + 2 * sl), desc(b_lo + 2 * sl), idesc_stack, (cnt + sl) ? 1u : 0u);
+                                        mma_f16(dj, desc(aj + 4 + 2 * sl), desc(b_lo + 2 * sl), idesc, 1u);
+                                    }
                                 } else if (POOL) {
                                     // stem window = 8 pixels x [hi4|lo4]: pass 0 against [w_hi|w_hi], pass 1 against [w_lo|0]
 #pragma unroll
@@ -376,7 +398,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                             if (!RESIDENT) commit(&b_empty[bstage]);
                         }
                         __syncwarp();
-                        cnt += (PREC == PREC_TF32) ? 4u : (POOL ? 8u : (PREC == PREC_BF16X3 ? 6u : 2u));
+                        cnt += (PREC == PREC_TF32 || C::kStack == 2) ? 4u : (POOL ? 8u : (PREC == PREC_BF16X3 ? 6u : 2u));
                         if (!RESIDENT) { if (++bstage == C::kBStages) { bstage = 0; bphase ^= 1; } }
                     }
                     if (ptx::elect_one()) commit(&a_empty[astage]);
@@ -530,7 +552,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                             for (int jj = 0; jj < 16; ++jj) { v[jj] = __uint_as_float(r0[jj]); v[16 + jj] = __uint_as_float(r1[jj]); }
                         }
 #pragma unroll
-                        for (int sp = 1; sp < C::kSplit; ++sp) {             // sum the partial accumulators
+                        for (int sp = 1; sp < C::kSplit * C::kStack; ++sp) { // sum the partial accumulators / the STACK column halves
                             uint32_t r0[16], r1[16];
                             ptx::tmem_ld16(taddr + sp * BN + c0, r0);
                             ptx::tmem_ld16(taddr + sp * BN + c0 + 16, r1);
@@ -624,7 +646,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                         for (int jj = 0; jj < 16; ++jj) { v[jj] = __uint_as_float(r0[jj]); v[16 + jj] = __uint_as_float(r1[jj]); }
                     }
 #pragma unroll
-                    for (int sp = 1; sp < C::kSplit; ++sp) {
+                    for (int sp = 1; sp < C::kSplit * C::kStack; ++sp) {
                         uint32_t r0[16], r1[16];
                         ptx::tmem_ld16(taddr + sp * BN, r0);
                         ptx::tmem_ld16(taddr + sp * BN + 16, r1);
@@ -708,7 +730,8 @@ cudaError_t launch2(const UmmaMaps& maps, const ConvGeom& g, const Umma2Plan& t,
     using C = Cfg2<BN, RESIDENT, KIND, MT, PREC, PAIR>;
     if (!plan_matches<KIND>(t)) return cudaErrorInvalidValue;
     if (PAIR && (p.img_wid || t.n_tiles != 1 || g.groups != 1)) return cudaErrorInvalidValue;
-    const int w_tiles = g.num_taps * t.chunks * C::kWPerTap;
+    if (C::kStack == 2 && KIND == KIND_S1 && t.chunks != 2) return cudaErrorInvalidValue;    // a stacked tile row is exactly two 32-channel chunks
+    const int w_tiles = C::kStack == 2 ? g.num_taps : g.num_taps * t.chunks * C::kWPerTap;
     const size_t smem = static_cast<size_t>(C::kAStages) * C::kAStage + static_cast<size_t>(RESIDENT ? w_tiles : C::kBStages) * C::kBTile +
                         C::kPoolBufs * ((kPoolStageBytes + 1023) & ~1023) + ((C::kEpiBytes + 1023) & ~1023) + 1024 + 512;
     if (smem > 232448) return cudaErrorInvalidConfiguration;

@@ -85,6 +85,8 @@ struct WeightSet {
     uint8_t* dev_bf16 = nullptr;    // blob-sized: conv weights as [32 bf16 hi | 32 bf16 lo] per 32-word K chunk
     uint8_t* dev_stem_bf16 = nullptr;  // 2 x [64][448 words]: stem weights, two tiles per filter row (see aux_kernels.cu)
     CUtensorMap bmap_bf16[14];
+    uint8_t* dev_stack = nullptr;   // 8 x [128][288 words]: resident-weight layers with hi / lo rows stacked along N (conv_umma2.cu STACK)
+    CUtensorMap bmap_stack[8];
     CUtensorMap bmap_pair[8], bmap_bf16_pair[8];   // Cout=64 layers for the CTA-pair kernels: box = 32 weight rows (half per CTA)
     float mean32[8], std32[8];
     double mean64[8], std64[8];
@@ -124,7 +126,7 @@ struct se3tn_ctx {
     float* d_mean32 = nullptr; float* d_std32 = nullptr; double* d_mean64 = nullptr; double* d_std64 = nullptr;
     int stats_rows = 0; bool stats_dirty = true; int stats_f64 = 0;
     // per-weight-set device tables for multi-set launches, rebuilt when a set is (re)loaded: entry [wid*14 + layer]
-    CUtensorMap* d_bmaps_tf32 = nullptr; CUtensorMap* d_bmaps_bf16 = nullptr;
+    CUtensorMap* d_bmaps_tf32 = nullptr; CUtensorMap* d_bmaps_bf16 = nullptr; CUtensorMap* d_bmaps_x3 = nullptr;
     const float** d_bias = nullptr; const float** d_fc = nullptr;   // d_fc[wid] -> [6][512] weights then [6] biases
     int table_rows = 0; bool tables_dirty = true;
     int launches = 0;
@@ -429,27 +431,32 @@ int sync_tables(se3tn_ctx* c, cudaStream_t s) {
     const int rows = max_id + 1;
     CU_TRY(c, cudaStreamSynchronize(s));
     if (rows > c->table_rows) {
-        cudaFree(c->d_bmaps_tf32); cudaFree(c->d_bmaps_bf16); cudaFree(c->d_bias); cudaFree(c->d_fc);
+        cudaFree(c->d_bmaps_tf32); cudaFree(c->d_bmaps_bf16); cudaFree(c->d_bmaps_x3); cudaFree(c->d_bias); cudaFree(c->d_fc);
+        CU_TRY(c, cudaMalloc(&c->d_bmaps_x3, sizeof(CUtensorMap) * rows * kLayersPerSet));
         CU_TRY(c, cudaMalloc(&c->d_bmaps_tf32, sizeof(CUtensorMap) * rows * kLayersPerSet));
         CU_TRY(c, cudaMalloc(&c->d_bmaps_bf16, sizeof(CUtensorMap) * rows * kLayersPerSet));
         CU_TRY(c, cudaMalloc(&c->d_bias, sizeof(float*) * rows * kLayersPerSet));
         CU_TRY(c, cudaMalloc(&c->d_fc, sizeof(float*) * rows));
         c->table_rows = rows;
     }
-    std::vector<CUtensorMap> m1(rows * kLayersPerSet), m2(rows * kLayersPerSet);
+    std::vector<CUtensorMap> m1(rows * kLayersPerSet), m2(rows * kLayersPerSet), m3(rows * kLayersPerSet);
+    memset(m3.data(), 0, m3.size() * sizeof(CUtensorMap));
     std::vector<const float*> bias(rows * kLayersPerSet, nullptr), fc(rows, nullptr);
     memset(m1.data(), 0, m1.size() * sizeof(CUtensorMap)); memset(m2.data(), 0, m2.size() * sizeof(CUtensorMap));
     for (auto& kv : c->weights) {
         if (!kv.second.dev || kv.first < 0) continue;
         for (int li = 0; li < kLayersPerSet; ++li) {
             m1[kv.first * kLayersPerSet + li] = kv.second.bmap[li];
-            m2[kv.first * kLayersPerSet + li] = kv.second.bmap_bf16[li];
+            // bf16: the stem always runs stacked; bf16x3: every resident-weight layer does
+            m2[kv.first * kLayersPerSet + li] = (li < 2) ? kv.second.bmap_stack[li] : kv.second.bmap_bf16[li];
+            m3[kv.first * kLayersPerSet + li] = (li < 8) ? kv.second.bmap_stack[li] : kv.second.bmap_bf16[li];
             bias[kv.first * kLayersPerSet + li] = kv.second.dev + kv.second.b_off[li];
         }
         fc[kv.first] = kv.second.dev + kv.second.fc_off;
     }
     CU_TRY(c, cudaMemcpy(c->d_bmaps_tf32, m1.data(), m1.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
     CU_TRY(c, cudaMemcpy(c->d_bmaps_bf16, m2.data(), m2.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    CU_TRY(c, cudaMemcpy(c->d_bmaps_x3, m3.data(), m3.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
     CU_TRY(c, cudaMemcpy(c->d_bias, bias.data(), bias.size() * sizeof(float*), cudaMemcpyHostToDevice));
     CU_TRY(c, cudaMemcpy(c->d_fc, fc.data(), fc.size() * sizeof(float*), cudaMemcpyHostToDevice));
     c->tables_dirty = false;
@@ -483,7 +490,7 @@ int run_network(se3tn_ctx* c, int weight_id, int first, int n, int precision,
         p.in = bufp(L.in); p.out = bufp(L.out); p.res = (L.res != NONE) ? bufp(L.res) : nullptr;
         p.w = wbase + ws.w_off[li]; p.bias = ws.dev + ws.b_off[li];
         p.img_wid = img_wid;
-        p.gbmaps = img_wid ? (bf16 ? c->d_bmaps_bf16 : c->d_bmaps_tf32) + li : nullptr;
+        p.gbmaps = img_wid ? (precision == SE3TN_PREC_BF16X3 ? c->d_bmaps_x3 : (bf16 ? c->d_bmaps_bf16 : c->d_bmaps_tf32)) + li : nullptr;
         p.gbias = img_wid ? c->d_bias + li : nullptr;
         if (tensor && c->conv_version == 2) {
             UmmaMaps maps;
@@ -495,6 +502,7 @@ int run_network(se3tn_ctx* c, int weight_id, int first, int n, int precision,
             const bool resident = (BN == 64 && L.cout == 64);
             const bool pair = resident && c->pair && !img_wid && li < 8;
             if (pair) maps.b = bf16 ? ws.bmap_bf16_pair[li] : ws.bmap_pair[li];
+            else if (resident && li < 8 && bf16 && (pool || precision == SE3TN_PREC_BF16X3)) maps.b = ws.bmap_stack[li];   // must mirror Cfg2::kStack
             Umma2Plan t; fill_plan2(c, L, first, n, BN, t);
             t.pair = pair ? 1 : 0;
             g.n_img = first + n;                       // absolute image indices (TMA maps address image 0)
@@ -612,9 +620,9 @@ int se3tn_create(int device, int max_batch, void* workspace, se3tn_ctx** out) {
 void se3tn_destroy(se3tn_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    for (auto& kv : c->weights) { cudaFree(kv.second.dev); cudaFree(kv.second.dev_tf32); cudaFree(kv.second.dev_bf16); cudaFree(kv.second.dev_stem_bf16); }
+    for (auto& kv : c->weights) { cudaFree(kv.second.dev); cudaFree(kv.second.dev_tf32); cudaFree(kv.second.dev_bf16); cudaFree(kv.second.dev_stem_bf16); cudaFree(kv.second.dev_stack); }
     cudaFree(c->d_mean32); cudaFree(c->d_std32); cudaFree(c->d_mean64); cudaFree(c->d_std64);
-    cudaFree(c->d_bmaps_tf32); cudaFree(c->d_bmaps_bf16); cudaFree(c->d_bias); cudaFree(c->d_fc);
+    cudaFree(c->d_bmaps_tf32); cudaFree(c->d_bmaps_bf16); cudaFree(c->d_bmaps_x3); cudaFree(c->d_bias); cudaFree(c->d_fc);
     for (int i = 0; i < SE3TN_PROFILE_SLOTS; ++i) { if (c->ev0[i]) cudaEventDestroy(c->ev0[i]); if (c->ev1[i]) cudaEventDestroy(c->ev1[i]); }
     if (c->own_workspace) cudaFree(c->workspace);
     delete c;
@@ -633,6 +641,7 @@ int se3tn_load_weights(se3tn_ctx* c, int weight_id, const float* blob, size_t n_
         CU_TRY(c, cudaMalloc(&ws.dev_tf32, expect * sizeof(float)));
         CU_TRY(c, cudaMalloc(&ws.dev_bf16, expect * sizeof(float)));
         CU_TRY(c, cudaMalloc(&ws.dev_stem_bf16, 2 * 64 * 448 * sizeof(float)));
+        CU_TRY(c, cudaMalloc(&ws.dev_stack, 8 * 128 * 288 * sizeof(float)));
     }
     CU_TRY(c, cudaDeviceSynchronize());
     CU_TRY(c, cudaMemcpy(ws.dev, blob, expect * sizeof(float), cudaMemcpyHostToDevice));
@@ -659,6 +668,11 @@ int se3tn_load_weights(se3tn_ctx* c, int weight_id, const float* blob, size_t n_
         }
         if (rc) return rc;
         if (L.cout == 64 && li < 8) {
+            snprintf(what, sizeof what, "layer %d stacked weights", li);
+            uint8_t* sdst = ws.dev_stack + static_cast<size_t>(li) * 128 * 288 * sizeof(float);
+            CU_TRY(c, launch_split_stack_weights(ws.dev + ws.w_off[li], sdst, L.kind == K_STEM, 0));
+            rc = make_map2(c, &ws.bmap_stack[li], sdst, L.kind == K_STEM ? 224 : 288, 128, 128, what);
+            if (rc) return rc;
             snprintf(what, sizeof what, "layer %d pair weights", li);
             rc = make_map2(c, &ws.bmap_pair[li], ws.dev_tf32 + ws.w_off[li], layer_ktot(L), layer_rows(L), 32, what);
             if (rc) return rc;
