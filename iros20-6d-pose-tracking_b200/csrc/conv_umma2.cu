@@ -434,6 +434,11 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                 const WorkUnit wu = decode_work(tile_of(tile), m_units, t);
                 ptx::mbar_wait(&tmem_full[acc], acc_phase);
                 ptx::tc_fence_after();
+                if (t.debug & 4) {                  // timing experiment: free the accumulator at once, no epilogue work
+                    ptx::tc_fence_before(); __syncwarp();
+                    if (lane == 0) { if (leader) ptx::mbar_arrive(&tmem_empty[acc]); else ptx::mbar_arrive_cluster(&tmem_empty[acc], 0); }
+                    continue;
+                }
                 if constexpr (C::kEpiT) {
                     // ---------------- transposed epilogue: lane = (pixel-in-group-of-4 sub, 16-byte column group grp) ----------------
                     float (*stg)[C::kEpiPitch] = reinterpret_cast<float (*)[C::kEpiPitch]>(sT + ew * C::kEpiWarpBytes);
@@ -533,7 +538,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                     if (m >= t.m_tiles) break;                               // odd tail (warp-uniform)
                     const TileCoord2 tc = decode2(m, t);
                     const int n = tc.n0 + pn, y = tc.ty * t.bh + py, x = tc.tx * t.bw + px;
-                    const bool valid = (pn < t.bn) && (n < g.n_img) && (y < g.Ho) && (x < g.Wo) && tile_valid(tile);
+                    const bool valid = (pn < t.bn) && (n < g.n_img) && (y < g.Ho) && (x < g.Wo) && tile_valid(tile) && !(t.debug & 8);   // bit3: TMEM drain only, no global traffic
                     const size_t pix = (static_cast<size_t>(n) * g.Ho + y) * g.Wo + x;
                     const int ch0 = wu.grp * g.cout + wu.n_tile * BN + half * kCols;
                     float* outp = p.out + pix * g.out_cstride + g.out_coff + ch0;
@@ -634,6 +639,11 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
 
                 ptx::mbar_wait(&tmem_full[acc], acc_phase);
                 ptx::tc_fence_after();
+                if (t.debug & 4) {                  // timing experiment: free the accumulator at once, no epilogue work
+                    ptx::tc_fence_before(); __syncwarp();
+                    if (lane == 0) { if (leader) ptx::mbar_arrive(&tmem_empty[acc]); else ptx::mbar_arrive_cluster(&tmem_empty[acc], 0); }
+                    continue;
+                }
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * C::kAccCols + half * kCols;
                 {
                     float v[32];
@@ -673,7 +683,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                     const int pp = v >> 4, c4 = (v & 15) * 4;
                     const int ppy = pp / 5, ppx = pp - ppy * 5;
                     const int oy = tc.ty * 5 + ppy, ox = tc.tx * 5 + ppx;     // pooled output coordinates
-                    if (oy >= g.Ho || ox >= g.Wo) continue;
+                    if (oy >= g.Ho || ox >= g.Wo || (t.debug & 8)) continue;
                     float4 m = make_float4(-3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f);
 #pragma unroll
                     for (int dy = 0; dy < 3; ++dy)
