@@ -506,6 +506,20 @@ __global__ void split_stem_stack_kernel(const float* __restrict__ src, uint8_t* 
         d1[c] = __float2bfloat16_rn(w[c] - __bfloat162float(h)); d1[4 + c] = __float2bfloat16_rn(0.f);
     }
 }
+// Resident 64-channel layers (conv_umma2.cu, 16x256b epilogue): accumulator column 8j + 2m + e of every 32-column block
+// must carry output channel 8m + 2j + e, so the weight ROWS are stored in that order.
+__global__ void permute_rows64_kernel(const float* __restrict__ src, float* __restrict__ dst, int ktot)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 64 * ktot) return;
+    const int col = i / ktot, k = i - col * ktot;
+    const int ch = (col & 32) | (((col >> 1) & 3) << 3) | (((col >> 3) & 3) << 1) | (col & 1);
+    dst[i] = src[ch * ktot + k];
+}
+cudaError_t launch_permute_rows64(const float* src, float* dst, int ktot, cudaStream_t s) {
+    permute_rows64_kernel<<<(64 * ktot + 255) / 256, 256, 0, s>>>(src, dst, ktot);
+    return cudaGetLastError();
+}
 cudaError_t launch_split_stack_weights(const float* src, void* dst, bool stem, cudaStream_t s) {
     if (stem) split_stem_stack_kernel<<<(64 * 7 * 8 + 127) / 128, 128, 0, s>>>(src, static_cast<uint8_t*>(dst));
     else split_stack_weights_kernel<<<(64 * 576 + 255) / 256, 256, 0, s>>>(src, static_cast<uint8_t*>(dst));

@@ -42,6 +42,7 @@ cudaError_t launch_head(const float* x, const float* fcw, const float* fcb, floa
                         int n_img, int npix, int split_bf16, const int* img_wid, const float* const* fc_table, cudaStream_t s);
 cudaError_t launch_nhwc_to_nchw(const float* in, float* out, int n_img, int HW, int C, int split_bf16, cudaStream_t s);
 cudaError_t launch_split_weights(const float* src, void* dst, size_t words, cudaStream_t s);
+cudaError_t launch_permute_rows64(const float* src /*[64][ktot]*/, float* dst, int ktot, cudaStream_t s);
 cudaError_t launch_split_stack_weights(const float* src, void* dst /*[128][9*32 | 7*32 words]*/, bool stem, cudaStream_t s);
 cudaError_t launch_split_stem_weights(const float* src /*[64][224]*/, void* dst /*[64][448 words]*/, cudaStream_t s);
 cudaError_t launch_pose_update(const double* poses_in, const float* trans, const float* rot, float tn, float rn,

@@ -59,6 +59,9 @@ struct ConvPtrs {
     const int* img_wid;            // nullable: single-set launch (maps.b / bias above)
     const CUtensorMap* gbmaps;     // device array of weight tensor maps
     const float* const* gbias;     // device array of bias pointers
+    // stream-K (ring-weight kernels): one 128 x 256 fp32 partial-accumulator slot and one flag per CTA; null = off
+    float* sk_part;
+    int* sk_flags;
 };
 
 // ---- tcgen05 path only ------------------------------------------------------------------
@@ -98,6 +101,7 @@ struct Umma2Plan {
     int base_off_mode;                   // 0: descriptor base_offset = 0; 1: (addr >> 7) & 7
     int pair;                            // resident-weight kernels: run as CTA pairs (cta_group::2); maps.b must then box BN/2 rows
     int pdl;                             // launch with programmatic stream serialization (overlap prologue with the previous conv's tail)
+    int sk_seq;                          // stream-K: value a partial's flag takes in THIS launch (unique per launch, never 0)
     int debug;                           // timing experiments only (results are garbage): bit0 skip B fills, bit1 skip A fills
 };
 

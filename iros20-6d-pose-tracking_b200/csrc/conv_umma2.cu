@@ -43,6 +43,11 @@
 //     TMEM columns) through the K loop, so every weight tile fetched from L2 feeds 8 MMAs instead
 //     of 4 -- the weight stream, which is >80% of the fill traffic of the deep layers, halves.
 //     At batch 64 each deep layer is exactly 128 work units: one wave on 148 SMs.
+//   * Stream-K (ring-weight kernels): at batch 64 every BN = 256 layer has 256 work units for 148 CTAs -- two waves, the second
+//     73 % full.  When there are more units than CTAs, the (unit, 32-channel chunk) steps are dealt out evenly instead: a
+//     CTA's contiguous range starts with the TAIL chunks of one unit (accumulate, dump the fp32 partial to its slot in
+//     p.sk_part, raise its flag), runs whole units, and ends with the HEAD chunks of another, whose epilogue first adds
+//     the partial its neighbour dumped long before.  Makespan 1.75 instead of 2 units.
 //   * PREC selects the arithmetic without touching the byte layout.  Every 128-byte K chunk of an
 //     activation pixel / weight row is either 32 fp32 words holding TF32 values (PREC_TF32) or
 //     [32 x bf16 hi | 32 x bf16 lo] of the same 32 channels (x = hi + lo to 16 mantissa bits):
@@ -201,6 +206,22 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
         return tl < total_tiles ? tl : total_tiles - 1;
     };
     auto tile_valid = [&](int work) -> bool { return !PAIR || 2 * work + static_cast<int>(crank) < total_tiles; };
+    // Work items: (unit, chunk range).  Without stream-K every item is a whole unit of [w_begin, w_end).
+    const int chunks = t.chunks;
+    const bool streamk = !RESIDENT && MT == 1 && p.sk_part != nullptr && total_tiles > static_cast<int>(gridDim.x);
+    int s_begin = w_begin * chunks, s_end = w_end * chunks;
+    if (streamk) {
+        const long long S = static_cast<long long>(total_tiles) * chunks;
+        s_begin = static_cast<int>(blockIdx.x * S / gridDim.x);
+        s_end = static_cast<int>((blockIdx.x + 1) * S / gridDim.x);
+    }
+    struct Item { int tile, c0, c1, next; };
+    auto item_at = [&](int sidx) -> Item {
+        Item im; im.tile = sidx / chunks;
+        const int base = im.tile * chunks;
+        im.c0 = sidx - base; im.c1 = min(chunks, s_end - base); im.next = base + im.c1;
+        return im;
+    };
     auto wid_of = [&](int work) -> int {            // weight-set id of a work unit (-1: single-set launch)
         if (!p.img_wid) return -1;
         const WorkUnit wu = decode_work(tile_of(work), m_units, t);
@@ -229,7 +250,9 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
         if (lane == 0) {
             ptx::grid_dep_wait();                   // activations come from the previous kernel
             int stage = 0; uint32_t phase = 0;
-            for (int tile = w_begin; tile < w_end; ++tile) {
+            for (int sidx = s_begin; sidx < s_end;) {
+                const Item im = item_at(sidx); sidx = im.next;
+                const int tile = im.tile;
                 const WorkUnit wu = decode_work(tile_of(tile), m_units, t);
                 TileCoord2 tc[MT];
 #pragma unroll
@@ -238,7 +261,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                     tc[j] = decode2(m, t);
                 }
                 const int cbase = g.in_coff + wu.grp * g.cin;
-                for (int ch = 0; ch < t.chunks; ++ch) {
+                for (int ch = im.c0; ch < im.c1; ++ch) {
                     for (int u = 0; u < t.units_per_chunk; ++u) {
                         const Unit un = t.units[u];
                         ptx::mbar_wait(&a_empty[stage], phase ^ 1);
@@ -284,12 +307,14 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                 }
             } else {
                 int stage = 0; uint32_t phase = 0;
-                for (int tile = w_begin; tile < w_end; ++tile) {
+                for (int sidx = s_begin; sidx < s_end;) {
+                    const Item im = item_at(sidx); sidx = im.next;
+                    const int tile = im.tile;
                     const WorkUnit wu = decode_work(tile_of(tile), m_units, t);
                     const int wrow = wu.grp * g.cout + wu.n_tile * BN;
                     const int wid = wid_of(tile);
                     const CUtensorMap* bm = wid < 0 ? &maps.b : p.gbmaps + wid * kLayersPerSet;
-                    for (int ch = 0; ch < t.chunks; ++ch)
+                    for (int ch = im.c0; ch < im.c1; ++ch)
                         for (int u = 0; u < t.units_per_chunk; ++u) {
                             const Unit un = t.units[u];
                             for (int k = 0; k < un.ntaps; ++k) {
@@ -318,7 +343,9 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
         int bstage = 0; uint32_t bphase = 0;
         int w_cur = -2; uint32_t w_gen = 0;        // RESIDENT: weight-set currently in shared memory
         int it = 0;
-        for (int tile = w_begin; tile < w_end; ++tile, ++it) {
+        for (int sidx = s_begin; sidx < s_end; ++it) {
+            const Item im = item_at(sidx); sidx = im.next;
+            const int tile = im.tile;
             if (RESIDENT) {
                 const int wid = wid_of(tile);
                 if (wid != w_cur) { ptx::mbar_wait(&b_full[0], w_gen & 1); ptx::tc_fence_after(); w_cur = wid; ++w_gen; }
@@ -328,8 +355,8 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
             ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
             ptx::tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * C::kAccCols;
-            uint32_t cnt = 0;                       // MMAs issued into this tile so far (per M tile)
-            for (int ch = 0; ch < t.chunks; ++ch) {
+            uint32_t cnt = 0;                       // MMAs issued into this item so far (per M tile)
+            for (int ch = im.c0; ch < im.c1; ++ch) {
 #pragma unroll
                 for (int u = 0; u < KT::NU; ++u) {
                     ptx::mbar_wait(&a_full[astage], aphase);
@@ -428,10 +455,36 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
             const int rem = row - pn * box;
             const int py = rem / t.bw;
             const int px = rem - py * t.bw;
-            for (int tile = w_begin; tile < w_end; ++tile, ++it) {
+            for (int sidx = s_begin; sidx < s_end; ++it) {
+                const Item im = item_at(sidx); sidx = im.next;
+                const int tile = im.tile;
                 const int acc = it % C::kNAcc;
                 const uint32_t acc_phase = (it / C::kNAcc) & 1;
                 const WorkUnit wu = decode_work(tile_of(tile), m_units, t);
+                // stream-K roles of a cut unit: its TAIL chunks are the first item of a CTA's range (dump the partial into this
+                // CTA's slot), its HEAD chunks the last item of the previous CTA's range (add that partial, then the normal epilogue)
+                const bool sk_dump = im.c0 > 0, sk_fix = im.c1 < chunks;
+                // resident layers: this lane's four pixels and their residual pieces are known before the accumulator is --
+                // issue the residual loads now so their latency hides behind the wait for the MMAs
+                size_t rpix[4]; bool rvalid[4]; uint4 rres[4][2];
+                if constexpr (!C::kEpiT) {
+                    const TileCoord2 tc = decode2(wu.mp, t);
+                    const int chr = wu.grp * g.cout + wu.n_tile * BN + half * kCols;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {                           // row q*32 + 8i + lane/4
+                        const int rw = q * 32 + 8 * i + (lane >> 2);
+                        const int pn_ = rw / box, rem_ = rw - pn_ * box, py_ = rem_ / t.bw, px_ = rem_ - py_ * t.bw;
+                        const int n = tc.n0 + pn_, y = tc.ty * t.bh + py_, x = tc.tx * t.bw + px_;
+                        rvalid[i] = (pn_ < t.bn) && (n < g.n_img) && (y < g.Ho) && (x < g.Wo) && tile_valid(tile) && !(t.debug & 8);   // bit3: TMEM drain only
+                        rpix[i] = (static_cast<size_t>(n) * g.Ho + y) * g.Wo + x;
+                        rres[i][0] = make_uint4(0u, 0u, 0u, 0u); rres[i][1] = make_uint4(0u, 0u, 0u, 0u);
+                        if (p.res && rvalid[i]) {
+                            const uint4* rp = reinterpret_cast<const uint4*>(p.res + rpix[i] * g.res_cstride + g.res_coff + chr);
+                            if (PREC == PREC_TF32) { rres[i][0] = __ldg(rp + 2 * (lane & 3)); rres[i][1] = __ldg(rp + 2 * (lane & 3) + 1); }   // 8 fp32 words
+                            else                   { rres[i][0] = __ldg(rp + (lane & 3));     rres[i][1] = __ldg(rp + 4 + (lane & 3)); }       // hi piece, lo piece
+                        }
+                    }
+                }
                 ptx::mbar_wait(&tmem_full[acc], acc_phase);
                 ptx::tc_fence_after();
                 if (t.debug & 4) {                  // timing experiment: free the accumulator at once, no epilogue work
@@ -458,12 +511,55 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                         const int ch0 = wu.grp * g.cout + wu.n_tile * BN + half * kCols;
                         const float* bias_base = p.img_wid ? p.gbias[p.img_wid[tc.n0] * kLayersPerSet] : p.bias;
                         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * C::kAccCols + j * (BN * C::kSplit) + half * kCols;
+                        // partial slot layout: [32-column block][16-byte piece][row] -> every load/store instruction covers 512 contiguous bytes
+                        if (sk_dump) {
+                            uint4* slot = reinterpret_cast<uint4*>(p.sk_part + static_cast<size_t>(blockIdx.x) * (kBlockM * BN));
+#pragma unroll 1
+                            for (int c0 = 0; c0 < kCols; c0 += 32) {
+                                uint32_t r0[16], r1[16];
+                                ptx::tmem_ld16(taddr + c0, r0);
+                                ptx::tmem_ld16(taddr + c0 + 16, r1);
+                                ptx::tmem_ld_wait();
+                                uint4* sb = slot + static_cast<size_t>((half * kCols + c0) >> 5) * 8 * kBlockM + row;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    sb[k * kBlockM] = make_uint4(r0[4 * k], r0[4 * k + 1], r0[4 * k + 2], r0[4 * k + 3]);
+                                    sb[(4 + k) * kBlockM] = make_uint4(r1[4 * k], r1[4 * k + 1], r1[4 * k + 2], r1[4 * k + 3]);
+                                }
+                            }
+                            __threadfence();
+                            continue;                                        // flag raised below, once all 8 warps have stored
+                        }
+                        const uint4* fix = nullptr;
+                        if (sk_fix) {
+                            if (lane == 0) while (ptx::ld_acquire_gpu(p.sk_flags + blockIdx.x + 1) != t.sk_seq) { }
+                            __syncwarp();
+                            fix = reinterpret_cast<const uint4*>(p.sk_part + static_cast<size_t>(blockIdx.x + 1) * (kBlockM * BN));
+                        }
 #pragma unroll 1
                         for (int c0 = 0; c0 < kCols; c0 += 32) {
                             {
                                 uint32_t r0[16], r1[16];
                                 ptx::tmem_ld16(taddr + c0, r0);
                                 ptx::tmem_ld16(taddr + c0 + 16, r1);
+                                if (fix) {
+                                    const uint4* fb = fix + static_cast<size_t>((half * kCols + c0) >> 5) * 8 * kBlockM + row;
+                                    uint4 f[8];
+#pragma unroll
+                                    for (int k = 0; k < 8; ++k) f[k] = __ldcg(fb + k * kBlockM);
+                                    ptx::tmem_ld_wait();
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        r0[4 * k]     = __float_as_uint(__uint_as_float(r0[4 * k])     + __uint_as_float(f[k].x));
+                                        r0[4 * k + 1] = __float_as_uint(__uint_as_float(r0[4 * k + 1]) + __uint_as_float(f[k].y));
+                                        r0[4 * k + 2] = __float_as_uint(__uint_as_float(r0[4 * k + 2]) + __uint_as_float(f[k].z));
+                                        r0[4 * k + 3] = __float_as_uint(__uint_as_float(r0[4 * k + 3]) + __uint_as_float(f[k].w));
+                                        r1[4 * k]     = __float_as_uint(__uint_as_float(r1[4 * k])     + __uint_as_float(f[4 + k].x));
+                                        r1[4 * k + 1] = __float_as_uint(__uint_as_float(r1[4 * k + 1]) + __uint_as_float(f[4 + k].y));
+                                        r1[4 * k + 2] = __float_as_uint(__uint_as_float(r1[4 * k + 2]) + __uint_as_float(f[4 + k].z));
+                                        r1[4 * k + 3] = __float_as_uint(__uint_as_float(r1[4 * k + 3]) + __uint_as_float(f[4 + k].w));
+                                    }
+                                }
                                 ptx::tmem_ld_wait();
                                 __syncwarp();                                // previous block's readers are done with stg
 #pragma unroll
@@ -532,97 +628,92 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                         }
                     }
                 } else {
-#pragma unroll 1
-                for (int j = 0; j < MT; ++j) {
-                    const int m = wu.mp * MT + j;
-                    if (m >= t.m_tiles) break;                               // odd tail (warp-uniform)
-                    const TileCoord2 tc = decode2(m, t);
-                    const int n = tc.n0 + pn, y = tc.ty * t.bh + py, x = tc.tx * t.bw + px;
-                    const bool valid = (pn < t.bn) && (n < g.n_img) && (y < g.Ho) && (x < g.Wo) && tile_valid(tile) && !(t.debug & 8);   // bit3: TMEM drain only, no global traffic
-                    const size_t pix = (static_cast<size_t>(n) * g.Ho + y) * g.Wo + x;
+                    // ---------------- resident 64-channel layers: 16x256b TMEM loads ----------------
+                    // Lane (R = lane/4, m = lane%4) receives, for each of its four rows q*32 + 8i + R, the accumulator columns
+                    // 8j + 2m + e (j < 4, e < 2) of this warp's 32-column block.  The weight rows of these layers are stored
+                    // permuted (column 8j + 2m + e carries output channel 8m + 2j + e, se3tn.cu), so the lane owns the 8
+                    // CONSECUTIVE channels 8m .. 8m+7 of each pixel: one 16-byte hi and one 16-byte lo piece (or 32 bytes of fp32)
+                    // per row, four lanes complete 64 (128) contiguous bytes, and a load/store instruction touches 8 lines
+                    // instead of the 32 of a row-per-lane epilogue.
+                    static_assert(MT == 1 && C::kSplit == 1, "resident epilogue: one tile, one accumulator");
+                    const int mm = lane & 3;
+                    const TileCoord2 tc = decode2(wu.mp, t);
                     const int ch0 = wu.grp * g.cout + wu.n_tile * BN + half * kCols;
-                    float* outp = p.out + pix * g.out_cstride + g.out_coff + ch0;
-                    const float* resp = p.res ? p.res + pix * g.res_cstride + g.res_coff + ch0 : nullptr;
-                    const float* biasp = (p.img_wid ? p.gbias[p.img_wid[tc.n0] * kLayersPerSet] : p.bias) + ch0;
-                    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * C::kAccCols + j * (BN * C::kSplit) + half * kCols;
-#pragma unroll 1
-                    for (int c0 = 0; c0 < kCols; c0 += 32) {
-                        float v[32];
-                        {
-                            uint32_t r0[16], r1[16];
-                            ptx::tmem_ld16(taddr + c0, r0);
-                            ptx::tmem_ld16(taddr + c0 + 16, r1);
-                            ptx::tmem_ld_wait();
+                    const float* bias_base = (p.img_wid ? p.gbias[p.img_wid[tc.n0] * kLayersPerSet] : p.bias) + ch0 + mm * 8;
+                    const float4 bA = __ldg(reinterpret_cast<const float4*>(bias_base)), bB = __ldg(reinterpret_cast<const float4*>(bias_base + 4));
+                    const float bias8[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
+                    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * C::kAccCols + half * kCols;
+                    uint32_t ra[16], rb[16];
+                    ptx::tmem_ld_16x256b_x4(taddr, ra);
+                    ptx::tmem_ld_16x256b_x4(taddr + (16u << 16), rb);
+                    if (C::kStack == 2) {
+                        uint32_t rc[16], rd[16];
+                        ptx::tmem_ld_16x256b_x4(taddr + BN, rc);
+                        ptx::tmem_ld_16x256b_x4(taddr + (16u << 16) + BN, rd);
+                        ptx::tmem_ld_wait();
 #pragma unroll
-                            for (int jj = 0; jj < 16; ++jj) { v[jj] = __uint_as_float(r0[jj]); v[16 + jj] = __uint_as_float(r1[jj]); }
+                        for (int i = 0; i < 16; ++i) {
+                            ra[i] = __float_as_uint(__uint_as_float(ra[i]) + __uint_as_float(rc[i]));
+                            rb[i] = __float_as_uint(__uint_as_float(rb[i]) + __uint_as_float(rd[i]));
                         }
+                    } else {
+                        ptx::tmem_ld_wait();
+                    }
 #pragma unroll
-                        for (int sp = 1; sp < C::kSplit * C::kStack; ++sp) { // sum the partial accumulators / the STACK column halves
-                            uint32_t r0[16], r1[16];
-                            ptx::tmem_ld16(taddr + sp * BN + c0, r0);
-                            ptx::tmem_ld16(taddr + sp * BN + c0 + 16, r1);
-                            ptx::tmem_ld_wait();
+                    for (int i = 0; i < 4; ++i) {                           // row q*32 + 8i + Rr; register 4j + 2(i&1) + e of ra (i < 2) / rb
+                        if (!rvalid[i]) continue;
+                        const size_t pix = rpix[i];
+                        float v[8];
 #pragma unroll
-                            for (int jj = 0; jj < 16; ++jj) { v[jj] += __uint_as_float(r0[jj]); v[16 + jj] += __uint_as_float(r1[jj]); }
-                        }
-                        if (valid) {
+                        for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
-                            for (int jj = 0; jj < 32; jj += 4) {
-                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(biasp + c0 + jj));
-                                v[jj] += b4.x; v[jj + 1] += b4.y; v[jj + 2] += b4.z; v[jj + 3] += b4.w;
-                            }
-                            if (resp) {
-                                if (PREC == PREC_TF32) {
-#pragma unroll
-                                    for (int jj = 0; jj < 32; jj += 4) {
-                                        const float4 r4 = __ldg(reinterpret_cast<const float4*>(resp + c0 + jj));
-                                        v[jj] += r4.x; v[jj + 1] += r4.y; v[jj + 2] += r4.z; v[jj + 3] += r4.w;
-                                    }
-                                } else {
-                                    // residual chunk = [32 bf16 hi | 32 bf16 lo]
-                                    const uint4* rc = reinterpret_cast<const uint4*>(resp + c0);
-#pragma unroll
-                                    for (int qd = 0; qd < 4; ++qd) {
-                                        const uint4 h4 = __ldg(rc + qd), l4 = __ldg(rc + 4 + qd);
-                                        const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
-#pragma unroll
-                                        for (int e = 0; e < 4; ++e) {
-                                            const float2 hf = unpack2(hw[e]), lf = unpack2(lw[e]);
-                                            v[qd * 8 + e * 2] += hf.x + lf.x; v[qd * 8 + e * 2 + 1] += hf.y + lf.y;
-                                        }
-                                    }
-                                }
-                            }
-#pragma unroll
-                            for (int jj = 0; jj < 32; ++jj) {
-                                if (g.act == ACT_RELU) v[jj] = fmaxf(v[jj], 0.f);
-                                else if (g.act == ACT_SELU) v[jj] = selu_fast(v[jj]);
-                            }
+                            for (int e = 0; e < 2; ++e)
+                                v[2 * jj + e] = __uint_as_float((i < 2 ? ra : rb)[4 * jj + 2 * (i & 1) + e]) + bias8[2 * jj + e];
+                        if (p.res) {
                             if (PREC == PREC_TF32) {
+                                const uint4 r0 = rres[i][0], r1 = rres[i][1];
+                                v[0] += __uint_as_float(r0.x); v[1] += __uint_as_float(r0.y); v[2] += __uint_as_float(r0.z); v[3] += __uint_as_float(r0.w);
+                                v[4] += __uint_as_float(r1.x); v[5] += __uint_as_float(r1.y); v[6] += __uint_as_float(r1.z); v[7] += __uint_as_float(r1.w);
+                            } else {                                         // chunk = [32 bf16 hi | 32 bf16 lo]
+                                const uint4 h4 = rres[i][0], l4 = rres[i][1];
+                                const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
-                                for (int jj = 0; jj < 32; jj += 4) {
-                                    float4 o = make_float4(v[jj], v[jj + 1], v[jj + 2], v[jj + 3]);
-                                    if (g.round_tf32) o = make_float4(ptx::to_tf32(o.x), ptx::to_tf32(o.y), ptx::to_tf32(o.z), ptx::to_tf32(o.w));
-                                    *reinterpret_cast<float4*>(outp + c0 + jj) = o;
-                                }
-                            } else {
-                                uint32_t hw[16], lw[16];
-#pragma unroll
-                                for (int e = 0; e < 16; ++e) split2(v[2 * e], v[2 * e + 1], hw[e], lw[e]);
-                                uint4* oc = reinterpret_cast<uint4*>(outp + c0);
-#pragma unroll
-                                for (int qd = 0; qd < 4; ++qd) {
-                                    oc[qd] = make_uint4(hw[qd * 4], hw[qd * 4 + 1], hw[qd * 4 + 2], hw[qd * 4 + 3]);
-                                    oc[4 + qd] = make_uint4(lw[qd * 4], lw[qd * 4 + 1], lw[qd * 4 + 2], lw[qd * 4 + 3]);
+                                for (int e = 0; e < 4; ++e) {
+                                    const float2 hf = unpack2(hw[e]), lf = unpack2(lw[e]);
+                                    v[2 * e] += hf.x + lf.x; v[2 * e + 1] += hf.y + lf.y;
                                 }
                             }
+                        }
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            if (g.act == ACT_RELU) v[e] = fmaxf(v[e], 0.f);
+                            else if (g.act == ACT_SELU) v[e] = selu_fast(v[e]);
+                        }
+                        float* outp = p.out + pix * g.out_cstride + g.out_coff + ch0;
+                        if (PREC == PREC_TF32) {
+                            float4 o0 = make_float4(v[0], v[1], v[2], v[3]), o1 = make_float4(v[4], v[5], v[6], v[7]);
+                            if (g.round_tf32) {
+                                o0 = make_float4(ptx::to_tf32(o0.x), ptx::to_tf32(o0.y), ptx::to_tf32(o0.z), ptx::to_tf32(o0.w));
+                                o1 = make_float4(ptx::to_tf32(o1.x), ptx::to_tf32(o1.y), ptx::to_tf32(o1.z), ptx::to_tf32(o1.w));
+                            }
+                            *reinterpret_cast<float4*>(outp + mm * 8) = o0;
+                            *reinterpret_cast<float4*>(outp + mm * 8 + 4) = o1;
+                        } else {
+                            uint32_t hw[4], lw[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) split2(v[2 * e], v[2 * e + 1], hw[e], lw[e]);
+                            reinterpret_cast<uint4*>(outp)[mm] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                            reinterpret_cast<uint4*>(outp)[4 + mm] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                         }
                     }
-                }
                 }
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) { if (leader) ptx::mbar_arrive(&tmem_empty[acc]); else ptx::mbar_arrive_cluster(&tmem_empty[acc], 0); }
+                if (C::kEpiT && sk_dump) {                                   // all 8 epilogue warps have stored (and fenced) their part of the partial
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (threadIdx.x == 128) ptx::st_release_gpu(p.sk_flags + blockIdx.x, t.sk_seq);
+                }
             }
         } else {
             // ---- stem: conv tile 11x11 -> 5x5 max-pooled outputs (MaxPool2d(3,2,1), -inf padding) ----

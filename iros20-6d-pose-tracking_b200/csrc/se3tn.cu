@@ -87,6 +87,10 @@ struct WeightSet {
     CUtensorMap bmap_bf16[14];
     uint8_t* dev_stack = nullptr;   // 8 x [128][288 words]: resident-weight layers with hi / lo rows stacked along N (conv_umma2.cu STACK)
     CUtensorMap bmap_stack[8];
+    // resident 64-channel layers (li 2..7) for the v2 kernel: weight rows in the epilogue's channel order (aux_kernels.cu
+    // permute_rows64_kernel); [li-2] -> tf32 words | bf16 [hi|lo] chunks, 64 x 576 words each.  bmap_res[0..1] = the stems' natural maps.
+    float* dev_perm = nullptr; float* dev_perm_tmp = nullptr;
+    CUtensorMap bmap_res[8], bmap_res_bf16[8];
     CUtensorMap bmap_pair[8], bmap_bf16_pair[8];   // Cout=64 layers for the CTA-pair kernels: box = 32 weight rows (half per CTA)
     float mean32[8], std32[8];
     double mean64[8], std64[8];
@@ -118,6 +122,10 @@ struct se3tn_ctx {
                                      // (64-ch layers equal, stem 18 % slower): the pair MMA's ~1.3x per-SM advantage at N=64 is eaten by
                                      // the cross-CTA barrier round trips; kept as an experiment
     int pdl = 1;                     // SE3TN_PDL=0 disables programmatic dependent launch between conv kernels
+    int streamk = 0;                 // SE3TN_STREAMK=1: deal (unit, chunk) steps evenly over the CTAs in the BN=256 layers.  Measured no net gain at batch 64
+                                     // (the 128 KB partial dump + fix-up per CTA costs what the 12.5 % shorter makespan wins) and results then
+                                     // depend in the last ulps on a pair's position in the batch, so off by default
+    float* sk_part = nullptr; int* sk_flags = nullptr; int sk_seq = 0;   // stream-K partial slots (one per SM), flags, launch counter
     int debug_flags = 0;             // SE3TN_DEBUG_SKIP: timing experiments (bit0 no B fills, bit1 no A fills); results invalid
     int base_off_mode = 0;           // SE3TN_BASE_OFF: UMMA descriptor base_offset convention for row-shifted starts
     EncodeTiledFn encode = nullptr;
@@ -446,9 +454,9 @@ int sync_tables(se3tn_ctx* c, cudaStream_t s) {
     for (auto& kv : c->weights) {
         if (!kv.second.dev || kv.first < 0) continue;
         for (int li = 0; li < kLayersPerSet; ++li) {
-            m1[kv.first * kLayersPerSet + li] = kv.second.bmap[li];
+            m1[kv.first * kLayersPerSet + li] = (li < 8) ? kv.second.bmap_res[li] : kv.second.bmap[li];
             // bf16: the stem always runs stacked; bf16x3: every resident-weight layer does
-            m2[kv.first * kLayersPerSet + li] = (li < 2) ? kv.second.bmap_stack[li] : kv.second.bmap_bf16[li];
+            m2[kv.first * kLayersPerSet + li] = (li < 2) ? kv.second.bmap_stack[li] : (li < 8 ? kv.second.bmap_res_bf16[li] : kv.second.bmap_bf16[li]);
             m3[kv.first * kLayersPerSet + li] = (li < 8) ? kv.second.bmap_stack[li] : kv.second.bmap_bf16[li];
             bias[kv.first * kLayersPerSet + li] = kv.second.dev + kv.second.b_off[li];
         }
@@ -492,6 +500,7 @@ int run_network(se3tn_ctx* c, int weight_id, int first, int n, int precision,
         p.img_wid = img_wid;
         p.gbmaps = img_wid ? (precision == SE3TN_PREC_BF16X3 ? c->d_bmaps_x3 : (bf16 ? c->d_bmaps_bf16 : c->d_bmaps_tf32)) + li : nullptr;
         p.gbias = img_wid ? c->d_bias + li : nullptr;
+        p.sk_part = nullptr; p.sk_flags = nullptr;
         if (tensor && c->conv_version == 2) {
             UmmaMaps maps;
             const int nmaps = (L.kind == K_STEM) ? 2 : (L.kind == K_S2 ? 4 : 1);
@@ -500,11 +509,18 @@ int run_network(se3tn_ctx* c, int weight_id, int first, int n, int precision,
             const int BN = block_n_of(c, L);
             const bool pool = (L.kind == K_STEM);
             const bool resident = (BN == 64 && L.cout == 64);
+            if (resident && li < 8) maps.b = bf16 ? ws.bmap_res_bf16[li] : ws.bmap_res[li];
             const bool pair = resident && c->pair && !img_wid && li < 8;
             if (pair) maps.b = bf16 ? ws.bmap_bf16_pair[li] : ws.bmap_pair[li];
             else if (resident && li < 8 && bf16 && (pool || precision == SE3TN_PREC_BF16X3)) maps.b = ws.bmap_stack[li];   // must mirror Cfg2::kStack
             Umma2Plan t; fill_plan2(c, L, first, n, BN, t);
             t.pair = pair ? 1 : 0;
+            t.sk_seq = 0;
+            if (BN == 256 && c->streamk && c->sk_part && !(c->dual_m && !img_wid)) {
+                p.sk_part = c->sk_part; p.sk_flags = c->sk_flags;
+                if (++c->sk_seq == 0x7fffffff) c->sk_seq = 1;
+                t.sk_seq = c->sk_seq;
+            }
             g.n_img = first + n;                       // absolute image indices (TMA maps address image 0)
             p.out = c->buf[L.out]; p.res = (L.res != NONE) ? c->buf[L.res] : nullptr;
             if (pool) {                                // fused MaxPool2d(3,2,1): write the pooled tensor directly
@@ -585,6 +601,7 @@ int se3tn_create(int device, int max_batch, void* workspace, se3tn_ctx** out) {
     if (const char* ov = getenv("SE3TN_DEBUG_SKIP")) c->debug_flags = atoi(ov);
     if (const char* ov = getenv("SE3TN_PDL")) c->pdl = atoi(ov) != 0;
     if (const char* ov = getenv("SE3TN_PAIR")) c->pair = atoi(ov) != 0;
+    if (const char* ov = getenv("SE3TN_STREAMK")) c->streamk = atoi(ov) != 0;
 
     void* fn = nullptr; cudaDriverEntryPointQueryResult qres;
     e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -601,6 +618,12 @@ int se3tn_create(int device, int max_batch, void* workspace, se3tn_ctx** out) {
         e = cudaMalloc(&c->workspace, bytes);
         if (e != cudaSuccess) { delete c; return fail(nullptr, SE3TN_ERR_NOMEM, std::string("se3tn_create: cudaMalloc(workspace): ") + cudaGetErrorString(e)); }
         c->own_workspace = true;
+    }
+    if (c->streamk) {
+        e = cudaMalloc(&c->sk_part, static_cast<size_t>(c->num_sms) * 128 * 256 * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&c->sk_flags, (c->num_sms + 1) * sizeof(int));
+        if (e == cudaSuccess) e = cudaMemset(c->sk_flags, 0, (c->num_sms + 1) * sizeof(int));
+        if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); se3tn_destroy(c); return fail(nullptr, SE3TN_ERR_NOMEM, "se3tn_create: stream-K workspace: " + m); }
     }
     // zero once: the stem buffers' 3-pixel halo is the conv padding and is never written again
     e = cudaMemset(c->workspace, 0, bytes);
@@ -620,10 +643,11 @@ int se3tn_create(int device, int max_batch, void* workspace, se3tn_ctx** out) {
 void se3tn_destroy(se3tn_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    for (auto& kv : c->weights) { cudaFree(kv.second.dev); cudaFree(kv.second.dev_tf32); cudaFree(kv.second.dev_bf16); cudaFree(kv.second.dev_stem_bf16); cudaFree(kv.second.dev_stack); }
+    for (auto& kv : c->weights) { cudaFree(kv.second.dev); cudaFree(kv.second.dev_tf32); cudaFree(kv.second.dev_bf16); cudaFree(kv.second.dev_stem_bf16); cudaFree(kv.second.dev_stack); cudaFree(kv.second.dev_perm); cudaFree(kv.second.dev_perm_tmp); }
     cudaFree(c->d_mean32); cudaFree(c->d_std32); cudaFree(c->d_mean64); cudaFree(c->d_std64);
     cudaFree(c->d_bmaps_tf32); cudaFree(c->d_bmaps_bf16); cudaFree(c->d_bmaps_x3); cudaFree(c->d_bias); cudaFree(c->d_fc);
     for (int i = 0; i < SE3TN_PROFILE_SLOTS; ++i) { if (c->ev0[i]) cudaEventDestroy(c->ev0[i]); if (c->ev1[i]) cudaEventDestroy(c->ev1[i]); }
+    cudaFree(c->sk_part); cudaFree(c->sk_flags);
     if (c->own_workspace) cudaFree(c->workspace);
     delete c;
 }
@@ -642,6 +666,8 @@ int se3tn_load_weights(se3tn_ctx* c, int weight_id, const float* blob, size_t n_
         CU_TRY(c, cudaMalloc(&ws.dev_bf16, expect * sizeof(float)));
         CU_TRY(c, cudaMalloc(&ws.dev_stem_bf16, 2 * 64 * 448 * sizeof(float)));
         CU_TRY(c, cudaMalloc(&ws.dev_stack, 8 * 128 * 288 * sizeof(float)));
+        CU_TRY(c, cudaMalloc(&ws.dev_perm, 6 * 2 * 64 * 576 * sizeof(float)));
+        CU_TRY(c, cudaMalloc(&ws.dev_perm_tmp, 64 * 576 * sizeof(float)));
     }
     CU_TRY(c, cudaDeviceSynchronize());
     CU_TRY(c, cudaMemcpy(ws.dev, blob, expect * sizeof(float), cudaMemcpyHostToDevice));
@@ -668,16 +694,33 @@ int se3tn_load_weights(se3tn_ctx* c, int weight_id, const float* blob, size_t n_
         }
         if (rc) return rc;
         if (L.cout == 64 && li < 8) {
+            // resident-weight layers of the v2 kernel.  Stems keep the natural row order; the 64-channel 3x3 layers use the
+            // row order of the 16x256b epilogue (all three precisions, single-CTA and pair maps alike).
+            const bool stem = (L.kind == K_STEM);
+            const float* wsrc = ws.dev + ws.w_off[li];
+            const float* w_tf32 = ws.dev_tf32 + ws.w_off[li];
+            const uint8_t* w_bf16 = stem ? ws.dev_stem_bf16 + static_cast<size_t>(li) * 64 * 448 * sizeof(float) : ws.dev_bf16 + ws.w_off[li] * sizeof(float);
+            if (!stem) {
+                if (layer_ktot(L) != 576 || layer_rows(L) != 64) return fail(c, SE3TN_ERR_STATE, "resident layer shape");
+                float* pt = ws.dev_perm + static_cast<size_t>(li - 2) * 2 * 64 * 576;
+                CU_TRY(c, launch_permute_rows64(wsrc, ws.dev_perm_tmp, 576, 0));
+                round_tf32_kernel<<<144, 256>>>(ws.dev_perm_tmp, pt, 64 * 576);
+                CU_TRY(c, cudaGetLastError());
+                CU_TRY(c, launch_split_weights(ws.dev_perm_tmp, pt + 64 * 576, 64 * 576, 0));
+                wsrc = ws.dev_perm_tmp; w_tf32 = pt; w_bf16 = reinterpret_cast<const uint8_t*>(pt + 64 * 576);
+            }
             snprintf(what, sizeof what, "layer %d stacked weights", li);
             uint8_t* sdst = ws.dev_stack + static_cast<size_t>(li) * 128 * 288 * sizeof(float);
-            CU_TRY(c, launch_split_stack_weights(ws.dev + ws.w_off[li], sdst, L.kind == K_STEM, 0));
-            rc = make_map2(c, &ws.bmap_stack[li], sdst, L.kind == K_STEM ? 224 : 288, 128, 128, what);
+            CU_TRY(c, launch_split_stack_weights(wsrc, sdst, stem, 0));
+            rc = make_map2(c, &ws.bmap_stack[li], sdst, stem ? 224 : 288, 128, 128, what);
+            if (rc) return rc;
+            snprintf(what, sizeof what, "layer %d resident weights", li);
+            rc = make_map2(c, &ws.bmap_res[li], w_tf32, layer_ktot(L), 64, 64, what);
+            if (!rc) rc = make_map2(c, &ws.bmap_res_bf16[li], w_bf16, stem ? 448 : layer_ktot(L), 64, 64, what);
             if (rc) return rc;
             snprintf(what, sizeof what, "layer %d pair weights", li);
-            rc = make_map2(c, &ws.bmap_pair[li], ws.dev_tf32 + ws.w_off[li], layer_ktot(L), layer_rows(L), 32, what);
-            if (rc) return rc;
-            if (L.kind == K_STEM) rc = make_map2(c, &ws.bmap_bf16_pair[li], ws.dev_stem_bf16 + static_cast<size_t>(li) * 64 * 448 * sizeof(float), 448, 64, 32, what);
-            else rc = make_map2(c, &ws.bmap_bf16_pair[li], ws.dev_bf16 + ws.w_off[li] * sizeof(float), layer_ktot(L), layer_rows(L), 32, what);
+            rc = make_map2(c, &ws.bmap_pair[li], w_tf32, layer_ktot(L), 64, 32, what);
+            if (!rc) rc = make_map2(c, &ws.bmap_bf16_pair[li], w_bf16, stem ? 448 : layer_ktot(L), 64, 32, what);
             if (rc) return rc;
         }
     }
