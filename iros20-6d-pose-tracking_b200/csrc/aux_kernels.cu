@@ -399,6 +399,47 @@ head_kernel(const float4* __restrict__ x, const float* __restrict__ fcw /*[6][51
     }
 }
 
+// Head on the fused average pool (conv_umma2.cu writes pool_part[image][4 row quadrants][1024] column sums): mean -> Linear -> tanh.
+__global__ void __launch_bounds__(128)
+head_pooled_kernel(const float4* __restrict__ part, const float* __restrict__ fcw, const float* __restrict__ fcb,
+                   float* __restrict__ out_trans, float* __restrict__ out_rot, int npix,
+                   const int* __restrict__ img_wid, const float* const* __restrict__ fc_table)
+{
+    ptx::grid_dep_launch();
+    __shared__ float red[4][3];
+    const int n = blockIdx.x, head = blockIdx.y, t = threadIdx.x;
+    ptx::grid_dep_wait();
+    if (img_wid) { fcw = fc_table[img_wid[n]]; fcb = fcw + 6 * 512; }
+    const float4* pp = part + static_cast<size_t>(n) * 4 * 256 + head * 128 + t;
+    const float4 a0 = pp[0], a1 = pp[256], a2 = pp[512], a3 = pp[768];
+    const float inv = 1.0f / static_cast<float>(npix);
+    const float mx = ((a0.x + a1.x) + (a2.x + a3.x)) * inv, my = ((a0.y + a1.y) + (a2.y + a3.y)) * inv;
+    const float mz = ((a0.z + a1.z) + (a2.z + a3.z)) * inv, mw = ((a0.w + a1.w) + (a2.w + a3.w)) * inv;
+    float acc[3];
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(fcw + (head * 3 + o) * 512 + t * 4));
+        acc[o] = mx * w.x + my * w.y + mz * w.z + mw * w.w;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+        for (int o = 0; o < 3; ++o) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], off);
+    if ((t & 31) == 0) { red[t >> 5][0] = acc[0]; red[t >> 5][1] = acc[1]; red[t >> 5][2] = acc[2]; }
+    __syncthreads();
+    if (t < 3) {
+        const float v = red[0][t] + red[1][t] + red[2][t] + red[3][t] + fcb[head * 3 + t];
+        (head == 0 ? out_trans : out_rot)[n * 3 + t] = tanhf(v);
+    }
+}
+cudaError_t launch_head_pooled(const float* part, const float* fcw, const float* fcb, float* out_trans, float* out_rot,
+                               int n_img, int npix, const int* img_wid, const float* const* fc_table, cudaStream_t s) {
+    if (n_img <= 0) return cudaSuccess;
+    const float4* p4 = reinterpret_cast<const float4*>(part);
+    void* args[] = {&p4, &fcw, &fcb, &out_trans, &out_rot, &npix, &img_wid, &fc_table};
+    return launch_pdl(reinterpret_cast<const void*>(head_pooled_kernel), dim3(n_img, 2), dim3(128), args, s);
+}
+
 cudaError_t launch_head(const float* x, const float* fcw, const float* fcb, float* out_trans, float* out_rot,
                         int n_img, int npix, int split_bf16, const int* img_wid, const float* const* fc_table, cudaStream_t s) {
     if (n_img <= 0) return cudaSuccess;

@@ -38,6 +38,8 @@ cudaError_t launch_crop(const uint8_t* frame_rgb, const uint16_t* frame_depth, i
                         int out_h, int out_w, uint8_t* crop_rgb, uint16_t* crop_depth, cudaStream_t s);
 cudaError_t launch_nchw_to_stem(const float* src, float* dst, int n, int round_tf32, cudaStream_t s);
 cudaError_t launch_maxpool(const float* in, float* out, int n_img, int Hin, int Win, int C, cudaStream_t s);
+cudaError_t launch_head_pooled(const float* part /*[n][4][1024]*/, const float* fcw, const float* fcb, float* out_trans, float* out_rot,
+                               int n_img, int npix, const int* img_wid, const float* const* fc_table, cudaStream_t s);
 cudaError_t launch_head(const float* x, const float* fcw, const float* fcb, float* out_trans, float* out_rot,
                         int n_img, int npix, int split_bf16, const int* img_wid, const float* const* fc_table, cudaStream_t s);
 cudaError_t launch_nhwc_to_nchw(const float* in, float* out, int n_img, int HW, int C, int split_bf16, cudaStream_t s);

@@ -62,6 +62,9 @@ struct ConvPtrs {
     // stream-K (ring-weight kernels): one 128 x 256 fp32 partial-accumulator slot and one flag per CTA; null = off
     float* sk_part;
     int* sk_flags;
+    // fused AdaptiveAvgPool2d(1) (last conv of the heads, one image per M tile): instead of storing the activation, every
+    // epilogue warp writes the column sums over its 32 rows to pool_part[image][row quadrant][channel]; null = normal store
+    float* pool_part;
 };
 
 // ---- tcgen05 path only ------------------------------------------------------------------

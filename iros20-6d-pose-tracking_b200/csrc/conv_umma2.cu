@@ -536,8 +536,31 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                             __syncwarp();
                             fix = reinterpret_cast<const uint4*>(p.sk_part + static_cast<size_t>(blockIdx.x + 1) * (kBlockM * BN));
                         }
+                        int pix[8];                                          // pixels this lane post-processes: rows 4k + sub (same for every block)
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) pix[k] = rowtab[4 * k + sub];
 #pragma unroll 1
                         for (int c0 = 0; c0 < kCols; c0 += 32) {
+                            const int chan = ch0 + c0;                        // first channel (word index) of this 32-channel chunk
+                            // residual pieces first: their L2 latency overlaps the TMEM load and the staging round trip below
+                            float4 r4[8];                                    // tf32 storage: 4 fp32 words
+                            uint2 rh[8], rl[8];                              // bf16 storage: 4 channels, hi at byte grp*8 of the chunk, lo 64 bytes further
+                            if (p.res) {
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) {
+                                    if (PREC == PREC_TF32) {
+                                        r4[k] = pix[k] >= 0 ? __ldg(reinterpret_cast<const float4*>(p.res + static_cast<size_t>(pix[k]) * g.res_cstride + g.res_coff + chan + grp * 4))
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+                                    } else {
+                                        rh[k] = make_uint2(0u, 0u); rl[k] = make_uint2(0u, 0u);
+                                        if (pix[k] >= 0) {
+                                            const uint8_t* cb = reinterpret_cast<const uint8_t*>(p.res + static_cast<size_t>(pix[k]) * g.res_cstride + g.res_coff + chan) + grp * 8;
+                                            rh[k] = __ldg(reinterpret_cast<const uint2*>(cb));
+                                            rl[k] = __ldg(reinterpret_cast<const uint2*>(cb + 64));
+                                        }
+                                    }
+                                }
+                            }
                             {
                                 uint32_t r0[16], r1[16];
                                 ptx::tmem_ld16(taddr + c0, r0);
@@ -569,11 +592,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                                 }
                             }
                             __syncwarp();
-                            const int chan = ch0 + c0;                        // first channel (word index) of this 32-channel chunk
                             const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias_base + chan + grp * 4));
-                            int pix[8];
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) pix[k] = rowtab[4 * k + sub];
                             float4 a4[8];
 #pragma unroll
                             for (int k = 0; k < 8; ++k) {
@@ -582,24 +601,9 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                             }
                             if (p.res) {
                                 if (PREC == PREC_TF32) {
-                                    float4 r4[8];
-#pragma unroll
-                                    for (int k = 0; k < 8; ++k)
-                                        r4[k] = pix[k] >= 0 ? __ldg(reinterpret_cast<const float4*>(p.res + static_cast<size_t>(pix[k]) * g.res_cstride + g.res_coff + chan + grp * 4))
-                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                                     for (int k = 0; k < 8; ++k) { a4[k].x += r4[k].x; a4[k].y += r4[k].y; a4[k].z += r4[k].z; a4[k].w += r4[k].w; }
                                 } else {
-                                    uint2 rh[8], rl[8];                      // 4 channels: bf16 hi at byte grp*8 of the chunk, lo 64 bytes further
-#pragma unroll
-                                    for (int k = 0; k < 8; ++k) {
-                                        rh[k] = make_uint2(0u, 0u); rl[k] = make_uint2(0u, 0u);
-                                        if (pix[k] >= 0) {
-                                            const uint8_t* cb = reinterpret_cast<const uint8_t*>(p.res + static_cast<size_t>(pix[k]) * g.res_cstride + g.res_coff + chan) + grp * 8;
-                                            rh[k] = __ldg(reinterpret_cast<const uint2*>(cb));
-                                            rl[k] = __ldg(reinterpret_cast<const uint2*>(cb + 64));
-                                        }
-                                    }
 #pragma unroll
                                     for (int k = 0; k < 8; ++k) {
                                         const float2 h0 = unpack2(rh[k].x), h1 = unpack2(rh[k].y), l0 = unpack2(rl[k].x), l1 = unpack2(rl[k].y);
@@ -607,12 +611,14 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                                     }
                                 }
                             }
+                            float4 psum = make_float4(0.f, 0.f, 0.f, 0.f);   // fused average pool: this lane's rows, 4 channels
 #pragma unroll
                             for (int k = 0; k < 8; ++k) {
                                 float4 o = a4[k];
                                 if (g.act == ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
                                 else if (g.act == ACT_SELU) { o.x = selu_fast(o.x); o.y = selu_fast(o.y); o.z = selu_fast(o.z); o.w = selu_fast(o.w); }
                                 if (pix[k] < 0) continue;
+                                if (p.pool_part) { psum.x += o.x; psum.y += o.y; psum.z += o.z; psum.w += o.w; continue; }
                                 float* po = p.out + static_cast<size_t>(pix[k]) * g.out_cstride + g.out_coff + chan;
                                 if (PREC == PREC_TF32) {
                                     if (g.round_tf32) o = make_float4(ptx::to_tf32(o.x), ptx::to_tf32(o.y), ptx::to_tf32(o.z), ptx::to_tf32(o.w));
@@ -624,6 +630,15 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                                     *reinterpret_cast<uint2*>(cb) = make_uint2(h0, h1);
                                     *reinterpret_cast<uint2*>(cb + 64) = make_uint2(l0, l1);
                                 }
+                            }
+                            if (p.pool_part) {                                // rows 4k + sub summed above; fold the four `sub` groups (fixed order: deterministic)
+#pragma unroll
+                                for (int off = 8; off <= 16; off <<= 1) {
+                                    psum.x += __shfl_xor_sync(0xffffffffu, psum.x, off); psum.y += __shfl_xor_sync(0xffffffffu, psum.y, off);
+                                    psum.z += __shfl_xor_sync(0xffffffffu, psum.z, off); psum.w += __shfl_xor_sync(0xffffffffu, psum.w, off);
+                                }
+                                if (sub == 0)
+                                    *reinterpret_cast<float4*>(p.pool_part + (static_cast<size_t>(tc.n0) * 4 + q) * g.out_cstride + g.out_coff + chan + grp * 4) = psum;
                             }
                         }
                     }
@@ -831,6 +846,7 @@ cudaError_t launch2(const UmmaMaps& maps, const ConvGeom& g, const Umma2Plan& t,
     using C = Cfg2<BN, RESIDENT, KIND, MT, PREC, PAIR>;
     if (!plan_matches<KIND>(t)) return cudaErrorInvalidValue;
     if (PAIR && (p.img_wid || t.n_tiles != 1 || g.groups != 1)) return cudaErrorInvalidValue;
+    if (p.pool_part && (!C::kEpiT || MT != 1 || t.bn != 1 || t.tiles_x != 1 || t.tiles_y != 1)) return cudaErrorInvalidValue;   // fused avg-pool: tile = whole image
     if (C::kStack == 2 && KIND == KIND_S1 && t.chunks != 2) return cudaErrorInvalidValue;    // a stacked tile row is exactly two 32-channel chunks
     const int w_tiles = C::kStack == 2 ? g.num_taps : g.num_taps * t.chunks * C::kWPerTap;
     const size_t smem = static_cast<size_t>(C::kAStages) * C::kAStage + static_cast<size_t>(RESIDENT ? w_tiles : C::kBStages) * C::kBTile +

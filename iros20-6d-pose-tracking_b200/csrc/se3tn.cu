@@ -122,6 +122,8 @@ struct se3tn_ctx {
                                      // (64-ch layers equal, stem 18 % slower): the pair MMA's ~1.3x per-SM advantage at N=64 is eaten by
                                      // the cross-CTA barrier round trips; kept as an experiment
     int pdl = 1;                     // SE3TN_PDL=0 disables programmatic dependent launch between conv kernels
+    int fuse_pool = 1;               // SE3TN_FUSE_POOL=0: store the last head activation (debug buffer H3) and pool it in head_kernel
+    float* pool_part = nullptr;      // [max_batch][4][1024] column sums from the last conv's epilogue
     int streamk = 0;                 // SE3TN_STREAMK=1: deal (unit, chunk) steps evenly over the CTAs in the BN=256 layers.  Measured no net gain at batch 64
                                      // (the 128 KB partial dump + fix-up per CTA costs what the 12.5 % shorter makespan wins) and results then
                                      // depend in the last ulps on a pair's position in the batch, so off by default
@@ -490,6 +492,7 @@ int run_network(se3tn_ctx* c, int weight_id, int first, int n, int precision,
         int rc = sync_tables(c, s); if (rc) return rc;
     }
     const float* wbase = tf32 ? ws.dev_tf32 : ws.dev;
+    const bool fused_pool = tensor && c->conv_version == 2 && c->fuse_pool && !c->dual_m;
     auto bufp = [&](Buf b) { return c->buf[b] + kBufFloats[b] * static_cast<size_t>(first); };
     for (int li = 0; li < 14; ++li) {
         const LayerSpec& L = kLayers[li];
@@ -500,7 +503,7 @@ int run_network(se3tn_ctx* c, int weight_id, int first, int n, int precision,
         p.img_wid = img_wid;
         p.gbmaps = img_wid ? (precision == SE3TN_PREC_BF16X3 ? c->d_bmaps_x3 : (bf16 ? c->d_bmaps_bf16 : c->d_bmaps_tf32)) + li : nullptr;
         p.gbias = img_wid ? c->d_bias + li : nullptr;
-        p.sk_part = nullptr; p.sk_flags = nullptr;
+        p.sk_part = nullptr; p.sk_flags = nullptr; p.pool_part = nullptr;
         if (tensor && c->conv_version == 2) {
             UmmaMaps maps;
             const int nmaps = (L.kind == K_STEM) ? 2 : (L.kind == K_S2 ? 4 : 1);
@@ -516,6 +519,7 @@ int run_network(se3tn_ctx* c, int weight_id, int first, int n, int precision,
             Umma2Plan t; fill_plan2(c, L, first, n, BN, t);
             t.pair = pair ? 1 : 0;
             t.sk_seq = 0;
+            if (li == 13 && fused_pool) p.pool_part = c->pool_part;   // indexed by absolute image (tile n0)
             if (BN == 256 && c->streamk && c->sk_part && !(c->dual_m && !img_wid)) {
                 p.sk_part = c->sk_part; p.sk_flags = c->sk_flags;
                 if (++c->sk_seq == 0x7fffffff) c->sk_seq = 1;
@@ -558,7 +562,11 @@ int run_network(se3tn_ctx* c, int weight_id, int first, int n, int precision,
         if (li == 0) { ProfScope ps(c, 14, s); CU_TRY(c, launch_maxpool(bufp(B_Y1A), bufp(B_P1A), n, 88, 88, 64, s)); ++c->launches; }
         if (li == 1) { ProfScope ps(c, 15, s); CU_TRY(c, launch_maxpool(bufp(B_Y1B), bufp(B_P1B), n, 88, 88, 64, s)); ++c->launches; }
     }
-    { ProfScope ps(c, 16, s); CU_TRY(c, launch_head(bufp(B_H3), ws.dev + ws.fc_off, ws.dev + ws.fc_off + 6 * 512, out_trans, out_rot, n, 121, bf16 ? 1 : 0,
+    if (fused_pool) {
+        ProfScope ps(c, 16, s);
+        CU_TRY(c, launch_head_pooled(c->pool_part + static_cast<size_t>(first) * 4 * 1024, ws.dev + ws.fc_off, ws.dev + ws.fc_off + 6 * 512, out_trans, out_rot, n, 121,
+                                     img_wid ? img_wid + first : nullptr, img_wid ? c->d_fc : nullptr, s));
+    } else { ProfScope ps(c, 16, s); CU_TRY(c, launch_head(bufp(B_H3), ws.dev + ws.fc_off, ws.dev + ws.fc_off + 6 * 512, out_trans, out_rot, n, 121, bf16 ? 1 : 0,
                                                    img_wid ? img_wid + first : nullptr, img_wid ? c->d_fc : nullptr, s)); }
     ++c->launches;
     if (out_feature) { CU_TRY(c, launch_nhwc_to_nchw(bufp(B_F2), out_feature, n, 22 * 22, 256, bf16 ? 1 : 0, s)); ++c->launches; }
@@ -602,6 +610,7 @@ int se3tn_create(int device, int max_batch, void* workspace, se3tn_ctx** out) {
     if (const char* ov = getenv("SE3TN_PDL")) c->pdl = atoi(ov) != 0;
     if (const char* ov = getenv("SE3TN_PAIR")) c->pair = atoi(ov) != 0;
     if (const char* ov = getenv("SE3TN_STREAMK")) c->streamk = atoi(ov) != 0;
+    if (const char* ov = getenv("SE3TN_FUSE_POOL")) c->fuse_pool = atoi(ov) != 0;
 
     void* fn = nullptr; cudaDriverEntryPointQueryResult qres;
     e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -619,6 +628,8 @@ int se3tn_create(int device, int max_batch, void* workspace, se3tn_ctx** out) {
         if (e != cudaSuccess) { delete c; return fail(nullptr, SE3TN_ERR_NOMEM, std::string("se3tn_create: cudaMalloc(workspace): ") + cudaGetErrorString(e)); }
         c->own_workspace = true;
     }
+    e = cudaMalloc(&c->pool_part, static_cast<size_t>(max_batch) * 4 * 1024 * sizeof(float));
+    if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); se3tn_destroy(c); return fail(nullptr, SE3TN_ERR_NOMEM, "se3tn_create: pool buffer: " + m); }
     if (c->streamk) {
         e = cudaMalloc(&c->sk_part, static_cast<size_t>(c->num_sms) * 128 * 256 * sizeof(float));
         if (e == cudaSuccess) e = cudaMalloc(&c->sk_flags, (c->num_sms + 1) * sizeof(int));
@@ -647,7 +658,7 @@ void se3tn_destroy(se3tn_ctx* c) {
     cudaFree(c->d_mean32); cudaFree(c->d_std32); cudaFree(c->d_mean64); cudaFree(c->d_std64);
     cudaFree(c->d_bmaps_tf32); cudaFree(c->d_bmaps_bf16); cudaFree(c->d_bmaps_x3); cudaFree(c->d_bias); cudaFree(c->d_fc);
     for (int i = 0; i < SE3TN_PROFILE_SLOTS; ++i) { if (c->ev0[i]) cudaEventDestroy(c->ev0[i]); if (c->ev1[i]) cudaEventDestroy(c->ev1[i]); }
-    cudaFree(c->sk_part); cudaFree(c->sk_flags);
+    cudaFree(c->sk_part); cudaFree(c->sk_flags); cudaFree(c->pool_part);
     if (c->own_workspace) cudaFree(c->workspace);
     delete c;
 }

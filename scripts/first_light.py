@@ -2,6 +2,7 @@
 things diverge.  python scripts/first_light.py [N]"""
 import importlib, os, sys, time, traceback
 import numpy as np, torch
+os.environ.setdefault("SE3TN_FUSE_POOL", "0")   # this diagnostic compares the H3 activation, which the fused pool does not store
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'oracle'))
 pkg = importlib.import_module('iros20-6d-pose-tracking_b200')
