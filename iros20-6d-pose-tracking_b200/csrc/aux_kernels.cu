@@ -67,7 +67,7 @@ __device__ __forceinline__ float depth_offset(unsigned d, double z1000, bool gl)
     return static_cast<float>(gl ? __dadd_rn(static_cast<double>(d), z1000) : __dsub_rn(static_cast<double>(d), z1000));
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 preprocess_kernel(PreprocessArgs a)
 {
     ptx::grid_dep_launch();
@@ -77,6 +77,19 @@ preprocess_kernel(PreprocessArgs a)
     // the crop window and cv2's inverse scales are per track: one thread computes them for the block
     __shared__ int s_win[4];
     __shared__ double s_inv[2];
+    // (v - mean) / std of an 8-bit colour value takes 256 values per channel: tabulate the six colour channels once per block
+    // with the SAME IEEE division the per-pixel code would use (bit-identical), leaving two divisions per pixel (the depths)
+    __shared__ float s_lut[6][256];
+    {
+        const int wi0 = a.weight_ids ? a.weight_ids[n] : 0;
+        const float v = static_cast<float>(threadIdx.x);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            const int mc = c < 3 ? c : c + 1;                   // A: mean[0..2], B: mean[4..6]
+            s_lut[c][threadIdx.x] = a.stats_f64 ? norm_f64(v, a.mean64[wi0 * 8 + mc], a.std64[wi0 * 8 + mc])
+                                                : norm_f32(v, a.mean32[wi0 * 8 + mc], a.std32[wi0 * 8 + mc]);
+        }
+    }
     ptx::grid_dep_wait();                                       // poses come from the previous step's pose update
     if (threadIdx.x == 0 && !a.b_precropped) {
         int top, left, ch, cw;
@@ -155,12 +168,12 @@ preprocess_kernel(PreprocessArgs a)
         const float zA = depth_offset(dA[i], z1000, gl), zB = depth_offset(dB[i], z1000, gl);
         if (a.stats_f64) {
             const double* m = a.mean64 + wi * 8; const double* s = a.std64 + wi * 8;
-            vA[i] = make_float4(norm_f64(rA[i], m[0], s[0]), norm_f64(gA[i], m[1], s[1]), norm_f64(bA[i], m[2], s[2]), norm_f64(zA, m[3], s[3]));
-            vB[i] = make_float4(norm_f64(rB[i], m[4], s[4]), norm_f64(gB[i], m[5], s[5]), norm_f64(bB[i], m[6], s[6]), norm_f64(zB, m[7], s[7]));
+            vA[i] = make_float4(s_lut[0][rA[i]], s_lut[1][gA[i]], s_lut[2][bA[i]], norm_f64(zA, m[3], s[3]));
+            vB[i] = make_float4(s_lut[3][rB[i]], s_lut[4][gB[i]], s_lut[5][bB[i]], norm_f64(zB, m[7], s[7]));
         } else {
             const float* m = a.mean32 + wi * 8; const float* s = a.std32 + wi * 8;
-            vA[i] = make_float4(norm_f32(rA[i], m[0], s[0]), norm_f32(gA[i], m[1], s[1]), norm_f32(bA[i], m[2], s[2]), norm_f32(zA, m[3], s[3]));
-            vB[i] = make_float4(norm_f32(rB[i], m[4], s[4]), norm_f32(gB[i], m[5], s[5]), norm_f32(bB[i], m[6], s[6]), norm_f32(zB, m[7], s[7]));
+            vA[i] = make_float4(s_lut[0][rA[i]], s_lut[1][gA[i]], s_lut[2][bA[i]], norm_f32(zA, m[3], s[3]));
+            vB[i] = make_float4(s_lut[3][rB[i]], s_lut[4][gB[i]], s_lut[5][bB[i]], norm_f32(zB, m[7], s[7]));
         }
     }
     if (a.nchwA) {
