@@ -171,6 +171,22 @@ int se3tn_add_adi(se3tn_ctx* ctx, const double* model_pts, int m, const double* 
  * (the reference raises IndexError there). */
 int se3tn_vocap(se3tn_ctx* ctx, const double* errs, int n, double* out_ap, void* stream);
 
+/* ---- input A: the rendered previous view (SURVEY.md 8(f) "next" row 2) ------------------------------------- */
+
+/* The CAD model the renderer draws: what VispyRenderer.__init__ uploads as vertex / index buffers (reference
+ * vispy_renderer.py:108-129).  HOST arrays, copied: pos float32 (nv,3) metres in the object frame, nrm float32 (nv,3)
+ * unit normals, col uint8 (nv,3), faces int32 (nf,3).  mesh_id >= 0; a later call with the same id replaces the model. */
+int se3tn_set_mesh(se3tn_ctx* ctx, int mesh_id, const float* pos, const float* nrm, const uint8_t* col,
+                   const int32_t* faces, int nv, int nf);
+
+/* Tracker.render_window for n tracks (reference predict.py:193-215 -> vispy_renderer.py:135-178): the model at `poses`
+ * rasterised into each track's 176x176 window (y-flipped orthographic crop of the pinhole projection, depth test LESS,
+ * no culling, Lambert + ambient shading) -> rgbA uint8 (n,176,176,3) and depthA uint16 (n,176,176) mm, 0 = background,
+ * both device -- exactly the arrays se3tn_preprocess / se3tn_track_batch take.  K: 4 doubles HOST (fx, fy, cx, cy);
+ * poses double (n,16) device; object_width double (n) device; mesh_ids int32 (n) device or NULL (all 0). */
+int se3tn_render(se3tn_ctx* ctx, const double* K, const double* poses, const double* object_width,
+                 const int32_t* mesh_ids, int n, uint8_t* rgbA, uint16_t* depthA, void* stream);
+
 /* ---- introspection (tests / profiling) -------------------------------------------------------- */
 
 /* Device pointer + per-image float count of an internal NHWC activation buffer.
@@ -181,8 +197,8 @@ int se3tn_debug_buffer(se3tn_ctx* ctx, int id, float** ptr, size_t* floats_per_i
  * is bracketed by CUDA events on the caller's stream.  se3tn_get_profile synchronises those events
  * and writes SE3TN_PROFILE_SLOTS durations (ms) of the LAST call: [0..13] the 14 conv launches in
  * schedule order, [14],[15] the two max-pools, [16] head, [17] preprocess/normalize, [18] pose update,
- * [19] input repack (se3tn_forward only).  Slots that did not run read 0. */
-#define SE3TN_PROFILE_SLOTS 20
+ * [19] input repack (se3tn_forward only), [20] render.  Slots that did not run read 0. */
+#define SE3TN_PROFILE_SLOTS 21
 int se3tn_set_profiling(se3tn_ctx* ctx, int enable);
 int se3tn_get_profile(se3tn_ctx* ctx, float* ms);
 

@@ -3,6 +3,7 @@
 // R^3 x so(3) pose update / label (K6 / K5).  Each replaces numpy/cv2 CPU code in the reference;
 // the file:line each follows is cited at the kernel.
 #include "aux_kernels.h"
+#include "bbox.cuh"
 #include "ptx.cuh"
 #include <cfloat>
 #include <cuda_bf16.h>
@@ -22,27 +23,6 @@ namespace se3tn {
 //         mean/std are float32 arrays (what train.py:121-125 saves), float64 otherwise.
 // pack:   reference data_augmentation.py:179-189 builds CHW float32; here the result goes straight
 //         into the stem conv's zero-padded NHWC4 layout (and optionally to NCHW for the drop-in API).
-
-__device__ __forceinline__ void bbox_window(const double* pose, double fx, double fy, double cx, double cy,
-                                            double width, double sx, double sy, double sz,
-                                            int& top, int& left, int& ch, int& cw)
-{
-    const double ox = __dmul_rn(pose[3], sx), oy = __dmul_rn(pose[7], sy), oz = __dmul_rn(pose[11], sz);
-    const double half = width / 2;
-    // u for x-half / x+half, v for y-half / y+half (the 4 corners share these two values each)
-    const double u0 = rint(__dadd_rn(__ddiv_rn(__dmul_rn(ox - half, fx), oz), cx));
-    const double u1 = rint(__dadd_rn(__ddiv_rn(__dmul_rn(ox + half, fx), oz), cx));
-    const double v0 = rint(__dadd_rn(__ddiv_rn(__dmul_rn(oy - half, fy), oz), cy));
-    const double v1 = rint(__dadd_rn(__ddiv_rn(__dmul_rn(oy + half, fy), oz), cy));
-    const double umin = fmin(u0, u1), umax = fmax(u0, u1), vmin = fmin(v0, v1), vmax = fmax(v0, v1);
-    // clamp to int range so degenerate poses (z ~ 0) cannot overflow
-    const double lim = 1.0e9;
-    if (!(umin == umin && umax == umax && vmin == vmin && vmax == vmax)) { top = left = 0; ch = cw = 0; return; }
-    left = static_cast<int>(fmax(-lim, fmin(lim, umin)));
-    top = static_cast<int>(fmax(-lim, fmin(lim, vmin)));
-    cw = static_cast<int>(fmax(-lim, fmin(lim, umax))) - left;
-    ch = static_cast<int>(fmax(-lim, fmin(lim, vmax))) - top;
-}
 
 // conv-input storage modes: 0 raw fp32, 1 fp32 words rounded to tf32, 2 per pixel [4 x bf16 hi | 4 x bf16 lo]
 __device__ __forceinline__ float4 pack_stem_pixel(float4 v, int mode) {

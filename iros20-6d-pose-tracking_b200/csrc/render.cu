@@ -1,0 +1,268 @@
+// CUDA rasteriser for input A: what the reference obtains from OpenGL through vispy
+//   window + matrices   predict.py:193-215 (Tracker.render_window), vispy_renderer.py:135-150 (update_cam_mat)
+//   light               vispy_renderer.py:171-173
+//   shaders             vispy_renderer.py:56-105 (Lambert term 0.4 * max(n.l, 0) + 0.65 ambient, clamp)
+//   read-back + depth   vispy_renderer.py:152-169 (glReadPixels RGB8 / DEPTH float, z-buffer -> metric distance -> uint16 mm)
+// for all tracks of a frame in one launch, straight into the buffers the preprocess kernel reads -- no GL context, no
+// glReadPixels, no host round trip.
+//
+// Pipeline (one CTA per (track, band of 44 image rows); grid = 4 x n):
+//   0. thread 0 builds the uniforms in float64 exactly as numpy does (window via bbox.cuh, orthographic matrix rounded to
+//      float32, projection product, light = R_gl * (0, .1, -.9) which is what inv(view^T) * (0,.1,-.9,1) evaluates to).
+//   1. visibility: triangles are dealt to threads; each projects its three vertices (float64 on the float32 uniforms),
+//      snaps them to 1/256 pixel, walks the pixel centres of its bounding box with exact integer edge functions
+//      (top-left rule, no culling -- the reference never enables GL_CULL_FACE), interpolates window z and does a 64-bit
+//      shared-memory atomicMin on (float32 z bits << 32 | triangle index): depth test LESS, first-drawn wins ties.
+//      Triangles with large boxes are rasterised by the whole warp.
+//   2. resolve: one thread per pixel re-derives its triangle's barycentrics, interpolates position / normal / colour
+//      perspective-correctly, shades, converts the depth the way on_draw does and writes uint8 rgb + uint16 mm.
+// All arithmetic is float64 with a fixed association and this file is compiled with -fmad=false, so it is bit-identical
+// to the numpy restatement in oracle/se3_oracle.py (render_window).  Scope limits (documented in DESIGN.md): no
+// near-plane polygon clipping (a triangle with a vertex at w <= 1e-6 is dropped; the tracking volume is 0.4-2 m, near =
+// 0.1 m), float32 depth buffer.
+#include "render.h"
+#include "bbox.cuh"
+#include "ptx.cuh"
+
+namespace se3tn {
+namespace {
+constexpr int kRS = 176, kBands = 4, kBandRows = kRS / kBands, kSub = 256, kHalf = kSub / 2;
+constexpr int kRenderThreads = 512;
+constexpr unsigned long long kClearKey = (0x3F800000ull << 32) | 0xFFFFFFFFull;       // depth 1.0, no triangle
+constexpr int kBigBox = 96;                                                            // bounding boxes above this many pixels go to the whole warp
+
+struct Uniforms {
+    double V[12];            // view (rows 0..2; row 3 = 0 0 0 1), float32 values
+    double P00, P02, P11, P12, P22, P23;   // projection (float32 values); P32 = -1
+    double A, B;             // projection_matrix[2][2], [3][2] in float64 (depth linearisation)
+    double light[3];
+    int valid;
+};
+
+__device__ __forceinline__ long long floor_div(long long a, long long b) {             // b > 0
+    long long q = a / b;
+    return (a % b != 0 && a < 0) ? q - 1 : q;
+}
+
+struct Vtx { long long X, Y; double zw, w; bool ok; };
+
+__device__ __forceinline__ Vtx project(const Uniforms& u, const float* __restrict__ pos, int vi) {
+    const double px = pos[3 * vi], py = pos[3 * vi + 1], pz = pos[3 * vi + 2];
+    const double v0 = ((u.V[0] * px + u.V[1] * py) + u.V[2] * pz) + u.V[3];
+    const double v1 = ((u.V[4] * px + u.V[5] * py) + u.V[6] * pz) + u.V[7];
+    const double v2 = ((u.V[8] * px + u.V[9] * py) + u.V[10] * pz) + u.V[11];
+    const double v3 = ((0.0 * px + 0.0 * py) + 0.0 * pz) + 1.0;
+    // clip = P . v with the zero entries of P kept in the sums (x + 0*y is exact for finite y)
+    const double c0 = ((u.P00 * v0 + 0.0 * v1) + u.P02 * v2) + 0.0 * v3;
+    const double c1 = ((0.0 * v0 + u.P11 * v1) + u.P12 * v2) + 0.0 * v3;
+    const double c2 = ((0.0 * v0 + 0.0 * v1) + u.P22 * v2) + u.P23 * v3;
+    const double c3 = ((0.0 * v0 + 0.0 * v1) + -1.0 * v2) + 0.0 * v3;
+    Vtx r;
+    r.w = c3;
+    const double xw = (c0 / c3 + 1.0) * (kRS * 0.5), yw = (c1 / c3 + 1.0) * (kRS * 0.5);
+    r.zw = (c2 / c3 + 1.0) * 0.5;
+    const double X = rint(xw * kSub), Y = rint(yw * kSub);
+    const double lim = 1073741824.0;
+    r.ok = (c3 > 1e-6) && (X == X) && (Y == Y) && fabs(X) < lim && fabs(Y) < lim;
+    r.X = r.ok ? static_cast<long long>(X) : 0;
+    r.Y = r.ok ? static_cast<long long>(Y) : 0;
+    return r;
+}
+
+struct Tri {
+    int i0, i1, i2;
+    long long x0, y0, x1, y1, x2, y2, area2;
+    double z0, z1, z2, w0, w1, w2;
+    bool ok;
+};
+
+__device__ __forceinline__ Tri setup(const Uniforms& u, const MeshDev& m, int t) {
+    Tri T;
+    T.i0 = m.faces[3 * t]; T.i1 = m.faces[3 * t + 1]; T.i2 = m.faces[3 * t + 2];
+    T.ok = static_cast<unsigned>(T.i0) < static_cast<unsigned>(m.nv) && static_cast<unsigned>(T.i1) < static_cast<unsigned>(m.nv) &&
+           static_cast<unsigned>(T.i2) < static_cast<unsigned>(m.nv);
+    if (!T.ok) return T;
+    const Vtx a = project(u, m.pos, T.i0), b = project(u, m.pos, T.i1), c = project(u, m.pos, T.i2);
+    T.ok = a.ok && b.ok && c.ok;
+    if (!T.ok) return T;
+    T.x0 = a.X; T.y0 = a.Y; T.z0 = a.zw; T.w0 = a.w;
+    T.x1 = b.X; T.y1 = b.Y; T.z1 = b.zw; T.w1 = b.w;
+    T.x2 = c.X; T.y2 = c.Y; T.z2 = c.zw; T.w2 = c.w;
+    T.area2 = (T.x1 - T.x0) * (T.y2 - T.y0) - (T.x2 - T.x0) * (T.y1 - T.y0);
+    if (T.area2 == 0) { T.ok = false; return T; }
+    if (T.area2 < 0) {                      // no culling: make it counter-clockwise (y up)
+        int ti = T.i1; T.i1 = T.i2; T.i2 = ti;
+        long long tl = T.x1; T.x1 = T.x2; T.x2 = tl; tl = T.y1; T.y1 = T.y2; T.y2 = tl;
+        double td = T.z1; T.z1 = T.z2; T.z2 = td; td = T.w1; T.w1 = T.w2; T.w2 = td;
+        T.area2 = -T.area2;
+    }
+    return T;
+}
+
+__device__ __forceinline__ void edges(const Tri& T, long long cx, long long cy, long long& e0, long long& e1, long long& e2) {
+    e0 = (T.x2 - T.x1) * (cy - T.y1) - (T.y2 - T.y1) * (cx - T.x1);
+    e1 = (T.x0 - T.x2) * (cy - T.y2) - (T.y0 - T.y2) * (cx - T.x2);
+    e2 = (T.x1 - T.x0) * (cy - T.y0) - (T.y1 - T.y0) * (cx - T.x0);
+}
+__device__ __forceinline__ bool top_left(long long dx, long long dy) { return dy < 0 || (dy == 0 && dx < 0); }
+
+__device__ __forceinline__ void raster_pixel(const Tri& T, int t, int i, int j, int j_lo, bool tl0, bool tl1, bool tl2, unsigned long long* keys) {
+    const long long cx = static_cast<long long>(i) * kSub + kHalf, cy = static_cast<long long>(j) * kSub + kHalf;
+    long long e0, e1, e2;
+    edges(T, cx, cy, e0, e1, e2);
+    if (!((e0 > 0 || (e0 == 0 && tl0)) && (e1 > 0 || (e1 == 0 && tl1)) && (e2 > 0 || (e2 == 0 && tl2)))) return;
+    const double ar = static_cast<double>(T.area2);
+    const double l0 = static_cast<double>(e0) / ar, l1 = static_cast<double>(e1) / ar, l2 = static_cast<double>(e2) / ar;
+    const double z = (l0 * T.z0 + l1 * T.z1) + l2 * T.z2;
+    const float z32 = static_cast<float>(z);
+    if (!(z32 >= 0.f && z32 < 1.f)) return;           // depth clip; LESS against the cleared 1.0
+    const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(z32)) << 32) | static_cast<unsigned>(t);
+    atomicMin(&keys[(j - j_lo) * kRS + i], key);
+}
+
+__global__ void __launch_bounds__(kRenderThreads)
+render_kernel(RenderArgs a)
+{
+    extern __shared__ unsigned long long keys[];            // [kBandRows][kRS]
+    __shared__ Uniforms u;
+    ptx::grid_dep_launch();
+    const int n = blockIdx.y, band = blockIdx.x;
+    const int j_lo = band * kBandRows, j_hi = j_lo + kBandRows - 1;
+    for (int k = threadIdx.x; k < kBandRows * kRS; k += blockDim.x) keys[k] = kClearKey;
+    ptx::grid_dep_wait();                                    // poses come from the previous step's pose update
+    int mid = a.mesh_ids ? a.mesh_ids[n] : 0;
+    if (mid < 0 || mid >= a.n_meshes) mid = 0;
+    const MeshDev m = a.meshes[mid];
+    if (threadIdx.x == 0) {
+        const double* pose = a.poses + n * 16;
+        int top, left, ch, cw;
+        bbox_window(pose, a.fx, a.fy, a.cx, a.cy, a.object_width[n], 1000.0, -1000.0, 1000.0, top, left, ch, cw);   // predict.py:202
+        const int right = left + cw, bottom = top + ch;
+        u.valid = (cw != 0 && ch != 0 && m.nf > 0) ? 1 : 0;
+        // view = inv(glcam_in_cvcam) . ob2cam (rows 1, 2 negated), uploaded as float32
+        for (int c = 0; c < 4; ++c) {
+            u.V[c] = static_cast<double>(static_cast<float>(pose[c]));
+            u.V[4 + c] = static_cast<double>(static_cast<float>(-pose[4 + c]));
+            u.V[8 + c] = static_cast<double>(static_cast<float>(-pose[8 + c]));
+        }
+        const double nr = 0.1, fr = 2.0;
+        const double o00 = static_cast<float>(2.0 / (right - left)), o03 = static_cast<float>(static_cast<double>(-(right + left)) / (right - left));
+        const double o11 = static_cast<float>(2.0 / (top - bottom)), o13 = static_cast<float>(static_cast<double>(-(top + bottom)) / (top - bottom));
+        const double o22 = static_cast<float>(-2.0 / (fr - nr)), o23 = static_cast<float>(-(fr + nr) / (fr - nr));
+        const double P00 = o00 * a.fx, P02 = o00 * (-a.cx) + o03 * (-1.0);
+        const double P11 = o11 * a.fy, P12 = o11 * (-a.cy) + o13 * (-1.0);
+        const double P22 = o22 * (nr + fr) + o23 * (-1.0), P23 = o22 * (nr * fr);
+        u.A = P22; u.B = P23;
+        u.P00 = static_cast<float>(P00); u.P02 = static_cast<float>(P02); u.P11 = static_cast<float>(P11);
+        u.P12 = static_cast<float>(P12); u.P22 = static_cast<float>(P22); u.P23 = static_cast<float>(P23);
+        if (!(isfinite(u.P00) && isfinite(u.P02) && isfinite(u.P11) && isfinite(u.P12))) u.valid = 0;
+        // light_direction = (inv(view^T) . (0, .1, -.9, 1))[:3] = R_gl . (0, .1, -.9)     (vispy_renderer.py:172)
+        for (int r = 0; r < 3; ++r) {
+            const double sgn = r == 0 ? 1.0 : -1.0;
+            const double r0 = sgn * pose[4 * r], r1 = sgn * pose[4 * r + 1], r2 = sgn * pose[4 * r + 2];
+            u.light[r] = static_cast<double>(static_cast<float>((r0 * 0.0 + r1 * 0.1) + r2 * (-0.9)));
+        }
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    if (u.valid) {
+        // ---------------- pass 1: visibility ----------------
+        const int nf_pad = (m.nf + 31) & ~31;                // whole warps walk the loop (ballots below)
+        for (int t = threadIdx.x; t < nf_pad; t += blockDim.x) {
+            bool big = false;
+            if (t < m.nf) {
+                const Tri T = setup(u, m, t);
+                if (T.ok) {
+                    const long long mnx = min(T.x0, min(T.x1, T.x2)), mxx = max(T.x0, max(T.x1, T.x2));
+                    const long long mny = min(T.y0, min(T.y1, T.y2)), mxy = max(T.y0, max(T.y1, T.y2));
+                    const int ia = static_cast<int>(max(0ll, floor_div(mnx - kHalf + kSub - 1, kSub))), ib = static_cast<int>(min(static_cast<long long>(kRS - 1), floor_div(mxx - kHalf, kSub)));
+                    const int ja = static_cast<int>(max(static_cast<long long>(j_lo), floor_div(mny - kHalf + kSub - 1, kSub))), jb = static_cast<int>(min(static_cast<long long>(j_hi), floor_div(mxy - kHalf, kSub)));
+                    if (ia <= ib && ja <= jb) {
+                        if ((ib - ia + 1) * (jb - ja + 1) > kBigBox) big = true;
+                        else {
+                            const bool tl0 = top_left(T.x2 - T.x1, T.y2 - T.y1), tl1 = top_left(T.x0 - T.x2, T.y0 - T.y2), tl2 = top_left(T.x1 - T.x0, T.y1 - T.y0);
+                            for (int j = ja; j <= jb; ++j)
+                                for (int i = ia; i <= ib; ++i) raster_pixel(T, t, i, j, j_lo, tl0, tl1, tl2, keys);
+                        }
+                    }
+                }
+            }
+            unsigned bigmask = __ballot_sync(0xffffffffu, big);
+            while (bigmask) {                                // large triangles: the whole warp walks the bounding box
+                const int src = __ffs(bigmask) - 1; bigmask &= bigmask - 1;
+                const int tb = __shfl_sync(0xffffffffu, t, src);
+                const Tri T = setup(u, m, tb);
+                const long long mnx = min(T.x0, min(T.x1, T.x2)), mxx = max(T.x0, max(T.x1, T.x2));
+                const long long mny = min(T.y0, min(T.y1, T.y2)), mxy = max(T.y0, max(T.y1, T.y2));
+                const int ia = static_cast<int>(max(0ll, floor_div(mnx - kHalf + kSub - 1, kSub))), ib = static_cast<int>(min(static_cast<long long>(kRS - 1), floor_div(mxx - kHalf, kSub)));
+                const int ja = static_cast<int>(max(static_cast<long long>(j_lo), floor_div(mny - kHalf + kSub - 1, kSub))), jb = static_cast<int>(min(static_cast<long long>(j_hi), floor_div(mxy - kHalf, kSub)));
+                const bool tl0 = top_left(T.x2 - T.x1, T.y2 - T.y1), tl1 = top_left(T.x0 - T.x2, T.y0 - T.y2), tl2 = top_left(T.x1 - T.x0, T.y1 - T.y0);
+                const int bw = ib - ia + 1, cnt = bw * (jb - ja + 1);
+                for (int k = lane; k < cnt; k += 32) raster_pixel(T, tb, ia + k % bw, ja + k / bw, j_lo, tl0, tl1, tl2, keys);
+            }
+        }
+    }
+    __syncthreads();
+    // ---------------- pass 2: resolve + shade ----------------
+    const double far_dist = u.B / (u.A + 1.0);
+    for (int k = threadIdx.x; k < kBandRows * kRS; k += blockDim.x) {
+        const int j = j_lo + k / kRS, i = k % kRS;
+        const unsigned long long key = keys[k];
+        const unsigned t = static_cast<unsigned>(key & 0xFFFFFFFFull);
+        unsigned r8 = 0, g8 = 0, b8 = 0, mm = 0;
+        if (u.valid && t != 0xFFFFFFFFu) {
+            const Tri T = setup(u, m, static_cast<int>(t));
+            const long long cx = static_cast<long long>(i) * kSub + kHalf, cy = static_cast<long long>(j) * kSub + kHalf;
+            long long e0, e1, e2;
+            edges(T, cx, cy, e0, e1, e2);
+            const double ar = static_cast<double>(T.area2);
+            const double l0 = static_cast<double>(e0) / ar, l1 = static_cast<double>(e1) / ar, l2 = static_cast<double>(e2) / ar;
+            const double q0 = l0 / T.w0, q1 = l1 / T.w1, q2 = l2 / T.w2;
+            const double qs = (q0 + q1) + q2;
+            double pos[3], nrm[3], col[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                pos[c] = ((q0 * static_cast<double>(m.pos[3 * T.i0 + c]) + q1 * static_cast<double>(m.pos[3 * T.i1 + c])) + q2 * static_cast<double>(m.pos[3 * T.i2 + c])) / qs;
+                nrm[c] = ((q0 * static_cast<double>(m.nrm[3 * T.i0 + c]) + q1 * static_cast<double>(m.nrm[3 * T.i1 + c])) + q2 * static_cast<double>(m.nrm[3 * T.i2 + c])) / qs;
+                const double c0 = static_cast<float>(m.col[3 * T.i0 + c] / 255.0), c1 = static_cast<float>(m.col[3 * T.i1 + c] / 255.0), c2 = static_cast<float>(m.col[3 * T.i2 + c] / 255.0);
+                col[c] = ((q0 * c0 + q1 * c1) + q2 * c2) / qs;
+            }
+            const double x0 = (-u.light[0]) - pos[0], x1 = (-u.light[1]) - pos[1], x2 = (-u.light[2]) - pos[2];
+            const double len = sqrt((x0 * x0 + x1 * x1) + x2 * x2);
+            const double d = (nrm[0] * (x0 / len) + nrm[1] * (x1 / len)) + nrm[2] * (x2 / len);
+            const double lightv = 0.4 * fmax(d, 0.0) + 0.65;
+            r8 = static_cast<unsigned>(rint(fmin(fmax(lightv * col[0], 0.0), 1.0) * 255.0));
+            g8 = static_cast<unsigned>(rint(fmin(fmax(lightv * col[1], 0.0), 1.0) * 255.0));
+            b8 = static_cast<unsigned>(rint(fmin(fmax(lightv * col[2], 0.0), 1.0) * 255.0));
+            // on_draw: distance = B / (depth * -2.0 + 1.0 - A) * -1 (float32 until `- A`), background -> 0, mm = uint16(distance * 1000)
+            const float d32 = __uint_as_float(static_cast<unsigned>(key >> 32));
+            const float tt = __fadd_rn(__fmul_rn(d32, -2.0f), 1.0f);
+            const double dist = (u.B / (static_cast<double>(tt) - u.A)) * -1.0;
+            if (!(dist >= far_dist)) mm = static_cast<unsigned>(static_cast<unsigned short>(static_cast<int>(dist * 1000.0)));
+        }
+        const size_t o = (static_cast<size_t>(n) * kRS + j) * kRS + i;
+        a.rgb[o * 3] = static_cast<uint8_t>(r8); a.rgb[o * 3 + 1] = static_cast<uint8_t>(g8); a.rgb[o * 3 + 2] = static_cast<uint8_t>(b8);
+        a.depth[o] = static_cast<uint16_t>(mm);
+    }
+}
+}  // namespace
+
+cudaError_t launch_render(const RenderArgs& a, int n, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    const size_t smem = static_cast<size_t>(kBandRows) * kRS * sizeof(unsigned long long);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kBands, n); cfg.blockDim = dim3(kRenderThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, render_kernel, a);
+}
+
+}  // namespace se3tn

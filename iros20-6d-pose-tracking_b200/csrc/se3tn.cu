@@ -4,6 +4,7 @@
 #include "conv_common.h"
 #include "aux_kernels.h"
 #include "metrics.h"
+#include "render.h"
 #include "ptx.cuh"
 
 #include <cstdio>
@@ -122,6 +123,8 @@ struct se3tn_ctx {
                                      // (64-ch layers equal, stem 18 % slower): the pair MMA's ~1.3x per-SM advantage at N=64 is eaten by
                                      // the cross-CTA barrier round trips; kept as an experiment
     int pdl = 1;                     // SE3TN_PDL=0 disables programmatic dependent launch between conv kernels
+    std::map<int, MeshDev> meshes;   // CAD models of the rasteriser (device copies), keyed by mesh id
+    MeshDev* d_meshes = nullptr; int mesh_rows = 0; bool meshes_dirty = false;
     int fuse_pool = 1;               // SE3TN_FUSE_POOL=0: store the last head activation (debug buffer H3) and pool it in head_kernel
     float* pool_part = nullptr;      // [max_batch][4][1024] column sums from the last conv's epilogue
     int streamk = 0;                 // SE3TN_STREAMK=1: deal (unit, chunk) steps evenly over the CTAs in the BN=256 layers.  Measured no net gain at batch 64
@@ -659,6 +662,8 @@ void se3tn_destroy(se3tn_ctx* c) {
     cudaFree(c->d_bmaps_tf32); cudaFree(c->d_bmaps_bf16); cudaFree(c->d_bmaps_x3); cudaFree(c->d_bias); cudaFree(c->d_fc);
     for (int i = 0; i < SE3TN_PROFILE_SLOTS; ++i) { if (c->ev0[i]) cudaEventDestroy(c->ev0[i]); if (c->ev1[i]) cudaEventDestroy(c->ev1[i]); }
     cudaFree(c->sk_part); cudaFree(c->sk_flags); cudaFree(c->pool_part);
+    for (auto& kv : c->meshes) { cudaFree(const_cast<float*>(kv.second.pos)); cudaFree(const_cast<float*>(kv.second.nrm)); cudaFree(const_cast<uint8_t*>(kv.second.col)); cudaFree(const_cast<int*>(kv.second.faces)); }
+    cudaFree(c->d_meshes);
     if (c->own_workspace) cudaFree(c->workspace);
     delete c;
 }
@@ -925,6 +930,58 @@ int se3tn_vocap(se3tn_ctx* c, const double* errs, int n, double* out_ap, void* s
     if (!out_ap || n < 0 || (n > 0 && !errs)) return fail(c, SE3TN_ERR_INVALID, "se3tn_vocap: null/invalid argument");
     CU_TRY(c, cudaSetDevice(c->device));
     CU_TRY(c, vocap(errs, n, out_ap, static_cast<cudaStream_t>(stream)));
+    return SE3TN_OK;
+}
+
+int se3tn_set_mesh(se3tn_ctx* c, int mesh_id, const float* pos, const float* nrm, const uint8_t* col,
+                   const int32_t* faces, int nv, int nf) {
+    if (!c) return SE3TN_ERR_INVALID;
+    if (mesh_id < 0 || mesh_id > 4095 || !pos || !nrm || !col || !faces || nv <= 0 || nf <= 0)
+        return fail(c, SE3TN_ERR_INVALID, "se3tn_set_mesh: bad arguments");
+    for (int i = 0; i < 3 * nf; ++i)
+        if (faces[i] < 0 || faces[i] >= nv) return fail(c, SE3TN_ERR_INVALID, "se3tn_set_mesh: face index out of range");
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaDeviceSynchronize());
+    MeshDev& m = c->meshes[mesh_id];
+    cudaFree(const_cast<float*>(m.pos)); cudaFree(const_cast<float*>(m.nrm)); cudaFree(const_cast<uint8_t*>(m.col)); cudaFree(const_cast<int*>(m.faces));
+    m = MeshDev{};
+    float* dpos; float* dnrm; uint8_t* dcol; int* dfaces;
+    CU_TRY(c, cudaMalloc(&dpos, sizeof(float) * 3 * nv)); m.pos = dpos;
+    CU_TRY(c, cudaMalloc(&dnrm, sizeof(float) * 3 * nv)); m.nrm = dnrm;
+    CU_TRY(c, cudaMalloc(&dcol, 3 * static_cast<size_t>(nv))); m.col = dcol;
+    CU_TRY(c, cudaMalloc(&dfaces, sizeof(int) * 3 * nf)); m.faces = dfaces;
+    CU_TRY(c, cudaMemcpy(dpos, pos, sizeof(float) * 3 * nv, cudaMemcpyHostToDevice));
+    CU_TRY(c, cudaMemcpy(dnrm, nrm, sizeof(float) * 3 * nv, cudaMemcpyHostToDevice));
+    CU_TRY(c, cudaMemcpy(dcol, col, 3 * static_cast<size_t>(nv), cudaMemcpyHostToDevice));
+    CU_TRY(c, cudaMemcpy(dfaces, faces, sizeof(int) * 3 * nf, cudaMemcpyHostToDevice));
+    m.nv = nv; m.nf = nf;
+    c->meshes_dirty = true;
+    return SE3TN_OK;
+}
+
+int se3tn_render(se3tn_ctx* c, const double* K, const double* poses, const double* object_width,
+                 const int32_t* mesh_ids, int n, uint8_t* rgbA, uint16_t* depthA, void* stream) {
+    if (!c) return SE3TN_ERR_INVALID;
+    if (n < 0 || !K || (n > 0 && (!poses || !object_width || !rgbA || !depthA))) return fail(c, SE3TN_ERR_INVALID, "se3tn_render: bad arguments");
+    if (n == 0) return SE3TN_OK;
+    if (c->meshes.empty()) return fail(c, SE3TN_ERR_STATE, "se3tn_render: no mesh loaded (se3tn_set_mesh)");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CU_TRY(c, cudaSetDevice(c->device));
+    if (c->meshes_dirty) {
+        const int rows = c->meshes.rbegin()->first + 1;
+        CU_TRY(c, cudaStreamSynchronize(s));
+        if (rows > c->mesh_rows) { cudaFree(c->d_meshes); CU_TRY(c, cudaMalloc(&c->d_meshes, sizeof(MeshDev) * rows)); c->mesh_rows = rows; }
+        std::vector<MeshDev> tab(rows, c->meshes.begin()->second);      // unused ids alias the first model
+        for (auto& kv : c->meshes) tab[kv.first] = kv.second;
+        CU_TRY(c, cudaMemcpy(c->d_meshes, tab.data(), sizeof(MeshDev) * rows, cudaMemcpyHostToDevice));
+        c->meshes_dirty = false;
+    }
+    RenderArgs a;
+    a.poses = poses; a.object_width = object_width; a.mesh_ids = mesh_ids; a.meshes = c->d_meshes; a.n_meshes = c->mesh_rows;
+    a.fx = K[0]; a.fy = K[1]; a.cx = K[2]; a.cy = K[3];
+    a.rgb = rgbA; a.depth = depthA;
+    { ProfScope ps(c, 20, s); CU_TRY(c, launch_render(a, n, s)); }
+    ++c->launches;
     return SE3TN_OK;
 }
 

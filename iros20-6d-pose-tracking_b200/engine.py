@@ -205,6 +205,28 @@ class Engine:
         _lib.check(self.lib.se3tn_vocap(self._ctx, _ptr(errs), int(errs.numel()), C.byref(ap), _stream(self.device)), self._ctx)
         return ap.value
 
+    # ------------------------------------------------------------------ input A renderer
+    def set_mesh(self, mesh, mesh_id=0):
+        """Upload a CAD model (dict pos float32 (nv,3), nrm float32 (nv,3), col uint8 (nv,3), faces int32 (nf,3)) -- the
+        vertex / index buffers of the reference's VispyRenderer (vispy_renderer.py:108-129)."""
+        pos = np.ascontiguousarray(mesh['pos'], dtype=np.float32); nrm = np.ascontiguousarray(mesh['nrm'], dtype=np.float32)
+        col = np.ascontiguousarray(mesh['col'], dtype=np.uint8); faces = np.ascontiguousarray(mesh['faces'], dtype=np.int32)
+        if pos.ndim != 2 or pos.shape[1] != 3 or nrm.shape != pos.shape or col.shape != pos.shape or faces.ndim != 2 or faces.shape[1] != 3:
+            raise ValueError('mesh arrays must be pos/nrm/col (nv,3) and faces (nf,3)')
+        _lib.check(self.lib.se3tn_set_mesh(self._ctx, int(mesh_id), pos.ctypes.data, nrm.ctypes.data, col.ctypes.data, faces.ctypes.data,
+                                           int(pos.shape[0]), int(faces.shape[0])), self._ctx)
+
+    def render(self, K, poses, object_width, mesh_ids=None, out_rgb=None, out_depth=None):
+        """Tracker.render_window for n tracks (reference predict.py:193-215): float64 CUDA poses (n,4,4) and widths (n) ->
+        rgbA uint8 (n,176,176,3), depthA uint16 (n,176,176) CUDA tensors."""
+        n = int(poses.shape[0])
+        rgb = out_rgb if out_rgb is not None else torch.empty((n, 176, 176, 3), dtype=torch.uint8, device=self.device)
+        dep = out_depth if out_depth is not None else torch.empty((n, 176, 176), dtype=torch.uint16, device=self.device)
+        Kh = self._k4(K)
+        _lib.check(self.lib.se3tn_render(self._ctx, Kh.ctypes.data_as(C.c_void_p), _ptr(poses), _ptr(object_width), _ptr(mesh_ids), n, _ptr(rgb), _ptr(dep),
+                                         _stream(self.device)), self._ctx)
+        return rgb, dep
+
     # ------------------------------------------------------------------ introspection
     def debug_buffer(self, buf_id, n):
         """A float32 view (n, floats_per_image) of an internal NHWC activation buffer."""
@@ -218,8 +240,8 @@ class Engine:
         _lib.check(self.lib.se3tn_set_profiling(self._ctx, int(bool(enable))), self._ctx)
 
     def get_profile(self):
-        """Device ms of each kernel of the last call (20 slots, see include/se3tn.h)."""
-        ms = (C.c_float * 20)()
+        """Device ms of each kernel of the last call (21 slots, see include/se3tn.h)."""
+        ms = (C.c_float * 21)()
         _lib.check(self.lib.se3tn_get_profile(self._ctx, ms), self._ctx)
         return np.array(ms[:], dtype=np.float64)
 

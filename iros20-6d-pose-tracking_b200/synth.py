@@ -164,3 +164,38 @@ def pose_pairs(n, seed=0, trans_noise=0.01, rot_noise_deg=5.0):
         pred[i, :3, :3] = R @ gt[i, :3, :3]
         pred[i, :3, 3] = gt[i, :3, 3] + rng.normal(size=3) * trans_noise
     return pred, gt
+
+
+def mesh(level=3, seed=0):
+    """A synthetic CAD model in the form the reference's renderer consumes (vispy_renderer.py:108-121: a .ply with per-vertex
+    position, normal and 8-bit colour, triangular faces): an icosphere subdivided `level` times (20 * 4**level faces, outward
+    counter-clockwise), pushed onto the bumpy ellipsoid of `model_points`, smooth procedural colours.
+    -> dict(pos float32 (nv,3) metres, nrm float32 (nv,3) unit, col uint8 (nv,3), faces int32 (nf,3))."""
+    t = (1.0 + 5 ** 0.5) / 2
+    v = [(-1, t, 0), (1, t, 0), (-1, -t, 0), (1, -t, 0), (0, -1, t), (0, 1, t), (0, -1, -t), (0, 1, -t), (t, 0, -1), (t, 0, 1), (-t, 0, -1), (-t, 0, 1)]
+    f = [(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4), (11, 10, 2), (10, 7, 6), (7, 1, 8),
+         (3, 9, 4), (3, 4, 2), (3, 2, 6), (3, 6, 8), (3, 8, 9), (4, 9, 5), (2, 4, 11), (6, 2, 10), (8, 6, 7), (9, 8, 1)]
+    v = [np.array(p, dtype=np.float64) / np.linalg.norm(p) for p in v]
+    for _ in range(level):
+        cache, nf = {}, []
+        def mid(a, b):
+            k = (min(a, b), max(a, b))
+            if k not in cache:
+                m = v[a] + v[b]; v.append(m / np.linalg.norm(m)); cache[k] = len(v) - 1
+            return cache[k]
+        for a, b, c in f:
+            ab, bc, ca = mid(a, b), mid(b, c), mid(c, a)
+            nf += [(a, ab, ca), (b, bc, ab), (c, ca, bc), (ab, bc, ca)]
+        f = nf
+    d = np.array(v); faces = np.array(f, dtype=np.int32)
+    r = 1.0 + 0.15 * np.sin(7 * d[:, 0]) * np.cos(5 * d[:, 1])
+    pos = (d * r[:, None] * np.array([0.05, 0.035, 0.025])).astype(np.float32)
+    fn = np.cross(pos[faces[:, 1]] - pos[faces[:, 0]], pos[faces[:, 2]] - pos[faces[:, 0]]).astype(np.float64)   # area-weighted
+    nrm = np.zeros((len(pos), 3))
+    for k in range(3): np.add.at(nrm, faces[:, k], fn)
+    nrm = nrm.astype(np.float32)
+    nrm = nrm / np.linalg.norm(nrm, axis=1).reshape(-1, 1)          # float32, as vispy_renderer.py:121 does to the ply normals
+    rng = np.random.default_rng(seed + 5)
+    base = 128 + 100 * np.stack((np.sin(9 * d[:, 0] + 1), np.sin(7 * d[:, 1] + 2), np.sin(11 * d[:, 2] + 3)), 1)
+    col = np.clip(base + rng.integers(-12, 13, size=base.shape), 0, 255).astype(np.uint8)
+    return dict(pos=pos, nrm=nrm.astype(np.float32), col=col, faces=faces)

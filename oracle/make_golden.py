@@ -9,6 +9,8 @@ What is executed from the reference, unmodified:
   Utils.compute_bbox / crop_bbox / normalize_rotation_matrix
   data_augmentation.OffsetDepth / NormalizeChannels / ToTensor, Utils.Compose
   datasets.TrackDataset.processData / processPredict  -> pre/post fixtures
+  Utils.add / Utils.adi, eval_ycb.VOCap                -> metric fixtures
+  vispy_renderer.VispyRenderer.update_cam_mat / render_image (numpy parts) -> renderer uniform fixtures
 
 Accommodations (nothing in the reference tree is edited; it is read-only):
   * `open3d` and `transformations` are not installed here; they are only
@@ -196,6 +198,40 @@ def main():
         mt['vocap_' + k] = np.float64(EV.VOCap(v))
     U.spatial = _spatial
     np.savez_compressed(os.path.join(args.out, 'golden_metrics.npz'), **mt)
+    # ------------------------------------------------------------------ renderer uniforms
+    # vispy / OpenGL / plyfile are not installed: stub modules let the reference's vispy_renderer.py import; the class's
+    # pure-numpy methods (update_cam_mat :135-150, render_image :171-178 up to the draw call) are then run unbound on a
+    # stand-in object.  The window (left/right/top/bottom) follows predict.py:202-207 on the reference's compute_bbox.
+    for name in ('vispy', 'vispy.app', 'vispy.gloo', 'OpenGL', 'OpenGL.GL', 'plyfile'):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules['vispy'].app = sys.modules['vispy.app']; sys.modules['vispy'].gloo = sys.modules['vispy.gloo']
+    sys.modules['vispy.app'].Canvas = object
+    sys.modules['OpenGL'].GL = sys.modules['OpenGL.GL']
+    sys.modules['plyfile'].PlyData = sys.modules['plyfile'].PlyElement = object
+    import vispy_renderer as VR                                        # noqa: reference module
+
+    class FakeRenderer:
+        def __init__(self): self.program = {}; self.rgb = self.depth = None
+        def update(self): pass
+        def on_draw(self, ev): pass
+    rd = {}
+    K = synth.CAMERA_K
+    poses = synth.raw_poses(6, seed=7)
+    glcam_in_cvcam = np.array([[1, 0, 0, 0], [0, -1, 0, 0], [0, 0, -1, 0], [0, 0, 0, 1]])
+    wins, projs, views, lights = [], [], [], []
+    for ob2cam in poses:
+        bbox = U.compute_bbox(ob2cam, K, 200.0, scale=(1000, -1000, 1000))
+        ob2cam_gl = np.linalg.inv(glcam_in_cvcam).dot(ob2cam)
+        left, right = np.min(bbox[:, 1]), np.max(bbox[:, 1]); top, bottom = np.min(bbox[:, 0]), np.max(bbox[:, 0])
+        fr = FakeRenderer()
+        VR.VispyRenderer.update_cam_mat(fr, K, left, right, bottom, top)
+        VR.VispyRenderer.render_image(fr, ob2cam_gl)
+        wins.append([left, right, top, bottom]); projs.append(np.asarray(fr.projection_matrix).T.copy())
+        views.append(np.asarray(fr.program['view']).T.copy()); lights.append(np.asarray(fr.program['light_direction']))
+    rd = dict(poses=poses, object_width=np.float64(200.0), window=np.array(wins, np.int64), proj64=np.array(projs),
+              view=np.array(views), light32=np.array(lights))
+    np.savez_compressed(os.path.join(args.out, 'golden_render.npz'), **rd)
     for f in sorted(os.listdir(args.out)):
         print(f, os.path.getsize(os.path.join(args.out, f)))
 

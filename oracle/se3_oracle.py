@@ -302,3 +302,133 @@ def vocap(rec):
     mpre = np.maximum.accumulate(np.concatenate(([0.0], prec, [prec[-1]])))
     i = np.where(mrec[1:] != mrec[:-1])[0] + 1
     return np.sum((mrec[i] - mrec[i - 1]) * mpre[i]) * 10
+
+
+# =============================================================================================
+# Input A: the rendered view of the object at the previous pose
+#   window + matrices   predict.py:193-215 (Tracker.render_window), vispy_renderer.py:135-150 (update_cam_mat)
+#   light               vispy_renderer.py:171-173 (render_image)
+#   shaders             vispy_renderer.py:56-105
+#   read-back, depth    vispy_renderer.py:152-169 (on_draw)
+# The reference hands the triangles to OpenGL (vispy/gloo); no GL exists in this container, so the rasterisation
+# itself is a restatement of the OpenGL pipeline the reference configures: 176x176 viewport, depth test LESS, NO
+# face culling (on_draw only calls set_cull_face, which selects the culled side; GL_CULL_FACE is never enabled),
+# clear colour 0 / depth 1, smooth (perspective-correct) varyings, float->unorm8 colour conversion, and
+# glReadPixels rows bottom-up taken as array rows top-down (which, with the y-flipped orthographic window, is an
+# upright image).  PARITY UNPINNED for the rasterisation rules a GL implementation is free to choose (sub-pixel
+# snapping: 8 bits here; tie rule on edges: top-left; depth-buffer format: float32 here).  The uniforms (window,
+# projection matrix, view matrix, light direction) ARE pinned against the reference's own code
+# (tests/golden/golden_render.npz, oracle/make_golden.py).
+# =============================================================================================
+GLCAM_IN_CVCAM = np.diag([1.0, -1.0, -1.0, 1.0])
+NEAR_PLANE, FAR_PLANE = 0.1, 2.0
+SUBPIXEL = 256
+
+
+def render_uniforms(ob2cam, K, object_width):
+    """-> dict(left,right,top,bottom, view32 (4,4) float32 [math convention: clip = P.V.p], proj64, proj32, light32)."""
+    bbox = compute_bbox(ob2cam, K, object_width, scale=(1000, -1000, 1000))          # predict.py:202
+    left, right = np.min(bbox[:, 1]), np.max(bbox[:, 1])                                # np.int32 scalars, as in the reference
+    top, bottom = np.min(bbox[:, 0]), np.max(bbox[:, 0])
+    ob2cam_gl = np.linalg.inv(GLCAM_IN_CVCAM).dot(ob2cam)                              # predict.py:203
+    n, f = NEAR_PLANE, FAR_PLANE
+    proj = np.array([[K[0, 0], 0, -K[0, 2], 0], [0, K[1, 1], -K[1, 2], 0], [0, 0, n + f, n * f], [0, 0, -1, 0]])
+    with np.errstate(divide='ignore', invalid='ignore'):
+        ortho = np.array([[2. / (right - left), 0, 0, -(right + left) / (right - left)],
+                          [0, 2. / (top - bottom), 0, -(top + bottom) / (top - bottom)],
+                          [0, 0, -2 / (f - n), -(f + n) / (f - n)], [0, 0, 0, 1]]).astype(np.float32)
+    proj64 = ortho.dot(proj)                                                            # = projection_matrix.T
+    light = np.dot(np.linalg.inv(ob2cam_gl.T), np.array([0, 0.1, -0.9, 1]))[:3]         # vispy_renderer.py:172
+    return dict(left=int(left), right=int(right), top=int(top), bottom=int(bottom), view32=ob2cam_gl.astype(np.float32),
+                proj64=proj64, proj32=proj64.astype(np.float32), light32=light.astype(np.float32))
+
+
+def _project_vertices(pos32, view32, proj32, size):
+    """float64 arithmetic on the float32 uniforms / attributes, fixed association (mirrored by render.cu)."""
+    p = pos32.astype(np.float64); V = view32.astype(np.float64); P = proj32.astype(np.float64)
+    v = [((V[i, 0] * p[:, 0] + V[i, 1] * p[:, 1]) + V[i, 2] * p[:, 2]) + V[i, 3] for i in range(4)]
+    c = [((P[i, 0] * v[0] + P[i, 1] * v[1]) + P[i, 2] * v[2]) + P[i, 3] * v[3] for i in range(4)]
+    w = c[3]
+    with np.errstate(divide='ignore', invalid='ignore'):
+        xw = (c[0] / w + 1.0) * (size * 0.5)
+        yw = (c[1] / w + 1.0) * (size * 0.5)
+        zw = (c[2] / w + 1.0) * 0.5
+        X = np.rint(xw * SUBPIXEL); Y = np.rint(yw * SUBPIXEL)
+    return X, Y, zw, w
+
+
+def render_window(ob2cam, K, object_width, mesh, size=176, uniforms=None):
+    """-> (rgb uint8 (size,size,3), depth uint16 (size,size) in mm, 0 = background).  mesh: dict(pos float32 (nv,3),
+    nrm float32 (nv,3), col uint8 (nv,3), faces int32 (nf,3))."""
+    u = uniforms if uniforms is not None else render_uniforms(ob2cam, K, object_width)
+    rgb = np.zeros((size, size, 3), np.uint8); depth = np.zeros((size, size), np.uint16)
+    if u['right'] == u['left'] or u['top'] == u['bottom'] or not np.all(np.isfinite(u['proj32'])):
+        return rgb, depth
+    X, Y, zw, w = _project_vertices(mesh['pos'], u['view32'], u['proj32'], size)
+    key = np.full((size, size), (np.uint64(0x3F800000) << np.uint64(32)) | np.uint64(0xFFFFFFFF), np.uint64)   # depth 1.0, no triangle
+    faces = mesh['faces']
+    lim = 1 << 30
+    setups = {}
+    for t in range(len(faces)):
+        i0, i1, i2 = (int(a) for a in faces[t])
+        if not (w[i0] > 1e-6 and w[i1] > 1e-6 and w[i2] > 1e-6): continue               # no near-plane polygon clipping
+        if not all(np.isfinite(a) and abs(a) < lim for a in (X[i0], Y[i0], X[i1], Y[i1], X[i2], Y[i2])): continue
+        x0, y0, x1, y1, x2, y2 = (int(a) for a in (X[i0], Y[i0], X[i1], Y[i1], X[i2], Y[i2]))
+        area2 = (x1 - x0) * (y2 - y0) - (x2 - x0) * (y1 - y0)
+        if area2 == 0: continue
+        if area2 < 0:                                                                    # no culling: make it counter-clockwise
+            i1, i2, x1, y1, x2, y2, area2 = i2, i1, x2, y2, x1, y1, -area2
+        half = SUBPIXEL // 2
+        ia, ib = max(0, (min(x0, x1, x2) - half + SUBPIXEL - 1) // SUBPIXEL), min(size - 1, (max(x0, x1, x2) - half) // SUBPIXEL)
+        ja, jb = max(0, (min(y0, y1, y2) - half + SUBPIXEL - 1) // SUBPIXEL), min(size - 1, (max(y0, y1, y2) - half) // SUBPIXEL)
+        if ia > ib or ja > jb: continue
+        cx = (np.arange(ia, ib + 1, dtype=np.int64) * SUBPIXEL + half)[None, :]
+        cy = (np.arange(ja, jb + 1, dtype=np.int64) * SUBPIXEL + half)[:, None]
+        inside = np.ones((jb - ja + 1, ib - ia + 1), bool); E = []
+        for (xa, ya, xb, yb) in ((x1, y1, x2, y2), (x2, y2, x0, y0), (x0, y0, x1, y1)):
+            dx, dy = xb - xa, yb - ya
+            e = dx * (cy - ya) - dy * (cx - xa)
+            tl = (dy < 0) or (dy == 0 and dx < 0)                                       # top-left rule, y up, counter-clockwise
+            inside &= (e > 0) | ((e == 0) & tl)
+            E.append(e)
+        if not inside.any(): continue
+        lam = [e.astype(np.float64) / float(area2) for e in E]
+        z = (lam[0] * zw[i0] + lam[1] * zw[i1]) + lam[2] * zw[i2]
+        z32 = z.astype(np.float32)
+        ok = inside & (z32 >= 0) & (z32 < 1)                                         # depth clip; LESS against the cleared 1.0
+        k = (z32.view(np.uint32).astype(np.uint64) << np.uint64(32)) | np.uint64(t)
+        sub = key[ja:jb + 1, ia:ib + 1]
+        upd = ok & (k < sub)
+        sub[upd] = k[upd]
+        setups[t] = (i0, i1, i2, x0, y0, x1, y1, x2, y2, area2)
+    A, B = u['proj64'][2, 2], u['proj64'][2, 3]
+    far_dist = B / (A + 1)
+    light = u['light32'].astype(np.float64)
+    half = SUBPIXEL // 2
+    for j, i in zip(*np.nonzero((key & np.uint64(0xFFFFFFFF)) != np.uint64(0xFFFFFFFF))):
+        t = int(key[j, i] & np.uint64(0xFFFFFFFF))
+        i0, i1, i2, x0, y0, x1, y1, x2, y2, area2 = setups[t]
+        cx, cy = i * SUBPIXEL + half, j * SUBPIXEL + half
+        e0 = (x2 - x1) * (cy - y1) - (y2 - y1) * (cx - x1)
+        e1 = (x0 - x2) * (cy - y2) - (y0 - y2) * (cx - x2)
+        e2 = (x1 - x0) * (cy - y0) - (y1 - y0) * (cx - x0)
+        l0, l1, l2 = float(e0) / float(area2), float(e1) / float(area2), float(e2) / float(area2)
+        q0, q1, q2 = l0 / w[i0], l1 / w[i1], l2 / w[i2]
+        qs = (q0 + q1) + q2
+        def interp(a0, a1, a2): return ((q0 * a0 + q1 * a1) + q2 * a2) / qs
+        pos = [interp(float(mesh['pos'][i0, c]), float(mesh['pos'][i1, c]), float(mesh['pos'][i2, c])) for c in range(3)]
+        nrm = [interp(float(mesh['nrm'][i0, c]), float(mesh['nrm'][i1, c]), float(mesh['nrm'][i2, c])) for c in range(3)]
+        col = [interp(float(np.float32(mesh['col'][i0, c] / 255.0)), float(np.float32(mesh['col'][i1, c] / 255.0)),
+                      float(np.float32(mesh['col'][i2, c] / 255.0))) for c in range(3)]
+        x = [(-light[c]) - pos[c] for c in range(3)]
+        ln = np.sqrt((x[0] * x[0] + x[1] * x[1]) + x[2] * x[2])
+        L = [x[c] / ln for c in range(3)]
+        d = (nrm[0] * L[0] + nrm[1] * L[1]) + nrm[2] * L[2]
+        lightv = 0.4 * max(d, 0.0) + 0.65
+        for c in range(3):
+            rgb[j, i, c] = np.uint8(np.rint(min(max(lightv * col[c], 0.0), 1.0) * 255.0))
+        d32 = np.uint32(key[j, i] >> np.uint64(32)).view(np.float32)
+        tt = np.float32(np.float32(d32 * np.float32(-2.0)) + np.float32(1.0))            # float32 array * python float stays float32
+        dist = (B / (np.float64(tt) - A)) * -1                                          # `- A` with a float64 scalar: float64 (numpy >= 2)
+        depth[j, i] = 0 if dist >= far_dist else np.uint16(dist * 1000)
+    return rgb, depth

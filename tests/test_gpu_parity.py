@@ -400,3 +400,76 @@ def test_add_adi_full_size_properties(synth, eng):
     assert torch.allclose(add[:64], add4, rtol=1e-12, atol=0) and torch.allclose(adi[:64], adi4, rtol=1e-12, atol=0)
     ap = eng.vocap(adi)
     assert 0.0 <= ap <= 1.0 and abs(ap - O.vocap(adi.cpu().numpy())) < 1e-12
+
+
+# ------------------------------------------------------------------------------ input A rasteriser
+def _render_both(eng, synth, mesh, poses, width, mesh_id=0):
+    dev = eng.device
+    eng.set_mesh(mesh, mesh_id)
+    ids = torch.full((len(poses),), mesh_id, dtype=torch.int32, device=dev)
+    rgb, dep = eng.render(synth.CAMERA_K, torch.from_numpy(poses).to(dev), torch.full((len(poses),), float(width), dtype=torch.float64, device=dev), ids)
+    rgb, dep = rgb.cpu().numpy(), dep.cpu().numpy()
+    ref = [O.render_window(p, synth.CAMERA_K, float(width), mesh) for p in poses]
+    return rgb, dep, np.stack([r[0] for r in ref]), np.stack([r[1] for r in ref])
+
+
+def test_render_bit_exact_vs_oracle(pkg, synth, eng):
+    """float64 + exact integer edge functions on both sides: the CUDA rasteriser must reproduce the numpy restatement bit for bit
+    (coverage, depth in mm, 8-bit colour), dense mesh and coarse mesh (warp-cooperative large triangles) alike."""
+    poses = synth.raw_poses(5, seed=11)
+    poses[4] = np.eye(4); poses[4, :3, 3] = (0.0, 0.0, 0.45)
+    for level, mid in ((3, 0), (0, 1), (1, 2)):
+        mesh = synth.mesh(level, seed=level)
+        rgb, dep, rrgb, rdep = _render_both(eng, synth, mesh, poses, 200.0, mid)
+        assert (dep > 0).sum() > 5000
+        assert np.array_equal(dep, rdep), 'level %d: %d depth pixels differ' % (level, (dep != rdep).sum())
+        assert np.array_equal(rgb, rrgb), 'level %d: %d colour values differ' % (level, (rgb != rrgb).sum())
+
+
+def test_render_edge_cases(pkg, synth, eng):
+    dev = eng.device
+    mesh = synth.mesh(2, seed=0)
+    eng.set_mesh(mesh, 0)
+    K = synth.CAMERA_K
+    poses = synth.raw_poses(3, seed=5)
+    P = torch.from_numpy(poses).to(dev)
+    # zero width -> degenerate window -> empty images (the reference would divide by zero in update_cam_mat)
+    rgb, dep = eng.render(K, P, torch.zeros(3, dtype=torch.float64, device=dev))
+    assert int(rgb.max()) == 0 and int(dep.to(torch.int32).max()) == 0
+    # object beyond the far plane (2 m) is clipped away; behind the camera likewise
+    far = poses.copy(); far[:, 2, 3] = 2.5; far[2, 2, 3] = -0.7
+    rgb, dep = eng.render(K, torch.from_numpy(far).to(dev), torch.full((3,), 200.0, dtype=torch.float64, device=dev))
+    assert int(dep.to(torch.int32).max()) == 0 and int(rgb.max()) == 0
+    # per-track models in one launch, n == 0, unknown mesh id falls back to model 0
+    eng.set_mesh(synth.mesh(1, seed=1), 3)
+    ids = torch.tensor([0, 3, 0], dtype=torch.int32, device=dev)
+    w = torch.full((3,), 200.0, dtype=torch.float64, device=dev)
+    rgb, dep = eng.render(K, P, w, ids)
+    r1 = O.render_window(poses[1], K, 200.0, synth.mesh(1, seed=1))
+    assert np.array_equal(dep[1].cpu().numpy(), r1[1]) and np.array_equal(rgb[1].cpu().numpy(), r1[0])
+    r0 = O.render_window(poses[2], K, 200.0, mesh)
+    assert np.array_equal(dep[2].cpu().numpy(), r0[1])
+    e_rgb, e_dep = eng.render(K, P[:0], w[:0])
+    assert e_rgb.shape == (0, 176, 176, 3) and e_dep.shape == (0, 176, 176)
+
+
+def test_render_feeds_track_batch(pkg, synth, eng):
+    """Device-resident loop: render -> K0 -> network -> K6 equals the oracle driven with the oracle's own render."""
+    dev = eng.device
+    mesh = synth.mesh(3, seed=0)
+    eng.set_mesh(mesh, 0)
+    n = 4
+    rgb, depth = synth.raw_frame(seed=2)
+    poses = synth.raw_poses(n, seed=6)
+    K = synth.CAMERA_K
+    w = torch.full((n,), 200.0, dtype=torch.float64, device=dev)
+    P = torch.from_numpy(poses).to(dev)
+    rgbA, depA = eng.render(K, P, w)
+    out_poses, _, _ = eng.track_batch(torch.from_numpy(rgb).to(dev), torch.from_numpy(depth).to(dev), K, P, w, rgbA, depA,
+                                      0.03, 5 * np.pi / 180)
+    mean, std = synth.default_mean_std()
+    sd = synth.make_state_dict(0)
+    for i in range(n):
+        ra, da = O.render_window(poses[i], K, 200.0, mesh)
+        ref = O.on_track(sd, poses[i], rgb, depth, ra, da, K, 200.0, mean, std, 0.03, 5 * np.pi / 180)
+        assert np.abs(out_poses[i].cpu().numpy() - ref).max() < POSE_ATOL

@@ -139,3 +139,36 @@ def test_metrics_oracle_vs_reference(synth, golden_dir):
     assert np.all(adi <= add + 1e-15)                      # nearest neighbour can only be closer
     for k in ('mixed', 'all_below', 'dups', 'single', 'sorted_add'):
         assert abs(O.vocap(g['curve_' + k]) - float(g['vocap_' + k])) < 1e-13, k
+
+
+def test_render_uniforms_vs_reference(synth, golden_dir):
+    """Window, projection matrix, view matrix and light direction of the renderer against the reference's own
+    update_cam_mat / render_image / compute_bbox (oracle/make_golden.py runs them with vispy stubbed)."""
+    g = np.load(os.path.join(golden_dir, 'golden_render.npz'))
+    for i, pose in enumerate(g['poses']):
+        u = O.render_uniforms(pose, synth.CAMERA_K, float(g['object_width']))
+        assert [u['left'], u['right'], u['top'], u['bottom']] == list(g['window'][i])
+        assert np.array_equal(u['proj64'], g['proj64'][i])
+        assert np.array_equal(u['view32'], g['view'][i].astype(np.float32))           # the GL upload casts to float32
+        assert np.array_equal(u['light32'], g['light32'][i]) and g['light32'].dtype == np.float32
+
+
+def test_render_oracle_properties(synth):
+    """The rasterisation restatement itself (no GL here: parity unpinned) must at least behave like a renderer."""
+    mesh = synth.mesh(2, seed=0)
+    pose = np.eye(4); pose[:3, 3] = (0.03, -0.02, 0.6)
+    rgb, dep = O.render_window(pose, synth.CAMERA_K, 200.0, mesh)
+    fg = dep > 0
+    assert 1500 < fg.sum() < 12000 and rgb[~fg].max() == 0 and rgb[fg].max() > 100
+    assert 600 - 30 <= dep[fg].min() and dep[fg].max() <= 600 + 30                      # a 5 x 3.5 x 2.5 cm half-extent body at z = 0.6 m
+    ys, xs = np.nonzero(fg)                                                             # centred in its own window
+    assert abs(xs.mean() - 88) < 6 and abs(ys.mean() - 88) < 6
+    # the same object twice as far away covers a quarter of the pixels of a window that is half as large in pixels ... i.e. the same share
+    pose2 = pose.copy(); pose2[:3, 3] *= 2
+    _, dep2 = O.render_window(pose2, synth.CAMERA_K, 200.0, mesh)
+    assert abs((dep2 > 0).sum() - fg.sum()) < 0.05 * fg.sum()
+    # front-most surface wins: every depth is no farther than the object's centre plus its smallest half-extent
+    assert (dep[fg] <= 600 + 26).all()
+    # degenerate window -> empty image
+    rgb0, dep0 = O.render_window(pose, synth.CAMERA_K, 0.0, mesh)
+    assert rgb0.max() == 0 and dep0.max() == 0
