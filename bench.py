@@ -41,6 +41,7 @@ def parse():
     ap.add_argument('--no-alt', action='store_true', help='skip the secondary precision-mode measurements')
     ap.add_argument('--weight-sets', type=int, default=1, help='object classes (one checkpoint each, reference README.md:132); track i uses set i*G//batch')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-render', action='store_true', help='skip the step-with-rendered-input-A measurement')
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     return ap.parse_args()
 
@@ -362,6 +363,39 @@ def main():
            'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(pinned_out.numel() * 8),
            'api': 'Tracker.on_track_batch (pinned host tensors in, pinned host poses out; wall clock over the K calls incl. all copies; uploads of call k overlap the kernels of call k-1 on a side stream)'}
 
+    # ---- (3b) the same step with input A RENDERED on the device instead of taken from HBM ----------
+    render = None
+    if rank == 0 and world == 1 and not args.no_render:
+        mesh = synth.mesh(5, seed=0)                       # 20,480 faces / 10,242 vertices
+        eng.set_mesh(mesh, 0)
+        rgbA_buf = torch.empty((nb, 176, 176, 3), dtype=torch.uint8, device=dev)
+        depA_buf = torch.empty((nb, 176, 176), dtype=torch.uint16, device=dev)
+
+        def render_step(k):
+            d = sets[k % N_INPUT_SETS][1]
+            eng.render(synth.CAMERA_K, d['poses'], ow, None, rgbA_buf, depA_buf)
+            return tracker.step(d['rgb'], d['depth'], d['poses'], rgbA_buf, depA_buf, gather=False)
+        for k in range(3):
+            render_step(k)
+        sync_all()
+        rsteps = min(args.steps, 20)
+        rev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(rsteps)]
+        for k in range(rsteps):
+            flush.zero_()
+            rev[k][0].record(); render_step(k); rev[k][1].record()
+        sync_all()
+        rms = float(np.mean([a.elapsed_time(b) for a, b in rev]))
+        eng.set_profiling(True)
+        acc = []
+        for k in range(5):
+            d = sets[k % N_INPUT_SETS][1]
+            eng.render(synth.CAMERA_K, d['poses'], ow, None, rgbA_buf, depA_buf); acc.append(eng.get_profile()[20])
+        eng.set_profiling(False)
+        kms = float(np.mean(acc))
+        render = {'mesh_faces': int(len(mesh['faces'])), 'mesh_vertices': int(len(mesh['pos'])), 'render_kernel_ms': kms,
+                  'renders_per_s': nb / (kms * 1e-3), 'step_with_render_ms': rms, 'pairs_per_s_with_render': nb / (rms * 1e-3),
+                  'note': 'render_kernel (csrc/render.cu): %d tracks x 176x176, float64 visibility + shading, one launch; replaces the reference\'s two OpenGL renders + glReadPixels per track and frame' % nb}
+
     clocks = None
     if sampler:
         sampler.stop_flag = True; time.sleep(0.15)
@@ -392,7 +426,7 @@ def main():
                            'l2': 'flushed between timed steps (256 MiB memset, untimed); %d rotating input sets; per-step CUDA events, max over ranks' % N_INPUT_SETS,
                            'weights': 'random-init (seeded), %d weight set(s)%s' % (G, '' if G == 1 else ' (one per object class; all classes batched into the same 14 conv launches)')},
                 'gpu_launches': int(launches), 'launches_per_step': int(launches // max(args.steps, 1)),
-                'roofline': roofline, 'alt_precisions': alt, 'parity': parity, 'cpu_baseline': cpu, 'e2e': e2e, 'clocks': clocks,
+                'roofline': roofline, 'alt_precisions': alt, 'parity': parity, 'cpu_baseline': cpu, 'e2e': e2e, 'render': render, 'clocks': clocks,
                 'ms_per_step_min': float(ms_steps.min()), 'ms_per_step_median': float(np.median(ms_steps))}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -125,6 +125,17 @@ class Tracker:
         self.engine.set_stats(np.asarray(images_mean), np.asarray(images_std), weight_id)
         U.set_engine(self.engine)
 
+        # Input A.  renderer='cuda' (or nothing, with a .ply model that has normals + colours): the CUDA rasteriser
+        # (csrc/render.cu) -- no OpenGL, all tracks in one launch.  Otherwise an object with render_window(ob2cam), or the
+        # reference's own OpenGL renderers when they are importable.
+        if renderer == 'cuda' or (renderer is None and model_path is not None and str(model_path).lower().endswith('.ply')):
+            from .cuda_renderer import CudaRenderer
+            try:
+                renderer = CudaRenderer(model_path, self.K, self.engine, self.object_width, mesh_id=weight_id)
+            except ValueError:
+                if renderer == 'cuda':
+                    raise
+                renderer = None                                    # e.g. a vertices-only ply: fall through to the GL renderers
         self.renderer = renderer if renderer is not None else self._try_reference_renderer(model_path, cam_cfg)
         self.prev_rgb = None
         self.prev_depth = None
@@ -191,8 +202,9 @@ class Tracker:
         self.frame_cnt += 1
         return final_estimate
 
-    def on_track_batch(self, prev_poses, current_rgb, current_depth, rgbA, depthA, weight_ids=None, object_width=None):
-        """N independent tracks of ONE frame -> (N,4,4) float64.
+    def on_track_batch(self, prev_poses, current_rgb, current_depth, rgbA=None, depthA=None, weight_ids=None, object_width=None):
+        """N independent tracks of ONE frame -> (N,4,4) float64.  rgbA / depthA None: rendered on the device by the CUDA
+        rasteriser (needs a CudaRenderer; per-track models follow weight_ids).
 
         numpy inputs   -> numpy result (synchronous, like the reference's on_track).
         CUDA tensors   -> CUDA tensor, nothing is synchronised.
@@ -201,7 +213,10 @@ class Tracker:
                           makes them truly asynchronous).  Nothing is synchronised."""
         dev = self.engine.device
         as_numpy = not torch.is_tensor(prev_poses)
-        staged = all(torch.is_tensor(x) and not x.is_cuda for x in (prev_poses, current_rgb, current_depth, rgbA, depthA))
+        render = rgbA is None or depthA is None
+        if render and not hasattr(self.renderer, 'render_batch'):
+            raise RuntimeError('on_track_batch without rgbA/depthA needs the CUDA renderer (Tracker(renderer="cuda", model_path=*.ply))')
+        staged = not render and all(torch.is_tensor(x) and not x.is_cuda for x in (prev_poses, current_rgb, current_depth, rgbA, depthA))
 
         def up(x, dt):
             if torch.is_tensor(x):
@@ -216,9 +231,15 @@ class Tracker:
         else:
             poses = up(prev_poses, torch.float64)
             rgb_d, depth_d = up(current_rgb, torch.uint8), up(current_depth, torch.uint16)
-            rgbA_d, depthA_d = up(rgbA, torch.uint8), up(depthA, torch.uint16)
+            if not render:
+                rgbA_d, depthA_d = up(rgbA, torch.uint8), up(depthA, torch.uint16)
         n = poses.shape[0]
         ow = torch.full((n,), float(self.object_width), dtype=torch.float64, device=dev) if object_width is None else up(object_width, torch.float64)
+        if render:
+            mids = None
+            if weight_ids is not None:
+                mids = (weight_ids if torch.is_tensor(weight_ids) else torch.as_tensor(np.asarray(weight_ids))).to(dev, torch.int32)
+            rgbA_d, depthA_d = self.renderer.render_batch(poses, ow, mids)
         wh = None
         if weight_ids is not None:
             wh = np.ascontiguousarray(weight_ids.cpu().numpy() if torch.is_tensor(weight_ids) else weight_ids, dtype=np.int32)

@@ -473,3 +473,41 @@ def test_render_feeds_track_batch(pkg, synth, eng):
         ra, da = O.render_window(poses[i], K, 200.0, mesh)
         ref = O.on_track(sd, poses[i], rgb, depth, ra, da, K, 200.0, mean, std, 0.03, 5 * np.pi / 180)
         assert np.abs(out_poses[i].cpu().numpy() - ref).max() < POSE_ATOL
+
+
+def test_tracker_with_cuda_renderer(pkg, synth, tmp_path):
+    """The reference's loop shape -- Tracker(model_path=*.ply) ; on_track(prev_pose, rgb, depth) renders input A itself
+    (predict.py:229-231) -- with the CUDA rasteriser standing in for VispyRenderer."""
+    mio = importlib.import_module('iros20-6d-pose-tracking_b200.mesh_io')
+    mesh = synth.mesh(3, seed=0)
+    ply = str(tmp_path / 'textured.ply')
+    mio.save_ply_mesh(ply, mesh)
+    mesh = mio.load_ply_mesh(ply)                                   # what both sides see (normals re-normalised on load)
+    info = {'resolution': 176, 'object_width': 200.0, 'boundingbox': 10,
+            'camera': {'focalX': synth.CAMERA_K[0, 0], 'focalY': synth.CAMERA_K[1, 1], 'centerX': synth.CAMERA_K[0, 2], 'centerY': synth.CAMERA_K[1, 2],
+                       'height': 480, 'width': 640}}
+    mean, std = synth.default_mean_std()
+    sd = synth.make_state_dict(0)
+    trk = pkg.Tracker(info, mean, std, {'state_dict': sd}, model_path=ply, max_batch=8)
+    assert type(trk.renderer).__name__ == 'CudaRenderer' and trk.object_cloud is not None
+    rgb, depth = synth.raw_frame(seed=4)
+    poses = synth.raw_poses(3, seed=8)
+    K = synth.CAMERA_K
+    ra, da = trk.render_window(poses[0])
+    ora, oda = O.render_window(poses[0], K, 200.0, mesh)
+    assert ra.dtype == np.uint8 and da.dtype == np.uint16 and np.array_equal(ra, ora) and np.array_equal(da, oda)
+    new = trk.on_track(poses[0], rgb, depth)
+    ref = O.on_track(sd, poses[0], rgb, depth, ora, oda, K, 200.0, mean, std, 0.03, 5 * np.pi / 180)
+    assert new.shape == (4, 4) and np.abs(new - ref).max() < POSE_ATOL
+    # all tracks of a frame, input A rendered on the device
+    out = trk.on_track_batch(poses, rgb, depth)
+    for i in range(3):
+        oa, od = O.render_window(poses[i], K, 200.0, mesh)
+        ref = O.on_track(sd, poses[i], rgb, depth, oa, od, K, 200.0, mean, std, 0.03, 5 * np.pi / 180)
+        assert np.abs(out[i] - ref).max() < POSE_ATOL
+    # a chain of frames stays on the device: poses out -> poses in
+    P = torch.from_numpy(poses).cuda(); R = torch.from_numpy(rgb).cuda(); D = torch.from_numpy(depth).cuda()
+    for _ in range(3):
+        P = trk.on_track_batch(P, R, D)
+    assert P.is_cuda and torch.isfinite(P).all()
+    trk.engine.close()

@@ -1,0 +1,58 @@
+"""CAD-model file handling for the CUDA rasteriser (host logic, no GPU)."""
+import importlib, os
+import numpy as np
+import pytest
+
+
+@pytest.fixture(scope='module')
+def mio():
+    return importlib.import_module('iros20-6d-pose-tracking_b200.mesh_io')
+
+
+@pytest.mark.parametrize('binary', [True, False])
+def test_ply_round_trip(mio, synth, tmp_path, binary):
+    m = synth.mesh(2, seed=3)
+    p = str(tmp_path / 'model.ply')
+    mio.save_ply_mesh(p, m, binary=binary)
+    r = mio.load_ply_mesh(p)
+    assert r['pos'].dtype == np.float32 and r['nrm'].dtype == np.float32 and r['col'].dtype == np.uint8 and r['faces'].dtype == np.int32
+    assert np.array_equal(r['pos'], m['pos']) and np.array_equal(r['col'], m['col']) and np.array_equal(r['faces'], m['faces'])
+    assert np.abs(r['nrm'] - m['nrm']).max() <= 2 ** -22          # the loader re-normalises in float32 (vispy_renderer.py:121)
+    assert np.allclose(np.linalg.norm(r['nrm'], axis=1), 1.0, atol=1e-6)
+    # the vertices-only reader Tracker uses for object_cloud sees the same points
+    pr = importlib.import_module('iros20-6d-pose-tracking_b200.predict')
+    assert np.array_equal(pr.load_vertices(p).astype(np.float32), m['pos'])
+
+
+def test_ply_rejects_what_the_reference_rejects(mio, synth, tmp_path):
+    m = synth.mesh(0)
+    p = str(tmp_path / 'no_normals.ply')
+    with open(p, 'w') as f:                                         # positions + faces only
+        f.write('ply\nformat ascii 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\n'
+                'element face %d\nproperty list uchar int vertex_indices\nend_header\n' % (len(m['pos']), len(m['faces'])))
+        for v in m['pos']: f.write('%g %g %g\n' % tuple(v))
+        for t in m['faces']: f.write('3 %d %d %d\n' % tuple(t))
+    with pytest.raises(ValueError, match='nx'):
+        mio.load_ply_mesh(p)
+    q = str(tmp_path / 'quads.ply')
+    with open(q, 'w') as f:
+        f.write('ply\nformat ascii 1.0\nelement vertex 4\nproperty float x\nproperty float y\nproperty float z\nproperty float nx\n'
+                'property float ny\nproperty float nz\nproperty uchar red\nproperty uchar green\nproperty uchar blue\n'
+                'element face 1\nproperty list uchar int vertex_indices\nend_header\n')
+        for i in range(4): f.write('%d %d 0 0 0 1 9 9 9\n' % (i & 1, i >> 1))
+        f.write('4 0 1 3 2\n')
+    with pytest.raises(ValueError):
+        mio.load_ply_mesh(q)
+    with pytest.raises(ValueError):
+        mio.load_ply_mesh(__file__)
+
+
+def test_synth_mesh_is_closed_and_outward(synth):
+    m = synth.mesh(2)
+    f = m['faces']
+    edges = np.sort(np.concatenate((f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]])), axis=1)
+    _, cnt = np.unique(edges, axis=0, return_counts=True)
+    assert (cnt == 2).all() and len(f) == 20 * 4 ** 2                # watertight
+    fn = np.cross(m['pos'][f[:, 1]] - m['pos'][f[:, 0]], m['pos'][f[:, 2]] - m['pos'][f[:, 0]])
+    assert ((fn * m['pos'][f].mean(1)).sum(1) > 0).all()            # counter-clockwise seen from outside
+    assert ((m['nrm'] * m['pos']).sum(1) > 0).all()
