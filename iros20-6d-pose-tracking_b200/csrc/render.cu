@@ -6,16 +6,22 @@
 // for all tracks of a frame in one launch, straight into the buffers the preprocess kernel reads -- no GL context, no
 // glReadPixels, no host round trip.
 //
-// Pipeline (one CTA per (track, band of 44 image rows); grid = 4 x n):
-//   0. thread 0 builds the uniforms in float64 exactly as numpy does (window via bbox.cuh, orthographic matrix rounded to
-//      float32, projection product, light = R_gl * (0, .1, -.9) which is what inv(view^T) * (0,.1,-.9,1) evaluates to).
-//   1. visibility: triangles are dealt to threads; each projects its three vertices (float64 on the float32 uniforms),
-//      snaps them to 1/256 pixel, walks the pixel centres of its bounding box with exact integer edge functions
+// Pipeline, two launches chained by programmatic dependent launch:
+//   A. render_project_kernel (grid = vertex blocks x n): thread 0 of every CTA builds the track's uniforms in float64 exactly
+//      as numpy does (window via bbox.cuh, orthographic matrix rounded to float32, projection product, light = R_gl *
+//      (0, .1, -.9) which is what inv(view^T) * (0,.1,-.9,1) evaluates to); every thread projects ONE vertex (float64 on the
+//      float32 uniforms), snaps it to 1/256 pixel and stores {X, Y, z_window, 1/w} (24 B) -- each vertex is projected once per
+//      track instead of ~6 times per band.
+//   B. render_kernel (one CTA per (track, set of every 4th image row); grid = 4 x n -- interleaved rows, so the four CTAs
+//      of a track share the object's pixels evenly wherever it sits in the window):
+//   1. visibility: triangles are dealt to threads; each gathers its three projected vertices,
+//      walks the pixel centres of its bounding box with exact integer edge functions
 //      (top-left rule, no culling -- the reference never enables GL_CULL_FACE), interpolates window z and does a 64-bit
 //      shared-memory atomicMin on (float32 z bits << 32 | triangle index): depth test LESS, first-drawn wins ties.
 //      Triangles with large boxes are rasterised by the whole warp.
 //   2. resolve: one thread per pixel re-derives its triangle's barycentrics, interpolates position / normal / colour
 //      perspective-correctly, shades, converts the depth the way on_draw does and writes uint8 rgb + uint16 mm.
+// Divisions are confined to reciprocals (1/w per vertex, 1/area per triangle, 1/sum(q) and 1/|l| per pixel), as GPUs do.
 // All arithmetic is float64 with a fixed association and this file is compiled with -fmad=false, so it is bit-identical
 // to the numpy restatement in oracle/se3_oracle.py (render_window).  Scope limits (documented in DESIGN.md): no
 // near-plane polygon clipping (a triangle with a vertex at w <= 1e-6 is dropped; the tracking volume is 0.4-2 m, near =
@@ -23,6 +29,7 @@
 #include "render.h"
 #include "bbox.cuh"
 #include "ptx.cuh"
+#include <climits>
 
 namespace se3tn {
 namespace {
@@ -45,6 +52,7 @@ __device__ __forceinline__ long long floor_div(long long a, long long b) {      
 }
 
 struct Vtx { long long X, Y; double zw, w; bool ok; };
+struct PVtx { int X, Y; double zw, iw; };         // stored form (iw = 1/w); X == INT_MIN marks a vertex that cannot be used (w <= 1e-6, non-finite)
 
 __device__ __forceinline__ Vtx project(const Uniforms& u, const float* __restrict__ pos, int vi) {
     const double px = pos[3 * vi], py = pos[3 * vi + 1], pz = pos[3 * vi + 2];
@@ -62,10 +70,16 @@ __device__ __forceinline__ Vtx project(const Uniforms& u, const float* __restric
     const double xw = (c0 / c3 + 1.0) * (kRS * 0.5), yw = (c1 / c3 + 1.0) * (kRS * 0.5);
     r.zw = (c2 / c3 + 1.0) * 0.5;
     const double X = rint(xw * kSub), Y = rint(yw * kSub);
-    const double lim = 1073741824.0;
+    const double lim = 33554432.0;                   // 2^25 sub-pixels: every edge-function product stays below 2^53, exact in float64
     r.ok = (c3 > 1e-6) && (X == X) && (Y == Y) && fabs(X) < lim && fabs(Y) < lim;
     r.X = r.ok ? static_cast<long long>(X) : 0;
     r.Y = r.ok ? static_cast<long long>(Y) : 0;
+    return r;
+}
+
+__device__ __forceinline__ Vtx load_projected(const PVtx* __restrict__ pv, int vi) {
+    const PVtx q = pv[vi];
+    Vtx r; r.ok = q.X != INT_MIN; r.X = q.X; r.Y = q.Y; r.zw = q.zw; r.w = q.iw;
     return r;
 }
 
@@ -76,13 +90,13 @@ struct Tri {
     bool ok;
 };
 
-__device__ __forceinline__ Tri setup(const Uniforms& u, const MeshDev& m, int t) {
+__device__ __forceinline__ Tri setup(const PVtx* __restrict__ pv, const MeshDev& m, int t) {     // T.w* hold 1/w
     Tri T;
     T.i0 = m.faces[3 * t]; T.i1 = m.faces[3 * t + 1]; T.i2 = m.faces[3 * t + 2];
     T.ok = static_cast<unsigned>(T.i0) < static_cast<unsigned>(m.nv) && static_cast<unsigned>(T.i1) < static_cast<unsigned>(m.nv) &&
            static_cast<unsigned>(T.i2) < static_cast<unsigned>(m.nv);
     if (!T.ok) return T;
-    const Vtx a = project(u, m.pos, T.i0), b = project(u, m.pos, T.i1), c = project(u, m.pos, T.i2);
+    const Vtx a = load_projected(pv, T.i0), b = load_projected(pv, T.i1), c = load_projected(pv, T.i2);
     T.ok = a.ok && b.ok && c.ok;
     if (!T.ok) return T;
     T.x0 = a.X; T.y0 = a.Y; T.z0 = a.zw; T.w0 = a.w;
@@ -99,46 +113,43 @@ __device__ __forceinline__ Tri setup(const Uniforms& u, const MeshDev& m, int t)
     return T;
 }
 
-__device__ __forceinline__ void edges(const Tri& T, long long cx, long long cy, long long& e0, long long& e1, long long& e2) {
-    e0 = (T.x2 - T.x1) * (cy - T.y1) - (T.y2 - T.y1) * (cx - T.x1);
-    e1 = (T.x0 - T.x2) * (cy - T.y2) - (T.y0 - T.y2) * (cx - T.x2);
-    e2 = (T.x1 - T.x0) * (cy - T.y0) - (T.y1 - T.y0) * (cx - T.x0);
+// Edge functions in float64: coordinates are integers below 2^25 in magnitude, so differences (< 2^26), products (< 2^52)
+// and their difference are exact -- the same values the int64 evaluation gives, at one DMUL instead of a multi-word multiply.
+struct EdgeSet { double dx0, dy0, dx1, dy1, dx2, dy2, x0, y0, x1, y1, x2, y2; };
+__device__ __forceinline__ EdgeSet edge_set(const Tri& T) {
+    EdgeSet E;
+    E.x0 = static_cast<double>(T.x0); E.y0 = static_cast<double>(T.y0); E.x1 = static_cast<double>(T.x1); E.y1 = static_cast<double>(T.y1);
+    E.x2 = static_cast<double>(T.x2); E.y2 = static_cast<double>(T.y2);
+    E.dx0 = E.x2 - E.x1; E.dy0 = E.y2 - E.y1; E.dx1 = E.x0 - E.x2; E.dy1 = E.y0 - E.y2; E.dx2 = E.x1 - E.x0; E.dy2 = E.y1 - E.y0;
+    return E;
+}
+__device__ __forceinline__ void edges(const EdgeSet& E, double cx, double cy, double& e0, double& e1, double& e2) {
+    e0 = E.dx0 * (cy - E.y1) - E.dy0 * (cx - E.x1);
+    e1 = E.dx1 * (cy - E.y2) - E.dy1 * (cx - E.x2);
+    e2 = E.dx2 * (cy - E.y0) - E.dy2 * (cx - E.x0);
 }
 __device__ __forceinline__ bool top_left(long long dx, long long dy) { return dy < 0 || (dy == 0 && dx < 0); }
 
-__device__ __forceinline__ void raster_pixel(const Tri& T, int t, int i, int j, int j_lo, bool tl0, bool tl1, bool tl2, unsigned long long* keys) {
-    const long long cx = static_cast<long long>(i) * kSub + kHalf, cy = static_cast<long long>(j) * kSub + kHalf;
-    long long e0, e1, e2;
-    edges(T, cx, cy, e0, e1, e2);
+// one pixel centre against one triangle.  Rows are interleaved over the four CTAs of a track: this CTA owns rows j = 4*jj + band.
+__device__ __forceinline__ void raster_pixel(const Tri& T, const EdgeSet& E, double inv_area, int t, int i, int j, bool tl0, bool tl1, bool tl2, unsigned long long* keys) {
+    const double cx = static_cast<double>(i * kSub + kHalf), cy = static_cast<double>(j * kSub + kHalf);
+    double e0, e1, e2;
+    edges(E, cx, cy, e0, e1, e2);
     if (!((e0 > 0 || (e0 == 0 && tl0)) && (e1 > 0 || (e1 == 0 && tl1)) && (e2 > 0 || (e2 == 0 && tl2)))) return;
-    const double ar = static_cast<double>(T.area2);
-    const double l0 = static_cast<double>(e0) / ar, l1 = static_cast<double>(e1) / ar, l2 = static_cast<double>(e2) / ar;
+    const double l0 = e0 * inv_area, l1 = e1 * inv_area, l2 = e2 * inv_area;
     const double z = (l0 * T.z0 + l1 * T.z1) + l2 * T.z2;
     const float z32 = static_cast<float>(z);
     if (!(z32 >= 0.f && z32 < 1.f)) return;           // depth clip; LESS against the cleared 1.0
     const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(z32)) << 32) | static_cast<unsigned>(t);
-    atomicMin(&keys[(j - j_lo) * kRS + i], key);
+    atomicMin(&keys[(j >> 2) * kRS + i], key);
 }
 
-__global__ void __launch_bounds__(kRenderThreads)
-render_kernel(RenderArgs a)
-{
-    extern __shared__ unsigned long long keys[];            // [kBandRows][kRS]
-    __shared__ Uniforms u;
-    ptx::grid_dep_launch();
-    const int n = blockIdx.y, band = blockIdx.x;
-    const int j_lo = band * kBandRows, j_hi = j_lo + kBandRows - 1;
-    for (int k = threadIdx.x; k < kBandRows * kRS; k += blockDim.x) keys[k] = kClearKey;
-    ptx::grid_dep_wait();                                    // poses come from the previous step's pose update
-    int mid = a.mesh_ids ? a.mesh_ids[n] : 0;
-    if (mid < 0 || mid >= a.n_meshes) mid = 0;
-    const MeshDev m = a.meshes[mid];
-    if (threadIdx.x == 0) {
+__device__ void make_uniforms(const RenderArgs& a, int n, int nf, Uniforms& u) {
         const double* pose = a.poses + n * 16;
         int top, left, ch, cw;
         bbox_window(pose, a.fx, a.fy, a.cx, a.cy, a.object_width[n], 1000.0, -1000.0, 1000.0, top, left, ch, cw);   // predict.py:202
         const int right = left + cw, bottom = top + ch;
-        u.valid = (cw != 0 && ch != 0 && m.nf > 0) ? 1 : 0;
+        u.valid = (cw != 0 && ch != 0 && nf > 0) ? 1 : 0;
         // view = inv(glcam_in_cvcam) . ob2cam (rows 1, 2 negated), uploaded as float32
         for (int c = 0; c < 4; ++c) {
             u.V[c] = static_cast<double>(static_cast<float>(pose[c]));
@@ -163,26 +174,92 @@ render_kernel(RenderArgs a)
             u.light[r] = static_cast<double>(static_cast<float>((r0 * 0.0 + r1 * 0.1) + r2 * (-0.9)));
         }
     }
+
+constexpr int kProjThreads = 256;
+__global__ void __launch_bounds__(kProjThreads)
+render_project_kernel(RenderArgs a)
+{
+    __shared__ Uniforms u;
+    ptx::grid_dep_launch();
+    const int n = blockIdx.y;
+    ptx::grid_dep_wait();                                    // poses come from the previous step's pose update
+    int mid = a.mesh_ids ? a.mesh_ids[n] : 0;
+    if (mid < 0 || mid >= a.n_meshes) mid = 0;
+    const MeshDev m = a.meshes[mid];
+    if (static_cast<int>(blockIdx.x * blockDim.x) >= m.nv && blockIdx.x != 0) return;
+    if (threadIdx.x == 0) make_uniforms(a, n, m.nf, u);
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x < sizeof(Uniforms) / sizeof(double))          // one copy per track for render_kernel
+        reinterpret_cast<double*>(a.uniforms + static_cast<size_t>(n) * sizeof(Uniforms))[threadIdx.x] = reinterpret_cast<const double*>(&u)[threadIdx.x];
+    const int vi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (vi >= m.nv) return;
+    PVtx q; q.X = INT_MIN; q.Y = 0; q.zw = 0; q.iw = 0;
+    if (u.valid) {
+        const Vtx v = project(u, m.pos, vi);
+        if (v.ok) { q.X = static_cast<int>(v.X); q.Y = static_cast<int>(v.Y); q.zw = v.zw; q.iw = 1.0 / v.w; }
+    }
+    reinterpret_cast<PVtx*>(a.projected)[static_cast<size_t>(n) * a.max_nv + vi] = q;
+}
+
+__global__ void __launch_bounds__(kRenderThreads, 2)
+render_kernel(RenderArgs a)
+{
+    extern __shared__ unsigned long long keys[];            // [kBandRows][kRS]: rows band, band + 4, band + 8, ...
+    __shared__ Uniforms u;
+    ptx::grid_dep_launch();
+    const int n = blockIdx.y, band = blockIdx.x;
+    for (int k = threadIdx.x; k < kBandRows * kRS; k += blockDim.x) keys[k] = kClearKey;
+    ptx::grid_dep_wait();                                    // projected vertices + uniforms come from render_project_kernel
+    int mid = a.mesh_ids ? a.mesh_ids[n] : 0;
+    if (mid < 0 || mid >= a.n_meshes) mid = 0;
+    const MeshDev m = a.meshes[mid];
+    const PVtx* __restrict__ pv = reinterpret_cast<const PVtx*>(a.projected) + static_cast<size_t>(n) * a.max_nv;
+    if (threadIdx.x < sizeof(Uniforms) / sizeof(double))
+        reinterpret_cast<double*>(&u)[threadIdx.x] = reinterpret_cast<const double*>(a.uniforms + static_cast<size_t>(n) * sizeof(Uniforms))[threadIdx.x];
     __syncthreads();
     const int lane = threadIdx.x & 31;
+    // first row >= ja that this CTA owns
+    auto first_row = [band](int ja) { return ja + ((band - (ja & 3)) & 3); };
     if (u.valid) {
         // ---------------- pass 1: visibility ----------------
         const int nf_pad = (m.nf + 31) & ~31;                // whole warps walk the loop (ballots below)
+        // the rows of triangle t decide whether this CTA has to look at it at all (three 4-byte loads instead of the full set-up);
+        // they are fetched one iteration ahead so the two dependent L2 round trips overlap the previous triangle's work
+        auto fetch_rows = [&](int t, int& y0, int& y1, int& y2) -> bool {
+            if (t >= m.nf) return false;
+            const unsigned i0 = m.faces[3 * t], i1 = m.faces[3 * t + 1], i2 = m.faces[3 * t + 2];
+            if (!(i0 < static_cast<unsigned>(m.nv) && i1 < static_cast<unsigned>(m.nv) && i2 < static_cast<unsigned>(m.nv))) return false;
+            y0 = pv[i0].Y; y1 = pv[i1].Y; y2 = pv[i2].Y;
+            return true;
+        };
+        int ny0 = 0, ny1 = 0, ny2 = 0;
+        bool nvalid = fetch_rows(threadIdx.x, ny0, ny1, ny2);
         for (int t = threadIdx.x; t < nf_pad; t += blockDim.x) {
             bool big = false;
-            if (t < m.nf) {
-                const Tri T = setup(u, m, t);
+            bool mine = false;
+            const bool valid = nvalid; const int y0 = ny0, y1 = ny1, y2 = ny2;
+            nvalid = fetch_rows(t + blockDim.x, ny0, ny1, ny2);
+            if (valid) {
+                const long long mny = min(y0, min(y1, y2)), mxy = max(y0, max(y1, y2));
+                const long long ja = max(0ll, floor_div(mny - kHalf + kSub - 1, kSub)), jb = min(static_cast<long long>(kRS - 1), floor_div(mxy - kHalf, kSub));
+                mine = ja <= jb && first_row(static_cast<int>(ja)) <= jb;
+            }
+            if (mine) {
+                const Tri T = setup(pv, m, t);
                 if (T.ok) {
                     const long long mnx = min(T.x0, min(T.x1, T.x2)), mxx = max(T.x0, max(T.x1, T.x2));
                     const long long mny = min(T.y0, min(T.y1, T.y2)), mxy = max(T.y0, max(T.y1, T.y2));
                     const int ia = static_cast<int>(max(0ll, floor_div(mnx - kHalf + kSub - 1, kSub))), ib = static_cast<int>(min(static_cast<long long>(kRS - 1), floor_div(mxx - kHalf, kSub)));
-                    const int ja = static_cast<int>(max(static_cast<long long>(j_lo), floor_div(mny - kHalf + kSub - 1, kSub))), jb = static_cast<int>(min(static_cast<long long>(j_hi), floor_div(mxy - kHalf, kSub)));
-                    if (ia <= ib && ja <= jb) {
-                        if ((ib - ia + 1) * (jb - ja + 1) > kBigBox) big = true;
+                    const int ja = static_cast<int>(max(0ll, floor_div(mny - kHalf + kSub - 1, kSub))), jb = static_cast<int>(min(static_cast<long long>(kRS - 1), floor_div(mxy - kHalf, kSub)));
+                    const int j0 = first_row(ja);
+                    if (ia <= ib && j0 <= jb) {
+                        if ((ib - ia + 1) * ((jb - j0) / 4 + 1) > kBigBox) big = true;
                         else {
                             const bool tl0 = top_left(T.x2 - T.x1, T.y2 - T.y1), tl1 = top_left(T.x0 - T.x2, T.y0 - T.y2), tl2 = top_left(T.x1 - T.x0, T.y1 - T.y0);
-                            for (int j = ja; j <= jb; ++j)
-                                for (int i = ia; i <= ib; ++i) raster_pixel(T, t, i, j, j_lo, tl0, tl1, tl2, keys);
+                            const double inv_area = 1.0 / static_cast<double>(T.area2);
+                            const EdgeSet E = edge_set(T);
+                            for (int j = j0; j <= jb; j += 4)
+                                for (int i = ia; i <= ib; ++i) raster_pixel(T, E, inv_area, t, i, j, tl0, tl1, tl2, keys);
                         }
                     }
                 }
@@ -191,14 +268,17 @@ render_kernel(RenderArgs a)
             while (bigmask) {                                // large triangles: the whole warp walks the bounding box
                 const int src = __ffs(bigmask) - 1; bigmask &= bigmask - 1;
                 const int tb = __shfl_sync(0xffffffffu, t, src);
-                const Tri T = setup(u, m, tb);
+                const Tri T = setup(pv, m, tb);
                 const long long mnx = min(T.x0, min(T.x1, T.x2)), mxx = max(T.x0, max(T.x1, T.x2));
                 const long long mny = min(T.y0, min(T.y1, T.y2)), mxy = max(T.y0, max(T.y1, T.y2));
                 const int ia = static_cast<int>(max(0ll, floor_div(mnx - kHalf + kSub - 1, kSub))), ib = static_cast<int>(min(static_cast<long long>(kRS - 1), floor_div(mxx - kHalf, kSub)));
-                const int ja = static_cast<int>(max(static_cast<long long>(j_lo), floor_div(mny - kHalf + kSub - 1, kSub))), jb = static_cast<int>(min(static_cast<long long>(j_hi), floor_div(mxy - kHalf, kSub)));
+                const int ja = static_cast<int>(max(0ll, floor_div(mny - kHalf + kSub - 1, kSub))), jb = static_cast<int>(min(static_cast<long long>(kRS - 1), floor_div(mxy - kHalf, kSub)));
+                const int j0 = first_row(ja);
                 const bool tl0 = top_left(T.x2 - T.x1, T.y2 - T.y1), tl1 = top_left(T.x0 - T.x2, T.y0 - T.y2), tl2 = top_left(T.x1 - T.x0, T.y1 - T.y0);
-                const int bw = ib - ia + 1, cnt = bw * (jb - ja + 1);
-                for (int k = lane; k < cnt; k += 32) raster_pixel(T, tb, ia + k % bw, ja + k / bw, j_lo, tl0, tl1, tl2, keys);
+                const double inv_area = 1.0 / static_cast<double>(T.area2);
+                const EdgeSet E = edge_set(T);
+                const int bw = ib - ia + 1, cnt = bw * ((jb - j0) / 4 + 1);
+                for (int k = lane; k < cnt; k += 32) raster_pixel(T, E, inv_area, tb, ia + k % bw, j0 + 4 * (k / bw), tl0, tl1, tl2, keys);
             }
         }
     }
@@ -206,30 +286,29 @@ render_kernel(RenderArgs a)
     // ---------------- pass 2: resolve + shade ----------------
     const double far_dist = u.B / (u.A + 1.0);
     for (int k = threadIdx.x; k < kBandRows * kRS; k += blockDim.x) {
-        const int j = j_lo + k / kRS, i = k % kRS;
+        const int j = 4 * (k / kRS) + band, i = k % kRS;
         const unsigned long long key = keys[k];
         const unsigned t = static_cast<unsigned>(key & 0xFFFFFFFFull);
         unsigned r8 = 0, g8 = 0, b8 = 0, mm = 0;
         if (u.valid && t != 0xFFFFFFFFu) {
-            const Tri T = setup(u, m, static_cast<int>(t));
-            const long long cx = static_cast<long long>(i) * kSub + kHalf, cy = static_cast<long long>(j) * kSub + kHalf;
-            long long e0, e1, e2;
-            edges(T, cx, cy, e0, e1, e2);
-            const double ar = static_cast<double>(T.area2);
-            const double l0 = static_cast<double>(e0) / ar, l1 = static_cast<double>(e1) / ar, l2 = static_cast<double>(e2) / ar;
-            const double q0 = l0 / T.w0, q1 = l1 / T.w1, q2 = l2 / T.w2;
-            const double qs = (q0 + q1) + q2;
+            const Tri T = setup(pv, m, static_cast<int>(t));
+            double e0, e1, e2;
+            edges(edge_set(T), static_cast<double>(i * kSub + kHalf), static_cast<double>(j * kSub + kHalf), e0, e1, e2);
+            const double inv_area = 1.0 / static_cast<double>(T.area2);
+            const double l0 = e0 * inv_area, l1 = e1 * inv_area, l2 = e2 * inv_area;
+            const double q0 = l0 * T.w0, q1 = l1 * T.w1, q2 = l2 * T.w2;       // T.w* = 1/w: perspective-correct weights
+            const double rq = 1.0 / ((q0 + q1) + q2);
             double pos[3], nrm[3], col[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                pos[c] = ((q0 * static_cast<double>(m.pos[3 * T.i0 + c]) + q1 * static_cast<double>(m.pos[3 * T.i1 + c])) + q2 * static_cast<double>(m.pos[3 * T.i2 + c])) / qs;
-                nrm[c] = ((q0 * static_cast<double>(m.nrm[3 * T.i0 + c]) + q1 * static_cast<double>(m.nrm[3 * T.i1 + c])) + q2 * static_cast<double>(m.nrm[3 * T.i2 + c])) / qs;
+                pos[c] = ((q0 * static_cast<double>(m.pos[3 * T.i0 + c]) + q1 * static_cast<double>(m.pos[3 * T.i1 + c])) + q2 * static_cast<double>(m.pos[3 * T.i2 + c])) * rq;
+                nrm[c] = ((q0 * static_cast<double>(m.nrm[3 * T.i0 + c]) + q1 * static_cast<double>(m.nrm[3 * T.i1 + c])) + q2 * static_cast<double>(m.nrm[3 * T.i2 + c])) * rq;
                 const double c0 = static_cast<float>(m.col[3 * T.i0 + c] / 255.0), c1 = static_cast<float>(m.col[3 * T.i1 + c] / 255.0), c2 = static_cast<float>(m.col[3 * T.i2 + c] / 255.0);
-                col[c] = ((q0 * c0 + q1 * c1) + q2 * c2) / qs;
+                col[c] = ((q0 * c0 + q1 * c1) + q2 * c2) * rq;
             }
             const double x0 = (-u.light[0]) - pos[0], x1 = (-u.light[1]) - pos[1], x2 = (-u.light[2]) - pos[2];
-            const double len = sqrt((x0 * x0 + x1 * x1) + x2 * x2);
-            const double d = (nrm[0] * (x0 / len) + nrm[1] * (x1 / len)) + nrm[2] * (x2 / len);
+            const double il = 1.0 / sqrt((x0 * x0 + x1 * x1) + x2 * x2);
+            const double d = (nrm[0] * (x0 * il) + nrm[1] * (x1 * il)) + nrm[2] * (x2 * il);
             const double lightv = 0.4 * fmax(d, 0.0) + 0.65;
             r8 = static_cast<unsigned>(rint(fmin(fmax(lightv * col[0], 0.0), 1.0) * 255.0));
             g8 = static_cast<unsigned>(rint(fmin(fmax(lightv * col[1], 0.0), 1.0) * 255.0));
@@ -247,6 +326,9 @@ render_kernel(RenderArgs a)
 }
 }  // namespace
 
+size_t render_uniform_bytes() { return sizeof(Uniforms); }
+size_t render_projected_bytes_per_vertex() { return sizeof(PVtx); }
+
 cudaError_t launch_render(const RenderArgs& a, int n, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
     const size_t smem = static_cast<size_t>(kBandRows) * kRS * sizeof(unsigned long long);
@@ -256,12 +338,16 @@ cudaError_t launch_render(const RenderArgs& a, int n, cudaStream_t s) {
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(kBands, n); cfg.blockDim = dim3(kRenderThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    if (!a.projected || !a.uniforms || a.max_nv <= 0) return cudaErrorInvalidValue;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((a.max_nv + kProjThreads - 1) / kProjThreads, n); cfg.blockDim = dim3(kProjThreads); cfg.dynamicSmemBytes = 0; cfg.stream = s;
     cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, render_project_kernel, a);
+    if (e != cudaSuccess) return e;
+    cfg.gridDim = dim3(kBands, n); cfg.blockDim = dim3(kRenderThreads); cfg.dynamicSmemBytes = smem;
     return cudaLaunchKernelEx(&cfg, render_kernel, a);
 }
 

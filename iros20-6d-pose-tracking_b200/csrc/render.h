@@ -17,8 +17,13 @@ struct RenderArgs {
     const MeshDev* meshes;         // device table indexed by mesh id
     int n_meshes;
     double fx, fy, cx, cy;
+    uint8_t* projected;            // workspace [n][max_nv] projected vertices (render_projected_bytes_per_vertex() each)
+    uint8_t* uniforms;             // workspace [n] per-track uniforms (render_uniform_bytes() each)
+    int max_nv;                    // vertex count of the largest model
     uint8_t* rgb;                  // [n][176][176][3]
     uint16_t* depth;               // [n][176][176] mm, 0 = background
 };
+size_t render_uniform_bytes();
+size_t render_projected_bytes_per_vertex();
 cudaError_t launch_render(const RenderArgs& a, int n, cudaStream_t s);
 }  // namespace se3tn

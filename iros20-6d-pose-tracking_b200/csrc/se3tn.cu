@@ -125,6 +125,7 @@ struct se3tn_ctx {
     int pdl = 1;                     // SE3TN_PDL=0 disables programmatic dependent launch between conv kernels
     std::map<int, MeshDev> meshes;   // CAD models of the rasteriser (device copies), keyed by mesh id
     MeshDev* d_meshes = nullptr; int mesh_rows = 0; bool meshes_dirty = false;
+    uint8_t* render_proj = nullptr; uint8_t* render_unif = nullptr; int render_max_nv = 0, render_proj_nv = 0;   // rasteriser workspace
     int fuse_pool = 1;               // SE3TN_FUSE_POOL=0: store the last head activation (debug buffer H3) and pool it in head_kernel
     float* pool_part = nullptr;      // [max_batch][4][1024] column sums from the last conv's epilogue
     int streamk = 0;                 // SE3TN_STREAMK=1: deal (unit, chunk) steps evenly over the CTAs in the BN=256 layers.  Measured no net gain at batch 64
@@ -663,7 +664,7 @@ void se3tn_destroy(se3tn_ctx* c) {
     for (int i = 0; i < SE3TN_PROFILE_SLOTS; ++i) { if (c->ev0[i]) cudaEventDestroy(c->ev0[i]); if (c->ev1[i]) cudaEventDestroy(c->ev1[i]); }
     cudaFree(c->sk_part); cudaFree(c->sk_flags); cudaFree(c->pool_part);
     for (auto& kv : c->meshes) { cudaFree(const_cast<float*>(kv.second.pos)); cudaFree(const_cast<float*>(kv.second.nrm)); cudaFree(const_cast<uint8_t*>(kv.second.col)); cudaFree(const_cast<int*>(kv.second.faces)); }
-    cudaFree(c->d_meshes);
+    cudaFree(c->d_meshes); cudaFree(c->render_proj); cudaFree(c->render_unif);
     if (c->own_workspace) cudaFree(c->workspace);
     delete c;
 }
@@ -964,6 +965,7 @@ int se3tn_render(se3tn_ctx* c, const double* K, const double* poses, const doubl
     if (!c) return SE3TN_ERR_INVALID;
     if (n < 0 || !K || (n > 0 && (!poses || !object_width || !rgbA || !depthA))) return fail(c, SE3TN_ERR_INVALID, "se3tn_render: bad arguments");
     if (n == 0) return SE3TN_OK;
+    if (n > c->max_batch) return fail(c, SE3TN_ERR_INVALID, "se3tn_render: n exceeds the context's max_batch");
     if (c->meshes.empty()) return fail(c, SE3TN_ERR_STATE, "se3tn_render: no mesh loaded (se3tn_set_mesh)");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     CU_TRY(c, cudaSetDevice(c->device));
@@ -974,14 +976,23 @@ int se3tn_render(se3tn_ctx* c, const double* K, const double* poses, const doubl
         std::vector<MeshDev> tab(rows, c->meshes.begin()->second);      // unused ids alias the first model
         for (auto& kv : c->meshes) tab[kv.first] = kv.second;
         CU_TRY(c, cudaMemcpy(c->d_meshes, tab.data(), sizeof(MeshDev) * rows, cudaMemcpyHostToDevice));
+        c->render_max_nv = 0;
+        for (auto& kv : c->meshes) c->render_max_nv = std::max(c->render_max_nv, kv.second.nv);
+        if (c->render_max_nv > c->render_proj_nv) {          // projected-vertex workspace: max_batch x largest model
+            cudaFree(c->render_proj); c->render_proj = nullptr;
+            CU_TRY(c, cudaMalloc(&c->render_proj, static_cast<size_t>(c->max_batch) * c->render_max_nv * render_projected_bytes_per_vertex()));
+            c->render_proj_nv = c->render_max_nv;
+        }
+        if (!c->render_unif) CU_TRY(c, cudaMalloc(&c->render_unif, static_cast<size_t>(c->max_batch) * render_uniform_bytes()));
         c->meshes_dirty = false;
     }
     RenderArgs a;
     a.poses = poses; a.object_width = object_width; a.mesh_ids = mesh_ids; a.meshes = c->d_meshes; a.n_meshes = c->mesh_rows;
     a.fx = K[0]; a.fy = K[1]; a.cx = K[2]; a.cy = K[3];
     a.rgb = rgbA; a.depth = depthA;
+    a.projected = c->render_proj; a.uniforms = c->render_unif; a.max_nv = c->render_max_nv;
     { ProfScope ps(c, 20, s); CU_TRY(c, launch_render(a, n, s)); }
-    ++c->launches;
+    c->launches += 2;
     return SE3TN_OK;
 }
 

@@ -367,7 +367,7 @@ def render_window(ob2cam, K, object_width, mesh, size=176, uniforms=None):
     X, Y, zw, w = _project_vertices(mesh['pos'], u['view32'], u['proj32'], size)
     key = np.full((size, size), (np.uint64(0x3F800000) << np.uint64(32)) | np.uint64(0xFFFFFFFF), np.uint64)   # depth 1.0, no triangle
     faces = mesh['faces']
-    lim = 1 << 30
+    lim = 1 << 25                      # render.cu evaluates the edge functions in float64: exact below 2^25 sub-pixels
     setups = {}
     for t in range(len(faces)):
         i0, i1, i2 = (int(a) for a in faces[t])
@@ -392,7 +392,8 @@ def render_window(ob2cam, K, object_width, mesh, size=176, uniforms=None):
             inside &= (e > 0) | ((e == 0) & tl)
             E.append(e)
         if not inside.any(): continue
-        lam = [e.astype(np.float64) / float(area2) for e in E]
+        inv_area = 1.0 / float(area2)                                                   # divisions only as reciprocals, like a GPU
+        lam = [e.astype(np.float64) * inv_area for e in E]
         z = (lam[0] * zw[i0] + lam[1] * zw[i1]) + lam[2] * zw[i2]
         z32 = z.astype(np.float32)
         ok = inside & (z32 >= 0) & (z32 < 1)                                         # depth clip; LESS against the cleared 1.0
@@ -412,17 +413,18 @@ def render_window(ob2cam, K, object_width, mesh, size=176, uniforms=None):
         e0 = (x2 - x1) * (cy - y1) - (y2 - y1) * (cx - x1)
         e1 = (x0 - x2) * (cy - y2) - (y0 - y2) * (cx - x2)
         e2 = (x1 - x0) * (cy - y0) - (y1 - y0) * (cx - x0)
-        l0, l1, l2 = float(e0) / float(area2), float(e1) / float(area2), float(e2) / float(area2)
-        q0, q1, q2 = l0 / w[i0], l1 / w[i1], l2 / w[i2]
-        qs = (q0 + q1) + q2
-        def interp(a0, a1, a2): return ((q0 * a0 + q1 * a1) + q2 * a2) / qs
+        inv_area = 1.0 / float(area2)
+        l0, l1, l2 = float(e0) * inv_area, float(e1) * inv_area, float(e2) * inv_area
+        q0, q1, q2 = l0 * (1.0 / w[i0]), l1 * (1.0 / w[i1]), l2 * (1.0 / w[i2])
+        rq = 1.0 / ((q0 + q1) + q2)
+        def interp(a0, a1, a2): return ((q0 * a0 + q1 * a1) + q2 * a2) * rq
         pos = [interp(float(mesh['pos'][i0, c]), float(mesh['pos'][i1, c]), float(mesh['pos'][i2, c])) for c in range(3)]
         nrm = [interp(float(mesh['nrm'][i0, c]), float(mesh['nrm'][i1, c]), float(mesh['nrm'][i2, c])) for c in range(3)]
         col = [interp(float(np.float32(mesh['col'][i0, c] / 255.0)), float(np.float32(mesh['col'][i1, c] / 255.0)),
                       float(np.float32(mesh['col'][i2, c] / 255.0))) for c in range(3)]
         x = [(-light[c]) - pos[c] for c in range(3)]
-        ln = np.sqrt((x[0] * x[0] + x[1] * x[1]) + x[2] * x[2])
-        L = [x[c] / ln for c in range(3)]
+        il = 1.0 / np.sqrt((x[0] * x[0] + x[1] * x[1]) + x[2] * x[2])
+        L = [x[c] * il for c in range(3)]
         d = (nrm[0] * L[0] + nrm[1] * L[1]) + nrm[2] * L[2]
         lightv = 0.4 * max(d, 0.0) + 0.65
         for c in range(3):
