@@ -277,3 +277,95 @@ class Tracker:
             ev = torch.cuda.Event(); ev.record(cs)
         torch.cuda.current_stream(dev).wait_event(ev)
         return bufs
+
+
+# ====================================================================================================
+# Sequence driver + on-disk formats: the reference's predictSequenceYcbInEOAT
+# (predict.py:579-623) and __main__ (predict.py:626-672) without the GUI (imshow / waitKey / VideoWriter).
+#   <seq>/rgb/*.png, <seq>/depth_filled/*.png (uint16 mm), <seq>/annotated_poses/*.txt (4x4, np.loadtxt)
+#   --train_data_path/../dataset_info.yml, --mean_std_path/{mean,std}.npy (train.py:124-125),
+#   --ckpt_dir model_best_val.pth.tar = {'epoch', 'state_dict', ...} (problems.py:149-151), --model_path *.ply
+#   -> <outdir>/%07d.txt written with np.savetxt (predict.py:611): what eval_ycb.py scores.
+# ====================================================================================================
+def read_rgb(path):
+    """np.array(Image.open(path))[:, :, :3] (predict.py:604)."""
+    from PIL import Image
+    return np.ascontiguousarray(np.array(Image.open(path))[:, :, :3])
+
+
+def read_depth(path):
+    """cv2.imread(path, IMREAD_UNCHANGED).astype(uint16) (predict.py:606): millimetres."""
+    import cv2
+    d = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+    if d is None:
+        raise FileNotFoundError(path)
+    return d.astype(np.uint16)
+
+
+def sequence_files(test_data_path):
+    """(rgb files, depth files, ground-truth pose files), each sorted (predict.py:584-590)."""
+    import glob
+    rgb = sorted(glob.glob('{}/rgb/*.png'.format(test_data_path)))
+    depth = sorted(glob.glob('{}/depth_filled/*.png'.format(test_data_path)))
+    gt = sorted(glob.glob('{}/annotated_poses/*.txt'.format(test_data_path)))
+    if not rgb or len(rgb) != len(depth):
+        raise FileNotFoundError('need the same number of rgb/*.png and depth_filled/*.png under ' + str(test_data_path))
+    if not gt:
+        raise FileNotFoundError('need annotated_poses/*.txt (frame 0 initialises the track) under ' + str(test_data_path))
+    return rgb, depth, gt
+
+
+def load_run_config(train_data_path, mean_std_path):
+    """dataset_info.yml next to the training data and the channel statistics (predict.py:657-664)."""
+    import yaml
+    with open(os.path.join(train_data_path, '../dataset_info.yml'), 'r') as ff:
+        dataset_info = yaml.safe_load(ff)
+    images_mean = np.load(os.path.join(mean_std_path, 'mean.npy'))
+    images_std = np.load(os.path.join(mean_std_path, 'std.npy'))
+    return dataset_info, images_mean, images_std
+
+
+def predictSequenceYcbInEOAT(test_data_path, dataset_info, images_mean, images_std, ckpt_dir, model_path, outdir,
+                             tracker=None, max_frames=None, **tracker_kwargs):
+    """Track one object through a recorded sequence, starting from the first annotated pose, one pose file per frame.
+    The reference's normalisers for this data set are 0.03 m / 30 degrees (predict.py:587).  Returns the (N,4,4) poses."""
+    rgb_files, depth_files, gt_files = sequence_files(test_data_path)
+    if tracker is None:
+        tracker = Tracker(dataset_info, images_mean, images_std, ckpt_dir, model_path=model_path, trans_normalizer=0.03,
+                          rot_normalizer=30 * np.pi / 180, **tracker_kwargs)
+    prev_pose = np.loadtxt(gt_files[0]).copy()
+    os.makedirs(outdir, exist_ok=True)
+    n = len(rgb_files) if max_frames is None else min(max_frames, len(rgb_files))
+    poses = []
+    for i in range(n):
+        rgb = read_rgb(rgb_files[i])
+        depth = read_depth(depth_files[i])
+        cur_pose = tracker.on_track(prev_pose.copy(), rgb, depth, gt_A_in_cam=np.eye(4), gt_B_in_cam=np.eye(4), debug=False, samples=1)
+        prev_pose = cur_pose.copy()
+        np.savetxt(os.path.join(outdir, '%07d.txt' % i), cur_pose)
+        poses.append(cur_pose)
+    return np.stack(poses)
+
+
+def main(argv=None):
+    import argparse
+    parser = argparse.ArgumentParser(description='headless se(3)-TrackNet sequence tracking on libse3tn (flags of the reference predict.py)')
+    parser.add_argument('--mode', default='ycbineoat', help='ycbineoat (the YCB-Video drivers need that data set\'s layout and are not included)')
+    parser.add_argument('--YCBInEOAT_dir', required=True)
+    parser.add_argument('--train_data_path', required=True, help='dataset_info.yml is read from <train_data_path>/../')
+    parser.add_argument('--model_path', type=str, required=True, help='path to mesh (.ply with normals and vertex colours)')
+    parser.add_argument('--ckpt_dir', type=str, required=True)
+    parser.add_argument('--mean_std_path', type=str, required=True)
+    parser.add_argument('--outdir', type=str, required=True)
+    parser.add_argument('--max_frames', type=int, default=None)
+    args = parser.parse_args(argv)
+    if args.mode != 'ycbineoat':
+        raise SystemExit('only --mode ycbineoat is available')
+    dataset_info, images_mean, images_std = load_run_config(args.train_data_path, args.mean_std_path)
+    poses = predictSequenceYcbInEOAT(args.YCBInEOAT_dir, dataset_info, images_mean, images_std, args.ckpt_dir, args.model_path,
+                                     args.outdir, max_frames=args.max_frames)
+    print('wrote %d poses to %s' % (len(poses), args.outdir))
+
+
+if __name__ == '__main__':
+    main()

@@ -511,3 +511,41 @@ def test_tracker_with_cuda_renderer(pkg, synth, tmp_path):
         P = trk.on_track_batch(P, R, D)
     assert P.is_cuda and torch.isfinite(P).all()
     trk.engine.close()
+
+
+def test_headless_sequence_driver(pkg, synth, tmp_path):
+    """the reference's on-disk formats end to end -- rgb / depth PNGs, annotated pose txt, dataset_info.yml,
+    mean.npy / std.npy, model_best_val.pth.tar, model .ply in; %07d.txt poses out -- against the oracle fed from the same files."""
+    import cv2, yaml
+    pr = importlib.import_module('iros20-6d-pose-tracking_b200.predict')
+    mio = importlib.import_module('iros20-6d-pose-tracking_b200.mesh_io')
+    K = synth.CAMERA_K
+    seq, train, out = tmp_path / 'bleach0', tmp_path / 'data' / 'train', tmp_path / 'out'
+    for d in (seq / 'rgb', seq / 'depth_filled', seq / 'annotated_poses', train):
+        d.mkdir(parents=True)
+    nframes = 3
+    for i in range(nframes):
+        rgb, depth = synth.raw_frame(seed=20 + i)
+        cv2.imwrite(str(seq / 'rgb' / ('%07d.png' % i)), rgb[..., ::-1])
+        cv2.imwrite(str(seq / 'depth_filled' / ('%07d.png' % i)), depth)
+    pose0 = synth.raw_poses(1, seed=3)[0]
+    np.savetxt(str(seq / 'annotated_poses' / '0000000.txt'), pose0)
+    info = {'resolution': 176, 'object_width': 200.0, 'boundingbox': 10,
+            'camera': {'focalX': float(K[0, 0]), 'focalY': float(K[1, 1]), 'centerX': float(K[0, 2]), 'centerY': float(K[1, 2]), 'height': 480, 'width': 640}}
+    yaml.safe_dump(info, open(tmp_path / 'data' / 'dataset_info.yml', 'w'))
+    mean, std = synth.default_mean_std()
+    np.save(tmp_path / 'mean.npy', mean); np.save(tmp_path / 'std.npy', std)
+    sd = synth.make_state_dict(0)
+    torch.save({'epoch': 7, 'state_dict': sd, 'best_prec': 0.0}, str(tmp_path / 'model_best_val.pth.tar'))
+    mio.save_ply_mesh(str(tmp_path / 'textured.ply'), synth.mesh(3, seed=0))
+    pr.main(['--YCBInEOAT_dir', str(seq), '--train_data_path', str(train), '--model_path', str(tmp_path / 'textured.ply'),
+             '--ckpt_dir', str(tmp_path / 'model_best_val.pth.tar'), '--mean_std_path', str(tmp_path), '--outdir', str(out)])
+    mesh = mio.load_ply_mesh(str(tmp_path / 'textured.ply'))
+    prev = pose0.copy()
+    for i in range(nframes):
+        got = np.loadtxt(str(out / ('%07d.txt' % i)))
+        rgb, depth = pr.read_rgb(str(seq / 'rgb' / ('%07d.png' % i))), pr.read_depth(str(seq / 'depth_filled' / ('%07d.png' % i)))
+        ra, da = O.render_window(prev, K, 200.0, mesh)
+        ref = O.on_track(sd, prev, rgb, depth, ra, da, K, 200.0, mean, std, 0.03, 30 * np.pi / 180)
+        assert got.shape == (4, 4) and np.abs(got - ref).max() < 6 * POSE_ATOL, 'frame %d: %.3g' % (i, np.abs(got - ref).max())
+        prev = got                                                  # follow the written trajectory, as eval_ycb.py reads it

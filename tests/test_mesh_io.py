@@ -56,3 +56,31 @@ def test_synth_mesh_is_closed_and_outward(synth):
     fn = np.cross(m['pos'][f[:, 1]] - m['pos'][f[:, 0]], m['pos'][f[:, 2]] - m['pos'][f[:, 0]])
     assert ((fn * m['pos'][f].mean(1)).sum(1) > 0).all()            # counter-clockwise seen from outside
     assert ((m['nrm'] * m['pos']).sum(1) > 0).all()
+
+
+def test_sequence_layout_helpers(synth, tmp_path):
+    """Host side of the headless sequence driver: file discovery, config loading, image readers (no GPU)."""
+    import cv2, yaml
+    pr = importlib.import_module('iros20-6d-pose-tracking_b200.predict')
+    seq = tmp_path / 'seq'
+    for d in ('rgb', 'depth_filled', 'annotated_poses'):
+        (seq / d).mkdir(parents=True)
+    with pytest.raises(FileNotFoundError):
+        pr.sequence_files(str(seq))
+    rgb, depth = synth.raw_frame(seed=1, h=48, w=64)
+    for i in (1, 0):                                                # written out of order: the driver sorts
+        cv2.imwrite(str(seq / 'rgb' / ('%04d.png' % i)), rgb[..., ::-1])
+        cv2.imwrite(str(seq / 'depth_filled' / ('%04d.png' % i)), depth)
+    pose = synth.raw_poses(1, seed=0)[0]
+    np.savetxt(str(seq / 'annotated_poses' / '0000.txt'), pose)
+    r, d, g = pr.sequence_files(str(seq))
+    assert [os.path.basename(x) for x in r] == ['0000.png', '0001.png'] and len(d) == 2 and len(g) == 1
+    assert np.array_equal(pr.read_rgb(r[0]), rgb) and np.array_equal(pr.read_depth(d[0]), depth) and pr.read_depth(d[0]).dtype == np.uint16
+    assert np.array_equal(np.loadtxt(g[0]), pose)                   # np.savetxt's %.18e round-trips float64
+    (tmp_path / 'train').mkdir()
+    info = {'resolution': 176, 'object_width': 200.0, 'boundingbox': 10, 'camera': {'focalX': 1.0, 'focalY': 1.0, 'centerX': 0.0, 'centerY': 0.0, 'height': 48, 'width': 64}}
+    yaml.safe_dump(info, open(tmp_path / 'dataset_info.yml', 'w'))
+    mean, std = synth.default_mean_std()
+    np.save(tmp_path / 'mean.npy', mean); np.save(tmp_path / 'std.npy', std)
+    di, m, s = pr.load_run_config(str(tmp_path / 'train'), str(tmp_path))
+    assert di == info and np.array_equal(m, mean) and np.array_equal(s, std)
