@@ -187,6 +187,16 @@ int se3tn_set_mesh(se3tn_ctx* ctx, int mesh_id, const float* pos, const float* n
 int se3tn_render(se3tn_ctx* ctx, const double* K, const double* poses, const double* object_width,
                  const int32_t* mesh_ids, int n, uint8_t* rgbA, uint16_t* depthA, void* stream);
 
+/* ---- live-sensor depth (SURVEY.md 8(f) "next" row 4) ------------------------------------------------------ */
+
+/* fill_depth as the reference's ROS node applies it to every depth image before tracking (reference Utils.py:455-514,
+ * predict_ros.py:38-41: extrapolate=False, bilateral): invert, 5x5 diamond dilate, 5x5 close, fill empties from a 7x7
+ * dilation, 5x5 median, bilateral(5, 1.5, 2.0), invert back.  depth_mm uint16 (H,W) device -> out_mm uint16 (H,W) device
+ * (= (fill_depth(depth/1e3) * 1000).astype(uint16)) and/or out_m float32 (H,W) metres; either may be NULL.  Bit-identical
+ * to OpenCV up to the median; the bilateral's float32 accumulation order differs (|diff| ~ 5e-7 m). */
+int se3tn_fill_depth(se3tn_ctx* ctx, const uint16_t* depth_mm, int H, int W, double max_depth,
+                     uint16_t* out_mm, float* out_m, void* stream);
+
 /* ---- introspection (tests / profiling) -------------------------------------------------------- */
 
 /* Device pointer + per-image float count of an internal NHWC activation buffer.

@@ -5,6 +5,7 @@
 #include "aux_kernels.h"
 #include "metrics.h"
 #include "render.h"
+#include "depth_fill.h"
 #include "ptx.cuh"
 
 #include <cstdio>
@@ -126,6 +127,7 @@ struct se3tn_ctx {
     std::map<int, MeshDev> meshes;   // CAD models of the rasteriser (device copies), keyed by mesh id
     MeshDev* d_meshes = nullptr; int mesh_rows = 0; bool meshes_dirty = false;
     uint8_t* render_proj = nullptr; uint8_t* render_unif = nullptr; int render_max_nv = 0, render_proj_nv = 0;   // rasteriser workspace
+    FillScratch fill = {nullptr, nullptr, nullptr, nullptr}; size_t fill_pixels = 0;   // depth hole-filling scratch (grows on demand)
     int fuse_pool = 1;               // SE3TN_FUSE_POOL=0: store the last head activation (debug buffer H3) and pool it in head_kernel
     float* pool_part = nullptr;      // [max_batch][4][1024] column sums from the last conv's epilogue
     int streamk = 0;                 // SE3TN_STREAMK=1: deal (unit, chunk) steps evenly over the CTAs in the BN=256 layers.  Measured no net gain at batch 64
@@ -665,6 +667,7 @@ void se3tn_destroy(se3tn_ctx* c) {
     cudaFree(c->sk_part); cudaFree(c->sk_flags); cudaFree(c->pool_part);
     for (auto& kv : c->meshes) { cudaFree(const_cast<float*>(kv.second.pos)); cudaFree(const_cast<float*>(kv.second.nrm)); cudaFree(const_cast<uint8_t*>(kv.second.col)); cudaFree(const_cast<int*>(kv.second.faces)); }
     cudaFree(c->d_meshes); cudaFree(c->render_proj); cudaFree(c->render_unif);
+    cudaFree(c->fill.a); cudaFree(c->fill.b); cudaFree(c->fill.lut); cudaFree(c->fill.minmax);
     if (c->own_workspace) cudaFree(c->workspace);
     delete c;
 }
@@ -931,6 +934,29 @@ int se3tn_vocap(se3tn_ctx* c, const double* errs, int n, double* out_ap, void* s
     if (!out_ap || n < 0 || (n > 0 && !errs)) return fail(c, SE3TN_ERR_INVALID, "se3tn_vocap: null/invalid argument");
     CU_TRY(c, cudaSetDevice(c->device));
     CU_TRY(c, vocap(errs, n, out_ap, static_cast<cudaStream_t>(stream)));
+    return SE3TN_OK;
+}
+
+int se3tn_fill_depth(se3tn_ctx* c, const uint16_t* depth_mm, int H, int W, double max_depth,
+                     uint16_t* out_mm, float* out_m, void* stream) {
+    if (!c) return SE3TN_ERR_INVALID;
+    if (!depth_mm || H <= 0 || W <= 0 || (!out_mm && !out_m)) return fail(c, SE3TN_ERR_INVALID, "se3tn_fill_depth: bad arguments");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CU_TRY(c, cudaSetDevice(c->device));
+    const size_t px = static_cast<size_t>(H) * W;
+    if (px > c->fill_pixels) {
+        CU_TRY(c, cudaStreamSynchronize(s));
+        cudaFree(c->fill.a); cudaFree(c->fill.b); c->fill.a = c->fill.b = nullptr; c->fill_pixels = 0;
+        CU_TRY(c, cudaMalloc(&c->fill.a, px * sizeof(float)));
+        CU_TRY(c, cudaMalloc(&c->fill.b, px * sizeof(float)));
+        c->fill_pixels = px;
+    }
+    if (!c->fill.lut) {
+        CU_TRY(c, cudaMalloc(&c->fill.lut, (kFillLutEntries + 1) * sizeof(float)));
+        CU_TRY(c, cudaMalloc(&c->fill.minmax, 2 * sizeof(unsigned)));
+    }
+    CU_TRY(c, launch_fill_depth(depth_mm, H, W, static_cast<float>(max_depth), c->fill, out_mm, out_m, s));
+    c->launches += 8;
     return SE3TN_OK;
 }
 

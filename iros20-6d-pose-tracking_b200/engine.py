@@ -227,6 +227,19 @@ class Engine:
                                          _stream(self.device)), self._ctx)
         return rgb, dep
 
+    # ------------------------------------------------------------------ live-sensor depth
+    def fill_depth(self, depth_mm, max_depth=2.0, want_metres=False):
+        """fill_depth as predict_ros.py:38-41 applies it (reference Utils.py:455-514): uint16 mm CUDA tensor (H,W) ->
+        uint16 mm CUDA tensor (and float32 metres with want_metres)."""
+        if depth_mm.dtype != torch.uint16 or depth_mm.dim() != 2 or not depth_mm.is_cuda or not depth_mm.is_contiguous():
+            raise ValueError('depth_mm must be a contiguous uint16 CUDA tensor (H,W)')
+        H, W = depth_mm.shape
+        out = torch.empty_like(depth_mm)
+        out_m = torch.empty((H, W), dtype=torch.float32, device=self.device) if want_metres else None
+        _lib.check(self.lib.se3tn_fill_depth(self._ctx, _ptr(depth_mm), int(H), int(W), float(max_depth), _ptr(out), _ptr(out_m),
+                                             _stream(self.device)), self._ctx)
+        return (out, out_m) if want_metres else out
+
     # ------------------------------------------------------------------ introspection
     def debug_buffer(self, buf_id, n):
         """A float32 view (n, floats_per_image) of an internal NHWC activation buffer."""

@@ -11,6 +11,7 @@ What is executed from the reference, unmodified:
   datasets.TrackDataset.processData / processPredict  -> pre/post fixtures
   Utils.add / Utils.adi, eval_ycb.VOCap                -> metric fixtures
   vispy_renderer.VispyRenderer.update_cam_mat / render_image (numpy parts) -> renderer uniform fixtures
+  Utils.fill_depth (as predict_ros.py:38-41 calls it)  -> depth hole-filling fixtures
 
 Accommodations (nothing in the reference tree is edited; it is read-only):
   * `open3d` and `transformations` are not installed here; they are only
@@ -232,6 +233,15 @@ def main():
     rd = dict(poses=poses, object_width=np.float64(200.0), window=np.array(wins, np.int64), proj64=np.array(projs),
               view=np.array(views), light32=np.array(lights))
     np.savez_compressed(os.path.join(args.out, 'golden_render.npz'), **rd)
+    # ------------------------------------------------------------------ depth hole filling
+    # the reference's own Utils.fill_depth exactly as predict_ros.py:38-41 drives it
+    fd = {}
+    for name, seed, hw in (('a', 31, (120, 160)), ('b', 32, (64, 96))):
+        _, dmm = synth.raw_frame(seed, *hw)
+        dmm = dmm.copy(); dmm[10:30, 20:50] = 0                   # a real hole, not only salt-and-pepper dropouts
+        filled = U.fill_depth(dmm / 1e3, max_depth=2.0, extrapolate=False)
+        fd['in_' + name] = dmm; fd['out_m_' + name] = filled; fd['out_mm_' + name] = (filled * 1000).astype(np.uint16)
+    np.savez_compressed(os.path.join(args.out, 'golden_fill.npz'), **fd)
     for f in sorted(os.listdir(args.out)):
         print(f, os.path.getsize(os.path.join(args.out, f)))
 

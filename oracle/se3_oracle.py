@@ -434,3 +434,34 @@ def render_window(ob2cam, K, object_width, mesh, size=176, uniforms=None):
         dist = (B / (np.float64(tt) - A)) * -1                                          # `- A` with a float64 scalar: float64 (numpy >= 2)
         depth[j, i] = 0 if dist >= far_dist else np.uint16(dist * 1000)
     return rgb, depth
+
+
+# =============================================================================================
+# Depth hole filling for live sensors: Utils.py:455-514 as predict_ros.py:38-41 calls it
+#   depth_mm uint16 -> fill_depth(depth / 1e3, max_depth=2.0, extrapolate=False, blur_type='bilateral') -> (x * 1000).astype(uint16)
+# Third-party arithmetic: cv2.dilate / morphologyEx / medianBlur / bilateralFilter, called directly (same library the
+# reference calls; pinned by tests/golden/golden_fill.npz, which oracle/make_golden.py produces with the reference's own
+# Utils.fill_depth).
+# =============================================================================================
+def fill_depth(depth, max_depth=2.0):
+    """Utils.py:455-514 with extrapolate=False, blur_type='bilateral'.  depth: metres (any float dtype) -> float32 metres."""
+    depth = np.asarray(depth).astype(np.float32)
+    diamond = np.array([[0, 0, 1, 0, 0], [0, 1, 1, 1, 0], [1, 1, 1, 1, 1], [0, 1, 1, 1, 0], [0, 0, 1, 0, 0]], dtype=np.uint8)
+    valid = depth > 0.1
+    depth[valid] = max_depth - depth[valid]                      # invert so that dilation prefers near surfaces
+    depth = cv2.dilate(depth, diamond)
+    depth = cv2.morphologyEx(depth, cv2.MORPH_CLOSE, np.ones((5, 5), np.uint8))
+    empty = depth < 0.1
+    dilated = cv2.dilate(depth, np.ones((7, 7), np.uint8))
+    depth[empty] = dilated[empty]
+    depth = cv2.medianBlur(depth, 5)
+    depth = cv2.bilateralFilter(depth, 5, 1.5, 2.0)
+    valid = depth > 0.1
+    depth[valid] = max_depth - depth[valid]
+    return depth
+
+
+def fill_depth_mm(depth_mm):
+    """predict_ros.py:38-41: uint16 millimetres in, uint16 millimetres out."""
+    d = fill_depth(np.asarray(depth_mm).astype(np.uint16) / 1e3, max_depth=2.0)
+    return (d * 1000).astype(np.uint16), d

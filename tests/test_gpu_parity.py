@@ -549,3 +549,42 @@ def test_headless_sequence_driver(pkg, synth, tmp_path):
         ref = O.on_track(sd, prev, rgb, depth, ra, da, K, 200.0, mean, std, 0.03, 30 * np.pi / 180)
         assert got.shape == (4, 4) and np.abs(got - ref).max() < 6 * POSE_ATOL, 'frame %d: %.3g' % (i, np.abs(got - ref).max())
         prev = got                                                  # follow the written trajectory, as eval_ycb.py reads it
+
+
+# ------------------------------------------------------------------------------ depth hole filling
+def test_fill_depth_vs_reference_and_oracle(pkg, synth, golden_dir, eng):
+    """Tolerances: metres within 2e-6 (float32 accumulation order of the bilateral sum; everything before it is bit-exact min /
+    max / median); millimetres equal except where the reference's value*1000 sits within 3e-3 of an integer (then +-1), and
+    except pixels beyond max_depth, whose negative float -> uint16 conversion is undefined behaviour in the reference itself."""
+    g = np.load(os.path.join(golden_dir, 'golden_fill.npz'))
+    dev = eng.device
+    cases = [(g['in_' + k], g['out_m_' + k], g['out_mm_' + k]) for k in 'ab']
+    _, full = synth.raw_frame(seed=9)                               # full 480x640 frame, against the oracle
+    full = full.copy(); full[100:160, 200:330] = 0
+    mm_ref, m_ref = O.fill_depth_mm(full)
+    cases.append((full, m_ref, mm_ref))
+    for din, m_ref, mm_ref in cases:
+        out_mm, out_m = eng.fill_depth(torch.from_numpy(np.ascontiguousarray(din)).to(dev), want_metres=True)
+        out_mm, out_m = out_mm.cpu().numpy(), out_m.cpu().numpy()
+        assert np.abs(out_m - m_ref).max() < 2e-6, np.abs(out_m - m_ref).max()
+        ok = m_ref >= 0                                             # defined conversions only
+        diff = np.abs(out_mm.astype(np.int32) - mm_ref.astype(np.int32))
+        assert diff[ok].max() <= 1
+        # a millimetre may only differ where the reference's own value sits on a truncation boundary (flat, dilation-filled
+        # regions give x.xxx000 +- 1 ulp, and which side OpenCV lands on depends on its SIMD summation order)
+        mmf = m_ref.astype(np.float64) * 1000
+        on_boundary = np.abs(mmf - np.rint(mmf)) < 3e-3
+        assert (on_boundary | (diff == 0) | ~ok).all()
+    # drop-in function (metres in, float32 metres out)
+    U = importlib.import_module('iros20-6d-pose-tracking_b200.Utils')
+    U.set_engine(eng)
+    got = U.fill_depth(cases[0][0] / 1e3, max_depth=2.0, extrapolate=False)
+    assert got.dtype == np.float32 and np.abs(got - cases[0][1]).max() < 2e-6
+    with pytest.raises(NotImplementedError):
+        U.fill_depth(cases[0][0] / 1e3, extrapolate=True)
+    # a constant image passes through the bilateral untouched (OpenCV copies when max - min < eps) and nothing is invented
+    # (800 mm comes back as 799: 2 - float32(0.8) and back is 0.79999995 -- the reference's own round trip)
+    flat = np.full((32, 48), 800, dtype=np.uint16)
+    assert np.array_equal(eng.fill_depth(torch.from_numpy(flat).to(dev)).cpu().numpy(), O.fill_depth_mm(flat)[0])
+    zero = torch.zeros((16, 16), dtype=torch.uint16, device=dev)
+    assert int(eng.fill_depth(zero).to(torch.int32).max()) == 0

@@ -172,3 +172,12 @@ def test_render_oracle_properties(synth):
     # degenerate window -> empty image
     rgb0, dep0 = O.render_window(pose, synth.CAMERA_K, 0.0, mesh)
     assert rgb0.max() == 0 and dep0.max() == 0
+
+
+def test_fill_depth_oracle_vs_reference(golden_dir):
+    """Depth hole filling restated (cv2 calls in the reference's order) against the reference's own Utils.fill_depth."""
+    g = np.load(os.path.join(golden_dir, 'golden_fill.npz'))
+    for k in 'ab':
+        mm, m = O.fill_depth_mm(g['in_' + k])
+        assert np.array_equal(m, g['out_m_' + k]) and np.array_equal(mm, g['out_mm_' + k])
+        assert (g['in_' + k] == 0).mean() > 0.1 and (mm == 0).mean() < 0.02          # the holes are actually filled
