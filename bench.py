@@ -342,7 +342,7 @@ def main():
         h = sets[k % N_INPUT_SETS][0]
         out = trk.on_track_batch(h['poses'], h['rgb'], h['depth'], h['rgbA'], h['depthA'])
         if world > 1:
-            out = dist_mod.all_gather_poses(out, tracker.shards, rank, world)[tracker.mine]
+            out = dist_mod.all_gather_poses(out, tracker.shards, rank, world).index_select(0, tracker.mine_dev)
         pinned_out.copy_(out, non_blocking=True)
         return out
 

@@ -70,6 +70,9 @@ class ShardedTracker:
         self.weight_ids = np.asarray(weight_ids, dtype=np.int32)
         self.shards = shard_tracks(self.weight_ids, world_size)
         self.mine = self.shards[rank]
+        # device-side index of this rank's tracks (indexing a CUDA tensor with the numpy array would stage a synchronous
+        # host->device copy on every call and serialise host and GPU)
+        self.mine_dev = torch.as_tensor(np.ascontiguousarray(self.mine), dtype=torch.long).to(engine.device)
         self.K = K
         self.tn, self.rn = trans_normalizer, rot_normalizer
         self.precision = precision
