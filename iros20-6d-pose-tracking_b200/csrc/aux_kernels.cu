@@ -52,7 +52,7 @@ preprocess_kernel(PreprocessArgs a)
 {
     ptx::grid_dep_launch();
     const int n = blockIdx.y;
-    const int quad = blockIdx.x * blockDim.x + threadIdx.x;     // 4 consecutive pixels of one row (176 = 44 * 4)
+    const int quad = blockIdx.x * blockDim.x + threadIdx.x;     // thread index within the image: 4 pixels each (see below)
     const double* pose = a.poses + n * 16;
     // the crop window and cv2's inverse scales are per track: one thread computes them for the block
     __shared__ int s_win[4];
@@ -80,103 +80,73 @@ preprocess_kernel(PreprocessArgs a)
         s_inv[1] = (ch > 0) ? 1.0 / (static_cast<double>(kImg) / ch) : 0.0;
     }
     __syncthreads();
-    if (quad >= kImg * kImg / 4) return;
-    const int pix0 = quad * 4;
-    const int y = pix0 / kImg, x0 = pix0 - y * kImg;
+    // A warp owns 128 consecutive pixels of the flat 176x176 image (30976 = 242 * 128); lane L handles pixels
+    // base + L, base + 32 + L, base + 64 + L, base + 96 + L, so every load / store instruction of the warp touches 32 CONSECUTIVE
+    // pixels: the 16-byte stem stores are 512 contiguous bytes per instruction (4 lines instead of 16 with 4 pixels per thread).
+    const int base = (quad >> 5) * 128 + (quad & 31);
+    if ((quad >> 5) * 128 >= kImg * kImg) return;
     const double z = pose[11];
     const bool gl = z < 0;
     const double z1000 = __dmul_rn(z, 1000.0);
-    const size_t ao = static_cast<size_t>(n) * kImg * kImg + pix0;
-
-    // ---- B: observed frame crop (4 pixels) -------------------------------------------------------
-    unsigned rB[4] = {0, 0, 0, 0}, gB[4] = {0, 0, 0, 0}, bB[4] = {0, 0, 0, 0}, dB[4] = {0, 0, 0, 0};
-    if (a.b_precropped) {
-        // frame_rgb / frame_depth already hold n 176x176 crops (TrackDataset.processData's inputs)
-        const uint32_t* pr = reinterpret_cast<const uint32_t*>(a.frame_rgb + ao * 3);      // 12 bytes, 4-byte aligned
-        const uint32_t w0 = pr[0], w1 = pr[1], w2 = pr[2];
-        rB[0] = w0 & 255; gB[0] = (w0 >> 8) & 255; bB[0] = (w0 >> 16) & 255;
-        rB[1] = w0 >> 24; gB[1] = w1 & 255; bB[1] = (w1 >> 8) & 255;
-        rB[2] = (w1 >> 16) & 255; gB[2] = w1 >> 24; bB[2] = w2 & 255;
-        rB[3] = (w2 >> 8) & 255; gB[3] = (w2 >> 16) & 255; bB[3] = w2 >> 24;
-        const uint2 dd = *reinterpret_cast<const uint2*>(a.frame_depth + ao);
-        dB[0] = dd.x & 0xffff; dB[1] = dd.x >> 16; dB[2] = dd.y & 0xffff; dB[3] = dd.y >> 16;
-    } else {
-        const int top = s_win[0], left = s_win[1], ch = s_win[2], cw = s_win[3];
-        if (ch > 0 && cw > 0) {
-            int sy = static_cast<int>(floor(y * s_inv[1])); if (sy > ch - 1) sy = ch - 1;
-            const int fy_ = top + sy;
-            if (fy_ >= 0 && fy_ < a.H) {
+    const int wi = a.weight_ids ? a.weight_ids[n] : 0;
+    const size_t img0 = static_cast<size_t>(n) * kImg * kImg;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    int sx = static_cast<int>(floor((x0 + i) * s_inv[0])); if (sx > cw - 1) sx = cw - 1;
-                    const int fx_ = left + sx;
-                    if (fx_ >= 0 && fx_ < a.W) {
-                        const size_t fo = static_cast<size_t>(fy_) * a.W + fx_;
-                        const uint8_t* pr = a.frame_rgb + fo * 3;
-                        rB[i] = pr[0]; gB[i] = pr[1]; bB[i] = pr[2];
-                        dB[i] = a.frame_depth[fo];
-                    }
+    for (int i = 0; i < 4; ++i) {
+        const int pix = base + 32 * i;
+        const int y = pix / kImg, x = pix - y * kImg;
+        const size_t ao = img0 + pix;
+        // ---- B: observed frame crop ------------------------------------------------------------------
+        unsigned rB = 0, gB = 0, bB = 0, dB = 0;
+        if (a.b_precropped) {
+            // frame_rgb / frame_depth already hold n 176x176 crops (TrackDataset.processData's inputs)
+            const uint8_t* pr = a.frame_rgb + ao * 3;
+            rB = pr[0]; gB = pr[1]; bB = pr[2];
+            dB = a.frame_depth[ao];
+        } else {
+            const int top = s_win[0], left = s_win[1], ch = s_win[2], cw = s_win[3];
+            if (ch > 0 && cw > 0) {
+                int sy = static_cast<int>(floor(y * s_inv[1])); if (sy > ch - 1) sy = ch - 1;
+                int sx = static_cast<int>(floor(x * s_inv[0])); if (sx > cw - 1) sx = cw - 1;
+                const int fy_ = top + sy, fx_ = left + sx;
+                if (fy_ >= 0 && fy_ < a.H && fx_ >= 0 && fx_ < a.W) {
+                    const size_t fo = static_cast<size_t>(fy_) * a.W + fx_;
+                    const uint8_t* pr = a.frame_rgb + fo * 3;
+                    rB = pr[0]; gB = pr[1]; bB = pr[2];
+                    dB = a.frame_depth[fo];
                 }
             }
         }
-    }
-    if (a.crop_rgb) {
-        uint32_t* o = reinterpret_cast<uint32_t*>(a.crop_rgb + ao * 3);
-        o[0] = rB[0] | (gB[0] << 8) | (bB[0] << 16) | (rB[1] << 24);
-        o[1] = gB[1] | (bB[1] << 8) | (rB[2] << 16) | (gB[2] << 24);
-        o[2] = bB[2] | (rB[3] << 8) | (gB[3] << 16) | (bB[3] << 24);
-    }
-    if (a.crop_depth) *reinterpret_cast<uint2*>(a.crop_depth + ao) = make_uint2(dB[0] | (dB[1] << 16), dB[2] | (dB[3] << 16));
+        if (a.crop_rgb) { uint8_t* o = a.crop_rgb + ao * 3; o[0] = static_cast<uint8_t>(rB); o[1] = static_cast<uint8_t>(gB); o[2] = static_cast<uint8_t>(bB); }
+        if (a.crop_depth) a.crop_depth[ao] = static_cast<uint16_t>(dB);
+        // ---- A: rendered previous view --------------------------------------------------------------
+        const uint8_t* pa = a.rgbA + ao * 3;
+        const unsigned rA = pa[0], gA = pa[1], bA = pa[2], dA = a.depthA[ao];
 
-    // ---- A: rendered previous view (4 pixels) ---------------------------------------------------
-    unsigned rA[4], gA[4], bA[4], dA[4];
-    {
-        const uint32_t* pr = reinterpret_cast<const uint32_t*>(a.rgbA + ao * 3);
-        const uint32_t w0 = pr[0], w1 = pr[1], w2 = pr[2];
-        rA[0] = w0 & 255; gA[0] = (w0 >> 8) & 255; bA[0] = (w0 >> 16) & 255;
-        rA[1] = w0 >> 24; gA[1] = w1 & 255; bA[1] = (w1 >> 8) & 255;
-        rA[2] = (w1 >> 16) & 255; gA[2] = w1 >> 24; bA[2] = w2 & 255;
-        rA[3] = (w2 >> 8) & 255; gA[3] = (w2 >> 16) & 255; bA[3] = w2 >> 24;
-        const uint2 dd = *reinterpret_cast<const uint2*>(a.depthA + ao);
-        dA[0] = dd.x & 0xffff; dA[1] = dd.x >> 16; dA[2] = dd.y & 0xffff; dA[3] = dd.y >> 16;
-    }
-
-    const int wi = a.weight_ids ? a.weight_ids[n] : 0;
-    float4 vA[4], vB[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float zA = depth_offset(dA[i], z1000, gl), zB = depth_offset(dB[i], z1000, gl);
+        const float zA = depth_offset(dA, z1000, gl), zB = depth_offset(dB, z1000, gl);
+        float4 vA, vB;
         if (a.stats_f64) {
             const double* m = a.mean64 + wi * 8; const double* s = a.std64 + wi * 8;
-            vA[i] = make_float4(s_lut[0][rA[i]], s_lut[1][gA[i]], s_lut[2][bA[i]], norm_f64(zA, m[3], s[3]));
-            vB[i] = make_float4(s_lut[3][rB[i]], s_lut[4][gB[i]], s_lut[5][bB[i]], norm_f64(zB, m[7], s[7]));
+            vA = make_float4(s_lut[0][rA], s_lut[1][gA], s_lut[2][bA], norm_f64(zA, m[3], s[3]));
+            vB = make_float4(s_lut[3][rB], s_lut[4][gB], s_lut[5][bB], norm_f64(zB, m[7], s[7]));
         } else {
             const float* m = a.mean32 + wi * 8; const float* s = a.std32 + wi * 8;
-            vA[i] = make_float4(s_lut[0][rA[i]], s_lut[1][gA[i]], s_lut[2][bA[i]], norm_f32(zA, m[3], s[3]));
-            vB[i] = make_float4(s_lut[3][rB[i]], s_lut[4][gB[i]], s_lut[5][bB[i]], norm_f32(zB, m[7], s[7]));
+            vA = make_float4(s_lut[0][rA], s_lut[1][gA], s_lut[2][bA], norm_f32(zA, m[3], s[3]));
+            vB = make_float4(s_lut[3][rB], s_lut[4][gB], s_lut[5][bB], norm_f32(zB, m[7], s[7]));
         }
-    }
-    if (a.nchwA) {
-        float* oa = a.nchwA + static_cast<size_t>(n) * 4 * kImg * kImg + pix0;
-        float* ob = a.nchwB + static_cast<size_t>(n) * 4 * kImg * kImg + pix0;
-        *reinterpret_cast<float4*>(oa) = make_float4(vA[0].x, vA[1].x, vA[2].x, vA[3].x);
-        *reinterpret_cast<float4*>(oa + kImg * kImg) = make_float4(vA[0].y, vA[1].y, vA[2].y, vA[3].y);
-        *reinterpret_cast<float4*>(oa + 2 * kImg * kImg) = make_float4(vA[0].z, vA[1].z, vA[2].z, vA[3].z);
-        *reinterpret_cast<float4*>(oa + 3 * kImg * kImg) = make_float4(vA[0].w, vA[1].w, vA[2].w, vA[3].w);
-        *reinterpret_cast<float4*>(ob) = make_float4(vB[0].x, vB[1].x, vB[2].x, vB[3].x);
-        *reinterpret_cast<float4*>(ob + kImg * kImg) = make_float4(vB[0].y, vB[1].y, vB[2].y, vB[3].y);
-        *reinterpret_cast<float4*>(ob + 2 * kImg * kImg) = make_float4(vB[0].z, vB[1].z, vB[2].z, vB[3].z);
-        *reinterpret_cast<float4*>(ob + 3 * kImg * kImg) = make_float4(vB[0].w, vB[1].w, vB[2].w, vB[3].w);
-    }
-    if (a.stemA) {
-        const size_t so = (static_cast<size_t>(n) * kStemH + (y + 3)) * kStemW + (x0 + 3);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            reinterpret_cast<float4*>(a.stemA)[so + i] = pack_stem_pixel(vA[i], a.round_tf32);
-            reinterpret_cast<float4*>(a.stemB)[so + i] = pack_stem_pixel(vB[i], a.round_tf32);
+        if (a.nchwA) {
+            float* oa = a.nchwA + static_cast<size_t>(n) * 4 * kImg * kImg + pix;
+            float* ob = a.nchwB + static_cast<size_t>(n) * 4 * kImg * kImg + pix;
+            oa[0] = vA.x; oa[kImg * kImg] = vA.y; oa[2 * kImg * kImg] = vA.z; oa[3 * kImg * kImg] = vA.w;
+            ob[0] = vB.x; ob[kImg * kImg] = vB.y; ob[2 * kImg * kImg] = vB.z; ob[3 * kImg * kImg] = vB.w;
+        }
+        if (a.stemA) {
+            const size_t so = (static_cast<size_t>(n) * kStemH + (y + 3)) * kStemW + (x + 3);
+            reinterpret_cast<float4*>(a.stemA)[so] = pack_stem_pixel(vA, a.round_tf32);
+            reinterpret_cast<float4*>(a.stemB)[so] = pack_stem_pixel(vB, a.round_tf32);
         }
     }
 }
+
 
 static cudaError_t launch_pdl(const void* func, dim3 grid, dim3 block, void** args, cudaStream_t s) {
     cudaLaunchConfig_t cfg = {};
