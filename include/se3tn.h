@@ -157,6 +157,15 @@ int se3tn_track_batch(se3tn_ctx* ctx, const uint8_t* frame_rgb, const uint16_t* 
                       double trans_normalizer, double rot_normalizer, int precision,
                       float* out_trans, float* out_rot, double* poses_out, void* stream);
 
+/* The one exchange step of the sharded path: all-gather of the updated poses over an EXISTING NCCL
+ * communicator, for hosts that drive libse3tn without torch.distributed (the Python layer uses
+ * torch.distributed.all_gather_into_tensor, dist.py).  nccl_comm: the host's ncclComm_t; local_poses double
+ * (n_local,16) device; all_poses double (world*n_local,16) device, rank-major; every rank passes the same n_local.
+ * NCCL is resolved at run time (dlopen of libnccl.so.2, the copy already loaded in the process if there is one);
+ * SE3TN_ERR_UNSUPPORTED if it cannot be found.  The reference has no multi-GPU code to replace. */
+int se3tn_allgather_poses(se3tn_ctx* ctx, void* nccl_comm, const double* local_poses, double* all_poses, int n_local,
+                          void* stream);
+
 /* ---- pose-error metrics (SURVEY.md 8(f) "next" row 1; not on the per-frame path) ----------------------- */
 
 /* Utils.add / Utils.adi (reference Utils.py:72-98) for n (pred, gt) pose pairs against one model point cloud:

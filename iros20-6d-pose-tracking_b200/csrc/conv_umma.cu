@@ -222,7 +222,10 @@ template <int BN>
 cudaError_t launch_bn(const UmmaMaps& maps, const ConvGeom& g, const UmmaTiling& t, const ConvPtrs& p,
                       int num_sms, cudaStream_t stream) {
     using C = Cfg<BN>;
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {};                       // per-device function attribute
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    bool& attr_set = attr_set_dev[dev];
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
         if (e != cudaSuccess) return e;

@@ -852,7 +852,11 @@ cudaError_t launch2(const UmmaMaps& maps, const ConvGeom& g, const Umma2Plan& t,
     const size_t smem = static_cast<size_t>(C::kAStages) * C::kAStage + static_cast<size_t>(RESIDENT ? w_tiles : C::kBStages) * C::kBTile +
                         C::kPoolBufs * ((kPoolStageBytes + 1023) & ~1023) + ((C::kEpiBytes + 1023) & ~1023) + 1024 + 512;
     if (smem > 232448) return cudaErrorInvalidConfiguration;
-    static size_t attr_smem = 0;
+    // the dynamic shared-memory limit is a per-device function attribute: cache what was set for each device
+    static size_t attr_smem_dev[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    size_t& attr_smem = attr_smem_dev[dev];
     if (smem > attr_smem) {
         cudaError_t e = cudaFuncSetAttribute(conv_umma2_kernel<BN, RESIDENT, KIND, MT, PREC, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;

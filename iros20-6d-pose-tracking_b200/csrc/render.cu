@@ -332,7 +332,10 @@ size_t render_projected_bytes_per_vertex() { return sizeof(PVtx); }
 cudaError_t launch_render(const RenderArgs& a, int n, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
     const size_t smem = static_cast<size_t>(kBandRows) * kRS * sizeof(unsigned long long);
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {};                       // per-device function attribute
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    bool& attr_set = attr_set_dev[dev];
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;

@@ -5,6 +5,7 @@
 #include "aux_kernels.h"
 #include "metrics.h"
 #include "render.h"
+#include <dlfcn.h>
 #include "depth_fill.h"
 #include "ptx.cuh"
 
@@ -934,6 +935,27 @@ int se3tn_vocap(se3tn_ctx* c, const double* errs, int n, double* out_ap, void* s
     if (!out_ap || n < 0 || (n > 0 && !errs)) return fail(c, SE3TN_ERR_INVALID, "se3tn_vocap: null/invalid argument");
     CU_TRY(c, cudaSetDevice(c->device));
     CU_TRY(c, vocap(errs, n, out_ap, static_cast<cudaStream_t>(stream)));
+    return SE3TN_OK;
+}
+
+int se3tn_allgather_poses(se3tn_ctx* c, void* nccl_comm, const double* local_poses, double* all_poses, int n_local, void* stream) {
+    if (!c) return SE3TN_ERR_INVALID;
+    if (!nccl_comm || n_local < 0 || (n_local > 0 && (!local_poses || !all_poses))) return fail(c, SE3TN_ERR_INVALID, "se3tn_allgather_poses: bad arguments");
+    if (n_local == 0) return SE3TN_OK;
+    // ncclResult_t ncclAllGather(const void* send, void* recv, size_t sendcount, ncclDataType_t, ncclComm_t, cudaStream_t)
+    typedef int (*AllGatherFn)(const void*, void*, size_t, int, void*, cudaStream_t);
+    static AllGatherFn fn = nullptr;
+    if (!fn) {
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);        // the copy torch (or the host) already loaded
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (h) fn = reinterpret_cast<AllGatherFn>(dlsym(h, "ncclAllGather"));
+        if (!fn) return fail(c, SE3TN_ERR_UNSUPPORTED, "se3tn_allgather_poses: libnccl.so.2 / ncclAllGather not found");
+    }
+    CU_TRY(c, cudaSetDevice(c->device));
+    const int kNcclFloat64 = 8;
+    const int rc = fn(local_poses, all_poses, static_cast<size_t>(n_local) * 16, kNcclFloat64, nccl_comm, static_cast<cudaStream_t>(stream));
+    if (rc != 0) return fail(c, SE3TN_ERR_CUDA, "se3tn_allgather_poses: ncclAllGather returned " + std::to_string(rc));
     return SE3TN_OK;
 }
 

@@ -227,6 +227,18 @@ class Engine:
                                          _stream(self.device)), self._ctx)
         return rgb, dep
 
+    # ------------------------------------------------------------------ pose exchange over a raw NCCL communicator
+    def allgather_poses_nccl(self, nccl_comm, local_poses, out=None, world_size=None):
+        """se3tn_allgather_poses: for hosts that own an ncclComm_t (an int / c_void_p handle).  torch.distributed users call
+        dist.all_gather_poses instead.  local_poses (n,4,4) float64 CUDA -> (world*n,4,4), rank-major."""
+        n = int(local_poses.shape[0])
+        if out is None:
+            if world_size is None:
+                raise ValueError('need out= or world_size=')
+            out = torch.empty((world_size * n, 4, 4), dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.se3tn_allgather_poses(self._ctx, C.c_void_p(int(nccl_comm)), _ptr(local_poses), _ptr(out), n, _stream(self.device)), self._ctx)
+        return out
+
     # ------------------------------------------------------------------ live-sensor depth (SURVEY 8f row 4)
     def fill_depth(self, depth_mm, max_depth=2.0, want_metres=False):
         """fill_depth as predict_ros.py:38-41 applies it (reference Utils.py:455-514): uint16 mm CUDA tensor (H,W) ->
