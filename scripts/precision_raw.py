@@ -1,3 +1,5 @@
+"""Precision study (CPU, not product code): exact emulation of TF32 / 3-product operand rounding per layer group on the
+raw-regime inputs, against the fp32 oracle -- the evidence behind the bf16x3 default.  Run from the repo root."""
 import importlib, sys, numpy as np, torch, torch.nn.functional as F
 sys.path.insert(0,'.'); sys.path.insert(0,'oracle')
 synth = importlib.import_module('iros20-6d-pose-tracking_b200.synth')
