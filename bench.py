@@ -396,6 +396,20 @@ def main():
                   'renders_per_s': nb / (kms * 1e-3), 'step_with_render_ms': rms, 'pairs_per_s_with_render': nb / (rms * 1e-3),
                   'note': 'render_kernel (csrc/render.cu): %d tracks x 176x176, float64 visibility + shading, one launch; replaces the reference\'s two OpenGL renders + glReadPixels per track and frame' % nb}
 
+    # ---- (3c) one object, one frame at a time, numpy in / numpy out: the reference's own calling pattern (predict.py:416) ----
+    single = None
+    if rank == 0 and world == 1:
+        h = sets[0][0]
+        f_rgb, f_depth = h['rgb'].numpy(), h['depth'].numpy()
+        p1, a1, d1 = h['poses'][0].numpy(), h['rgbA'][0].numpy(), h['depthA'][0].numpy()
+        for _ in range(5):
+            trk.on_track(p1, f_rgb, f_depth, rgbA=a1, depthA=d1)
+        t0 = time.perf_counter(); reps = 100
+        for _ in range(reps):
+            trk.on_track(p1, f_rgb, f_depth, rgbA=a1, depthA=d1)
+        single = {'ms_per_frame': (time.perf_counter() - t0) / reps * 1e3, 'frames_per_s': reps / (time.perf_counter() - t0),
+                  'note': 'Tracker.on_track(prev_pose, rgb, depth) for ONE object: synchronous, pageable numpy frame in (1.5 MB), numpy pose out, wall clock'}
+
     clocks = None
     if sampler:
         sampler.stop_flag = True; time.sleep(0.15)
@@ -426,7 +440,7 @@ def main():
                            'l2': 'flushed between timed steps (256 MiB memset, untimed); %d rotating input sets; per-step CUDA events, max over ranks' % N_INPUT_SETS,
                            'weights': 'random-init (seeded), %d weight set(s)%s' % (G, '' if G == 1 else ' (one per object class; all classes batched into the same 14 conv launches)')},
                 'gpu_launches': int(launches), 'launches_per_step': int(launches // max(args.steps, 1)),
-                'roofline': roofline, 'alt_precisions': alt, 'parity': parity, 'cpu_baseline': cpu, 'e2e': e2e, 'render': render, 'clocks': clocks,
+                'roofline': roofline, 'alt_precisions': alt, 'parity': parity, 'cpu_baseline': cpu, 'e2e': e2e, 'render': render, 'single_track': single, 'clocks': clocks,
                 'ms_per_step_min': float(ms_steps.min()), 'ms_per_step_median': float(np.median(ms_steps))}
         print(json.dumps(line), flush=True)
     if world > 1:
