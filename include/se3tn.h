@@ -221,6 +221,13 @@ int se3tn_debug_buffer(se3tn_ctx* ctx, int id, float** ptr, size_t* floats_per_i
 int se3tn_set_profiling(se3tn_ctx* ctx, int enable);
 int se3tn_get_profile(se3tn_ctx* ctx, float* ms);
 
+/* Device-side timeline of the conv kernels (contexts created with SE3TN_TRACE=1 in the environment): synchronises the
+ * device and copies 14 x 256 x 8 uint64 to the HOST: for conv launch l and CTA b, 8 %globaltimer (ns) stamps of the LAST
+ * forward -- 0 entry, 1 setup done, 2 first weights in shared memory, 3 first activation unit, 4 last MMA committed,
+ * 5 first accumulator ready, 6 last epilogue done, 7 exit (low 8 bits replaced by the SM id).  Profiling tool only. */
+#define SE3TN_TRACE_WORDS (14 * 256 * 8)
+int se3tn_get_trace(se3tn_ctx* ctx, unsigned long long* out);
+
 /* Number of kernels the last forward / track_batch call on this context launched. */
 int se3tn_last_launch_count(se3tn_ctx* ctx);
 

@@ -65,6 +65,8 @@ struct ConvPtrs {
     // fused AdaptiveAvgPool2d(1) (last conv of the heads, one image per M tile): instead of storing the activation, every
     // epilogue warp writes the column sums over its 32 rows to pool_part[image][row quadrant][channel]; null = normal store
     float* pool_part;
+    // device-side timeline (SE3TN_TRACE=1; null = off): 8 globaltimer stamps per CTA, see conv_umma2.cu trace_stamp()
+    unsigned long long* trace;
 };
 
 // ---- tcgen05 path only ------------------------------------------------------------------

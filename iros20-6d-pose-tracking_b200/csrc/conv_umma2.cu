@@ -127,6 +127,11 @@ __device__ __forceinline__ float selu_fast(float x) {
     return x > 0.f ? kScale * x : (kScale * kAlpha) * (__expf(x) - 1.f);
 }
 
+// timeline stamps (debug): slot 0 kernel entry, 1 setup done, 2 MMA warp has its first weights, 3 MMA warp has its first A unit,
+// 4 MMA warp issued its last commit, 5 epilogue got its first accumulator, 6 epilogue finished its last tile, 7 CTA exit (low 8 bits: SM id)
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ void trace_stamp(unsigned long long* tr, int slot) { if (tr) tr[blockIdx.x * 8 + slot] = gtimer(); }
+
 struct TileCoord2 { int ox, oy, n0, tx, ty; };
 struct WorkUnit { int mp, n_tile, grp; };
 
@@ -187,6 +192,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
     ptx::grid_dep_launch();
+    if (threadIdx.x == 0) trace_stamp(p.trace, 0);
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int m_units = (t.m_tiles + MT - 1) / MT;
@@ -244,6 +250,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
     if (PAIR) ptx::cluster_sync(); else __syncthreads();     // barrier inits must be visible to the peer before any remote signal
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) trace_stamp(p.trace, 1);
 
     if (warp == 0) {
         // ============================== A producer ================================
@@ -348,7 +355,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
             const int tile = im.tile;
             if (RESIDENT) {
                 const int wid = wid_of(tile);
-                if (wid != w_cur) { ptx::mbar_wait(&b_full[0], w_gen & 1); ptx::tc_fence_after(); w_cur = wid; ++w_gen; }
+                if (wid != w_cur) { ptx::mbar_wait(&b_full[0], w_gen & 1); ptx::tc_fence_after(); w_cur = wid; ++w_gen; if (it == 0 && lane == 0) trace_stamp(p.trace, 2); }
             }
             const int acc = it % C::kNAcc;
             const uint32_t acc_phase = (it / C::kNAcc) & 1;
@@ -361,6 +368,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                 for (int u = 0; u < KT::NU; ++u) {
                     ptx::mbar_wait(&a_full[astage], aphase);
                     ptx::tc_fence_after();
+                    if (it == 0 && ch == im.c0 && u == 0 && lane == 0) trace_stamp(p.trace, 3);
                     // low descriptor words: (addr >> 4) | LBO(=1) << 16; +2 per 32-byte K step, +8 per pixel row.
                     // base_offset stays 0: the 128B swizzle is a function of absolute smem address bits
                     // (profiles/r01_umma_desc_rowshift_probe.txt)
@@ -375,6 +383,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                         } else {
                             ptx::mbar_wait(&b_full[bstage], bphase);
                             ptx::tc_fence_after();
+                            if (it == 0 && ch == im.c0 && u == 0 && k == 0 && lane == 0) trace_stamp(p.trace, 2);
                             b_lo = ((ptx::smem_u32(sB + bstage * C::kBTile) & 0x3FFFFu) >> 4) | (1u << 16);
                         }
                         const uint32_t a_lo = a_unit_lo + KT::shift(u, k) * (kChunkBytes >> 4);
@@ -440,6 +449,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
             }
             __syncwarp();
         }
+        if (lane == 0) trace_stamp(p.trace, 4);
     } else if (warp >= 4) {
         // ============================== epilogue (8 warps) ==========================
         ptx::grid_dep_wait();                       // residual reads / output writes must follow the previous kernel
@@ -487,6 +497,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                 }
                 ptx::mbar_wait(&tmem_full[acc], acc_phase);
                 ptx::tc_fence_after();
+                if (it == 0 && threadIdx.x == 128) trace_stamp(p.trace, 5);
                 if (t.debug & 4) {                  // timing experiment: free the accumulator at once, no epilogue work
                     ptx::tc_fence_before(); __syncwarp();
                     if (lane == 0) { if (leader) ptx::mbar_arrive(&tmem_empty[acc]); else ptx::mbar_arrive_cluster(&tmem_empty[acc], 0); }
@@ -507,6 +518,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
                             const bool valid = (pn < t.bn) && (n < g.n_img) && (y < g.Ho) && (x < g.Wo);
                             __syncwarp();
                             rowtab[lane] = valid ? (n * g.Ho + y) * g.Wo + x : -1;   // pixel index of TMEM row q*32 + lane
+                            __syncwarp();
                         }
                         const int ch0 = wu.grp * g.cout + wu.n_tile * BN + half * kCols;
                         const float* bias_base = p.img_wid ? p.gbias[p.img_wid[tc.n0] * kLayersPerSet] : p.bias;
@@ -745,6 +757,7 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
 
                 ptx::mbar_wait(&tmem_full[acc], acc_phase);
                 ptx::tc_fence_after();
+                if (it == 0 && threadIdx.x == 128) trace_stamp(p.trace, 5);
                 if (t.debug & 4) {                  // timing experiment: free the accumulator at once, no epilogue work
                     ptx::tc_fence_before(); __syncwarp();
                     if (lane == 0) { if (leader) ptx::mbar_arrive(&tmem_empty[acc]); else ptx::mbar_arrive_cluster(&tmem_empty[acc], 0); }
@@ -821,8 +834,10 @@ conv_umma2_kernel(const __grid_constant__ UmmaMaps maps, const ConvGeom g, const
         }
     }
 
+    if (threadIdx.x == 128) trace_stamp(p.trace, 6);
     ptx::tc_fence_before();
     if (PAIR) ptx::cluster_sync(); else __syncthreads();
+    if (threadIdx.x == 0 && p.trace) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); p.trace[blockIdx.x * 8 + 7] = (gtimer() & ~0xffull) | (smid & 0xff); }
     if (warp == 2) {
         ptx::tc_fence_after();
         if (PAIR) ptx::tmem_dealloc_2sm(tmem_base, C::kTmemCols); else ptx::tmem_dealloc(tmem_base, C::kTmemCols);

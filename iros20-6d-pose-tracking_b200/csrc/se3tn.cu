@@ -135,6 +135,7 @@ struct se3tn_ctx {
                                      // (the 128 KB partial dump + fix-up per CTA costs what the 12.5 % shorter makespan wins) and results then
                                      // depend in the last ulps on a pair's position in the batch, so off by default
     float* sk_part = nullptr; int* sk_flags = nullptr; int sk_seq = 0;   // stream-K partial slots (one per SM), flags, launch counter
+    unsigned long long* trace = nullptr;   // SE3TN_TRACE=1: [14 layers][256 CTAs][8] globaltimer stamps of the last forward (conv_umma2.cu trace_stamp)
     int debug_flags = 0;             // SE3TN_DEBUG_SKIP: timing experiments (bit0 no B fills, bit1 no A fills); results invalid
     int base_off_mode = 0;           // SE3TN_BASE_OFF: UMMA descriptor base_offset convention for row-shifted starts
     EncodeTiledFn encode = nullptr;
@@ -511,6 +512,7 @@ int run_network(se3tn_ctx* c, int weight_id, int first, int n, int precision,
         p.gbmaps = img_wid ? (precision == SE3TN_PREC_BF16X3 ? c->d_bmaps_x3 : (bf16 ? c->d_bmaps_bf16 : c->d_bmaps_tf32)) + li : nullptr;
         p.gbias = img_wid ? c->d_bias + li : nullptr;
         p.sk_part = nullptr; p.sk_flags = nullptr; p.pool_part = nullptr;
+        p.trace = c->trace ? c->trace + static_cast<size_t>(li) * 256 * 8 : nullptr;
         if (tensor && c->conv_version == 2) {
             UmmaMaps maps;
             const int nmaps = (L.kind == K_STEM) ? 2 : (L.kind == K_S2 ? 4 : 1);
@@ -618,6 +620,9 @@ int se3tn_create(int device, int max_batch, void* workspace, se3tn_ctx** out) {
     if (const char* ov = getenv("SE3TN_PAIR")) c->pair = atoi(ov) != 0;
     if (const char* ov = getenv("SE3TN_STREAMK")) c->streamk = atoi(ov) != 0;
     if (const char* ov = getenv("SE3TN_FUSE_POOL")) c->fuse_pool = atoi(ov) != 0;
+    if (const char* ov = getenv("SE3TN_TRACE")) {
+        if (atoi(ov) != 0 && cudaMalloc(&c->trace, 14 * 256 * 8 * sizeof(unsigned long long)) == cudaSuccess) cudaMemset(c->trace, 0, 14 * 256 * 8 * sizeof(unsigned long long));
+    }
 
     void* fn = nullptr; cudaDriverEntryPointQueryResult qres;
     e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -665,7 +670,7 @@ void se3tn_destroy(se3tn_ctx* c) {
     cudaFree(c->d_mean32); cudaFree(c->d_std32); cudaFree(c->d_mean64); cudaFree(c->d_std64);
     cudaFree(c->d_bmaps_tf32); cudaFree(c->d_bmaps_bf16); cudaFree(c->d_bmaps_x3); cudaFree(c->d_bias); cudaFree(c->d_fc);
     for (int i = 0; i < SE3TN_PROFILE_SLOTS; ++i) { if (c->ev0[i]) cudaEventDestroy(c->ev0[i]); if (c->ev1[i]) cudaEventDestroy(c->ev1[i]); }
-    cudaFree(c->sk_part); cudaFree(c->sk_flags); cudaFree(c->pool_part);
+    cudaFree(c->sk_part); cudaFree(c->sk_flags); cudaFree(c->pool_part); cudaFree(c->trace);
     for (auto& kv : c->meshes) { cudaFree(const_cast<float*>(kv.second.pos)); cudaFree(const_cast<float*>(kv.second.nrm)); cudaFree(const_cast<uint8_t*>(kv.second.col)); cudaFree(const_cast<int*>(kv.second.faces)); }
     cudaFree(c->d_meshes); cudaFree(c->render_proj); cudaFree(c->render_unif);
     cudaFree(c->fill.a); cudaFree(c->fill.b); cudaFree(c->fill.lut); cudaFree(c->fill.minmax);
@@ -1052,6 +1057,16 @@ int se3tn_debug_buffer(se3tn_ctx* c, int id, float** ptr, size_t* floats_per_ima
 }
 
 int se3tn_last_launch_count(se3tn_ctx* c) { return c ? c->launches : 0; }
+
+int se3tn_get_trace(se3tn_ctx* c, unsigned long long* out) {
+    if (!c) return SE3TN_ERR_INVALID;
+    if (!out) return fail(c, SE3TN_ERR_INVALID, "se3tn_get_trace: null argument");
+    if (!c->trace) return fail(c, SE3TN_ERR_STATE, "se3tn_get_trace: the context was created without SE3TN_TRACE=1");
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaDeviceSynchronize());
+    CU_TRY(c, cudaMemcpy(out, c->trace, 14 * 256 * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return SE3TN_OK;
+}
 
 int se3tn_set_profiling(se3tn_ctx* c, int enable) {
     if (!c) return SE3TN_ERR_INVALID;

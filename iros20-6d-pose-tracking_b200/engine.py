@@ -270,6 +270,12 @@ class Engine:
         _lib.check(self.lib.se3tn_get_profile(self._ctx, ms), self._ctx)
         return np.array(ms[:], dtype=np.float64)
 
+    def get_trace(self):
+        """(14, 256, 8) uint64 globaltimer stamps of the last forward's conv CTAs (needs SE3TN_TRACE=1 at Engine creation)."""
+        out = np.zeros((14, 256, 8), dtype=np.uint64)
+        _lib.check(self.lib.se3tn_get_trace(self._ctx, out.ctypes.data_as(C.c_void_p)), self._ctx)
+        return out
+
     def last_launch_count(self):
         return self.lib.se3tn_last_launch_count(self._ctx)
 
