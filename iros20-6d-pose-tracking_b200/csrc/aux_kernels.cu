@@ -61,7 +61,7 @@ preprocess_kernel(PreprocessArgs a)
     // with the SAME IEEE division the per-pixel code would use (bit-identical), leaving two divisions per pixel (the depths)
     __shared__ float s_lut[6][256];
     {
-        const int wi0 = a.weight_ids ? a.weight_ids[n] : 0;
+        const int wi0 = a.weight_ids ? min(max(a.weight_ids[n], 0), a.stats_rows - 1) : 0;   // ids without statistics are rejected on the host where it can see them; never index past the table
         const float v = static_cast<float>(threadIdx.x);
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
@@ -88,7 +88,7 @@ preprocess_kernel(PreprocessArgs a)
     const double z = pose[11];
     const bool gl = z < 0;
     const double z1000 = __dmul_rn(z, 1000.0);
-    const int wi = a.weight_ids ? a.weight_ids[n] : 0;
+    const int wi = a.weight_ids ? min(max(a.weight_ids[n], 0), a.stats_rows - 1) : 0;
     const size_t img0 = static_cast<size_t>(n) * kImg * kImg;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -362,16 +362,73 @@ head_kernel(const float4* __restrict__ x, const float* __restrict__ fcw /*[6][51
     }
 }
 
-// Head on the fused average pool (conv_umma2.cu writes pool_part[image][4 row quadrants][1024] column sums): mean -> Linear -> tanh.
-__global__ void __launch_bounds__(128)
+// =============================================================================================
+// K6 pose update (reference datasets.py:159-175): t' = t + float32(trans*tn);
+// R' = float32(Rodrigues(float32(rot*rn))) . R, all remaining arithmetic in float64 (F9/F10).
+// Rodrigues follows OpenCV's cvRodrigues2 vector->matrix branch:
+//   theta = |r|; theta < DBL_EPSILON -> I; else R = cos*I + (1-cos)*rr^T + sin*[r]x, r <- r/theta.
+// =============================================================================================
+__device__ __forceinline__ void rodrigues_exp_f32in(float rx32, float ry32, float rz32, double R[9], bool round_f32)
+{
+    double rx = rx32, ry = ry32, rz = rz32;
+    const double theta = sqrt(rx * rx + ry * ry + rz * rz);
+    if (theta < DBL_EPSILON) {
+        R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
+        return;
+    }
+    const double c = cos(theta), s = sin(theta), c1 = 1.0 - c, it = 1.0 / theta;
+    rx *= it; ry *= it; rz *= it;
+    // same association as cv::Matx: c*I + c1*(r r^T) + s*[r]x, outer products formed first
+    const double xx = rx * rx, xy = rx * ry, xz = rx * rz, yy = ry * ry, yz = ry * rz, zz = rz * rz;
+    R[0] = c + c1 * xx;      R[1] = c1 * xy - s * rz; R[2] = c1 * xz + s * ry;
+    R[3] = c1 * xy + s * rz; R[4] = c + c1 * yy;      R[5] = c1 * yz - s * rx;
+    R[6] = c1 * xz - s * ry; R[7] = c1 * yz + s * rx; R[8] = c + c1 * zz;
+    if (round_f32)
+#pragma unroll
+        for (int i = 0; i < 9; ++i) R[i] = static_cast<double>(static_cast<float>(R[i]));
+}
+
+// one track: A (row-major 4x4) and the network's 3+3 output -> B
+__device__ __forceinline__ void pose_update_one(const double* A, const float tr[3], const float ro[3], float tn, float rn,
+                                                double* B /* may alias A */)
+{
+    // float32 * python-float stays float32 in numpy
+    const float t0 = __fmul_rn(tr[0], tn), t1 = __fmul_rn(tr[1], tn), t2 = __fmul_rn(tr[2], tn);
+    const float r0 = __fmul_rn(ro[0], rn), r1 = __fmul_rn(ro[1], rn), r2 = __fmul_rn(ro[2], rn);
+    double R[9];
+    rodrigues_exp_f32in(r0, r1, r2, R, true);
+    double out[16];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            out[r * 4 + c] = __dadd_rn(__dadd_rn(__dmul_rn(R[r * 3 + 0], A[0 * 4 + c]), __dmul_rn(R[r * 3 + 1], A[1 * 4 + c])),
+                                       __dmul_rn(R[r * 3 + 2], A[2 * 4 + c]));
+    out[3] = static_cast<double>(t0) + A[3];
+    out[7] = static_cast<double>(t1) + A[7];
+    out[11] = static_cast<double>(t2) + A[11];
+    out[12] = 0; out[13] = 0; out[14] = 0; out[15] = 1;        // B_in_cam starts as np.eye(4)
+#pragma unroll
+    for (int k = 0; k < 16; ++k) B[k] = out[k];
+}
+
+// Head on the fused average pool (conv_umma2.cu writes pool_part[image][4 row quadrants][1024] column sums): mean -> Linear -> tanh for
+// BOTH heads of one image per CTA (threads 0-127 translation, 128-255 rotation), and -- when poses_in is given -- the pose update of that
+// track by thread 0 (K4 + K6 in one launch: the update is a 650-instruction fp64 chain per track, pure latency as its own kernel).
+// `zero_words` (nullable): scheduler / dependency counters of the step that just finished, cleared for the next one by block 0.
+__global__ void __launch_bounds__(256)
 head_pooled_kernel(const float4* __restrict__ part, const float* __restrict__ fcw, const float* __restrict__ fcb,
                    float* __restrict__ out_trans, float* __restrict__ out_rot, int npix,
-                   const int* __restrict__ img_wid, const float* const* __restrict__ fc_table)
+                   const int* __restrict__ img_wid, const float* const* __restrict__ fc_table,
+                   const double* poses_in, double* poses_out /* may alias */, float tn, float rn,
+                   unsigned* __restrict__ zero_words, int n_zero)
 {
     ptx::grid_dep_launch();
-    __shared__ float red[4][3];
-    const int n = blockIdx.x, head = blockIdx.y, t = threadIdx.x;
+    __shared__ float red[8][3];
+    __shared__ float six[6];
+    const int n = blockIdx.x, head = threadIdx.x >> 7, t = threadIdx.x & 127;
     ptx::grid_dep_wait();
+    if (zero_words && blockIdx.x == 0) for (int i = threadIdx.x; i < n_zero; i += blockDim.x) zero_words[i] = 0u;
     if (img_wid) { fcw = fc_table[img_wid[n]]; fcb = fcw + 6 * 512; }
     const float4* pp = part + static_cast<size_t>(n) * 4 * 256 + head * 128 + t;
     const float4 a0 = pp[0], a1 = pp[256], a2 = pp[512], a3 = pp[768];
@@ -388,19 +445,25 @@ head_pooled_kernel(const float4* __restrict__ part, const float* __restrict__ fc
     for (int off = 16; off > 0; off >>= 1)
 #pragma unroll
         for (int o = 0; o < 3; ++o) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], off);
-    if ((t & 31) == 0) { red[t >> 5][0] = acc[0]; red[t >> 5][1] = acc[1]; red[t >> 5][2] = acc[2]; }
+    if ((t & 31) == 0) { red[threadIdx.x >> 5][0] = acc[0]; red[threadIdx.x >> 5][1] = acc[1]; red[threadIdx.x >> 5][2] = acc[2]; }
     __syncthreads();
-    if (t < 3) {
-        const float v = red[0][t] + red[1][t] + red[2][t] + red[3][t] + fcb[head * 3 + t];
-        (head == 0 ? out_trans : out_rot)[n * 3 + t] = tanhf(v);
+    if (threadIdx.x < 6) {
+        const int h = threadIdx.x / 3, o = threadIdx.x - 3 * h;
+        const float v = tanhf(red[4 * h + 0][o] + red[4 * h + 1][o] + red[4 * h + 2][o] + red[4 * h + 3][o] + fcb[h * 3 + o]);
+        (h == 0 ? out_trans : out_rot)[n * 3 + o] = v;
+        six[threadIdx.x] = v;
     }
+    if (!poses_in) return;
+    __syncthreads();
+    if (threadIdx.x == 0) pose_update_one(poses_in + n * 16, six, six + 3, tn, rn, poses_out + n * 16);
 }
 cudaError_t launch_head_pooled(const float* part, const float* fcw, const float* fcb, float* out_trans, float* out_rot,
-                               int n_img, int npix, const int* img_wid, const float* const* fc_table, cudaStream_t s) {
+                               int n_img, int npix, const int* img_wid, const float* const* fc_table,
+                               const double* poses_in, double* poses_out, float tn, float rn, unsigned* zero_words, int n_zero, cudaStream_t s) {
     if (n_img <= 0) return cudaSuccess;
     const float4* p4 = reinterpret_cast<const float4*>(part);
-    void* args[] = {&p4, &fcw, &fcb, &out_trans, &out_rot, &npix, &img_wid, &fc_table};
-    return launch_pdl(reinterpret_cast<const void*>(head_pooled_kernel), dim3(n_img, 2), dim3(128), args, s);
+    void* args[] = {&p4, &fcw, &fcb, &out_trans, &out_rot, &npix, &img_wid, &fc_table, &poses_in, &poses_out, &tn, &rn, &zero_words, &n_zero};
+    return launch_pdl(reinterpret_cast<const void*>(head_pooled_kernel), dim3(n_img), dim3(256), args, s);
 }
 
 cudaError_t launch_head(const float* x, const float* fcw, const float* fcb, float* out_trans, float* out_rot,
@@ -414,8 +477,9 @@ cudaError_t launch_head(const float* x, const float* fcw, const float* fcb, floa
 // =============================================================================================
 // NHWC -> NCHW (the 'feature' entry of the reference's output dict, se3_tracknet.py:96)
 // =============================================================================================
+// storage: 0 fp32 words, 1 [32 x bf16 hi | 32 x bf16 lo] per 32-channel chunk, 2 plain bf16 (conv_common.h)
 __global__ void __launch_bounds__(256)
-nhwc_to_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int HW, int C, int split_bf16)
+nhwc_to_nchw_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, int HW, int C, int storage)
 {
     __shared__ float tile[32][33];
     const int n = blockIdx.z;
@@ -425,11 +489,12 @@ nhwc_to_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int H
         const int p = p0 + j, c = c0 + tx;
         float val = 0.f;
         if (p < HW && c < C) {
-            if (!split_bf16) val = in[(static_cast<size_t>(n) * HW + p) * C + c];
-            else {
-                const uint8_t* cb = reinterpret_cast<const uint8_t*>(in + (static_cast<size_t>(n) * HW + p) * C + (c & ~31)) + (c & 31) * 2;
+            const size_t pix = static_cast<size_t>(n) * HW + p;
+            if (storage == 0) val = reinterpret_cast<const float*>(in)[pix * C + c];
+            else if (storage == 1) {
+                const uint8_t* cb = in + (pix * C + (c & ~31)) * 4 + (c & 31) * 2;
                 val = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(cb)) + __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(cb + 64));
-            }
+            } else val = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(in)[pix * C + c]);
         }
         tile[j][tx] = val;
     }
@@ -440,17 +505,16 @@ nhwc_to_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int H
     }
 }
 
-cudaError_t launch_nhwc_to_nchw(const float* in, float* out, int n_img, int HW, int C, int split_bf16, cudaStream_t s) {
+cudaError_t launch_nhwc_to_nchw(const void* in, float* out, int n_img, int HW, int C, int storage, cudaStream_t s) {
     if (n_img <= 0) return cudaSuccess;
     dim3 grid((HW + 31) / 32, (C + 31) / 32, n_img);
-    nhwc_to_nchw_kernel<<<grid, 256, 0, s>>>(in, out, HW, C, split_bf16);
+    nhwc_to_nchw_kernel<<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(in), out, HW, C, storage);
     return cudaGetLastError();
 }
 
 // =============================================================================================
-// Weight preparation for the bf16 hi/lo modes (conv_umma2.cu PREC_BF16X3 / PREC_BF16).
-// 3x3 layers: every 32-word K chunk of a weight row becomes [32 x bf16 hi | 32 x bf16 lo].
-// Stem: per (filter row r, pass): 8 pixels x 16 B; pass 0 = [w_hi(4) | w_hi(4)], pass 1 = [w_lo(4) | 0].
+// Weight preparation for the bf16 modes (conv_umma2.cu PREC_BF16X3 / PREC_BF16).
+// Trunk layers, PREC_BF16X3: every 32-word K chunk of a weight row becomes [32 x bf16 hi | 32 x bf16 lo].
 // =============================================================================================
 __global__ void split_weights_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, size_t words)
 {
@@ -466,20 +530,17 @@ __global__ void split_weights_kernel(const float* __restrict__ src, uint8_t* __r
     }
 }
 
-__global__ void split_stem_weights_kernel(const float* __restrict__ src /*[64][7*32]*/, uint8_t* __restrict__ dst /*[64][7*2*32 words]*/)
+// plain bf16 copy of a K-major weight matrix (PREC_BF16: 64 channels per 128-byte K chunk)
+__global__ void to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;      // one thread per (co, r, p): 4 channels
-    if (i >= 64 * 7 * 8) return;
-    const int p = i & 7, r = (i >> 3) % 7, co = i / 56;
-    const float* w = src + co * 224 + r * 32 + p * 4;
-    __nv_bfloat16 h[4], l[4];
-    for (int c = 0; c < 4; ++c) { h[c] = __float2bfloat16_rn(w[c]); l[c] = __float2bfloat16_rn(w[c] - __bfloat162float(h[c])); }
-    uint8_t* d0 = dst + (static_cast<size_t>(co) * 448 + (r * 2 + 0) * 32 + p * 4) * 4;
-    uint8_t* d1 = dst + (static_cast<size_t>(co) * 448 + (r * 2 + 1) * 32 + p * 4) * 4;
-    for (int c = 0; c < 4; ++c) {
-        reinterpret_cast<__nv_bfloat16*>(d0)[c] = h[c]; reinterpret_cast<__nv_bfloat16*>(d0)[4 + c] = h[c];
-        reinterpret_cast<__nv_bfloat16*>(d1)[c] = l[c]; reinterpret_cast<__nv_bfloat16*>(d1)[4 + c] = __float2bfloat16_rn(0.f);
-    }
+    size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (; i < n; i += stride) dst[i] = __float2bfloat16_rn(src[i]);
+}
+cudaError_t launch_to_bf16(const float* src, void* dst, size_t n, cudaStream_t s) {
+    if (!n) return cudaSuccess;
+    to_bf16_kernel<<<1024, 256, 0, s>>>(src, static_cast<__nv_bfloat16*>(dst), n);
+    return cudaGetLastError();
 }
 
 // STACK layouts for the resident-weight kernels (conv_umma2.cu): 128 rows, rows 0-63 carry the hi parts, rows 64-127 the lo parts.
@@ -535,65 +596,18 @@ cudaError_t launch_split_weights(const float* src, void* dst, size_t words, cuda
     split_weights_kernel<<<1024, 256, 0, s>>>(src, static_cast<uint8_t*>(dst), words);
     return cudaGetLastError();
 }
-cudaError_t launch_split_stem_weights(const float* src, void* dst, cudaStream_t s) {
-    split_stem_weights_kernel<<<(64 * 7 * 8 + 127) / 128, 128, 0, s>>>(src, static_cast<uint8_t*>(dst));
-    return cudaGetLastError();
-}
-
-// =============================================================================================
-// K6 pose update (reference datasets.py:159-175): t' = t + float32(trans*tn);
-// R' = float32(Rodrigues(float32(rot*rn))) . R, all remaining arithmetic in float64 (F9/F10).
-// Rodrigues follows OpenCV's cvRodrigues2 vector->matrix branch:
-//   theta = |r|; theta < DBL_EPSILON -> I; else R = cos*I + (1-cos)*rr^T + sin*[r]x, r <- r/theta.
-// =============================================================================================
-__device__ __forceinline__ void rodrigues_exp_f32in(float rx32, float ry32, float rz32, double R[9], bool round_f32)
-{
-    double rx = rx32, ry = ry32, rz = rz32;
-    const double theta = sqrt(rx * rx + ry * ry + rz * rz);
-    if (theta < DBL_EPSILON) {
-        R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
-        return;
-    }
-    const double c = cos(theta), s = sin(theta), c1 = 1.0 - c, it = 1.0 / theta;
-    rx *= it; ry *= it; rz *= it;
-    // same association as cv::Matx: c*I + c1*(r r^T) + s*[r]x, outer products formed first
-    const double xx = rx * rx, xy = rx * ry, xz = rx * rz, yy = ry * ry, yz = ry * rz, zz = rz * rz;
-    R[0] = c + c1 * xx;      R[1] = c1 * xy - s * rz; R[2] = c1 * xz + s * ry;
-    R[3] = c1 * xy + s * rz; R[4] = c + c1 * yy;      R[5] = c1 * yz - s * rx;
-    R[6] = c1 * xz - s * ry; R[7] = c1 * yz + s * rx; R[8] = c + c1 * zz;
-    if (round_f32)
-#pragma unroll
-        for (int i = 0; i < 9; ++i) R[i] = static_cast<double>(static_cast<float>(R[i]));
-}
-
-__global__ void pose_update_kernel(const double* __restrict__ poses_in, const float* __restrict__ trans,
+// stand-alone K6 (se3tn_pose_update; the batched path runs it inside head_pooled_kernel)
+__global__ void pose_update_kernel(const double* poses_in, const float* __restrict__ trans,
                                    const float* __restrict__ rot, float tn, float rn,
-                                   double* __restrict__ poses_out, int n)
+                                   double* poses_out /* may alias poses_in */, int n)
 {
     ptx::grid_dep_launch();
     ptx::grid_dep_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const double* A = poses_in + i * 16;
-    double* B = poses_out + i * 16;
-    // float32 * python-float stays float32 in numpy
-    const float t0 = __fmul_rn(trans[i * 3 + 0], tn), t1 = __fmul_rn(trans[i * 3 + 1], tn), t2 = __fmul_rn(trans[i * 3 + 2], tn);
-    const float r0 = __fmul_rn(rot[i * 3 + 0], rn), r1 = __fmul_rn(rot[i * 3 + 1], rn), r2 = __fmul_rn(rot[i * 3 + 2], rn);
-    double R[9];
-    rodrigues_exp_f32in(r0, r1, r2, R, true);
-    double out[16];
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-            out[r * 4 + c] = __dadd_rn(__dadd_rn(__dmul_rn(R[r * 3 + 0], A[0 * 4 + c]), __dmul_rn(R[r * 3 + 1], A[1 * 4 + c])),
-                                       __dmul_rn(R[r * 3 + 2], A[2 * 4 + c]));
-    out[3] = static_cast<double>(t0) + A[3];
-    out[7] = static_cast<double>(t1) + A[7];
-    out[11] = static_cast<double>(t2) + A[11];
-    out[12] = 0; out[13] = 0; out[14] = 0; out[15] = 1;        // B_in_cam starts as np.eye(4)
-#pragma unroll
-    for (int k = 0; k < 16; ++k) B[k] = out[k];
+    const float tr[3] = {trans[i * 3 + 0], trans[i * 3 + 1], trans[i * 3 + 2]};
+    const float ro[3] = {rot[i * 3 + 0], rot[i * 3 + 1], rot[i * 3 + 2]};
+    pose_update_one(poses_in + i * 16, tr, ro, tn, rn, poses_out + i * 16);
 }
 
 cudaError_t launch_pose_update(const double* poses_in, const float* trans, const float* rot, float tn, float rn,

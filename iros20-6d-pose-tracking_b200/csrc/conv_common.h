@@ -1,13 +1,20 @@
-// Shared host/device descriptors for one convolution launch of the se(3)-TrackNet conv stack.
+// Shared host/device descriptors for the convolution launches of the se(3)-TrackNet conv stack.
 //
 // Every conv on the path (reference se3_tracknet.py:57-78; 7x7 s2 stem, 3x3 s1, 3x3 s2) is
 // described the same way: an NHWC activation tensor, a list of filter "taps", each tap a
-// displacement in input pixels plus `k_per_tap` contiguous input floats, and a K-major weight
+// displacement in input pixels plus `k_per_tap` contiguous input channels, and a K-major weight
 // matrix W[g*Cout + co][tap*k_per_tap + c] with the eval-mode BatchNorm folded in.
 //
 //  * 3x3:  9 taps (dy,dx) in {-1,0,1}^2, k_per_tap = Cin (channels of one pixel)
 //  * stem: 7 taps (one per filter ROW r), k_per_tap = 32 = 8 pixels x 4 channels of the
 //          zero-padded NHWC4 input starting at x = 2*ox (7 real filter columns + 1 zero column)
+//
+// Two tcgen05 kernels (conv_umma2.cu) cover the 14 launches' worth of layers:
+//  * conv_resident_kernel: Cout = 64 layers (the two stems, the six 64-channel 3x3 convs); the whole weight
+//    matrix lives in shared memory; one launch per layer, static tile ranges.
+//  * conv_trunk_kernel: the Cout >= 256 layers (convAB1, convAB2.*, {trans,rot}_conv1, {trans,rot}_conv2.*) as ONE
+//    launch: a persistent CTA per SM pulls (layer, image, tile) work units from a global counter and per-image
+//    completion counters carry the layer-to-layer dependencies, so no SM idles at a layer boundary.
 #pragma once
 #include <cstdint>
 #include <cuda.h>
@@ -17,21 +24,23 @@ namespace se3tn {
 
 constexpr int kMaxTaps = 9;
 constexpr int kBlockM = 128;          // UMMA M (TMEM lanes)
-constexpr int kChunkBytes = 128;      // one SWIZZLE_128B row: 32 tf32 / 64 bf16 along K
+constexpr int kChunkBytes = 128;      // one SWIZZLE_128B row of K: 32 tf32 words / 32 x [bf16 hi, bf16 lo] / 64 bf16
 
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_SELU = 2 };
+enum { KIND_S1 = 0, KIND_S2 = 1, KIND_STEM = 2 };            // conv kinds (compile-time unit tables in conv_umma2.cu)
+enum { PREC_TF32 = 0, PREC_BF16X3 = 1, PREC_BF16 = 2 };      // arithmetic / storage of the tcgen05 kernels
+// Activation storage per precision: PREC_TF32 fp32 words (tf32-rounded); PREC_BF16X3 the same 4 bytes per channel as
+// [32 x bf16 hi | 32 x bf16 lo] per 32-channel chunk; PREC_BF16 2 bytes per channel, 64 channels per 128-byte chunk
+// (the stem INPUT stays 16 bytes per pixel [4 x hi | 4 x lo] in both bf16 modes).
+__host__ __device__ constexpr int prec_bytes_per_channel(int prec) { return prec == PREC_BF16 ? 2 : 4; }
 
 struct Tap {
     int16_t dy, dx;      // input-pixel displacement of this tap relative to (oy*stride, ox*stride)
-    int8_t  map;         // tcgen05 path: which A tensor map (s2: 4 parity views; stem: one per filter row)
-    int8_t  c1, c2;      // tcgen05 path: TMA coordinate deltas for dims 1 (x) and 2 (y)
-    int8_t  pad_;
 };
 
+// geometry of one conv for the FFMA cross-check kernel (conv_direct.cu) -- fp32 NHWC, 4 bytes per channel
 struct ConvGeom {
-    // input (NHWC, `in_cstride` floats per pixel, channel window starting at in_coff (+ g*cin))
     int Hin, Win, in_cstride, in_coff;
-    // output
     int Ho, Wo, stride;
     int cin;             // K floats per tap per group
     int cout;            // per group
@@ -39,14 +48,10 @@ struct ConvGeom {
     int num_taps;
     int n_img;
     Tap taps[kMaxTaps];
-    // epilogue
     int out_cstride, out_coff;
     int res_cstride, res_coff;
     int act;
-    int round_tf32;      // fp32-word storage: round stored activations to tf32 (rna) so the next UMMA sees exact operands
 };
-
-constexpr int kLayersPerSet = 14;     // conv launches per weight set (stride of the per-set device tables)
 
 struct ConvPtrs {
     const float* in;
@@ -54,68 +59,71 @@ struct ConvPtrs {
     const float* bias;   // [groups*cout]
     const float* res;    // nullable, NHWC
     float* out;
-    // multi-weight-set launches (v2 kernel): weight-set id per absolute image index, and per-set tables that are
-    // already offset to this layer (entry of set w at [w * kLayersPerSet])
-    const int* img_wid;            // nullable: single-set launch (maps.b / bias above)
-    const CUtensorMap* gbmaps;     // device array of weight tensor maps
-    const float* const* gbias;     // device array of bias pointers
-    // stream-K (ring-weight kernels): one 128 x 256 fp32 partial-accumulator slot and one flag per CTA; null = off
-    float* sk_part;
-    int* sk_flags;
-    // fused AdaptiveAvgPool2d(1) (last conv of the heads, one image per M tile): instead of storing the activation, every
-    // epilogue warp writes the column sums over its 32 rows to pool_part[image][row quadrant][channel]; null = normal store
-    float* pool_part;
-    // device-side timeline (SE3TN_TRACE=1; null = off): 8 globaltimer stamps per CTA, see conv_umma2.cu trace_stamp()
+};
+
+constexpr int kLayersPerSet = 14;     // conv layers per weight set (stride of the per-set device tables)
+
+// ---- tcgen05 kernels ----------------------------------------------------------------------------------------
+// One layer as the device sees it.  Channel counts are in CHANNELS; byte strides follow from the precision.
+struct LayerDesc {
+    CUtensorMap amap[4];   // activation views: S1 one map; S2 four parity views (py*2+px); stem two (even / odd input rows)
+    CUtensorMap bmap;      // weights of weight set `single_wid` (multi-set launches take theirs from gbmaps)
+    const float* bias;     // [groups*cout] fp32 (single-set)
+    uint8_t* out;          // NHWC output buffer (image 0)
+    const uint8_t* res;    // residual input (nullable), same storage format as out
+    float* pool_part;      // non-null: fused AdaptiveAvgPool2d(1): column sums [image][4 row quadrants][out_c] instead of the activation
+    int kind;              // KIND_*
+    int chunks;            // 128-byte K chunks per pixel per group (cin * bytes / 128)
+    int cin_words;         // 32-bit words of K per tap per group (weight-matrix K offset of a tap = tap * cin_words)
+    int in_cbase_words;    // word offset of group 0's channels inside a pixel of the input buffer
+    int in_gstride_words;  // word offset between groups
+    int cout;              // per group
+    int groups;
+    int n_tiles;           // cout / BN
+    int tiles_x, tiles_y;  // 11x11 output tiles per image
+    int Ho, Wo;
+    int act;
+    int out_c, out_coff;   // channels per pixel of the output buffer, channel offset of this layer's channel 0
+    int res_c;             // channels per pixel of the residual buffer
+    int li;                // layer index (row of the per-set tables)
+    // trunk scheduling
+    int unit_base;         // first global work-unit index of this layer
+    int units_per_image;   // tiles_x * tiles_y * n_tiles * groups
+    int dep_layer;         // index (within the launch) of the layer whose per-image completion this layer waits for; -1: none
+    unsigned dep_target;   // value done[dep_layer][image] reaches when that image is complete (8 epilogue warps x units per image)
+};
+
+constexpr int kTrunkMaxLayers = 6;
+
+struct TrunkParams {
+    LayerDesc layer[kTrunkMaxLayers];
+    int n_layers;
+    int total_units;
+    int img_first, n_img;          // absolute image range [img_first, img_first + n_img)
+    int max_batch;                 // row length of the done[] table
+    unsigned* sched;               // [0] next work unit; then done[layer][image] counters (zeroed before the launch)
+    const int* img_wid;            // nullable: weight-set id per absolute image index
+    const CUtensorMap* gbmaps;     // per-set weight maps, entry [wid * kLayersPerSet + li]
+    const float* const* gbias;     // per-set bias pointers, same indexing
+    unsigned long long* trace;     // nullable (SE3TN_TRACE)
+};
+
+struct ResidentParams {
+    LayerDesc L;
+    int img_first, n_img;
+    int m_tiles;                   // n_img * tiles_x * tiles_y
+    int step_x, step_y, off_x, off_y;   // tile origin in A-map coordinates = tile index * step + off (stem: pooled 5x5 blocks)
+    const int* img_wid;
+    const CUtensorMap* gbmaps;
+    const float* const* gbias;
     unsigned long long* trace;
 };
 
-// ---- tcgen05 path only ------------------------------------------------------------------
-struct UmmaTiling {
-    int bw, bh, bn;          // pixel box of one M tile: bw*bh*bn <= 128 rows
-    int tiles_x, tiles_y;    // boxes per image
-    int m_tiles;             // ceil(n_img/bn) * tiles_y * tiles_x
-    int n_tiles;             // cout / BLOCK_N
-    int chunks_per_tap;      // cin / 32
-    int img_first;           // absolute index of the first image this launch covers
-};
+cudaError_t launch_conv_resident(const ResidentParams& p, int kind, int prec, int num_sms, bool pdl, cudaStream_t stream);
+cudaError_t launch_conv_trunk(const TrunkParams& p, int prec, int num_sms, bool pdl, cudaStream_t stream);
+// 32-bit words of scheduler state a trunk launch needs (next-unit counter + done[layers][max_batch])
+inline size_t trunk_sched_words(int max_batch) { return 1 + static_cast<size_t>(kTrunkMaxLayers) * max_batch; }
 
-struct alignas(64) UmmaMaps {
-    CUtensorMap a[7];
-    CUtensorMap b;
-};
-
-// ---- tcgen05 path, second generation (conv_umma2.cu) ---------------------------------------
-enum { KIND_S1 = 0, KIND_S2 = 1, KIND_STEM = 2 };   // conv kinds of the v2 kernel (compile-time unit tables)
-struct UnitTap { int8_t row_shift; int8_t w_tap; };   // rows to advance the A descriptor; weight tap index
-struct Unit {
-    int8_t map;            // A tensor map index
-    int8_t c1, c2;         // TMA coordinate deltas (x, y) relative to the tile origin
-    int8_t ntaps;
-    uint16_t rows;         // rows the TMA box writes (bw * extended height * bn): expect_tx = rows*128
-    UnitTap taps[4];
-};
-
-struct Umma2Plan {
-    int units_per_chunk;
-    Unit units[6];
-    int chunks;                          // cin / 32
-    int step_x, step_y, off_x, off_y;    // tile origin in A-map coordinates = tile index * step + off
-    int bw, bh, bn;                      // output pixel box per tile (normal epilogue)
-    int tiles_x, tiles_y, m_tiles, n_tiles;
-    int img_first;
-    int base_off_mode;                   // 0: descriptor base_offset = 0; 1: (addr >> 7) & 7
-    int pair;                            // resident-weight kernels: run as CTA pairs (cta_group::2); maps.b must then box BN/2 rows
-    int pdl;                             // launch with programmatic stream serialization (overlap prologue with the previous conv's tail)
-    int sk_seq;                          // stream-K: value a partial's flag takes in THIS launch (unique per launch, never 0)
-    int debug;                           // timing experiments only (results are garbage): bit0 skip B fills, bit1 skip A fills
-};
-
-cudaError_t launch_conv_umma2(const UmmaMaps& maps, const ConvGeom& g, const Umma2Plan& t, const ConvPtrs& p,
-                              int block_n, bool resident, int kind /*KIND_*/, int m_per_cta, int prec /*0 tf32, 1 bf16x3, 2 bf16*/,
-                              int num_sms, cudaStream_t stream);
-
-cudaError_t launch_conv_umma(const UmmaMaps& maps, const ConvGeom& g, const UmmaTiling& t,
-                             const ConvPtrs& p, int block_n, int num_sms, cudaStream_t stream);
 cudaError_t launch_conv_direct(const ConvGeom& g, const ConvPtrs& p, cudaStream_t stream);
 
 }  // namespace se3tn

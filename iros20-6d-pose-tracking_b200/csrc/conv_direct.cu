@@ -90,7 +90,6 @@ conv_direct_kernel(const ConvGeom g, const ConvPtrs p)
             float o = v[j];
             if (g.act == ACT_RELU) o = fmaxf(o, 0.f);
             else if (g.act == ACT_SELU) o = selu_d(o);
-            if (g.round_tf32) o = ptx::to_tf32(o);
             v[j] = o;
         }
         *reinterpret_cast<float4*>(p.out + static_cast<size_t>(pix) * g.out_cstride + g.out_coff + ch) = make_float4(v[0], v[1], v[2], v[3]);

@@ -20,7 +20,7 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 e0.record(); step(); e1.record(); torch.cuda.synchronize()
 tr = eng.get_trace().astype(np.int64)
 print('%s n=%d step %.1f us' % (prec, nb, e0.elapsed_time(e1) * 1e3))
-names = ['stemA', 'stemB', 'A2c1', 'A2c2', 'B2c1', 'B2c2', 'B3c1', 'B3c2', 'AB1', 'AB2c1', 'AB2c2', 'H1', 'H2c1', 'H2c2']
+names = ['stemA', 'stemB', 'A2c1', 'A2c2', 'B2c1', 'B2c2', 'B3c1', 'B3c2', 'trunk', '-', '-', '-', '-', '-']   # slot 8 = conv_trunk_kernel (six layers, one launch)
 t_first = None
 prev_end = None
 print('layer  ctas | start(first,last)  end(first,last) | per-CTA medians: setup  wgt  firstA  mma_span  acc0  epi_tail  exit | span  gap_prev')

@@ -8,7 +8,7 @@ Tolerances:
     north_star) on EVERY case here, including large-magnitude raw-regime inputs and both weight seeds
   * network 6-vector, TF32 tensor-core path:    same gate where its 10-bit operands allow it (tensor
     regime, raw regime with weight seed 0); documented to exceed it on raw regime / weight seed 1
-  * network 6-vector, BF16 (1 product) path:    rtol 5e-2 / atol 2e-2 (BASELINE configs[2], bf16 operands)
+  * network 6-vector, BF16 (1 product) path:    rtol 5e-3 / atol 2e-3 (BASELINE configs[2]: bf16 operands AND 2-byte activations)
   * network 6-vector, FP32 FFMA path:           rtol 1e-4 / atol 2e-6
   * pose update / so(3) log (fp64 + libm trig): atol 1e-7 / 1e-9
   * poses produced from a TF32 6-vector: the gate propagated through datasets.py:169-174,
@@ -23,7 +23,11 @@ import se3_oracle as O
 pytestmark = pytest.mark.gpu
 RTOL, ATOL = 1e-3, 1e-4
 POSE_ATOL = 1e-4
-GATES = {'bf16x3': (RTOL, ATOL), 'tf32': (RTOL, ATOL), 'fp32': (1e-4, 2e-6), 'bf16': (5e-2, 2e-2)}
+# bf16: 2-byte activations / weights, fp32 accumulate.  A CPU emulation of exactly that rounding (scripts/precision_study.py)
+# gives max |err| 6.2e-4 .. 6.7e-4 on the 6-vector over 16 pairs and both weight seeds; the gate leaves ~3x headroom, so a
+# regression by a factor of a few fails (the round-1 gate of (5e-2, 2e-2) would have hidden a 40x one).
+RAW_BF16_GATE = (5e-2, 2e-2)
+GATES = {'bf16x3': (RTOL, ATOL), 'tf32': (RTOL, ATOL), 'fp32': (1e-4, 2e-6), 'bf16': (5e-3, 2e-3)}
 
 
 def sha(a):
@@ -323,6 +327,95 @@ def test_track_batch_mixed_weight_sets(synth, eng):
     # with weight seed 1 (CPU emulation of exact TF32 rounding predicts err/tol 3.4) -- this is why BF16X3 is the
     # default.  Keep TF32 honest: it must stay in the same ballpark, not silently drift.
     assert worst['bf16x3'] < 0.5 and worst['tf32'] < 8.0
+
+
+
+# ------------------------------------------------------------------------------ BASELINE configs at full size
+def test_raw_regime_full_path_batch64_both_weight_seeds(synth, eng):
+    """BASELINE configs[1] at its real size: 64 tracks of one raw frame (large-magnitude normalised inputs, F13) through
+    K0 -> conv stack -> K6, half of the tracks on weight seed 0 and half on seed 1 (per-object checkpoints in the same
+    launches), every 6-vector and pose against the oracle.  bf16x3 must meet the north-star gate on all 64."""
+    n = 64
+    rgb, depth, poses, rgbA, depthA = _frame_case(synth, n, 11)
+    dev = eng.device
+    wid = np.repeat(np.array([0, 1], dtype=np.int32), n // 2)
+    ow = torch.full((n,), 200.0, dtype=torch.float64, device=dev)
+    args = (torch.from_numpy(rgb).to(dev), torch.from_numpy(depth).to(dev), synth.CAMERA_K, torch.from_numpy(poses).to(dev), ow,
+            torch.from_numpy(rgbA).to(dev), torch.from_numpy(depthA).to(dev), 0.03, 5 * np.pi / 180)
+    mean, std = synth.default_mean_std()
+    stats = {0: (mean, std), 1: (mean + 1.5, std * 1.25)}
+    sds = {0: synth.make_state_dict(0), 1: synth.make_state_dict(1)}
+    refs = [O.on_track(sds[int(wid[i])], poses[i], rgb, depth, rgbA[i], depthA[i], synth.CAMERA_K, 200.0, *stats[int(wid[i])], return_all=True)
+            for i in range(n)]
+    ref6 = torch.from_numpy(np.stack([np.concatenate([d['trans'], d['rot']]) for _, d in refs]))
+    ref_pose = np.stack([r[0] for r in refs])
+    out, tr, ro = eng.track_batch(*args, weight_ids_host=wid, precision='bf16x3')
+    worst = assert_gate(torch.cat((tr, ro), 1).cpu(), ref6)
+    assert np.abs(out.cpu().numpy() - ref_pose).max() < POSE_ATOL
+    # the same tracks one weight set at a time (single-set launches) give the same bits as the mixed launch
+    for w in (0, 1):
+        sel = np.nonzero(wid == w)[0]
+        a2 = (args[0], args[1], args[2], args[3][sel[0]:sel[-1] + 1].contiguous(), ow[:len(sel)], args[5][sel[0]:sel[-1] + 1].contiguous(),
+              args[6][sel[0]:sel[-1] + 1].contiguous(), 0.03, 5 * np.pi / 180)
+        o2, _, _ = eng.track_batch(*a2, weight_ids_host=np.full(len(sel), w, np.int32), precision='bf16x3')
+        assert torch.equal(o2, out[sel[0]:sel[-1] + 1])
+    # bf16 on raw-regime inputs: normalised magnitudes up to ~40 (F13) enter 17 layers of 8-bit-mantissa operands, so the
+    # 6-vector error is an order of magnitude above the tensor-regime one; RAW_BF16_GATE is ~3x the worst observed on B200
+    out_b, tr_b, ro_b = eng.track_batch(*args, weight_ids_host=wid, precision='bf16')
+    worst_b = assert_gate(torch.cat((tr_b, ro_b), 1).cpu(), ref6, *RAW_BF16_GATE)
+    print('raw regime n=64, seeds 0/1: worst err/tol bf16x3 %.3f (gate 1e-3/1e-4), bf16 %.3f (gate %g/%g)' % ((worst, worst_b) + RAW_BF16_GATE))
+
+
+def test_batch256_bf16_and_bf16x3_vs_oracle(pkg, synth):
+    """BASELINE configs[2]: batch 256 through one Engine(max_batch=256): the 2-byte bf16 path against its gate and the
+    default bf16x3 path against the north-star gate, all 256 pairs vs the oracle; determinism and the equality of a pair's
+    result at batch 256 and in a batch of its own."""
+    n = 256
+    e = pkg.Engine(max_batch=n)
+    try:
+        sd = synth.make_state_dict(0)
+        e.load_state_dict(sd, 0)
+        A, B = synth.tensor_pairs(n, seed=5)
+        ref = O.forward(sd, A, B)
+        ref6 = torch.cat((ref['trans'], ref['rot']), 1)
+        Ad, Bd = A.to(e.device), B.to(e.device)
+        for prec in ('bf16', 'bf16x3'):
+            t1, r1, _ = e.forward(Ad, Bd, precision=prec)
+            worst = assert_gate(six(t1, r1), ref6, *GATES[prec])
+            print('batch-256 %s worst err/tol: %.3f' % (prec, worst))
+            t2, r2, _ = e.forward(Ad, Bd, precision=prec)
+            assert torch.equal(t1, t2) and torch.equal(r1, r2)
+            t3, r3, _ = e.forward(Ad[200:203].contiguous(), Bd[200:203].contiguous(), precision=prec)
+            assert torch.equal(t3, t1[200:203]) and torch.equal(r3, r1[200:203])
+    finally:
+        e.close()
+
+
+def test_missing_stats_or_weights_are_errors(pkg, synth):
+    """an id with weights but no statistics (or statistics but no weights) must be refused, not normalised / convolved
+    with garbage."""
+    e = pkg.Engine(max_batch=4)
+    try:
+        mean, std = synth.default_mean_std()
+        e.load_state_dict(synth.make_state_dict(0), 0); e.set_stats(mean, std, 0)
+        e.load_state_dict(synth.make_state_dict(1), 1)                       # weights, no stats
+        e.set_stats(mean, std, 2)                                            # stats, no weights
+        n = 2
+        rgb, depth, poses, rgbA, depthA = _frame_case(synth, n, 2)
+        dev = e.device
+        args = (torch.from_numpy(rgb).to(dev), torch.from_numpy(depth).to(dev), synth.CAMERA_K, torch.from_numpy(poses).to(dev),
+                torch.full((n,), 200.0, dtype=torch.float64, device=dev), torch.from_numpy(rgbA).to(dev), torch.from_numpy(depthA).to(dev), 0.03, 0.0873)
+        for bad in ([0, 1], [0, 2], [0, 7]):
+            with pytest.raises(pkg._lib.Se3tnError) as ei:
+                e.track_batch(*args, weight_ids_host=np.array(bad, np.int32))
+            assert ei.value.code == pkg._lib.ERR_STATE
+        A, B = synth.tensor_pairs(1, seed=0)
+        with pytest.raises(pkg._lib.Se3tnError):
+            e.forward(A.to(dev), B.to(dev), weight_id=2)                     # set_stats alone does not make a weight set
+        out, _, _ = e.track_batch(*args, weight_ids_host=np.array([0, 0], np.int32))   # the context still works
+        assert torch.isfinite(out).all()
+    finally:
+        e.close()
 
 
 def test_empty_and_oversized_batches(synth, eng):
