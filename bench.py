@@ -8,11 +8,16 @@ One "step" = one pass of the hot path over one batch of synthetic input: `batch`
 independent object tracks of one 480x640 RGB-D frame go through K0 (crop / depth clip / normalise),
 the 17-conv two-branch network and K6 (R^3 x so(3) pose update)  -- BASELINE.json configs[1].
 With N GPUs every rank runs its own `batch` tracks (weak scaling: 64 tracks per GPU, 512 on 8 =
-configs[3]) and the per-step exchange is one NCCL all-gather of the updated poses.
+configs[3]) and the per-step exchange is one NCCL all-gather of the updated poses, issued on a side
+stream (nothing on a rank's data path needs its result) and waited for at the start of the next step.
+Default --steps: 500 (timed region ~0.4 s); --impl reference: 20 steps of the same 64-pair workload.
 
 Prints ONE JSON line (rank 0).  Keys beyond the base contract:
-  roofline      conv stack (the 14 tcgen05 launches) algorithmic FLOPs / their summed device time
-                (CUDA events recorded inside libse3tn on the launching stream) vs the tensor peak
+  roofline      conv stack (8 resident-weight launches + the 6-layer trunk launch) algorithmic FLOPs / their summed
+                device time (CUDA events recorded inside libse3tn on the launching stream) vs the tensor peak
+  weight_sets_21  the same step with 21 object classes (one checkpoint each, reference README.md:132) in the batch
+  parity        N=1: every tensor-core mode vs the CPU oracle on the cpu_baseline sample; N>1: every rank's sharded
+                poses vs a single-GPU rerun of the same tracks on rank 0 (must be bit-identical)
   cpu_baseline  the oracle's on_track path (torch CPU + numpy/cv2) timed on this box's host cores
   e2e           same metric through Tracker.on_track_batch with pinned HOST buffers: H2D of the frame,
                 poses, rendered views and D2H of the poses inside every timed step
@@ -33,7 +38,7 @@ TN, RN = 0.03, 5 * np.pi / 180
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--steps', type=int, default=None, help='default 500 (ours) / 20 (--impl reference)')
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=64)
@@ -42,8 +47,18 @@ def parse():
     ap.add_argument('--weight-sets', type=int, default=1, help='object classes (one checkpoint each, reference README.md:132); track i uses set i*G//batch')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-render', action='store_true', help='skip the step-with-rendered-input-A measurement')
+    ap.add_argument('--no-g21', action='store_true', help='skip the 21-weight-set leg')
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 20 if args.impl == 'reference' else 500
+    return args
+
+
+def workload_string(nb):
+    """config.workload: identical for both arms (the driver compares them)."""
+    return ('BASELINE configs[1]: %d synthetic RGB-D pairs/GPU per step, full path K0 crop/normalise -> two-branch 17-conv forward -> '
+            'se(3) update, 176x176, one 480x640 frame' % nb)
 
 
 def peaks():
@@ -149,7 +164,7 @@ def run_reference(args, synth, rank, world):
     """--impl reference: CPU, rank 0 only."""
     if rank != 0:
         return
-    per_step = 8
+    per_step = args.batch                              # the SAME workload as the GPU arm: every step is all `batch` pairs of one frame
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import se3_oracle as O
     sd = synth.make_state_dict(0)
@@ -176,12 +191,13 @@ def run_reference(args, synth, rank, world):
         step()
     dt = time.perf_counter() - t0
     val = args.steps * per_step / dt
-    sample = 'each step = %d of the %d pairs of the workload (one batched CPU forward + per-pair numpy/cv2 pre/post)' % (per_step, args.batch)
+    sample = 'each step = all %d pairs of the workload (per-pair numpy/cv2 crop + normalise, ONE batched torch CPU forward, per-pair pose update); %d steps' % (per_step, args.steps)
     line = {'impl': 'reference', 'metric': 'rgbd_pair_frames_per_sec', 'value': val, 'unit': 'pairs/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'on_track hot path, %d tracks/step of one 480x640 frame @176x176 (BASELINE configs[1])' % args.batch,
-                       'tracks_per_gpu': args.batch, 'precision': 'fp32 CPU (torch oneDNN)'},
+            'config': {'workload': workload_string(args.batch), 'tracks_per_gpu': args.batch, 'total_tracks': args.batch,
+                       'precision': 'fp32 CPU (torch oneDNN)',
+                       'note': 'one CPU process on rank 0 whatever --gpus says: at N > 1 the GPU arm processes N x %d pairs per step, this arm still %d' % (args.batch, args.batch)},
             'cpu_baseline': {'value': val, 'unit': 'pairs/s', 'cores': threads, 'kind': 'port', 'sample': sample},
             'e2e': {'value': val, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line), flush=True)
@@ -257,9 +273,12 @@ def main():
         step(k)
         ev[k][1].record()
         launches += eng.last_launch_count()
+    # the last step's pose all-gather runs on the side stream: its completion belongs to the timed region too
+    tail = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    tail[0].record(); tracker.wait_gather(); tail[1].record()
     sync_all()
     ms_steps = np.array([a.elapsed_time(b) for a, b in ev])
-    total_ms = torch.tensor([float(ms_steps.sum())], device=dev)
+    total_ms = torch.tensor([float(ms_steps.sum()) + tail[0].elapsed_time(tail[1])], device=dev)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
@@ -285,14 +304,17 @@ def main():
     def roofline_of(prec, conv_ms, per_slot):
         achieved = nb * FLOP_PER_PAIR / (conv_ms * 1e-3) / 1e12
         if prec == 'tf32':
-            peak, executed = pk['bf16_tflops'] / 2.0, 1.0
+            peak, executed = (pk['bf16_tflops_sustained'] if (total_ms >= 250.0 and pk.get('bf16_tflops_sustained')) else pk['bf16_tflops']) / 2.0, 1.0
             note = 'tf32 dense = measured bf16 cuBLAS burst (%s: %.1f TF/s) / 2 (kind::tf32 issues at half the bf16 rate; no tf32 line in the file)' % (pk_src, pk['bf16_tflops'])
         elif prec in ('bf16x3', 'bf16'):
-            peak, executed = pk['bf16_tflops'], (3.0 if prec == 'bf16x3' else 1.0)
-            note = 'measured bf16 cuBLAS burst (%s); sustained %.1f.  bf16x3 executes 3 bf16 products per algorithmic MAC, so the tensor pipe does executed_mult x the algorithmic work' % (pk_src, pk.get('bf16_tflops_sustained', 0))
+            # burst peak for a short timed region, the sustained (power-capped) one when the kernels run inside a long step loop
+            sustained = total_ms >= 250.0 and pk.get('bf16_tflops_sustained')
+            peak, executed = (pk['bf16_tflops_sustained'] if sustained else pk['bf16_tflops']), (3.0 if prec == 'bf16x3' else 1.0)
+            note = 'measured bf16 cuBLAS %s (%s; burst %.1f, sustained %.1f; timed region %.0f ms).  bf16x3 executes 3 bf16 products per algorithmic MAC, so the tensor pipe does executed_mult x the algorithmic work' % (
+                'SUSTAINED throughput' if sustained else 'burst', pk_src, pk['bf16_tflops'], pk.get('bf16_tflops_sustained', 0), total_ms)
         else:
             peak, executed, note = 75.0, 1.0, 'nominal fp32 FFMA peak (no tensor cores in this mode)'
-        return {'bound': 'tensor', 'kernel': 'conv_umma2_kernel (14 launches/step)' if prec != 'fp32' else 'conv_direct_kernel',
+        return {'bound': 'tensor', 'kernel': 'conv_resident_kernel x8 + conv_trunk_kernel x1 (17 convs, 9 launches/step)' if prec != 'fp32' else 'conv_direct_kernel',
                 'precision': prec, 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
                 'executed_mult': executed, 'tensor_pipe_frac': achieved * executed / peak, 'traffic': None,
                 'conv_stack_ms': conv_ms, 'peak_note': note,
@@ -306,7 +328,7 @@ def main():
     if os.path.exists(tj):            # dram__bytes_read+write per launch from the committed `ncu --set full` capture
         tr = json.load(open(tj))
         roofline['traffic'] = tr['dram_bytes_per_launch']
-        roofline['traffic_note'] = '%s; %s' % (tr['kernel'], tr['source'])
+        roofline['traffic_note'] = 'NOT measured in this run: dram__bytes_read+write per launch from the committed `ncu --set full` capture of this build (%s; %s)' % (tr['kernel'], tr['source'])
 
     # ---- (2b) the other tensor-core modes on the same workload (secondary numbers) -------------------
     alt = {}
@@ -330,6 +352,55 @@ def main():
                          'conv_ms': r2['per_kernel_ms']['conv']}
         tracker.precision = args.precision
 
+    # ---- (2c) the same step with 21 object classes in the batch (G in {1, 21}) -----------------
+    g21 = None
+    if not args.no_g21 and G == 1 and args.precision != 'fp32':
+        G21 = 21
+        for wid in range(1, G21):
+            eng.load_state_dict(synth.make_state_dict(wid), wid); eng.set_stats(mean, std, wid)
+        wids21 = np.tile((np.arange(nb) * G21 // nb).astype(np.int32), world)
+        tr21 = dist_mod.ShardedTracker(eng, wids21, synth.CAMERA_K, 200.0, TN, RN, rank, world, args.precision)
+
+        def step21(k):
+            d = sets[k % N_INPUT_SETS][1]
+            return tr21.step(d['rgb'], d['depth'], d['poses'], d['rgbA'], d['depthA'], gather=(world > 1))
+        for k in range(3):
+            step21(k)
+        sync_all()
+        n21 = min(args.steps, 50)
+        ev3 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n21)]
+        for k in range(n21):
+            flush.zero_(); ev3[k][0].record(); step21(k); ev3[k][1].record()
+        tr21.wait_gather()
+        sync_all()
+        t21 = torch.tensor([float(sum(a.elapsed_time(b) for a, b in ev3))], device=dev)
+        if world > 1:
+            dist.all_reduce(t21, op=dist.ReduceOp.MAX)
+        v21 = nb * world * n21 / (float(t21.item()) * 1e-3)
+        g21 = {'weight_sets': G21, 'value': v21, 'unit': 'pairs/s', 'ms_per_step': float(t21.item()) / n21, 'steps': n21, 'ratio_vs_1_set': v21 / value,
+               'note': 'track i uses set i*21//%d: 21 checkpoints (54 MB fp32 each) in the same 8 + 1 conv launches; resident-weight layers reload shared memory when the id changes between a CTA\'s consecutive tiles' % nb}
+
+    # ---- (2d) N > 1: the sharded run must equal a single-GPU run of the same tracks, bit for bit (SURVEY 4 tier 3) ----
+    shard_parity = None
+    if world > 1:
+        d0 = sets[0][1]
+        mine_out, gathered = tracker.step(d0['rgb'], d0['depth'], d0['poses'], d0['rgbA'], d0['depthA'], gather=True)
+        tracker.wait_gather()
+        torch.cuda.synchronize(dev)
+        if rank == 0:
+            worst, checked = 0.0, 0
+            g_np = gathered.cpu().numpy()
+            for r in range(world):                      # rank r's input set 0 is seeded 1000*r: regenerate it here and run it on THIS GPU alone
+                rgb_r, depth_r = synth.raw_frame(1000 * r)
+                poses_r = synth.raw_poses(nb, seed=1000 * r)
+                rgbA_r, depthA_r = synth.rendered_views(nb, poses_r, seed=1000 * r)
+                t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+                solo, _, _ = eng.track_batch(t(rgb_r), t(depth_r), synth.CAMERA_K, t(poses_r), ow, t(rgbA_r), t(depthA_r), TN, RN,
+                                             weight_ids_host=tracker.weight_ids[tracker.shards[r]], precision=args.precision)
+                worst = max(worst, float(np.abs(solo.cpu().numpy() - g_np[tracker.shards[r]]).max())); checked += nb
+            shard_parity = {'sharded_vs_single_gpu_max_abs_pose_diff': worst, 'tracks': checked, 'bit_identical': worst == 0.0,
+                            'note': 'every rank\'s gathered poses vs the same tracks run on rank 0 alone'}
+
     # ---- (3) end to end through the public API with pinned HOST buffers -----------------------------
     info = {'resolution': 176, 'boundingbox': 10, 'object_width': 200.0,
             'camera': {'focalX': synth.CAMERA_K[0, 0], 'focalY': synth.CAMERA_K[1, 1], 'centerX': synth.CAMERA_K[0, 2],
@@ -341,10 +412,24 @@ def main():
         # pinned HOST tensors in (uploads pipelined on the Tracker's copy stream), pinned host poses out
         h = sets[k % N_INPUT_SETS][0]
         out = trk.on_track_batch(h['poses'], h['rgb'], h['depth'], h['rgbA'], h['depthA'])
-        if world > 1:
-            out = dist_mod.all_gather_poses(out, tracker.shards, rank, world).index_select(0, tracker.mine_dev)
-        pinned_out.copy_(out, non_blocking=True)
+        pinned_out.copy_(out, non_blocking=True)       # this rank's result back to the host
+        if world > 1:                                   # exchange step: every rank receives all poses (side stream, see dist.ShardedTracker)
+            e2e_gather(out)
         return out
+
+    comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+    gather_state = {'done': None, 'last': None}
+
+    def e2e_gather(out):
+        cur = torch.cuda.current_stream(dev)
+        if gather_state['done'] is not None:
+            cur.wait_event(gather_state['done'])        # bound the pipeline to one gather in flight
+        ready = torch.cuda.Event(); ready.record(cur)
+        comm_stream.wait_event(ready)
+        with torch.cuda.stream(comm_stream):
+            gather_state['last'] = dist_mod.all_gather_poses(out, tracker.shards, rank, world)
+            gather_state['done'] = torch.cuda.Event(); gather_state['done'].record(comm_stream)
+        out.record_stream(comm_stream)
 
     for k in range(3):
         e2e_step(k)
@@ -434,13 +519,14 @@ def main():
         line = {'metric': 'rgbd_pair_frames_per_sec', 'value': value, 'unit': 'pairs/s', 'n_gpus': world, 'steps': args.steps,
                 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': {'tf32': 'tf32', 'bf16x3': 'bf16x3 (bf16 hi/lo split operands, 3 products/MAC, fp32 accumulate)', 'bf16': 'bf16', 'fp32': 'f32'}[args.precision], 'data': 'synthetic',
-                'config': {'workload': 'BASELINE configs[1]: %d synthetic RGB-D pairs/GPU per step, full path K0 crop/normalise -> two-branch 17-conv forward -> se(3) update, 176x176, one 480x640 frame' % nb,
+                'config': {'workload': workload_string(nb),
                            'tracks_per_gpu': nb, 'total_tracks': nb * world, 'precision': args.precision,
-                           'parallelism': 'tracks sharded, %d/GPU, NCCL all-gather of poses per step' % nb if world > 1 else 'single GPU',
+                           'parallelism': 'tracks sharded, %d/GPU, NCCL all-gather of poses per step (side stream, overlapped with the next step)' % nb if world > 1 else 'single GPU',
                            'l2': 'flushed between timed steps (256 MiB memset, untimed); %d rotating input sets; per-step CUDA events, max over ranks' % N_INPUT_SETS,
-                           'weights': 'random-init (seeded), %d weight set(s)%s' % (G, '' if G == 1 else ' (one per object class; all classes batched into the same 14 conv launches)')},
+                           'weights': 'random-init (seeded), %d weight set(s)%s' % (G, '' if G == 1 else ' (one per object class; all classes batched into the same conv launches)')},
                 'gpu_launches': int(launches), 'launches_per_step': int(launches // max(args.steps, 1)),
-                'roofline': roofline, 'alt_precisions': alt, 'parity': parity, 'cpu_baseline': cpu, 'e2e': e2e, 'render': render, 'single_track': single, 'clocks': clocks,
+                'graph_launches_per_step': 1 if eng.last_step_was_graph() else None,
+                'roofline': roofline, 'alt_precisions': alt, 'weight_sets_21': g21, 'parity': parity if world == 1 else shard_parity, 'cpu_baseline': cpu, 'e2e': e2e, 'render': render, 'single_track': single, 'clocks': clocks,
                 'ms_per_step_min': float(ms_steps.min()), 'ms_per_step_median': float(np.median(ms_steps))}
         print(json.dumps(line), flush=True)
     if world > 1:

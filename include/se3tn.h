@@ -228,7 +228,12 @@ int se3tn_get_profile(se3tn_ctx* ctx, float* ms);
 #define SE3TN_TRACE_WORDS (14 * 256 * 8)
 int se3tn_get_trace(se3tn_ctx* ctx, unsigned long long* out);
 
-/* Number of kernels the last forward / track_batch call on this context launched. */
+/* Number of kernels the last forward / track_batch call on this context launched (for a replayed CUDA graph: the kernels
+ * inside it).  se3tn_track_batch captures each distinct step (same pointers, sizes and precision) into a CUDA graph the
+ * first time it sees it and replays it afterwards -- one graph launch per step; SE3TN_GRAPH=0 in the environment, an
+ * enabled profiler or SE3TN_PREC_FP32 use plain stream launches.  se3tn_last_step_was_graph: 1 if the last track_batch
+ * call was a graph launch. */
+int se3tn_last_step_was_graph(se3tn_ctx* ctx);
 int se3tn_last_launch_count(se3tn_ctx* ctx);
 
 #ifdef __cplusplus

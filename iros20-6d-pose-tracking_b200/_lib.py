@@ -37,6 +37,7 @@ SIGNATURES = {
     'se3tn_debug_buffer': (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_sz)]),
     'se3tn_last_launch_count': (_i, [_vp]),
     'se3tn_get_trace': (_i, [_vp, _vp]),
+    'se3tn_last_step_was_graph': (_i, [_vp]),
     'se3tn_set_profiling': (_i, [_vp, _i]),
     'se3tn_get_profile': (_i, [_vp, _vp]),
 }

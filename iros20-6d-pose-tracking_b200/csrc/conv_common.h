@@ -61,7 +61,8 @@ struct ConvPtrs {
     float* out;
 };
 
-constexpr int kLayersPerSet = 14;     // conv layers per weight set (stride of the per-set device tables)
+constexpr int kLayersPerSet = 20;     // stride of the per-set device tables: rows 0..13 the 14 conv layers, rows 14..19 the trunk layers'
+                                      // maps again with 128-row boxes (small-batch trunk tiles; same biases)
 
 // ---- tcgen05 kernels ----------------------------------------------------------------------------------------
 // One layer as the device sees it.  Channel counts are in CHANNELS; byte strides follow from the precision.
@@ -85,7 +86,7 @@ struct LayerDesc {
     int act;
     int out_c, out_coff;   // channels per pixel of the output buffer, channel offset of this layer's channel 0
     int res_c;             // channels per pixel of the residual buffer
-    int li;                // layer index (row of the per-set tables)
+    int li;                // row of the per-set tables (layer index; trunk layers with 128-row weight boxes: 14 + layer - 8)
     // trunk scheduling
     int unit_base;         // first global work-unit index of this layer
     int units_per_image;   // tiles_x * tiles_y * n_tiles * groups
@@ -120,7 +121,7 @@ struct ResidentParams {
 };
 
 cudaError_t launch_conv_resident(const ResidentParams& p, int kind, int prec, int num_sms, bool pdl, cudaStream_t stream);
-cudaError_t launch_conv_trunk(const TrunkParams& p, int prec, int num_sms, bool pdl, cudaStream_t stream);
+cudaError_t launch_conv_trunk(const TrunkParams& p, int prec, int block_n /*256 | 128*/, int num_sms, bool pdl, cudaStream_t stream);
 // 32-bit words of scheduler state a trunk launch needs (next-unit counter + done[layers][max_batch])
 inline size_t trunk_sched_words(int max_batch) { return 1 + static_cast<size_t>(kTrunkMaxLayers) * max_batch; }
 

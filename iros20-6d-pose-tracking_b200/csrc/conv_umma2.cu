@@ -537,15 +537,16 @@ conv_resident_kernel(const __grid_constant__ ResidentParams p)
 // ================================================================================================================
 // conv_trunk_kernel
 // ================================================================================================================
-template <int PREC> struct TCfg {
-    static constexpr int BN = 256;
+template <int PREC, int BN_> struct TCfg {
+    static constexpr int BN = BN_;                                      // 256; 128 for small batches (twice the work units per layer)
     static constexpr int kAStages = 3;
-    static constexpr int kBStages = 4;
-    static constexpr int kBTile = BN * kChunkBytes;                     // 32 KB
+    static constexpr int kBStages = BN == 256 ? 4 : 6;
+    static constexpr int kBTile = BN * kChunkBytes;                     // 32 KB / 16 KB
     static constexpr int kEpiPitch = 36;                                // words per staged row (32 + 4: conflict-free 16 B accesses)
     static constexpr int kEpiWarpBytes = 32 * kEpiPitch * 4 + 128;      // 32 rows + 32-entry pixel-index table
     static constexpr int kEpiBytes = 8 * kEpiWarpBytes;
     static constexpr int kSched = 4;                                    // work-unit ring between the scheduler (A producer) and the other roles
+    static constexpr int kTmemCols = 2 * BN;
     static constexpr int kSmem = kAStages * kAUnit3 + kBStages * kBTile + ((kEpiBytes + 1023) & ~1023) + 1024 + 512;
     static_assert(kSmem <= 232448, "shared memory budget");
 };
@@ -593,12 +594,12 @@ __device__ __forceinline__ void trunk_load_unit(const LayerDesc& L, const UnitCo
 }
 
 // weight-tile loads of one work unit (B producer thread)
-template <int KIND, int PREC>
+template <int KIND, int PREC, int BN>
 __device__ __forceinline__ void trunk_load_weights(const LayerDesc& L, const CUtensorMap* bm, const UnitCoord& c, uint8_t* sB,
                                                    uint64_t* b_full, uint64_t* b_empty, int& stage, uint32_t& phase)
 {
     using KT = KTab<KIND>;
-    using C = TCfg<PREC>;
+    using C = TCfg<PREC, BN>;
     const int wrow = c.grp * L.cout + c.n_tile * C::BN;
     for (int ch = 0; ch < L.chunks; ++ch) {
 #pragma unroll
@@ -615,13 +616,13 @@ __device__ __forceinline__ void trunk_load_weights(const LayerDesc& L, const CUt
 }
 
 // MMAs of one work unit (whole MMA warp, warp-uniform)
-template <int KIND, int PREC>
+template <int KIND, int PREC, int BN>
 __device__ __forceinline__ void trunk_mma_unit(int chunks, uint32_t d_tmem, uint8_t* sA, uint8_t* sB, uint64_t* a_full, uint64_t* a_empty,
                                                uint64_t* b_full, uint64_t* b_empty, int& astage, uint32_t& aphase, int& bstage, uint32_t& bphase,
                                                unsigned long long* trace, bool first_unit)
 {
     using KT = KTab<KIND>;
-    using C = TCfg<PREC>;
+    using C = TCfg<PREC, BN>;
     constexpr uint32_t idesc = ptx::umma_idesc(PREC == PREC_TF32 ? 2u : 1u, kBlockM, C::BN);
     uint32_t fresh = 0;
     for (int ch = 0; ch < chunks; ++ch) {
@@ -668,12 +669,11 @@ __device__ __forceinline__ void trunk_mma_unit(int chunks, uint32_t d_tmem, uint
     }
 }
 
-template <int PREC>
+template <int PREC, int BN>
 __global__ void __launch_bounds__(kThreads2, 1)
 conv_trunk_kernel(const __grid_constant__ TrunkParams p)
 {
-    using C = TCfg<PREC>;
-    constexpr int BN = C::BN;
+    using C = TCfg<PREC, BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;                                                 // [kAStages][unit]
@@ -705,7 +705,7 @@ conv_trunk_kernel(const __grid_constant__ TrunkParams p)
         ptx::fence_barrier_init();
         ptx::fence_proxy_async();
     }
-    if (warp == 2) { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
+    if (warp == 2) { ptx::tmem_alloc(tmem_slot, C::kTmemCols); ptx::tmem_relinquish(); }
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -765,8 +765,8 @@ conv_trunk_kernel(const __grid_constant__ TrunkParams p)
                 const UnitCoord c = decode_unit(p, u);
                 const LayerDesc& L = p.layer[c.l];
                 const CUtensorMap* bm = p.img_wid ? p.gbmaps + p.img_wid[c.img] * kLayersPerSet + L.li : &L.bmap;
-                if (L.kind == KIND_S1) trunk_load_weights<KIND_S1, PREC>(L, bm, c, sB, b_full, b_empty, stage, phase);
-                else                   trunk_load_weights<KIND_S2, PREC>(L, bm, c, sB, b_full, b_empty, stage, phase);
+                if (L.kind == KIND_S1) trunk_load_weights<KIND_S1, PREC, BN>(L, bm, c, sB, b_full, b_empty, stage, phase);
+                else                   trunk_load_weights<KIND_S2, PREC, BN>(L, bm, c, sB, b_full, b_empty, stage, phase);
             }
         }
     } else if (warp == 1) {
@@ -784,8 +784,8 @@ conv_trunk_kernel(const __grid_constant__ TrunkParams p)
             ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
             ptx::tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * BN;
-            if (kind == KIND_S1) trunk_mma_unit<KIND_S1, PREC>(chunks, d_tmem, sA, sB, a_full, a_empty, b_full, b_empty, astage, aphase, bstage, bphase, p.trace, it == 0);
-            else                 trunk_mma_unit<KIND_S2, PREC>(chunks, d_tmem, sA, sB, a_full, a_empty, b_full, b_empty, astage, aphase, bstage, bphase, p.trace, it == 0);
+            if (kind == KIND_S1) trunk_mma_unit<KIND_S1, PREC, BN>(chunks, d_tmem, sA, sB, a_full, a_empty, b_full, b_empty, astage, aphase, bstage, bphase, p.trace, it == 0);
+            else                 trunk_mma_unit<KIND_S2, PREC, BN>(chunks, d_tmem, sA, sB, a_full, a_empty, b_full, b_empty, astage, aphase, bstage, bphase, p.trace, it == 0);
             if (ptx::elect_one()) ptx::umma_commit(&tmem_full[acc]);
             __syncwarp();
         }
@@ -932,7 +932,7 @@ conv_trunk_kernel(const __grid_constant__ TrunkParams p)
     if (threadIdx.x == 0) trace_exit(p.trace);
     if (warp == 2) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, 512);
+        ptx::tmem_dealloc(tmem_base, C::kTmemCols);
     }
 }
 
@@ -967,9 +967,9 @@ cudaError_t launch_resident_t(const ResidentParams& p, int num_sms, bool pdl, cu
     return cudaLaunchKernelEx(&cfg, conv_resident_kernel<KIND, PREC>, p);
 }
 
-template <int PREC>
+template <int PREC, int BN>
 cudaError_t launch_trunk_t(const TrunkParams& p, int num_sms, bool pdl, cudaStream_t stream) {
-    using C = TCfg<PREC>;
+    using C = TCfg<PREC, BN>;
     if (p.n_layers < 1 || p.n_layers > kTrunkMaxLayers || p.total_units <= 0 || !p.sched) return cudaErrorInvalidValue;
     for (int l = 0; l < p.n_layers; ++l) {
         const LayerDesc& L = p.layer[l];
@@ -978,7 +978,7 @@ cudaError_t launch_trunk_t(const TrunkParams& p, int num_sms, bool pdl, cudaStre
         if (L.dep_layer >= l) return cudaErrorInvalidValue;                                    // dependencies point backwards in the pull order
     }
     static size_t attr[64] = {};
-    cudaError_t e = set_smem(conv_trunk_kernel<PREC>, C::kSmem, attr);
+    cudaError_t e = set_smem(conv_trunk_kernel<PREC, BN>, C::kSmem, attr);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
     // all CTAs must be co-resident (one per SM): the dependency waits rely on it
@@ -986,7 +986,7 @@ cudaError_t launch_trunk_t(const TrunkParams& p, int num_sms, bool pdl, cudaStre
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, conv_trunk_kernel<PREC>, p);
+    return cudaLaunchKernelEx(&cfg, conv_trunk_kernel<PREC, BN>, p);
 }
 
 }  // namespace
@@ -1008,13 +1008,21 @@ cudaError_t launch_conv_resident(const ResidentParams& p, int kind, int prec, in
     return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_conv_trunk(const TrunkParams& p, int prec, int num_sms, bool pdl, cudaStream_t stream) {
-    switch (prec) {
-        case PREC_TF32:   return launch_trunk_t<PREC_TF32>(p, num_sms, pdl, stream);
-        case PREC_BF16X3: return launch_trunk_t<PREC_BF16X3>(p, num_sms, pdl, stream);
-        case PREC_BF16:   return launch_trunk_t<PREC_BF16>(p, num_sms, pdl, stream);
-        default:          return cudaErrorInvalidValue;
+cudaError_t launch_conv_trunk(const TrunkParams& p, int prec, int block_n, int num_sms, bool pdl, cudaStream_t stream) {
+    if (block_n == 256) {
+        switch (prec) {
+            case PREC_TF32:   return launch_trunk_t<PREC_TF32, 256>(p, num_sms, pdl, stream);
+            case PREC_BF16X3: return launch_trunk_t<PREC_BF16X3, 256>(p, num_sms, pdl, stream);
+            case PREC_BF16:   return launch_trunk_t<PREC_BF16, 256>(p, num_sms, pdl, stream);
+        }
+    } else if (block_n == 128) {
+        switch (prec) {
+            case PREC_TF32:   return launch_trunk_t<PREC_TF32, 128>(p, num_sms, pdl, stream);
+            case PREC_BF16X3: return launch_trunk_t<PREC_BF16X3, 128>(p, num_sms, pdl, stream);
+            case PREC_BF16:   return launch_trunk_t<PREC_BF16, 128>(p, num_sms, pdl, stream);
+        }
     }
+    return cudaErrorInvalidValue;
 }
 
 }  // namespace se3tn

@@ -93,7 +93,7 @@ struct WeightSet {
     size_t w_off[14], b_off[14];
     size_t fc_off;
     // weight tensor maps per precision: [li] -> the map the kernel of that layer wants
-    CUtensorMap bmap_tf32[14], bmap_x3[14], bmap_h[14];
+    CUtensorMap bmap_tf32[kLayersPerSet], bmap_x3[kLayersPerSet], bmap_h[kLayersPerSet];   // rows 14..19: trunk layers with 128-row boxes
     float mean32[8], std32[8];
     double mean64[8], std64[8];
     int stats_f64 = 0;
@@ -137,6 +137,11 @@ struct se3tn_ctx {
     int table_rows = 0; bool tables_dirty = true;
     int launches = 0;
     bool profiling = false;
+    // CUDA graphs of whole track_batch steps (preprocess -> 8 resident convs -> trunk -> head + pose update), keyed by every baked-in argument
+    int use_graphs = 1;              // SE3TN_GRAPH=0: plain stream launches; set to 0 at run time if capture is not possible
+    bool last_was_graph = false;
+    struct StepGraph { std::vector<unsigned long long> key; cudaGraphExec_t exec; int launches; unsigned long long last_use; };
+    std::vector<StepGraph> graphs; unsigned long long graph_clock = 0;
     cudaEvent_t ev0[SE3TN_PROFILE_SLOTS] = {}, ev1[SE3TN_PROFILE_SLOTS] = {};
     bool ev_used[SE3TN_PROFILE_SLOTS] = {};
     std::string err;
@@ -291,14 +296,16 @@ void fill_geom(const LayerSpec& L, int n, ConvGeom& g) {
 }
 
 // one layer as the tcgen05 kernels see it (conv_common.h LayerDesc)
-void fill_layer_desc(const se3tn_ctx* c, const WeightSet& ws, int li, int kprec, LayerDesc& d) {
+void fill_layer_desc(const se3tn_ctx* c, const WeightSet& ws, int li, int kprec, LayerDesc& d, int block_n = 0) {
     const LayerSpec& L = kLayers[li];
+    if (!block_n) block_n = L.block_n;
+    const int row = (block_n == L.block_n) ? li : 14 + li - kFirstTrunkLayer;      // table row / weight map with the matching box height
     memset(&d, 0, sizeof d);
     const int bpc = prec_bytes_per_channel(kprec);
     const bool stem = (L.kind == K_STEM);
     const CUtensorMap (*amaps)[4] = (bpc == 2 && !stem) ? c->amap2 : c->amap4;
     for (int m = 0; m < 4; ++m) d.amap[m] = amaps[li][m];
-    d.bmap = (kprec == PREC_TF32) ? ws.bmap_tf32[li] : (kprec == PREC_BF16X3 ? ws.bmap_x3[li] : ws.bmap_h[li]);
+    d.bmap = (kprec == PREC_TF32) ? ws.bmap_tf32[row] : (kprec == PREC_BF16X3 ? ws.bmap_x3[row] : ws.bmap_h[row]);
     d.bias = ws.dev + ws.b_off[li];
     d.kind = stem ? KIND_STEM : (L.kind == K_S2 ? KIND_S2 : KIND_S1);
     if (stem) {                                    // K = 8 pixels x 4 channels x 4 bytes per filter row in every mode
@@ -314,8 +321,8 @@ void fill_layer_desc(const se3tn_ctx* c, const WeightSet& ws, int li, int kprec,
     }
     d.res = (L.res != NONE) ? reinterpret_cast<const uint8_t*>(c->buf[L.res]) : nullptr;
     d.res_c = (L.res != NONE) ? res_channels(L) : 0;
-    d.cout = L.cout; d.groups = L.groups; d.n_tiles = L.cout / L.block_n;
-    d.act = L.act; d.li = li;
+    d.cout = L.cout; d.groups = L.groups; d.n_tiles = L.cout / block_n;
+    d.act = L.act; d.li = row;
     d.units_per_image = d.tiles_x * d.tiles_y * d.n_tiles * d.groups;
     d.dep_layer = -1; d.dep_target = 0; d.unit_base = 0;
 }
@@ -385,7 +392,7 @@ int sync_tables(se3tn_ctx* c, cudaStream_t s) {
             m1[kv.first * kLayersPerSet + li] = kv.second.bmap_tf32[li];
             m2[kv.first * kLayersPerSet + li] = kv.second.bmap_h[li];
             m3[kv.first * kLayersPerSet + li] = kv.second.bmap_x3[li];
-            bias[kv.first * kLayersPerSet + li] = kv.second.dev + kv.second.b_off[li];
+            bias[kv.first * kLayersPerSet + li] = kv.second.dev + kv.second.b_off[li < 14 ? li : kFirstTrunkLayer + li - 14];
         }
         fc[kv.first] = kv.second.dev + kv.second.fc_off;
     }
@@ -396,6 +403,11 @@ int sync_tables(se3tn_ctx* c, cudaStream_t s) {
     CU_TRY(c, cudaMemcpy(c->d_fc, fc.data(), fc.size() * sizeof(float*), cudaMemcpyHostToDevice));
     c->tables_dirty = false;
     return SE3TN_OK;
+}
+
+void drop_graphs(se3tn_ctx* c) {
+    for (auto& g : c->graphs) cudaGraphExecDestroy(g.exec);
+    c->graphs.clear();
 }
 
 // optional pose update fused into the head kernel (tensor-core modes): K6 for the same n tracks
@@ -456,10 +468,13 @@ int run_network(se3tn_ctx* c, int weight_id, int first, int n, int precision,
     {
         TrunkParams tp;
         memset(&tp, 0, sizeof tp);
+        // work units of 256 output channels; small batches (at most half of the SMs busy per layer otherwise) use 128:
+        // twice the units per layer and half the latency of each -- the layers of one image are a serial chain
+        const int bn = (n * 4 * 2 <= c->num_sms) ? 128 : 256;
         int base = 0;
         for (int l = 0; l < 14 - kFirstTrunkLayer; ++l) {
             LayerDesc& d = tp.layer[l];
-            fill_layer_desc(c, ws, kFirstTrunkLayer + l, kprec, d);
+            fill_layer_desc(c, ws, kFirstTrunkLayer + l, kprec, d, bn);
             d.unit_base = base; base += n * d.units_per_image;
             if (l > 0) { d.dep_layer = l - 1; d.dep_target = 8u * static_cast<unsigned>(tp.layer[l - 1].units_per_image); }
         }
@@ -469,7 +484,7 @@ int run_network(se3tn_ctx* c, int weight_id, int first, int n, int precision,
         tp.sched = c->sched; tp.img_wid = img_wid; tp.gbmaps = gbmaps; tp.gbias = gbias;
         tp.trace = c->trace ? c->trace + static_cast<size_t>(kFirstTrunkLayer) * 256 * 8 : nullptr;
         c->sched_dirty = true;                     // cleared again by the head kernel below
-        { ProfScope ps(c, kFirstTrunkLayer, s); CU_TRY(c, launch_conv_trunk(tp, kprec, c->num_sms, c->pdl != 0, s)); }
+        { ProfScope ps(c, kFirstTrunkLayer, s); CU_TRY(c, launch_conv_trunk(tp, kprec, bn, c->num_sms, c->pdl != 0, s)); }
         ++c->launches;
     }
     {
@@ -517,6 +532,7 @@ int se3tn_create(int device, int max_batch, void* workspace, se3tn_ctx** out) {
     se3tn_ctx* c = new se3tn_ctx();
     c->device = device; c->max_batch = max_batch; c->num_sms = prop.multiProcessorCount;
     if (const char* ov = getenv("SE3TN_PDL")) c->pdl = atoi(ov) != 0;
+    if (const char* ov = getenv("SE3TN_GRAPH")) c->use_graphs = atoi(ov) != 0;
     if (const char* ov = getenv("SE3TN_TRACE")) {
         if (atoi(ov) != 0 && cudaMalloc(&c->trace, SE3TN_TRACE_WORDS * sizeof(unsigned long long)) == cudaSuccess) cudaMemset(c->trace, 0, SE3TN_TRACE_WORDS * sizeof(unsigned long long));
     }
@@ -564,6 +580,7 @@ void se3tn_destroy(se3tn_ctx* c) {
     cudaFree(c->d_mean32); cudaFree(c->d_std32); cudaFree(c->d_mean64); cudaFree(c->d_std64);
     cudaFree(c->d_bmaps_tf32); cudaFree(c->d_bmaps_bf16); cudaFree(c->d_bmaps_x3); cudaFree(c->d_bias); cudaFree(c->d_fc);
     for (int i = 0; i < SE3TN_PROFILE_SLOTS; ++i) { if (c->ev0[i]) cudaEventDestroy(c->ev0[i]); if (c->ev1[i]) cudaEventDestroy(c->ev1[i]); }
+    drop_graphs(c);
     cudaFree(c->sched); cudaFree(c->pool_part); cudaFree(c->trace);
     for (auto& kv : c->meshes) { cudaFree(const_cast<float*>(kv.second.pos)); cudaFree(const_cast<float*>(kv.second.nrm)); cudaFree(const_cast<uint8_t*>(kv.second.col)); cudaFree(const_cast<int*>(kv.second.faces)); }
     cudaFree(c->d_meshes); cudaFree(c->render_proj); cudaFree(c->render_unif);
@@ -612,6 +629,11 @@ int se3tn_load_weights(se3tn_ctx* c, int weight_id, const float* blob, size_t n_
             uint8_t* dh = ws.dev_h + ws.w_off[li] * sizeof(uint16_t);
             CU_TRY(c, launch_to_bf16(wsrc, dh, words, 0));                                // plain bf16, 64 channels per 128-byte chunk
             if (!rc) rc = make_map2(c, &ws.bmap_h[li], dh, layer_ktot(L) / 2, layer_rows(L), 256, what);
+            // the same matrices in 128-row boxes: small batches run the trunk with 128-channel work units (twice the units per layer)
+            const int ls = 14 + li - kFirstTrunkLayer;
+            if (!rc) rc = make_map2(c, &ws.bmap_tf32[ls], ws.dev_tf32 + ws.w_off[li], layer_ktot(L), layer_rows(L), 128, what);
+            if (!rc) rc = make_map2(c, &ws.bmap_x3[ls], d3, layer_ktot(L), layer_rows(L), 128, what);
+            if (!rc) rc = make_map2(c, &ws.bmap_h[ls], dh, layer_ktot(L) / 2, layer_rows(L), 128, what);
         } else {
             // resident-weight layers.  Stems keep the natural row order; the 64-channel 3x3 layers use the row order of the
             // 16x256b epilogue (all precisions).  bf16 modes: hi / lo rows stacked along N, except the 64-channel layers in PREC_BF16.
@@ -643,6 +665,7 @@ int se3tn_load_weights(se3tn_ctx* c, int weight_id, const float* blob, size_t n_
     CU_TRY(c, cudaDeviceSynchronize());
     ws.fc_off = off;
     c->tables_dirty = true;
+    drop_graphs(c);                                // captured steps hold the old tensor maps / table pointers
     return SE3TN_OK;
 }
 
@@ -661,6 +684,7 @@ int se3tn_set_stats(se3tn_ctx* c, int weight_id, const void* mean8, const void* 
     }
     ws.stats_f64 = is_f64 ? 1 : 0; ws.has_stats = true;
     c->stats_dirty = true;
+    drop_graphs(c);
     return SE3TN_OK;
 }
 
@@ -775,6 +799,13 @@ int se3tn_so3_log(se3tn_ctx* c, const double* poses_a, const double* poses_b, do
     return SE3TN_OK;
 }
 
+static int track_batch_launches(se3tn_ctx* c, const uint8_t* frame_rgb, const uint16_t* frame_depth, int H, int W,
+                                const double* K, const double* poses_in, const double* object_width,
+                                const uint8_t* rgbA, const uint16_t* depthA,
+                                const int32_t* weight_ids_host, const int32_t* weight_ids_dev, int n,
+                                double tn, double rn, int precision,
+                                float* out_trans, float* out_rot, double* poses_out, bool multi, cudaStream_t s);
+
 int se3tn_track_batch(se3tn_ctx* c, const uint8_t* frame_rgb, const uint16_t* frame_depth, int H, int W,
                       const double* K, const double* poses_in, const double* object_width,
                       const uint8_t* rgbA, const uint16_t* depthA,
@@ -797,13 +828,82 @@ int se3tn_track_batch(se3tn_ctx* c, const uint8_t* frame_rgb, const uint16_t* fr
         if (wid != (weight_ids_host ? weight_ids_host[0] : 0)) multi = true;
         if (!weight_ids_host) break;                // all tracks use set 0
     }
+    if (n == 0) return SE3TN_OK;
+    DeviceGuard guard(c->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // ---- one CUDA graph per distinct step: every argument that ends up inside a kernel parameter is part of the key ----
+    const bool graphable = c->use_graphs && !c->profiling && precision != SE3TN_PREC_FP32;
+    std::vector<unsigned long long> key;
+    c->last_was_graph = false;
+    if (graphable) {
+        auto bits = [](double d) { unsigned long long u; memcpy(&u, &d, 8); return u; };
+        const void* ptrs[] = {frame_rgb, frame_depth, poses_in, object_width, rgbA, depthA, weight_ids_dev, out_trans, out_rot, poses_out, s};
+        for (const void* p : ptrs) key.push_back(reinterpret_cast<unsigned long long>(p));
+        key.push_back(static_cast<unsigned long long>(H)); key.push_back(static_cast<unsigned long long>(W));
+        key.push_back(static_cast<unsigned long long>(n)); key.push_back(static_cast<unsigned long long>(precision));
+        key.push_back(multi ? 1ull : 0ull); key.push_back(static_cast<unsigned long long>(weight_ids_host ? weight_ids_host[0] : 0));
+        for (int i = 0; i < 4; ++i) key.push_back(bits(K[i]));
+        key.push_back(bits(tn)); key.push_back(bits(rn));
+        for (auto& g : c->graphs)
+            if (g.key == key) {
+                CU_TRY(c, cudaGraphLaunch(g.exec, s));
+                g.last_use = ++c->graph_clock; c->launches = g.launches; c->last_was_graph = true;
+                return SE3TN_OK;
+            }
+        // a new step shape: host-side table refreshes (synchronous copies) must not happen inside the capture
+        int rc0 = sync_stats(c, s); if (rc0) return rc0;
+        if (multi) { rc0 = sync_tables(c, s); if (rc0) return rc0; }
+        if (c->sched_dirty) { CU_TRY(c, cudaMemsetAsync(c->sched, 0, trunk_sched_words(c->max_batch) * sizeof(unsigned), s)); c->sched_dirty = false; }
+        if (cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); key.clear(); }
+    }
+    const bool capturing = graphable && !key.empty();
+    auto end_capture = [&](int rc_launch) -> int {
+        // turn what was recorded into an executable graph and run it; any failure falls back to plain stream launches for good
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamEndCapture(s, &graph);
+        if (rc_launch != SE3TN_OK || e != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError(); c->use_graphs = 0; c->sched_dirty = true;
+            return rc_launch != SE3TN_OK ? rc_launch : 1;      // 1: capture failed, caller relaunches directly
+        }
+        cudaGraphExec_t exec = nullptr;
+        e = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { cudaGetLastError(); c->use_graphs = 0; return 1; }
+        if (c->graphs.size() >= 64) {                          // evict the least recently used step
+            size_t lru = 0;
+            for (size_t i = 1; i < c->graphs.size(); ++i) if (c->graphs[i].last_use < c->graphs[lru].last_use) lru = i;
+            cudaGraphExecDestroy(c->graphs[lru].exec); c->graphs.erase(c->graphs.begin() + lru);
+        }
+        c->graphs.push_back({key, exec, c->launches, ++c->graph_clock});
+        CU_TRY(c, cudaGraphLaunch(exec, s));
+        c->last_was_graph = true;
+        return SE3TN_OK;
+    };
+    if (capturing) {
+        const int rc = track_batch_launches(c, frame_rgb, frame_depth, H, W, K, poses_in, object_width, rgbA, depthA, weight_ids_host, weight_ids_dev, n,
+                                            tn, rn, precision, out_trans, out_rot, poses_out, multi, s);
+        const int grc = end_capture(rc);
+        if (grc == SE3TN_OK) return SE3TN_OK;
+        if (grc != 1) return grc;                              // a real launch error
+        // capture was not possible on this stream / driver: plain launches from here on
+    }
+    return track_batch_launches(c, frame_rgb, frame_depth, H, W, K, poses_in, object_width, rgbA, depthA, weight_ids_host, weight_ids_dev, n,
+                                tn, rn, precision, out_trans, out_rot, poses_out, multi, s);
+}
+
+// the launches of one step, on stream s (being captured or not)
+static int track_batch_launches(se3tn_ctx* c, const uint8_t* frame_rgb, const uint16_t* frame_depth, int H, int W,
+                                const double* K, const double* poses_in, const double* object_width,
+                                const uint8_t* rgbA, const uint16_t* depthA,
+                                const int32_t* weight_ids_host, const int32_t* weight_ids_dev, int n,
+                                double tn, double rn, int precision,
+                                float* out_trans, float* out_rot, double* poses_out, bool multi, cudaStream_t s) {
+    void* stream = s;
     c->launches = 0;
     int rc = se3tn_preprocess(c, frame_rgb, frame_depth, H, W, K, poses_in, object_width, rgbA, depthA, weight_ids_dev, n,
                               precision, nullptr, nullptr, nullptr, nullptr, stream);
     if (rc) return rc;
-    if (n == 0) return SE3TN_OK;
-    DeviceGuard guard(c->device);
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
     PoseArgs pose; pose.in = poses_in; pose.out = poses_out; pose.tn = static_cast<float>(tn); pose.rn = static_cast<float>(rn);
     bool pose_done = false;
     if (precision != SE3TN_PREC_FP32) {
@@ -957,6 +1057,7 @@ int se3tn_debug_buffer(se3tn_ctx* c, int id, float** ptr, size_t* floats_per_ima
 }
 
 int se3tn_last_launch_count(se3tn_ctx* c) { return c ? c->launches : 0; }
+int se3tn_last_step_was_graph(se3tn_ctx* c) { return (c && c->last_was_graph) ? 1 : 0; }
 
 int se3tn_get_trace(se3tn_ctx* c, unsigned long long* out) {
     if (!c) return SE3TN_ERR_INVALID;

@@ -279,6 +279,10 @@ class Engine:
     def last_launch_count(self):
         return self.lib.se3tn_last_launch_count(self._ctx)
 
+    def last_step_was_graph(self):
+        """True when the last track_batch call replayed (or just captured and launched) a CUDA graph of the whole step."""
+        return bool(self.lib.se3tn_last_step_was_graph(self._ctx))
+
     # ------------------------------------------------------------------ checks
     def _check_img(self, t):
         if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.dim() == 4 and

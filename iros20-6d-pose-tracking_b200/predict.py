@@ -43,15 +43,27 @@ class PointCloud:
         return PointCloud(sums / cnt)
 
 
-def load_vertices(model_path):
-    """Vertices of a .ply (ascii / binary little endian) or .obj mesh (trimesh.load(..).vertices in
-    the reference, predict.py:131)."""
+def load_vertices(model_path, merge=True):
+    """Vertices of a .ply (ascii / binary little endian) or .obj mesh, as trimesh.load(..).vertices gives them to the
+    reference (predict.py:131).  trimesh loads with process=True, which MERGES duplicate vertices (positions equal to its
+    tol.merge = 1e-8); duplicates would otherwise weigh twice in the voxel means of voxel_down_sample and move the
+    convex-hull diameter -> object_width -> crop window.  merge=True reproduces that (first occurrence kept, file order)."""
     ext = os.path.splitext(model_path)[1].lower()
     if ext == '.obj':
         v = [list(map(float, l.split()[1:4])) for l in open(model_path) if l.startswith('v ')]
-        return np.asarray(v, dtype=np.float64)
-    if ext != '.ply':
+        pts = np.asarray(v, dtype=np.float64)
+    elif ext == '.ply':
+        pts = _ply_vertices(model_path)
+    else:
         raise ValueError('unsupported mesh format: ' + model_path)
+    if merge and len(pts):
+        key = np.round(pts / 1e-8).astype(np.int64)
+        _, first = np.unique(key, axis=0, return_index=True)
+        pts = pts[np.sort(first)]
+    return pts
+
+
+def _ply_vertices(model_path):
     with open(model_path, 'rb') as f:
         fmt, nvert, props, in_vertex = None, 0, [], False
         while True:
@@ -157,11 +169,14 @@ class Tracker:
         try:
             if self.dataset_info.get('renderer') == 'pyrenderer':
                 from offscreen_renderer import Renderer            # reference module, if on sys.path
-                return Renderer([model_path], self.K, cam_cfg['height'], cam_cfg['width'])
-            from vispy_renderer import VispyRenderer               # reference module, if on sys.path
-            return VispyRenderer(model_path, self.K, H=self.dataset_info['resolution'], W=self.dataset_info['resolution'])
-        except Exception:
-            return None
+            else:
+                from vispy_renderer import VispyRenderer           # reference module, if on sys.path
+        except ImportError:
+            return None                                            # no OpenGL stack in this environment: rgbA/depthA must be passed in
+        # the renderer module IS there: a failure to construct it (no GL context, bad mesh) is the user's to see
+        if self.dataset_info.get('renderer') == 'pyrenderer':
+            return Renderer([model_path], self.K, cam_cfg['height'], cam_cfg['width'])
+        return VispyRenderer(model_path, self.K, H=self.dataset_info['resolution'], W=self.dataset_info['resolution'])
 
     def render_window(self, ob2cam):
         """rgb u8 (176,176,3), depth u16 mm (176,176) of the model at `ob2cam` inside the crop window
@@ -347,24 +362,234 @@ def predictSequenceYcbInEOAT(test_data_path, dataset_info, images_mean, images_s
     return np.stack(poses)
 
 
+# ----------------------------------------------------------------------------------------------------
+# YCB-Video drivers (reference predict.py:299-575): predictSequenceYcb (one sequence, optional PoseCNN / PoseRBPF
+# initialisation and re-initialisation frames, per-sequence ADD-S AUC) and getResultsYcb (every test sequence 0048-0059
+# that contains the class; what eval_ycb.py scores).  Headless: no VideoWriter / imshow.  The data-set layout is the
+# reference's:  <ycb_dir>/<seq %04d>/{color,depth_filled,seg,pose_gt/<class_id>}/..., <ycb_dir>/image_sets/keyframe.txt,
+# <ycb_dir>/YCB_Video_toolbox/results_PoseCNN_RSS2018/%06d.mat (rois, poses_icp), .../PoseRBPF_Results/YCB_results_RGBD/.
+# ----------------------------------------------------------------------------------------------------
+def quaternion_matrix3(q_wxyz):
+    """3x3 rotation of a (w, x, y, z) quaternion -- transformations.quaternion_matrix(q)[:3,:3] (reference predict.py:117)."""
+    q = np.array(q_wxyz, dtype=np.float64, copy=True)
+    n = np.dot(q, q)
+    if n < np.finfo(float).eps * 4.0:
+        return np.identity(3)
+    q *= np.sqrt(2.0 / n)
+    q = np.outer(q, q)
+    return np.array([[1.0 - q[2, 2] - q[3, 3], q[1, 2] - q[3, 0], q[1, 3] + q[2, 0]],
+                     [q[1, 2] + q[3, 0], 1.0 - q[1, 1] - q[3, 3], q[2, 3] - q[1, 0]],
+                     [q[1, 3] - q[2, 0], q[2, 3] + q[1, 0], 1.0 - q[1, 1] - q[2, 2]]])
+
+
+def read_keyframes(ycb_dir):
+    with open('{}/image_sets/keyframe.txt'.format(ycb_dir), 'r') as ff:
+        return [l.rstrip() for l in ff.readlines()]
+
+
+def nearest_keyframe(seq_frames, seq_id, start_frame):
+    """The keyframe of `seq_id` closest to `start_frame`, searching outwards (reference predict.py:93-107, 485-496)."""
+    neighbor = 0
+    while neighbor < 100000:
+        for cand in (start_frame + neighbor, start_frame - neighbor):
+            tmp = '%04d/%06d' % (seq_id, cand)
+            if tmp in seq_frames:
+                return tmp, seq_frames.index(tmp), cand
+        neighbor += 1
+    raise ValueError('sequence %04d has no keyframe' % seq_id)
+
+
+def posecnn_pose(mat_path, class_id):
+    """Pose of `class_id` from a PoseCNN result file: rois[:,1] == class id, poses_icp = (qw,qx,qy,qz,x,y,z) (predict.py:111-122)."""
+    import scipy.io
+    res = scipy.io.loadmat(mat_path)
+    idx = np.where(res['rois'][:, 1] == class_id)
+    tmp = res['poses_icp'][idx].reshape(-1)
+    if tmp.size < 7:
+        raise ValueError('class %d not in %s' % (class_id, mat_path))
+    pose = np.eye(4)
+    pose[:3, :3] = quaternion_matrix3(tmp[:4])
+    pose[:3, 3] = tmp[4:7]
+    return pose
+
+
+def use_posecnn_res(class_id, seq_frame_str, ycb_dir, posecnn_dir=None):
+    """PoseCNN's estimate at the keyframe nearest to `seq_frame_str` = '%04d/%06d' (reference predict.py:89-123)."""
+    seq_frames = read_keyframes(ycb_dir)
+    seq_id, start_frame = int(seq_frame_str.split('/')[0]), int(seq_frame_str.split('/')[1])
+    _, index, _ = nearest_keyframe(seq_frames, seq_id, start_frame)
+    posecnn_dir = posecnn_dir or '{}/YCB_Video_toolbox/results_PoseCNN_RSS2018/'.format(ycb_dir)
+    return posecnn_pose(os.path.join(posecnn_dir, '%06d.mat' % index), class_id)
+
+
+def poserbpf_pose(ycb_dir, class_id, seq_id, seqs):
+    """First pose of PoseRBPF's result file for (class, sequence) (reference predict.py:376-390, 498-513): 'x y z qw qx qy qz' after two tokens."""
+    import glob
+    res_dir = '{}/YCB_Video_toolbox/PoseRBPF_Results/YCB_results_RGBD/'.format(ycb_dir)
+    folders = sorted(os.listdir(res_dir))
+    cur = res_dir + folders[class_id - 1] + '/' + 'seq_{}/'.format(seqs.index(seq_id) + 1)
+    with open(glob.glob(cur + 'Pose*.txt')[0], 'r') as ff:
+        pose = ff.readlines()[0].rstrip().split()[2:]
+    out = np.eye(4)
+    out[:3, 3] = np.array(pose[:3], dtype=np.float64)
+    out[:3, :3] = quaternion_matrix3(np.array(pose[3:7], dtype=np.float64))
+    return out
+
+
+def findClassContainedVideosYcb(class_id, data_dir, testset=True):
+    """Sequence ids under `data_dir` whose pose_gt/ has a folder for `class_id` (reference Utils.py:108-123; test set = 0048..0059)."""
+    import glob, re
+    out = []
+    for gt_dir in sorted(glob.glob(os.path.join(data_dir, '**/pose_gt'))):
+        video_index = int(re.findall(r'/[0-9]{4}/', gt_dir + '/')[0][1:-1])
+        if testset and (video_index < 48 or video_index > 59):
+            continue
+        if class_id in list(map(int, os.listdir(gt_dir))):
+            out.append(video_index)
+    return out
+
+
+def _ycb_sequence_files(seq_dir, class_id):
+    import glob
+    rgb = sorted(glob.glob(os.path.join(seq_dir, 'color/*')))
+    depth = sorted(glob.glob(os.path.join(seq_dir, 'depth_filled/*')))
+    gt = sorted(glob.glob(os.path.join(seq_dir, 'pose_gt/{}/*'.format(class_id))))
+    if not rgb or len(rgb) != len(depth) or len(gt) < len(rgb):
+        raise FileNotFoundError('need matching color/, depth_filled/ and pose_gt/%d/ files under %s' % (class_id, seq_dir))
+    return rgb, depth, gt
+
+
+def predictSequenceYcb(ycb_dir, seq_id, class_id, dataset_info, images_mean, images_std, ckpt_dir, model_path, outdir,
+                       init='gt', reinit_frames=None, start_frame=0, tracker=None, max_frames=None, **tracker_kwargs):
+    """Track `class_id` through YCB-Video sequence `seq_id` (reference predict.py:446-575).  init: 'gt' | 'posecnn' | 'poserbpf'.
+    reinit_frames: '%04d/%06d' strings (1-based frame ids, as the reference compares them): the track restarts there from
+    PoseCNN's estimate.  Writes <outdir>/%05d.txt and %05dgt.txt and returns (poses (N,4,4), ADD-S AUC in percent)."""
+    test_data_path = '{}/%04d'.format(ycb_dir) % seq_id
+    rgb_files, depth_files, gt_files = _ycb_sequence_files(test_data_path, class_id)
+    gt_poses = [np.loadtxt(f) for f in gt_files]
+    reinit_frames = list(reinit_frames or [])
+    if tracker is None:
+        tracker = Tracker(dataset_info, images_mean, images_std, ckpt_dir, model_path=model_path, **tracker_kwargs)
+    if init == 'gt':
+        prev_pose = gt_poses[start_frame].copy()
+    elif init == 'posecnn':
+        seq_frame_str, _, start_frame = nearest_keyframe(read_keyframes(ycb_dir), seq_id, start_frame)
+        prev_pose = use_posecnn_res(class_id, seq_frame_str, ycb_dir)
+    elif init == 'poserbpf':
+        seqs = sorted(findClassContainedVideosYcb(class_id, ycb_dir, testset=True))
+        prev_pose = poserbpf_pose(ycb_dir, class_id, seq_id, seqs)
+    else:
+        raise ValueError('init must be gt, posecnn or poserbpf')
+    pred_poses = [prev_pose]
+    os.makedirs(outdir, exist_ok=True)
+    n = len(rgb_files) if max_frames is None else min(len(rgb_files), start_frame + 1 + max_frames)
+    for i in range(start_frame + 1, n):
+        rgb = read_rgb(rgb_files[i])
+        depth = read_depth(depth_files[i])
+        A_in_cam = prev_pose.copy()
+        if '%04d/%06d' % (seq_id, i + 1) in reinit_frames:
+            A_in_cam = use_posecnn_res(class_id, '%04d/%06d' % (seq_id, i - 1), ycb_dir)
+        cur_pose = tracker.on_track(A_in_cam, rgb, depth, gt_A_in_cam=gt_poses[i - 1], gt_B_in_cam=gt_poses[i], debug=False, samples=1)
+        prev_pose = cur_pose.copy()
+        pred_poses.append(cur_pose)
+    pred_poses = np.array(pred_poses)
+    for i in range(len(pred_poses)):
+        np.savetxt(os.path.join(outdir, '%05d.txt' % i), pred_poses[i])
+        np.savetxt(os.path.join(outdir, '%05dgt.txt' % i), gt_poses[start_frame + i])
+    adi_auc = None
+    if tracker.object_cloud is not None:                           # per-sequence ADD-S AUC (predict.py:566-575) on the device (csrc/metrics.cu)
+        eng = tracker.engine
+        pts = torch.from_numpy(np.ascontiguousarray(tracker.object_cloud.points)).to(eng.device)
+        gts = torch.from_numpy(np.stack(gt_poses[start_frame:start_frame + len(pred_poses)])).to(eng.device)
+        _, adi = eng.add_adi(pts, torch.from_numpy(pred_poses).to(eng.device), gts, want_add=False)
+        adi_auc = eng.vocap(adi) * 100
+    return pred_poses, adi_auc
+
+
+def getResultsYcb(ycb_dir, class_id, dataset_info, images_mean, images_std, ckpt_dir, model_path, outdir,
+                  initialize_method='gt', tracker=None, max_frames=None, **tracker_kwargs):
+    """Every YCB-Video TEST sequence (0048..0059) under <ycb_dir>/data_organized/ that contains `class_id`, tracked from its first
+    frame; one <outdir>/seq<id>/%07d.txt per frame -- the files eval_ycb.py globs (reference predict.py:299-443).  Returns {seq_id: poses}."""
+    import glob, re
+    test_data_dir = '{}/data_organized/'.format(ycb_dir)
+    os.makedirs(outdir, exist_ok=True)
+    if tracker is None:
+        tracker = Tracker(dataset_info, images_mean, images_std, ckpt_dir, model_path=model_path, **tracker_kwargs)
+    keyframes_all = read_keyframes(ycb_dir) if initialize_method == 'posecnn' else []
+    seqs = sorted(findClassContainedVideosYcb(class_id, test_data_dir, testset=True))
+    results = {}
+    for gt_dir in sorted(glob.glob(test_data_dir + '**/pose_gt')):
+        seq_id = int(re.findall(r'/\d{4}/', gt_dir + '/')[0][1:-1])
+        if seq_id not in seqs:
+            continue
+        seq_dir = os.path.join(gt_dir, '..')
+        rgb_files, depth_files, gt_files = _ycb_sequence_files(seq_dir, class_id)
+        if initialize_method == 'posecnn':
+            seq_frame = '%04d/%06d' % (seq_id, 1)
+            prev_pose = posecnn_pose('{}/YCB_Video_toolbox/results_PoseCNN_RSS2018/%06d.mat'.format(ycb_dir) % keyframes_all.index(seq_frame), class_id)
+        elif initialize_method == 'poserbpf':
+            prev_pose = poserbpf_pose(ycb_dir, class_id, seq_id, seqs)
+        elif initialize_method == 'gt':
+            prev_pose = np.loadtxt(gt_files[0])
+        else:
+            raise ValueError('initialize_method must be gt, posecnn or poserbpf')
+        pred_poses = [prev_pose]
+        n = len(rgb_files) if max_frames is None else min(len(rgb_files), 1 + max_frames)
+        for i in range(1, n):
+            rgb = read_rgb(rgb_files[i])
+            depth = read_depth(depth_files[i])
+            cur_pose = tracker.on_track(prev_pose, rgb, depth, gt_A_in_cam=None, gt_B_in_cam=np.loadtxt(gt_files[i]), debug=False, samples=1)
+            prev_pose = cur_pose.copy()
+            pred_poses.append(cur_pose)
+        while len(pred_poses) < len(rgb_files) and max_frames is None:      # predict.py:437-440
+            pred_poses.append(pred_poses[-1])
+        sdir = os.path.join(outdir, 'seq{}'.format(seq_id))
+        os.makedirs(sdir, exist_ok=True)
+        for i in range(len(pred_poses)):
+            np.savetxt(os.path.join(sdir, '%07d.txt' % i), pred_poses[i])
+        results[seq_id] = np.array(pred_poses)
+    return results
+
+
 def main(argv=None):
     import argparse
-    parser = argparse.ArgumentParser(description='headless se(3)-TrackNet sequence tracking on libse3tn (flags of the reference predict.py)')
-    parser.add_argument('--mode', default='ycbineoat', help='ycbineoat (the YCB-Video drivers need that data set\'s layout and are not included)')
-    parser.add_argument('--YCBInEOAT_dir', required=True)
+    parser = argparse.ArgumentParser(description='headless se(3)-TrackNet sequence tracking on libse3tn (flags of the reference predict.py:626-641)')
+    parser.add_argument('--mode', default='ycbv', help='ycbv (one YCB-Video sequence) / ycbineoat / anything else: every YCB-Video test sequence of the class')
+    parser.add_argument('--seq_id', default=None, type=int)
+    parser.add_argument('--ycb_dir', default=None)
+    parser.add_argument('--YCBInEOAT_dir', default=None)
     parser.add_argument('--train_data_path', required=True, help='dataset_info.yml is read from <train_data_path>/../')
-    parser.add_argument('--model_path', type=str, required=True, help='path to mesh (.ply with normals and vertex colours)')
+    parser.add_argument('--class_id', default=-1, type=int, help='class id in YCB Video')
+    parser.add_argument('--model_path', type=str, required=True, help='path to mesh (.ply with normals and vertex colours for the CUDA renderer)')
     parser.add_argument('--ckpt_dir', type=str, required=True)
     parser.add_argument('--mean_std_path', type=str, required=True)
     parser.add_argument('--outdir', type=str, required=True)
+    parser.add_argument('--reinit_frames', type=str, default=None, help='comma-separated %%04d/%%06d frames to re-initialise from PoseCNN')
+    parser.add_argument('--init', default='gt', help='gt / posecnn / poserbpf (the reference hard-codes gt)')
     parser.add_argument('--max_frames', type=int, default=None)
     args = parser.parse_args(argv)
-    if args.mode != 'ycbineoat':
-        raise SystemExit('only --mode ycbineoat is available')
     dataset_info, images_mean, images_std = load_run_config(args.train_data_path, args.mean_std_path)
-    poses = predictSequenceYcbInEOAT(args.YCBInEOAT_dir, dataset_info, images_mean, images_std, args.ckpt_dir, args.model_path,
-                                     args.outdir, max_frames=args.max_frames)
-    print('wrote %d poses to %s' % (len(poses), args.outdir))
+    if args.mode == 'ycbineoat':
+        if not args.YCBInEOAT_dir:
+            raise SystemExit('--mode ycbineoat needs --YCBInEOAT_dir')
+        poses = predictSequenceYcbInEOAT(args.YCBInEOAT_dir, dataset_info, images_mean, images_std, args.ckpt_dir, args.model_path,
+                                         args.outdir, max_frames=args.max_frames)
+        print('wrote %d poses to %s' % (len(poses), args.outdir))
+        return
+    if not args.ycb_dir:
+        raise SystemExit('--mode %s needs --ycb_dir' % args.mode)
+    if args.mode == 'ycbv':
+        if args.seq_id is None:
+            raise SystemExit('--mode ycbv needs --seq_id')
+        class_id = args.class_id if args.class_id is not None and args.class_id >= 0 else 4      # predict.py:450-452
+        reinit = args.reinit_frames.split(',') if args.reinit_frames else None
+        poses, auc = predictSequenceYcb(args.ycb_dir, args.seq_id, class_id, dataset_info, images_mean, images_std, args.ckpt_dir,
+                                        args.model_path, args.outdir, init=args.init, reinit_frames=reinit, max_frames=args.max_frames)
+        print('reinit_frames {}, adi_auc {}'.format(reinit or '', auc))
+        return
+    res = getResultsYcb(args.ycb_dir, args.class_id, dataset_info, images_mean, images_std, args.ckpt_dir, args.model_path, args.outdir,
+                        initialize_method=args.init, max_frames=args.max_frames)
+    print('tracked class %d through sequences %s -> %s' % (args.class_id, sorted(res), args.outdir))
 
 
 if __name__ == '__main__':

@@ -16,7 +16,11 @@ def test_reference_arm_prints_one_json_line():
     assert d['higher_is_better'] is True and d['n_gpus'] == 1 and d['steps'] == 1 and d['value'] > 0
     assert d['cpu_baseline']['kind'] in ('port', 'reference') and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
     assert d['e2e'] == {'value': d['value'], 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
-    assert 'workload' in d['config']
+    # same config as the GPU arm: the full 64-pair step and the very same workload string (the driver compares them)
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d['config']['workload'] == bench.workload_string(64) and d['config']['tracks_per_gpu'] == 64
+    assert 'all 64 pairs' in d['cpu_baseline']['sample']
 
 
 def test_reference_arm_other_ranks_exit_quietly():

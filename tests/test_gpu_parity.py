@@ -8,7 +8,7 @@ Tolerances:
     north_star) on EVERY case here, including large-magnitude raw-regime inputs and both weight seeds
   * network 6-vector, TF32 tensor-core path:    same gate where its 10-bit operands allow it (tensor
     regime, raw regime with weight seed 0); documented to exceed it on raw regime / weight seed 1
-  * network 6-vector, BF16 (1 product) path:    rtol 5e-3 / atol 2e-3 (BASELINE configs[2]: bf16 operands AND 2-byte activations)
+  * network 6-vector, BF16 (1 product) path:    rtol 1e-2 / atol 5e-3 (BASELINE configs[2]: bf16 operands AND 2-byte activations)
   * network 6-vector, FP32 FFMA path:           rtol 1e-4 / atol 2e-6
   * pose update / so(3) log (fp64 + libm trig): atol 1e-7 / 1e-9
   * poses produced from a TF32 6-vector: the gate propagated through datasets.py:169-174,
@@ -24,10 +24,10 @@ pytestmark = pytest.mark.gpu
 RTOL, ATOL = 1e-3, 1e-4
 POSE_ATOL = 1e-4
 # bf16: 2-byte activations / weights, fp32 accumulate.  A CPU emulation of exactly that rounding (scripts/precision_study.py)
-# gives max |err| 6.2e-4 .. 6.7e-4 on the 6-vector over 16 pairs and both weight seeds; the gate leaves ~3x headroom, so a
-# regression by a factor of a few fails (the round-1 gate of (5e-2, 2e-2) would have hidden a 40x one).
-RAW_BF16_GATE = (5e-2, 2e-2)
-GATES = {'bf16x3': (RTOL, ATOL), 'tf32': (RTOL, ATOL), 'fp32': (1e-4, 2e-6), 'bf16': (5e-3, 2e-3)}
+# gives max |err| 6.2e-4 .. 6.7e-4 on the 6-vector for tensor-regime inputs (16 pairs, both weight seeds); on config 1 (the shipped
+# image pair, normalised magnitudes up to ~40) B200 measures 3.8e-3.  The gate is ~2x that worst case -- 5x tighter than the
+# round-1 gate of (5e-2, 2e-2), which would have hidden a 40x regression.
+GATES = {'bf16x3': (RTOL, ATOL), 'tf32': (RTOL, ATOL), 'fp32': (1e-4, 2e-6), 'bf16': (1e-2, 5e-3)}
 
 
 def sha(a):
@@ -642,6 +642,93 @@ def test_headless_sequence_driver(pkg, synth, tmp_path):
         ref = O.on_track(sd, prev, rgb, depth, ra, da, K, 200.0, mean, std, 0.03, 30 * np.pi / 180)
         assert got.shape == (4, 4) and np.abs(got - ref).max() < 6 * POSE_ATOL, 'frame %d: %.3g' % (i, np.abs(got - ref).max())
         prev = got                                                  # follow the written trajectory, as eval_ycb.py reads it
+
+
+def test_ycb_video_drivers_on_synthetic_layout(pkg, synth, tmp_path):
+    """SURVEY 8f row 3, the YCB-Video half (reference predict.py:299-575): a synthetic data set in the YCB-Video layout (two test
+    sequences, keyframe.txt, a PoseCNN result file) through predictSequenceYcb (gt init, then PoseCNN init + a re-initialisation
+    frame) and getResultsYcb, every written pose against the oracle fed from the same files."""
+    import cv2, scipy.io
+    pr = importlib.import_module('iros20-6d-pose-tracking_b200.predict')
+    mio = importlib.import_module('iros20-6d-pose-tracking_b200.mesh_io')
+    K = synth.CAMERA_K
+    ycb = tmp_path / 'ycb'
+    cls, nframes = 4, 4
+    traj = {}
+    for seq in (48, 49):
+        base = ycb / 'data_organized' / ('%04d' % seq)
+        for d in ('color', 'depth_filled', 'seg', 'pose_gt/%d' % cls):
+            (base / d).mkdir(parents=True)
+        gt = synth.raw_poses(nframes, seed=seq)
+        gt[1:, :3, 3] = gt[0, :3, 3] + 0.002 * np.arange(1, nframes)[:, None]     # a slowly drifting object
+        gt[1:, :3, :3] = gt[0, :3, :3]
+        traj[seq] = gt
+        for i in range(nframes):
+            rgb, depth = synth.raw_frame(seed=100 * seq + i)
+            cv2.imwrite(str(base / 'color' / ('%06d-color.png' % (i + 1))), rgb[..., ::-1])
+            cv2.imwrite(str(base / 'depth_filled' / ('%06d-depth.png' % (i + 1))), depth)
+            np.savetxt(str(base / 'pose_gt' / str(cls) / ('%06d.txt' % (i + 1))), gt[i])
+    (ycb / 'image_sets').mkdir()
+    (ycb / 'image_sets' / 'keyframe.txt').write_text('0048/000001\n0048/000002\n0049/000001\n')
+    pc = ycb / 'YCB_Video_toolbox' / 'results_PoseCNN_RSS2018'
+    pc.mkdir(parents=True)
+    from scipy.spatial.transform import Rotation
+    def to_icp(pose):
+        q = Rotation.from_matrix(pose[:3, :3]).as_quat()              # x y z w
+        return np.r_[q[3], q[0], q[1], q[2], pose[:3, 3]]
+    posecnn0 = traj[48][0].copy(); posecnn0[:3, 3] += [0.003, -0.002, 0.004]
+    posecnn1 = traj[48][1].copy(); posecnn1[:3, 3] += [-0.002, 0.001, 0.002]
+    for idx, pz in ((0, posecnn0), (1, posecnn1), (2, traj[49][0])):
+        scipy.io.savemat(str(pc / ('%06d.mat' % idx)), {'rois': np.array([[0, 1, 0, 0, 0, 0], [0, cls, 0, 0, 0, 0]], dtype=np.float64),
+                                                        'poses_icp': np.stack([to_icp(np.eye(4)), to_icp(pz)])})
+    info = {'resolution': 176, 'object_width': 200.0, 'boundingbox': 10,
+            'camera': {'focalX': float(K[0, 0]), 'focalY': float(K[1, 1]), 'centerX': float(K[0, 2]), 'centerY': float(K[1, 2]), 'height': 480, 'width': 640}}
+    mean, std = synth.default_mean_std()
+    sd = synth.make_state_dict(0)
+    ply = str(tmp_path / 'textured.ply')
+    mio.save_ply_mesh(ply, synth.mesh(3, seed=0))
+    mesh = mio.load_ply_mesh(ply)
+    trk = pkg.Tracker(info, mean, std, {'state_dict': sd}, model_path=ply, max_batch=4)
+
+    def oracle_chain(seq, start_pose, reinit=None, start=0):
+        base = ycb / 'data_organized' / ('%04d' % seq)
+        prev, out = start_pose.copy(), [start_pose.copy()]
+        for i in range(start + 1, nframes):
+            rgb = pr.read_rgb(str(base / 'color' / ('%06d-color.png' % (i + 1)))); depth = pr.read_depth(str(base / 'depth_filled' / ('%06d-depth.png' % (i + 1))))
+            if reinit and i in reinit:
+                prev = reinit[i].copy()
+            ra, da = O.render_window(prev, K, 200.0, mesh)
+            prev = O.on_track(sd, prev, rgb, depth, ra, da, K, 200.0, mean, std, 0.03, 5 * np.pi / 180)
+            out.append(prev)
+        return np.stack(out)
+
+    # (1) one sequence from its ground-truth pose
+    poses, auc = pr.predictSequenceYcb(str(ycb / 'data_organized'), 48, cls, info, mean, std, None, ply, str(tmp_path / 'o1'), init='gt', tracker=trk)
+    ref = oracle_chain(48, traj[48][0])
+    assert poses.shape == (nframes, 4, 4) and np.abs(poses - ref).max() < 6 * POSE_ATOL
+    assert np.allclose(np.loadtxt(str(tmp_path / 'o1' / '00002.txt')), poses[2]) and np.allclose(np.loadtxt(str(tmp_path / 'o1' / '00002gt.txt')), traj[48][2])
+    ref_adi = np.array([O.adi(ref[i], traj[48][i], np.asarray(trk.object_cloud.points)) for i in range(nframes)])
+    assert auc is not None and abs(auc - O.vocap(ref_adi) * 100) < 0.5
+
+    # (2) PoseCNN initialisation (start_frame 1: keyframe 0048/000001 = result file 0) and a re-initialisation at 0048/000004:
+    #     frame index i = 3 restarts from PoseCNN's estimate at the keyframe nearest to 0048/%06d % (i - 1) = 000002 -> file 1
+    ycb_root = ycb / 'data_organized'
+    for sub in ('image_sets', 'YCB_Video_toolbox'):
+        os.symlink(str(ycb / sub), str(ycb_root / sub))              # the reference reads both roots from the same --ycb_dir
+    poses2, _ = pr.predictSequenceYcb(str(ycb_root), 48, cls, info, mean, std, None, ply, str(tmp_path / 'o2'), init='posecnn',
+                                      reinit_frames=['0048/000004'], start_frame=1, tracker=trk)
+    ref2 = oracle_chain(48, posecnn0, reinit={3: posecnn1}, start=1)
+    assert poses2.shape == ref2.shape == (nframes - 1, 4, 4) and np.abs(poses2 - ref2).max() < 6 * POSE_ATOL
+    assert np.abs(poses2[2] - oracle_chain(48, posecnn0, start=1)[2]).max() > 1e-4      # the re-initialisation really took another path
+
+    # (3) every test sequence of the class (what eval_ycb.py scores)
+    res = pr.getResultsYcb(str(ycb), cls, info, mean, std, None, ply, str(tmp_path / 'o3'), tracker=trk)
+    assert sorted(res) == [48, 49]
+    for seq in (48, 49):
+        refq = oracle_chain(seq, traj[seq][0])
+        got = np.stack([np.loadtxt(str(tmp_path / 'o3' / ('seq%d' % seq) / ('%07d.txt' % i))) for i in range(nframes)])
+        assert np.abs(got - refq).max() < 6 * POSE_ATOL and np.allclose(got, res[seq])
+    trk.engine.close()
 
 
 # ------------------------------------------------------------------------------ depth hole filling (SURVEY 8f row 4)
