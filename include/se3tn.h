@@ -206,6 +206,14 @@ int se3tn_render(se3tn_ctx* ctx, const double* K, const double* poses, const dou
 int se3tn_fill_depth(se3tn_ctx* ctx, const uint16_t* depth_mm, int H, int W, double max_depth,
                      uint16_t* out_mm, float* out_m, void* stream);
 
+/* The same with the reference's two optional arguments (Utils.py:455: extrapolate=False, blur_type='bilateral'):
+ * extrapolate != 0: every column's first valid value is extended to the top row and what is still empty takes a 31x31
+ * dilation (Utils.py:486-497); blur_type SE3TN_BLUR_GAUSSIAN: cv2.GaussianBlur(5x5, sigma 0) on the valid pixels instead of
+ * the bilateral filter (Utils.py:506-510). */
+enum { SE3TN_BLUR_BILATERAL = 0, SE3TN_BLUR_GAUSSIAN = 1 };
+int se3tn_fill_depth_ex(se3tn_ctx* ctx, const uint16_t* depth_mm, int H, int W, double max_depth, int extrapolate, int blur_type,
+                        uint16_t* out_mm, float* out_m, void* stream);
+
 /* ---- introspection (tests / profiling) -------------------------------------------------------- */
 
 /* Device pointer + per-image float count of an internal NHWC activation buffer.

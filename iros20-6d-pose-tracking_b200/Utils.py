@@ -73,14 +73,15 @@ def adi(pred, gt, model):
 
 
 def fill_depth(depth, max_depth=2.0, extrapolate=False, blur_type='bilateral'):
-    """Drop-in for reference Utils.py:455-514 in the configuration its ROS node uses (predict_ros.py:38-41): depth in METRES
-    (any float array, as the reference takes it) -> float32 metres, computed by libse3tn.  The pipeline quantises the input
-    to whole millimetres first -- exact for the node's `uint16 / 1e3` input."""
-    if extrapolate or blur_type != 'bilateral':
-        raise NotImplementedError('libse3tn implements the configuration predict_ros.py uses: extrapolate=False, bilateral')
+    """Drop-in for reference Utils.py:455-514: depth in METRES (any float array, as the reference takes it) -> float32 metres,
+    computed by libse3tn.  The pipeline quantises the input to whole millimetres first -- exact for the ROS node's
+    `uint16 / 1e3` input (predict_ros.py:38-41)."""
+    if blur_type not in ('bilateral', 'gaussian'):
+        raise ValueError("blur_type must be 'bilateral' or 'gaussian'")           # the reference silently skips the blur for anything else
     eng = _eng()
     mm = np.rint(np.asarray(depth, dtype=np.float64) * 1e3)
     if mm.min() < 0 or mm.max() > 65535:
         raise ValueError('depth must be within 0 .. 65.535 m')
-    _, out_m = eng.fill_depth(torch.from_numpy(mm.astype(np.uint16)).to(eng.device), max_depth=max_depth, want_metres=True)
+    _, out_m = eng.fill_depth(torch.from_numpy(mm.astype(np.uint16)).to(eng.device), max_depth=max_depth, want_metres=True,
+                              extrapolate=extrapolate, blur_type=blur_type)
     return out_m.cpu().numpy()

@@ -47,53 +47,81 @@ __device__ __forceinline__ float depth_offset(unsigned d, double z1000, bool gl)
     return static_cast<float>(gl ? __dadd_rn(static_cast<double>(d), z1000) : __dsub_rn(static_cast<double>(d), z1000));
 }
 
+// One CTA = one quarter (44 rows) of one track's 176x176 window.  Everything that depends only on the pixel VALUE is tabulated once
+// per CTA with the same IEEE operations the per-pixel code would use (bit-identical results):
+//   * (v - mean) / std of an 8-bit colour value: 6 channels x 256 entries;
+//   * the whole depth chain  u16 mm -> clip -> float32(double(d) -+ z*1000) -> (x - mean) / std : a function of d alone for a given
+//     track, non-constant only for 100 < d < 2000 -> 2 x 1899 entries (A and B use different statistics);
+//   * cv2's nearest-neighbour source index floor(dst * (1 / (176 / size))) for the 176 columns and this CTA's 44 rows.
+// The per-pixel work is then byte loads, table look-ups, the bf16 / tf32 packing and two 16-byte stores: ~3x fewer instructions
+// than dividing per pixel (ncu, round 2: the kernel was issue-bound at 274 instructions per pixel, DRAM at 7 %).
+constexpr int kPreRows = 44;                      // rows per CTA (4 CTAs per track)
+constexpr int kDepthLo = 101, kDepthN = 1899;     // valid raw depths 101..1999
+
 __global__ void __launch_bounds__(256, 4)
 preprocess_kernel(PreprocessArgs a)
 {
     ptx::grid_dep_launch();
     const int n = blockIdx.y;
-    const int quad = blockIdx.x * blockDim.x + threadIdx.x;     // thread index within the image: 4 pixels each (see below)
+    const int row0 = blockIdx.x * kPreRows;
     const double* pose = a.poses + n * 16;
-    // the crop window and cv2's inverse scales are per track: one thread computes them for the block
-    __shared__ int s_win[4];
-    __shared__ double s_inv[2];
-    // (v - mean) / std of an 8-bit colour value takes 256 values per channel: tabulate the six colour channels once per block
-    // with the SAME IEEE division the per-pixel code would use (bit-identical), leaving two divisions per pixel (the depths)
     __shared__ float s_lut[6][256];
+    __shared__ float s_dlut[2][kDepthN];
+    __shared__ float s_dinv[2];                    // normalised value of an invalid depth (2000)
+    __shared__ short s_sx[kImg], s_sy[kPreRows];
+    __shared__ int s_win[4];
+    const int wi = a.weight_ids ? min(max(a.weight_ids[n], 0), a.stats_rows - 1) : 0;   // ids without statistics are rejected on the host where it can see them; never index past the table
     {
-        const int wi0 = a.weight_ids ? min(max(a.weight_ids[n], 0), a.stats_rows - 1) : 0;   // ids without statistics are rejected on the host where it can see them; never index past the table
         const float v = static_cast<float>(threadIdx.x);
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
             const int mc = c < 3 ? c : c + 1;                   // A: mean[0..2], B: mean[4..6]
-            s_lut[c][threadIdx.x] = a.stats_f64 ? norm_f64(v, a.mean64[wi0 * 8 + mc], a.std64[wi0 * 8 + mc])
-                                                : norm_f32(v, a.mean32[wi0 * 8 + mc], a.std32[wi0 * 8 + mc]);
+            s_lut[c][threadIdx.x] = a.stats_f64 ? norm_f64(v, a.mean64[wi * 8 + mc], a.std64[wi * 8 + mc])
+                                                : norm_f32(v, a.mean32[wi * 8 + mc], a.std32[wi * 8 + mc]);
         }
     }
     ptx::grid_dep_wait();                                       // poses come from the previous step's pose update
-    if (threadIdx.x == 0 && !a.b_precropped) {
-        int top, left, ch, cw;
-        bbox_window(pose, a.fx, a.fy, a.cx, a.cy, a.object_width[n], 1000.0, 1000.0, 1000.0, top, left, ch, cw);
-        s_win[0] = top; s_win[1] = left; s_win[2] = ch; s_win[3] = cw;
-        // cv2 resizeNN index: floor(dst * ifx), ifx = 1/(dsize/ssize) in double, clamped to ssize-1
-        s_inv[0] = (cw > 0) ? 1.0 / (static_cast<double>(kImg) / cw) : 0.0;
-        s_inv[1] = (ch > 0) ? 1.0 / (static_cast<double>(kImg) / ch) : 0.0;
-    }
-    __syncthreads();
-    // A warp owns 128 consecutive pixels of the flat 176x176 image (30976 = 242 * 128); lane L handles pixels
-    // base + L, base + 32 + L, base + 64 + L, base + 96 + L, so every load / store instruction of the warp touches 32 CONSECUTIVE
-    // pixels: the 16-byte stem stores are 512 contiguous bytes per instruction (4 lines instead of 16 with 4 pixels per thread).
-    const int base = (quad >> 5) * 128 + (quad & 31);
-    if ((quad >> 5) * 128 >= kImg * kImg) return;
     const double z = pose[11];
     const bool gl = z < 0;
     const double z1000 = __dmul_rn(z, 1000.0);
-    const int wi = a.weight_ids ? min(max(a.weight_ids[n], 0), a.stats_rows - 1) : 0;
+    for (int i = threadIdx.x; i < 2 * kDepthN + 2; i += blockDim.x) {
+        const int which = i >= kDepthN + 1;                     // 0: A statistics (channel 3), 1: B statistics (channel 7)
+        const int j = which ? i - (kDepthN + 1) : i;            // j == kDepthN: the invalid-depth value
+        const float zf = (j == kDepthN) ? 2000.f : depth_offset(static_cast<unsigned>(kDepthLo + j), z1000, gl);
+        const int mc = which ? 7 : 3;
+        const float r = a.stats_f64 ? norm_f64(zf, a.mean64[wi * 8 + mc], a.std64[wi * 8 + mc]) : norm_f32(zf, a.mean32[wi * 8 + mc], a.std32[wi * 8 + mc]);
+        if (j == kDepthN) s_dinv[which] = r; else s_dlut[which][j] = r;
+    }
+    if (!a.b_precropped) {
+        if (threadIdx.x == 0) {
+            int top, left, ch, cw;
+            bbox_window(pose, a.fx, a.fy, a.cx, a.cy, a.object_width[n], 1000.0, 1000.0, 1000.0, top, left, ch, cw);
+            s_win[0] = top; s_win[1] = left; s_win[2] = ch; s_win[3] = cw;
+        }
+        __syncthreads();
+        const int ch = s_win[2], cw = s_win[3];
+        // cv2 resizeNN index: floor(dst * ifx), ifx = 1/(dsize/ssize) in double, clamped to ssize-1
+        const double ifx = (cw > 0) ? 1.0 / (static_cast<double>(kImg) / cw) : 0.0;
+        const double ify = (ch > 0) ? 1.0 / (static_cast<double>(kImg) / ch) : 0.0;
+        if (threadIdx.x < kImg) { int sx = static_cast<int>(floor(threadIdx.x * ifx)); if (sx > cw - 1) sx = cw - 1; s_sx[threadIdx.x] = static_cast<short>(sx); }
+        if (threadIdx.x >= 192 && threadIdx.x < 192 + kPreRows) {
+            const int y = row0 + threadIdx.x - 192;
+            int sy = static_cast<int>(floor(y * ify)); if (sy > ch - 1) sy = ch - 1; s_sy[threadIdx.x - 192] = static_cast<short>(sy);
+        }
+    }
+    __syncthreads();
+    const int top = s_win[0], left = s_win[1], ch = s_win[2], cw = s_win[3];
     const size_t img0 = static_cast<size_t>(n) * kImg * kImg;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int pix = base + 32 * i;
-        const int y = pix / kImg, x = pix - y * kImg;
+    auto depth_norm = [&](unsigned d, int which) -> float {
+        const unsigned j = d - kDepthLo;
+        return j < static_cast<unsigned>(kDepthN) ? s_dlut[which][j] : s_dinv[which];
+    };
+    // consecutive threads take consecutive pixels: every load / store instruction of a warp touches 32 consecutive pixels
+    // (the 16-byte stem stores are 512 contiguous bytes per instruction)
+    for (int lp = threadIdx.x; lp < kPreRows * kImg; lp += blockDim.x) {
+        const int ly = lp / kImg, x = lp - ly * kImg;
+        const int y = row0 + ly;
+        const int pix = y * kImg + x;
         const size_t ao = img0 + pix;
         // ---- B: observed frame crop ------------------------------------------------------------------
         unsigned rB = 0, gB = 0, bB = 0, dB = 0;
@@ -102,18 +130,13 @@ preprocess_kernel(PreprocessArgs a)
             const uint8_t* pr = a.frame_rgb + ao * 3;
             rB = pr[0]; gB = pr[1]; bB = pr[2];
             dB = a.frame_depth[ao];
-        } else {
-            const int top = s_win[0], left = s_win[1], ch = s_win[2], cw = s_win[3];
-            if (ch > 0 && cw > 0) {
-                int sy = static_cast<int>(floor(y * s_inv[1])); if (sy > ch - 1) sy = ch - 1;
-                int sx = static_cast<int>(floor(x * s_inv[0])); if (sx > cw - 1) sx = cw - 1;
-                const int fy_ = top + sy, fx_ = left + sx;
-                if (fy_ >= 0 && fy_ < a.H && fx_ >= 0 && fx_ < a.W) {
-                    const size_t fo = static_cast<size_t>(fy_) * a.W + fx_;
-                    const uint8_t* pr = a.frame_rgb + fo * 3;
-                    rB = pr[0]; gB = pr[1]; bB = pr[2];
-                    dB = a.frame_depth[fo];
-                }
+        } else if (ch > 0 && cw > 0) {
+            const int fy_ = top + s_sy[ly], fx_ = left + s_sx[x];
+            if (fy_ >= 0 && fy_ < a.H && fx_ >= 0 && fx_ < a.W) {
+                const size_t fo = static_cast<size_t>(fy_) * a.W + fx_;
+                const uint8_t* pr = a.frame_rgb + fo * 3;
+                rB = pr[0]; gB = pr[1]; bB = pr[2];
+                dB = a.frame_depth[fo];
             }
         }
         if (a.crop_rgb) { uint8_t* o = a.crop_rgb + ao * 3; o[0] = static_cast<uint8_t>(rB); o[1] = static_cast<uint8_t>(gB); o[2] = static_cast<uint8_t>(bB); }
@@ -121,18 +144,8 @@ preprocess_kernel(PreprocessArgs a)
         // ---- A: rendered previous view --------------------------------------------------------------
         const uint8_t* pa = a.rgbA + ao * 3;
         const unsigned rA = pa[0], gA = pa[1], bA = pa[2], dA = a.depthA[ao];
-
-        const float zA = depth_offset(dA, z1000, gl), zB = depth_offset(dB, z1000, gl);
-        float4 vA, vB;
-        if (a.stats_f64) {
-            const double* m = a.mean64 + wi * 8; const double* s = a.std64 + wi * 8;
-            vA = make_float4(s_lut[0][rA], s_lut[1][gA], s_lut[2][bA], norm_f64(zA, m[3], s[3]));
-            vB = make_float4(s_lut[3][rB], s_lut[4][gB], s_lut[5][bB], norm_f64(zB, m[7], s[7]));
-        } else {
-            const float* m = a.mean32 + wi * 8; const float* s = a.std32 + wi * 8;
-            vA = make_float4(s_lut[0][rA], s_lut[1][gA], s_lut[2][bA], norm_f32(zA, m[3], s[3]));
-            vB = make_float4(s_lut[3][rB], s_lut[4][gB], s_lut[5][bB], norm_f32(zB, m[7], s[7]));
-        }
+        const float4 vA = make_float4(s_lut[0][rA], s_lut[1][gA], s_lut[2][bA], depth_norm(dA, 0));
+        const float4 vB = make_float4(s_lut[3][rB], s_lut[4][gB], s_lut[5][bB], depth_norm(dB, 1));
         if (a.nchwA) {
             float* oa = a.nchwA + static_cast<size_t>(n) * 4 * kImg * kImg + pix;
             float* ob = a.nchwB + static_cast<size_t>(n) * 4 * kImg * kImg + pix;
@@ -160,7 +173,7 @@ static cudaError_t launch_pdl(const void* func, dim3 grid, dim3 block, void** ar
 
 cudaError_t launch_preprocess(const PreprocessArgs& a, int n, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
-    dim3 grid((kImg * kImg / 4 + 255) / 256, n);
+    dim3 grid(kImg / kPreRows, n);
     PreprocessArgs aa = a;
     void* args[] = {&aa};
     return launch_pdl(reinterpret_cast<const void*>(preprocess_kernel), grid, dim3(256), args, s);

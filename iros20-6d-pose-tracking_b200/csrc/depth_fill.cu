@@ -11,6 +11,11 @@
 // accumulation whose order OpenCV's SIMD code does not expose, so the final metres agree to ~5e-7 and the uint16 millimetres
 // to +-1 on the rare pixel that sits on a truncation boundary (tests state both tolerances).
 // One thread per pixel, seven small launches per frame (1.2 MB images, L2 resident); latency matters here, not bandwidth.
+// The two optional branches of the reference (never used by its ROS node) are here too:
+//   extrapolate=True   every column's first valid value is extended to the top of the image, then the remaining empty pixels
+//                      take the 31x31 dilation (separable row / column maxima; exact)
+//   blur_type='gaussian'  cv2.GaussianBlur(5x5, sigma 0 = the fixed [1 4 6 4 1]/16 kernel, BORDER_REFLECT_101) on the valid
+//                      pixels instead of the bilateral filter (float32 row pass then column pass, as OpenCV's separable filter)
 #include "depth_fill.h"
 #include "ptx.cuh"
 #include <cfloat>
@@ -185,9 +190,90 @@ bilateral_finish_kernel(const float* __restrict__ in, const float* __restrict__ 
     if (out_m) out_m[y * W + x] = res;
     if (out_mm) out_mm[y * W + x] = static_cast<uint16_t>(static_cast<int>(res * 1000.0f));      // (depth * 1000).astype(uint16)
 }
+
+// extrapolate: depth[0:top, col] = depth[top, col], top = first row with depth > 0.1 (np.argmax of an all-False column = 0: nothing to do)
+__global__ void extrapolate_top_kernel(float* __restrict__ d, int H, int W)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= W) return;
+    int top = 0;
+    for (int y = 0; y < H; ++y) if (d[y * W + x] > 0.1f) { top = y; break; }
+    const float v = d[top * W + x];
+    for (int y = 0; y < top; ++y) d[y * W + x] = v;
+}
+
+// 31x31 dilation, separable: row maxima ...
+__global__ void __launch_bounds__(kBX * kBY)
+rowmax31_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W)
+{
+    const int x = blockIdx.x * kBX + threadIdx.x, y = blockIdx.y * kBY + threadIdx.y;
+    if (x >= W || y >= H) return;
+    float m = -FLT_MAX;
+    for (int dx = -15; dx <= 15; ++dx) { const int xx = x + dx; if (xx >= 0 && xx < W) m = fmaxf(m, in[y * W + xx]); }
+    out[y * W + x] = m;
+}
+// ... then column maxima, written only where the image is still empty (depth < 0.1)
+__global__ void __launch_bounds__(kBX * kBY)
+large_fill_kernel(const float* __restrict__ rowmax, float* __restrict__ d, int H, int W)
+{
+    const int x = blockIdx.x * kBX + threadIdx.x, y = blockIdx.y * kBY + threadIdx.y;
+    if (x >= W || y >= H) return;
+    if (!(d[y * W + x] < 0.1f)) return;
+    float m = -FLT_MAX;
+    for (int dy = -15; dy <= 15; ++dy) { const int yy = y + dy; if (yy >= 0 && yy < H) m = fmaxf(m, rowmax[yy * W + x]); }
+    d[y * W + x] = m;
+}
+
+__global__ void __launch_bounds__(kBX * kBY)
+median5_plain_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W)
+{
+    const int x = blockIdx.x * kBX + threadIdx.x, y = blockIdx.y * kBY + threadIdx.y;
+    if (x >= W || y >= H) return;
+    float v[25];
+#pragma unroll
+    for (int dy = -2; dy <= 2; ++dy)
+#pragma unroll
+        for (int dx = -2; dx <= 2; ++dx) {
+            const int yy = min(max(y + dy, 0), H - 1), xx = min(max(x + dx, 0), W - 1);
+            v[(dy + 2) * 5 + dx + 2] = in[yy * W + xx];
+        }
+#pragma unroll
+    for (int k = 0; k <= 12; ++k)
+#pragma unroll
+        for (int j = k + 1; j < 25; ++j) { const float a = v[k], b = v[j]; v[k] = fminf(a, b); v[j] = fmaxf(a, b); }
+    out[y * W + x] = v[12];
+}
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * n - 2 - i;
+    return min(max(i, 0), n - 1);
+}
+// cv2.GaussianBlur(depth, (5,5), 0): rows then columns with the fixed kernel [1 4 6 4 1]/16 in float32; result only where depth > 0.1
+__global__ void __launch_bounds__(kBX * kBY)
+gaussian_finish_kernel(const float* __restrict__ in, int H, int W, float max_depth, uint16_t* __restrict__ out_mm, float* __restrict__ out_m)
+{
+    const int x = blockIdx.x * kBX + threadIdx.x, y = blockIdx.y * kBY + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const float k0 = 0.375f, k1 = 0.25f, k2 = 0.0625f;
+    float res = in[y * W + x];
+    if (res > 0.1f) {
+        float rows[5];
+#pragma unroll
+        for (int dy = -2; dy <= 2; ++dy) {
+            const float* r = in + reflect101(y + dy, H) * W;
+            const float c = r[x], l1 = r[reflect101(x - 1, W)], r1 = r[reflect101(x + 1, W)], l2 = r[reflect101(x - 2, W)], r2 = r[reflect101(x + 2, W)];
+            rows[dy + 2] = __fadd_rn(__fadd_rn(__fmul_rn(c, k0), __fmul_rn(__fadd_rn(l1, r1), k1)), __fmul_rn(__fadd_rn(l2, r2), k2));
+        }
+        res = __fadd_rn(__fadd_rn(__fmul_rn(rows[2], k0), __fmul_rn(__fadd_rn(rows[1], rows[3]), k1)), __fmul_rn(__fadd_rn(rows[0], rows[4]), k2));
+    }
+    if (res > 0.1f) res = max_depth - res;
+    if (out_m) out_m[y * W + x] = res;
+    if (out_mm) out_mm[y * W + x] = static_cast<uint16_t>(static_cast<int>(res * 1000.0f));
+}
 }  // namespace
 
-cudaError_t launch_fill_depth(const uint16_t* depth_mm, int H, int W, float max_depth, const FillScratch& sc,
+cudaError_t launch_fill_depth(const uint16_t* depth_mm, int H, int W, float max_depth, bool extrapolate, bool gaussian, const FillScratch& sc,
                               uint16_t* out_mm, float* out_m, cudaStream_t s) {
     if (H <= 0 || W <= 0) return cudaSuccess;
     const dim3 block(kBX, kBY), grid((W + kBX - 1) / kBX, (H + kBY - 1) / kBY);
@@ -195,6 +281,16 @@ cudaError_t launch_fill_depth(const uint16_t* depth_mm, int H, int W, float max_
     box_morph_kernel<2, false><<<grid, block, 0, s>>>(sc.a, sc.b, H, W);            // close = dilate ...
     box_morph_kernel<2, true><<<grid, block, 0, s>>>(sc.b, sc.a, H, W);             // ... then erode
     fill_empty_kernel<<<grid, block, 0, s>>>(sc.a, sc.b, H, W);
+    if (extrapolate) {
+        extrapolate_top_kernel<<<(W + 127) / 128, 128, 0, s>>>(sc.b, H, W);
+        rowmax31_kernel<<<grid, block, 0, s>>>(sc.b, sc.a, H, W);
+        large_fill_kernel<<<grid, block, 0, s>>>(sc.a, sc.b, H, W);
+    }
+    if (gaussian) {
+        median5_plain_kernel<<<grid, block, 0, s>>>(sc.b, sc.a, H, W);
+        gaussian_finish_kernel<<<grid, block, 0, s>>>(sc.a, H, W, max_depth, out_mm, out_m);
+        return cudaGetLastError();
+    }
     init_minmax_kernel<<<1, 1, 0, s>>>(sc.minmax);
     median5_kernel<<<grid, block, 0, s>>>(sc.b, sc.a, H, W, sc.minmax);
     lut_kernel<<<1, 256, 0, s>>>(sc.minmax, sc.lut, 1.5f);

@@ -5,6 +5,6 @@
 namespace se3tn {
 constexpr int kFillLutEntries = (1 << 12) + 2;
 struct FillScratch { float* a; float* b; float* lut; unsigned* minmax; };   // a, b: H*W floats each; lut: kFillLutEntries + 1 floats (scale at the end)
-cudaError_t launch_fill_depth(const uint16_t* depth_mm, int H, int W, float max_depth, const FillScratch& sc,
+cudaError_t launch_fill_depth(const uint16_t* depth_mm, int H, int W, float max_depth, bool extrapolate, bool gaussian, const FillScratch& sc,
                               uint16_t* out_mm, float* out_m, cudaStream_t s);
 }  // namespace se3tn

@@ -964,10 +964,11 @@ int se3tn_allgather_poses(se3tn_ctx* c, void* nccl_comm, const double* local_pos
     return SE3TN_OK;
 }
 
-int se3tn_fill_depth(se3tn_ctx* c, const uint16_t* depth_mm, int H, int W, double max_depth,
-                     uint16_t* out_mm, float* out_m, void* stream) {
+int se3tn_fill_depth_ex(se3tn_ctx* c, const uint16_t* depth_mm, int H, int W, double max_depth, int extrapolate, int blur_type,
+                        uint16_t* out_mm, float* out_m, void* stream) {
     if (!c) return SE3TN_ERR_INVALID;
-    if (!depth_mm || H <= 0 || W <= 0 || (!out_mm && !out_m)) return fail(c, SE3TN_ERR_INVALID, "se3tn_fill_depth: bad arguments");
+    if (!depth_mm || H <= 0 || W <= 0 || (!out_mm && !out_m) || (blur_type != SE3TN_BLUR_BILATERAL && blur_type != SE3TN_BLUR_GAUSSIAN))
+        return fail(c, SE3TN_ERR_INVALID, "se3tn_fill_depth: bad arguments");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     DeviceGuard guard(c->device);
     const size_t px = static_cast<size_t>(H) * W;
@@ -982,9 +983,14 @@ int se3tn_fill_depth(se3tn_ctx* c, const uint16_t* depth_mm, int H, int W, doubl
         CU_TRY(c, cudaMalloc(&c->fill.lut, (kFillLutEntries + 1) * sizeof(float)));
         CU_TRY(c, cudaMalloc(&c->fill.minmax, 2 * sizeof(unsigned)));
     }
-    CU_TRY(c, launch_fill_depth(depth_mm, H, W, static_cast<float>(max_depth), c->fill, out_mm, out_m, s));
+    CU_TRY(c, launch_fill_depth(depth_mm, H, W, static_cast<float>(max_depth), extrapolate != 0, blur_type == SE3TN_BLUR_GAUSSIAN, c->fill, out_mm, out_m, s));
     c->launches += 8;
     return SE3TN_OK;
+}
+
+int se3tn_fill_depth(se3tn_ctx* c, const uint16_t* depth_mm, int H, int W, double max_depth,
+                     uint16_t* out_mm, float* out_m, void* stream) {
+    return se3tn_fill_depth_ex(c, depth_mm, H, W, max_depth, 0, SE3TN_BLUR_BILATERAL, out_mm, out_m, stream);
 }
 
 int se3tn_set_mesh(se3tn_ctx* c, int mesh_id, const float* pos, const float* nrm, const uint8_t* col,

@@ -240,16 +240,18 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ live-sensor depth
-    def fill_depth(self, depth_mm, max_depth=2.0, want_metres=False):
-        """fill_depth as predict_ros.py:38-41 applies it (reference Utils.py:455-514): uint16 mm CUDA tensor (H,W) ->
+    def fill_depth(self, depth_mm, max_depth=2.0, want_metres=False, extrapolate=False, blur_type='bilateral'):
+        """fill_depth (reference Utils.py:455-514; predict_ros.py:38-41 uses the defaults): uint16 mm CUDA tensor (H,W) ->
         uint16 mm CUDA tensor (and float32 metres with want_metres)."""
         if depth_mm.dtype != torch.uint16 or depth_mm.dim() != 2 or not depth_mm.is_cuda or not depth_mm.is_contiguous():
             raise ValueError('depth_mm must be a contiguous uint16 CUDA tensor (H,W)')
+        if blur_type not in ('bilateral', 'gaussian'):
+            raise ValueError("blur_type must be 'bilateral' or 'gaussian'")
         H, W = depth_mm.shape
         out = torch.empty_like(depth_mm)
         out_m = torch.empty((H, W), dtype=torch.float32, device=self.device) if want_metres else None
-        _lib.check(self.lib.se3tn_fill_depth(self._ctx, _ptr(depth_mm), int(H), int(W), float(max_depth), _ptr(out), _ptr(out_m),
-                                             _stream(self.device)), self._ctx)
+        _lib.check(self.lib.se3tn_fill_depth_ex(self._ctx, _ptr(depth_mm), int(H), int(W), float(max_depth), int(bool(extrapolate)),
+                                                1 if blur_type == 'gaussian' else 0, _ptr(out), _ptr(out_m), _stream(self.device)), self._ctx)
         return (out, out_m) if want_metres else out
 
     # ------------------------------------------------------------------ introspection

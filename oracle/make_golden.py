@@ -241,6 +241,9 @@ def main():
         dmm = dmm.copy(); dmm[10:30, 20:50] = 0                   # a real hole, not only salt-and-pepper dropouts
         filled = U.fill_depth(dmm / 1e3, max_depth=2.0, extrapolate=False)
         fd['in_' + name] = dmm; fd['out_m_' + name] = filled; fd['out_mm_' + name] = (filled * 1000).astype(np.uint16)
+        # the two optional branches (Utils.py:486-497, 506-510), alone and together
+        for tag, ex, blur in (('ex', True, 'bilateral'), ('ga', False, 'gaussian'), ('exga', True, 'gaussian')):
+            fd['out_m_%s_%s' % (name, tag)] = U.fill_depth(dmm / 1e3, max_depth=2.0, extrapolate=ex, blur_type=blur)
     np.savez_compressed(os.path.join(args.out, 'golden_fill.npz'), **fd)
     for f in sorted(os.listdir(args.out)):
         print(f, os.path.getsize(os.path.join(args.out, f)))

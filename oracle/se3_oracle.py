@@ -443,8 +443,8 @@ def render_window(ob2cam, K, object_width, mesh, size=176, uniforms=None):
 # reference calls; pinned by tests/golden/golden_fill.npz, which oracle/make_golden.py produces with the reference's own
 # Utils.fill_depth).
 # =============================================================================================
-def fill_depth(depth, max_depth=2.0):
-    """Utils.py:455-514 with extrapolate=False, blur_type='bilateral'.  depth: metres (any float dtype) -> float32 metres."""
+def fill_depth(depth, max_depth=2.0, extrapolate=False, blur_type='bilateral'):
+    """Utils.py:455-514.  depth: metres (any float dtype) -> float32 metres."""
     depth = np.asarray(depth).astype(np.float32)
     diamond = np.array([[0, 0, 1, 0, 0], [0, 1, 1, 1, 0], [1, 1, 1, 1, 1], [0, 1, 1, 1, 0], [0, 0, 1, 0, 0]], dtype=np.uint8)
     valid = depth > 0.1
@@ -454,14 +454,27 @@ def fill_depth(depth, max_depth=2.0):
     empty = depth < 0.1
     dilated = cv2.dilate(depth, np.ones((7, 7), np.uint8))
     depth[empty] = dilated[empty]
+    if extrapolate:                                              # Utils.py:486-497
+        top_row = np.argmax(depth > 0.1, axis=0)
+        top_val = depth[top_row, range(depth.shape[1])]
+        for col in range(depth.shape[1]):
+            depth[0:top_row[col], col] = top_val[col]
+        empty = depth < 0.1
+        dilated = cv2.dilate(depth, np.ones((31, 31), np.uint8))
+        depth[empty] = dilated[empty]
     depth = cv2.medianBlur(depth, 5)
-    depth = cv2.bilateralFilter(depth, 5, 1.5, 2.0)
+    if blur_type == 'bilateral':
+        depth = cv2.bilateralFilter(depth, 5, 1.5, 2.0)
+    elif blur_type == 'gaussian':                                # Utils.py:506-510
+        valid = depth > 0.1
+        blurred = cv2.GaussianBlur(depth, (5, 5), 0)
+        depth[valid] = blurred[valid]
     valid = depth > 0.1
     depth[valid] = max_depth - depth[valid]
     return depth
 
 
-def fill_depth_mm(depth_mm):
+def fill_depth_mm(depth_mm, extrapolate=False, blur_type='bilateral'):
     """predict_ros.py:38-41: uint16 millimetres in, uint16 millimetres out."""
-    d = fill_depth(np.asarray(depth_mm).astype(np.uint16) / 1e3, max_depth=2.0)
+    d = fill_depth(np.asarray(depth_mm).astype(np.uint16) / 1e3, max_depth=2.0, extrapolate=extrapolate, blur_type=blur_type)
     return (d * 1000).astype(np.uint16), d

@@ -14,3 +14,4 @@ timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out
 tail -c 1500 gpurun_out/r02_bench_c.json; tail -5 gpurun_out/r02_bench_c.err
 SE3TN_GRAPH=0 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-alt --no-g21 --no-render > gpurun_out/r02_bench_c_nograph.json 2> gpurun_out/r02_bench_c_nograph.err
 tail -c 1200 gpurun_out/r02_bench_c_nograph.json
+timeout 60 ./scripts/umma_tmemA_probe > gpurun_out/r02_tmemA_probe.txt 2>&1; cat gpurun_out/r02_tmemA_probe.txt

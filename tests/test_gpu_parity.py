@@ -760,8 +760,18 @@ def test_fill_depth_vs_reference_and_oracle(pkg, synth, golden_dir, eng):
     U.set_engine(eng)
     got = U.fill_depth(cases[0][0] / 1e3, max_depth=2.0, extrapolate=False)
     assert got.dtype == np.float32 and np.abs(got - cases[0][1]).max() < 2e-6
-    with pytest.raises(NotImplementedError):
-        U.fill_depth(cases[0][0] / 1e3, extrapolate=True)
+    # the reference's optional branches: column extrapolation + 31x31 fill (exact max / copy operations before the blur) and the
+    # 5x5 Gaussian blur (float32 [1 4 6 4 1]/16 rows then columns; 2e-6 m covers OpenCV's SIMD summation order), vs the
+    # reference's own outputs on the two fixtures and vs the oracle on the full frame
+    for tag, ex, blur in (('ex', True, 'bilateral'), ('ga', False, 'gaussian'), ('exga', True, 'gaussian')):
+        refs = [g['out_m_%s_%s' % (k, tag)] for k in 'ab'] + [O.fill_depth(full / 1e3, 2.0, extrapolate=ex, blur_type=blur)]
+        for (din, _, _), ref in zip(cases, refs):
+            _, om = eng.fill_depth(torch.from_numpy(np.ascontiguousarray(din)).to(dev), want_metres=True, extrapolate=ex, blur_type=blur)
+            assert np.abs(om.cpu().numpy() - ref).max() < 2e-6, (tag, np.abs(om.cpu().numpy() - ref).max())
+    got = U.fill_depth(cases[0][0] / 1e3, extrapolate=True, blur_type='gaussian')
+    assert np.abs(got - g['out_m_a_exga']).max() < 2e-6
+    with pytest.raises(ValueError):
+        U.fill_depth(cases[0][0] / 1e3, blur_type='box')
     # a constant image passes through the bilateral untouched (OpenCV copies when max - min < eps) and nothing is invented
     # (800 mm comes back as 799: 2 - float32(0.8) and back is 0.79999995 -- the reference's own round trip)
     flat = np.full((32, 48), 800, dtype=np.uint16)

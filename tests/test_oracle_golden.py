@@ -181,6 +181,10 @@ def test_fill_depth_oracle_vs_reference(golden_dir):
         mm, m = O.fill_depth_mm(g['in_' + k])
         assert np.array_equal(m, g['out_m_' + k]) and np.array_equal(mm, g['out_mm_' + k])
         assert (g['in_' + k] == 0).mean() > 0.1 and (mm == 0).mean() < 0.02          # the holes are actually filled
+        # the optional branches (Utils.py:486-497 extrapolate, :506-510 gaussian), alone and together
+        for tag, ex, blur in (('ex', True, 'bilateral'), ('ga', False, 'gaussian'), ('exga', True, 'gaussian')):
+            assert np.array_equal(O.fill_depth(g['in_' + k] / 1e3, 2.0, extrapolate=ex, blur_type=blur), g['out_m_%s_%s' % (k, tag)])
+        assert not np.array_equal(g['out_m_%s_ex' % k], g['out_m_' + k]) and not np.array_equal(g['out_m_%s_ga' % k], g['out_m_' + k])
 
 
 def test_render_oracle_vs_ray_casting(synth):
