@@ -15,7 +15,7 @@ STAMP = os.path.join(HERE, 'libse3tn.stamp')
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 COMMON = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', '-I' + os.path.join(ROOT, 'include')]
 # aux_kernels.cu restates numpy/cv2 float arithmetic: no FMA contraction there.
-SOURCES = [('conv_umma2.cu', []), ('conv_direct.cu', []), ('aux_kernels.cu', ['-fmad=false']), ('metrics.cu', ['-fmad=false']), ('render.cu', ['-fmad=false']), ('depth_fill.cu', ['-fmad=false']), ('se3tn.cu', [])]
+SOURCES = [('conv_umma2.cu', []), ('conv_stem_t.cu', []), ('conv_direct.cu', []), ('aux_kernels.cu', ['-fmad=false']), ('metrics.cu', ['-fmad=false']), ('render.cu', ['-fmad=false']), ('depth_fill.cu', ['-fmad=false']), ('se3tn.cu', [])]
 
 
 def _nvcc():

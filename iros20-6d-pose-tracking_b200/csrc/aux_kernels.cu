@@ -55,20 +55,20 @@ __device__ __forceinline__ float depth_offset(unsigned d, double z1000, bool gl)
 //   * cv2's nearest-neighbour source index floor(dst * (1 / (176 / size))) for the 176 columns and this CTA's 44 rows.
 // The per-pixel work is then byte loads, table look-ups, the bf16 / tf32 packing and two 16-byte stores: ~3x fewer instructions
 // than dividing per pixel (ncu, round 2: the kernel was issue-bound at 274 instructions per pixel, DRAM at 7 %).
-constexpr int kPreRows = 44;                      // rows per CTA (4 CTAs per track)
+constexpr int kPreRowsMax = 44;                   // most rows one CTA handles (rows per CTA is a launch parameter: 44, 22 or 11)
 constexpr int kDepthLo = 101, kDepthN = 1899;     // valid raw depths 101..1999
 
 __global__ void __launch_bounds__(256, 4)
-preprocess_kernel(PreprocessArgs a)
+preprocess_kernel(PreprocessArgs a, int rows_per_cta)
 {
     ptx::grid_dep_launch();
     const int n = blockIdx.y;
-    const int row0 = blockIdx.x * kPreRows;
+    const int row0 = blockIdx.x * rows_per_cta;
     const double* pose = a.poses + n * 16;
     __shared__ float s_lut[6][256];
     __shared__ float s_dlut[2][kDepthN];
     __shared__ float s_dinv[2];                    // normalised value of an invalid depth (2000)
-    __shared__ short s_sx[kImg], s_sy[kPreRows];
+    __shared__ short s_sx[kImg], s_sy[kPreRowsMax];
     __shared__ int s_win[4];
     const int wi = a.weight_ids ? min(max(a.weight_ids[n], 0), a.stats_rows - 1) : 0;   // ids without statistics are rejected on the host where it can see them; never index past the table
     {
@@ -104,7 +104,7 @@ preprocess_kernel(PreprocessArgs a)
         const double ifx = (cw > 0) ? 1.0 / (static_cast<double>(kImg) / cw) : 0.0;
         const double ify = (ch > 0) ? 1.0 / (static_cast<double>(kImg) / ch) : 0.0;
         if (threadIdx.x < kImg) { int sx = static_cast<int>(floor(threadIdx.x * ifx)); if (sx > cw - 1) sx = cw - 1; s_sx[threadIdx.x] = static_cast<short>(sx); }
-        if (threadIdx.x >= 192 && threadIdx.x < 192 + kPreRows) {
+        if (threadIdx.x >= 192 && threadIdx.x < 192 + rows_per_cta) {
             const int y = row0 + threadIdx.x - 192;
             int sy = static_cast<int>(floor(y * ify)); if (sy > ch - 1) sy = ch - 1; s_sy[threadIdx.x - 192] = static_cast<short>(sy);
         }
@@ -117,45 +117,61 @@ preprocess_kernel(PreprocessArgs a)
         return j < static_cast<unsigned>(kDepthN) ? s_dlut[which][j] : s_dinv[which];
     };
     // consecutive threads take consecutive pixels: every load / store instruction of a warp touches 32 consecutive pixels
-    // (the 16-byte stem stores are 512 contiguous bytes per instruction)
-    for (int lp = threadIdx.x; lp < kPreRows * kImg; lp += blockDim.x) {
-        const int ly = lp / kImg, x = lp - ly * kImg;
-        const int y = row0 + ly;
-        const int pix = y * kImg + x;
-        const size_t ao = img0 + pix;
-        // ---- B: observed frame crop ------------------------------------------------------------------
-        unsigned rB = 0, gB = 0, bB = 0, dB = 0;
-        if (a.b_precropped) {
-            // frame_rgb / frame_depth already hold n 176x176 crops (TrackDataset.processData's inputs)
-            const uint8_t* pr = a.frame_rgb + ao * 3;
-            rB = pr[0]; gB = pr[1]; bB = pr[2];
-            dB = a.frame_depth[ao];
-        } else if (ch > 0 && cw > 0) {
-            const int fy_ = top + s_sy[ly], fx_ = left + s_sx[x];
-            if (fy_ >= 0 && fy_ < a.H && fx_ >= 0 && fx_ < a.W) {
-                const size_t fo = static_cast<size_t>(fy_) * a.W + fx_;
-                const uint8_t* pr = a.frame_rgb + fo * 3;
-                rB = pr[0]; gB = pr[1]; bB = pr[2];
-                dB = a.frame_depth[fo];
+    // (the 16-byte stem stores are 512 contiguous bytes per instruction); four pixels per thread and iteration so that four
+    // sets of byte loads are in flight at once (the loop is latency-bound otherwise)
+    const int npix = rows_per_cta * kImg;
+    for (int lp0 = threadIdx.x; lp0 < npix; lp0 += 4 * blockDim.x) {
+        unsigned rA[4], gA[4], bA[4], dA[4], rB[4], gB[4], bB[4], dB[4];
+        int pixs[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int lp = lp0 + u * blockDim.x;
+            rA[u] = gA[u] = bA[u] = dA[u] = rB[u] = gB[u] = bB[u] = dB[u] = 0; pixs[u] = -1;
+            if (lp >= npix) continue;
+            const int ly = lp / kImg, x = lp - ly * kImg;
+            const int pix = (row0 + ly) * kImg + x;
+            pixs[u] = pix;
+            const size_t ao = img0 + pix;
+            // ---- B: observed frame crop ------------------------------------------------------------------
+            if (a.b_precropped) {
+                // frame_rgb / frame_depth already hold n 176x176 crops (TrackDataset.processData's inputs)
+                const uint8_t* pr = a.frame_rgb + ao * 3;
+                rB[u] = pr[0]; gB[u] = pr[1]; bB[u] = pr[2];
+                dB[u] = a.frame_depth[ao];
+            } else if (ch > 0 && cw > 0) {
+                const int fy_ = top + s_sy[ly], fx_ = left + s_sx[x];
+                if (fy_ >= 0 && fy_ < a.H && fx_ >= 0 && fx_ < a.W) {
+                    const size_t fo = static_cast<size_t>(fy_) * a.W + fx_;
+                    const uint8_t* pr = a.frame_rgb + fo * 3;
+                    rB[u] = pr[0]; gB[u] = pr[1]; bB[u] = pr[2];
+                    dB[u] = a.frame_depth[fo];
+                }
             }
+            // ---- A: rendered previous view --------------------------------------------------------------
+            const uint8_t* pa = a.rgbA + ao * 3;
+            rA[u] = pa[0]; gA[u] = pa[1]; bA[u] = pa[2]; dA[u] = a.depthA[ao];
         }
-        if (a.crop_rgb) { uint8_t* o = a.crop_rgb + ao * 3; o[0] = static_cast<uint8_t>(rB); o[1] = static_cast<uint8_t>(gB); o[2] = static_cast<uint8_t>(bB); }
-        if (a.crop_depth) a.crop_depth[ao] = static_cast<uint16_t>(dB);
-        // ---- A: rendered previous view --------------------------------------------------------------
-        const uint8_t* pa = a.rgbA + ao * 3;
-        const unsigned rA = pa[0], gA = pa[1], bA = pa[2], dA = a.depthA[ao];
-        const float4 vA = make_float4(s_lut[0][rA], s_lut[1][gA], s_lut[2][bA], depth_norm(dA, 0));
-        const float4 vB = make_float4(s_lut[3][rB], s_lut[4][gB], s_lut[5][bB], depth_norm(dB, 1));
-        if (a.nchwA) {
-            float* oa = a.nchwA + static_cast<size_t>(n) * 4 * kImg * kImg + pix;
-            float* ob = a.nchwB + static_cast<size_t>(n) * 4 * kImg * kImg + pix;
-            oa[0] = vA.x; oa[kImg * kImg] = vA.y; oa[2 * kImg * kImg] = vA.z; oa[3 * kImg * kImg] = vA.w;
-            ob[0] = vB.x; ob[kImg * kImg] = vB.y; ob[2 * kImg * kImg] = vB.z; ob[3 * kImg * kImg] = vB.w;
-        }
-        if (a.stemA) {
-            const size_t so = (static_cast<size_t>(n) * kStemH + (y + 3)) * kStemW + (x + 3);
-            reinterpret_cast<float4*>(a.stemA)[so] = pack_stem_pixel(vA, a.round_tf32);
-            reinterpret_cast<float4*>(a.stemB)[so] = pack_stem_pixel(vB, a.round_tf32);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int pix = pixs[u];
+            if (pix < 0) continue;
+            const int y = pix / kImg, x = pix - y * kImg;
+            const size_t ao = img0 + pix;
+            if (a.crop_rgb) { uint8_t* o = a.crop_rgb + ao * 3; o[0] = static_cast<uint8_t>(rB[u]); o[1] = static_cast<uint8_t>(gB[u]); o[2] = static_cast<uint8_t>(bB[u]); }
+            if (a.crop_depth) a.crop_depth[ao] = static_cast<uint16_t>(dB[u]);
+            const float4 vA = make_float4(s_lut[0][rA[u]], s_lut[1][gA[u]], s_lut[2][bA[u]], depth_norm(dA[u], 0));
+            const float4 vB = make_float4(s_lut[3][rB[u]], s_lut[4][gB[u]], s_lut[5][bB[u]], depth_norm(dB[u], 1));
+            if (a.nchwA) {
+                float* oa = a.nchwA + static_cast<size_t>(n) * 4 * kImg * kImg + pix;
+                float* ob = a.nchwB + static_cast<size_t>(n) * 4 * kImg * kImg + pix;
+                oa[0] = vA.x; oa[kImg * kImg] = vA.y; oa[2 * kImg * kImg] = vA.z; oa[3 * kImg * kImg] = vA.w;
+                ob[0] = vB.x; ob[kImg * kImg] = vB.y; ob[2 * kImg * kImg] = vB.z; ob[3 * kImg * kImg] = vB.w;
+            }
+            if (a.stemA) {
+                const size_t so = (static_cast<size_t>(n) * kStemH + (y + 3)) * kStemW + (x + 3);
+                reinterpret_cast<float4*>(a.stemA)[so] = pack_stem_pixel(vA, a.round_tf32);
+                reinterpret_cast<float4*>(a.stemB)[so] = pack_stem_pixel(vB, a.round_tf32);
+            }
         }
     }
 }
@@ -173,9 +189,11 @@ static cudaError_t launch_pdl(const void* func, dim3 grid, dim3 block, void** ar
 
 cudaError_t launch_preprocess(const PreprocessArgs& a, int n, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
-    dim3 grid(kImg / kPreRows, n);
+    // rows per CTA: big strips amortise the per-CTA tables, small ones fill the machine when there are few tracks
+    int rows = n >= 32 ? 22 : 11;
+    dim3 grid(kImg / rows, n);
     PreprocessArgs aa = a;
-    void* args[] = {&aa};
+    void* args[] = {&aa, &rows};
     return launch_pdl(reinterpret_cast<const void*>(preprocess_kernel), grid, dim3(256), args, s);
 }
 

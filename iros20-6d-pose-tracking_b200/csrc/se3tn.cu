@@ -118,6 +118,7 @@ struct se3tn_ctx {
     CUtensorMap amap4[14][4];        // activation views, 4 bytes per channel (TF32 / BF16X3; also the stems' input in every mode)
     CUtensorMap amap2[14][4];        // activation views, 2 bytes per channel (PREC_BF16, layers 2..13)
     int pdl = 1;                     // SE3TN_PDL=0 disables programmatic dependent launch between the kernels of a step
+    int stem_ws = 0;                 // SE3TN_STEM_WS=1: weights-stationary stem (conv_stem_t.cu); higher bits = timing experiments (value >> 1: bit0 swapped bf16 packing, bit1 no pooling, bit2 no dump)
     std::map<int, MeshDev> meshes;   // CAD models of the rasteriser (device copies), keyed by mesh id
     MeshDev* d_meshes = nullptr; int mesh_rows = 0; bool meshes_dirty = false;
     uint8_t* render_proj = nullptr; uint8_t* render_unif = nullptr; int render_max_nv = 0, render_proj_nv = 0;   // rasteriser workspace
@@ -462,7 +463,10 @@ int run_network(se3tn_ctx* c, int weight_id, int first, int n, int precision,
         else { rp.step_x = rp.step_y = 11; rp.off_x = rp.off_y = 0; }
         rp.img_wid = img_wid; rp.gbmaps = gbmaps; rp.gbias = gbias;
         rp.trace = c->trace ? c->trace + static_cast<size_t>(li) * 256 * 8 : nullptr;
-        { ProfScope ps(c, li, s); CU_TRY(c, launch_conv_resident(rp, rp.L.kind, kprec, c->num_sms, c->pdl != 0, s)); }
+        if (kLayers[li].kind == K_STEM && c->stem_ws && !img_wid && kprec != PREC_TF32) {
+            ProfScope ps(c, li, s);
+            CU_TRY(c, launch_conv_stem_ws(rp, ws.dev_stack + static_cast<size_t>(li) * 128 * 288 * sizeof(float), kprec, c->stem_ws >> 1, c->num_sms, c->pdl != 0, s));
+        } else { ProfScope ps(c, li, s); CU_TRY(c, launch_conv_resident(rp, rp.L.kind, kprec, c->num_sms, c->pdl != 0, s)); }
         ++c->launches;
     }
     {
@@ -533,6 +537,7 @@ int se3tn_create(int device, int max_batch, void* workspace, se3tn_ctx** out) {
     c->device = device; c->max_batch = max_batch; c->num_sms = prop.multiProcessorCount;
     if (const char* ov = getenv("SE3TN_PDL")) c->pdl = atoi(ov) != 0;
     if (const char* ov = getenv("SE3TN_GRAPH")) c->use_graphs = atoi(ov) != 0;
+    if (const char* ov = getenv("SE3TN_STEM_WS")) c->stem_ws = atoi(ov);
     if (const char* ov = getenv("SE3TN_TRACE")) {
         if (atoi(ov) != 0 && cudaMalloc(&c->trace, SE3TN_TRACE_WORDS * sizeof(unsigned long long)) == cudaSuccess) cudaMemset(c->trace, 0, SE3TN_TRACE_WORDS * sizeof(unsigned long long));
     }

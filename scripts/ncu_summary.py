@@ -24,7 +24,7 @@ for r in data:
     for h, n in want:
         v = r[hdr.index(h)] if h in hdr else ''
         if h == 'Kernel Name':
-            v = v[v.find('conv_umma2_kernel'):].split('(se3tn')[0].replace('(int)', '').replace('(bool)', '')
+            v = v.split('(se3tn')[0].split('(const')[0].replace('(int)', '').replace('(bool)', '').replace('void ', '').replace('se3tn::', '').replace('<unnamed>::', '')
         else:
             try: v = '%.2f' % float(v)
             except ValueError: pass
@@ -34,7 +34,7 @@ for r in data:
 n = len(data)
 lines += ['', '%d launches: time %.1f us, dram read %.1f MB + write %.1f MB -> %.1f MB per launch on average' % (n, tot_t, tot_r, tot_w, (tot_r + tot_w) / max(n, 1))]
 open(out_txt, 'w').write('\n'.join(lines) + '\n')
-json.dump({'kernel': 'conv_umma2_kernel (average over the %d conv launches of one step)' % n, 'launches': n,
+json.dump({'kernel': 'conv_resident_kernel x8 + conv_trunk_kernel x1 (average over the %d conv launches of one step)' % n, 'launches': n,
            'dram_bytes_per_launch': (tot_r + tot_w) * 1e6 / max(n, 1), 'dram_read_MB_total': tot_r, 'dram_write_MB_total': tot_w,
            'source': out_txt, 'note': note}, open(out_json, 'w'), indent=1)
 print('\n'.join(lines[-3:]))
