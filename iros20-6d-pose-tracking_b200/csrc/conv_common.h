@@ -123,7 +123,7 @@ struct ResidentParams {
 cudaError_t launch_conv_resident(const ResidentParams& p, int kind, int prec, int num_sms, bool pdl, cudaStream_t stream);
 cudaError_t launch_conv_trunk(const TrunkParams& p, int prec, int block_n /*256 | 128*/, int num_sms, bool pdl, cudaStream_t stream);
 // weights-stationary stem (conv_stem_t.cu): bf16 modes, single weight set; wstack = the stem's stacked weight matrix [128][224 words]
-cudaError_t launch_conv_stem_ws(const ResidentParams& p, const void* wstack, int prec, int swap_pack, int num_sms, bool pdl, cudaStream_t stream);
+cudaError_t launch_conv_stem_ws(const ResidentParams& p, const void* wstack, int prec, int debug_flags, int num_sms, bool pdl, cudaStream_t stream);
 // 32-bit words of scheduler state a trunk launch needs (next-unit counter + done[layers][max_batch])
 inline size_t trunk_sched_words(int max_batch) { return 1 + static_cast<size_t>(kTrunkMaxLayers) * max_batch; }
 

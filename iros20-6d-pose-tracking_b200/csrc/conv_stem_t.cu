@@ -10,11 +10,14 @@
 //     TENSOR MEMORY (tcgen05.st, 224 columns) and read from there by every MMA (tcgen05.mma with [a_tmem]);
 //   * B operand = the activation unit tile in shared memory exactly as before (K-major, SWIZZLE_128B, the 7 filter rows as
 //     row shifts of two TMA units), now the N = 128 side: 4 KB of shared-memory reads per MMA instead of 8.
-//   * the accumulator holds one OUTPUT CHANNEL per TMEM lane and the 11 x 11 conv positions along the columns, so MaxPool2d is
-//     register arithmetic inside a thread (no staging tile); only the lo-row partial sums (lanes 64-127: a_hi * w_lo) cross
-//     to their hi-row partners (lanes 0-63) through a 32 KB shared-memory exchange.
-// Shared-memory traffic per tile: 28 x 4 KB + 2 x 32 KB = 176 KB (was 224 + 90 = 314 KB) -> the 28 MMAs run at their 64-cycle floor.
-// TMEM: 2 x 128 accumulator columns + 224 weight columns = 480 of 512.
+//   * the accumulator holds one stacked weight ROW per TMEM lane and the 11 x 11 conv positions along the columns, so
+//     MaxPool2d is register arithmetic inside a thread (no staging tile).  The rows are ordered so that the hi-stack and the
+//     lo-stack row of a channel sit 16 lanes apart in the SAME warp (lane l of quadrant q: channel 16q + l % 16, stack l / 16):
+//     the two partial sums meet through one __shfl_xor per value, and the pair splits the pooling work -- the low lane takes
+//     pooled columns 0..2, the high lane the mirrored columns 4..2 -- with identical code (no divergence, no shared memory,
+//     no block barrier in the epilogue).
+// Shared-memory traffic per tile: 28 x 4 KB = 112 KB (was 224 + 90 = 314 KB).  TMEM: 2 x 128 accumulator columns + 224
+// weight columns = 480 of 512.
 #include "conv_common.h"
 #include "ptx.cuh"
 #include <cuda_bf16.h>
@@ -23,12 +26,10 @@
 namespace se3tn {
 namespace {
 
-constexpr int kThreadsS = 384;                 // warps: 0 A-TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue
+constexpr int kThreadsS = 512;                 // warps: 0 A-TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..15 epilogue (three per TMEM lane quadrant)
 constexpr int kAUnitS = 21 * 1024;             // (33 + 128) rows * 128 B
-constexpr int kStagesS = 6;
-constexpr int kXPitch = 129;                   // words per channel row of the exchange buffer (odd: conflict-free across lanes)
-constexpr int kXBytes = ((64 * kXPitch * 4 + 1023) / 1024) * 1024;
-constexpr int kSmemS = kStagesS * kAUnitS + 2 * kXBytes + 1024 + 512;
+constexpr int kStagesS = 8;
+constexpr int kSmemS = kStagesS * kAUnitS + 1024 + 512;
 static_assert(kSmemS <= 232448, "shared memory budget");
 constexpr uint32_t kDescHiS = (1024u >> 4) | (1u << 14) | (2u << 29);
 constexpr int kWCol = 256;                     // first TMEM column of the weights
@@ -62,70 +63,76 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
         ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-// The hi-row half of the epilogue for one tile.  This thread owns output channel c (TMEM lane) at the conv positions of
-//   HALF 0: conv rows 0..6  (pooled rows 0..2) = tile positions 0..76,   read as accumulator columns [0, 80)
-//   HALF 1: conv rows 6..10 (pooled rows 3..4) = tile positions 66..120, read as accumulator columns [64, 128)
-// adds the lo-row partial sums from the exchange buffer, masks positions outside the 88 x 88 conv output (MaxPool2d's -inf
-// padding), pools 3x3 / stride 2 in registers, + bias, SELU (monotone: max first), and stores channel c of each pooled pixel
-// (a warp = 32 consecutive channels = 64 contiguous bytes per store instruction).
-template <int HALF, int PREC>
-__device__ __forceinline__ void pool_tile(const LayerDesc& L, const ResidentParams& p, uint32_t taddr, const float* X, int c, float bias,
+// The epilogue of one tile for one warp.  TMEM lane = (channel ch, stack): lanes l and l ^ 16 of a warp hold the hi-stack
+// (a_hi*w_hi + a_lo*w_hi) and lo-stack (a_hi*w_lo) partial sums of the same channel.  The three warps of a lane quadrant
+// split the conv rows:
+//   PART 0: rows 0..4  (pooled rows 0, 1), accumulator columns [0, 64)
+//   PART 1: rows 4..8  (pooled rows 2, 3), accumulator columns [32, 112)
+//   PART 2: rows 8..10 (pooled row 4),     accumulator columns [80, 128)
+// and within a pair the low lane (grp 0) works on conv columns 0..6 (pooled columns 0, 1, 2), the high lane (grp 1) on the
+// mirrored columns 10..4 (pooled columns 4, 3, 2): register (row, j) means column j for grp 0 and 10 - j for grp 1, so both
+// run the same instructions.  Per value: select what the partner needs, one shuffle, one add; then -inf for positions outside
+// the 88 x 88 conv output (MaxPool2d's padding), 3x3 / stride 2 max in registers, + bias, SELU (monotone: max first), store.
+template <int PART, int PREC>
+__device__ __forceinline__ void pool_tile(const LayerDesc& L, const ResidentParams& p, uint32_t taddr, int ch, int grp, float bias,
                                           int n0, int ty, int tx, int lane, uint64_t* tmem_empty_bar)
 {
-    constexpr int kCol0 = HALF ? 64 : 0, kCols = HALF ? 64 : 80;
-    constexpr int kRow0 = HALF ? 6 : 0, kRows = HALF ? 5 : 7;
-    constexpr int kPr0 = HALF ? 3 : 0, kPr = HALF ? 2 : 3;
-    float v[kCols];
+    constexpr int kCol0 = PART == 0 ? 0 : (PART == 1 ? 32 : 80), kCols = PART == 0 ? 64 : (PART == 1 ? 80 : 48);
+    constexpr int kRow0 = PART * 4, kRows = PART == 2 ? 3 : 5;
+    constexpr int kPr0 = PART * 2, kPr = PART == 2 ? 1 : 2;
+    float own[kCols];
+    {
+        uint32_t t16[kCols / 16][16];
 #pragma unroll
-    for (int c0 = 0; c0 < kCols; c0 += 16) {
-        uint32_t t16[16];
-        ptx::tmem_ld16(taddr + kCol0 + c0, t16);
+        for (int c0 = 0; c0 < kCols; c0 += 16) ptx::tmem_ld16(taddr + kCol0 + c0, t16[c0 / 16]);      // all loads in flight, one wait
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[c0 + j] = __uint_as_float(t16[j]);
+        for (int c0 = 0; c0 < kCols; c0 += 16)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) own[c0 + j] = __uint_as_float(t16[c0 / 16][j]);
     }
     ptx::tc_fence_before();
     __syncwarp();
     if (lane == 0) ptx::mbar_arrive(tmem_empty_bar);                   // accumulator is in registers
-    asm volatile("bar.sync 1, 256;" ::: "memory");                     // the lo-row partial sums of this tile are in X
-    const float* xr = X + c * kXPitch + kCol0;
     // conv coordinates of tile position (lr, lc): (10*ty - 1 + lr, 10*tx - 1 + lc)
     const int cy0 = ty * p.step_y + p.off_y, cx0 = tx * p.step_x + p.off_x;
+    float sum[kRows][7];
 #pragma unroll
-    for (int lr = kRow0; lr < kRow0 + kRows; ++lr) {
-        const bool rv = static_cast<unsigned>(cy0 + lr) < 88u;
+    for (int r = 0; r < kRows; ++r) {
+        const bool rv = static_cast<unsigned>(cy0 + kRow0 + r) < 88u;
 #pragma unroll
-        for (int lc = 0; lc < 11; ++lc) {
-            constexpr int dummy = 0; (void)dummy;
-            const int k = lr * 11 + lc - kCol0;                         // compile-time after unrolling
-            const bool ok = rv && static_cast<unsigned>(cx0 + lc) < 88u;
-            const float val = v[k] + xr[k];
-            v[k] = ok ? val : kNegInf;
+        for (int j = 0; j < 7; ++j) {
+            const float a = own[(kRow0 + r) * 11 + j - kCol0], b = own[(kRow0 + r) * 11 + (10 - j) - kCol0];
+            const float mine = grp ? b : a;
+            const float recv = __shfl_xor_sync(0xffffffffu, grp ? a : b, 16);      // the partner stack's sum at MY position
+            const bool ok = rv && static_cast<unsigned>(cx0 + (grp ? 10 - j : j)) < 88u;
+            sum[r][j] = ok ? mine + recv : kNegInf;
         }
     }
+    const int c = L.out_coff + ch;
+    uint8_t* const obase = L.out + (PREC == PREC_BF16X3 ? static_cast<size_t>(c & ~31) * 4 + (c & 31) * 2 : static_cast<size_t>(c) * 2);
+    const size_t pix_bytes = static_cast<size_t>(L.out_c) * (PREC == PREC_BF16X3 ? 4 : 2);
 #pragma unroll
-    for (int pr = kPr0; pr < kPr0 + kPr; ++pr) {
-        const int oy = ty * 5 + pr;
+    for (int pr = 0; pr < kPr; ++pr) {
+        const int oy = ty * 5 + kPr0 + pr;
 #pragma unroll
-        for (int px = 0; px < 5; ++px) {
+        for (int jx = 0; jx < 3; ++jx) {
+            const int ox = tx * 5 + (grp ? 4 - jx : jx);
+            if (oy >= L.Ho || ox >= L.Wo || (grp && jx == 2)) continue;         // pooled column 2 is the low lane's
             float m = kNegInf;
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-                for (int dx = 0; dx < 3; ++dx) m = fmaxf(m, v[(2 * pr + dy) * 11 + 2 * px + dx - kCol0]);
-            const int ox = tx * 5 + px;
-            if (oy >= L.Ho || ox >= L.Wo) continue;
+                for (int dx = 0; dx < 3; ++dx) m = fmaxf(m, sum[2 * (kPr0 + pr) + dy - kRow0][2 * jx + dx]);
             const float o = selu_s(m + bias);
-            const size_t pix = (static_cast<size_t>(n0) * L.Ho + oy) * L.Wo + ox;
-            const int ch = L.out_coff + c;
+            uint8_t* po = obase + ((static_cast<size_t>(n0) * L.Ho + oy) * L.Wo + ox) * pix_bytes;
             if (PREC == PREC_BF16X3) {
                 const __nv_bfloat16 h = __float2bfloat16_rn(o);
                 const __nv_bfloat16 l = __float2bfloat16_rn(o - __bfloat162float(h));
-                uint8_t* po = L.out + (pix * L.out_c + (ch & ~31)) * 4 + (ch & 31) * 2;
                 *reinterpret_cast<__nv_bfloat16*>(po) = h;
                 *reinterpret_cast<__nv_bfloat16*>(po + 64) = l;
             } else {
-                *reinterpret_cast<__nv_bfloat16*>(L.out + (pix * L.out_c + ch) * 2) = __float2bfloat16_rn(o);
+                *reinterpret_cast<__nv_bfloat16*>(po) = __float2bfloat16_rn(o);
             }
         }
     }
@@ -134,14 +141,13 @@ __device__ __forceinline__ void pool_tile(const LayerDesc& L, const ResidentPara
 // PREC_BF16X3: output [32 hi | 32 lo] chunks; PREC_BF16: plain bf16
 template <int PREC>
 __global__ void __launch_bounds__(kThreadsS, 1)
-conv_stem_ws_kernel(const __grid_constant__ ResidentParams p, const uint32_t* __restrict__ wstack /*[128][224 words]*/, int swap_pack)
+conv_stem_ws_kernel(const __grid_constant__ ResidentParams p, const uint32_t* __restrict__ wstack /*[128][224 words]*/, int debug_flags)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const LayerDesc& L = p.L;
     uint8_t* sA = smem;                                                 // [kStagesS][unit]
-    float* sX = reinterpret_cast<float*>(sA + kStagesS * kAUnitS);      // [2][64 channels][kXPitch]: lo-row partial sums
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sX) + 2 * kXBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sA + kStagesS * kAUnitS);
     uint64_t* a_full = bars;                       // [kStagesS]
     uint64_t* a_empty = a_full + kStagesS;         // [kStagesS]
     uint64_t* tmem_full = a_empty + kStagesS;      // [2]
@@ -158,7 +164,7 @@ conv_stem_ws_kernel(const __grid_constant__ ResidentParams p, const uint32_t* __
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStagesS; ++s) { ptx::mbar_init(&a_full[s], 1); ptx::mbar_init(&a_empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], 8); }
+        for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], 12); }
         ptx::mbar_init(&w_ready[0], 4);
         ptx::fence_barrier_init();
         ptx::fence_proxy_async();
@@ -228,13 +234,14 @@ conv_stem_ws_kernel(const __grid_constant__ ResidentParams p, const uint32_t* __
             __syncwarp();
         }
     } else if (warp >= 4) {
-        // ============================== epilogue (8 warps) ==========================
+        // ============================== epilogue (12 warps) ==========================
         const int ew = warp - 4;
-        const int q = ew & 3;                       // TMEM lane quadrant: 0,1 = hi rows (channels 32q + lane), 2,3 = lo rows
-        const int half = ew >> 2;                   // 0: conv rows 0..6 / columns [0,64) ; 1: conv rows 6..10 / columns [64,128)
+        const int q = ew & 3;                       // TMEM lane quadrant: channels 16q .. 16q + 15, hi stack in lanes 0-15, lo stack in lanes 16-31
+        const int part = ew >> 2;                   // which conv rows of the tile (pool_tile)
+        const int grp = lane >> 4, ch = q * 16 + (lane & 15);
         if (ew < 4) {
-            // ---- weights -> tensor memory: thread = one stacked row, 7 filter rows x 32 columns ----
-            const uint32_t* wrow = wstack + static_cast<size_t>(q * 32 + lane) * 224;
+            // ---- weights -> tensor memory: this thread's lane holds row (stack grp, channel ch) of [w_hi|w_hi ; w_lo|0]: 7 filter rows x 32 columns
+            const uint32_t* wrow = wstack + static_cast<size_t>(grp * 64 + ch) * 224;
 #pragma unroll 1
             for (int tap = 0; tap < 7; ++tap) {
                 uint32_t r[32];
@@ -243,10 +250,6 @@ conv_stem_ws_kernel(const __grid_constant__ ResidentParams p, const uint32_t* __
                     const uint4 v = __ldg(reinterpret_cast<const uint4*>(wrow + tap * 32 + j));
                     r[j] = v.x; r[j + 1] = v.y; r[j + 2] = v.z; r[j + 3] = v.w;
                 }
-                if (swap_pack & 1) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) r[j] = __byte_perm(r[j], 0, 0x1032);
-                }
                 tmem_st32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + kWCol + tap * 32, r);
             }
             tmem_st_wait();
@@ -254,51 +257,25 @@ conv_stem_ws_kernel(const __grid_constant__ ResidentParams p, const uint32_t* __
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&w_ready[0]);
         }
-        ptx::grid_dep_wait();                       // output buffers are read by the previous step's kernels
-        const bool pooler = q < 2;
-        const int c = (q & 1) * 32 + lane;          // output channel of this thread
-        const float bias = __ldg(L.bias + c);
+        ptx::grid_dep_wait();                       // the output buffers are still read by the previous step's kernels
+        const float bias = __ldg(L.bias + ch);
         int it = 0;
         for (int tile = w_begin; tile < w_end; ++tile, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const int n0 = p.img_first + tile / tiles_img, r = tile % tiles_img;
             const int ty = r / L.tiles_x, tx = r - ty * L.tiles_x;
-            float* X = sX + (it & 1) * (kXBytes / 4);
             ptx::mbar_wait(&tmem_full[acc], acc_phase);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 128;
-            if (!pooler && (swap_pack & 4)) {         // timing experiment: no dump either
+            if (debug_flags & 1) {                    // timing experiment: free the accumulator, no pooling (results are garbage)
                 ptx::tc_fence_before(); __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
-                asm volatile("bar.sync 1, 256;" ::: "memory");
                 continue;
             }
-            if (!pooler) {
-                // ---- lo rows: a_hi * w_lo partial sums of channel c, columns [64*half, 64*half + 64) -> exchange buffer ----
-                float* xr = X + c * kXPitch + half * 64;
-#pragma unroll
-                for (int c0 = 0; c0 < 64; c0 += 16) {
-                    uint32_t v[16];
-                    ptx::tmem_ld16(taddr + half * 64 + c0, v);
-                    ptx::tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) xr[c0 + j] = __uint_as_float(v[j]);
-                }
-                ptx::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
-                asm volatile("bar.sync 1, 256;" ::: "memory");             // exchange buffer complete
-                continue;
-            }
-            if (swap_pack & 2) {                      // timing experiment: free the accumulator, no pooling (results are garbage)
-                ptx::tc_fence_before(); __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                continue;
-            }
-            if (half == 0) pool_tile<0, PREC>(L, p, taddr, X, c, bias, n0, ty, tx, lane, &tmem_empty[acc]);
-            else           pool_tile<1, PREC>(L, p, taddr, X, c, bias, n0, ty, tx, lane, &tmem_empty[acc]);
+            if (part == 0)      pool_tile<0, PREC>(L, p, taddr, ch, grp, bias, n0, ty, tx, lane, &tmem_empty[acc]);
+            else if (part == 1) pool_tile<1, PREC>(L, p, taddr, ch, grp, bias, n0, ty, tx, lane, &tmem_empty[acc]);
+            else                pool_tile<2, PREC>(L, p, taddr, ch, grp, bias, n0, ty, tx, lane, &tmem_empty[acc]);
         }
     }
 
@@ -311,7 +288,7 @@ conv_stem_ws_kernel(const __grid_constant__ ResidentParams p, const uint32_t* __
 }
 
 template <int PREC>
-cudaError_t launch_stem_ws_t(const ResidentParams& p, const uint32_t* wstack, int swap_pack, int num_sms, bool pdl, cudaStream_t stream) {
+cudaError_t launch_stem_ws_t(const ResidentParams& p, const uint32_t* wstack, int debug_flags, int num_sms, bool pdl, cudaStream_t stream) {
     if (p.L.kind != KIND_STEM || p.img_wid || p.m_tiles <= 0 || !wstack) return cudaErrorInvalidValue;
     static size_t attr[64] = {};
     int dev = 0;
@@ -326,14 +303,14 @@ cudaError_t launch_stem_ws_t(const ResidentParams& p, const uint32_t* wstack, in
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, conv_stem_ws_kernel<PREC>, p, wstack, swap_pack);
+    return cudaLaunchKernelEx(&cfg, conv_stem_ws_kernel<PREC>, p, wstack, debug_flags);
 }
 
 }  // namespace
 
-cudaError_t launch_conv_stem_ws(const ResidentParams& p, const void* wstack, int prec, int swap_pack, int num_sms, bool pdl, cudaStream_t stream) {
-    if (prec == PREC_BF16X3) return launch_stem_ws_t<PREC_BF16X3>(p, static_cast<const uint32_t*>(wstack), swap_pack, num_sms, pdl, stream);
-    if (prec == PREC_BF16) return launch_stem_ws_t<PREC_BF16>(p, static_cast<const uint32_t*>(wstack), swap_pack, num_sms, pdl, stream);
+cudaError_t launch_conv_stem_ws(const ResidentParams& p, const void* wstack, int prec, int debug_flags, int num_sms, bool pdl, cudaStream_t stream) {
+    if (prec == PREC_BF16X3) return launch_stem_ws_t<PREC_BF16X3>(p, static_cast<const uint32_t*>(wstack), debug_flags, num_sms, pdl, stream);
+    if (prec == PREC_BF16) return launch_stem_ws_t<PREC_BF16>(p, static_cast<const uint32_t*>(wstack), debug_flags, num_sms, pdl, stream);
     return cudaErrorInvalidValue;
 }
 

@@ -118,7 +118,7 @@ struct se3tn_ctx {
     CUtensorMap amap4[14][4];        // activation views, 4 bytes per channel (TF32 / BF16X3; also the stems' input in every mode)
     CUtensorMap amap2[14][4];        // activation views, 2 bytes per channel (PREC_BF16, layers 2..13)
     int pdl = 1;                     // SE3TN_PDL=0 disables programmatic dependent launch between the kernels of a step
-    int stem_ws = 0;                 // SE3TN_STEM_WS=1: weights-stationary stem (conv_stem_t.cu); higher bits = timing experiments (value >> 1: bit0 swapped bf16 packing, bit1 no pooling, bit2 no dump)
+    int stem_ws = 0;                 // SE3TN_STEM_WS=1: weights-stationary stem (conv_stem_t.cu); 3 = timing experiment without the pooling epilogue
     std::map<int, MeshDev> meshes;   // CAD models of the rasteriser (device copies), keyed by mesh id
     MeshDev* d_meshes = nullptr; int mesh_rows = 0; bool meshes_dirty = false;
     uint8_t* render_proj = nullptr; uint8_t* render_unif = nullptr; int render_max_nv = 0, render_proj_nv = 0;   // rasteriser workspace
@@ -143,6 +143,7 @@ struct se3tn_ctx {
     bool last_was_graph = false;
     struct StepGraph { std::vector<unsigned long long> key; cudaGraphExec_t exec; int launches; unsigned long long last_use; };
     std::vector<StepGraph> graphs; unsigned long long graph_clock = 0;
+    cudaStream_t cap_stream = nullptr;   // steps are captured on this private stream (the caller's may be the legacy default stream, which cannot be captured) and replayed on the caller's
     cudaEvent_t ev0[SE3TN_PROFILE_SLOTS] = {}, ev1[SE3TN_PROFILE_SLOTS] = {};
     bool ev_used[SE3TN_PROFILE_SLOTS] = {};
     std::string err;
@@ -586,6 +587,7 @@ void se3tn_destroy(se3tn_ctx* c) {
     cudaFree(c->d_bmaps_tf32); cudaFree(c->d_bmaps_bf16); cudaFree(c->d_bmaps_x3); cudaFree(c->d_bias); cudaFree(c->d_fc);
     for (int i = 0; i < SE3TN_PROFILE_SLOTS; ++i) { if (c->ev0[i]) cudaEventDestroy(c->ev0[i]); if (c->ev1[i]) cudaEventDestroy(c->ev1[i]); }
     drop_graphs(c);
+    if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
     cudaFree(c->sched); cudaFree(c->pool_part); cudaFree(c->trace);
     for (auto& kv : c->meshes) { cudaFree(const_cast<float*>(kv.second.pos)); cudaFree(const_cast<float*>(kv.second.nrm)); cudaFree(const_cast<uint8_t*>(kv.second.col)); cudaFree(const_cast<int*>(kv.second.faces)); }
     cudaFree(c->d_meshes); cudaFree(c->render_proj); cudaFree(c->render_unif);
@@ -842,7 +844,7 @@ int se3tn_track_batch(se3tn_ctx* c, const uint8_t* frame_rgb, const uint16_t* fr
     c->last_was_graph = false;
     if (graphable) {
         auto bits = [](double d) { unsigned long long u; memcpy(&u, &d, 8); return u; };
-        const void* ptrs[] = {frame_rgb, frame_depth, poses_in, object_width, rgbA, depthA, weight_ids_dev, out_trans, out_rot, poses_out, s};
+        const void* ptrs[] = {frame_rgb, frame_depth, poses_in, object_width, rgbA, depthA, weight_ids_dev, out_trans, out_rot, poses_out};
         for (const void* p : ptrs) key.push_back(reinterpret_cast<unsigned long long>(p));
         key.push_back(static_cast<unsigned long long>(H)); key.push_back(static_cast<unsigned long long>(W));
         key.push_back(static_cast<unsigned long long>(n)); key.push_back(static_cast<unsigned long long>(precision));
@@ -859,13 +861,14 @@ int se3tn_track_batch(se3tn_ctx* c, const uint8_t* frame_rgb, const uint16_t* fr
         int rc0 = sync_stats(c, s); if (rc0) return rc0;
         if (multi) { rc0 = sync_tables(c, s); if (rc0) return rc0; }
         if (c->sched_dirty) { CU_TRY(c, cudaMemsetAsync(c->sched, 0, trunk_sched_words(c->max_batch) * sizeof(unsigned), s)); c->sched_dirty = false; }
-        if (cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); key.clear(); }
+        if (!c->cap_stream && cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); c->cap_stream = nullptr; c->use_graphs = 0; key.clear(); }
+        if (!key.empty() && cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); c->use_graphs = 0; key.clear(); }
     }
     const bool capturing = graphable && !key.empty();
     auto end_capture = [&](int rc_launch) -> int {
         // turn what was recorded into an executable graph and run it; any failure falls back to plain stream launches for good
         cudaGraph_t graph = nullptr;
-        cudaError_t e = cudaStreamEndCapture(s, &graph);
+        cudaError_t e = cudaStreamEndCapture(c->cap_stream, &graph);
         if (rc_launch != SE3TN_OK || e != cudaSuccess || !graph) {
             if (graph) cudaGraphDestroy(graph);
             cudaGetLastError(); c->use_graphs = 0; c->sched_dirty = true;
@@ -887,7 +890,7 @@ int se3tn_track_batch(se3tn_ctx* c, const uint8_t* frame_rgb, const uint16_t* fr
     };
     if (capturing) {
         const int rc = track_batch_launches(c, frame_rgb, frame_depth, H, W, K, poses_in, object_width, rgbA, depthA, weight_ids_host, weight_ids_dev, n,
-                                            tn, rn, precision, out_trans, out_rot, poses_out, multi, s);
+                                            tn, rn, precision, out_trans, out_rot, poses_out, multi, c->cap_stream);
         const int grc = end_capture(rc);
         if (grc == SE3TN_OK) return SE3TN_OK;
         if (grc != 1) return grc;                              // a real launch error

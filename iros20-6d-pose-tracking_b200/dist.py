@@ -90,6 +90,12 @@ class ShardedTracker:
         self.overlap_gather = bool(overlap_gather) and world_size > 1
         self._comm_stream = torch.cuda.Stream(device=dev) if self.overlap_gather else None
         self._gather_done = None
+        # two rotating sets of output tensors: stable device addresses keep the step's CUDA graph key stable (libse3tn replays one
+        # graph per distinct set of pointers); a returned pose tensor stays valid until the step after the next one
+        n = len(self.mine)
+        self._outs = [(torch.empty(n, 4, 4, dtype=torch.float64, device=dev), torch.empty(n, 3, dtype=torch.float32, device=dev),
+                       torch.empty(n, 3, dtype=torch.float32, device=dev)) for _ in range(2)]
+        self._flip = 0
 
     def wait_gather(self):
         """Make the current stream wait for the last overlapped all-gather (no-op when none is pending)."""
@@ -99,10 +105,12 @@ class ShardedTracker:
 
     def step(self, frame_rgb, frame_depth, local_poses, local_rgbA, local_depthA, gather=True):
         self.wait_gather()
+        self._flip ^= 1
+        o = self._outs[self._flip]
         out, _, _ = self.engine.track_batch(frame_rgb, frame_depth, self.K, local_poses, self.local_ow,
                                             local_rgbA, local_depthA, self.tn, self.rn,
                                             weight_ids_host=self.local_wids_host, weight_ids_dev=self.local_wids_dev,
-                                            precision=self.precision)
+                                            precision=self.precision, out_poses=o[0], out_trans=o[1], out_rot=o[2])
         if not gather:
             return out, None
         if not self.overlap_gather:
@@ -113,6 +121,5 @@ class ShardedTracker:
         with torch.cuda.stream(self._comm_stream):
             gathered = all_gather_poses(out, self.shards, self.rank, self.world_size)
             self._gather_done = torch.cuda.Event(); self._gather_done.record(self._comm_stream)
-        out.record_stream(self._comm_stream)       # allocator: `out` is still being read over there
         gathered.record_stream(cur)                # ... and `gathered` will be read here after wait_gather()
         return out, gathered

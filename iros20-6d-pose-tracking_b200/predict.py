@@ -149,6 +149,7 @@ class Tracker:
                     raise
                 renderer = None                                    # e.g. a vertices-only ply: fall through to the GL renderers
         self.renderer = renderer if renderer is not None else self._try_reference_renderer(model_path, cam_cfg)
+        self._np_bufs = {}
         self.prev_rgb = None
         self.prev_depth = None
         self.frame_cnt = 0
@@ -233,23 +234,38 @@ class Tracker:
             raise RuntimeError('on_track_batch without rgbA/depthA needs the CUDA renderer (Tracker(renderer="cuda", model_path=*.ply))')
         staged = not render and all(torch.is_tensor(x) and not x.is_cuda for x in (prev_poses, current_rgb, current_depth, rgbA, depthA))
 
-        def up(x, dt):
+        def up(x, dt, slot=None):
             if torch.is_tensor(x):
                 return x.to(dev, dt).contiguous()
             a = np.ascontiguousarray(x)
             if dt == torch.uint16 and a.dtype != np.uint16:
                 a = a.astype(np.uint16)
-            return torch.from_numpy(a).to(dev).to(dt)
+            src = torch.from_numpy(a)
+            if slot is None:
+                return src.to(dev).to(dt)
+            # numpy inputs land in persistent device buffers (one per argument and shape): the step's CUDA graph is keyed by its
+            # device pointers, so stable addresses mean every frame after the first is one graph launch
+            key = (slot, tuple(a.shape), dt)
+            buf = self._np_bufs.get(key)
+            if buf is None:
+                buf = self._np_bufs[key] = torch.empty(a.shape, dtype=dt, device=dev)
+            buf.copy_(src if src.dtype == dt else src.to(dt))
+            return buf
 
         if staged:
             poses, rgb_d, depth_d, rgbA_d, depthA_d = self._stage_uploads(prev_poses, current_rgb, current_depth, rgbA, depthA)
         else:
-            poses = up(prev_poses, torch.float64)
-            rgb_d, depth_d = up(current_rgb, torch.uint8), up(current_depth, torch.uint16)
+            poses = up(prev_poses, torch.float64, 'poses')
+            rgb_d, depth_d = up(current_rgb, torch.uint8, 'rgb'), up(current_depth, torch.uint16, 'depth')
             if not render:
-                rgbA_d, depthA_d = up(rgbA, torch.uint8), up(depthA, torch.uint16)
+                rgbA_d, depthA_d = up(rgbA, torch.uint8, 'rgbA'), up(depthA, torch.uint16, 'depthA')
         n = poses.shape[0]
-        ow = torch.full((n,), float(self.object_width), dtype=torch.float64, device=dev) if object_width is None else up(object_width, torch.float64)
+        if object_width is None:
+            ow = self._np_bufs.get(('ow', n))
+            if ow is None:
+                ow = self._np_bufs[('ow', n)] = torch.full((n,), float(self.object_width), dtype=torch.float64, device=dev)
+        else:
+            ow = up(object_width, torch.float64, 'ow_arg')
         if render:
             mids = None
             if weight_ids is not None:
@@ -260,9 +276,22 @@ class Tracker:
             wh = np.ascontiguousarray(weight_ids.cpu().numpy() if torch.is_tensor(weight_ids) else weight_ids, dtype=np.int32)
         elif self.weight_id != 0:
             wh = np.full(n, self.weight_id, dtype=np.int32)
+        outs = {}
+        if as_numpy:                                  # results go back to the host: persistent output buffers keep the graph key stable too
+            ob = self._np_bufs.get(('out', n))
+            if ob is None:
+                ob = self._np_bufs[('out', n)] = (torch.empty(n, 4, 4, dtype=torch.float64, device=dev),
+                                                  torch.empty(n, 3, dtype=torch.float32, device=dev), torch.empty(n, 3, dtype=torch.float32, device=dev))
+            outs = dict(out_poses=ob[0], out_trans=ob[1], out_rot=ob[2])
+        wd = None
+        if wh is not None:                            # device copy of the ids, cached by value
+            wk = ('wids', wh.tobytes())
+            wd = self._np_bufs.get(wk)
+            if wd is None:
+                wd = self._np_bufs[wk] = torch.from_numpy(wh).to(dev)
         out, _, _ = self.engine.track_batch(rgb_d, depth_d, self.K, poses, ow, rgbA_d, depthA_d,
                                             self.trans_normalizer, self.rot_normalizer,
-                                            weight_ids_host=wh, precision=self.precision)
+                                            weight_ids_host=wh, weight_ids_dev=wd, precision=self.precision, **outs)
         if staged:
             self._stage_done[self._stage_slot].record(torch.cuda.current_stream(dev))
         return out.cpu().numpy() if as_numpy else out

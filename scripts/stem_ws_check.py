@@ -14,7 +14,7 @@ def decode(buf, n):      # P1 buffers: (n, 44*44, 64 ch) as [32 hi | 32 lo] chun
     return (w[:, :, :, 0] + w[:, :, :, 1]).reshape(n, 44 * 44, 64)
 
 res = {}
-for mode in ('0', '1', '2'):
+for mode in ('0', '1', '3'):
     os.environ['SE3TN_STEM_WS'] = mode
     eng = pkg.Engine(max_batch=nb); eng.load_state_dict(sd, 0)
     try:
@@ -35,7 +35,7 @@ for mode in ('0', '1', '2'):
 if '0' in res:
     import se3_oracle as O
     ref = O.forward(sd, A[:8], B[:8]); ref6 = torch.cat((ref['trans'], ref['rot']), 1)
-    for mode in ('1', '2'):
+    for mode in ('1',):
         if mode not in res: continue
         d6 = (res[mode][0] - res['0'][0]).abs().max().item()
         da = (res[mode][1] - res['0'][1]).abs().max().item(); db = (res[mode][2] - res['0'][2]).abs().max().item()

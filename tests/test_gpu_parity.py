@@ -331,6 +331,29 @@ def test_track_batch_mixed_weight_sets(synth, eng):
 
 
 
+def test_weights_stationary_stem_is_bit_identical(pkg, synth, monkeypatch):
+    """conv_stem_ws_kernel (SE3TN_STEM_WS=1: stem weights as the tensor-memory A operand, pooling in registers) must produce exactly
+    the bits of the default resident-weight stem: both accumulate hi*w_hi + lo*w_hi + hi*w_lo per MMA in the same K order."""
+    sd = synth.make_state_dict(0)
+    A, B = synth.tensor_pairs(5, seed=17)
+    outs = []
+    for mode in ('0', '1'):
+        monkeypatch.setenv('SE3TN_STEM_WS', mode)
+        e = pkg.Engine(max_batch=8)
+        try:
+            e.load_state_dict(sd, 0)
+            res = []
+            for prec in ('bf16x3', 'bf16'):
+                t, r, f = e.forward(A.to(e.device), B.to(e.device), precision=prec, want_feature=True)
+                res.append((t.cpu(), r.cpu(), f.cpu(), e.debug_buffer(4, 5).clone().cpu(), e.debug_buffer(5, 5).clone().cpu()))
+            outs.append(res)
+        finally:
+            e.close()
+    for a, b in zip(outs[0], outs[1]):
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+
+
 # ------------------------------------------------------------------------------ BASELINE configs at full size
 def test_raw_regime_full_path_batch64_both_weight_seeds(synth, eng):
     """BASELINE configs[1] at its real size: 64 tracks of one raw frame (large-magnitude normalised inputs, F13) through
