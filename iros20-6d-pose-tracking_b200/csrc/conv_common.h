@@ -88,8 +88,9 @@ struct LayerDesc {
     int res_c;             // channels per pixel of the residual buffer
     int li;                // row of the per-set tables (layer index; trunk layers with 128-row weight boxes: 14 + layer - 8)
     // trunk scheduling
-    int unit_base;         // first global work-unit index of this layer
-    int units_per_image;   // tiles_x * tiles_y * n_tiles * groups
+    int unit_base;         // first global work-unit index of this layer (units are K-split pieces when TrunkParams::ksplit > 1)
+    int base_unit0;        // index of this layer's first UNSPLIT unit among all unsplit units of the launch (split-K scratch / counters)
+    int units_per_image;   // tiles_x * tiles_y * n_tiles * groups (unsplit)
     int dep_layer;         // index (within the launch) of the layer whose per-image completion this layer waits for; -1: none
     unsigned dep_target;   // value done[dep_layer][image] reaches when that image is complete (8 epilogue warps x units per image)
 };
@@ -107,6 +108,12 @@ struct TrunkParams {
     const CUtensorMap* gbmaps;     // per-set weight maps, entry [wid * kLayersPerSet + li]
     const float* const* gbias;     // per-set bias pointers, same indexing
     unsigned long long* trace;     // nullable (SE3TN_TRACE)
+    // latency mode (a handful of tracks): every unit's K loop is cut into `ksplit` pieces run by different CTAs; each piece dumps
+    // its fp32 accumulator to `partial`, and per (unit, epilogue-warp slice) the LAST piece to arrive sums all pieces in a fixed
+    // order and runs the normal epilogue.  1 = off.
+    int ksplit;
+    float* partial;                // [unsplit unit][piece][8 warp slices][32 rows x BN/2 columns]
+    unsigned* slice_cnt;           // [unsplit unit][8] arrival counters (zeroed before the launch)
 };
 
 struct ResidentParams {
@@ -124,8 +131,11 @@ cudaError_t launch_conv_resident(const ResidentParams& p, int kind, int prec, in
 cudaError_t launch_conv_trunk(const TrunkParams& p, int prec, int block_n /*256 | 128*/, int num_sms, bool pdl, cudaStream_t stream);
 // weights-stationary stem (conv_stem_t.cu): bf16 modes, single weight set; wstack = the stem's stacked weight matrix [128][224 words]
 cudaError_t launch_conv_stem_ws(const ResidentParams& p, const void* wstack, int prec, int debug_flags, int num_sms, bool pdl, cudaStream_t stream);
-// 32-bit words of scheduler state a trunk launch needs (next-unit counter + done[layers][max_batch])
-inline size_t trunk_sched_words(int max_batch) { return 1 + static_cast<size_t>(kTrunkMaxLayers) * max_batch; }
+// latency mode: at most kSplitMaxImages images, ksplit = kSplitK pieces, 128-channel units (at most 8 per image and layer)
+constexpr int kSplitMaxImages = 4, kSplitK = 4, kSplitMaxUnits = kSplitMaxImages * 8 * kTrunkMaxLayers;
+// 32-bit words of scheduler state a trunk launch needs: next-unit counter + done[layers][max_batch] + split-K slice counters
+inline size_t trunk_sched_words(int max_batch) { return 1 + static_cast<size_t>(kTrunkMaxLayers) * max_batch + static_cast<size_t>(kSplitMaxUnits) * 8; }
+inline size_t trunk_partial_floats() { return static_cast<size_t>(kSplitMaxUnits) * kSplitK * 128 * 128; }
 
 cudaError_t launch_conv_direct(const ConvGeom& g, const ConvPtrs& p, cudaStream_t stream);
 

@@ -551,7 +551,13 @@ template <int PREC, int BN_> struct TCfg {
     static_assert(kSmem <= 232448, "shared memory budget");
 };
 
-struct UnitCoord { int l, img, tx, ty, n_tile, grp; };
+struct UnitCoord { int l, img, tx, ty, n_tile, grp, c0, c1, piece, gidx; };
+// per-unit timeline (SE3TN_TRACE, small launches only): 5 stamps per work unit behind the trunk's per-CTA stamps:
+// 0 dependency satisfied (producer), 1 first A unit landed (MMA warp), 2 last MMA committed, 3 accumulator seen by epilogue warp 0,
+// 4 epilogue warp 0 finished (stores + completion signal)
+__device__ __forceinline__ void unit_stamp(const TrunkParams& p, int u, int k) {
+    if (p.trace && u < 2048) p.trace[256 * 8 + u * 5 + k] = gtimer();
+}   // [c0, c1): K chunks of this piece; gidx: unsplit unit index in the launch
 
 __device__ __forceinline__ int unit_layer(const TrunkParams& p, int u) {
     int l = 0;
@@ -564,7 +570,13 @@ __device__ __forceinline__ UnitCoord decode_unit(const TrunkParams& p, int u) {
     UnitCoord c;
     c.l = unit_layer(p, u);
     const LayerDesc& L = p.layer[c.l];
-    const int local = u - L.unit_base;
+    int local = u - L.unit_base;
+    c.piece = 0; c.c0 = 0; c.c1 = L.chunks;
+    if (p.ksplit > 1) {                            // consecutive indices = the pieces of one unit (pulled by different CTAs at about the same time)
+        c.piece = local % p.ksplit; local /= p.ksplit;
+        c.c0 = c.piece * L.chunks / p.ksplit; c.c1 = (c.piece + 1) * L.chunks / p.ksplit;
+    }
+    c.gidx = L.base_unit0 + local;
     const int im = local / L.units_per_image;
     int r = local - im * L.units_per_image;
     c.img = p.img_first + im;
@@ -582,7 +594,7 @@ __device__ __forceinline__ void trunk_load_unit(const LayerDesc& L, const UnitCo
     using KT = KTab<KIND>;
     const int cbase = L.in_cbase_words + c.grp * L.in_gstride_words;
     const int ox = c.tx * 11, oy = c.ty * 11;
-    for (int ch = 0; ch < L.chunks; ++ch) {
+    for (int ch = c.c0; ch < c.c1; ++ch) {
 #pragma unroll
         for (int u = 0; u < KT::NU; ++u) {
             ptx::mbar_wait(&a_empty[stage], phase ^ 1);
@@ -601,7 +613,7 @@ __device__ __forceinline__ void trunk_load_weights(const LayerDesc& L, const CUt
     using KT = KTab<KIND>;
     using C = TCfg<PREC, BN>;
     const int wrow = c.grp * L.cout + c.n_tile * C::BN;
-    for (int ch = 0; ch < L.chunks; ++ch) {
+    for (int ch = c.c0; ch < c.c1; ++ch) {
 #pragma unroll
         for (int u = 0; u < KT::NU; ++u) {
 #pragma unroll
@@ -619,7 +631,7 @@ __device__ __forceinline__ void trunk_load_weights(const LayerDesc& L, const CUt
 template <int KIND, int PREC, int BN>
 __device__ __forceinline__ void trunk_mma_unit(int chunks, uint32_t d_tmem, uint8_t* sA, uint8_t* sB, uint64_t* a_full, uint64_t* a_empty,
                                                uint64_t* b_full, uint64_t* b_empty, int& astage, uint32_t& aphase, int& bstage, uint32_t& bphase,
-                                               unsigned long long* trace, bool first_unit)
+                                               unsigned long long* trace, bool first_unit, unsigned long long* ustamp)
 {
     using KT = KTab<KIND>;
     using C = TCfg<PREC, BN>;
@@ -631,6 +643,7 @@ __device__ __forceinline__ void trunk_mma_unit(int chunks, uint32_t d_tmem, uint
             ptx::mbar_wait(&a_full[astage], aphase);
             ptx::tc_fence_after();
             if (first_unit && ch == 0 && u == 0 && (threadIdx.x & 31) == 0) trace_stamp(trace, 3);
+            if (ustamp && ch == 0 && u == 0 && (threadIdx.x & 31) == 0) *ustamp = gtimer();
             const uint32_t a_unit_lo = desc_lo(sA + astage * kAUnit3);
 #pragma unroll
             for (int k = 0; k < KT::ntaps(u); ++k) {
@@ -745,11 +758,12 @@ conv_trunk_kernel(const __grid_constant__ TrunkParams p)
                         const long long t0 = clock64();
                         while (static_cast<unsigned>(ptx::ld_acquire_gpu(flag)) < L.dep_target) {
                             __nanosleep(64);
-                            if (clock64() - t0 > (1ll << 31)) __trap();     // a scheduling bug becomes an error, not a hung GPU
+                            if (clock64() - t0 > (1ll << 34)) __trap();     // ~10 s: a scheduling bug becomes an error, not a hung GPU (long enough for compute-sanitizer's slowdown)
                         }
                     }
                     ptx::fence_proxy_async_all();   // the TMA (async proxy) reads below must observe what the acquire made visible
                 }
+                unit_stamp(p, u, 0);
                 if (L.kind == KIND_S1) trunk_load_unit<KIND_S1>(L, c, sA, a_full, a_empty, stage, phase, C::kAStages);
                 else                   trunk_load_unit<KIND_S2>(L, c, sA, a_full, a_empty, stage, phase, C::kAStages);
                 u = static_cast<int>(atomicAdd(p.sched, 1u));   // pull the next unit only now: look-ahead = the A pipeline depth
@@ -778,16 +792,18 @@ conv_trunk_kernel(const __grid_constant__ TrunkParams p)
             const int u = next_unit(true);
             if (u >= p.total_units) break;
             const int l = unit_layer(p, u);
-            const int kind = p.layer[l].kind, chunks = p.layer[l].chunks;
+            const int kind = p.layer[l].kind, chunks = p.layer[l].chunks / p.ksplit;      // K chunks of this piece (the host makes chunks divisible)
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
             ptx::tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * BN;
-            if (kind == KIND_S1) trunk_mma_unit<KIND_S1, PREC, BN>(chunks, d_tmem, sA, sB, a_full, a_empty, b_full, b_empty, astage, aphase, bstage, bphase, p.trace, it == 0);
-            else                 trunk_mma_unit<KIND_S2, PREC, BN>(chunks, d_tmem, sA, sB, a_full, a_empty, b_full, b_empty, astage, aphase, bstage, bphase, p.trace, it == 0);
+            unsigned long long* ust = (p.trace && u < 2048) ? p.trace + 256 * 8 + u * 5 + 1 : nullptr;
+            if (kind == KIND_S1) trunk_mma_unit<KIND_S1, PREC, BN>(chunks, d_tmem, sA, sB, a_full, a_empty, b_full, b_empty, astage, aphase, bstage, bphase, p.trace, it == 0, ust);
+            else                 trunk_mma_unit<KIND_S2, PREC, BN>(chunks, d_tmem, sA, sB, a_full, a_empty, b_full, b_empty, astage, aphase, bstage, bphase, p.trace, it == 0, ust);
             if (ptx::elect_one()) ptx::umma_commit(&tmem_full[acc]);
             __syncwarp();
+            if (lane == 0) unit_stamp(p, u, 2);
         }
         if (lane == 0) trace_stamp(p.trace, 4);
     } else if (warp >= 4) {
@@ -831,7 +847,39 @@ conv_trunk_kernel(const __grid_constant__ TrunkParams p)
             ptx::mbar_wait(&tmem_full[acc], acc_phase);
             ptx::tc_fence_after();
             if (it == 0 && threadIdx.x == 128) trace_stamp(p.trace, 5);
+            if (threadIdx.x == 128) unit_stamp(p, u, 3);
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + half * kCols;
+            const bool split = p.ksplit > 1;
+            // this warp's slice (32 rows x kCols columns) of piece `pc` of this unit in the split-K scratch: row-major, 32-column blocks
+            auto slice_of = [&](int pc) -> float* {
+                return p.partial + ((static_cast<size_t>(c.gidx) * p.ksplit + pc) * 8 + ew) * (32 * kCols);
+            };
+            if (split) {
+                // latency mode: this CTA only summed K chunks [c0, c1).  Dump the fp32 slice, hand the accumulator back, and let the
+                // LAST piece to arrive for this slice add all pieces (fixed order 0..ksplit-1: the result does not depend on arrival order)
+                float* dst = slice_of(c.piece);
+#pragma unroll 1
+                for (int c0 = 0; c0 < kCols; c0 += 32) {
+                    uint32_t r0[16], r1[16];
+                    ptx::tmem_ld16(taddr + c0, r0);
+                    ptx::tmem_ld16(taddr + c0 + 16, r1);
+                    ptx::tmem_ld_wait();
+                    float4* d4 = reinterpret_cast<float4*>(dst + (c0 / 32) * 1024 + lane * 32);
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        d4[jj] = make_float4(__uint_as_float(r0[4 * jj]), __uint_as_float(r0[4 * jj + 1]), __uint_as_float(r0[4 * jj + 2]), __uint_as_float(r0[4 * jj + 3]));
+                        d4[4 + jj] = make_float4(__uint_as_float(r1[4 * jj]), __uint_as_float(r1[4 * jj + 1]), __uint_as_float(r1[4 * jj + 2]), __uint_as_float(r1[4 * jj + 3]));
+                    }
+                }
+                ptx::tc_fence_before();
+                __threadfence();
+                __syncwarp();
+                unsigned arrived = 0;
+                if (lane == 0) { ptx::mbar_arrive(&tmem_empty[acc]); arrived = atomicAdd(p.slice_cnt + c.gidx * 8 + ew, 1u); }
+                arrived = __shfl_sync(0xffffffffu, arrived, 0);
+                if (arrived + 1 != static_cast<unsigned>(p.ksplit)) { if (threadIdx.x == 128) unit_stamp(p, u, 4); continue; }   // another piece finishes this slice
+                __threadfence();                                                     // order the reads below after the other pieces' dumps
+            }
 #pragma unroll 1
             for (int c0 = 0; c0 < kCols; c0 += 32) {
                 const int chan = ch0 + c0;                        // first channel of this 32-channel block
@@ -849,7 +897,7 @@ conv_trunk_kernel(const __grid_constant__ TrunkParams p)
                         }
                     }
                 }
-                {
+                if (!split) {
                     uint32_t r0[16], r1[16];
                     ptx::tmem_ld16(taddr + c0, r0);
                     ptx::tmem_ld16(taddr + c0 + 16, r1);
@@ -860,8 +908,21 @@ conv_trunk_kernel(const __grid_constant__ TrunkParams p)
                         *reinterpret_cast<uint4*>(&stg[lane][jj]) = make_uint4(r0[jj], r0[jj + 1], r0[jj + 2], r0[jj + 3]);
                         *reinterpret_cast<uint4*>(&stg[lane][16 + jj]) = make_uint4(r1[jj], r1[jj + 1], r1[jj + 2], r1[jj + 3]);
                     }
+                } else {
+                    // sum of the pieces, row `lane` of this block, in piece order
+                    float4 a[8];
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) a[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int pc = 0; pc < p.ksplit; ++pc) {
+                        const float4* s4 = reinterpret_cast<const float4*>(slice_of(pc) + (c0 / 32) * 1024 + lane * 32);
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj) { const float4 v = __ldcg(s4 + jj); a[jj].x += v.x; a[jj].y += v.y; a[jj].z += v.z; a[jj].w += v.w; }
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) *reinterpret_cast<float4*>(&stg[lane][4 * jj]) = a[jj];
                 }
-                if (c0 + 32 == kCols) {                           // last TMEM read of this unit: hand the accumulator back to the MMA warp
+                if (!split && c0 + 32 == kCols) {                 // last TMEM read of this unit: hand the accumulator back to the MMA warp
                     ptx::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
@@ -923,6 +984,7 @@ conv_trunk_kernel(const __grid_constant__ TrunkParams p)
                 __syncwarp();
                 if (lane == 0) atomicAdd(done + c.l * p.max_batch + c.img, 1u);
             }
+            if (threadIdx.x == 128) unit_stamp(p, u, 4);
         }
         if (threadIdx.x == 128) trace_stamp(p.trace, 6);
     }
@@ -971,11 +1033,13 @@ template <int PREC, int BN>
 cudaError_t launch_trunk_t(const TrunkParams& p, int num_sms, bool pdl, cudaStream_t stream) {
     using C = TCfg<PREC, BN>;
     if (p.n_layers < 1 || p.n_layers > kTrunkMaxLayers || p.total_units <= 0 || !p.sched) return cudaErrorInvalidValue;
+    if (p.ksplit < 1 || (p.ksplit > 1 && (!p.partial || !p.slice_cnt || p.ksplit > kSplitK || C::BN != 128))) return cudaErrorInvalidValue;
     for (int l = 0; l < p.n_layers; ++l) {
         const LayerDesc& L = p.layer[l];
         if ((L.kind != KIND_S1 && L.kind != KIND_S2) || L.cout % C::BN || L.n_tiles != L.cout / C::BN) return cudaErrorInvalidValue;
         if (L.pool_part && (L.tiles_x != 1 || L.tiles_y != 1)) return cudaErrorInvalidValue;   // fused avg-pool: tile = whole image
         if (L.dep_layer >= l) return cudaErrorInvalidValue;                                    // dependencies point backwards in the pull order
+        if (L.chunks % p.ksplit) return cudaErrorInvalidValue;
     }
     static size_t attr[64] = {};
     cudaError_t e = set_smem(conv_trunk_kernel<PREC, BN>, C::kSmem, attr);

@@ -67,12 +67,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 // Spin on try_wait (which itself suspends for a HW-defined time slice).  A protocol bug turns
-// into a trap after ~2 s (2^32 SM cycles) instead of a hung GPU.
+// into a trap after ~20 s (2^35 SM cycles; long enough for compute-sanitizer runs) instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > (1ll << 32)) __trap();
+        if (clock64() - t0 > (1ll << 35)) __trap();
     }
 }
 

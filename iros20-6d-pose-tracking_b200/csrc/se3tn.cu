@@ -124,7 +124,8 @@ struct se3tn_ctx {
     uint8_t* render_proj = nullptr; uint8_t* render_unif = nullptr; int render_max_nv = 0, render_proj_nv = 0;   // rasteriser workspace
     FillScratch fill = {nullptr, nullptr, nullptr, nullptr}; size_t fill_pixels = 0;   // depth hole-filling scratch (grows on demand)
     float* pool_part = nullptr;      // [max_batch][4][1024] column sums from the last conv's epilogue
-    unsigned* sched = nullptr;       // trunk kernel: next-unit counter + done[6][max_batch]; zero between steps (head_pooled_kernel clears it)
+    unsigned* sched = nullptr;       // trunk kernel: next-unit counter + done[6][max_batch] + split-K slice counters; zero between steps (head_pooled_kernel clears it)
+    float* partial = nullptr;        // split-K scratch of the latency mode (n <= 4): trunk_partial_floats()
     bool sched_dirty = false;        // a step failed between the trunk launch and the head launch: clear before the next one
     unsigned long long* trace = nullptr;   // SE3TN_TRACE=1: [14 slots][256 CTAs][8] globaltimer stamps of the last forward (conv_umma2.cu trace_stamp)
     EncodeTiledFn encode = nullptr;
@@ -476,13 +477,24 @@ int run_network(se3tn_ctx* c, int weight_id, int first, int n, int precision,
         // work units of 256 output channels; small batches (at most half of the SMs busy per layer otherwise) use 128:
         // twice the units per layer and half the latency of each -- the layers of one image are a serial chain
         const int bn = (n * 4 * 2 <= c->num_sms) ? 128 : 256;
-        int base = 0;
+        // latency mode: a handful of tracks keep only 8 CTAs per layer busy, and the six layers of an image are a serial chain:
+        // cut every unit's K loop into kSplitK pieces (conv_trunk_kernel).  Its fp32 sums are grouped differently, so results agree
+        // with the throughput mode to rounding, not bit for bit; within the mode (n = 1..4) they do not depend on n.
+        int ksplit = (n <= kSplitMaxImages) ? kSplitK : 1;
+        for (int l = 0; l < 14 - kFirstTrunkLayer; ++l) {
+            fill_layer_desc(c, ws, kFirstTrunkLayer + l, kprec, tp.layer[l], bn);
+            while (tp.layer[l].chunks % ksplit) ksplit /= 2;       // 2-byte storage: convAB1 has only two 128-byte chunks per pixel
+        }
+        int base = 0, base0 = 0;
         for (int l = 0; l < 14 - kFirstTrunkLayer; ++l) {
             LayerDesc& d = tp.layer[l];
-            fill_layer_desc(c, ws, kFirstTrunkLayer + l, kprec, d, bn);
-            d.unit_base = base; base += n * d.units_per_image;
+            d.unit_base = base; base += n * d.units_per_image * ksplit;
+            d.base_unit0 = base0; base0 += n * d.units_per_image;
             if (l > 0) { d.dep_layer = l - 1; d.dep_target = 8u * static_cast<unsigned>(tp.layer[l - 1].units_per_image); }
         }
+        if (ksplit > 1 && base0 > kSplitMaxUnits) return fail(c, SE3TN_ERR_STATE, "split-K scratch too small");
+        tp.ksplit = ksplit; tp.partial = c->partial;
+        tp.slice_cnt = c->sched + 1 + static_cast<size_t>(kTrunkMaxLayers) * c->max_batch;
         tp.layer[5].pool_part = c->pool_part;      // AdaptiveAvgPool2d(1) fused into the last conv's epilogue (indexed by absolute image)
         tp.n_layers = 6; tp.total_units = base;
         tp.img_first = first; tp.n_img = n; tp.max_batch = c->max_batch;
@@ -561,7 +573,8 @@ int se3tn_create(int device, int max_batch, void* workspace, se3tn_ctx** out) {
     }
     e = cudaMalloc(&c->pool_part, static_cast<size_t>(max_batch) * 4 * 1024 * sizeof(float));
     if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); se3tn_destroy(c); return fail(nullptr, SE3TN_ERR_NOMEM, "se3tn_create: pool buffer: " + m); }
-    e = cudaMalloc(&c->sched, trunk_sched_words(max_batch) * sizeof(unsigned));
+    e = cudaMalloc(&c->partial, trunk_partial_floats() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&c->sched, trunk_sched_words(max_batch) * sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMemset(c->sched, 0, trunk_sched_words(max_batch) * sizeof(unsigned));
     if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); se3tn_destroy(c); return fail(nullptr, SE3TN_ERR_NOMEM, "se3tn_create: scheduler state: " + m); }
     // zero once: the stem buffers' 3-pixel halo is the conv padding and is never written again
@@ -588,7 +601,7 @@ void se3tn_destroy(se3tn_ctx* c) {
     for (int i = 0; i < SE3TN_PROFILE_SLOTS; ++i) { if (c->ev0[i]) cudaEventDestroy(c->ev0[i]); if (c->ev1[i]) cudaEventDestroy(c->ev1[i]); }
     drop_graphs(c);
     if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
-    cudaFree(c->sched); cudaFree(c->pool_part); cudaFree(c->trace);
+    cudaFree(c->sched); cudaFree(c->partial); cudaFree(c->pool_part); cudaFree(c->trace);
     for (auto& kv : c->meshes) { cudaFree(const_cast<float*>(kv.second.pos)); cudaFree(const_cast<float*>(kv.second.nrm)); cudaFree(const_cast<uint8_t*>(kv.second.col)); cudaFree(const_cast<int*>(kv.second.faces)); }
     cudaFree(c->d_meshes); cudaFree(c->render_proj); cudaFree(c->render_unif);
     cudaFree(c->fill.a); cudaFree(c->fill.b); cudaFree(c->fill.lut); cudaFree(c->fill.minmax);

@@ -331,6 +331,27 @@ def test_track_batch_mixed_weight_sets(synth, eng):
 
 
 
+def test_latency_mode_split_k_consistency(synth, eng):
+    """n <= 4 runs the trunk with split-K work units (latency mode): results within the gate of the oracle, independent of n inside
+    the mode (1 vs 4 pairs: bit-identical), and equal to the throughput mode (n = 5: same pairs) to fp32 rounding."""
+    sd = synth.make_state_dict(0)
+    A, B = synth.tensor_pairs(5, seed=23)
+    Ad, Bd = A.to(eng.device), B.to(eng.device)
+    ref = O.forward(sd, A, B); ref6 = torch.cat((ref['trans'], ref['rot']), 1)
+    for prec in ('bf16x3', 'tf32', 'bf16'):
+        t5, r5, _ = eng.forward(Ad, Bd, precision=prec)                                   # throughput mode
+        t4, r4, _ = eng.forward(Ad[:4].contiguous(), Bd[:4].contiguous(), precision=prec)   # latency mode
+        assert_gate(six(t4, r4), ref6[:4], *GATES[prec])
+        singles = [eng.forward(Ad[i:i + 1].contiguous(), Bd[i:i + 1].contiguous(), precision=prec) for i in range(4)]
+        for i, (t1, r1, _) in enumerate(singles):
+            assert torch.equal(t1[0], t4[i]) and torch.equal(r1[0], r4[i])
+        d = (six(t4, r4) - six(t5, r5)[:4]).abs().max().item()
+        # a last-bit change of an fp32 sum can flip the rounding of a stored activation (2^-16 relative in bf16x3, 2^-11 in tf32, 2^-9 in bf16)
+        assert d < {'bf16x3': 5e-6, 'tf32': 5e-4, 'bf16': 5e-3}[prec], d
+        t4b, r4b, _ = eng.forward(Ad[:4].contiguous(), Bd[:4].contiguous(), precision=prec)
+        assert torch.equal(t4, t4b) and torch.equal(r4, r4b)                              # deterministic whatever the arrival order of the pieces
+
+
 def test_weights_stationary_stem_is_bit_identical(pkg, synth, monkeypatch):
     """conv_stem_ws_kernel (SE3TN_STEM_WS=1: stem weights as the tensor-memory A operand, pooling in registers) must produce exactly
     the bits of the default resident-weight stem: both accumulate hi*w_hi + lo*w_hi + hi*w_lo per MMA in the same K order."""
@@ -409,8 +430,8 @@ def test_batch256_bf16_and_bf16x3_vs_oracle(pkg, synth):
             print('batch-256 %s worst err/tol: %.3f' % (prec, worst))
             t2, r2, _ = e.forward(Ad, Bd, precision=prec)
             assert torch.equal(t1, t2) and torch.equal(r1, r2)
-            t3, r3, _ = e.forward(Ad[200:203].contiguous(), Bd[200:203].contiguous(), precision=prec)
-            assert torch.equal(t3, t1[200:203]) and torch.equal(r3, r1[200:203])
+            t3, r3, _ = e.forward(Ad[200:205].contiguous(), Bd[200:205].contiguous(), precision=prec)      # (n > 4: not the split-K latency mode)
+            assert torch.equal(t3, t1[200:205]) and torch.equal(r3, r1[200:205])
     finally:
         e.close()
 
