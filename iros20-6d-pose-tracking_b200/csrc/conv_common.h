@@ -112,7 +112,7 @@ struct TrunkParams {
     // its fp32 accumulator to `partial`, and per (unit, epilogue-warp slice) the LAST piece to arrive sums all pieces in a fixed
     // order and runs the normal epilogue.  1 = off.
     int ksplit;
-    float* partial;                // [unsplit unit][piece][8 warp slices][32 rows x BN/2 columns]
+    float* partial;                // [unsplit unit][piece][8 warp slices][32-column block][float4 0..7][row]
     unsigned* slice_cnt;           // [unsplit unit][8] arrival counters (zeroed before the launch)
 };
 

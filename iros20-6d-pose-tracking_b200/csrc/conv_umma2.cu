@@ -739,6 +739,8 @@ conv_trunk_kernel(const __grid_constant__ TrunkParams p)
     if (warp == 0) {
         // ============================== scheduler + A producer ================================
         if (lane == 0) {
+            for (int l = 0; l < p.n_layers; ++l)    // every layer brings its own tensor maps: fetch the descriptors now, not at each layer's first load
+                for (int m = 0; m < (p.layer[l].kind == KIND_S2 ? 4 : 1); ++m) ptx::prefetch_tmap(&p.layer[l].amap[m]);
             ptx::grid_dep_wait();                   // the first layer's input comes from the previous kernel
             int stage = 0; uint32_t phase = 0;
             int ps = 0; uint32_t pph = 0;
@@ -772,6 +774,7 @@ conv_trunk_kernel(const __grid_constant__ TrunkParams p)
     } else if (warp == 3) {
         // ============================== B producer ================================
         if (lane == 0) {
+            if (!p.img_wid) for (int l = 0; l < p.n_layers; ++l) ptx::prefetch_tmap(&p.layer[l].bmap);
             int stage = 0; uint32_t phase = 0;
             for (;;) {
                 const int u = next_unit(false);
@@ -864,11 +867,12 @@ conv_trunk_kernel(const __grid_constant__ TrunkParams p)
                     ptx::tmem_ld16(taddr + c0, r0);
                     ptx::tmem_ld16(taddr + c0 + 16, r1);
                     ptx::tmem_ld_wait();
-                    float4* d4 = reinterpret_cast<float4*>(dst + (c0 / 32) * 1024 + lane * 32);
+                    // float4 number jj of row `lane` lives at [block][jj][lane]: every store / load instruction of the warp is 512 contiguous bytes
+                    float4* d4 = reinterpret_cast<float4*>(dst + (c0 / 32) * 1024) + lane;
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) {
-                        d4[jj] = make_float4(__uint_as_float(r0[4 * jj]), __uint_as_float(r0[4 * jj + 1]), __uint_as_float(r0[4 * jj + 2]), __uint_as_float(r0[4 * jj + 3]));
-                        d4[4 + jj] = make_float4(__uint_as_float(r1[4 * jj]), __uint_as_float(r1[4 * jj + 1]), __uint_as_float(r1[4 * jj + 2]), __uint_as_float(r1[4 * jj + 3]));
+                        d4[jj * 32] = make_float4(__uint_as_float(r0[4 * jj]), __uint_as_float(r0[4 * jj + 1]), __uint_as_float(r0[4 * jj + 2]), __uint_as_float(r0[4 * jj + 3]));
+                        d4[(4 + jj) * 32] = make_float4(__uint_as_float(r1[4 * jj]), __uint_as_float(r1[4 * jj + 1]), __uint_as_float(r1[4 * jj + 2]), __uint_as_float(r1[4 * jj + 3]));
                     }
                 }
                 ptx::tc_fence_before();
@@ -914,9 +918,9 @@ conv_trunk_kernel(const __grid_constant__ TrunkParams p)
 #pragma unroll
                     for (int jj = 0; jj < 8; ++jj) a[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
                     for (int pc = 0; pc < p.ksplit; ++pc) {
-                        const float4* s4 = reinterpret_cast<const float4*>(slice_of(pc) + (c0 / 32) * 1024 + lane * 32);
+                        const float4* s4 = reinterpret_cast<const float4*>(slice_of(pc) + (c0 / 32) * 1024) + lane;
 #pragma unroll
-                        for (int jj = 0; jj < 8; ++jj) { const float4 v = __ldcg(s4 + jj); a[jj].x += v.x; a[jj].y += v.y; a[jj].z += v.z; a[jj].w += v.w; }
+                        for (int jj = 0; jj < 8; ++jj) { const float4 v = __ldcg(s4 + jj * 32); a[jj].x += v.x; a[jj].y += v.y; a[jj].z += v.z; a[jj].w += v.w; }
                     }
                     __syncwarp();
 #pragma unroll

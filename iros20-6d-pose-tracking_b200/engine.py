@@ -189,6 +189,13 @@ class Engine:
                                               _stream(self.device)), self._ctx)
         return out_poses, out_trans, out_rot
 
+    def upload_frame_window(self, rgb_host, depth_host, rgb_dev, depth_dev, y0, y1, x0, x1):
+        """Copy rows [y0,y1) x columns [x0,x1) of contiguous numpy frames (uint8 (H,W,3), uint16 (H,W)) into full-size device frame
+        buffers: K0 only reads a frame inside the tracks' crop windows."""
+        H, W = depth_host.shape
+        _lib.check(self.lib.se3tn_upload_frame_window(self._ctx, rgb_host.ctypes.data_as(C.c_void_p), depth_host.ctypes.data_as(C.c_void_p), int(H), int(W),
+                                                      int(y0), int(y1), int(x0), int(x1), _ptr(rgb_dev), _ptr(depth_dev), _stream(self.device)), self._ctx)
+
     # ------------------------------------------------------------------ metrics (SURVEY 8f row 1)
     def add_adi(self, model_pts, pred, gt, want_add=True, want_adi=True):
         """ADD / ADD-S (reference Utils.py:72-98) of n pose pairs: float64 CUDA tensors model (m,3), pred/gt (n,4,4)."""

@@ -101,6 +101,27 @@ def _as_numpy_pose(p):
     return np.ascontiguousarray(p, dtype=np.float64)
 
 
+def crop_windows_union(poses, K, object_width, H, W, margin=2):
+    """Bounding rectangle (y0, y1, x0, x1), clipped to the frame, of the crop windows compute_bbox gives these poses (reference
+    Utils.py:302-316, same float64 arithmetic and np.round) plus a safety margin; None if a pose is degenerate (then upload everything)."""
+    poses = np.asarray(poses, dtype=np.float64).reshape(-1, 4, 4)
+    ow = np.broadcast_to(np.asarray(object_width, dtype=np.float64), (len(poses),))
+    y0, y1, x0, x1 = H, 0, W, 0
+    for p, w in zip(poses, ow):
+        ox, oy, oz = p[0, 3] * 1000.0, p[1, 3] * 1000.0, p[2, 3] * 1000.0
+        with np.errstate(all='ignore'):
+            us = np.round(np.array([ox - w / 2, ox + w / 2]) * K[0, 0] / oz + K[0, 2])
+            vs = np.round(np.array([oy - w / 2, oy + w / 2]) * K[1, 1] / oz + K[1, 2])
+        if not (np.all(np.isfinite(us)) and np.all(np.isfinite(vs))):
+            return None
+        y0 = min(y0, int(vs.min()) - margin); y1 = max(y1, int(vs.max()) + margin)
+        x0 = min(x0, int(us.min()) - margin); x1 = max(x1, int(us.max()) + margin)
+    y0, y1, x0, x1 = max(y0, 0), min(y1, H), max(x0, 0), min(x1, W)
+    if y1 <= y0 or x1 <= x0:
+        return (0, 0, 0, 0)                        # every window lies outside the frame: nothing to upload
+    return (y0, y1, x0, x1)
+
+
 class Tracker:
     def __init__(self, dataset_info, images_mean, images_std, ckpt_dir, model_path=None, trans_normalizer=0.03,
                  rot_normalizer=5 * np.pi / 180, engine=None, weight_id=0, renderer=None, precision='bf16x3', max_batch=64):
@@ -256,7 +277,21 @@ class Tracker:
             poses, rgb_d, depth_d, rgbA_d, depthA_d = self._stage_uploads(prev_poses, current_rgb, current_depth, rgbA, depthA)
         else:
             poses = up(prev_poses, torch.float64, 'poses')
-            rgb_d, depth_d = up(current_rgb, torch.uint8, 'rgb'), up(current_depth, torch.uint16, 'depth')
+            win = None
+            if (not torch.is_tensor(current_rgb) and not torch.is_tensor(current_depth) and not torch.is_tensor(prev_poses) and object_width is None
+                    and len(prev_poses) <= 4 and current_rgb.dtype == np.uint8 and current_depth.dtype == np.uint16
+                    and current_rgb.flags['C_CONTIGUOUS'] and current_depth.flags['C_CONTIGUOUS']):
+                # a few objects: K0 only reads the frame inside their crop windows -> upload that rectangle, not the whole 1.5 MB frame
+                win = crop_windows_union(prev_poses, self.K, self.object_width, current_depth.shape[0], current_depth.shape[1])
+            if win is not None and (win[1] - win[0]) * (win[3] - win[2]) * 2 < current_depth.size:
+                rk, dk = ('rgb', tuple(current_rgb.shape), torch.uint8), ('depth', tuple(current_depth.shape), torch.uint16)
+                for k2, dt in ((rk, torch.uint8), (dk, torch.uint16)):
+                    if k2 not in self._np_bufs:
+                        self._np_bufs[k2] = torch.zeros(k2[1], dtype=dt, device=dev)
+                rgb_d, depth_d = self._np_bufs[rk], self._np_bufs[dk]
+                self.engine.upload_frame_window(current_rgb, current_depth, rgb_d, depth_d, *win)
+            else:
+                rgb_d, depth_d = up(current_rgb, torch.uint8, 'rgb'), up(current_depth, torch.uint16, 'depth')
             if not render:
                 rgbA_d, depthA_d = up(rgbA, torch.uint8, 'rgbA'), up(depthA, torch.uint16, 'depthA')
         n = poses.shape[0]

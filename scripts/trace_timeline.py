@@ -24,7 +24,7 @@ names = ['stemA', 'stemB', 'A2c1', 'A2c2', 'B2c1', 'B2c2', 'B3c1', 'B3c2', 'trun
 t_first = None
 prev_end = None
 print('layer  ctas | start(first,last)  end(first,last) | per-CTA medians: setup  wgt  firstA  mma_span  acc0  epi_tail  exit | span  gap_prev')
-for l in range(14):
+for l in range(9):                          # slots 9..13 hold the trunk's per-unit stamps (scripts/trunk_units.py)
     t = tr[l]; used = t[:, 0] > 0
     t = t[used]
     if not len(t): continue
