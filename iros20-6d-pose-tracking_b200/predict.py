@@ -104,18 +104,19 @@ def _as_numpy_pose(p):
 def crop_windows_union(poses, K, object_width, H, W, margin=2):
     """Bounding rectangle (y0, y1, x0, x1), clipped to the frame, of the crop windows compute_bbox gives these poses (reference
     Utils.py:302-316, same float64 arithmetic and np.round) plus a safety margin; None if a pose is degenerate (then upload everything)."""
+    import math
     poses = np.asarray(poses, dtype=np.float64).reshape(-1, 4, 4)
-    ow = np.broadcast_to(np.asarray(object_width, dtype=np.float64), (len(poses),))
+    fx, fy, cx, cy = float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2])
     y0, y1, x0, x1 = H, 0, W, 0
-    for p, w in zip(poses, ow):
-        ox, oy, oz = p[0, 3] * 1000.0, p[1, 3] * 1000.0, p[2, 3] * 1000.0
-        with np.errstate(all='ignore'):
-            us = np.round(np.array([ox - w / 2, ox + w / 2]) * K[0, 0] / oz + K[0, 2])
-            vs = np.round(np.array([oy - w / 2, oy + w / 2]) * K[1, 1] / oz + K[1, 2])
-        if not (np.all(np.isfinite(us)) and np.all(np.isfinite(vs))):
+    for i in range(len(poses)):                    # plain Python floats: IEEE double like numpy's, round() is half-to-even like np.round
+        w = float(object_width if np.ndim(object_width) == 0 else object_width[i])
+        ox, oy, oz = float(poses[i, 0, 3]) * 1000.0, float(poses[i, 1, 3]) * 1000.0, float(poses[i, 2, 3]) * 1000.0
+        if oz == 0.0 or not all(math.isfinite(v) for v in (ox, oy, oz, w)):
             return None
-        y0 = min(y0, int(vs.min()) - margin); y1 = max(y1, int(vs.max()) + margin)
-        x0 = min(x0, int(us.min()) - margin); x1 = max(x1, int(us.max()) + margin)
+        us = (round((ox - w / 2) * fx / oz + cx), round((ox + w / 2) * fx / oz + cx))
+        vs = (round((oy - w / 2) * fy / oz + cy), round((oy + w / 2) * fy / oz + cy))
+        y0 = min(y0, min(vs) - margin); y1 = max(y1, max(vs) + margin)
+        x0 = min(x0, min(us) - margin); x1 = max(x1, max(us) + margin)
     y0, y1, x0, x1 = max(y0, 0), min(y1, H), max(x0, 0), min(x1, W)
     if y1 <= y0 or x1 <= x0:
         return (0, 0, 0, 0)                        # every window lies outside the frame: nothing to upload
@@ -171,6 +172,7 @@ class Tracker:
                 renderer = None                                    # e.g. a vertices-only ply: fall through to the GL renderers
         self.renderer = renderer if renderer is not None else self._try_reference_renderer(model_path, cam_cfg)
         self._np_bufs = {}
+        self._pin_busy = False
         self.prev_rgb = None
         self.prev_depth = None
         self.frame_cnt = 0
@@ -278,7 +280,7 @@ class Tracker:
         else:
             poses = up(prev_poses, torch.float64, 'poses')
             win = None
-            if (not torch.is_tensor(current_rgb) and not torch.is_tensor(current_depth) and not torch.is_tensor(prev_poses) and object_width is None
+            if (os.environ.get('SE3TN_WINDOW_UPLOAD', 'pinned') != 'off' and not torch.is_tensor(current_rgb) and not torch.is_tensor(current_depth) and not torch.is_tensor(prev_poses) and object_width is None
                     and len(prev_poses) <= 4 and current_rgb.dtype == np.uint8 and current_depth.dtype == np.uint16
                     and current_rgb.flags['C_CONTIGUOUS'] and current_depth.flags['C_CONTIGUOUS']):
                 # a few objects: K0 only reads the frame inside their crop windows -> upload that rectangle, not the whole 1.5 MB frame
@@ -289,7 +291,23 @@ class Tracker:
                     if k2 not in self._np_bufs:
                         self._np_bufs[k2] = torch.zeros(k2[1], dtype=dt, device=dev)
                 rgb_d, depth_d = self._np_bufs[rk], self._np_bufs[dk]
-                self.engine.upload_frame_window(current_rgb, current_depth, rgb_d, depth_d, *win)
+                # through pinned staging (same geometry): a 2-D copy from pageable memory is staged row by row by the driver,
+                # from pinned memory it is one strided DMA
+                pk = ('pin', tuple(current_rgb.shape))
+                if os.environ.get('SE3TN_WINDOW_UPLOAD', 'pinned') == 'pageable':
+                    self.engine.upload_frame_window(current_rgb, current_depth, rgb_d, depth_d, *win)
+                    pk = None
+                elif pk not in self._np_bufs:
+                    self._np_bufs[pk] = (torch.empty(current_rgb.shape, dtype=torch.uint8).pin_memory().numpy(),
+                                         torch.empty(current_depth.shape, dtype=torch.uint16).pin_memory().numpy())
+                if pk is not None:
+                    pin_rgb, pin_depth = self._np_bufs[pk]
+                    y0, y1, x0, x1 = win
+                    if self._pin_busy:
+                        torch.cuda.current_stream(dev).synchronize()          # the previous call's DMA may still be reading the staging
+                    np.copyto(pin_rgb[y0:y1, x0:x1], current_rgb[y0:y1, x0:x1]); np.copyto(pin_depth[y0:y1, x0:x1], current_depth[y0:y1, x0:x1])
+                    self.engine.upload_frame_window(pin_rgb, pin_depth, rgb_d, depth_d, *win)
+                    self._pin_busy = not as_numpy
             else:
                 rgb_d, depth_d = up(current_rgb, torch.uint8, 'rgb'), up(current_depth, torch.uint16, 'depth')
             if not render:
