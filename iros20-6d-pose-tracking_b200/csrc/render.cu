@@ -23,9 +23,9 @@
 //      perspective-correctly, shades, converts the depth the way on_draw does and writes uint8 rgb + uint16 mm.
 // Divisions are confined to reciprocals (1/w per vertex, 1/area per triangle, 1/sum(q) and 1/|l| per pixel), as GPUs do.
 // All arithmetic is float64 with a fixed association and this file is compiled with -fmad=false, so it is bit-identical
-// to the numpy restatement in oracle/se3_oracle.py (render_window).  Scope limits (documented in DESIGN.md): no
-// near-plane polygon clipping (a triangle with a vertex at w <= 1e-6 is dropped; the tracking volume is 0.4-2 m, near =
-// 0.1 m), float32 depth buffer.
+// to the numpy restatement in oracle/se3_oracle.py (render_window).  Near-plane clipping: triangles wholly in front of the
+// eye are cut per pixel by the depth test; a triangle with a vertex at or behind the eye plane (w <= 1e-6) takes the
+// homogeneous path below (straddler_*), which yields the fragments GL's polygon clipping would.  Scope limit: float32 depth buffer.
 #include "render.h"
 #include "bbox.cuh"
 #include "ptx.cuh"
@@ -54,17 +54,24 @@ __device__ __forceinline__ long long floor_div(long long a, long long b) {      
 struct Vtx { long long X, Y; double zw, w; bool ok; };
 struct PVtx { int X, Y; double zw, iw; };         // stored form (iw = 1/w); X == INT_MIN marks a vertex that cannot be used (w <= 1e-6, non-finite)
 
-__device__ __forceinline__ Vtx project(const Uniforms& u, const float* __restrict__ pos, int vi) {
+// clip = P . V . p in float64 on the float32 uniforms, fixed association (oracle/se3_oracle.py _project_vertices)
+__device__ __forceinline__ void clip_coords(const Uniforms& u, const float* __restrict__ pos, int vi, double c[4]) {
     const double px = pos[3 * vi], py = pos[3 * vi + 1], pz = pos[3 * vi + 2];
     const double v0 = ((u.V[0] * px + u.V[1] * py) + u.V[2] * pz) + u.V[3];
     const double v1 = ((u.V[4] * px + u.V[5] * py) + u.V[6] * pz) + u.V[7];
     const double v2 = ((u.V[8] * px + u.V[9] * py) + u.V[10] * pz) + u.V[11];
     const double v3 = ((0.0 * px + 0.0 * py) + 0.0 * pz) + 1.0;
-    // clip = P . v with the zero entries of P kept in the sums (x + 0*y is exact for finite y)
-    const double c0 = ((u.P00 * v0 + 0.0 * v1) + u.P02 * v2) + 0.0 * v3;
-    const double c1 = ((0.0 * v0 + u.P11 * v1) + u.P12 * v2) + 0.0 * v3;
-    const double c2 = ((0.0 * v0 + 0.0 * v1) + u.P22 * v2) + u.P23 * v3;
-    const double c3 = ((0.0 * v0 + 0.0 * v1) + -1.0 * v2) + 0.0 * v3;
+    // the zero entries of P stay in the sums (x + 0*y is exact for finite y)
+    c[0] = ((u.P00 * v0 + 0.0 * v1) + u.P02 * v2) + 0.0 * v3;
+    c[1] = ((0.0 * v0 + u.P11 * v1) + u.P12 * v2) + 0.0 * v3;
+    c[2] = ((0.0 * v0 + 0.0 * v1) + u.P22 * v2) + u.P23 * v3;
+    c[3] = ((0.0 * v0 + 0.0 * v1) + -1.0 * v2) + 0.0 * v3;
+}
+
+__device__ __forceinline__ Vtx project(const Uniforms& u, const float* __restrict__ pos, int vi) {
+    double c[4];
+    clip_coords(u, pos, vi, c);
+    const double c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3];
     Vtx r;
     r.w = c3;
     const double xw = (c0 / c3 + 1.0) * (kRS * 0.5), yw = (c1 / c3 + 1.0) * (kRS * 0.5);
@@ -142,6 +149,106 @@ __device__ __forceinline__ void raster_pixel(const Tri& T, const EdgeSet& E, dou
     if (!(z32 >= 0.f && z32 < 1.f)) return;           // depth clip; LESS against the cleared 1.0
     const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(z32)) << 32) | static_cast<unsigned>(t);
     atomicMin(&keys[(j >> 2) * kRS + i], key);
+}
+
+// ---- triangles the screen-space set-up cannot take (a vertex at or behind the eye plane, or projected beyond 2^25 sub-pixels) ----
+// GL clips such a triangle against the near plane.  Here it is rasterised in homogeneous coordinates: with M the clip-space
+// (x, y, w) of the three vertices as columns, beta = M^-1 (px, py, 1) are the perspective-correct weights of the point seen through
+// the pixel centre (px, py in NDC), scaled so that its w is 1 -- the point lies inside the triangle and in front of the eye iff all
+// beta >= 0 -- and the ordinary depth test 0 <= z_window removes what lies before the near plane: the same fragments polygon
+// clipping produces, with no new vertices.  Same arithmetic, same association as oracle/se3_oracle.py (_straddler_setup).
+struct Strad {
+    double A[3], B[3], C[3], idet, z[3], w[3];
+    int i[3];
+    int ia, ib, ja, jb;
+    bool ok;
+};
+
+__device__ __noinline__ void straddler_setup(const Uniforms& u, const MeshDev& m, int t, Strad& S) {
+    S.ok = false;
+    double cl[3][4];
+    bool finite = true, eye_side = true;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        S.i[k] = m.faces[3 * t + k];
+        clip_coords(u, m.pos, S.i[k], cl[k]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) finite = finite && isfinite(cl[k][c]);
+        eye_side = eye_side && (cl[k][2] + cl[k][3] < 0.0);
+    }
+    if (!finite || eye_side) return;                // nothing of it lies beyond the near plane
+    // pixel box of the part beyond the near plane (only has to be conservative: one pixel of margin, the whole window when in doubt)
+    double mnx = 1e300, mxx = -1e300, mny = 1e300, mxy = -1e300;
+    bool any = false, wild = false;
+    auto take = [&](double x, double y, double w) {
+        const double xs = (x / w + 1.0) * (kRS * 0.5), ys = (y / w + 1.0) * (kRS * 0.5);
+        if (!(isfinite(xs) && isfinite(ys) && fabs(xs) < 1e9 && fabs(ys) < 1e9)) wild = true;
+        mnx = fmin(mnx, xs); mxx = fmax(mxx, xs); mny = fmin(mny, ys); mxy = fmax(mxy, ys);
+        any = true;
+    };
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const int b = (a + 1) % 3;
+        const double da = cl[a][2] + cl[a][3], db = cl[b][2] + cl[b][3];
+        if (da >= 0.0) take(cl[a][0], cl[a][1], cl[a][3]);
+        if ((da >= 0.0) != (db >= 0.0)) {
+            const double s = da / (da - db);
+            take(cl[a][0] + s * (cl[b][0] - cl[a][0]), cl[a][1] + s * (cl[b][1] - cl[a][1]), cl[a][3] + s * (cl[b][3] - cl[a][3]));
+        }
+    }
+    if (!any) return;
+    if (wild) { S.ia = 0; S.ib = kRS - 1; S.ja = 0; S.jb = kRS - 1; }
+    else {
+        S.ia = max(0, static_cast<int>(floor(mnx)) - 1); S.ib = min(kRS - 1, static_cast<int>(ceil(mxx)) + 1);
+        S.ja = max(0, static_cast<int>(floor(mny)) - 1); S.jb = min(kRS - 1, static_cast<int>(ceil(mxy)) + 1);
+    }
+    if (S.ia > S.ib || S.ja > S.jb) return;
+    const double x0 = cl[0][0], y0 = cl[0][1], w0 = cl[0][3], x1 = cl[1][0], y1 = cl[1][1], w1 = cl[1][3], x2 = cl[2][0], y2 = cl[2][1], w2 = cl[2][3];
+    S.A[0] = y1 * w2 - y2 * w1; S.A[1] = y2 * w0 - y0 * w2; S.A[2] = y0 * w1 - y1 * w0;
+    S.B[0] = x2 * w1 - x1 * w2; S.B[1] = x0 * w2 - x2 * w0; S.B[2] = x1 * w0 - x0 * w1;
+    S.C[0] = x1 * y2 - x2 * y1; S.C[1] = x2 * y0 - x0 * y2; S.C[2] = x0 * y1 - x1 * y0;
+    const double det = (x0 * S.A[0] + x1 * S.A[1]) + x2 * S.A[2];
+    if (det == 0.0 || !isfinite(det)) return;
+    S.idet = 1.0 / det;
+    S.z[0] = cl[0][2]; S.z[1] = cl[1][2]; S.z[2] = cl[2][2];
+    S.w[0] = w0; S.w[1] = w1; S.w[2] = w2;
+    S.ok = true;
+}
+
+__device__ __forceinline__ void straddler_weights(const Strad& S, int i, int j, double& b0, double& b1, double& b2) {
+    const double px = static_cast<double>(2 * i + 1 - kRS) / static_cast<double>(kRS), py = static_cast<double>(2 * j + 1 - kRS) / static_cast<double>(kRS);
+    b0 = ((S.A[0] * px + S.B[0] * py) + S.C[0]) * S.idet;
+    b1 = ((S.A[1] * px + S.B[1] * py) + S.C[1]) * S.idet;
+    b2 = ((S.A[2] * px + S.B[2] * py) + S.C[2]) * S.idet;
+}
+
+__device__ __forceinline__ void straddler_pixel(const Strad& S, int t, int i, int j, unsigned long long* keys) {
+    double b0, b1, b2;
+    straddler_weights(S, i, j, b0, b1, b2);
+    if (!(b0 >= 0.0 && b1 >= 0.0 && b2 >= 0.0)) return;
+    const double zc = (b0 * S.z[0] + b1 * S.z[1]) + b2 * S.z[2], wc = (b0 * S.w[0] + b1 * S.w[1]) + b2 * S.w[2];
+    const float z32 = static_cast<float>((zc / wc + 1.0) * 0.5);
+    if (!(z32 >= 0.f && z32 < 1.f)) return;           // the near-plane cut (and the far one)
+    const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(z32)) << 32) | static_cast<unsigned>(t);
+    atomicMin(&keys[(j >> 2) * kRS + i], key);
+}
+
+// out of line (own stack frame): the ordinary triangles' register allocation must not pay for the rare path
+__device__ __noinline__ void raster_straddler(const Uniforms& u, const MeshDev& m, int t, int band, int lane, unsigned long long* keys) {
+    Strad S;
+    straddler_setup(u, m, t, S);
+    if (!S.ok) return;
+    const int j0 = S.ja + ((band - (S.ja & 3)) & 3);         // first row >= ja that this CTA owns
+    if (j0 > S.jb) return;
+    const int bw = S.ib - S.ia + 1, cnt = bw * ((S.jb - j0) / 4 + 1);
+    for (int k = lane; k < cnt; k += 32) straddler_pixel(S, t, S.ia + k % bw, j0 + 4 * (k / bw), keys);
+}
+
+__device__ __noinline__ void resolve_straddler(const Uniforms& u, const MeshDev& m, int t, int i, int j, double* q, int* idx) {
+    Strad S;
+    straddler_setup(u, m, t, S);
+    straddler_weights(S, i, j, q[0], q[1], q[2]);
+    idx[0] = S.i[0]; idx[1] = S.i[1]; idx[2] = S.i[2];
 }
 
 __device__ void make_uniforms(const RenderArgs& a, int n, int nf, Uniforms& u) {
@@ -225,19 +332,21 @@ render_kernel(RenderArgs a)
         const int nf_pad = (m.nf + 31) & ~31;                // whole warps walk the loop (ballots below)
         // the rows of triangle t decide whether this CTA has to look at it at all (three 4-byte loads instead of the full set-up);
         // they are fetched one iteration ahead so the two dependent L2 round trips overlap the previous triangle's work
-        auto fetch_rows = [&](int t, int& y0, int& y1, int& y2) -> bool {
-            if (t >= m.nf) return false;
+        // returns 0: nothing to do, 1: ordinary triangle (rows in y0..y2), 2: a vertex has no screen position (near-plane straddler)
+        auto fetch_rows = [&](int t, int& y0, int& y1, int& y2) -> int {
+            if (t >= m.nf) return 0;
             const unsigned i0 = m.faces[3 * t], i1 = m.faces[3 * t + 1], i2 = m.faces[3 * t + 2];
-            if (!(i0 < static_cast<unsigned>(m.nv) && i1 < static_cast<unsigned>(m.nv) && i2 < static_cast<unsigned>(m.nv))) return false;
-            y0 = pv[i0].Y; y1 = pv[i1].Y; y2 = pv[i2].Y;
-            return true;
+            if (!(i0 < static_cast<unsigned>(m.nv) && i1 < static_cast<unsigned>(m.nv) && i2 < static_cast<unsigned>(m.nv))) return 0;
+            const int2 a = *reinterpret_cast<const int2*>(&pv[i0]), b = *reinterpret_cast<const int2*>(&pv[i1]), c = *reinterpret_cast<const int2*>(&pv[i2]);
+            y0 = a.y; y1 = b.y; y2 = c.y;
+            return (a.x == INT_MIN || b.x == INT_MIN || c.x == INT_MIN) ? 2 : 1;
         };
         int ny0 = 0, ny1 = 0, ny2 = 0;
-        bool nvalid = fetch_rows(threadIdx.x, ny0, ny1, ny2);
+        int nvalid = fetch_rows(threadIdx.x, ny0, ny1, ny2);
         for (int t = threadIdx.x; t < nf_pad; t += blockDim.x) {
             bool big = false;
             bool mine = false;
-            const bool valid = nvalid; const int y0 = ny0, y1 = ny1, y2 = ny2;
+            const bool valid = nvalid == 1, strad = nvalid == 2; const int y0 = ny0, y1 = ny1, y2 = ny2;
             nvalid = fetch_rows(t + blockDim.x, ny0, ny1, ny2);
             if (valid) {
                 const long long mny = min(y0, min(y1, y2)), mxy = max(y0, max(y1, y2));
@@ -280,6 +389,12 @@ render_kernel(RenderArgs a)
                 const int bw = ib - ia + 1, cnt = bw * ((jb - j0) / 4 + 1);
                 for (int k = lane; k < cnt; k += 32) raster_pixel(T, E, inv_area, tb, ia + k % bw, j0 + 4 * (k / bw), tl0, tl1, tl2, keys);
             }
+            unsigned smask = __ballot_sync(0xffffffffu, strad);
+            while (smask) {                                  // near-plane straddlers (rare): the whole warp, homogeneous weights
+                const int src = __ffs(smask) - 1; smask &= smask - 1;
+                const int tb = __shfl_sync(0xffffffffu, t, src);
+                raster_straddler(u, m, tb, band, lane, keys);
+            }
         }
     }
     __syncthreads();
@@ -292,18 +407,27 @@ render_kernel(RenderArgs a)
         unsigned r8 = 0, g8 = 0, b8 = 0, mm = 0;
         if (u.valid && t != 0xFFFFFFFFu) {
             const Tri T = setup(pv, m, static_cast<int>(t));
-            double e0, e1, e2;
-            edges(edge_set(T), static_cast<double>(i * kSub + kHalf), static_cast<double>(j * kSub + kHalf), e0, e1, e2);
-            const double inv_area = 1.0 / static_cast<double>(T.area2);
-            const double l0 = e0 * inv_area, l1 = e1 * inv_area, l2 = e2 * inv_area;
-            const double q0 = l0 * T.w0, q1 = l1 * T.w1, q2 = l2 * T.w2;       // T.w* = 1/w: perspective-correct weights
+            double q0, q1, q2;                               // perspective-correct weights (not normalised)
+            int i0, i1, i2;
+            if (T.ok) {
+                double e0, e1, e2;
+                edges(edge_set(T), static_cast<double>(i * kSub + kHalf), static_cast<double>(j * kSub + kHalf), e0, e1, e2);
+                const double inv_area = 1.0 / static_cast<double>(T.area2);
+                const double l0 = e0 * inv_area, l1 = e1 * inv_area, l2 = e2 * inv_area;
+                q0 = l0 * T.w0; q1 = l1 * T.w1; q2 = l2 * T.w2;                  // T.w* = 1/w
+                i0 = T.i0; i1 = T.i1; i2 = T.i2;
+            } else {                                         // near-plane straddler: the homogeneous weights are the perspective-correct ones
+                double q[3]; int idx[3];
+                resolve_straddler(u, m, static_cast<int>(t), i, j, q, idx);
+                q0 = q[0]; q1 = q[1]; q2 = q[2]; i0 = idx[0]; i1 = idx[1]; i2 = idx[2];
+            }
             const double rq = 1.0 / ((q0 + q1) + q2);
             double pos[3], nrm[3], col[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                pos[c] = ((q0 * static_cast<double>(m.pos[3 * T.i0 + c]) + q1 * static_cast<double>(m.pos[3 * T.i1 + c])) + q2 * static_cast<double>(m.pos[3 * T.i2 + c])) * rq;
-                nrm[c] = ((q0 * static_cast<double>(m.nrm[3 * T.i0 + c]) + q1 * static_cast<double>(m.nrm[3 * T.i1 + c])) + q2 * static_cast<double>(m.nrm[3 * T.i2 + c])) * rq;
-                const double c0 = static_cast<float>(m.col[3 * T.i0 + c] / 255.0), c1 = static_cast<float>(m.col[3 * T.i1 + c] / 255.0), c2 = static_cast<float>(m.col[3 * T.i2 + c] / 255.0);
+                pos[c] = ((q0 * static_cast<double>(m.pos[3 * i0 + c]) + q1 * static_cast<double>(m.pos[3 * i1 + c])) + q2 * static_cast<double>(m.pos[3 * i2 + c])) * rq;
+                nrm[c] = ((q0 * static_cast<double>(m.nrm[3 * i0 + c]) + q1 * static_cast<double>(m.nrm[3 * i1 + c])) + q2 * static_cast<double>(m.nrm[3 * i2 + c])) * rq;
+                const double c0 = static_cast<float>(m.col[3 * i0 + c] / 255.0), c1 = static_cast<float>(m.col[3 * i1 + c] / 255.0), c2 = static_cast<float>(m.col[3 * i2 + c] / 255.0);
                 col[c] = ((q0 * c0 + q1 * c1) + q2 * c2) * rq;
             }
             const double x0 = (-u.light[0]) - pos[0], x1 = (-u.light[1]) - pos[1], x2 = (-u.light[2]) - pos[2];

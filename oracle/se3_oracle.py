@@ -354,7 +354,42 @@ def _project_vertices(pos32, view32, proj32, size):
         yw = (c[1] / w + 1.0) * (size * 0.5)
         zw = (c[2] / w + 1.0) * 0.5
         X = np.rint(xw * SUBPIXEL); Y = np.rint(yw * SUBPIXEL)
-    return X, Y, zw, w
+    return X, Y, zw, w, c
+
+
+def _near_clipped_box(cl, size):
+    """Pixel box (ia, ib, ja, jb) that contains the part of a clip-space triangle in front of the near plane (z + w >= 0),
+    one pixel of margin; the whole window when the arithmetic does not stay finite.  Only has to be conservative."""
+    pts = []
+    for a in range(3):
+        b = (a + 1) % 3
+        da, db = cl[a][2] + cl[a][3], cl[b][2] + cl[b][3]
+        if da >= 0: pts.append((cl[a][0], cl[a][1], cl[a][3]))
+        if (da >= 0) != (db >= 0):
+            s = da / (da - db)
+            pts.append(tuple(cl[a][k] + s * (cl[b][k] - cl[a][k]) for k in (0, 1, 3)))
+    if not pts: return None
+    with np.errstate(all='ignore'):
+        xs = [(x / w + 1.0) * (size * 0.5) for x, y, w in pts]; ys = [(y / w + 1.0) * (size * 0.5) for x, y, w in pts]
+    if not all(np.isfinite(v) and abs(v) < 1e9 for v in xs + ys): return 0, size - 1, 0, size - 1
+    return (max(0, int(np.floor(min(xs))) - 1), min(size - 1, int(np.ceil(max(xs))) + 1),
+            max(0, int(np.floor(min(ys))) - 1), min(size - 1, int(np.ceil(max(ys))) + 1))
+
+
+def _straddler_setup(clip, i0, i1, i2, size):
+    """Adjugate of M = [[x0 x1 x2], [y0 y1 y2], [w0 w1 w2]] (clip space), fixed association (mirrored by render.cu)."""
+    cl = [tuple(float(clip[k][i]) for k in range(4)) for i in (i0, i1, i2)]
+    if not all(np.isfinite(v) for c in cl for v in c): return None
+    if all(c[2] + c[3] < 0 for c in cl): return None                                 # wholly on the eye side of the near plane
+    box = _near_clipped_box(cl, size)
+    if box is None or box[0] > box[1] or box[2] > box[3]: return None
+    (x0, y0, z0, w0), (x1, y1, z1, w1), (x2, y2, z2, w2) = cl
+    A = (y1 * w2 - y2 * w1, y2 * w0 - y0 * w2, y0 * w1 - y1 * w0)
+    B = (x2 * w1 - x1 * w2, x0 * w2 - x2 * w0, x1 * w0 - x0 * w1)
+    C = (x1 * y2 - x2 * y1, x2 * y0 - x0 * y2, x0 * y1 - x1 * y0)
+    det = (x0 * A[0] + x1 * A[1]) + x2 * A[2]
+    if det == 0 or not np.isfinite(det): return None
+    return dict(idx=(i0, i1, i2), A=A, B=B, C=C, idet=1.0 / det, z=(z0, z1, z2), w=(w0, w1, w2), box=box)
 
 
 def render_window(ob2cam, K, object_width, mesh, size=176, uniforms=None):
@@ -364,15 +399,37 @@ def render_window(ob2cam, K, object_width, mesh, size=176, uniforms=None):
     rgb = np.zeros((size, size, 3), np.uint8); depth = np.zeros((size, size), np.uint16)
     if u['right'] == u['left'] or u['top'] == u['bottom'] or not np.all(np.isfinite(u['proj32'])):
         return rgb, depth
-    X, Y, zw, w = _project_vertices(mesh['pos'], u['view32'], u['proj32'], size)
+    X, Y, zw, w, clip = _project_vertices(mesh['pos'], u['view32'], u['proj32'], size)
     key = np.full((size, size), (np.uint64(0x3F800000) << np.uint64(32)) | np.uint64(0xFFFFFFFF), np.uint64)   # depth 1.0, no triangle
     faces = mesh['faces']
     lim = 1 << 25                      # render.cu evaluates the edge functions in float64: exact below 2^25 sub-pixels
     setups = {}
     for t in range(len(faces)):
         i0, i1, i2 = (int(a) for a in faces[t])
-        if not (w[i0] > 1e-6 and w[i1] > 1e-6 and w[i2] > 1e-6): continue               # no near-plane polygon clipping
-        if not all(np.isfinite(a) and abs(a) < lim for a in (X[i0], Y[i0], X[i1], Y[i1], X[i2], Y[i2])): continue
+        usable = all(w[i] > 1e-6 and np.isfinite(X[i]) and np.isfinite(Y[i]) and abs(X[i]) < lim and abs(Y[i]) < lim for i in (i0, i1, i2))
+        if not usable:
+            # A vertex at or behind the eye plane (or projected out of the exact-integer range): the screen-space set-up does
+            # not exist.  GL clips such a triangle against the near plane; here it is rasterised in homogeneous coordinates
+            # (weights beta = M^-1 (px, py, 1) with M the clip-space (x, y, w) columns -- inside iff all beta >= 0) and the
+            # per-pixel depth test 0 <= z_window cuts it at the near plane, which is the same set of fragments.
+            st = _straddler_setup(clip, i0, i1, i2, size)
+            if st is None: continue
+            ia, ib, ja, jb = st['box']
+            px = ((2 * np.arange(ia, ib + 1) + 1 - size).astype(np.float64) / float(size))[None, :]
+            py = ((2 * np.arange(ja, jb + 1) + 1 - size).astype(np.float64) / float(size))[:, None]
+            with np.errstate(all='ignore'):
+                beta = [((st['A'][k] * px + st['B'][k] * py) + st['C'][k]) * st['idet'] for k in range(3)]
+                zc = (beta[0] * st['z'][0] + beta[1] * st['z'][1]) + beta[2] * st['z'][2]
+                wc = (beta[0] * st['w'][0] + beta[1] * st['w'][1]) + beta[2] * st['w'][2]
+                z32 = ((zc / wc + 1.0) * 0.5).astype(np.float32)
+                ok = (beta[0] >= 0) & (beta[1] >= 0) & (beta[2] >= 0) & (z32 >= 0) & (z32 < 1)
+            if not ok.any(): continue
+            k = (z32.view(np.uint32).astype(np.uint64) << np.uint64(32)) | np.uint64(t)
+            sub = key[ja:jb + 1, ia:ib + 1]
+            upd = ok & (k < sub)
+            sub[upd] = k[upd]
+            setups[t] = st
+            continue
         x0, y0, x1, y1, x2, y2 = (int(a) for a in (X[i0], Y[i0], X[i1], Y[i1], X[i2], Y[i2]))
         area2 = (x1 - x0) * (y2 - y0) - (x2 - x0) * (y1 - y0)
         if area2 == 0: continue
@@ -408,14 +465,20 @@ def render_window(ob2cam, K, object_width, mesh, size=176, uniforms=None):
     half = SUBPIXEL // 2
     for j, i in zip(*np.nonzero((key & np.uint64(0xFFFFFFFF)) != np.uint64(0xFFFFFFFF))):
         t = int(key[j, i] & np.uint64(0xFFFFFFFF))
-        i0, i1, i2, x0, y0, x1, y1, x2, y2, area2 = setups[t]
-        cx, cy = i * SUBPIXEL + half, j * SUBPIXEL + half
-        e0 = (x2 - x1) * (cy - y1) - (y2 - y1) * (cx - x1)
-        e1 = (x0 - x2) * (cy - y2) - (y0 - y2) * (cx - x2)
-        e2 = (x1 - x0) * (cy - y0) - (y1 - y0) * (cx - x0)
-        inv_area = 1.0 / float(area2)
-        l0, l1, l2 = float(e0) * inv_area, float(e1) * inv_area, float(e2) * inv_area
-        q0, q1, q2 = l0 * (1.0 / w[i0]), l1 * (1.0 / w[i1]), l2 * (1.0 / w[i2])
+        if isinstance(setups[t], dict):                                                  # near-plane straddler: homogeneous weights
+            st = setups[t]
+            i0, i1, i2 = st['idx']
+            px, py = float(2 * i + 1 - size) / float(size), float(2 * j + 1 - size) / float(size)
+            q0, q1, q2 = (((st['A'][k] * px + st['B'][k] * py) + st['C'][k]) * st['idet'] for k in range(3))
+        else:
+            i0, i1, i2, x0, y0, x1, y1, x2, y2, area2 = setups[t]
+            cx, cy = i * SUBPIXEL + half, j * SUBPIXEL + half
+            e0 = (x2 - x1) * (cy - y1) - (y2 - y1) * (cx - x1)
+            e1 = (x0 - x2) * (cy - y2) - (y0 - y2) * (cx - x2)
+            e2 = (x1 - x0) * (cy - y0) - (y1 - y0) * (cx - x0)
+            inv_area = 1.0 / float(area2)
+            l0, l1, l2 = float(e0) * inv_area, float(e1) * inv_area, float(e2) * inv_area
+            q0, q1, q2 = l0 * (1.0 / w[i0]), l1 * (1.0 / w[i1]), l2 * (1.0 / w[i2])
         rq = 1.0 / ((q0 + q1) + q2)
         def interp(a0, a1, a2): return ((q0 * a0 + q1 * a1) + q2 * a2) * rq
         pos = [interp(float(mesh['pos'][i0, c]), float(mesh['pos'][i1, c]), float(mesh['pos'][i2, c])) for c in range(3)]

@@ -564,6 +564,29 @@ def test_render_bit_exact_vs_oracle(pkg, synth, eng):
         assert np.array_equal(rgb, rrgb), 'level %d: %d colour values differ' % (level, (rgb != rrgb).sum())
 
 
+def test_render_near_plane_clipping_bit_exact(pkg, synth, eng):
+    """Models that pass through the eye plane: triangles with vertices at w <= 0 are cut at the near plane (homogeneous path in
+    render.cu) -- same pixels, depths and colours as the numpy restatement, whose clipped surface tests/test_oracle_golden.py
+    checks against ray casting."""
+    import cv2
+    K = synth.CAMERA_K
+    poses = []
+    for rvec, tr in (((0.05, 0.02, 0.1), (0.045, 0.0, 0.45)), ((0.0, 0.08, 0.5), (0.045, 0.0, 0.45)), ((0.1, -0.05, 1.0), (0.06, 0.0, 0.45)),
+                     ((0.3, 0.2, 0.1), (0.02, -0.01, 0.45)), ((1.2, 0.1, -0.4), (0.0, 0.04, 0.4))):
+        p = np.eye(4); p[:3, :3] = cv2.Rodrigues(np.array(rvec))[0]; p[:3, 3] = tr
+        poses.append(p)
+    poses = np.stack(poses)
+    for level, mid in ((1, 4), (2, 5)):
+        mesh = dict(synth.mesh(level, seed=2))
+        mesh['pos'] = (mesh['pos'] * np.array([1.0, 1.0, 24.0], np.float32)).astype(np.float32)
+        zcam = mesh['pos'].astype(np.float64) @ poses[0][2, :3] + poses[0][2, 3]
+        assert zcam.min() < -0.05 and zcam.max() > 0.8
+        rgb, dep, rrgb, rdep = _render_both(eng, synth, mesh, poses, 200.0, mid)
+        assert (dep > 0).sum() > 5000
+        assert np.array_equal(dep, rdep), 'level %d: %d depth pixels differ' % (level, (dep != rdep).sum())
+        assert np.array_equal(rgb, rrgb), 'level %d: %d colour values differ' % (level, (rgb != rrgb).sum())
+
+
 def test_render_edge_cases(pkg, synth, eng):
     dev = eng.device
     mesh = synth.mesh(2, seed=0)

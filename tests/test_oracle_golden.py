@@ -187,16 +187,9 @@ def test_fill_depth_oracle_vs_reference(golden_dir):
         assert not np.array_equal(g['out_m_%s_ex' % k], g['out_m_' + k]) and not np.array_equal(g['out_m_%s_ga' % k], g['out_m_' + k])
 
 
-def test_render_oracle_vs_ray_casting(synth):
-    """Independent geometric cross-check of the rasterisation restatement (no GL here): cast a pinhole ray through every pixel
-    centre of the crop window and intersect it with the posed triangles (Moeller-Trumbore, float64).  The rasteriser must see the
-    same surface: identical coverage away from silhouette edges, depth within 1 mm (uint16 truncation + float32 z-buffer)."""
-    mesh = synth.mesh(1, seed=2)                                   # 80 faces
-    K = synth.CAMERA_K
-    pose = synth.raw_poses(3, seed=21)[2]
-    u = O.render_uniforms(pose, K, 200.0)
-    rgb, dep = O.render_window(pose, K, 200.0, mesh)
-    S = 176
+def _ray_cast_depth(mesh, pose, K, u, S=176):
+    """Pinhole ray through every pixel centre of the crop window against the posed triangles (Moeller-Trumbore, float64);
+    -> camera-space depth (S, S), inf where nothing is hit between the near (0.1 m) and far (2 m) planes."""
     cols = u['left'] + (np.arange(S) + 0.5) * (u['right'] - u['left']) / S
     # the window rows live in the y-flipped image v' = 2*cy - v (compute_bbox with scale -1000); array row 0 is v' = bottom
     vflip = u['bottom'] - (np.arange(S) + 0.5) * (u['bottom'] - u['top']) / S
@@ -218,11 +211,57 @@ def test_render_oracle_vs_ray_casting(synth):
             t = (qv @ e2) * inv
         hit = (np.abs(det) > 1e-15) & (uu >= 0) & (vv >= 0) & (uu + vv <= 1) & (t > 0.1) & (t < 2.0)
         best = np.where(hit & (t < best), t, best)
-    z = best.reshape(S, S)                                          # direction z-component is 1: t is the camera-space depth
-    ray_fg, ras_fg = np.isfinite(z), dep > 0
-    assert ras_fg.sum() > 3000
+    return best.reshape(S, S)                                       # direction z-component is 1: t is the camera-space depth
+
+
+def _assert_same_surface(dep, z, min_pixels):
     import cv2
+    ray_fg, ras_fg = np.isfinite(z), dep > 0
+    assert ras_fg.sum() > min_pixels
     edge = cv2.dilate(ray_fg.astype(np.uint8), np.ones((3, 3), np.uint8)) != cv2.erode(ray_fg.astype(np.uint8), np.ones((3, 3), np.uint8))
     assert (ray_fg == ras_fg)[~edge].all() and (ray_fg != ras_fg).sum() < 0.02 * ras_fg.sum()
     both = ray_fg & ras_fg & ~edge
     assert np.abs(dep[both].astype(np.float64) - z[both] * 1000).max() < 1.5
+
+
+def test_render_oracle_vs_ray_casting(synth):
+    """Independent geometric cross-check of the rasterisation restatement (no GL here): cast a pinhole ray through every pixel
+    centre of the crop window and intersect it with the posed triangles.  The rasteriser must see the same surface: identical
+    coverage away from silhouette edges, depth within 1 mm (uint16 truncation + float32 z-buffer)."""
+    mesh = synth.mesh(1, seed=2)                                   # 80 faces
+    K = synth.CAMERA_K
+    pose = synth.raw_poses(3, seed=21)[2]
+    u = O.render_uniforms(pose, K, 200.0)
+    rgb, dep = O.render_window(pose, K, 200.0, mesh)
+    _assert_same_surface(dep, _ray_cast_depth(mesh, pose, K, u), 3000)
+
+
+def _long_mesh(synth, level, seed, stretch=24.0):
+    """A synthetic model stretched along its z axis until it reaches from behind the camera to well in front of it."""
+    mesh = dict(synth.mesh(level, seed=seed))
+    mesh['pos'] = (mesh['pos'] * np.array([1.0, 1.0, stretch], np.float32)).astype(np.float32)
+    return mesh
+
+
+def test_render_oracle_near_plane_clipping_vs_ray_casting(synth):
+    """Triangles with vertices behind the eye plane (w <= 0) and in front of the near plane are cut AT the near plane, as GL's
+    polygon clipping does: the visible part must coincide with what rays limited to t in (0.1 m, 2 m) see."""
+    import cv2
+    K = synth.CAMERA_K
+    for level, rvec, tr in ((1, (0.05, 0.02, 0.1), (0.045, 0.0, 0.45)), (2, (0.0, 0.08, 0.5), (0.045, 0.0, 0.45))):
+        mesh = _long_mesh(synth, level, seed=2)
+        pose = np.eye(4); pose[:3, :3] = cv2.Rodrigues(np.array(rvec))[0]; pose[:3, 3] = tr
+        zcam = mesh['pos'].astype(np.float64) @ pose[2, :3] + pose[2, 3]
+        assert zcam.min() < -0.05 and zcam.max() > 0.8                      # the model really passes through the eye plane
+        f = mesh['faces']; zf = zcam[f]
+        assert ((zf.min(1) <= 1e-6) & (zf.max(1) > 0.1)).sum() >= 4          # ... and some triangles straddle it
+        u = O.render_uniforms(pose, K, 200.0)
+        rgb, dep = O.render_window(pose, K, 200.0, mesh)
+        z = _ray_cast_depth(mesh, pose, K, u)
+        _assert_same_surface(dep, z, 3000)
+        # the test bites: without the straddling triangles a visible part of the surface would be missing
+        kept = dict(mesh); kept['faces'] = f[~((zf.min(1) <= 1e-6) & (zf.max(1) > 0.1))]
+        with np.errstate(invalid='ignore'):
+            lost = np.isfinite(z) & ~(np.abs(z - _ray_cast_depth(kept, pose, K, u)) < 1e-6)   # a closed model: the far side shows instead
+        assert lost.sum() > 300 and (dep[lost] > 0).mean() > 0.98
+        assert rgb[dep > 0].max() > 0
