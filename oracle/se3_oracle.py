@@ -319,6 +319,9 @@ def vocap(rec):
 # snapping: 8 bits here; tie rule on edges: top-left; depth-buffer format: float32 here).  The uniforms (window,
 # projection matrix, view matrix, light direction) ARE pinned against the reference's own code
 # (tests/golden/golden_render.npz, oracle/make_golden.py).
+# Near-plane clipping (GL clips polygons at z_clip = -w): triangles in front of the eye are cut per pixel by the depth test;
+# triangles crossing the eye plane take the homogeneous path in render_window (_straddler_setup).  The geometry of both is
+# cross-checked against ray casting in tests/test_oracle_golden.py.
 # =============================================================================================
 GLCAM_IN_CVCAM = np.diag([1.0, -1.0, -1.0, 1.0])
 NEAR_PLANE, FAR_PLANE = 0.1, 2.0
