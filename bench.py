@@ -31,7 +31,7 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 FLOP_PER_PAIR = 5_527_109_632            # 17 convs, SURVEY.md 8d / BASELINE.md section 2
-N_INPUT_SETS = 16                        # rotated so the inputs of consecutive steps differ
+MAX_INPUT_SETS = 16                      # inputs rotate so consecutive steps differ; at most this many distinct sets
 TN, RN = 0.03, 5 * np.pi / 180
 
 
@@ -231,7 +231,10 @@ def main():
     for wid in range(1, G):
         eng.load_state_dict(synth.make_state_dict(wid), wid); eng.set_stats(mean, std, wid)
 
-    # ---- synthetic inputs, N_INPUT_SETS distinct sets resident in HBM -------
+    # ---- synthetic inputs, distinct sets resident in HBM -------------------------
+    # One set per warm-up step (at most MAX_INPUT_SETS): the library keeps one CUDA graph per distinct set of step arguments
+    # (the device pointers are part of it), so every set's graph is recorded during warm-up and the timed steps only replay.
+    N_INPUT_SETS = min(MAX_INPUT_SETS, max(args.warmup, 3))
     frames, sets = [], []
     for k in range(N_INPUT_SETS):
         seed = 1000 * rank + k
@@ -335,7 +338,7 @@ def main():
     if not args.no_alt:
         for prec in [q for q in ('tf32', 'bf16x3', 'bf16') if q != args.precision]:
             tracker.precision = prec
-            for k in range(3):
+            for k in range(N_INPUT_SETS):          # every input set once: its CUDA graph is recorded here, not in the timed steps
                 step(k)
             sync_all()
             ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(args.steps, 20))]
@@ -364,7 +367,7 @@ def main():
         def step21(k):
             d = sets[k % N_INPUT_SETS][1]
             return tr21.step(d['rgb'], d['depth'], d['poses'], d['rgbA'], d['depthA'], gather=(world > 1))
-        for k in range(3):
+        for k in range(N_INPUT_SETS):          # every input set once: its CUDA graph is recorded here, not in the timed steps
             step21(k)
         sync_all()
         n21 = min(args.steps, 50)
@@ -460,7 +463,7 @@ def main():
             d = sets[k % N_INPUT_SETS][1]
             eng.render(synth.CAMERA_K, d['poses'], ow, None, rgbA_buf, depA_buf)
             return tracker.step(d['rgb'], d['depth'], d['poses'], rgbA_buf, depA_buf, gather=False)
-        for k in range(3):
+        for k in range(N_INPUT_SETS):          # every input set once: its CUDA graph is recorded here, not in the timed steps
             render_step(k)
         sync_all()
         rsteps = min(args.steps, 20)
