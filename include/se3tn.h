@@ -204,6 +204,19 @@ int se3tn_set_mesh(se3tn_ctx* ctx, int mesh_id, const float* pos, const float* n
 int se3tn_render(se3tn_ctx* ctx, const double* K, const double* poses, const double* object_width,
                  const int32_t* mesh_ids, int n, uint8_t* rgbA, uint16_t* depthA, void* stream);
 
+/* The same for either of the reference's two producers of input A (predict.py:161-182 picks one from dataset_info['renderer']):
+ *   SE3TN_RENDER_VISPY     what se3tn_render does (H, W ignored).
+ *   SE3TN_RENDER_PYRENDER  offscreen_renderer.py:47-83 + predict.py:210-214: the model is drawn into the WHOLE H x W camera image
+ *                          (pinhole K, near 0.1 m, far 2 m, ambient light only: unlit vertex colours), the metric depth becomes
+ *                          uint16 mm, and crop_bbox (Utils.py:320-359: window from compute_bbox, zero outside the image, nearest-
+ *                          neighbour resize to 176 x 176) cuts the track's window out of both.  Only the camera pixels the resize
+ *                          picks are ever shaded; the full image is never materialised.  Per-fragment texture lookups of a
+ *                          textured .obj are replaced by per-vertex colours. */
+#define SE3TN_RENDER_VISPY 0
+#define SE3TN_RENDER_PYRENDER 1
+int se3tn_render_ex(se3tn_ctx* ctx, const double* K, const double* poses, const double* object_width,
+                    const int32_t* mesh_ids, int n, int mode, int H, int W, uint8_t* rgbA, uint16_t* depthA, void* stream);
+
 /* ---- live-sensor depth (SURVEY.md 8(f) "next" row 4) ------------------------------------------------------ */
 
 /* fill_depth as the reference's ROS node applies it to every depth image before tracking (reference Utils.py:455-514,
@@ -221,6 +234,18 @@ int se3tn_fill_depth(se3tn_ctx* ctx, const uint16_t* depth_mm, int H, int W, dou
 enum { SE3TN_BLUR_BILATERAL = 0, SE3TN_BLUR_GAUSSIAN = 1 };
 int se3tn_fill_depth_ex(se3tn_ctx* ctx, const uint16_t* depth_mm, int H, int W, double max_depth, int extrapolate, int blur_type,
                         uint16_t* out_mm, float* out_m, void* stream);
+
+/* The reference's own calling pattern as ONE call (Tracker.on_track, predict.py:217-296: numpy arrays in, numpy pose out):
+ * every pointer is HOST memory.  The frame's crop-window rectangle, the poses, widths, input A and the ids are staged
+ * through context-owned pinned memory into context-owned device buffers (stable addresses, so the step's CUDA graph is
+ * replayed), se3tn_track_batch runs on them, and the call returns once poses_out (n x 16 doubles; out_trans / out_rot n x 3
+ * floats, nullable) hold the result -- it synchronises `stream`.  frame_rgb uint8 (H,W,3), frame_depth uint16 (H,W) mm,
+ * K = fx fy cx cy, poses double (n,16), object_width double (n) mm, rgbA uint8 (n,176,176,3), depthA uint16 (n,176,176),
+ * weight_ids int32 (n) or NULL (all tracks use set 0).  Errors as se3tn_track_batch. */
+int se3tn_track_host(se3tn_ctx* ctx, const uint8_t* frame_rgb, const uint16_t* frame_depth, int H, int W, const double* K,
+                     const double* poses, const double* object_width, const uint8_t* rgbA, const uint16_t* depthA,
+                     const int32_t* weight_ids, int n, double trans_normalizer, double rot_normalizer, int precision,
+                     double* poses_out, float* out_trans, float* out_rot, void* stream);
 
 /* ---- introspection (tests / profiling) -------------------------------------------------------- */
 

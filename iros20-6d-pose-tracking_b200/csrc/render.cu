@@ -43,8 +43,12 @@ struct Uniforms {
     double P00, P02, P11, P12, P22, P23;   // projection (float32 values); P32 = -1
     double A, B;             // projection_matrix[2][2], [3][2] in float64 (depth linearisation)
     double light[3];
-    int valid;
+    double hx, hy;           // half the viewport in pixels: window x = (ndc + 1) * hx
+    int valid, mode;         // mode 0: the 176 x 176 crop window IS the viewport (vispy); 1: the whole camera image is (pyrender)
+    int vw, vh;              // viewport in pixels
+    int top, left, ch, cw;   // mode 1: crop window in image pixels (rows from the top), what crop_bbox cuts out of the full render
 };
+static_assert(sizeof(Uniforms) % sizeof(double) == 0, "Uniforms is copied as doubles");
 
 __device__ __forceinline__ long long floor_div(long long a, long long b) {             // b > 0
     long long q = a / b;
@@ -74,7 +78,7 @@ __device__ __forceinline__ Vtx project(const Uniforms& u, const float* __restric
     const double c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3];
     Vtx r;
     r.w = c3;
-    const double xw = (c0 / c3 + 1.0) * (kRS * 0.5), yw = (c1 / c3 + 1.0) * (kRS * 0.5);
+    const double xw = (c0 / c3 + 1.0) * u.hx, yw = (c1 / c3 + 1.0) * u.hy;
     r.zw = (c2 / c3 + 1.0) * 0.5;
     const double X = rint(xw * kSub), Y = rint(yw * kSub);
     const double lim = 33554432.0;                   // 2^25 sub-pixels: every edge-function product stays below 2^53, exact in float64
@@ -138,8 +142,13 @@ __device__ __forceinline__ void edges(const EdgeSet& E, double cx, double cy, do
 __device__ __forceinline__ bool top_left(long long dx, long long dy) { return dy < 0 || (dy == 0 && dx < 0); }
 
 // one pixel centre against one triangle.  Rows are interleaved over the four CTAs of a track: this CTA owns rows j = 4*jj + band.
-__device__ __forceinline__ void raster_pixel(const Tri& T, const EdgeSet& E, double inv_area, int t, int i, int j, bool tl0, bool tl1, bool tl2, unsigned long long* keys) {
-    const double cx = static_cast<double>(i * kSub + kHalf), cy = static_cast<double>(j * kSub + kHalf);
+// The sample of output pixel (i, j) sits at sub-pixel position (xs[i], ys[j]) of the viewport: the pixel's own centre in mode 0, the
+// centre of the camera-image pixel crop_bbox's nearest-neighbour resize picks in mode 1 (outside the viewport: no fragment).
+struct Samples { const int* xs; const int* ys; int vw, vh; };
+__device__ __forceinline__ void raster_pixel(const Tri& T, const EdgeSet& E, double inv_area, int t, int i, int j, bool tl0, bool tl1, bool tl2, const Samples& sm, unsigned long long* keys) {
+    const int sx = sm.xs[i], sy = sm.ys[j];
+    if (static_cast<unsigned>(sx >> 8) >= static_cast<unsigned>(sm.vw) || static_cast<unsigned>(sy >> 8) >= static_cast<unsigned>(sm.vh)) return;
+    const double cx = static_cast<double>(sx), cy = static_cast<double>(sy);
     double e0, e1, e2;
     edges(E, cx, cy, e0, e1, e2);
     if (!((e0 > 0 || (e0 == 0 && tl0)) && (e1 > 0 || (e1 == 0 && tl1)) && (e2 > 0 || (e2 == 0 && tl2)))) return;
@@ -181,7 +190,7 @@ __device__ __noinline__ void straddler_setup(const Uniforms& u, const MeshDev& m
     double mnx = 1e300, mxx = -1e300, mny = 1e300, mxy = -1e300;
     bool any = false, wild = false;
     auto take = [&](double x, double y, double w) {
-        const double xs = (x / w + 1.0) * (kRS * 0.5), ys = (y / w + 1.0) * (kRS * 0.5);
+        const double xs = (x / w + 1.0) * u.hx, ys = (y / w + 1.0) * u.hy;
         if (!(isfinite(xs) && isfinite(ys) && fabs(xs) < 1e9 && fabs(ys) < 1e9)) wild = true;
         mnx = fmin(mnx, xs); mxx = fmax(mxx, xs); mny = fmin(mny, ys); mxy = fmax(mxy, ys);
         any = true;
@@ -197,10 +206,10 @@ __device__ __noinline__ void straddler_setup(const Uniforms& u, const MeshDev& m
         }
     }
     if (!any) return;
-    if (wild) { S.ia = 0; S.ib = kRS - 1; S.ja = 0; S.jb = kRS - 1; }
+    if (wild) { S.ia = 0; S.ib = u.vw - 1; S.ja = 0; S.jb = u.vh - 1; }          // viewport pixels
     else {
-        S.ia = max(0, static_cast<int>(floor(mnx)) - 1); S.ib = min(kRS - 1, static_cast<int>(ceil(mxx)) + 1);
-        S.ja = max(0, static_cast<int>(floor(mny)) - 1); S.jb = min(kRS - 1, static_cast<int>(ceil(mxy)) + 1);
+        S.ia = max(0, static_cast<int>(floor(mnx)) - 1); S.ib = min(u.vw - 1, static_cast<int>(ceil(mxx)) + 1);
+        S.ja = max(0, static_cast<int>(floor(mny)) - 1); S.jb = min(u.vh - 1, static_cast<int>(ceil(mxy)) + 1);
     }
     if (S.ia > S.ib || S.ja > S.jb) return;
     const double x0 = cl[0][0], y0 = cl[0][1], w0 = cl[0][3], x1 = cl[1][0], y1 = cl[1][1], w1 = cl[1][3], x2 = cl[2][0], y2 = cl[2][1], w2 = cl[2][3];
@@ -215,16 +224,19 @@ __device__ __noinline__ void straddler_setup(const Uniforms& u, const MeshDev& m
     S.ok = true;
 }
 
-__device__ __forceinline__ void straddler_weights(const Strad& S, int i, int j, double& b0, double& b1, double& b2) {
-    const double px = static_cast<double>(2 * i + 1 - kRS) / static_cast<double>(kRS), py = static_cast<double>(2 * j + 1 - kRS) / static_cast<double>(kRS);
+// (i, j): VIEWPORT pixel (its centre in NDC is ((2i + 1 - vw) / vw, (2j + 1 - vh) / vh))
+__device__ __forceinline__ void straddler_weights(const Strad& S, int i, int j, int vw, int vh, double& b0, double& b1, double& b2) {
+    const double px = static_cast<double>(2 * i + 1 - vw) / static_cast<double>(vw), py = static_cast<double>(2 * j + 1 - vh) / static_cast<double>(vh);
     b0 = ((S.A[0] * px + S.B[0] * py) + S.C[0]) * S.idet;
     b1 = ((S.A[1] * px + S.B[1] * py) + S.C[1]) * S.idet;
     b2 = ((S.A[2] * px + S.B[2] * py) + S.C[2]) * S.idet;
 }
 
-__device__ __forceinline__ void straddler_pixel(const Strad& S, int t, int i, int j, unsigned long long* keys) {
+__device__ __forceinline__ void straddler_pixel(const Strad& S, int t, int i, int j, const Samples& sm, unsigned long long* keys) {
+    const int ipx = sm.xs[i] >> 8, jpx = sm.ys[j] >> 8;
+    if (static_cast<unsigned>(ipx) >= static_cast<unsigned>(sm.vw) || static_cast<unsigned>(jpx) >= static_cast<unsigned>(sm.vh)) return;
     double b0, b1, b2;
-    straddler_weights(S, i, j, b0, b1, b2);
+    straddler_weights(S, ipx, jpx, sm.vw, sm.vh, b0, b1, b2);
     if (!(b0 >= 0.0 && b1 >= 0.0 && b2 >= 0.0)) return;
     const double zc = (b0 * S.z[0] + b1 * S.z[1]) + b2 * S.z[2], wc = (b0 * S.w[0] + b1 * S.w[1]) + b2 * S.w[2];
     const float z32 = static_cast<float>((zc / wc + 1.0) * 0.5);
@@ -234,29 +246,42 @@ __device__ __forceinline__ void straddler_pixel(const Strad& S, int t, int i, in
 }
 
 // out of line (own stack frame): the ordinary triangles' register allocation must not pay for the rare path
-__device__ __noinline__ void raster_straddler(const Uniforms& u, const MeshDev& m, int t, int band, int lane, unsigned long long* keys) {
+// output pixels whose sample lies in [lo, hi] (sub-pixel units): tab is non-decreasing
+__device__ __forceinline__ int first_at_least(const int* tab, long long v) {       // first index with tab[i] >= v (kRS if none)
+    int lo = 0, hi = kRS;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (tab[mid] < v) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+__device__ __forceinline__ int last_at_most(const int* tab, long long v) {         // last index with tab[i] <= v (-1 if none)
+    int lo = 0, hi = kRS;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (tab[mid] <= v) lo = mid + 1; else hi = mid; }
+    return lo - 1;
+}
+
+__device__ __noinline__ void raster_straddler(const Uniforms& u, const MeshDev& m, int t, int band, int lane, const Samples& sm, unsigned long long* keys) {
     Strad S;
     straddler_setup(u, m, t, S);
     if (!S.ok) return;
-    const int j0 = S.ja + ((band - (S.ja & 3)) & 3);         // first row >= ja that this CTA owns
-    if (j0 > S.jb) return;
-    const int bw = S.ib - S.ia + 1, cnt = bw * ((S.jb - j0) / 4 + 1);
-    for (int k = lane; k < cnt; k += 32) straddler_pixel(S, t, S.ia + k % bw, j0 + 4 * (k / bw), keys);
+    // viewport-pixel box -> output pixels whose sample falls inside it
+    const int ia = first_at_least(sm.xs, static_cast<long long>(S.ia) * kSub), ib = last_at_most(sm.xs, static_cast<long long>(S.ib) * kSub + (kSub - 1));
+    const int ja = first_at_least(sm.ys, static_cast<long long>(S.ja) * kSub), jb = last_at_most(sm.ys, static_cast<long long>(S.jb) * kSub + (kSub - 1));
+    if (ia > ib || ja > jb) return;
+    const int j0 = ja + ((band - (ja & 3)) & 3);             // first row >= ja that this CTA owns
+    if (j0 > jb) return;
+    const int bw = ib - ia + 1, cnt = bw * ((jb - j0) / 4 + 1);
+    for (int k = lane; k < cnt; k += 32) straddler_pixel(S, t, ia + k % bw, j0 + 4 * (k / bw), sm, keys);
 }
 
-__device__ __noinline__ void resolve_straddler(const Uniforms& u, const MeshDev& m, int t, int i, int j, double* q, int* idx) {
+__device__ __noinline__ void resolve_straddler(const Uniforms& u, const MeshDev& m, int t, int ipx, int jpx, double* q, int* idx) {
     Strad S;
     straddler_setup(u, m, t, S);
-    straddler_weights(S, i, j, q[0], q[1], q[2]);
+    straddler_weights(S, ipx, jpx, u.vw, u.vh, q[0], q[1], q[2]);
     idx[0] = S.i[0]; idx[1] = S.i[1]; idx[2] = S.i[2];
 }
 
 __device__ void make_uniforms(const RenderArgs& a, int n, int nf, Uniforms& u) {
         const double* pose = a.poses + n * 16;
         int top, left, ch, cw;
-        bbox_window(pose, a.fx, a.fy, a.cx, a.cy, a.object_width[n], 1000.0, -1000.0, 1000.0, top, left, ch, cw);   // predict.py:202
-        const int right = left + cw, bottom = top + ch;
-        u.valid = (cw != 0 && ch != 0 && nf > 0) ? 1 : 0;
         // view = inv(glcam_in_cvcam) . ob2cam (rows 1, 2 negated), uploaded as float32
         for (int c = 0; c < 4; ++c) {
             u.V[c] = static_cast<double>(static_cast<float>(pose[c]));
@@ -264,6 +289,26 @@ __device__ void make_uniforms(const RenderArgs& a, int n, int nf, Uniforms& u) {
             u.V[8 + c] = static_cast<double>(static_cast<float>(-pose[8 + c]));
         }
         const double nr = 0.1, fr = 2.0;
+        u.mode = a.mode;
+        if (a.mode == 1) {
+            // the whole camera image is the viewport (pyrender IntrinsicsCamera, offscreen_renderer.py:52-53); crop_bbox's window
+            // (predict.py:211: scale (1000, 1000, 1000), no y flip) selects the samples
+            bbox_window(pose, a.fx, a.fy, a.cx, a.cy, a.object_width[n], 1000.0, 1000.0, 1000.0, top, left, ch, cw);
+            u.valid = (cw > 0 && ch > 0 && nf > 0 && a.vw > 0 && a.vh > 0) ? 1 : 0;
+            u.vw = a.vw; u.vh = a.vh; u.hx = a.vw * 0.5; u.hy = a.vh * 0.5;
+            u.top = top; u.left = left; u.ch = ch; u.cw = cw;
+            u.P00 = static_cast<float>(2.0 * a.fx / a.vw); u.P02 = static_cast<float>(1.0 - 2.0 * a.cx / a.vw);
+            u.P11 = static_cast<float>(2.0 * a.fy / a.vh); u.P12 = static_cast<float>(2.0 * a.cy / a.vh - 1.0);
+            u.P22 = static_cast<float>((fr + nr) / (nr - fr)); u.P23 = static_cast<float>((2 * fr * nr) / (nr - fr));
+            u.A = u.B = 0.0; u.light[0] = u.light[1] = u.light[2] = 0.0;
+            if (!(isfinite(u.P00) && isfinite(u.P02) && isfinite(u.P11) && isfinite(u.P12))) u.valid = 0;
+            return;
+        }
+        bbox_window(pose, a.fx, a.fy, a.cx, a.cy, a.object_width[n], 1000.0, -1000.0, 1000.0, top, left, ch, cw);   // predict.py:202
+        const int right = left + cw, bottom = top + ch;
+        u.valid = (cw != 0 && ch != 0 && nf > 0) ? 1 : 0;
+        u.vw = u.vh = kRS; u.hx = u.hy = kRS * 0.5;
+        u.top = top; u.left = left; u.ch = ch; u.cw = cw;
         const double o00 = static_cast<float>(2.0 / (right - left)), o03 = static_cast<float>(static_cast<double>(-(right + left)) / (right - left));
         const double o11 = static_cast<float>(2.0 / (top - bottom)), o13 = static_cast<float>(static_cast<double>(-(top + bottom)) / (top - bottom));
         const double o22 = static_cast<float>(-2.0 / (fr - nr)), o23 = static_cast<float>(-(fr + nr) / (fr - nr));
@@ -324,9 +369,36 @@ render_kernel(RenderArgs a)
     if (threadIdx.x < sizeof(Uniforms) / sizeof(double))
         reinterpret_cast<double*>(&u)[threadIdx.x] = reinterpret_cast<const double*>(a.uniforms + static_cast<size_t>(n) * sizeof(Uniforms))[threadIdx.x];
     __syncthreads();
+    // sample positions of the 176 output columns / rows (rows bottom-up: window y grows with the index)
+    __shared__ int s_xs[kRS], s_ys[kRS];
+    if (threadIdx.x < 2 * kRS) {
+        const int k = threadIdx.x < kRS ? threadIdx.x : threadIdx.x - kRS;
+        const bool isx = threadIdx.x < kRS;
+        int v = k * kSub + kHalf;                               // mode 0: the pixel's own centre
+        if (u.mode == 1 && u.valid) {
+            // crop_bbox (Utils.py:343-344): cv2 INTER_NEAREST source index floor(dst * (1 / (176 / size))), clamped -- as in crop_kernel
+            const int size = isx ? u.cw : u.ch;
+            const int dst = isx ? k : (kRS - 1 - k);            // output row r = 175 - k (the image's rows run top-down)
+            const double inv = 1.0 / (static_cast<double>(kRS) / size);
+            int src = static_cast<int>(floor(dst * inv)); if (src > size - 1) src = size - 1;
+            long long pix = static_cast<long long>(isx ? u.left : u.top) + src;           // camera-image column / row
+            if (!isx) pix = static_cast<long long>(u.vh) - 1 - pix;                        // GL window rows run bottom-up
+            pix = max(-1ll, min(static_cast<long long>(isx ? u.vw : u.vh), pix));         // outside the viewport: no fragment (kept monotone)
+            v = static_cast<int>(pix) * kSub + kHalf;
+        }
+        (isx ? s_xs : s_ys)[k] = v;
+    }
+    __syncthreads();
+    const Samples sm = {s_xs, s_ys, u.vw, u.vh};
+    const bool tables = u.mode != 0;
     const int lane = threadIdx.x & 31;
     // first row >= ja that this CTA owns
     auto first_row = [band](int ja) { return ja + ((band - (ja & 3)) & 3); };
+    // output columns / rows whose sample lies inside [mn, mx] (sub-pixel units)
+    auto span = [&](const int* tab, long long mn, long long mx, int& a0, int& a1) {
+        if (tables) { a0 = first_at_least(tab, mn); a1 = last_at_most(tab, mx); }
+        else { a0 = static_cast<int>(max(0ll, floor_div(mn - kHalf + kSub - 1, kSub))); a1 = static_cast<int>(min(static_cast<long long>(kRS - 1), floor_div(mx - kHalf, kSub))); }
+    };
     if (u.valid) {
         // ---------------- pass 1: visibility ----------------
         const int nf_pad = (m.nf + 31) & ~31;                // whole warps walk the loop (ballots below)
@@ -350,16 +422,17 @@ render_kernel(RenderArgs a)
             nvalid = fetch_rows(t + blockDim.x, ny0, ny1, ny2);
             if (valid) {
                 const long long mny = min(y0, min(y1, y2)), mxy = max(y0, max(y1, y2));
-                const long long ja = max(0ll, floor_div(mny - kHalf + kSub - 1, kSub)), jb = min(static_cast<long long>(kRS - 1), floor_div(mxy - kHalf, kSub));
-                mine = ja <= jb && first_row(static_cast<int>(ja)) <= jb;
+                int ja, jb;
+                span(s_ys, mny, mxy, ja, jb);
+                mine = ja <= jb && first_row(ja) <= jb;
             }
             if (mine) {
                 const Tri T = setup(pv, m, t);
                 if (T.ok) {
                     const long long mnx = min(T.x0, min(T.x1, T.x2)), mxx = max(T.x0, max(T.x1, T.x2));
                     const long long mny = min(T.y0, min(T.y1, T.y2)), mxy = max(T.y0, max(T.y1, T.y2));
-                    const int ia = static_cast<int>(max(0ll, floor_div(mnx - kHalf + kSub - 1, kSub))), ib = static_cast<int>(min(static_cast<long long>(kRS - 1), floor_div(mxx - kHalf, kSub)));
-                    const int ja = static_cast<int>(max(0ll, floor_div(mny - kHalf + kSub - 1, kSub))), jb = static_cast<int>(min(static_cast<long long>(kRS - 1), floor_div(mxy - kHalf, kSub)));
+                    int ia, ib, ja, jb;
+                    span(s_xs, mnx, mxx, ia, ib); span(s_ys, mny, mxy, ja, jb);
                     const int j0 = first_row(ja);
                     if (ia <= ib && j0 <= jb) {
                         if ((ib - ia + 1) * ((jb - j0) / 4 + 1) > kBigBox) big = true;
@@ -368,7 +441,7 @@ render_kernel(RenderArgs a)
                             const double inv_area = 1.0 / static_cast<double>(T.area2);
                             const EdgeSet E = edge_set(T);
                             for (int j = j0; j <= jb; j += 4)
-                                for (int i = ia; i <= ib; ++i) raster_pixel(T, E, inv_area, t, i, j, tl0, tl1, tl2, keys);
+                                for (int i = ia; i <= ib; ++i) raster_pixel(T, E, inv_area, t, i, j, tl0, tl1, tl2, sm, keys);
                         }
                     }
                 }
@@ -380,20 +453,20 @@ render_kernel(RenderArgs a)
                 const Tri T = setup(pv, m, tb);
                 const long long mnx = min(T.x0, min(T.x1, T.x2)), mxx = max(T.x0, max(T.x1, T.x2));
                 const long long mny = min(T.y0, min(T.y1, T.y2)), mxy = max(T.y0, max(T.y1, T.y2));
-                const int ia = static_cast<int>(max(0ll, floor_div(mnx - kHalf + kSub - 1, kSub))), ib = static_cast<int>(min(static_cast<long long>(kRS - 1), floor_div(mxx - kHalf, kSub)));
-                const int ja = static_cast<int>(max(0ll, floor_div(mny - kHalf + kSub - 1, kSub))), jb = static_cast<int>(min(static_cast<long long>(kRS - 1), floor_div(mxy - kHalf, kSub)));
+                int ia, ib, ja, jb;
+                span(s_xs, mnx, mxx, ia, ib); span(s_ys, mny, mxy, ja, jb);
                 const int j0 = first_row(ja);
                 const bool tl0 = top_left(T.x2 - T.x1, T.y2 - T.y1), tl1 = top_left(T.x0 - T.x2, T.y0 - T.y2), tl2 = top_left(T.x1 - T.x0, T.y1 - T.y0);
                 const double inv_area = 1.0 / static_cast<double>(T.area2);
                 const EdgeSet E = edge_set(T);
                 const int bw = ib - ia + 1, cnt = bw * ((jb - j0) / 4 + 1);
-                for (int k = lane; k < cnt; k += 32) raster_pixel(T, E, inv_area, tb, ia + k % bw, j0 + 4 * (k / bw), tl0, tl1, tl2, keys);
+                for (int k = lane; k < cnt; k += 32) raster_pixel(T, E, inv_area, tb, ia + k % bw, j0 + 4 * (k / bw), tl0, tl1, tl2, sm, keys);
             }
             unsigned smask = __ballot_sync(0xffffffffu, strad);
             while (smask) {                                  // near-plane straddlers (rare): the whole warp, homogeneous weights
                 const int src = __ffs(smask) - 1; smask &= smask - 1;
                 const int tb = __shfl_sync(0xffffffffu, t, src);
-                raster_straddler(u, m, tb, band, lane, keys);
+                raster_straddler(u, m, tb, band, lane, sm, keys);
             }
         }
     }
@@ -411,39 +484,56 @@ render_kernel(RenderArgs a)
             int i0, i1, i2;
             if (T.ok) {
                 double e0, e1, e2;
-                edges(edge_set(T), static_cast<double>(i * kSub + kHalf), static_cast<double>(j * kSub + kHalf), e0, e1, e2);
+                edges(edge_set(T), static_cast<double>(s_xs[i]), static_cast<double>(s_ys[j]), e0, e1, e2);
                 const double inv_area = 1.0 / static_cast<double>(T.area2);
                 const double l0 = e0 * inv_area, l1 = e1 * inv_area, l2 = e2 * inv_area;
                 q0 = l0 * T.w0; q1 = l1 * T.w1; q2 = l2 * T.w2;                  // T.w* = 1/w
                 i0 = T.i0; i1 = T.i1; i2 = T.i2;
             } else {                                         // near-plane straddler: the homogeneous weights are the perspective-correct ones
                 double q[3]; int idx[3];
-                resolve_straddler(u, m, static_cast<int>(t), i, j, q, idx);
+                resolve_straddler(u, m, static_cast<int>(t), s_xs[i] >> 8, s_ys[j] >> 8, q, idx);
                 q0 = q[0]; q1 = q[1]; q2 = q[2]; i0 = idx[0]; i1 = idx[1]; i2 = idx[2];
             }
             const double rq = 1.0 / ((q0 + q1) + q2);
             double pos[3], nrm[3], col[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                pos[c] = ((q0 * static_cast<double>(m.pos[3 * i0 + c]) + q1 * static_cast<double>(m.pos[3 * i1 + c])) + q2 * static_cast<double>(m.pos[3 * i2 + c])) * rq;
-                nrm[c] = ((q0 * static_cast<double>(m.nrm[3 * i0 + c]) + q1 * static_cast<double>(m.nrm[3 * i1 + c])) + q2 * static_cast<double>(m.nrm[3 * i2 + c])) * rq;
                 const double c0 = static_cast<float>(m.col[3 * i0 + c] / 255.0), c1 = static_cast<float>(m.col[3 * i1 + c] / 255.0), c2 = static_cast<float>(m.col[3 * i2 + c] / 255.0);
                 col[c] = ((q0 * c0 + q1 * c1) + q2 * c2) * rq;
             }
-            const double x0 = (-u.light[0]) - pos[0], x1 = (-u.light[1]) - pos[1], x2 = (-u.light[2]) - pos[2];
-            const double il = 1.0 / sqrt((x0 * x0 + x1 * x1) + x2 * x2);
-            const double d = (nrm[0] * (x0 * il) + nrm[1] * (x1 * il)) + nrm[2] * (x2 * il);
-            const double lightv = 0.4 * fmax(d, 0.0) + 0.65;
-            r8 = static_cast<unsigned>(rint(fmin(fmax(lightv * col[0], 0.0), 1.0) * 255.0));
-            g8 = static_cast<unsigned>(rint(fmin(fmax(lightv * col[1], 0.0), 1.0) * 255.0));
-            b8 = static_cast<unsigned>(rint(fmin(fmax(lightv * col[2], 0.0), 1.0) * 255.0));
-            // on_draw: distance = B / (depth * -2.0 + 1.0 - A) * -1 (float32 until `- A`), background -> 0, mm = uint16(distance * 1000)
             const float d32 = __uint_as_float(static_cast<unsigned>(key >> 32));
-            const float tt = __fadd_rn(__fmul_rn(d32, -2.0f), 1.0f);
-            const double dist = (u.B / (static_cast<double>(tt) - u.A)) * -1.0;
-            if (!(dist >= far_dist)) mm = static_cast<unsigned>(static_cast<unsigned short>(static_cast<int>(dist * 1000.0)));
+            if (u.mode == 1) {
+                // pyrender with ambient light 1 and no other light (offscreen_renderer.py:50): the fragment is its base colour;
+                // depth read-back linearised in float32: 2 n f / (f + n - (2 d - 1)(f - n)), then (depth * 1000).astype(uint16) (predict.py:213)
+                r8 = static_cast<unsigned>(rint(fmin(fmax(col[0], 0.0), 1.0) * 255.0));
+                g8 = static_cast<unsigned>(rint(fmin(fmax(col[1], 0.0), 1.0) * 255.0));
+                b8 = static_cast<unsigned>(rint(fmin(fmax(col[2], 0.0), 1.0) * 255.0));
+                const float zn = 0.1f, zf = 2.0f;
+                const float zndc = __fsub_rn(__fmul_rn(2.0f, d32), 1.0f);
+                const float den = __fsub_rn(__fadd_rn(zf, zn), __fmul_rn(zndc, __fsub_rn(zf, zn)));
+                const float metres = __fdiv_rn(__fmul_rn(__fmul_rn(2.0f, zn), zf), den);
+                mm = static_cast<unsigned>(static_cast<unsigned short>(static_cast<int>(__fmul_rn(metres, 1000.0f))));
+            } else {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    pos[c] = ((q0 * static_cast<double>(m.pos[3 * i0 + c]) + q1 * static_cast<double>(m.pos[3 * i1 + c])) + q2 * static_cast<double>(m.pos[3 * i2 + c])) * rq;
+                    nrm[c] = ((q0 * static_cast<double>(m.nrm[3 * i0 + c]) + q1 * static_cast<double>(m.nrm[3 * i1 + c])) + q2 * static_cast<double>(m.nrm[3 * i2 + c])) * rq;
+                }
+                const double x0 = (-u.light[0]) - pos[0], x1 = (-u.light[1]) - pos[1], x2 = (-u.light[2]) - pos[2];
+                const double il = 1.0 / sqrt((x0 * x0 + x1 * x1) + x2 * x2);
+                const double d = (nrm[0] * (x0 * il) + nrm[1] * (x1 * il)) + nrm[2] * (x2 * il);
+                const double lightv = 0.4 * fmax(d, 0.0) + 0.65;
+                r8 = static_cast<unsigned>(rint(fmin(fmax(lightv * col[0], 0.0), 1.0) * 255.0));
+                g8 = static_cast<unsigned>(rint(fmin(fmax(lightv * col[1], 0.0), 1.0) * 255.0));
+                b8 = static_cast<unsigned>(rint(fmin(fmax(lightv * col[2], 0.0), 1.0) * 255.0));
+                // on_draw: distance = B / (depth * -2.0 + 1.0 - A) * -1 (float32 until `- A`), background -> 0, mm = uint16(distance * 1000)
+                const float tt = __fadd_rn(__fmul_rn(d32, -2.0f), 1.0f);
+                const double dist = (u.B / (static_cast<double>(tt) - u.A)) * -1.0;
+                if (!(dist >= far_dist)) mm = static_cast<unsigned>(static_cast<unsigned short>(static_cast<int>(dist * 1000.0)));
+            }
         }
-        const size_t o = (static_cast<size_t>(n) * kRS + j) * kRS + i;
+        const int orow = u.mode == 1 ? (kRS - 1 - j) : j;         // mode 1: rows were walked bottom-up, the image is stored top-down
+        const size_t o = (static_cast<size_t>(n) * kRS + orow) * kRS + i;
         a.rgb[o * 3] = static_cast<uint8_t>(r8); a.rgb[o * 3 + 1] = static_cast<uint8_t>(g8); a.rgb[o * 3 + 2] = static_cast<uint8_t>(b8);
         a.depth[o] = static_cast<uint16_t>(mm);
     }

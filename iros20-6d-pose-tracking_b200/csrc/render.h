@@ -20,6 +20,8 @@ struct RenderArgs {
     uint8_t* projected;            // workspace [n][max_nv] projected vertices (render_projected_bytes_per_vertex() each)
     uint8_t* uniforms;             // workspace [n] per-track uniforms (render_uniform_bytes() each)
     int max_nv;                    // vertex count of the largest model
+    int mode;                      // 0: vispy-style (lit, the crop window is the viewport); 1: pyrender-style (unlit full camera image vw x vh, then crop_bbox)
+    int vw, vh;                    // mode 1: camera image size
     uint8_t* rgb;                  // [n][176][176][3]
     uint16_t* depth;               // [n][176][176] mm, 0 = background
 };

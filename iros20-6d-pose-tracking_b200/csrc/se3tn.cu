@@ -9,6 +9,8 @@
 #include "depth_fill.h"
 #include "ptx.cuh"
 
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -147,6 +149,12 @@ struct se3tn_ctx {
     cudaStream_t cap_stream = nullptr;   // steps are captured on this private stream (the caller's may be the legacy default stream, which cannot be captured) and replayed on the caller's
     cudaEvent_t ev0[SE3TN_PROFILE_SLOTS] = {}, ev1[SE3TN_PROFILE_SLOTS] = {};
     bool ev_used[SE3TN_PROFILE_SLOTS] = {};
+    // se3tn_track_host: context-owned pinned staging and device-side inputs / outputs (stable addresses -> the step's graph is reused)
+    struct HostIO {
+        uint8_t* pin = nullptr; size_t pin_bytes = 0;          // pinned host staging: inputs, then outputs
+        uint8_t* dev = nullptr; size_t dev_bytes = 0;          // device: frame rgb | frame depth | poses | widths | rgbA | depthA | ids | out poses | out trans | out rot
+        int H = 0, W = 0, n_cap = 0;
+    } hio;
     std::string err;
 };
 
@@ -605,6 +613,7 @@ void se3tn_destroy(se3tn_ctx* c) {
     for (auto& kv : c->meshes) { cudaFree(const_cast<float*>(kv.second.pos)); cudaFree(const_cast<float*>(kv.second.nrm)); cudaFree(const_cast<uint8_t*>(kv.second.col)); cudaFree(const_cast<int*>(kv.second.faces)); }
     cudaFree(c->d_meshes); cudaFree(c->render_proj); cudaFree(c->render_unif);
     cudaFree(c->fill.a); cudaFree(c->fill.b); cudaFree(c->fill.lut); cudaFree(c->fill.minmax);
+    cudaFree(c->hio.dev); if (c->hio.pin) cudaFreeHost(c->hio.pin);
     if (c->own_workspace) cudaFree(c->workspace);
     delete c;
 }
@@ -980,6 +989,112 @@ int se3tn_upload_frame_window(se3tn_ctx* c, const uint8_t* rgb_host, const uint1
     return SE3TN_OK;
 }
 
+namespace {
+// crop window of one track in frame pixels: compute_bbox + crop_bbox's window (reference Utils.py:302-316, 324-327), the same
+// arithmetic as bbox.cuh on the device
+inline void host_crop_window(const double* pose, const double* K, double width, int& top, int& left, int& ch, int& cw) {
+    const double ox = pose[3] * 1000.0, oy = pose[7] * 1000.0, oz = pose[11] * 1000.0, half = width / 2;
+    const double u0 = std::nearbyint((ox - half) * K[0] / oz + K[2]), u1 = std::nearbyint((ox + half) * K[0] / oz + K[2]);
+    const double v0 = std::nearbyint((oy - half) * K[1] / oz + K[3]), v1 = std::nearbyint((oy + half) * K[1] / oz + K[3]);
+    const double umin = std::fmin(u0, u1), umax = std::fmax(u0, u1), vmin = std::fmin(v0, v1), vmax = std::fmax(v0, v1);
+    const double lim = 1.0e9;
+    if (!(umin == umin && umax == umax && vmin == vmin && vmax == vmax)) { top = left = ch = cw = 0; return; }
+    left = static_cast<int>(std::fmax(-lim, std::fmin(lim, umin))); top = static_cast<int>(std::fmax(-lim, std::fmin(lim, vmin)));
+    cw = static_cast<int>(std::fmax(-lim, std::fmin(lim, umax))) - left; ch = static_cast<int>(std::fmax(-lim, std::fmin(lim, vmax))) - top;
+}
+inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+}  // namespace
+
+int se3tn_track_host(se3tn_ctx* c, const uint8_t* frame_rgb, const uint16_t* frame_depth, int H, int W, const double* K,
+                     const double* poses, const double* object_width, const uint8_t* rgbA, const uint16_t* depthA,
+                     const int32_t* weight_ids, int n, double tn, double rn, int precision,
+                     double* poses_out, float* out_trans, float* out_rot, void* stream) {
+    if (!c) return SE3TN_ERR_INVALID;
+    if (!frame_rgb || !frame_depth || !K || !poses || !object_width || !rgbA || !depthA || !poses_out || H <= 0 || W <= 0)
+        return fail(c, SE3TN_ERR_INVALID, "se3tn_track_host: null argument or empty frame");
+    if (n < 0 || n > c->max_batch) return fail(c, SE3TN_ERR_INVALID, "se3tn_track_host: n exceeds max_batch");
+    if (n == 0) return SE3TN_OK;
+    DeviceGuard guard(c->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    auto& io = c->hio;
+    const size_t px = static_cast<size_t>(H) * W, img = static_cast<size_t>(kImg) * kImg;
+    // ---- (re)size the context-owned buffers: stable addresses from then on, so the captured step is replayed ----
+    if (io.H != H || io.W != W || io.n_cap < n) {
+        CU_TRY(c, cudaStreamSynchronize(s));
+        const int cap = std::max(n, io.n_cap);
+        const size_t per = 128 + 8 + img * 3 + img * 2 + 4 + 128 + 12 + 12;
+        const size_t dev_bytes = align256(px * 3) + align256(px * 2) + align256(per * cap) + 8 * 256;
+        cudaFree(io.dev); io.dev = nullptr; if (io.pin) { cudaFreeHost(io.pin); io.pin = nullptr; }
+        io.H = io.W = io.n_cap = 0;
+        CU_TRY(c, cudaMalloc(&io.dev, dev_bytes));
+        CU_TRY(c, cudaMemset(io.dev, 0, dev_bytes));            // frame pixels outside the uploaded windows are never read; keep them defined
+        CU_TRY(c, cudaHostAlloc(&io.pin, px * 5 + per * cap + 4096, cudaHostAllocDefault));
+        io.dev_bytes = dev_bytes; io.pin_bytes = px * 5 + per * cap + 4096; io.H = H; io.W = W; io.n_cap = cap;
+        drop_graphs(c);                                          // steps captured against the old addresses
+    }
+    uint8_t* d = io.dev;
+    uint8_t* d_rgb = d; d += align256(px * 3);
+    uint16_t* d_depth = reinterpret_cast<uint16_t*>(d); d += align256(px * 2);
+    const size_t cap = static_cast<size_t>(io.n_cap);
+    double* d_poses = reinterpret_cast<double*>(d); d += align256(cap * 128);
+    double* d_ow = reinterpret_cast<double*>(d); d += align256(cap * 8);
+    uint8_t* d_rgbA = d; d += align256(cap * img * 3);
+    uint16_t* d_depthA = reinterpret_cast<uint16_t*>(d); d += align256(cap * img * 2);
+    int32_t* d_wid = reinterpret_cast<int32_t*>(d); d += align256(cap * 4);
+    double* d_out = reinterpret_cast<double*>(d); d += align256(cap * 128);
+    float* d_tr = reinterpret_cast<float*>(d); d += align256(cap * 12);
+    float* d_ro = reinterpret_cast<float*>(d);
+    // ---- the part of the frame the tracks' crop windows touch (K0 reads nothing else) ----
+    int y0 = H, y1 = 0, x0 = W, x1 = 0;
+    for (int i = 0; i < n; ++i) {
+        int top, left, ch, cw;
+        host_crop_window(poses + 16 * i, K, object_width[i], top, left, ch, cw);
+        if (ch <= 0 || cw <= 0) continue;
+        y0 = std::min(y0, std::max(top - 1, 0)); y1 = std::max(y1, std::min(top + ch + 1, H));       // one pixel of margin
+        x0 = std::min(x0, std::max(left - 1, 0)); x1 = std::max(x1, std::min(left + cw + 1, W));
+    }
+    if (y1 <= y0 || x1 <= x0) { y0 = y1 = x0 = x1 = 0; }         // every window misses the frame: nothing of it is read
+    if (static_cast<size_t>(y1 - y0) * (x1 - x0) * 2 >= px) { y0 = 0; y1 = H; x0 = 0; x1 = W; }
+    // ---- stage through pinned memory, one asynchronous copy per array ----
+    uint8_t* hp = io.pin;
+    const int wh = y1 - y0, ww = x1 - x0;
+    if (wh > 0 && ww > 0) {
+        uint8_t* st_rgb = hp; hp += static_cast<size_t>(wh) * ww * 3;
+        uint8_t* st_dep = hp; hp += align256(static_cast<size_t>(wh) * ww * 2);
+        for (int y = 0; y < wh; ++y) {
+            memcpy(st_rgb + static_cast<size_t>(y) * ww * 3, frame_rgb + (static_cast<size_t>(y0 + y) * W + x0) * 3, static_cast<size_t>(ww) * 3);
+            memcpy(st_dep + static_cast<size_t>(y) * ww * 2, frame_depth + static_cast<size_t>(y0 + y) * W + x0, static_cast<size_t>(ww) * 2);
+        }
+        const size_t off = static_cast<size_t>(y0) * W + x0;
+        CU_TRY(c, cudaMemcpy2DAsync(d_rgb + off * 3, static_cast<size_t>(W) * 3, st_rgb, static_cast<size_t>(ww) * 3, static_cast<size_t>(ww) * 3, wh, cudaMemcpyHostToDevice, s));
+        CU_TRY(c, cudaMemcpy2DAsync(d_depth + off, static_cast<size_t>(W) * 2, st_dep, static_cast<size_t>(ww) * 2, static_cast<size_t>(ww) * 2, wh, cudaMemcpyHostToDevice, s));
+    }
+    auto put = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
+        memcpy(hp, src, bytes);
+        cudaError_t e = cudaMemcpyAsync(dst, hp, bytes, cudaMemcpyHostToDevice, s);
+        hp += align256(bytes);
+        return e;
+    };
+    const size_t nn = static_cast<size_t>(n);
+    CU_TRY(c, put(d_poses, poses, nn * 128));
+    CU_TRY(c, put(d_ow, object_width, nn * 8));
+    CU_TRY(c, put(d_rgbA, rgbA, nn * img * 3));
+    CU_TRY(c, put(d_depthA, depthA, nn * img * 2));
+    if (weight_ids) CU_TRY(c, put(d_wid, weight_ids, nn * 4));
+    const int rc = se3tn_track_batch(c, d_rgb, d_depth, H, W, K, d_poses, d_ow, d_rgbA, d_depthA, weight_ids, weight_ids ? d_wid : nullptr, n,
+                                     tn, rn, precision, d_tr, d_ro, d_out, stream);
+    if (rc != SE3TN_OK) return rc;
+    uint8_t* ho = hp;                                            // outputs come back through the same pinned block
+    CU_TRY(c, cudaMemcpyAsync(ho, d_out, nn * 128, cudaMemcpyDeviceToHost, s));
+    if (out_trans) CU_TRY(c, cudaMemcpyAsync(ho + align256(nn * 128), d_tr, nn * 12, cudaMemcpyDeviceToHost, s));
+    if (out_rot) CU_TRY(c, cudaMemcpyAsync(ho + align256(nn * 128) + align256(nn * 12), d_ro, nn * 12, cudaMemcpyDeviceToHost, s));
+    CU_TRY(c, cudaStreamSynchronize(s));
+    memcpy(poses_out, ho, nn * 128);
+    if (out_trans) memcpy(out_trans, ho + align256(nn * 128), nn * 12);
+    if (out_rot) memcpy(out_rot, ho + align256(nn * 128) + align256(nn * 12), nn * 12);
+    return SE3TN_OK;
+}
+
 int se3tn_allgather_poses(se3tn_ctx* c, void* nccl_comm, const double* local_poses, double* all_poses, int n_local, void* stream) {
     if (!c) return SE3TN_ERR_INVALID;
     if (!nccl_comm || n_local < 0 || (n_local > 0 && (!local_poses || !all_poses))) return fail(c, SE3TN_ERR_INVALID, "se3tn_allgather_poses: bad arguments");
@@ -1058,8 +1173,16 @@ int se3tn_set_mesh(se3tn_ctx* c, int mesh_id, const float* pos, const float* nrm
 
 int se3tn_render(se3tn_ctx* c, const double* K, const double* poses, const double* object_width,
                  const int32_t* mesh_ids, int n, uint8_t* rgbA, uint16_t* depthA, void* stream) {
+    return se3tn_render_ex(c, K, poses, object_width, mesh_ids, n, SE3TN_RENDER_VISPY, 0, 0, rgbA, depthA, stream);
+}
+
+int se3tn_render_ex(se3tn_ctx* c, const double* K, const double* poses, const double* object_width,
+                    const int32_t* mesh_ids, int n, int mode, int H, int W, uint8_t* rgbA, uint16_t* depthA, void* stream) {
     if (!c) return SE3TN_ERR_INVALID;
     if (n < 0 || !K || (n > 0 && (!poses || !object_width || !rgbA || !depthA))) return fail(c, SE3TN_ERR_INVALID, "se3tn_render: bad arguments");
+    if (mode != SE3TN_RENDER_VISPY && mode != SE3TN_RENDER_PYRENDER) return fail(c, SE3TN_ERR_INVALID, "se3tn_render_ex: unknown mode");
+    // the camera image of the pyrender-style mode: sample positions are kept in 1/256 pixel as int32
+    if (mode == SE3TN_RENDER_PYRENDER && (H <= 0 || W <= 0 || H > 65536 || W > 65536)) return fail(c, SE3TN_ERR_INVALID, "se3tn_render_ex: camera image size out of range");
     if (n == 0) return SE3TN_OK;
     if (n > c->max_batch) return fail(c, SE3TN_ERR_INVALID, "se3tn_render: n exceeds the context's max_batch");
     if (c->meshes.empty()) return fail(c, SE3TN_ERR_STATE, "se3tn_render: no mesh loaded (se3tn_set_mesh)");
@@ -1086,6 +1209,7 @@ int se3tn_render(se3tn_ctx* c, const double* K, const double* poses, const doubl
     a.poses = poses; a.object_width = object_width; a.mesh_ids = mesh_ids; a.meshes = c->d_meshes; a.n_meshes = c->mesh_rows;
     a.fx = K[0]; a.fy = K[1]; a.cx = K[2]; a.cy = K[3];
     a.rgb = rgbA; a.depth = depthA;
+    a.mode = mode == SE3TN_RENDER_PYRENDER ? 1 : 0; a.vw = W; a.vh = H;
     a.projected = c->render_proj; a.uniforms = c->render_unif; a.max_nv = c->render_max_nv;
     { ProfScope ps(c, 20, s); CU_TRY(c, launch_render(a, n, s)); }
     c->launches += 2;

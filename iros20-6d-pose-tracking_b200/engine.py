@@ -189,6 +189,35 @@ class Engine:
                                               _stream(self.device)), self._ctx)
         return out_poses, out_trans, out_rot
 
+    def track_host(self, frame_rgb, frame_depth, K, poses, object_width, rgbA, depthA, trans_normalizer, rot_normalizer,
+                   weight_ids=None, precision='bf16x3', want_residuals=False):
+        """The reference's calling pattern as one library call: numpy arrays in, numpy poses out, synchronous (se3tn_track_host).
+        frame_rgb uint8 (H,W,3), frame_depth uint16 (H,W), poses float64 (n,4,4), object_width float64 (n), rgbA uint8
+        (n,176,176,3), depthA uint16 (n,176,176), weight_ids int32 (n) or None -- all C-contiguous."""
+        n = int(poses.shape[0])
+        for name, a, dt, shape in (('frame_rgb', frame_rgb, np.uint8, frame_depth.shape + (3,)), ('frame_depth', frame_depth, np.uint16, frame_depth.shape),
+                                   ('poses', poses, np.float64, (n, 4, 4)), ('object_width', object_width, np.float64, (n,)),
+                                   ('rgbA', rgbA, np.uint8, (n, IMAGE_SIZE, IMAGE_SIZE, 3)), ('depthA', depthA, np.uint16, (n, IMAGE_SIZE, IMAGE_SIZE))):
+            if not (isinstance(a, np.ndarray) and a.dtype == dt and tuple(a.shape) == tuple(shape) and a.flags['C_CONTIGUOUS']):
+                raise ValueError('track_host: %s must be a C-contiguous %s array of shape %s' % (name, np.dtype(dt).name, tuple(shape)))
+        if frame_depth.ndim != 2:
+            raise ValueError('track_host: frame_depth must be (H, W)')
+        H, W = frame_depth.shape
+        Kh = self._k4(K)
+        wid = None
+        if weight_ids is not None:
+            wid = np.ascontiguousarray(weight_ids, dtype=np.int32)
+            if wid.shape != (n,):
+                raise ValueError('track_host: weight_ids must have one entry per track')
+        out = np.empty((n, 4, 4), dtype=np.float64)
+        tr = np.empty((n, 3), dtype=np.float32) if want_residuals else None
+        ro = np.empty((n, 3), dtype=np.float32) if want_residuals else None
+        vp = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else C.c_void_p(0)
+        _lib.check(self.lib.se3tn_track_host(self._ctx, vp(frame_rgb), vp(frame_depth), int(H), int(W), vp(Kh), vp(poses), vp(object_width),
+                                             vp(rgbA), vp(depthA), vp(wid), n, float(trans_normalizer), float(rot_normalizer), PREC[precision],
+                                             vp(out), vp(tr), vp(ro), _stream(self.device)), self._ctx)
+        return (out, tr, ro) if want_residuals else out
+
     def upload_frame_window(self, rgb_host, depth_host, rgb_dev, depth_dev, y0, y1, x0, x1):
         """Copy rows [y0,y1) x columns [x0,x1) of contiguous numpy frames (uint8 (H,W,3), uint16 (H,W)) into full-size device frame
         buffers: K0 only reads a frame inside the tracks' crop windows."""
@@ -223,15 +252,22 @@ class Engine:
         _lib.check(self.lib.se3tn_set_mesh(self._ctx, int(mesh_id), pos.ctypes.data, nrm.ctypes.data, col.ctypes.data, faces.ctypes.data,
                                            int(pos.shape[0]), int(faces.shape[0])), self._ctx)
 
-    def render(self, K, poses, object_width, mesh_ids=None, out_rgb=None, out_depth=None):
+    def render(self, K, poses, object_width, mesh_ids=None, out_rgb=None, out_depth=None, mode='vispy', image_hw=None):
         """Tracker.render_window for n tracks (reference predict.py:193-215): float64 CUDA poses (n,4,4) and widths (n) ->
-        rgbA uint8 (n,176,176,3), depthA uint16 (n,176,176) CUDA tensors."""
+        rgbA uint8 (n,176,176,3), depthA uint16 (n,176,176) CUDA tensors.  mode 'vispy' (lit, the crop window is the GL viewport) or
+        'pyrender' (unlit render of the whole image_hw = (H, W) camera image, then crop_bbox; dataset_info['renderer'] == 'pyrenderer')."""
         n = int(poses.shape[0])
         rgb = out_rgb if out_rgb is not None else torch.empty((n, 176, 176, 3), dtype=torch.uint8, device=self.device)
         dep = out_depth if out_depth is not None else torch.empty((n, 176, 176), dtype=torch.uint16, device=self.device)
         Kh = self._k4(K)
-        _lib.check(self.lib.se3tn_render(self._ctx, Kh.ctypes.data_as(C.c_void_p), _ptr(poses), _ptr(object_width), _ptr(mesh_ids), n, _ptr(rgb), _ptr(dep),
-                                         _stream(self.device)), self._ctx)
+        if mode not in ('vispy', 'pyrender'):
+            raise ValueError("render mode must be 'vispy' or 'pyrender'")
+        if mode == 'pyrender' and image_hw is None:
+            raise ValueError("render(mode='pyrender') needs image_hw=(H, W), the camera image pyrender draws")
+        H, W = (int(image_hw[0]), int(image_hw[1])) if image_hw is not None else (0, 0)
+        _lib.check(self.lib.se3tn_render_ex(self._ctx, Kh.ctypes.data_as(C.c_void_p), _ptr(poses), _ptr(object_width), _ptr(mesh_ids), n,
+                                            _lib.RENDER_PYRENDER if mode == 'pyrender' else _lib.RENDER_VISPY, H, W, _ptr(rgb), _ptr(dep),
+                                            _stream(self.device)), self._ctx)
         return rgb, dep
 
     # ------------------------------------------------------------------ pose exchange over a raw NCCL communicator (SURVEY 8e)

@@ -162,10 +162,14 @@ class Tracker:
         # Input A.  renderer='cuda' (or nothing, with a .ply model that has normals + colours): the CUDA rasteriser
         # (csrc/render.cu) -- no OpenGL, all tracks in one launch.  Otherwise an object with render_window(ob2cam), or the
         # reference's own OpenGL renderers when they are importable.
-        if renderer == 'cuda' or (renderer is None and model_path is not None and str(model_path).lower().endswith('.ply')):
+        # dataset_info['renderer'] == 'pyrenderer' selects the reference's pyrender producer (predict.py:161-164): the rasteriser's
+        # unlit full-camera-image mode followed by crop_bbox; anything else its vispy producer.
+        pyr = dataset_info.get('renderer') == 'pyrenderer'
+        if renderer == 'cuda' or (renderer is None and model_path is not None and str(model_path).lower().endswith(('.ply', '.obj') if pyr else '.ply')):
             from .cuda_renderer import CudaRenderer
             try:
-                renderer = CudaRenderer(model_path, self.K, self.engine, self.object_width, mesh_id=weight_id)
+                renderer = CudaRenderer(model_path, self.K, self.engine, self.object_width, mesh_id=weight_id,
+                                        mode='pyrender' if pyr else 'vispy', image_hw=(cam_cfg['height'], cam_cfg['width']) if pyr else None)
             except ValueError:
                 if renderer == 'cuda':
                     raise
@@ -255,6 +259,21 @@ class Tracker:
         render = rgbA is None or depthA is None
         if render and not hasattr(self.renderer, 'render_batch'):
             raise RuntimeError('on_track_batch without rgbA/depthA needs the CUDA renderer (Tracker(renderer="cuda", model_path=*.ply))')
+        if (not render and all(isinstance(x, np.ndarray) for x in (current_rgb, current_depth, rgbA, depthA)) and not torch.is_tensor(prev_poses)
+                and not torch.is_tensor(weight_ids) and not torch.is_tensor(object_width) and os.environ.get('SE3TN_HOST_CALL', '1') != '0'):
+            # numpy in, numpy out -- the reference's own calling pattern: ONE library call stages the crop-window rectangle of the
+            # frame, the poses and input A through pinned memory, replays the step's graph and hands the poses back
+            c = lambda a, dt: a if (a.dtype == dt and a.flags['C_CONTIGUOUS']) else np.ascontiguousarray(a).astype(dt, copy=False)
+            poses_h = np.ascontiguousarray(prev_poses, dtype=np.float64).reshape(-1, 4, 4)
+            n = len(poses_h)
+            ow_h = np.full(n, float(self.object_width)) if object_width is None else np.ascontiguousarray(np.broadcast_to(np.asarray(object_width, dtype=np.float64), (n,)))
+            wh = None
+            if weight_ids is not None:
+                wh = np.ascontiguousarray(weight_ids, dtype=np.int32)
+            elif self.weight_id != 0:
+                wh = np.full(n, self.weight_id, dtype=np.int32)
+            return self.engine.track_host(c(current_rgb, np.uint8), c(current_depth, np.uint16), self.K, poses_h, ow_h, c(rgbA, np.uint8), c(depthA, np.uint16),
+                                          self.trans_normalizer, self.rot_normalizer, weight_ids=wh, precision=self.precision)
         staged = not render and all(torch.is_tensor(x) and not x.is_cuda for x in (prev_poses, current_rgb, current_depth, rgbA, depthA))
 
         def up(x, dt, slot=None):

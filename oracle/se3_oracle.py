@@ -346,23 +346,23 @@ def render_uniforms(ob2cam, K, object_width):
                 proj64=proj64, proj32=proj64.astype(np.float32), light32=light.astype(np.float32))
 
 
-def _project_vertices(pos32, view32, proj32, size):
+def _project_vertices(pos32, view32, proj32, width, height):
     """float64 arithmetic on the float32 uniforms / attributes, fixed association (mirrored by render.cu)."""
     p = pos32.astype(np.float64); V = view32.astype(np.float64); P = proj32.astype(np.float64)
     v = [((V[i, 0] * p[:, 0] + V[i, 1] * p[:, 1]) + V[i, 2] * p[:, 2]) + V[i, 3] for i in range(4)]
     c = [((P[i, 0] * v[0] + P[i, 1] * v[1]) + P[i, 2] * v[2]) + P[i, 3] * v[3] for i in range(4)]
     w = c[3]
     with np.errstate(divide='ignore', invalid='ignore'):
-        xw = (c[0] / w + 1.0) * (size * 0.5)
-        yw = (c[1] / w + 1.0) * (size * 0.5)
+        xw = (c[0] / w + 1.0) * (width * 0.5)
+        yw = (c[1] / w + 1.0) * (height * 0.5)
         zw = (c[2] / w + 1.0) * 0.5
         X = np.rint(xw * SUBPIXEL); Y = np.rint(yw * SUBPIXEL)
     return X, Y, zw, w, c
 
 
-def _near_clipped_box(cl, size):
-    """Pixel box (ia, ib, ja, jb) that contains the part of a clip-space triangle in front of the near plane (z + w >= 0),
-    one pixel of margin; the whole window when the arithmetic does not stay finite.  Only has to be conservative."""
+def _near_clipped_box(cl, width, height):
+    """Pixel box (ia, ib, ja, jb) that contains the part of a clip-space triangle beyond the near plane (z + w >= 0),
+    one pixel of margin; the whole viewport when the arithmetic does not stay finite.  Only has to be conservative."""
     pts = []
     for a in range(3):
         b = (a + 1) % 3
@@ -373,18 +373,18 @@ def _near_clipped_box(cl, size):
             pts.append(tuple(cl[a][k] + s * (cl[b][k] - cl[a][k]) for k in (0, 1, 3)))
     if not pts: return None
     with np.errstate(all='ignore'):
-        xs = [(x / w + 1.0) * (size * 0.5) for x, y, w in pts]; ys = [(y / w + 1.0) * (size * 0.5) for x, y, w in pts]
-    if not all(np.isfinite(v) and abs(v) < 1e9 for v in xs + ys): return 0, size - 1, 0, size - 1
-    return (max(0, int(np.floor(min(xs))) - 1), min(size - 1, int(np.ceil(max(xs))) + 1),
-            max(0, int(np.floor(min(ys))) - 1), min(size - 1, int(np.ceil(max(ys))) + 1))
+        xs = [(x / w + 1.0) * (width * 0.5) for x, y, w in pts]; ys = [(y / w + 1.0) * (height * 0.5) for x, y, w in pts]
+    if not all(np.isfinite(v) and abs(v) < 1e9 for v in xs + ys): return 0, width - 1, 0, height - 1
+    return (max(0, int(np.floor(min(xs))) - 1), min(width - 1, int(np.ceil(max(xs))) + 1),
+            max(0, int(np.floor(min(ys))) - 1), min(height - 1, int(np.ceil(max(ys))) + 1))
 
 
-def _straddler_setup(clip, i0, i1, i2, size):
+def _straddler_setup(clip, i0, i1, i2, width, height):
     """Adjugate of M = [[x0 x1 x2], [y0 y1 y2], [w0 w1 w2]] (clip space), fixed association (mirrored by render.cu)."""
     cl = [tuple(float(clip[k][i]) for k in range(4)) for i in (i0, i1, i2)]
     if not all(np.isfinite(v) for c in cl for v in c): return None
     if all(c[2] + c[3] < 0 for c in cl): return None                                 # wholly on the eye side of the near plane
-    box = _near_clipped_box(cl, size)
+    box = _near_clipped_box(cl, width, height)
     if box is None or box[0] > box[1] or box[2] > box[3]: return None
     (x0, y0, z0, w0), (x1, y1, z1, w1), (x2, y2, z2, w2) = cl
     A = (y1 * w2 - y2 * w1, y2 * w0 - y0 * w2, y0 * w1 - y1 * w0)
@@ -395,17 +395,14 @@ def _straddler_setup(clip, i0, i1, i2, size):
     return dict(idx=(i0, i1, i2), A=A, B=B, C=C, idet=1.0 / det, z=(z0, z1, z2), w=(w0, w1, w2), box=box)
 
 
-def render_window(ob2cam, K, object_width, mesh, size=176, uniforms=None):
-    """-> (rgb uint8 (size,size,3), depth uint16 (size,size) in mm, 0 = background).  mesh: dict(pos float32 (nv,3),
-    nrm float32 (nv,3), col uint8 (nv,3), faces int32 (nf,3))."""
-    u = uniforms if uniforms is not None else render_uniforms(ob2cam, K, object_width)
-    rgb = np.zeros((size, size, 3), np.uint8); depth = np.zeros((size, size), np.uint16)
-    if u['right'] == u['left'] or u['top'] == u['bottom'] or not np.all(np.isfinite(u['proj32'])):
-        return rgb, depth
-    X, Y, zw, w, clip = _project_vertices(mesh['pos'], u['view32'], u['proj32'], size)
-    key = np.full((size, size), (np.uint64(0x3F800000) << np.uint64(32)) | np.uint64(0xFFFFFFFF), np.uint64)   # depth 1.0, no triangle
+def _rasterise(mesh, view32, proj32, width, height):
+    """Visibility pass of the GL pipeline restated (see the header of this section): -> (key, setups, w).  key (height, width)
+    uint64 = float32 window-z bits << 32 | triangle index (depth test LESS, first drawn wins ties), row 0 = window y 0 (bottom)."""
+    X, Y, zw, w, clip = _project_vertices(mesh['pos'], view32, proj32, width, height)
+    key = np.full((height, width), (np.uint64(0x3F800000) << np.uint64(32)) | np.uint64(0xFFFFFFFF), np.uint64)   # depth 1.0, no triangle
     faces = mesh['faces']
     lim = 1 << 25                      # render.cu evaluates the edge functions in float64: exact below 2^25 sub-pixels
+    half = SUBPIXEL // 2
     setups = {}
     for t in range(len(faces)):
         i0, i1, i2 = (int(a) for a in faces[t])
@@ -415,11 +412,11 @@ def render_window(ob2cam, K, object_width, mesh, size=176, uniforms=None):
             # not exist.  GL clips such a triangle against the near plane; here it is rasterised in homogeneous coordinates
             # (weights beta = M^-1 (px, py, 1) with M the clip-space (x, y, w) columns -- inside iff all beta >= 0) and the
             # per-pixel depth test 0 <= z_window cuts it at the near plane, which is the same set of fragments.
-            st = _straddler_setup(clip, i0, i1, i2, size)
+            st = _straddler_setup(clip, i0, i1, i2, width, height)
             if st is None: continue
             ia, ib, ja, jb = st['box']
-            px = ((2 * np.arange(ia, ib + 1) + 1 - size).astype(np.float64) / float(size))[None, :]
-            py = ((2 * np.arange(ja, jb + 1) + 1 - size).astype(np.float64) / float(size))[:, None]
+            px = ((2 * np.arange(ia, ib + 1) + 1 - width).astype(np.float64) / float(width))[None, :]
+            py = ((2 * np.arange(ja, jb + 1) + 1 - height).astype(np.float64) / float(height))[:, None]
             with np.errstate(all='ignore'):
                 beta = [((st['A'][k] * px + st['B'][k] * py) + st['C'][k]) * st['idet'] for k in range(3)]
                 zc = (beta[0] * st['z'][0] + beta[1] * st['z'][1]) + beta[2] * st['z'][2]
@@ -438,9 +435,8 @@ def render_window(ob2cam, K, object_width, mesh, size=176, uniforms=None):
         if area2 == 0: continue
         if area2 < 0:                                                                    # no culling: make it counter-clockwise
             i1, i2, x1, y1, x2, y2, area2 = i2, i1, x2, y2, x1, y1, -area2
-        half = SUBPIXEL // 2
-        ia, ib = max(0, (min(x0, x1, x2) - half + SUBPIXEL - 1) // SUBPIXEL), min(size - 1, (max(x0, x1, x2) - half) // SUBPIXEL)
-        ja, jb = max(0, (min(y0, y1, y2) - half + SUBPIXEL - 1) // SUBPIXEL), min(size - 1, (max(y0, y1, y2) - half) // SUBPIXEL)
+        ia, ib = max(0, (min(x0, x1, x2) - half + SUBPIXEL - 1) // SUBPIXEL), min(width - 1, (max(x0, x1, x2) - half) // SUBPIXEL)
+        ja, jb = max(0, (min(y0, y1, y2) - half + SUBPIXEL - 1) // SUBPIXEL), min(height - 1, (max(y0, y1, y2) - half) // SUBPIXEL)
         if ia > ib or ja > jb: continue
         cx = (np.arange(ia, ib + 1, dtype=np.int64) * SUBPIXEL + half)[None, :]
         cy = (np.arange(ja, jb + 1, dtype=np.int64) * SUBPIXEL + half)[:, None]
@@ -462,32 +458,53 @@ def render_window(ob2cam, K, object_width, mesh, size=176, uniforms=None):
         upd = ok & (k < sub)
         sub[upd] = k[upd]
         setups[t] = (i0, i1, i2, x0, y0, x1, y1, x2, y2, area2)
+    return key, setups, w
+
+
+def _fragment_weights(setup, w, i, j, width, height):
+    """Perspective-correct (unnormalised) weights q0..q2 of the three vertices at pixel (i, j), and their vertex ids."""
+    half = SUBPIXEL // 2
+    if isinstance(setup, dict):                                                          # near-plane straddler: homogeneous weights
+        i0, i1, i2 = setup['idx']
+        px, py = float(2 * i + 1 - width) / float(width), float(2 * j + 1 - height) / float(height)
+        q0, q1, q2 = (((setup['A'][k] * px + setup['B'][k] * py) + setup['C'][k]) * setup['idet'] for k in range(3))
+        return (i0, i1, i2), (q0, q1, q2)
+    i0, i1, i2, x0, y0, x1, y1, x2, y2, area2 = setup
+    cx, cy = i * SUBPIXEL + half, j * SUBPIXEL + half
+    e0 = (x2 - x1) * (cy - y1) - (y2 - y1) * (cx - x1)
+    e1 = (x0 - x2) * (cy - y2) - (y0 - y2) * (cx - x2)
+    e2 = (x1 - x0) * (cy - y0) - (y1 - y0) * (cx - x0)
+    inv_area = 1.0 / float(area2)
+    l0, l1, l2 = float(e0) * inv_area, float(e1) * inv_area, float(e2) * inv_area
+    return (i0, i1, i2), (l0 * (1.0 / w[i0]), l1 * (1.0 / w[i1]), l2 * (1.0 / w[i2]))
+
+
+def _interp_colour(mesh, ids, q):
+    i0, i1, i2 = ids; q0, q1, q2 = q
+    rq = 1.0 / ((q0 + q1) + q2)
+    return [((q0 * float(np.float32(mesh['col'][i0, c] / 255.0)) + q1 * float(np.float32(mesh['col'][i1, c] / 255.0)))
+             + q2 * float(np.float32(mesh['col'][i2, c] / 255.0))) * rq for c in range(3)]
+
+
+def render_window(ob2cam, K, object_width, mesh, size=176, uniforms=None):
+    """-> (rgb uint8 (size,size,3), depth uint16 (size,size) in mm, 0 = background).  mesh: dict(pos float32 (nv,3),
+    nrm float32 (nv,3), col uint8 (nv,3), faces int32 (nf,3))."""
+    u = uniforms if uniforms is not None else render_uniforms(ob2cam, K, object_width)
+    rgb = np.zeros((size, size, 3), np.uint8); depth = np.zeros((size, size), np.uint16)
+    if u['right'] == u['left'] or u['top'] == u['bottom'] or not np.all(np.isfinite(u['proj32'])):
+        return rgb, depth
+    key, setups, w = _rasterise(mesh, u['view32'], u['proj32'], size, size)
     A, B = u['proj64'][2, 2], u['proj64'][2, 3]
     far_dist = B / (A + 1)
     light = u['light32'].astype(np.float64)
-    half = SUBPIXEL // 2
     for j, i in zip(*np.nonzero((key & np.uint64(0xFFFFFFFF)) != np.uint64(0xFFFFFFFF))):
         t = int(key[j, i] & np.uint64(0xFFFFFFFF))
-        if isinstance(setups[t], dict):                                                  # near-plane straddler: homogeneous weights
-            st = setups[t]
-            i0, i1, i2 = st['idx']
-            px, py = float(2 * i + 1 - size) / float(size), float(2 * j + 1 - size) / float(size)
-            q0, q1, q2 = (((st['A'][k] * px + st['B'][k] * py) + st['C'][k]) * st['idet'] for k in range(3))
-        else:
-            i0, i1, i2, x0, y0, x1, y1, x2, y2, area2 = setups[t]
-            cx, cy = i * SUBPIXEL + half, j * SUBPIXEL + half
-            e0 = (x2 - x1) * (cy - y1) - (y2 - y1) * (cx - x1)
-            e1 = (x0 - x2) * (cy - y2) - (y0 - y2) * (cx - x2)
-            e2 = (x1 - x0) * (cy - y0) - (y1 - y0) * (cx - x0)
-            inv_area = 1.0 / float(area2)
-            l0, l1, l2 = float(e0) * inv_area, float(e1) * inv_area, float(e2) * inv_area
-            q0, q1, q2 = l0 * (1.0 / w[i0]), l1 * (1.0 / w[i1]), l2 * (1.0 / w[i2])
+        (i0, i1, i2), (q0, q1, q2) = _fragment_weights(setups[t], w, i, j, size, size)
         rq = 1.0 / ((q0 + q1) + q2)
         def interp(a0, a1, a2): return ((q0 * a0 + q1 * a1) + q2 * a2) * rq
         pos = [interp(float(mesh['pos'][i0, c]), float(mesh['pos'][i1, c]), float(mesh['pos'][i2, c])) for c in range(3)]
         nrm = [interp(float(mesh['nrm'][i0, c]), float(mesh['nrm'][i1, c]), float(mesh['nrm'][i2, c])) for c in range(3)]
-        col = [interp(float(np.float32(mesh['col'][i0, c] / 255.0)), float(np.float32(mesh['col'][i1, c] / 255.0)),
-                      float(np.float32(mesh['col'][i2, c] / 255.0))) for c in range(3)]
+        col = _interp_colour(mesh, (i0, i1, i2), (q0, q1, q2))
         x = [(-light[c]) - pos[c] for c in range(3)]
         il = 1.0 / np.sqrt((x[0] * x[0] + x[1] * x[1]) + x[2] * x[2])
         L = [x[c] * il for c in range(3)]
@@ -500,6 +517,56 @@ def render_window(ob2cam, K, object_width, mesh, size=176, uniforms=None):
         dist = (B / (np.float64(tt) - A)) * -1                                          # `- A` with a float64 scalar: float64 (numpy >= 2)
         depth[j, i] = 0 if dist >= far_dist else np.uint16(dist * 1000)
     return rgb, depth
+
+
+# ---------------------------------------------------------------------------------------------
+# The reference's OTHER producer of input A: dataset_info['renderer'] == 'pyrenderer' (predict.py:161-164, 210-214;
+# offscreen_renderer.py:47-83): pyrender renders the WHOLE camera image (IntrinsicsCamera fx fy cx cy, znear 0.1, zfar 2,
+# ambient light 1 and no other light, background 0), the metric depth goes to uint16 mm and crop_bbox (Utils.py:320-359) cuts
+# the 176 x 176 window out of both.  pyrender is a third-party package that is neither vendored in the reference nor installed
+# here (reference docker/dockerfile: `pip install pyrender`, unpinned; 0.1.45 is the release of that time), so its part is
+# restated from its published sources: camera.py IntrinsicsCamera.get_projection_matrix, renderer.py _read_main_framebuffer
+# (depth linearisation), shaders/mesh.frag (colour = base colour * ambient when the scene has no lights).  PARITY UNPINNED,
+# twice: the GL rasterisation rules (as above) and pyrender itself; per-fragment texture lookups (textured .obj) are replaced
+# by per-vertex colours, as the reference's own vispy path does for the same models (predict.py:167-179).
+# ---------------------------------------------------------------------------------------------
+def pyrender_uniforms(ob2cam, K, H, W):
+    n, f = NEAR_PLANE, FAR_PLANE
+    P = np.zeros((4, 4))
+    P[0, 0] = 2.0 * K[0, 0] / W; P[1, 1] = 2.0 * K[1, 1] / H
+    P[0, 2] = 1.0 - 2.0 * K[0, 2] / W; P[1, 2] = 2.0 * K[1, 2] / H - 1.0
+    P[3, 2] = -1.0
+    P[2, 2] = (f + n) / (n - f); P[2, 3] = (2 * f * n) / (n - f)
+    ob2cam_gl = np.linalg.inv(GLCAM_IN_CVCAM).dot(ob2cam)                              # offscreen_renderer.py:80
+    return dict(view32=ob2cam_gl.astype(np.float32), proj32=P.astype(np.float32))
+
+
+def render_full_frame_unlit(ob2cam, K, mesh, H, W):
+    """-> (color uint8 (H,W,3), depth float32 (H,W) metres, 0 = background): what Renderer.render returns
+    (offscreen_renderer.py:77-83), image rows top-down."""
+    u = pyrender_uniforms(ob2cam, K, H, W)
+    key, setups, w = _rasterise(mesh, u['view32'], u['proj32'], W, H)
+    color = np.zeros((H, W, 3), np.uint8); depth = np.zeros((H, W), np.float32)
+    zn, zf = np.float32(NEAR_PLANE), np.float32(FAR_PLANE)
+    for j, i in zip(*np.nonzero((key & np.uint64(0xFFFFFFFF)) != np.uint64(0xFFFFFFFF))):
+        t = int(key[j, i] & np.uint64(0xFFFFFFFF))
+        ids, q = _fragment_weights(setups[t], w, i, j, W, H)
+        col = _interp_colour(mesh, ids, q)
+        r = H - 1 - j                                                                   # glReadPixels rows are bottom-up; pyrender flips them
+        for c in range(3):
+            color[r, i, c] = np.uint8(np.rint(min(max(col[c], 0.0), 1.0) * 255.0))
+        d32 = np.uint32(key[j, i] >> np.uint64(32)).view(np.float32)
+        zn_ = np.float32(np.float32(np.float32(2.0) * d32) - np.float32(1.0))            # float32 throughout, as numpy does on the float32 read-back
+        depth[r, i] = np.float32(np.float32(np.float32(2.0) * zn * zf) / np.float32(np.float32(zf + zn) - np.float32(zn_ * np.float32(zf - zn))))
+    return color, depth
+
+
+def render_window_pyrender(ob2cam, K, object_width, mesh, H, W, size=176):
+    """Tracker.render_window with the pyrender renderer (predict.py:210-214) -> (rgb uint8 (size,size,3), depth uint16 (size,size))."""
+    bbox = compute_bbox(ob2cam, K, object_width, scale=(1000, 1000, 1000))
+    rgb, depth = render_full_frame_unlit(ob2cam, K, mesh, H, W)
+    depth = (depth * np.float32(1000)).astype(np.uint16)
+    return crop_bbox(rgb, depth, bbox, (size, size))
 
 
 # =============================================================================================

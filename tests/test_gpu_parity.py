@@ -299,6 +299,49 @@ def test_on_track_end_to_end_vs_oracle(pkg, synth):
         assert staged.is_cuda and np.array_equal(staged.cpu().numpy(), batch)
 
 
+def test_track_host_one_call_equals_device_path(pkg, synth, eng, monkeypatch):
+    """se3tn_track_host (numpy in / numpy out in ONE library call: pinned staging of the crop-window rectangle, graph replay, read
+    back) runs the same kernels on the same bytes as se3tn_track_batch on device tensors: identical poses, for windows inside,
+    across and outside the frame, several frame sizes, per-track weight sets and widths, and repeated calls (graph replay)."""
+    dev = eng.device
+    mean, std = synth.default_mean_std()
+    TN, RN = 0.03, 5 * np.pi / 180
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    for n, seed, shape in ((1, 3, None), (3, 4, None), (6, 6, None), (2, 8, (240, 320))):
+        rgb, depth, poses, rgbA, depthA = _frame_case(synth, n, seed)
+        if shape is not None:                                   # another frame size: the context re-sizes its staging
+            rgb, depth = np.ascontiguousarray(rgb[:shape[0], :shape[1]]), np.ascontiguousarray(depth[:shape[0], :shape[1]])
+        poses = poses.copy()
+        poses[0, :3, 3] = (0.32, -0.2, 0.5)                      # window hangs over the frame's edge
+        if n > 1:
+            poses[1, :3, 3] = (2.0, 2.0, 0.5)                    # window misses the frame entirely
+        ow = np.full(n, 200.0); ow[-1] = 150.0
+        wid = (np.arange(n) * 2 // max(n, 1)).astype(np.int32) if n >= 3 else None
+        want, wtr, wro = eng.track_batch(t(rgb), t(depth), synth.CAMERA_K, t(poses), t(ow), t(rgbA), t(depthA), TN, RN,
+                                         weight_ids_host=wid)
+        want, wtr, wro = want.cpu().numpy(), wtr.cpu().numpy(), wro.cpu().numpy()
+        for rep in range(3):
+            got, tr, ro = eng.track_host(rgb, depth, synth.CAMERA_K, poses, ow, rgbA, depthA, TN, RN, weight_ids=wid, want_residuals=True)
+            assert np.array_equal(got, want) and np.array_equal(tr, wtr) and np.array_equal(ro, wro), (n, rep)
+        assert eng.last_step_was_graph()
+    with pytest.raises(ValueError):
+        eng.track_host(rgb, depth.astype(np.float32), synth.CAMERA_K, poses, ow, rgbA, depthA, TN, RN)
+    with pytest.raises(RuntimeError):                           # more tracks than the context was created for
+        big = 70
+        eng.track_host(rgb, depth, synth.CAMERA_K, np.tile(poses[:1], (big, 1, 1)), np.full(big, 200.0), np.tile(rgbA[:1], (big, 1, 1, 1)),
+                       np.tile(depthA[:1], (big, 1, 1)), TN, RN)
+    # the Tracker's numpy path is this call; SE3TN_HOST_CALL=0 keeps the tensor plumbing -- same poses either way
+    info = {'resolution': 176, 'boundingbox': 10, 'object_width': 200.0,
+            'camera': {'focalX': synth.CAMERA_K[0, 0], 'focalY': synth.CAMERA_K[1, 1], 'centerX': synth.CAMERA_K[0, 2],
+                       'centerY': synth.CAMERA_K[1, 2], 'height': 480, 'width': 640}}
+    trk = pkg.Tracker(info, mean, std, {'state_dict': synth.make_state_dict(0)}, model_path=None, engine=eng)
+    rgb, depth, poses, rgbA, depthA = _frame_case(synth, 2, 5)
+    a = trk.on_track_batch(poses, rgb, depth, rgbA, depthA)
+    monkeypatch.setenv('SE3TN_HOST_CALL', '0')
+    b = trk.on_track_batch(poses, rgb, depth, rgbA, depthA)
+    assert np.array_equal(a, b)
+
+
 def test_track_batch_mixed_weight_sets(synth, eng):
     n = 6
     rgb, depth, poses, rgbA, depthA = _frame_case(synth, n, 6)
@@ -585,6 +628,75 @@ def test_render_near_plane_clipping_bit_exact(pkg, synth, eng):
         assert (dep > 0).sum() > 5000
         assert np.array_equal(dep, rdep), 'level %d: %d depth pixels differ' % (level, (dep != rdep).sum())
         assert np.array_equal(rgb, rrgb), 'level %d: %d colour values differ' % (level, (rgb != rrgb).sum())
+
+
+def test_render_pyrender_mode_bit_exact_vs_oracle(pkg, synth, eng):
+    """The reference's other producer of input A (dataset_info['renderer'] == 'pyrenderer': offscreen_renderer.py:77-83, then
+    crop_bbox, predict.py:210-214).  The oracle literally renders the whole 480 x 640 camera image and crops it; the CUDA
+    rasteriser shades only the camera pixels crop_bbox's nearest-neighbour resize picks -- same bytes, for windows that are
+    enlarged (far object), reduced (near object), hang over the image border, and for a model crossing the near plane."""
+    import cv2
+    K, H, W = synth.CAMERA_K, 480, 640
+    poses = synth.raw_poses(4, seed=11)
+    poses[0, :3, 3] = (0.05, -0.04, 0.33)           # near: window larger than 176 px -> the resize skips camera pixels
+    poses[1, :3, 3] = (-0.08, 0.06, 1.4)            # far: window smaller than 176 px -> camera pixels are repeated
+    poses[2, :3, 3] = (0.13, -0.09, 0.55)           # window hangs over the right / top border of the camera image
+    for level, mid in ((2, 6), (1, 7)):
+        mesh = synth.mesh(level, seed=level)
+        eng.set_mesh(mesh, mid)
+        dev = eng.device
+        ids = torch.full((len(poses),), mid, dtype=torch.int32, device=dev)
+        ow = torch.full((len(poses),), 200.0, dtype=torch.float64, device=dev)
+        rgb, dep = eng.render(K, torch.from_numpy(poses).to(dev), ow, ids, mode='pyrender', image_hw=(H, W))
+        rgb, dep = rgb.cpu().numpy(), dep.cpu().numpy()
+        for i, p in enumerate(poses):
+            rr, rd = O.render_window_pyrender(p, K, 200.0, mesh, H, W)
+            assert np.array_equal(dep[i], rd), 'level %d pose %d: %d depth pixels differ' % (level, i, (dep[i] != rd).sum())
+            assert np.array_equal(rgb[i], rr), 'level %d pose %d: %d colour values differ' % (level, i, (rgb[i] != rr).sum())
+        assert (dep > 0).sum() > 4000
+        # not the vispy-style image: unlit colours, another depth linearisation
+        lit, _ = eng.render(K, torch.from_numpy(poses).to(dev), ow, ids)
+        assert not np.array_equal(lit.cpu().numpy(), rgb)
+    # near-plane straddlers through the same mode
+    mesh = dict(synth.mesh(1, seed=2))
+    mesh['pos'] = (mesh['pos'] * np.array([1.0, 1.0, 24.0], np.float32)).astype(np.float32)
+    eng.set_mesh(mesh, 8)
+    p = np.eye(4); p[:3, :3] = cv2.Rodrigues(np.array((0.05, 0.02, 0.1)))[0]; p[:3, 3] = (0.045, 0.0, 0.45)
+    rgb, dep = eng.render(K, torch.from_numpy(p[None]).to(eng.device), torch.full((1,), 200.0, dtype=torch.float64, device=eng.device),
+                          torch.full((1,), 8, dtype=torch.int32, device=eng.device), mode='pyrender', image_hw=(H, W))
+    rr, rd = O.render_window_pyrender(p, K, 200.0, mesh, H, W)
+    assert np.array_equal(dep[0].cpu().numpy(), rd) and np.array_equal(rgb[0].cpu().numpy(), rr) and (rd > 0).sum() > 3000
+    with pytest.raises(ValueError):
+        eng.render(K, torch.from_numpy(p[None]).to(eng.device), torch.full((1,), 200.0, dtype=torch.float64, device=eng.device), mode='pyrender')
+
+
+def test_tracker_selects_the_pyrender_style_renderer(pkg, synth, tmp_path):
+    """dataset_info['renderer'] == 'pyrenderer' with a .obj model (predict.py:161-164): Tracker builds the CUDA rasteriser in
+    its full-camera-image mode, and on_track(prev_pose, rgb, depth) equals the oracle fed with the oracle's render."""
+    mesh = synth.mesh(2, seed=4)
+    obj = str(tmp_path / 'model.obj')
+    with open(obj, 'w') as f:
+        for v, c in zip(mesh['pos'], mesh['col']):
+            f.write('v %.9g %.9g %.9g %.9g %.9g %.9g\n' % (*v, *(c / 255.0)))
+        for t in mesh['faces']:
+            f.write('f %d %d %d\n' % tuple(t + 1))
+    sd = synth.make_state_dict(0)
+    mean, std = synth.default_mean_std()
+    K = synth.CAMERA_K
+    info = {'resolution': 176, 'boundingbox': 10, 'object_width': 200.0, 'renderer': 'pyrenderer',
+            'camera': {'focalX': K[0, 0], 'focalY': K[1, 1], 'centerX': K[0, 2], 'centerY': K[1, 2], 'height': 480, 'width': 640}}
+    trk = pkg.Tracker(info, mean, std, {'state_dict': sd}, model_path=obj, max_batch=4)
+    assert type(trk.renderer).__name__ == 'CudaRenderer' and trk.renderer.mode == 'pyrender' and trk.renderer.image_hw == (480, 640)
+    loaded = trk.renderer.mesh
+    assert np.array_equal(loaded['pos'], mesh['pos']) and np.array_equal(loaded['faces'], mesh['faces']) and np.array_equal(loaded['col'], mesh['col'])
+    rgb, depth = synth.raw_frame(9)
+    pose = synth.raw_poses(2, seed=9)[1]
+    ra, da = trk.render_window(pose)
+    ora, oda = O.render_window_pyrender(pose, K, 200.0, loaded, 480, 640)
+    assert np.array_equal(ra, ora) and np.array_equal(da, oda) and (da > 0).sum() > 1000
+    got = trk.on_track(pose, rgb, depth)
+    ref = O.on_track(sd, pose, rgb, depth, ora, oda, K, 200.0, mean, std)
+    assert np.abs(got - ref).max() < POSE_ATOL
 
 
 def test_render_edge_cases(pkg, synth, eng):

@@ -84,3 +84,43 @@ def test_sequence_layout_helpers(synth, tmp_path):
     np.save(tmp_path / 'mean.npy', mean); np.save(tmp_path / 'std.npy', std)
     di, m, s = pr.load_run_config(str(tmp_path / 'train'), str(tmp_path))
     assert di == info and np.array_equal(m, mean) and np.array_equal(s, std)
+
+
+def test_obj_loader_vertex_colours_polygons_and_texture(mio, tmp_path):
+    """What the pyrender producer's model files look like (offscreen_renderer.py:57-60 loads them through trimesh):
+    v/vt/vn index triples become unique vertices, polygons are fanned, colours come from `v x y z r g b`, else from the
+    texture at each vertex's uv (nearest texel, rows flipped: predict.py:167-179), else from the material."""
+    import cv2
+    # a quad (fanned into two triangles) with per-vertex colours and no normals
+    p = str(tmp_path / 'quad.obj')
+    with open(p, 'w') as f:
+        f.write('# quad\nv 0 0 0 1 0 0\nv 1 0 0 0 1 0\nv 1 1 0 0 0 1\nv 0 1 0 1 1 1\nf 1 2 3 4\n')
+    m = mio.load_obj_mesh(p)
+    assert m['pos'].shape == (4, 3) and m['pos'].dtype == np.float32 and m['faces'].dtype == np.int32
+    assert m['faces'].tolist() == [[0, 1, 2], [0, 2, 3]]
+    assert m['col'].tolist() == [[255, 0, 0], [0, 255, 0], [0, 0, 255], [255, 255, 255]]
+    assert np.allclose(m['nrm'], [[0, 0, 1]] * 4)                                      # derived: the quad lies in z = 0, counter-clockwise
+    # textured: the same position with two different uv's is two vertices; texel lookup with the v axis flipped
+    tex = np.zeros((4, 8, 3), np.uint8)
+    tex[0, 0] = (10, 20, 30); tex[3, 7] = (200, 100, 50); tex[3, 0] = (1, 2, 3)      # RGB; row 0 is the TOP of the image = v 1
+    cv2.imwrite(str(tmp_path / 'tex.png'), tex[..., ::-1])
+    with open(str(tmp_path / 'm.mtl'), 'w') as f:
+        f.write('newmtl a\nKd 0.2 0.4 0.6\nmap_Kd tex.png\n')
+    q = str(tmp_path / 'tri.obj')
+    with open(q, 'w') as f:
+        f.write('mtllib m.mtl\nv 0 0 0\nv 1 0 0\nv 0 1 0\nvt 0 1\nvt 1 0\nvt 0 0\nvn 0 0 1\nusemtl a\nf 1/1/1 2/2/1 3/3/1\nf 1/3/1 2/2/1 3/1/1\n')
+    t = mio.load_obj_mesh(q)
+    assert t['pos'].shape == (5, 3)                                                   # (v1,vt1) (v2,vt2) (v3,vt3) (v1,vt3) (v3,vt1); (v2,vt2) shared
+    assert t['faces'].tolist() == [[0, 1, 2], [3, 1, 4]]
+    assert t['col'][0].tolist() == [10, 20, 30] and t['col'][1].tolist() == [200, 100, 50] and t['col'][2].tolist() == [1, 2, 3]
+    assert t['col'][3].tolist() == [1, 2, 3] and t['col'][4].tolist() == [10, 20, 30]
+    assert np.allclose(t['nrm'], [[0, 0, 1]] * 5)
+    # no texture file: the material's diffuse colour; no material at all: mid grey
+    os.remove(str(tmp_path / 'tex.png'))
+    assert mio.load_obj_mesh(q)['col'][0].tolist() == [51, 102, 153]
+    os.remove(str(tmp_path / 'm.mtl'))
+    assert mio.load_obj_mesh(q)['col'][0].tolist() == [128, 128, 128]
+    assert mio.load_mesh(q)['faces'].shape == (2, 3)
+    with pytest.raises(ValueError):
+        open(str(tmp_path / 'empty.obj'), 'w').write('# nothing\n')
+        mio.load_obj_mesh(str(tmp_path / 'empty.obj'))

@@ -265,3 +265,50 @@ def test_render_oracle_near_plane_clipping_vs_ray_casting(synth):
             lost = np.isfinite(z) & ~(np.abs(z - _ray_cast_depth(kept, pose, K, u)) < 1e-6)   # a closed model: the far side shows instead
         assert lost.sum() > 300 and (dep[lost] > 0).mean() > 0.98
         assert rgb[dep > 0].max() > 0
+
+
+def test_render_full_frame_unlit_vs_ray_casting(synth):
+    """The pyrender-style producer of input A (offscreen_renderer.py:77-83; no pyrender here: parity unpinned): the full camera
+    image must show the surface a pinhole ray through every pixel centre (u + 0.5, v + 0.5) hits, with the metric depth pyrender
+    reports, unlit colours, and Tracker.render_window's crop (predict.py:210-214) must be crop_bbox of exactly that image."""
+    import cv2
+    mesh = synth.mesh(1, seed=2)
+    K = synth.CAMERA_K
+    H, W = 480, 640
+    pose = synth.raw_poses(3, seed=21)[2]
+    color, depth = O.render_full_frame_unlit(pose, K, mesh, H, W)
+    assert color.shape == (H, W, 3) and depth.dtype == np.float32
+    ys, xs = np.nonzero(depth > 0)
+    assert len(ys) > 500
+    y0, y1, x0, x1 = max(ys.min() - 6, 0), min(ys.max() + 7, H), max(xs.min() - 6, 0), min(xs.max() + 7, W)
+    uu, vv = np.meshgrid(np.arange(x0, x1) + 0.5, np.arange(y0, y1) + 0.5)
+    D = np.stack([(uu - K[0, 2]) / K[0, 0], (vv - K[1, 2]) / K[1, 1], np.ones_like(uu)], -1).reshape(-1, 3)
+    P = mesh['pos'].astype(np.float64) @ pose[:3, :3].T + pose[:3, 3]
+    best = np.full(len(D), np.inf)
+    for f in mesh['faces']:
+        v0, v1, v2 = P[f[0]], P[f[1]], P[f[2]]
+        e1, e2 = v1 - v0, v2 - v0
+        pv = np.cross(D, e2); det = pv @ e1
+        with np.errstate(divide='ignore', invalid='ignore'):
+            inv = 1.0 / det; tv = -v0
+            a = (pv @ tv) * inv; qv = np.cross(tv, e1); b = (D @ qv) * inv; t = (qv @ e2) * inv
+        hit = (np.abs(det) > 1e-15) & (a >= 0) & (b >= 0) & (a + b <= 1) & (t > 0.1) & (t < 2.0)
+        best = np.where(hit & (t < best), t, best)
+    z = best.reshape(y1 - y0, x1 - x0)
+    sub = depth[y0:y1, x0:x1]
+    ray_fg, ras_fg = np.isfinite(z), sub > 0
+    edge = cv2.dilate(ray_fg.astype(np.uint8), np.ones((3, 3), np.uint8)) != cv2.erode(ray_fg.astype(np.uint8), np.ones((3, 3), np.uint8))
+    assert (ray_fg == ras_fg)[~edge].all() and (ray_fg != ras_fg).sum() < 0.05 * ras_fg.sum()
+    both = ray_fg & ras_fg & ~edge
+    assert np.abs(sub[both].astype(np.float64) - z[both]).max() < 2e-4          # float32 z-buffer + float32 linearisation
+    outside = np.ones((H, W), bool); outside[y0:y1, x0:x1] = False
+    assert not depth[outside].any() and not color[outside].any()
+    # unlit: every foreground colour lies within the hull of the model's vertex colours
+    fg = color[depth > 0].astype(int)
+    assert fg.min() >= int(mesh['col'].min()) - 1 and fg.max() <= int(mesh['col'].max()) + 1
+    # the crop: what predict.py:210-214 does with that image
+    rgbA, depthA = O.render_window_pyrender(pose, K, 200.0, mesh, H, W)
+    bbox = O.compute_bbox(pose, K, 200.0, scale=(1000, 1000, 1000))
+    want = O.crop_bbox(color, (depth * np.float32(1000)).astype(np.uint16), bbox, (176, 176))
+    assert rgbA.shape == (176, 176, 3) and depthA.dtype == np.uint16
+    assert np.array_equal(rgbA, want[0]) and np.array_equal(depthA, want[1]) and (depthA > 0).sum() > 1500
