@@ -913,18 +913,29 @@ conv_trunk_kernel(const __grid_constant__ TrunkParams p)
                         *reinterpret_cast<uint4*>(&stg[lane][16 + jj]) = make_uint4(r1[jj], r1[jj + 1], r1[jj + 2], r1[jj + 3]);
                     }
                 } else {
-                    // sum of the pieces, row `lane` of this block, in piece order
-                    float4 a[8];
-#pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) a[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    for (int pc = 0; pc < p.ksplit; ++pc) {
-                        const float4* s4 = reinterpret_cast<const float4*>(slice_of(pc) + (c0 / 32) * 1024) + lane;
-#pragma unroll
-                        for (int jj = 0; jj < 8; ++jj) { const float4 v = __ldcg(s4 + jj * 32); a[jj].x += v.x; a[jj].y += v.y; a[jj].z += v.z; a[jj].w += v.w; }
-                    }
+                    // sum of the pieces, row `lane` of this block, in piece order.  All pieces' loads of half a row are issued before the
+                    // first add (16 x 16 bytes in flight per lane): two L2 round trips per block instead of one per piece
                     __syncwarp();
 #pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) *reinterpret_cast<float4*>(&stg[lane][4 * jj]) = a[jj];
+                    for (int hh = 0; hh < 2; ++hh) {
+                        float4 v[kSplitK][4];
+#pragma unroll
+                        for (int pc = 0; pc < kSplitK; ++pc) {
+                            if (pc < p.ksplit) {
+                                const float4* s4 = reinterpret_cast<const float4*>(slice_of(pc) + (c0 / 32) * 1024) + lane + hh * 128;
+#pragma unroll
+                                for (int jj = 0; jj < 4; ++jj) v[pc][jj] = __ldcg(s4 + jj * 32);
+                            }
+                        }
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                            for (int pc = 0; pc < kSplitK; ++pc)
+                                if (pc < p.ksplit) { a.x += v[pc][jj].x; a.y += v[pc][jj].y; a.z += v[pc][jj].z; a.w += v[pc][jj].w; }
+                            *reinterpret_cast<float4*>(&stg[lane][4 * (hh * 4 + jj)]) = a;
+                        }
+                    }
                 }
                 if (!split && c0 + 32 == kCols) {                 // last TMEM read of this unit: hand the accumulator back to the MMA warp
                     ptx::tc_fence_before();
