@@ -92,7 +92,7 @@ struct LayerDesc {
     int base_unit0;        // index of this layer's first UNSPLIT unit among all unsplit units of the launch (split-K scratch / counters)
     int units_per_image;   // tiles_x * tiles_y * n_tiles * groups (unsplit)
     int dep_layer;         // index (within the launch) of the layer whose per-image completion this layer waits for; -1: none
-    unsigned dep_target;   // value done[dep_layer][image] reaches when that image is complete (8 epilogue warps x units per image)
+    unsigned dep_target;   // value done[dep_layer][image] reaches when that image is complete (one signal per epilogue warp that finishes part of a unit: 8 x units per image; 16 x in 4-piece latency mode)
 };
 
 constexpr int kTrunkMaxLayers = 6;
@@ -108,12 +108,12 @@ struct TrunkParams {
     const CUtensorMap* gbmaps;     // per-set weight maps, entry [wid * kLayersPerSet + li]
     const float* const* gbias;     // per-set bias pointers, same indexing
     unsigned long long* trace;     // nullable (SE3TN_TRACE)
-    // latency mode (a handful of tracks): every unit's K loop is cut into `ksplit` pieces run by different CTAs; each piece dumps
-    // its fp32 accumulator to `partial`, and per (unit, epilogue-warp slice) the LAST piece to arrive sums all pieces in a fixed
-    // order and runs the normal epilogue.  1 = off.
+    // latency mode (a handful of tracks): every unit's K loop is cut into `ksplit` pieces run by different CTAs (units are dealt
+    // round robin so that they are); each piece dumps its fp32 accumulator to `partial`, then finishes ITS share of the unit's
+    // 32-column blocks: it waits for the other pieces' dumps, sums all pieces in a fixed order and runs the normal epilogue.  1 = off.
     int ksplit;
     float* partial;                // [unsplit unit][piece][8 warp slices][32-column block][float4 0..7][row]
-    unsigned* slice_cnt;           // [unsplit unit][8] arrival counters (zeroed before the launch)
+    unsigned* slice_cnt;           // [unsplit unit][8 warp slices] number of pieces that have dumped the slice (zeroed before the launch)
 };
 
 struct ResidentParams {

@@ -744,7 +744,11 @@ conv_trunk_kernel(const __grid_constant__ TrunkParams p)
             ptx::grid_dep_wait();                   // the first layer's input comes from the previous kernel
             int stage = 0; uint32_t phase = 0;
             int ps = 0; uint32_t pph = 0;
-            int u = static_cast<int>(atomicAdd(p.sched, 1u));
+            // latency mode: the pieces of a unit (consecutive indices) must sit on DIFFERENT CTAs, because a piece's epilogue waits for
+            // the others' partial sums -- units are dealt round robin (index i goes to CTA i mod grid; every wait then points at a
+            // smaller index or at a piece whose CTA only has smaller indices left to finish: no cycle).  Throughput mode: first come, first served.
+            const bool dealt = BN == 128 && p.ksplit > 1;
+            int u = dealt ? static_cast<int>(blockIdx.x) : static_cast<int>(atomicAdd(p.sched, 1u));
             for (;;) {
                 ptx::mbar_wait(&sched_empty[ps], pph ^ 1);
                 sched_slot[ps] = u;
@@ -768,7 +772,7 @@ conv_trunk_kernel(const __grid_constant__ TrunkParams p)
                 unit_stamp(p, u, 0);
                 if (L.kind == KIND_S1) trunk_load_unit<KIND_S1>(L, c, sA, a_full, a_empty, stage, phase, C::kAStages);
                 else                   trunk_load_unit<KIND_S2>(L, c, sA, a_full, a_empty, stage, phase, C::kAStages);
-                u = static_cast<int>(atomicAdd(p.sched, 1u));   // pull the next unit only now: look-ahead = the A pipeline depth
+                u = dealt ? u + static_cast<int>(gridDim.x) : static_cast<int>(atomicAdd(p.sched, 1u));   // pull the next unit only now: look-ahead = the A pipeline depth
             }
         }
     } else if (warp == 3) {
@@ -852,14 +856,16 @@ conv_trunk_kernel(const __grid_constant__ TrunkParams p)
             if (it == 0 && threadIdx.x == 128) trace_stamp(p.trace, 5);
             if (threadIdx.x == 128) unit_stamp(p, u, 3);
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + half * kCols;
-            const bool split = p.ksplit > 1;
+            const bool split = BN == 128 && p.ksplit > 1;      // latency mode exists for the 128-channel units only (checked at launch)
             // this warp's slice (32 rows x kCols columns) of piece `pc` of this unit in the split-K scratch: row-major, 32-column blocks
             auto slice_of = [&](int pc) -> float* {
                 return p.partial + ((static_cast<size_t>(c.gidx) * p.ksplit + pc) * 8 + ew) * (32 * kCols);
             };
+            unsigned own = 0xFu;                                 // which of this warp's 32-column blocks it post-processes (bit per block)
             if (split) {
-                // latency mode: this CTA only summed K chunks [c0, c1).  Dump the fp32 slice, hand the accumulator back, and let the
-                // LAST piece to arrive for this slice add all pieces (fixed order 0..ksplit-1: the result does not depend on arrival order)
+                // latency mode: this CTA only summed K chunks [c0, c1).  Dump the fp32 slice and hand the accumulator back.  The unit's
+                // four 32-column blocks are then finished by its pieces in parallel: block b by piece b * ksplit / 4, which waits until
+                // every piece has dumped and adds them in piece order 0..ksplit-1 (the result does not depend on arrival order).
                 float* dst = slice_of(c.piece);
 #pragma unroll 1
                 for (int c0 = 0; c0 < kCols; c0 += 32) {
@@ -878,16 +884,30 @@ conv_trunk_kernel(const __grid_constant__ TrunkParams p)
                 ptx::tc_fence_before();
                 __threadfence();
                 __syncwarp();
-                unsigned arrived = 0;
-                if (lane == 0) { ptx::mbar_arrive(&tmem_empty[acc]); arrived = atomicAdd(p.slice_cnt + c.gidx * 8 + ew, 1u); }
-                arrived = __shfl_sync(0xffffffffu, arrived, 0);
-                if (arrived + 1 != static_cast<unsigned>(p.ksplit)) { if (threadIdx.x == 128) unit_stamp(p, u, 4); continue; }   // another piece finishes this slice
+                if (lane == 0) { ptx::mbar_arrive(&tmem_empty[acc]); atomicAdd(p.slice_cnt + c.gidx * 8 + ew, 1u); }
+                own = 0u;
+#pragma unroll
+                for (int bi = 0; bi < kCols / 32; ++bi)
+                    if ((half * (kCols / 32) + bi) * p.ksplit / (BN / 32) == c.piece) own |= 1u << bi;
+                if (!own) { if (threadIdx.x == 128) unit_stamp(p, u, 4); continue; }   // other pieces finish this warp's blocks
+                if (lane == 0) {
+                    const int* cnt = reinterpret_cast<const int*>(p.slice_cnt + c.gidx * 8 + ew);
+                    const long long t0 = clock64();
+                    while (ptx::ld_acquire_gpu(cnt) < p.ksplit) {
+                        __nanosleep(32);
+                        if (clock64() - t0 > (1ll << 34)) __trap();
+                    }
+                }
+                __syncwarp();
                 __threadfence();                                                     // order the reads below after the other pieces' dumps
             }
 #pragma unroll 1
             for (int c0 = 0; c0 < kCols; c0 += 32) {
+                if (!((own >> (c0 / 32)) & 1u)) continue;
                 const int chan = ch0 + c0;                        // first channel of this 32-channel block
-                // residual pieces first: their L2 latency overlaps the TMEM load and the staging round trip below
+                // bias and residual pieces first: their L2 latency overlaps the TMEM load / the split-K reads and the staging round trip below
+                float4 b4;
+                if (BN == 128) b4 = __ldg(reinterpret_cast<const float4*>(bias_base + chan + grp * 4));
                 float4 r4[8];                                    // TF32: 4 fp32 words
                 uint2 rh[8], rl[8];                              // bf16: 4 channels hi (and lo, BF16X3)
                 if (L.res) {
@@ -944,7 +964,7 @@ conv_trunk_kernel(const __grid_constant__ TrunkParams p)
                 } else {
                     __syncwarp();
                 }
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias_base + chan + grp * 4));
+                if (BN != 128) b4 = __ldg(reinterpret_cast<const float4*>(bias_base + chan + grp * 4));   // 256-channel units: registers are tight, and the latency hides behind the next unit's MMAs
                 float4 a4[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {

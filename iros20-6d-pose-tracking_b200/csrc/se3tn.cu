@@ -498,7 +498,8 @@ int run_network(se3tn_ctx* c, int weight_id, int first, int n, int precision,
             LayerDesc& d = tp.layer[l];
             d.unit_base = base; base += n * d.units_per_image * ksplit;
             d.base_unit0 = base0; base0 += n * d.units_per_image;
-            if (l > 0) { d.dep_layer = l - 1; d.dep_target = 8u * static_cast<unsigned>(tp.layer[l - 1].units_per_image); }
+            // completion signals per unit: one per epilogue warp that finishes part of it (8; in 4-piece latency mode 4 warps of each piece finish one block each)
+            if (l > 0) { d.dep_layer = l - 1; d.dep_target = (ksplit == 4 ? 16u : 8u) * static_cast<unsigned>(tp.layer[l - 1].units_per_image); }
         }
         if (ksplit > 1 && base0 > kSplitMaxUnits) return fail(c, SE3TN_ERR_STATE, "split-K scratch too small");
         tp.ksplit = ksplit; tp.partial = c->partial;
