@@ -729,8 +729,9 @@ conv_trunk_kernel(const __grid_constant__ TrunkParams p)
     int sslot = 0; uint32_t sphase = 0;
     auto next_unit = [&](bool whole_warp) -> int {  // a consumer role's next work unit: called by a whole warp, or by lane 0 alone
         ptx::mbar_wait(&sched_full[sslot], sphase);
-        const int u = sched_slot[sslot];
-        if (whole_warp) __syncwarp();               // every lane has read the slot before it is handed back
+        int u = 0;
+        if (lane == 0) u = sched_slot[sslot];       // read by the one thread that hands the slot back (a direct mbarrier edge to the writer)
+        if (whole_warp) u = __shfl_sync(0xffffffffu, u, 0);
         if (lane == 0) ptx::mbar_arrive(&sched_empty[sslot]);
         if (++sslot == C::kSched) { sslot = 0; sphase ^= 1; }
         return u;

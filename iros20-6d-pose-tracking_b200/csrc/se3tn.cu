@@ -597,6 +597,9 @@ int se3tn_create(int device, int max_batch, void* workspace, se3tn_ctx** out) {
     int rc = build_activation_maps(c, 4, c->amap4);
     if (!rc) rc = build_activation_maps(c, 2, c->amap2);
     if (rc) { g_create_error = c->err; se3tn_destroy(c); return rc; }
+    // the memsets above ran on the NULL stream: later launches may use non-blocking streams, which do not wait for it
+    e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); se3tn_destroy(c); return fail(nullptr, SE3TN_ERR_CUDA, "se3tn_create: " + m); }
     *out = c;
     return SE3TN_OK;
 }
@@ -1028,7 +1031,7 @@ int se3tn_track_host(se3tn_ctx* c, const uint8_t* frame_rgb, const uint16_t* fra
         cudaFree(io.dev); io.dev = nullptr; if (io.pin) { cudaFreeHost(io.pin); io.pin = nullptr; }
         io.H = io.W = io.n_cap = 0;
         CU_TRY(c, cudaMalloc(&io.dev, dev_bytes));
-        CU_TRY(c, cudaMemset(io.dev, 0, dev_bytes));            // frame pixels outside the uploaded windows are never read; keep them defined
+        CU_TRY(c, cudaMemsetAsync(io.dev, 0, dev_bytes, s));    // on the caller's stream, ahead of the copies below; frame pixels outside the uploaded windows are never read, keep them defined
         CU_TRY(c, cudaHostAlloc(&io.pin, px * 5 + per * cap + 4096, cudaHostAllocDefault));
         io.dev_bytes = dev_bytes; io.pin_bytes = px * 5 + per * cap + 4096; io.H = H; io.W = W; io.n_cap = cap;
         drop_graphs(c);                                          // steps captured against the old addresses
