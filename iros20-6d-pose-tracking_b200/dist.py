@@ -30,34 +30,60 @@ def padded_count(n_tracks, world_size):
     return (n_tracks + world_size - 1) // world_size
 
 
+class GatherPlan:
+    """The pose exchange for one partition of the track set, prepared once: shard sizes, padding, and -- when the shards are
+    not simply consecutive blocks of the original order (e.g. weight_id = i mod G) -- the permutation
+    that puts the rank-major gathered buffer back into ORIGINAL track order, resident on the device.  gather() is then one
+    all_gather_into_tensor plus at most one index_select; nothing is copied from the host per call (a per-call index
+    upload is a synchronous copy: it blocks the host until the step in front of it has finished, and the next step's launch
+    with it)."""
+    def __init__(self, shards, rank, world_size, device=None):
+        self.shards, self.rank, self.world_size = shards, rank, world_size
+        self.sizes = [len(s) for s in shards]
+        self.n_total = int(sum(self.sizes))
+        self.per = max(self.sizes) if self.sizes else 0
+        self.identity = (all(z == self.per for z in self.sizes)
+                         and np.array_equal(np.concatenate(shards) if shards else np.zeros(0, np.int64), np.arange(self.n_total)))
+        self.perm = None
+        if not self.identity:
+            pos = np.empty(self.n_total, dtype=np.int64)          # original track t sits at gathered[pos[t]]
+            for r, idx in enumerate(shards):
+                pos[idx] = r * self.per + np.arange(len(idx))
+            self.perm = torch.from_numpy(pos)
+            if device is not None:
+                self.perm = self.perm.to(device)
+
+    def gather(self, local_poses, group=None):
+        """local_poses: (len(shards[rank]),4,4) on this rank's device -> (n_tracks,4,4) in original track order on every rank."""
+        dev = local_poses.device
+        if self.perm is not None and self.perm.device != dev:
+            self.perm = self.perm.to(dev)
+        if self.identity:
+            # equal consecutive shards in original order: the gathered buffer IS the result (one NCCL call, no other kernel)
+            out = torch.empty(self.n_total, 4, 4, dtype=local_poses.dtype, device=dev)
+            if self.world_size == 1:
+                out.copy_(local_poses)
+            else:
+                dist.all_gather_into_tensor(out.view(-1), local_poses.contiguous().view(-1), group=group)
+            return out
+        buf = local_poses.contiguous()
+        if buf.shape[0] != self.per:                               # uneven shards are padded to the largest one
+            buf = torch.zeros(self.per, 4, 4, dtype=local_poses.dtype, device=dev)
+            buf[:local_poses.shape[0]] = local_poses
+        gathered = torch.empty(self.world_size * self.per, 4, 4, dtype=local_poses.dtype, device=dev)
+        if self.world_size == 1:
+            gathered.copy_(buf)
+        else:
+            dist.all_gather_into_tensor(gathered.view(-1), buf.view(-1), group=group)
+        return gathered.index_select(0, self.perm)
+
+
 def all_gather_poses(local_poses, shards, rank, world_size, group=None):
     """local_poses: (len(shards[rank]),4,4) float64 on this rank's device.  Returns the full
     (n_tracks,4,4) tensor in ORIGINAL track order on every rank.  Uneven shards are padded to the
-    largest shard so a single fixed-size all_gather_into_tensor suffices."""
-    n_total = int(sum(len(s) for s in shards))
-    per = max(len(s) for s in shards)
-    sizes = [len(s) for s in shards]
-    # fast path: equal contiguous shards in original order -> the gathered buffer IS the result (one NCCL call, no
-    # scatter kernels); this is the case whenever the track list is already grouped by weight id
-    if all(z == per for z in sizes) and np.array_equal(np.concatenate(shards), np.arange(n_total)):
-        out = torch.empty(n_total, 4, 4, dtype=local_poses.dtype, device=local_poses.device)
-        if world_size == 1:
-            out.copy_(local_poses)
-        else:
-            dist.all_gather_into_tensor(out.view(-1), local_poses.contiguous().view(-1), group=group)
-        return out
-    buf = torch.zeros(per, 4, 4, dtype=local_poses.dtype, device=local_poses.device)
-    buf[:local_poses.shape[0]] = local_poses
-    gathered = torch.empty(world_size * per, 4, 4, dtype=local_poses.dtype, device=local_poses.device)
-    if world_size == 1:
-        gathered.copy_(buf)
-    else:
-        dist.all_gather_into_tensor(gathered.view(-1), buf.view(-1), group=group)
-    out = torch.empty(n_total, 4, 4, dtype=local_poses.dtype, device=local_poses.device)
-    for r in range(world_size):
-        idx = torch.as_tensor(shards[r], device=local_poses.device)
-        out[idx] = gathered[r * per:r * per + len(shards[r])]
-    return out
+    largest shard so a single fixed-size all_gather_into_tensor suffices.  One-off convenience: callers that exchange
+    poses every frame keep a GatherPlan (ShardedTracker does)."""
+    return GatherPlan(shards, rank, world_size, local_poses.device).gather(local_poses, group=group)
 
 
 class ShardedTracker:
@@ -67,8 +93,11 @@ class ShardedTracker:
     overlap_gather (default): the pose all-gather is the only exchange step and nothing on this rank's data path needs
     its result (frame k+1's crop uses the rank's OWN updated poses), so it is issued on a side stream behind an event
     and the next step's kernels do not wait for it -- a 4 KB-per-rank NCCL call costs ~25 us of latency that would
-    otherwise sit on the critical path of a 0.8 ms step.  The gathered tensor of step k may be read on the compute stream
-    after wait_gather() (step k+1 calls it first thing, which also keeps per-step device timing honest)."""
+    otherwise sit on the critical path of a 0.8 ms step.  Nor does a step wait for the PREVIOUS step's gather: an all-gather
+    completes only when every rank has reached it, so waiting for it at the start of each step would put the ranks in lock
+    step (one slow step anywhere stalls all of them); a step only waits for the gather issued TWO steps earlier, the last
+    reader of the output set it is about to overwrite.  The gathered tensor of step k may be read on the compute stream
+    after wait_gather(), which waits for every gather still in flight."""
     def __init__(self, engine, weight_ids, K, object_width, trans_normalizer, rot_normalizer,
                  rank=0, world_size=1, precision='bf16x3', overlap_gather=True):
         self.engine = engine
@@ -76,6 +105,7 @@ class ShardedTracker:
         self.weight_ids = np.asarray(weight_ids, dtype=np.int32)
         self.shards = shard_tracks(self.weight_ids, world_size)
         self.mine = self.shards[rank]
+        self.plan = GatherPlan(self.shards, rank, world_size, engine.device)
         # device-side index of this rank's tracks (indexing a CUDA tensor with the numpy array would stage a synchronous
         # host->device copy on every call and serialise host and GPU)
         self.mine_dev = torch.as_tensor(np.ascontiguousarray(self.mine), dtype=torch.long).to(engine.device)
@@ -89,7 +119,7 @@ class ShardedTracker:
         self.local_ow = torch.from_numpy(np.ascontiguousarray(ow[self.mine])).to(dev)
         self.overlap_gather = bool(overlap_gather) and world_size > 1
         self._comm_stream = torch.cuda.Stream(device=dev) if self.overlap_gather else None
-        self._gather_done = None
+        self._pending = []                         # events of the all-gathers still in flight, oldest first
         # two rotating sets of output tensors: stable device addresses keep the step's CUDA graph key stable (libse3tn replays one
         # graph per distinct set of pointers); a returned pose tensor stays valid until the step after the next one
         n = len(self.mine)
@@ -98,13 +128,16 @@ class ShardedTracker:
         self._flip = 0
 
     def wait_gather(self):
-        """Make the current stream wait for the last overlapped all-gather (no-op when none is pending)."""
-        if self._gather_done is not None:
-            torch.cuda.current_stream(self.engine.device).wait_event(self._gather_done)
-            self._gather_done = None
+        """Make the current stream wait for every overlapped all-gather still in flight (no-op when none is)."""
+        cur = torch.cuda.current_stream(self.engine.device)
+        for ev in self._pending:
+            cur.wait_event(ev)
+        self._pending = []
 
     def step(self, frame_rgb, frame_depth, local_poses, local_rgbA, local_depthA, gather=True):
-        self.wait_gather()
+        # two rotating output sets: the one written now was last read by the gather issued two steps ago
+        while len(self._pending) >= 2:
+            torch.cuda.current_stream(self.engine.device).wait_event(self._pending.pop(0))
         self._flip ^= 1
         o = self._outs[self._flip]
         out, _, _ = self.engine.track_batch(frame_rgb, frame_depth, self.K, local_poses, self.local_ow,
@@ -114,12 +147,13 @@ class ShardedTracker:
         if not gather:
             return out, None
         if not self.overlap_gather:
-            return out, all_gather_poses(out, self.shards, self.rank, self.world_size)
+            return out, self.plan.gather(out)
         cur = torch.cuda.current_stream(self.engine.device)
         ready = torch.cuda.Event(); ready.record(cur)
         self._comm_stream.wait_event(ready)
         with torch.cuda.stream(self._comm_stream):
-            gathered = all_gather_poses(out, self.shards, self.rank, self.world_size)
-            self._gather_done = torch.cuda.Event(); self._gather_done.record(self._comm_stream)
+            gathered = self.plan.gather(out)
+            done = torch.cuda.Event(); done.record(self._comm_stream)
+            self._pending.append(done)
         gathered.record_stream(cur)                # ... and `gathered` will be read here after wait_gather()
         return out, gathered
