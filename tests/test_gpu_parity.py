@@ -909,6 +909,40 @@ def test_ycb_video_drivers_on_synthetic_layout(pkg, synth, tmp_path):
         refq = oracle_chain(seq, traj[seq][0])
         got = np.stack([np.loadtxt(str(tmp_path / 'o3' / ('seq%d' % seq) / ('%07d.txt' % i))) for i in range(nframes)])
         assert np.abs(got - refq).max() < 6 * POSE_ATOL and np.allclose(got, res[seq])
+
+    # (4) eval_ycb.py's scoring of those folders (reference eval_ycb.py:67-119): key frames only, model points from CADmodels/*/points.xyz,
+    #     keyframe.txt under YCB_Video_toolbox/ -- against the oracle's ADD / ADD-S / VOCap on the same files
+    E = importlib.import_module('iros20-6d-pose-tracking_b200.eval_ycb')
+    import argparse, shutil
+    pts = np.asarray(trk.object_cloud.points)
+    for k in range(1, 6):
+        d = ycb / 'CADmodels' / ('%03d_object' % k)
+        d.mkdir(parents=True)
+        np.savetxt(str(d / 'points.xyz'), pts if k == cls else pts * (1 + 0.1 * k))
+    shutil.copy(str(ycb / 'image_sets' / 'keyframe.txt'), str(ycb / 'YCB_Video_toolbox' / 'keyframe.txt'))
+    adi_errs, add_errs = E.eval_one_class(argparse.Namespace(res_dir=str(tmp_path / 'o3') + '/', ycb_dir=str(ycb), class_id=cls))
+    keyed = [(48, 0), (48, 1), (49, 0)]                              # keyframe.txt above: 0048/000001, 0048/000002, 0049/000001
+    want_adi = np.sort([O.adi(res[s][i], traj[s][i], pts) for s, i in keyed])
+    want_add = np.sort([O.add(res[s][i], traj[s][i], pts) for s, i in keyed])
+    assert adi_errs.shape == (3,) and np.allclose(adi_errs, want_adi, rtol=0, atol=1e-12) and np.allclose(add_errs, want_add, rtol=0, atol=1e-12)
+    assert abs(E.VOCap(adi_errs) - O.vocap(want_adi)) < 1e-12
+    root = tmp_path / 'all'
+    for k in range(1, 22):                                            # eval_all: 21 class folders, each with one run folder
+        (root / ('%02d' % k)).mkdir(parents=True)
+        os.symlink(str(tmp_path / 'o3'), str(root / ('%02d' % k) / 'run'))
+    for k in range(6, 22):
+        d = ycb / 'CADmodels' / ('%03d_object' % k)
+        d.mkdir(parents=True); np.savetxt(str(d / 'points.xyz'), pts)
+        (ycb / 'data_organized' / '0048' / 'pose_gt' / str(k)).mkdir()
+    for k in list(range(1, cls)) + list(range(cls + 1, 22)):          # the other classes: same poses as ground truth files
+        for seq in (48, 49):
+            src = ycb / 'data_organized' / ('%04d' % seq) / 'pose_gt' / str(cls)
+            dst = ycb / 'data_organized' / ('%04d' % seq) / 'pose_gt' / str(k)
+            dst.mkdir(parents=True, exist_ok=True)
+            for f in os.listdir(str(src)):
+                shutil.copy(str(src / f), str(dst / f))
+    adi_ap, add_ap, total = E.main(['--ycb_dir', str(ycb), '--res_root', str(root), '--expected_total', '63'])
+    assert total == 63 and 0.0 <= add_ap <= adi_ap <= 100.0
     trk.engine.close()
 
 
