@@ -56,3 +56,27 @@ def test_all_gather_single_rank_is_identity_permutation():
     local = torch.arange(4, dtype=torch.float64).view(4, 1, 1).expand(4, 4, 4).contiguous()[torch.as_tensor(shards[0])]
     full = D.all_gather_poses(local, shards, 0, 1)
     assert [float(full[i, 0, 0]) for i in range(4)] == [0.0, 1.0, 2.0, 3.0]
+
+
+def test_gather_plan_identity_and_permutation():
+    """GatherPlan: consecutive equal shards need no permutation (the gathered buffer IS the result); anything else gets the
+    inverse permutation once, and a plan is reusable call after call (ShardedTracker keeps one)."""
+    wid = np.repeat(np.arange(4), 4)                               # already grouped and sorted: shards are consecutive blocks
+    plan = D.GatherPlan(D.shard_tracks(wid, 4), 2, 4)
+    assert plan.identity and plan.perm is None and plan.per == 4 and plan.n_total == 16
+    wid = np.array([i % 5 for i in range(13)])                     # weight_id = i mod G (SURVEY 8d config 4), uneven shards
+    shards = D.shard_tracks(wid, 3)
+    plan = D.GatherPlan(shards, 0, 3)
+    assert not plan.identity and plan.per == 5 and plan.perm.shape == (13,)
+    # what the ranks would send, rank-major and padded, and what comes out in original order
+    gathered = torch.zeros(3 * plan.per, 4, 4, dtype=torch.float64)
+    for r, idx in enumerate(shards):
+        for j, t in enumerate(idx):
+            gathered[r * plan.per + j] = float(t)
+    out = gathered.index_select(0, plan.perm)
+    assert [float(out[t, 0, 0]) for t in range(13)] == [float(t) for t in range(13)]
+    one = D.GatherPlan(D.shard_tracks(wid, 1), 0, 1)               # a single rank still has to undo the sort by weight id
+    local = torch.stack([torch.full((4, 4), float(t), dtype=torch.float64) for t in one.shards[0]])
+    for _ in range(2):
+        full = one.gather(local)
+        assert [float(full[t, 0, 0]) for t in range(13)] == [float(t) for t in range(13)]
