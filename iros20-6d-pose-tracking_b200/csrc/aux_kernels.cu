@@ -55,10 +55,12 @@ __device__ __forceinline__ float depth_offset(unsigned d, double z1000, bool gl)
 //   * cv2's nearest-neighbour source index floor(dst * (1 / (176 / size))) for the 176 columns and this CTA's 44 rows.
 // The per-pixel work is then byte loads, table look-ups, the bf16 / tf32 packing and two 16-byte stores: ~3x fewer instructions
 // than dividing per pixel (ncu, round 2: the kernel was issue-bound at 274 instructions per pixel, DRAM at 7 %).
-constexpr int kPreRowsMax = 44;                   // most rows one CTA handles (rows per CTA is a launch parameter: 44, 22 or 11)
+constexpr int kPreRowsMax = 88;                   // most rows one CTA handles (rows per CTA is a launch parameter: 88, 22 or 11)
 constexpr int kDepthLo = 101, kDepthN = 1899;     // valid raw depths 101..1999
 
-__global__ void __launch_bounds__(256, 4)
+// THREADS = 256 (strips of 11 / 22 rows) or 1024 (half an image per CTA: the per-CTA tables are built twice per track instead of eight times)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 1)
 preprocess_kernel(PreprocessArgs a, int rows_per_cta)
 {
     ptx::grid_dep_launch();
@@ -71,7 +73,7 @@ preprocess_kernel(PreprocessArgs a, int rows_per_cta)
     __shared__ short s_sx[kImg], s_sy[kPreRowsMax];
     __shared__ int s_win[4];
     const int wi = a.weight_ids ? min(max(a.weight_ids[n], 0), a.stats_rows - 1) : 0;   // ids without statistics are rejected on the host where it can see them; never index past the table
-    {
+    if (threadIdx.x < 256) {
         const float v = static_cast<float>(threadIdx.x);
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
@@ -104,9 +106,10 @@ preprocess_kernel(PreprocessArgs a, int rows_per_cta)
         const double ifx = (cw > 0) ? 1.0 / (static_cast<double>(kImg) / cw) : 0.0;
         const double ify = (ch > 0) ? 1.0 / (static_cast<double>(kImg) / ch) : 0.0;
         if (threadIdx.x < kImg) { int sx = static_cast<int>(floor(threadIdx.x * ifx)); if (sx > cw - 1) sx = cw - 1; s_sx[threadIdx.x] = static_cast<short>(sx); }
-        if (threadIdx.x >= 192 && threadIdx.x < 192 + rows_per_cta) {
-            const int y = row0 + threadIdx.x - 192;
-            int sy = static_cast<int>(floor(y * ify)); if (sy > ch - 1) sy = ch - 1; s_sy[threadIdx.x - 192] = static_cast<short>(sy);
+        constexpr int kSyFirst = THREADS == 256 ? 192 : 256;     // threads that fill the row table (the column table takes 0..175)
+        if (threadIdx.x >= kSyFirst && threadIdx.x < kSyFirst + rows_per_cta) {
+            const int y = row0 + threadIdx.x - kSyFirst;
+            int sy = static_cast<int>(floor(y * ify)); if (sy > ch - 1) sy = ch - 1; s_sy[threadIdx.x - kSyFirst] = static_cast<short>(sy);
         }
     }
     __syncthreads();
@@ -190,11 +193,12 @@ static cudaError_t launch_pdl(const void* func, dim3 grid, dim3 block, void** ar
 cudaError_t launch_preprocess(const PreprocessArgs& a, int n, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
     // rows per CTA: big strips amortise the per-CTA tables, small ones fill the machine when there are few tracks
-    int rows = n >= 32 ? 22 : 11;
+    int rows = n >= 64 ? 88 : (n >= 32 ? 22 : 11);
     dim3 grid(kImg / rows, n);
     PreprocessArgs aa = a;
     void* args[] = {&aa, &rows};
-    return launch_pdl(reinterpret_cast<const void*>(preprocess_kernel), grid, dim3(256), args, s);
+    if (rows == 88) return launch_pdl(reinterpret_cast<const void*>(preprocess_kernel<1024>), grid, dim3(1024), args, s);
+    return launch_pdl(reinterpret_cast<const void*>(preprocess_kernel<256>), grid, dim3(256), args, s);
 }
 
 // =============================================================================================
