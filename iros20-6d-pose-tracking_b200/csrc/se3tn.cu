@@ -1039,15 +1039,22 @@ int se3tn_track_host(se3tn_ctx* c, const uint8_t* frame_rgb, const uint16_t* fra
     uint8_t* d = io.dev;
     uint8_t* d_rgb = d; d += align256(px * 3);
     uint16_t* d_depth = reinterpret_cast<uint16_t*>(d); d += align256(px * 2);
-    const size_t cap = static_cast<size_t>(io.n_cap);
-    double* d_poses = reinterpret_cast<double*>(d); d += align256(cap * 128);
-    double* d_ow = reinterpret_cast<double*>(d); d += align256(cap * 8);
-    uint8_t* d_rgbA = d; d += align256(cap * img * 3);
-    uint16_t* d_depthA = reinterpret_cast<uint16_t*>(d); d += align256(cap * img * 2);
-    int32_t* d_wid = reinterpret_cast<int32_t*>(d); d += align256(cap * 4);
-    double* d_out = reinterpret_cast<double*>(d); d += align256(cap * 128);
-    float* d_tr = reinterpret_cast<float*>(d); d += align256(cap * 12);
-    float* d_ro = reinterpret_cast<float*>(d);
+    // the per-track arrays are packed by THIS call's n (a step's graph is keyed by n anyway), inputs first, outputs behind them:
+    // one host -> device copy carries all inputs, one device -> host copy all outputs
+    const size_t nn = static_cast<size_t>(n);
+    const size_t o_ow = align256(nn * 128), o_rgbA = o_ow + align256(nn * 8), o_depthA = o_rgbA + align256(nn * img * 3),
+                 o_wid = o_depthA + align256(nn * img * 2), in_bytes = o_wid + align256(nn * 4);
+    const size_t o_tr = align256(nn * 128), o_ro = o_tr + align256(nn * 12), out_bytes = o_ro + align256(nn * 12);
+    uint8_t* d_in = d;
+    double* d_poses = reinterpret_cast<double*>(d_in);
+    double* d_ow = reinterpret_cast<double*>(d_in + o_ow);
+    uint8_t* d_rgbA = d_in + o_rgbA;
+    uint16_t* d_depthA = reinterpret_cast<uint16_t*>(d_in + o_depthA);
+    int32_t* d_wid = reinterpret_cast<int32_t*>(d_in + o_wid);
+    uint8_t* d_res = d_in + in_bytes;
+    double* d_out = reinterpret_cast<double*>(d_res);
+    float* d_tr = reinterpret_cast<float*>(d_res + o_tr);
+    float* d_ro = reinterpret_cast<float*>(d_res + o_ro);
     // ---- the part of the frame the tracks' crop windows touch (K0 reads nothing else) ----
     int y0 = H, y1 = 0, x0 = W, x1 = 0;
     for (int i = 0; i < n; ++i) {
@@ -1073,29 +1080,23 @@ int se3tn_track_host(se3tn_ctx* c, const uint8_t* frame_rgb, const uint16_t* fra
         CU_TRY(c, cudaMemcpy2DAsync(d_rgb + off * 3, static_cast<size_t>(W) * 3, st_rgb, static_cast<size_t>(ww) * 3, static_cast<size_t>(ww) * 3, wh, cudaMemcpyHostToDevice, s));
         CU_TRY(c, cudaMemcpy2DAsync(d_depth + off, static_cast<size_t>(W) * 2, st_dep, static_cast<size_t>(ww) * 2, static_cast<size_t>(ww) * 2, wh, cudaMemcpyHostToDevice, s));
     }
-    auto put = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
-        memcpy(hp, src, bytes);
-        cudaError_t e = cudaMemcpyAsync(dst, hp, bytes, cudaMemcpyHostToDevice, s);
-        hp += align256(bytes);
-        return e;
-    };
-    const size_t nn = static_cast<size_t>(n);
-    CU_TRY(c, put(d_poses, poses, nn * 128));
-    CU_TRY(c, put(d_ow, object_width, nn * 8));
-    CU_TRY(c, put(d_rgbA, rgbA, nn * img * 3));
-    CU_TRY(c, put(d_depthA, depthA, nn * img * 2));
-    if (weight_ids) CU_TRY(c, put(d_wid, weight_ids, nn * 4));
+    hp = io.pin + align256(static_cast<size_t>(hp - io.pin));
+    memcpy(hp, poses, nn * 128);
+    memcpy(hp + o_ow, object_width, nn * 8);
+    memcpy(hp + o_rgbA, rgbA, nn * img * 3);
+    memcpy(hp + o_depthA, depthA, nn * img * 2);
+    if (weight_ids) memcpy(hp + o_wid, weight_ids, nn * 4);
+    CU_TRY(c, cudaMemcpyAsync(d_in, hp, weight_ids ? in_bytes : o_wid, cudaMemcpyHostToDevice, s));
+    hp += in_bytes;
     const int rc = se3tn_track_batch(c, d_rgb, d_depth, H, W, K, d_poses, d_ow, d_rgbA, d_depthA, weight_ids, weight_ids ? d_wid : nullptr, n,
                                      tn, rn, precision, d_tr, d_ro, d_out, stream);
     if (rc != SE3TN_OK) return rc;
     uint8_t* ho = hp;                                            // outputs come back through the same pinned block
-    CU_TRY(c, cudaMemcpyAsync(ho, d_out, nn * 128, cudaMemcpyDeviceToHost, s));
-    if (out_trans) CU_TRY(c, cudaMemcpyAsync(ho + align256(nn * 128), d_tr, nn * 12, cudaMemcpyDeviceToHost, s));
-    if (out_rot) CU_TRY(c, cudaMemcpyAsync(ho + align256(nn * 128) + align256(nn * 12), d_ro, nn * 12, cudaMemcpyDeviceToHost, s));
+    CU_TRY(c, cudaMemcpyAsync(ho, d_res, (out_trans || out_rot) ? out_bytes : nn * 128, cudaMemcpyDeviceToHost, s));
     CU_TRY(c, cudaStreamSynchronize(s));
     memcpy(poses_out, ho, nn * 128);
-    if (out_trans) memcpy(out_trans, ho + align256(nn * 128), nn * 12);
-    if (out_rot) memcpy(out_rot, ho + align256(nn * 128) + align256(nn * 12), nn * 12);
+    if (out_trans) memcpy(out_trans, ho + o_tr, nn * 12);
+    if (out_rot) memcpy(out_rot, ho + o_ro, nn * 12);
     return SE3TN_OK;
 }
 
