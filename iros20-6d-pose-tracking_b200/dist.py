@@ -120,6 +120,7 @@ class ShardedTracker:
         self.overlap_gather = bool(overlap_gather) and world_size > 1
         self._comm_stream = torch.cuda.Stream(device=dev) if self.overlap_gather else None
         self._pending = []                         # events of the all-gathers still in flight, oldest first
+        self._readers = [None, None]               # per rotating output set: the gather that last read it
         # two rotating sets of output tensors: stable device addresses keep the step's CUDA graph key stable (libse3tn replays one
         # graph per distinct set of pointers); a returned pose tensor stays valid until the step after the next one
         n = len(self.mine)
@@ -135,10 +136,11 @@ class ShardedTracker:
         self._pending = []
 
     def step(self, frame_rgb, frame_depth, local_poses, local_rgbA, local_depthA, gather=True):
-        # two rotating output sets: the one written now was last read by the gather issued two steps ago
-        while len(self._pending) >= 2:
-            torch.cuda.current_stream(self.engine.device).wait_event(self._pending.pop(0))
+        # two rotating output sets: the one written now was last read by the gather of the step before the previous one
         self._flip ^= 1
+        if self._readers[self._flip] is not None:
+            torch.cuda.current_stream(self.engine.device).wait_event(self._readers[self._flip])
+            self._readers[self._flip] = None
         o = self._outs[self._flip]
         out, _, _ = self.engine.track_batch(frame_rgb, frame_depth, self.K, local_poses, self.local_ow,
                                             local_rgbA, local_depthA, self.tn, self.rn,
@@ -154,6 +156,7 @@ class ShardedTracker:
         with torch.cuda.stream(self._comm_stream):
             gathered = self.plan.gather(out)
             done = torch.cuda.Event(); done.record(self._comm_stream)
-            self._pending.append(done)
+            self._readers[self._flip] = done
+            self._pending = self._pending[-1:] + [done]          # anything older is ordered before these on the side stream
         gathered.record_stream(cur)                # ... and `gathered` will be read here after wait_gather()
         return out, gathered
